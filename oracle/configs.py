@@ -1,0 +1,61 @@
+"""TEST INFRASTRUCTURE ONLY -- the parity-test cases (BASELINE.json configs, SURVEY.md
+section 8d) shared by oracle/make_golden.py and tests/.  Buffer sizes are scaled down
+(the full-size rings are exercised by bench.py and the full-size property tests)."""
+
+SAC_KW = dict(reward_scale=1.0, discount=0.99, soft_target_tau=0.005, policy_lr=3e-4,
+              qf_lr=3e-4, policy_mean_reg_weight=1e-3, policy_std_reg_weight=1e-3)
+
+CASES = {
+    # exp_specs/sac/sac_hopper.yaml:38-47 (script sac_alpha_exp_script.py), B=256 per BASELINE
+    "sac_hopper": dict(algo="sac_alpha", obs_dim=11, act_dim=3, batch=256, n_fill=20000,
+                       steps=6, sac=dict(SAC_KW, alpha=0.2), seed=11),
+    # exp_specs/sac/sac_ant.yaml:38-48 (target_entropy -4)
+    "sac_ant": dict(algo="sac_alpha", obs_dim=111, act_dim=8, batch=256, n_fill=8000,
+                    steps=3, sac=dict(SAC_KW, alpha=0.2, target_entropy=-4.0), seed=12),
+    # yaml batch (512) variant of hopper, fixed alpha branch coverage
+    "sac_hopper_b512_fixed_alpha": dict(algo="sac_alpha", obs_dim=11, act_dim=3, batch=512,
+                                        n_fill=20000, steps=3,
+                                        sac=dict(SAC_KW, alpha=0.2, train_alpha=False), seed=13),
+    # run_scripts/sac_exp_script.py -> sac.py (V variant)
+    "sacv_hopper": dict(algo="sac_v", obs_dim=11, act_dim=3, batch=256, n_fill=20000, steps=4,
+                        sac=dict(SAC_KW, vf_lr=3e-4, alpha=1.0), seed=14),
+    # exp_specs/td3/td3_humanoid.yaml:13-14,44-50; B=1024 per BASELINE config 4
+    "td3_humanoid": dict(algo="td3", obs_dim=376, act_dim=17, batch=1024, n_fill=6000, steps=4,
+                         td3=dict(reward_scale=1.0, discount=0.99, soft_target_tau=0.005,
+                                  policy_lr=3e-4, qf_lr=3e-4, policy_and_target_update_period=2),
+                         policy_noise=0.2, policy_noise_clip=0.5, seed=15),
+    "td3_hopper": dict(algo="td3", obs_dim=11, act_dim=3, batch=256, n_fill=20000, steps=5,
+                       td3=dict(reward_scale=1.0, discount=0.99, soft_target_tau=0.005,
+                                policy_lr=3e-4, qf_lr=3e-4, policy_and_target_update_period=2),
+                       policy_noise=0.2, policy_noise_clip=0.5, seed=16),
+    # exp_specs/gail/gail_walker.yaml (gail2, grad_pen 8, reward_scale 2, beta_1 0.25)
+    "gail_walker": dict(algo="adv_irl", obs_dim=17, act_dim=6, batch=256, n_fill=20000,
+                        n_expert=4000, steps=4, mode="gail2",
+                        disc=dict(disc_lr=3e-4, disc_momentum=0.9, use_grad_pen=True,
+                                  grad_pen_weight=8.0),
+                        sac=dict(SAC_KW, reward_scale=2.0, beta_1=0.25, alpha=0.2), seed=17),
+    "airl_hopper_clip": dict(algo="adv_irl", obs_dim=11, act_dim=3, batch=128, n_fill=5000,
+                             n_expert=2000, steps=3, mode="airl", rew_clip_min=-2.0,
+                             rew_clip_max=2.0,
+                             disc=dict(disc_lr=3e-4, disc_momentum=0.0, use_grad_pen=True,
+                                       grad_pen_weight=10.0),
+                             sac=dict(SAC_KW, reward_scale=1.0, alpha=0.2), seed=18),
+    "fairl_hopper_nogp": dict(algo="adv_irl", obs_dim=11, act_dim=3, batch=128, n_fill=5000,
+                              n_expert=2000, steps=3, mode="fairl",
+                              disc=dict(disc_lr=3e-4, disc_momentum=0.9, use_grad_pen=False,
+                                        grad_pen_weight=10.0),
+                              sac=dict(SAC_KW, reward_scale=1.0, alpha=0.2), seed=19),
+    "gail_hopper": dict(algo="adv_irl", obs_dim=11, act_dim=3, batch=128, n_fill=5000,
+                        n_expert=2000, steps=3, mode="gail",
+                        disc=dict(disc_lr=3e-4, disc_momentum=0.9, use_grad_pen=True,
+                                  grad_pen_weight=4.0),
+                        sac=dict(SAC_KW, reward_scale=1.0, alpha=0.2), seed=20),
+}
+
+HIDDEN = (256, 256)
+DISC_HID = 128
+BUFFER_SEED = 1      # policy replay buffer index RNG
+EXPERT_SEED = 3      # expert replay buffer index RNG
+DATA_SEED = 7
+EXPERT_DATA_SEED = 8
+EPS_SEED0 = 1000     # torch.manual_seed(EPS_SEED0 + t) before step t
