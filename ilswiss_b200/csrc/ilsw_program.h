@@ -1,0 +1,480 @@
+// ilswiss_b200 -- host-side compiler from (algorithm, shapes, hyper-parameters) to the phase
+// program executed by the persistent engine kernel.  Header-only so that the product library
+// (device pointers) and the test-only host simulator (host pointers) build the identical
+// program.  See ilsw_types.h for the program model.
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/ilswiss_b200.h"
+#include "ilsw_types.h"
+
+namespace ilsw {
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// two-pass bump allocator: pass 1 (base==nullptr) measures, pass 2 hands out pointers
+struct Bump {
+  char* base = nullptr;
+  size_t off = 0;
+  template <class T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) / 256 * 256;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += bytes;
+    return p;
+  }
+  float* f(size_t n) { return take<float>(n); }
+};
+
+inline int mlp_num_params(int in_dim, int hid, int out_dim, int heads2) {
+  int n = hid * in_dim + hid + hid * hid + hid + out_dim * hid + out_dim;
+  if (heads2) n += out_dim * hid + out_dim;
+  return n;
+}
+
+inline MlpPtrs make_mlp(const ilsw_mlp& n, float* grad) {
+  MlpPtrs m;
+  memset(&m, 0, sizeof(m));
+  m.p = n.p; m.m = n.m; m.v = n.v; m.g = grad;
+  m.in_dim = n.in_dim; m.hid = n.hidden; m.out_dim = n.out_dim; m.heads = n.log_std_head ? 2 : 1;
+  m.oW0 = 0;
+  m.ob0 = m.oW0 + n.hidden * n.in_dim;
+  m.oW1 = m.ob0 + n.hidden;
+  m.ob1 = m.oW1 + n.hidden * n.hidden;
+  m.oW2 = m.ob1 + n.hidden;
+  m.ob2 = m.oW2 + n.out_dim * n.hidden;
+  m.oW3 = m.ob2 + n.out_dim;
+  m.ob3 = m.oW3 + (n.log_std_head ? n.out_dim * n.hidden : 0);
+  m.n_params = mlp_num_params(n.in_dim, n.hidden, n.out_dim, n.log_std_head);
+  return m;
+}
+
+struct Builder {
+  Program& P;
+  explicit Builder(Program& p) : P(p) { P.n_phases = 0; P.n_ops = 0; }
+  bool overflow = false;
+
+  void phase(int cond = COND_ALWAYS, int collective = 0) {
+    if (P.n_phases >= kMaxPhases) { overflow = true; return; }
+    Phase& ph = P.phases[P.n_phases++];
+    ph.op_begin = P.n_ops; ph.op_count = 0; ph.total_jobs = 0; ph.cond = cond; ph.collective = collective;
+  }
+  Op* add(int kind, int n_jobs) {
+    if (P.n_ops >= kMaxOps || P.n_phases == 0) { overflow = true; return nullptr; }
+    Op& o = P.ops[P.n_ops++];
+    memset(&o, 0, sizeof(o));
+    o.kind = kind; o.n_jobs = n_jobs;
+    Phase& ph = P.phases[P.n_phases - 1];
+    ph.op_count++; ph.total_jobs += n_jobs;
+    return &o;
+  }
+  void gemm(GemmOp g) {
+    g.tiles_m = (g.M + 31) / 32;
+    g.tiles_n = (g.N + g.aug_ones + 31) / 32;
+    Op* o = add(OP_GEMM, g.tiles_m * g.tiles_n);
+    if (o) o->gemm = g;
+  }
+  // Y[M,N] = act(X[M,K] W[N,K]^T + b)          (N1: networks.py:85-101)
+  void fwd(const float* X, int ldx, int M, int K, const float* W, const float* b, int N, float* Y, int ldy, int act) {
+    GemmOp g; memset(&g, 0, sizeof(g));
+    g.A = X; g.lda = ldx; g.a_mc = 0; g.B = W; g.ldb = K; g.b_nc = 0; g.M = M; g.N = N; g.K = K;
+    g.C = Y; g.ldc = ldy; g.bias = b; g.act = act;
+    gemm(g);
+  }
+  // dX[M,Nin] = (D[M,Kred] W[Kred, ldw(:Nin)]) (.) act'(Hm)      (backward through a Linear)
+  void dx(const float* D, int ldd, int M, int Kred, const float* W, int ldw, int Nin, const float* Hm, int ldh,
+          int mask, float* out, int ldo, float* raw = nullptr) {
+    GemmOp g; memset(&g, 0, sizeof(g));
+    g.A = D; g.lda = ldd; g.a_mc = 0; g.B = W; g.ldb = ldw; g.b_nc = 1; g.M = M; g.N = Nin; g.K = Kred;
+    g.C = out; g.ldc = ldo; g.C2 = raw; g.H = Hm; g.ldh = ldh; g.mask = mask;
+    gemm(g);
+  }
+  // G[Mout,Nin] (+)= D[Kb,Mout]^T X[Kb,Nin] ; gbias[Mout] (+)= colsum(D)   (weight gradient)
+  void dw(const float* D, int ldd, int Mout, const float* X, int ldx, int Nin, int Kb, float* G, float* gbias,
+          int accumulate = 0) {
+    GemmOp g; memset(&g, 0, sizeof(g));
+    g.A = D; g.lda = ldd; g.a_mc = 1; g.B = X; g.ldb = ldx; g.b_nc = 1; g.M = Mout; g.N = Nin; g.K = Kb;
+    g.C = G; g.ldc = Nin; g.aug_ones = gbias ? 1 : 0; g.bias_out = gbias; g.accumulate = accumulate;
+    gemm(g);
+  }
+  void row(int kind, int rows) {
+    Op* o = add(OP_ROW, (rows + kRowsPerJob - 1) / kRowsPerJob);
+    if (o) { o->row.kind = kind; o->row.rows = rows; }
+  }
+  void adam(const MlpPtrs& n, const MlpPtrs* target, double lr, double b1, double b2, double eps, float tau, int slot,
+            int world_scale = 0) {
+    Op* o = add(OP_ADAM, (n.n_params + kAdamChunk - 1) / kAdamChunk);
+    if (!o) return;
+    o->adam.p = n.p; o->adam.g = n.g; o->adam.m = n.m; o->adam.v = n.v;
+    o->adam.target = target ? target->p : nullptr;
+    o->adam.n = n.n_params; o->adam.lr = lr; o->adam.beta1 = b1; o->adam.beta2 = b2; o->adam.eps = eps;
+    o->adam.tau = tau; o->adam.slot = slot; o->adam.grad_scale_world = world_scale;
+  }
+  void polyak(const MlpPtrs& src, const MlpPtrs& tgt, float tau) {
+    Op* o = add(OP_POLYAK, (src.n_params + kAdamChunk - 1) / kAdamChunk);
+    if (!o) return;
+    o->polyak.target = tgt.p; o->polyak.src = src.p; o->polyak.n = src.n_params; o->polyak.tau = tau;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// scratch layout
+// ------------------------------------------------------------------------------------------
+inline void alloc_sac_bufs(Bump& mem, SacBufs& S, int algo, int B, int O, int A, int Hd) {
+  S.B = B; S.O = O; S.A = A; S.Hd = Hd;
+  S.ld_oa = round_up(O + A, 4);
+  S.ld_o = round_up(O, 4);
+  const bool td3 = algo == ILSW_ALGO_TD3;
+  const int PB = td3 ? B : 2 * B;  // policy rows per step
+  S.idx = mem.take<int>(B);
+  S.Xoa = mem.f((size_t)B * S.ld_oa); S.rew = mem.f(B); S.term = mem.f(B);
+  S.Xpi = mem.f((size_t)2 * B * S.ld_o);
+  S.Xna = mem.f((size_t)B * S.ld_oa); S.Xon = mem.f((size_t)B * S.ld_oa);
+  S.eps = mem.f((size_t)2 * B * A); S.noise = mem.f((size_t)B * A);
+  for (int i = 0; i < 2; ++i) {
+    S.h0q[i] = mem.f((size_t)B * Hd); S.h1q[i] = mem.f((size_t)B * Hd);
+    S.h0t[i] = mem.f((size_t)B * Hd); S.h1t[i] = mem.f((size_t)B * Hd);
+    S.h0n[i] = mem.f((size_t)B * Hd); S.h1n[i] = mem.f((size_t)B * Hd);
+    S.qp[i] = mem.f(B); S.tq[i] = mem.f(B); S.qn[i] = mem.f(B); S.dq[i] = mem.f(B);
+    S.d1q[i] = mem.f((size_t)B * Hd); S.d0q[i] = mem.f((size_t)B * Hd);
+    S.e1[i] = mem.f((size_t)B * Hd); S.e0[i] = mem.f((size_t)B * Hd);
+    S.dA[i] = mem.f((size_t)B * A);
+    S.lossterm[i] = mem.f(B);
+    S.qn_old[i] = mem.f(B);
+  }
+  S.h0p = mem.f((size_t)PB * Hd); S.h1p = mem.f((size_t)PB * Hd);
+  S.mean = mem.f((size_t)PB * A); S.lraw = mem.f((size_t)PB * A); S.lstd = mem.f((size_t)PB * A);
+  S.act = mem.f((size_t)PB * A); S.logpi = mem.f(PB);
+  S.y = mem.f(B);
+  S.dmean = mem.f((size_t)B * A); S.dlraw = mem.f((size_t)B * A);
+  S.d1p = mem.f((size_t)B * Hd); S.d0p = mem.f((size_t)B * Hd);
+  S.plterm = mem.f(B); S.regmu = mem.f(B); S.regls = mem.f(B); S.aterm = mem.f(B);
+  S.h0tp = mem.f((size_t)B * Hd); S.h1tp = mem.f((size_t)B * Hd);
+  S.h0v = S.h1v = S.h0tv = S.h1tv = S.vp = S.tv = S.dv = S.d1v = S.d0v = S.lossterm_v = nullptr;
+}
+
+inline void alloc_disc_bufs(Bump& mem, DiscBufs& D, int B, int Din, int Hd) {
+  D.B = B; D.D = Din; D.Hd = Hd; D.ld_d = round_up(Din, 4);
+  D.idx_e = mem.take<int>(B); D.idx_p = mem.take<int>(B);
+  D.X3 = mem.f((size_t)3 * B * D.ld_d); D.gp_eps = mem.f(B);
+  D.h1 = mem.f((size_t)3 * B * Hd); D.h2 = mem.f((size_t)3 * B * Hd);
+  D.y = mem.f(3 * B); D.dlogit = mem.f(2 * B); D.cmask = mem.f(B);
+  D.d2 = mem.f((size_t)2 * B * Hd); D.d1 = mem.f((size_t)2 * B * Hd);
+  D.dl2 = mem.f((size_t)B * Hd); D.u1 = mem.f((size_t)B * Hd); D.dl1 = mem.f((size_t)B * Hd);
+  D.g = mem.f((size_t)B * D.ld_d); D.gbar = mem.f((size_t)B * D.ld_d); D.nrm = mem.f(B);
+  D.db1 = mem.f((size_t)B * Hd); D.ub1 = mem.f((size_t)B * Hd); D.sb1 = mem.f((size_t)B * Hd);
+  D.db2 = mem.f((size_t)B * Hd); D.t3 = mem.f((size_t)B * Hd); D.zb2 = mem.f((size_t)B * Hd);
+  D.hb1 = mem.f((size_t)B * Hd); D.zb1 = mem.f((size_t)B * Hd);
+  D.ceterm = mem.f(2 * B); D.accterm = mem.f(2 * B); D.gpterm = mem.f(B);
+  D.rh1 = mem.f((size_t)B * Hd); D.rh2 = mem.f((size_t)B * Hd); D.rewraw = mem.f(B);
+}
+
+inline int stats_floats_for(int algo, int B, int A) {
+  return algo == ILSW_ALGO_TD3 ? 6 * B + B * A : 7 * B + 2 * B * A;
+}
+
+// ------------------------------------------------------------------------------------------
+// program builders
+// ------------------------------------------------------------------------------------------
+// D1: discriminator update (adv_irl.py:133-216) incl. the closed-form double backward of the
+// gradient penalty (formula block: SURVEY.md section 8a row D1).
+inline void build_disc_step(Builder& b, const Ctx& c) {
+  const DiscBufs& D = c.d;
+  const MlpPtrs& N = c.disc;
+  const int B = D.B, Hd = D.Hd, Din = D.D, ld = D.ld_d;
+  const bool gp = c.hp.use_gp != 0;
+  const int R = gp ? 3 * B : 2 * B;
+  const float* W1 = N.p + N.oW0; const float* b1 = N.p + N.ob0;
+  const float* W2 = N.p + N.oW1; const float* b2 = N.p + N.ob1;
+  float* G1 = N.g + N.oW0; float* gb1 = N.g + N.ob0;
+  float* G2 = N.g + N.oW1; float* gb2 = N.g + N.ob1;
+  float* G3 = N.g + N.oW2; float* gb3 = N.g + N.ob2;
+  const float* xhat = D.X3 + (size_t)2 * B * ld;
+  const float* h1i = D.h1 + (size_t)2 * B * Hd;
+
+  b.phase(); b.row(ROW_DISC_GATHER, B);
+  b.phase(); b.fwd(D.X3, ld, R, Din, W1, b1, Hd, D.h1, Hd, ACT_TANH);
+  b.phase(); b.fwd(D.h1, Hd, R, Hd, W2, b2, Hd, D.h2, Hd, ACT_TANH);
+  b.phase(); b.row(ROW_DISC_HEAD, R);
+  b.phase();
+  b.dx(D.d2, Hd, 2 * B, Hd, W2, Hd, Hd, D.h1, Hd, ACT_TANH, D.d1, Hd);          // CE: delta1
+  b.dw(D.d2, Hd, Hd, D.h1, Hd, Hd, 2 * B, G2, gb2);                             // CE: dW2,db2
+  b.dw(D.dlogit, 1, 1, D.h2, Hd, Hd, 2 * B, G3, gb3);                            // CE: dw3,db3
+  if (gp) b.dx(D.dl2, Hd, B, Hd, W2, Hd, Hd, h1i, Hd, ACT_TANH, D.dl1, Hd, D.u1);  // u1, delta1_gp
+  b.phase();
+  b.dw(D.d1, Hd, Hd, D.X3, ld, Din, 2 * B, G1, gb1);                             // CE: dW1,db1
+  if (gp) b.dx(D.dl1, Hd, B, Hd, W1, Din, Din, nullptr, 0, ACT_NONE, D.g, ld);   // g = delta1 W1
+  if (gp) {
+    b.phase(); b.row(ROW_DISC_GNORM, B);
+    b.phase();
+    b.fwd(D.gbar, ld, B, Din, W1, nullptr, Hd, D.db1, Hd, ACT_NONE);             // dbar1 = gbar W1^T
+    b.dw(D.dl1, Hd, Hd, D.gbar, ld, Din, B, G1, nullptr, 1);                     // dW1 += delta1^T gbar
+    b.phase(); b.row(ROW_DISC_EW1, B);
+    b.phase();
+    b.fwd(D.ub1, Hd, B, Hd, W2, nullptr, Hd, D.db2, Hd, ACT_NONE);               // dbar2 = ubar1 W2^T
+    b.dw(D.dl2, Hd, Hd, D.ub1, Hd, Hd, B, G2, nullptr, 1);                       // dW2 += delta2^T ubar1
+    b.phase(); b.row(ROW_DISC_EW2, B);
+    b.phase();
+    b.dw(D.zb2, Hd, Hd, h1i, Hd, Hd, B, G2, gb2, 1);                             // dW2 += zbar2^T h1 ; db2
+    b.dw(D.cmask, 1, 1, D.t3, Hd, Hd, B, G3, nullptr, 1);                        // dw3 += c^T (dbar2*s2)
+    b.dx(D.zb2, Hd, B, Hd, W2, Hd, Hd, nullptr, 0, ACT_NONE, D.hb1, Hd);         // hbar1_raw = zbar2 W2
+    b.phase(); b.row(ROW_DISC_EW3, B);
+    b.phase(); b.dw(D.zb1, Hd, Hd, xhat, ld, Din, B, G1, gb1, 1);                // dW1 += zbar1^T xhat ; db1
+  }
+  b.phase();
+  b.adam(N, nullptr, c.hp.disc_lr, c.hp.disc_beta1, 0.999, c.hp.adam_eps, 0.f, SLOT_DISC);
+  b.row(ROW_DISC_FINAL, 1);
+}
+
+// S1 (+ D2 reward relabel when a discriminator is attached)
+inline void build_sac_alpha(Builder& b, const Ctx& c) {
+  const SacBufs& S = c.s;
+  const int B = S.B, O = S.O, A = S.A, Hd = S.Hd, K0 = O + A;
+  const MlpPtrs& P = c.policy;
+  const bool disc = c.hp.has_disc != 0;
+  const double b1 = c.hp.beta1, b2 = c.hp.beta2, eps = c.hp.adam_eps;
+  const float* obs_rows = S.Xpi + (size_t)B * S.ld_o;
+  const float* h0p_obs = S.h0p + (size_t)B * Hd;
+  const float* h1p_obs = S.h1p + (size_t)B * Hd;
+
+  b.phase(); b.row(ROW_SAC_GATHER, B);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.fwd(S.Xoa, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0q[i], Hd, ACT_RELU);
+  b.fwd(S.Xpi, S.ld_o, 2 * B, O, P.p + P.oW0, P.p + P.ob0, Hd, S.h0p, Hd, ACT_RELU);
+  if (disc) b.fwd(S.Xoa, S.ld_oa, B, K0, c.disc.p + c.disc.oW0, c.disc.p + c.disc.ob0, c.d.Hd, c.d.rh1, c.d.Hd, ACT_TANH);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.fwd(S.h0q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1q[i], Hd, ACT_RELU);
+  b.fwd(S.h0p, Hd, 2 * B, Hd, P.p + P.oW1, P.p + P.ob1, Hd, S.h1p, Hd, ACT_RELU);
+  if (disc) b.fwd(c.d.rh1, c.d.Hd, B, c.d.Hd, c.disc.p + c.disc.oW1, c.disc.p + c.disc.ob1, c.d.Hd, c.d.rh2, c.d.Hd, ACT_TANH);
+  b.phase();
+  b.row(ROW_SAC_HEADS, 2 * B);
+  if (disc) b.row(ROW_DISC_REWARD, B);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.fwd(S.Xna, S.ld_oa, B, K0, c.tqf[i].p + c.tqf[i].oW0, c.tqf[i].p + c.tqf[i].ob0, Hd, S.h0t[i], Hd, ACT_RELU);
+  if (disc) b.row(ROW_DISC_REWARD_FINAL, 1);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.fwd(S.h0t[i], Hd, B, Hd, c.tqf[i].p + c.tqf[i].oW1, c.tqf[i].p + c.tqf[i].ob1, Hd, S.h1t[i], Hd, ACT_RELU);
+  b.phase(); b.row(ROW_SAC_TARGET, B);
+  b.phase();
+  for (int i = 0; i < 2; ++i) {
+    const MlpPtrs& Q = c.qf[i];
+    b.dx(S.d1q[i], Hd, B, Hd, Q.p + Q.oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
+    b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, Q.g + Q.oW1, Q.g + Q.ob1);
+    b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, Q.g + Q.oW2, Q.g + Q.ob2);
+  }
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0);
+  b.phase();
+  b.adam(c.qf[0], &c.tqf[0], c.hp.qf_lr, b1, b2, eps, c.hp.tau, SLOT_QF1);   // Adam + Polyak of the target
+  b.adam(c.qf[1], &c.tqf[1], c.hp.qf_lr, b1, b2, eps, c.hp.tau, SLOT_QF2);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0n[i], Hd, ACT_RELU);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.fwd(S.h0n[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1n[i], Hd, ACT_RELU);
+  b.phase(); b.row(ROW_SAC_PLOSS, B);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.dx(S.e1[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0n[i], Hd, ACT_RELU, S.e0[i], Hd);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.dx(S.e0[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW0 + O, K0, A, nullptr, 0, ACT_NONE, S.dA[i], A);
+  b.phase(); b.row(ROW_SAC_PIBWD, B);
+  b.phase();
+  b.dx(S.d1p, Hd, B, Hd, P.p + P.oW1, Hd, Hd, h0p_obs, Hd, ACT_RELU, S.d0p, Hd);
+  b.dw(S.d1p, Hd, Hd, h0p_obs, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);
+  b.dw(S.dmean, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2);
+  b.dw(S.dlraw, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW3, P.g + P.ob3);
+  b.phase();
+  b.dw(S.d0p, Hd, Hd, obs_rows, S.ld_o, O, B, P.g + P.oW0, P.g + P.ob0);
+  b.phase(COND_ALWAYS, 1);
+  b.adam(P, nullptr, c.hp.policy_lr, b1, b2, eps, 0.f, SLOT_POLICY, 1);
+  b.row(ROW_SAC_FINAL, 1);
+}
+
+// S3
+inline void build_td3(Builder& b, const Ctx& c) {
+  const SacBufs& S = c.s;
+  const int B = S.B, O = S.O, A = S.A, Hd = S.Hd, K0 = O + A;
+  const MlpPtrs& P = c.policy; const MlpPtrs& TP = c.tpolicy;
+  const double b1 = 0.9, b2 = 0.999, eps = c.hp.adam_eps;   // optimizer defaults (td3.py:56-67)
+
+  b.phase(); b.row(ROW_TD3_GATHER, B);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.fwd(S.Xoa, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0q[i], Hd, ACT_RELU);
+  b.fwd(S.Xna, S.ld_oa, B, O, TP.p + TP.oW0, TP.p + TP.ob0, Hd, S.h0tp, Hd, ACT_RELU);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.fwd(S.h0q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1q[i], Hd, ACT_RELU);
+  b.fwd(S.h0tp, Hd, B, Hd, TP.p + TP.oW1, TP.p + TP.ob1, Hd, S.h1tp, Hd, ACT_RELU);
+  b.phase(); b.row(ROW_TD3_THEAD, B);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.fwd(S.Xna, S.ld_oa, B, K0, c.tqf[i].p + c.tqf[i].oW0, c.tqf[i].p + c.tqf[i].ob0, Hd, S.h0t[i], Hd, ACT_RELU);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.fwd(S.h0t[i], Hd, B, Hd, c.tqf[i].p + c.tqf[i].oW1, c.tqf[i].p + c.tqf[i].ob1, Hd, S.h1t[i], Hd, ACT_RELU);
+  b.phase(); b.row(ROW_TD3_TARGET, B);
+  b.phase();
+  for (int i = 0; i < 2; ++i) {
+    const MlpPtrs& Q = c.qf[i];
+    b.dx(S.d1q[i], Hd, B, Hd, Q.p + Q.oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
+    b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, Q.g + Q.oW1, Q.g + Q.ob1);
+    b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, Q.g + Q.oW2, Q.g + Q.ob2);
+  }
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0);
+  b.phase();
+  b.adam(c.qf[0], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF1);
+  b.adam(c.qf[1], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF2);
+  b.row(ROW_TD3_FINAL, 1);
+  // delayed policy + target update (td3.py:113-124), steps with (n_train_steps_total % period)==0
+  const int PC = COND_TD3_POLICY;
+  b.phase(PC); b.fwd(S.Xoa, S.ld_oa, B, O, P.p + P.oW0, P.p + P.ob0, Hd, S.h0p, Hd, ACT_RELU);
+  b.phase(PC); b.fwd(S.h0p, Hd, B, Hd, P.p + P.oW1, P.p + P.ob1, Hd, S.h1p, Hd, ACT_RELU);
+  b.phase(PC); b.row(ROW_TD3_PHEAD, B);
+  b.phase(PC); b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[0].p + c.qf[0].oW0, c.qf[0].p + c.qf[0].ob0, Hd, S.h0n[0], Hd, ACT_RELU);
+  b.phase(PC); b.fwd(S.h0n[0], Hd, B, Hd, c.qf[0].p + c.qf[0].oW1, c.qf[0].p + c.qf[0].ob1, Hd, S.h1n[0], Hd, ACT_RELU);
+  b.phase(PC); b.row(ROW_TD3_PLOSS, B);
+  b.phase(PC); b.dx(S.e1[0], Hd, B, Hd, c.qf[0].p + c.qf[0].oW1, Hd, Hd, S.h0n[0], Hd, ACT_RELU, S.e0[0], Hd);
+  b.phase(PC); b.dx(S.e0[0], Hd, B, Hd, c.qf[0].p + c.qf[0].oW0 + O, K0, A, nullptr, 0, ACT_NONE, S.dA[0], A);
+  b.phase(PC); b.row(ROW_TD3_PIBWD, B);
+  b.phase(PC);
+  b.dx(S.d1p, Hd, B, Hd, P.p + P.oW1, Hd, Hd, S.h0p, Hd, ACT_RELU, S.d0p, Hd);
+  b.dw(S.d1p, Hd, Hd, S.h0p, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);
+  b.dw(S.dmean, A, A, S.h1p, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2);
+  b.phase(PC);
+  b.dw(S.d0p, Hd, Hd, S.Xoa, S.ld_oa, O, B, P.g + P.oW0, P.g + P.ob0);
+  b.phase(PC, 1);
+  b.adam(P, &c.tpolicy, c.hp.policy_lr, b1, b2, eps, c.hp.tau, SLOT_POLICY, 1);
+  b.polyak(c.qf[0], c.tqf[0], c.hp.tau);
+  b.polyak(c.qf[1], c.tqf[1], c.hp.tau);
+  b.row(ROW_TD3_FINAL_POLICY, 1);
+}
+
+inline Hyper make_hyper(const ilsw_trainer_config& cfg) {
+  Hyper h; memset(&h, 0, sizeof(h));
+  h.algo = cfg.algo;
+  h.reward_scale = (float)cfg.reward_scale; h.discount = (float)cfg.discount; h.tau = (float)cfg.soft_target_tau;
+  h.policy_lr = cfg.policy_lr; h.qf_lr = cfg.qf_lr; h.vf_lr = cfg.vf_lr; h.alpha_lr = cfg.alpha_lr;
+  h.beta1 = cfg.beta_1; h.beta2 = cfg.beta_2 > 0 ? cfg.beta_2 : 0.999; h.adam_eps = cfg.adam_eps > 0 ? cfg.adam_eps : 1e-8;
+  h.mean_reg = (float)cfg.policy_mean_reg_weight; h.std_reg = (float)cfg.policy_std_reg_weight;
+  h.target_entropy = (float)cfg.target_entropy; h.train_alpha = cfg.train_alpha; h.fixed_alpha = (float)cfg.alpha;
+  h.period = cfg.policy_and_target_update_period > 0 ? cfg.policy_and_target_update_period : 1;
+  h.policy_noise = (float)cfg.policy_noise; h.noise_clip = (float)cfg.policy_noise_clip;
+  h.max_act = cfg.max_act != 0 ? (float)cfg.max_act : 1.0f;
+  return h;
+}
+
+inline void apply_disc_hyper(Hyper& h, const ilsw_disc_config& d) {
+  h.has_disc = 1; h.disc_mode = d.mode; h.disc_lr = d.disc_lr; h.disc_beta1 = d.disc_momentum;
+  h.gp_weight = (float)d.grad_pen_weight; h.disc_clamp = (float)d.clamp_magnitude; h.use_gp = d.use_grad_pen;
+  h.clip_min_on = d.rew_clip_min_on; h.clip_max_on = d.rew_clip_max_on;
+  h.rew_clip_min = (float)d.rew_clip_min; h.rew_clip_max = (float)d.rew_clip_max;
+}
+
+inline int build_program(Program& P);
+
+struct TrainerSpec {
+  ilsw_trainer_config cfg;
+  ilsw_mlp nets[6];
+  int n_nets;
+  int has_disc;
+  ilsw_disc_config dcfg;
+  ilsw_mlp disc;
+};
+
+inline int validate_spec(const TrainerSpec& sp, std::string* why) {
+  const ilsw_trainer_config& c = sp.cfg;
+  auto fail = [&](const char* m) { if (why) *why = m; return (int)ILSW_ERR_ARG; };
+  if (c.obs_dim <= 0 || c.act_dim <= 0 || c.batch <= 0) return fail("obs_dim/act_dim/batch must be positive");
+  if (c.act_dim > 64) return fail("act_dim > 64 unsupported");
+  if (c.max_steps_per_call <= 0) return fail("max_steps_per_call must be positive");
+  int need = c.algo == ILSW_ALGO_SAC_ALPHA ? 5 : (c.algo == ILSW_ALGO_TD3 ? 6 : -1);
+  if (need < 0) return fail("unsupported algo");
+  if (sp.n_nets != need) return fail("wrong number of networks for this algorithm");
+  const int Hd = sp.nets[0].hidden;
+  for (int i = 0; i < sp.n_nets; ++i) {
+    const ilsw_mlp& n = sp.nets[i];
+    if (!n.p) return fail("null parameter arena");
+    if (n.hidden != Hd || Hd <= 0) return fail("all networks must share one hidden width");
+    bool is_policy = (i == 0) || (c.algo == ILSW_ALGO_TD3 && i == 5);
+    int in_dim = is_policy ? c.obs_dim : c.obs_dim + c.act_dim;
+    int out_dim = is_policy ? c.act_dim : 1;
+    if (n.in_dim != in_dim || n.out_dim != out_dim) return fail("network in/out dims do not match obs/act dims");
+    if ((n.log_std_head != 0) != (is_policy && c.algo != ILSW_ALGO_TD3)) return fail("log_std_head mismatch");
+    bool trainable = i < 3;
+    if (trainable && (!n.m || !n.v)) return fail("trainable network needs Adam moment arenas");
+  }
+  if (sp.has_disc) {
+    if (c.algo != ILSW_ALGO_SAC_ALPHA) return fail("discriminator requires the SAC-alpha trainer");
+    if (sp.dcfg.batch != c.batch) return fail("disc batch must equal policy batch");
+    if (sp.disc.in_dim != c.obs_dim + c.act_dim || sp.disc.out_dim != 1 || sp.disc.log_std_head) return fail("disc dims");
+    if (!sp.disc.p || !sp.disc.m || !sp.disc.v) return fail("disc arenas");
+    if (sp.dcfg.mode < 0 || sp.dcfg.mode > 3) return fail("disc mode");
+  }
+  return ILSW_OK;
+}
+
+// Lays out scratch in `mem` (two-pass capable), fills P.ctx and compiles the program.
+inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem) {
+  memset(&P, 0, sizeof(P));
+  Ctx& c = P.ctx;
+  const ilsw_trainer_config& cfg = sp.cfg;
+  c.hp = make_hyper(cfg);
+  if (sp.has_disc) apply_disc_hyper(c.hp, sp.dcfg);
+  const int B = cfg.batch, O = cfg.obs_dim, A = cfg.act_dim, Hd = sp.nets[0].hidden;
+  c.dyn = mem.take<DynState>(1);
+  c.loss_log = mem.f((size_t)cfg.max_steps_per_call * kLossSlots);
+  c.stats_floats = stats_floats_for(cfg.algo, B, A);
+  c.stats = mem.f(c.stats_floats);
+  alloc_sac_bufs(mem, c.s, cfg.algo, B, O, A, Hd);
+  auto grad = [&](const ilsw_mlp& n) { return mem.f(mlp_num_params(n.in_dim, n.hidden, n.out_dim, n.log_std_head)); };
+  c.policy = make_mlp(sp.nets[0], grad(sp.nets[0]));
+  c.qf[0] = make_mlp(sp.nets[1], grad(sp.nets[1]));
+  c.qf[1] = make_mlp(sp.nets[2], grad(sp.nets[2]));
+  c.tqf[0] = make_mlp(sp.nets[3], nullptr);
+  c.tqf[1] = make_mlp(sp.nets[4], nullptr);
+  if (cfg.algo == ILSW_ALGO_TD3) c.tpolicy = make_mlp(sp.nets[5], nullptr);
+  if (sp.has_disc) {
+    alloc_disc_bufs(mem, c.d, B, O + A, sp.disc.hidden);
+    c.disc = make_mlp(sp.disc, grad(sp.disc));
+  }
+  return build_program(P);
+}
+
+// Assembles the whole step program.  Returns 0 or a negative ilsw_status.
+inline int build_program(Program& P) {
+  Builder b(P);
+  const Ctx& c = P.ctx;
+  if (c.hp.has_disc) build_disc_step(b, c);
+  if (c.hp.algo == ILSW_ALGO_SAC_ALPHA) build_sac_alpha(b, c);
+  else if (c.hp.algo == ILSW_ALGO_TD3) build_td3(b, c);
+  else return ILSW_ERR_UNSUPPORTED;
+  return b.overflow ? ILSW_ERR_STATE : ILSW_OK;
+}
+
+inline std::string describe_program(const Program& P) {
+  std::string out;
+  char line[256];
+  static const char* kinds[] = {"?", "GEMM", "ADAM", "ROW", "POLYAK"};
+  for (int i = 0; i < P.n_phases; ++i) {
+    const Phase& ph = P.phases[i];
+    snprintf(line, sizeof(line), "phase %2d jobs=%4d%s%s:", i, ph.total_jobs, ph.cond ? " [td3-policy-step]" : "",
+             ph.collective ? " [replica-exchange]" : "");
+    out += line;
+    for (int j = 0; j < ph.op_count; ++j) {
+      const Op& o = P.ops[ph.op_begin + j];
+      if (o.kind == OP_GEMM)
+        snprintf(line, sizeof(line), " GEMM(%dx%dx%d%s%s)", o.gemm.M, o.gemm.N, o.gemm.K, o.gemm.aug_ones ? "+1" : "",
+                 o.gemm.accumulate ? ",acc" : "");
+      else if (o.kind == OP_ROW)
+        snprintf(line, sizeof(line), " ROW(k%d,%d)", o.row.kind, o.row.rows);
+      else if (o.kind == OP_ADAM)
+        snprintf(line, sizeof(line), " ADAM(%d%s)", o.adam.n, o.adam.target ? ",polyak" : "");
+      else
+        snprintf(line, sizeof(line), " %s(%d)", kinds[o.kind], o.polyak.n);
+      out += line;
+    }
+    out += "\n";
+  }
+  return out;
+}
+
+}  // namespace ilsw

@@ -1,0 +1,221 @@
+// ilswiss_b200 -- plain-old-data structures shared by the program builder (host C++),
+// the persistent engine kernel (sm_100a) and the test-only host simulator.
+//
+// One "program" = the whole gradient step of one algorithm (SAC-alpha: sac_alpha.py:78-181,
+// TD3: td3.py:72-124, AdvIRL disc step + reward relabel: adv_irl.py:133-314) expressed as an
+// ordered list of PHASES; a phase is a set of independent tile jobs (GEMM tiles, row jobs,
+// flat Adam/Polyak chunks) separated from the next phase by a grid-wide barrier.  The engine
+// kernel is launched ONCE per train call and loops `n_steps x phases` on-chip.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ILSW_HD __host__ __device__ __forceinline__
+#else
+#define ILSW_HD inline
+#endif
+
+namespace ilsw {
+
+constexpr int kMaxPhases = 96;
+constexpr int kMaxOps = 256;
+constexpr int kMaxNets = 8;       // Adam step-counter slots
+constexpr int kLossSlots = 16;    // floats per step in the loss log
+constexpr int kThreads = 256;     // CTA size of the engine kernel
+constexpr int kRowsPerJob = 8;    // one warp per batch row
+constexpr int kAdamChunk = 2048;  // elements per flat Adam/Polyak job
+
+enum OpKind : int { OP_GEMM = 1, OP_ADAM = 2, OP_ROW = 3, OP_POLYAK = 4 };
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
+
+// phase conditions
+enum Cond : int { COND_ALWAYS = 0, COND_TD3_POLICY = 1 };
+
+// loss-log slots (per step)
+enum LossSlot : int {
+  L_QF1 = 0, L_QF2 = 1, L_POLICY = 2, L_ALPHA_LOSS = 3, L_ALPHA = 4, L_VF = 5,
+  L_DISC_CE = 6, L_DISC_ACC = 7, L_GRAD_PEN = 8, L_REW_MEAN = 9, L_REW_STD = 10,
+  L_REW_MAX = 11, L_REW_MIN = 12, L_Q1_MEAN = 13, L_LOGPI_MEAN = 14, L_QT_MEAN = 15
+};
+
+struct GemmOp {
+  // C[m,n] = epilogue( sum_k A(m,k) * B(k,n) )
+  const float* A; int lda; int a_mc;  // a_mc=0: A(m,k)=A[m*lda+k] (k contiguous); 1: A[k*lda+m]
+  const float* B; int ldb; int b_nc;  // b_nc=0: B(k,n)=B[n*ldb+k] (k contiguous); 1: B[k*ldb+n]
+  int M, N, K;
+  int aug_ones;         // 1: logical extra column n==N with B(k,N)=1, routed to bias_out[m]
+  float* C; int ldc;
+  float* C2;            // optional second output: value BEFORE the mask (ldc shared)
+  float* bias_out;      // aug_ones destination (bias gradient)
+  const float* bias;    // forward: + bias[n]
+  const float* H; int ldh;  // mask source (post-activation values of the layer below)
+  int act;              // forward activation
+  int mask;             // backward mask: ACT_RELU -> (H>0), ACT_TANH -> (1-H^2)
+  int accumulate;       // C += value (and bias_out +=)
+  int tiles_m, tiles_n;
+};
+
+struct AdamOp {
+  float* p; const float* g; float* m; float* v;
+  float* target;        // optional Polyak target updated from the NEW p (nullptr: none)
+  int n;
+  double lr, beta1, beta2, eps; float tau;
+  int slot;             // Adam step-counter slot
+  int grad_scale_world; // 1: divide g by world size (replica-averaged policy gradient)
+};
+
+struct PolyakOp { float* target; const float* src; int n; float tau; };
+
+struct RowOp {
+  int kind;             // algorithm-specific row kernel id
+  int rows;             // number of rows (jobs = ceil(rows / kRowsPerJob))
+  int arg0, arg1;
+};
+
+struct Op {
+  int kind;
+  int n_jobs;
+  union {
+    GemmOp gemm;
+    AdamOp adam;
+    PolyakOp polyak;
+    RowOp row;
+  };
+};
+
+struct Phase {
+  int op_begin, op_count;
+  int total_jobs;
+  int cond;
+  int collective;       // 1: cross-replica gradient exchange happens at the START of this phase
+};
+
+// ---- per-algorithm buffer tables (device or host pointers) --------------------------------
+
+struct MlpPtrs {        // canonical 2-hidden-layer layout inside one flat arena
+  float* p; float* m; float* v; float* g;   // params, Adam moments, gradient arena
+  int in_dim, hid, out_dim, heads;          // heads=2: extra log-std head (policy)
+  int n_params;
+  // element offsets
+  int oW0, ob0, oW1, ob1, oW2, ob2, oW3, ob3;
+};
+
+struct SacBufs {        // SAC-alpha / TD3 / SAC-V scratch (all fp32, row-major)
+  int B, O, A, Hd, ld_oa, ld_o;
+  int* idx;
+  float *Xoa, *rew, *term, *Xpi, *Xna, *Xon, *eps;
+  float *h0q[2], *h1q[2], *h0t[2], *h1t[2], *h0n[2], *h1n[2];
+  float *h0p, *h1p, *mean, *lraw, *lstd, *act, *logpi;
+  float *qp[2], *tq[2], *y, *qn[2], *dq[2];
+  float *d1q[2], *d0q[2], *e1[2], *e0[2], *dA[2];
+  float *dmean, *dlraw, *d1p, *d0p;
+  float *lossterm[2], *plterm, *regmu, *regls, *aterm;
+  // TD3 extras
+  float *h0tp, *h1tp;   // target policy activations
+  float *noise;
+  // SAC-V extras
+  float *h0v, *h1v, *h0tv, *h1tv, *vp, *tv, *dv, *d1v, *d0v, *lossterm_v, *qn_old[2];
+};
+
+struct DiscBufs {
+  int B, D, Hd, ld_d;
+  int *idx_e, *idx_p;
+  float *X3;            // [3B x ld_d]: expert rows, policy rows, interpolated rows
+  float *gp_eps;
+  float *h1, *h2;       // [3B x Hd]
+  float *y, *dlogit, *cmask;      // [3B], [2B], [B]
+  float *d2, *d1;       // CE deltas [2B x Hd]
+  float *dl2, *u1, *dl1, *g, *gbar, *nrm;   // GP: delta2, u1, delta1, g [B x ld_d], gbar, norms
+  float *db1, *ub1, *sb1, *db2, *t3, *zb2, *hb1, *zb1;
+  float *ceterm, *accterm, *gpterm;
+  // reward relabel (D2)
+  float *rh1, *rh2, *rewraw;
+};
+
+struct DynState {       // device-resident mutable scalars (persist across launches)
+  double log_alpha, alpha_m, alpha_v;
+  int alpha_t;
+  float alpha;          // exp(log_alpha) as used by the fp32 graph
+  int abort_flag;
+  int error_code;
+};
+
+struct Hyper {
+  int algo;             // 1 sac_alpha, 2 td3, 3 sac_v
+  float reward_scale, discount, tau;
+  double policy_lr, qf_lr, vf_lr, alpha_lr, beta1, beta2, adam_eps;
+  float mean_reg, std_reg, target_entropy;
+  int train_alpha;
+  float fixed_alpha;
+  // td3
+  int period; float policy_noise, noise_clip, max_act;
+  // disc
+  int has_disc; int disc_mode;    // 0 airl 1 gail 2 gail2 3 fairl
+  double disc_lr, disc_beta1; float gp_weight, disc_clamp; int use_gp;
+  int clip_min_on, clip_max_on; float rew_clip_min, rew_clip_max;
+};
+
+struct Ctx {            // everything a row kernel needs
+  Hyper hp;
+  SacBufs s;
+  DiscBufs d;
+  MlpPtrs policy, qf[2], tqf[2], tpolicy, vf, tvf, disc;
+  DynState* dyn;
+  float* loss_log;      // [max_steps x kLossSlots]
+  float* stats;         // snapshot area (see ilsw_stats layout in include/ilswiss_b200.h)
+  int stats_floats;
+};
+
+struct RingView {       // replay ring as seen by the gather row kernel
+  const float* rows; int stride; int size;   // hot rows [capacity x stride]
+};
+
+struct Inject {         // optional injected randomness (parity mode); all device pointers
+  const int* idx;       // [T x B]
+  const float* eps_next;  // [T x B x A]   (TD3: target-policy noise)
+  const float* eps_cur;   // [T x B x A]
+  const int* idx_expert;  // [T x B]   (disc step)
+  const int* idx_policy_d;  // [T x B]
+  const float* gp_eps;    // [T x B]
+};
+
+struct DirectBatch {    // optional: train on a caller-provided dense batch instead of the ring
+  const float *obs, *act, *rew, *term, *next_obs;   // [B x O], [B x A], [B], [B], [B x O]
+};
+
+struct RunArgs {
+  int n_steps;
+  int step0;            // global train-step counter at launch (TD3 delay phase, Philox offset)
+  int stats_step;       // step index (within launch) whose vectors are snapshotted; -1 none
+  int t0[kMaxNets];     // Adam step counts at launch, per slot
+  uint64_t seed;
+  RingView ring_policy, ring_expert;
+  Inject inj; int has_inject;
+  DirectBatch direct; int has_direct;
+  // replicas
+  int world, rank;
+  int loss_log_offset;  // first row of loss_log to write
+};
+
+struct Program {
+  int n_phases, n_ops;
+  Phase phases[kMaxPhases];
+  Op ops[kMaxOps];
+  Ctx ctx;
+};
+
+// Adam slots
+enum Slot : int { SLOT_QF1 = 0, SLOT_QF2 = 1, SLOT_POLICY = 2, SLOT_VF = 3, SLOT_DISC = 4 };
+
+// row kernel ids
+enum RowKind : int {
+  ROW_SAC_GATHER = 1, ROW_SAC_HEADS, ROW_SAC_TARGET, ROW_SAC_PLOSS, ROW_SAC_PIBWD, ROW_SAC_FINAL,
+  ROW_TD3_GATHER, ROW_TD3_THEAD, ROW_TD3_TARGET, ROW_TD3_PHEAD, ROW_TD3_PLOSS, ROW_TD3_PIBWD,
+  ROW_TD3_FINAL, ROW_TD3_FINAL_POLICY,
+  ROW_DISC_GATHER, ROW_DISC_HEAD, ROW_DISC_GNORM, ROW_DISC_EW1, ROW_DISC_EW2, ROW_DISC_EW3,
+  ROW_DISC_FINAL, ROW_DISC_REWARD, ROW_DISC_REWARD_FINAL,
+  ROW_SACV_HEADS, ROW_SACV_TARGET, ROW_SACV_VTARGET, ROW_SACV_PLOSS, ROW_SACV_FINAL
+};
+
+}  // namespace ilsw

@@ -1,0 +1,243 @@
+"""Shared test helpers: seed-reproducible inputs for the parity cases (oracle/configs.py)
+following the step protocol documented in oracle/make_golden.py."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import configs as CFG  # noqa: E402
+from oracle import make_golden as G  # noqa: E402
+from oracle import restate as R  # noqa: E402
+from ilswiss_b200 import _abi, layout  # noqa: E402
+
+STAT_TO_SLOT = {
+    "QF1 Loss": _abi.L_QF1, "QF2 Loss": _abi.L_QF2, "Policy Loss": _abi.L_POLICY,
+    "Alpha Loss": _abi.L_ALPHA_LOSS, "Alpha Mean": _abi.L_ALPHA, "Disc CE Loss": _abi.L_DISC_CE,
+    "Disc Acc": _abi.L_DISC_ACC, "Grad Pen": _abi.L_GRAD_PEN, "Disc Rew Mean": _abi.L_REW_MEAN,
+    "Disc Rew Std": _abi.L_REW_STD, "Disc Rew Max": _abi.L_REW_MAX, "Disc Rew Min": _abi.L_REW_MIN,
+    "Q1 Predictions Mean": _abi.L_Q1_MEAN, "Log Pis Mean": _abi.L_LOGPI_MEAN,
+    "Q Targets Mean": _abi.L_QT_MEAN,
+}
+
+
+def case_data(case):
+    O, A = case["obs_dim"], case["act_dim"]
+    term_p = 0.0 if case["algo"] == "adv_irl" else 0.01
+    data = R.synth_transitions(case["n_fill"], O, A, CFG.DATA_SEED, term_p)
+    edata = None
+    if case["algo"] == "adv_irl":
+        edata = R.synth_transitions(case["n_expert"], O, A, CFG.EXPERT_DATA_SEED, 0.0)
+    return data, edata
+
+
+def case_injection(case, steps=None):
+    """idx / eps streams exactly as the reference run consumed them."""
+    B, A = case["batch"], case["act_dim"]
+    T = steps or case["steps"]
+    rs = np.random.RandomState(CFG.BUFFER_SEED)
+    ers = np.random.RandomState(CFG.EXPERT_SEED)
+    algo = case["algo"]
+    out = dict(idx=np.zeros((T, B), np.int32), eps_next=np.zeros((T, B, A), np.float32),
+               eps_cur=np.zeros((T, B, A), np.float32), idx_expert=np.zeros((T, B), np.int32),
+               idx_policy_d=np.zeros((T, B), np.int32), gp_eps=np.zeros((T, B), np.float32))
+    for t in range(T):
+        torch.manual_seed(CFG.EPS_SEED0 + t)
+        if algo == "adv_irl":
+            out["idx_expert"][t] = ers.randint(0, case["n_expert"], B)
+            out["idx_policy_d"][t] = rs.randint(0, case["n_fill"], B)
+            if case["disc"]["use_grad_pen"]:
+                out["gp_eps"][t] = torch.rand(B, 1).numpy().ravel()
+        out["idx"][t] = rs.randint(0, case["n_fill"], B)
+        out["eps_next"][t] = torch.randn(B, A).numpy()
+        if algo in ("sac_alpha", "adv_irl"):
+            out["eps_cur"][t] = torch.randn(B, A).numpy()
+        elif algo == "sac_v":
+            out["eps_cur"][t] = out["eps_next"][t]
+    return out
+
+
+def trainer_config(case, max_steps=64):
+    algo = case["algo"]
+    cfg = _abi.TrainerConfig()
+    cfg.obs_dim, cfg.act_dim, cfg.batch = case["obs_dim"], case["act_dim"], case["batch"]
+    cfg.max_steps_per_call = max_steps
+    cfg.beta_2, cfg.adam_eps = 0.999, 1e-8
+    cfg.max_act = 1.0
+    if algo in ("sac_alpha", "adv_irl"):
+        kw = case["sac"]
+        cfg.algo = _abi.ALGO_SAC_ALPHA
+        cfg.reward_scale, cfg.discount = kw["reward_scale"], kw["discount"]
+        cfg.soft_target_tau = kw["soft_target_tau"]
+        cfg.policy_lr, cfg.qf_lr = kw["policy_lr"], kw["qf_lr"]
+        cfg.alpha_lr = kw.get("alpha_lr", 3e-4)
+        cfg.beta_1 = kw.get("beta_1", 0.9)
+        cfg.alpha = kw.get("alpha", 0.2)
+        cfg.train_alpha = int(kw.get("train_alpha", True))
+        te = kw.get("target_entropy")
+        cfg.target_entropy = (-case["act_dim"] / 2.0) if te is None else te
+        cfg.policy_mean_reg_weight = kw["policy_mean_reg_weight"]
+        cfg.policy_std_reg_weight = kw["policy_std_reg_weight"]
+    elif algo == "td3":
+        kw = case["td3"]
+        cfg.algo = _abi.ALGO_TD3
+        cfg.reward_scale, cfg.discount = kw["reward_scale"], kw["discount"]
+        cfg.soft_target_tau = kw["soft_target_tau"]
+        cfg.policy_lr, cfg.qf_lr = kw["policy_lr"], kw["qf_lr"]
+        cfg.beta_1 = 0.9
+        cfg.alpha = 1.0
+        cfg.policy_and_target_update_period = kw["policy_and_target_update_period"]
+        cfg.policy_noise, cfg.policy_noise_clip = case["policy_noise"], case["policy_noise_clip"]
+    else:
+        raise NotImplementedError(algo)
+    return cfg
+
+
+def disc_config(case):
+    d = case["disc"]
+    dc = _abi.DiscConfig()
+    dc.mode = _abi.DISC_MODES[case["mode"]]
+    dc.batch = case["batch"]
+    dc.disc_lr, dc.disc_momentum = d["disc_lr"], d["disc_momentum"]
+    dc.use_grad_pen, dc.grad_pen_weight = int(d["use_grad_pen"]), d["grad_pen_weight"]
+    dc.clamp_magnitude = 10.0
+    dc.rew_clip_min_on = int(case.get("rew_clip_min") is not None)
+    dc.rew_clip_max_on = int(case.get("rew_clip_max") is not None)
+    dc.rew_clip_min = case.get("rew_clip_min") or 0.0
+    dc.rew_clip_max = case.get("rew_clip_max") or 0.0
+    return dc
+
+
+def net_order(case):
+    """Order of networks expected by ilsw_trainer_create."""
+    if case["algo"] == "td3":
+        return ["policy", "qf1", "qf2", "target_qf1", "target_qf2", "target_policy"]
+    return ["policy", "qf1", "qf2", "target_qf1", "target_qf2"]
+
+
+def initial_arenas(case):
+    """name -> float32 flat parameter arena (targets are copies, like PyTorchModule.copy())."""
+    nets = G.build_oracle_nets(case)
+    flat = {k: n.flat().astype(np.float32) for k, n in nets.items()}
+    flat["target_qf1"], flat["target_qf2"] = flat["qf1"].copy(), flat["qf2"].copy()
+    if case["algo"] == "td3":
+        flat["target_policy"] = flat["policy"].copy()
+    return flat
+
+
+def mlp_dims(case, name):
+    O, A = case["obs_dim"], case["act_dim"]
+    if name in ("policy", "target_policy"):
+        return O, CFG.HIDDEN[0], A, int(case["algo"] != "td3")
+    if name == "disc":
+        return O + A, CFG.DISC_HID, 1, 0
+    return O + A, CFG.HIDDEN[0], 1, 0
+
+
+# ---------------------------------------------------------------------------------------------
+# host simulator (tests/hostsim) loader
+# ---------------------------------------------------------------------------------------------
+def load_hostsim():
+    d = os.path.join(ROOT, "tests", "hostsim")
+    so = os.path.join(d, "libilsw_hostsim.so")
+    srcs = [os.path.join(d, "hostsim.cpp")] + [
+        os.path.join(ROOT, "ilswiss_b200", "csrc", f) for f in ("ilsw_ops.cuh", "ilsw_program.h", "ilsw_types.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, srcs[0]])
+    lib = C.CDLL(so)
+    lib.hs_create.restype = C.c_void_p
+    lib.hs_create.argtypes = [C.POINTER(_abi.TrainerConfig), C.POINTER(_abi.Mlp), C.c_int,
+                              C.POINTER(_abi.DiscConfig), C.POINTER(_abi.Mlp), C.c_char_p, C.c_int]
+    lib.hs_destroy.argtypes = [C.c_void_p]
+    lib.hs_train.restype = C.c_int
+    lib.hs_train.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                             C.POINTER(_abi.Inject), C.POINTER(_abi.Batch), C.c_uint64, C.c_int]
+    lib.hs_losses.restype = C.POINTER(C.c_float)
+    lib.hs_losses.argtypes = [C.c_void_p]
+    lib.hs_stats.restype = C.POINTER(C.c_float)
+    lib.hs_stats.argtypes = [C.c_void_p]
+    lib.hs_stats_floats.restype = C.c_int
+    lib.hs_stats_floats.argtypes = [C.c_void_p]
+    lib.hs_log_alpha.restype = C.c_double
+    lib.hs_log_alpha.argtypes = [C.c_void_p]
+    lib.hs_num_phases.restype = C.c_int
+    lib.hs_num_phases.argtypes = [C.c_void_p]
+    lib.hs_describe.restype = C.c_int
+    lib.hs_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    lib.hs_grad.restype = C.POINTER(C.c_float)
+    lib.hs_grad.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    return lib
+
+
+def np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class HostSimRun:
+    """Runs one parity case through the host simulator with injected randomness."""
+
+    def __init__(self, lib, case, max_steps=64):
+        self.lib, self.case = lib, case
+        self.arenas = initial_arenas(case)
+        self.moms = {}
+        names = net_order(case)
+        mlps = (_abi.Mlp * len(names))()
+        for i, n in enumerate(names):
+            i_d, h_d, o_d, ls = mlp_dims(case, n)
+            a = self.arenas[n]
+            assert a.size == layout.mlp_num_params(i_d, h_d, o_d, ls), (n, a.size)
+            m, v = np.zeros_like(a), np.zeros_like(a)
+            self.moms[n] = (m, v)
+            mlps[i] = _abi.Mlp(np_ptr(a), np_ptr(m), np_ptr(v), i_d, h_d, o_d, ls)
+        cfg = trainer_config(case, max_steps)
+        dcfg_p, disc_p = None, None
+        if case["algo"] == "adv_irl":
+            self.dcfg = disc_config(case)
+            i_d, h_d, o_d, ls = mlp_dims(case, "disc")
+            a = self.arenas["disc"]
+            m, v = np.zeros_like(a), np.zeros_like(a)
+            self.moms["disc"] = (m, v)
+            self.disc = _abi.Mlp(np_ptr(a), np_ptr(m), np_ptr(v), i_d, h_d, o_d, ls)
+            dcfg_p, disc_p = C.byref(self.dcfg), C.byref(self.disc)
+        err = C.create_string_buffer(256)
+        self.h = lib.hs_create(C.byref(cfg), mlps, len(names), dcfg_p, disc_p, err, 256)
+        assert self.h, err.value
+        data, edata = case_data(case)
+        self.ring = layout.pack_hot_rows(**data)
+        self.ering = layout.pack_hot_rows(**edata) if edata is not None else None
+
+    def train(self, n_steps, inj, stats_step=-1, t_offset=0, seed=0):
+        keep = {k: np.ascontiguousarray(v[t_offset:t_offset + n_steps]) for k, v in inj.items()}
+        ij = _abi.Inject(np_ptr(keep["idx"]), np_ptr(keep["eps_next"]), np_ptr(keep["eps_cur"]),
+                         np_ptr(keep["idx_expert"]), np_ptr(keep["idx_policy_d"]), np_ptr(keep["gp_eps"]))
+        er = self.ering
+        rc = self.lib.hs_train(self.h, np_ptr(self.ring), self.ring.shape[1], self.ring.shape[0],
+                               np_ptr(er) if er is not None else None, er.shape[1] if er is not None else 0,
+                               er.shape[0] if er is not None else 0, n_steps, C.byref(ij), None, seed, stats_step)
+        assert rc == 0
+        L = np.ctypeslib.as_array(self.lib.hs_losses(self.h), shape=(n_steps, _abi.LOSS_SLOTS)).copy()
+        return L
+
+    def close(self):
+        self.lib.hs_destroy(self.h)
+
+
+def assert_params_close(got, ref, steps, lr=3e-4, msg=""):
+    """Parameter parity bar.  <=1e-5 abs for all but a vanishing fraction of
+    elements: Adam's normalised update m/(sqrt(v)+eps) is +-lr in the first steps REGARDLESS of
+    |g|, so an element whose true gradient is ~0 (|g| ~ 1e-9, pure summation-order noise) can
+    legitimately differ by up to 2*lr per step between two fp32 implementations.  Those
+    elements are bounded by 2*lr*steps and must be rarer than 1e-4 of the tensor."""
+    got = np.asarray(got, dtype=np.float64).ravel()
+    ref = np.asarray(ref, dtype=np.float64).ravel()
+    assert got.shape == ref.shape, (msg, got.shape, ref.shape)
+    diff = np.abs(got - ref)
+    bad = int((diff > 1e-5).sum())
+    assert bad <= max(1, int(1e-4 * diff.size)), (msg, bad, diff.size, float(diff.max()))
+    assert float(diff.max()) <= 2.0 * lr * steps + 1e-6, (msg, float(diff.max()))

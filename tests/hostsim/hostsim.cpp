@@ -1,0 +1,129 @@
+// TEST INFRASTRUCTURE ONLY -- host simulator of the ilswiss_b200 step engine.
+//
+// Compiles the product's op semantics (ilswiss_b200/csrc/ilsw_ops.cuh) and program builder
+// (ilsw_program.h) for the CPU with a 1-lane "warp", and executes the phase program
+// sequentially on host memory.  tests/test_hostsim.py compares it with the oracle so that the
+// program wiring and the hand-derived backward passes are verified without a GPU.  This file
+// is never linked into libilswiss_b200.so and the product never falls back to it.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../ilswiss_b200/csrc/ilsw_ops.cuh"
+#include "../../ilswiss_b200/csrc/ilsw_program.h"
+
+using namespace ilsw;
+
+struct HostSim {
+  Program prog;
+  std::vector<char> scratch;
+  TrainerSpec spec;
+  int t[kMaxNets];
+  int n_total;
+};
+
+static void run_op(const Program& P, const Op& o, const RunArgs& a, int s) {
+  const Ctx& c = P.ctx;
+  if (o.kind == OP_GEMM) {
+    const GemmOp& g = o.gemm;
+    int Nt = g.N + g.aug_ones;
+    for (int m = 0; m < g.M; ++m)
+      for (int n = 0; n < Nt; ++n) {
+        float acc = 0.f;
+        for (int k = 0; k < g.K; ++k) acc += gemm_A(g, m, k) * gemm_B(g, k, n);
+        gemm_epilogue(g, m, n, acc);
+      }
+  } else if (o.kind == OP_ROW) {
+    for (int r = 0; r < o.row.rows; ++r) run_row(c, a, o.row.kind, s, r, 0, 1);
+  } else if (o.kind == OP_ADAM) {
+    AdamCoef cf = adam_coef(o.adam, adam_t(a, c.hp, o.adam.slot, s), a.world);
+    for (int i = 0; i < o.adam.n; ++i) adam_elem(o.adam, cf, i);
+  } else if (o.kind == OP_POLYAK) {
+    for (int i = 0; i < o.polyak.n; ++i) polyak_elem(o.polyak, i);
+  }
+}
+
+extern "C" {
+
+void* hs_create(const ilsw_trainer_config* cfg, const ilsw_mlp* nets, int n_nets, const ilsw_disc_config* dcfg,
+                const ilsw_mlp* disc, char* err, int err_len) {
+  HostSim* h = new HostSim();
+  memset(&h->spec, 0, sizeof(h->spec));
+  h->spec.cfg = *cfg;
+  for (int i = 0; i < n_nets && i < 6; ++i) h->spec.nets[i] = nets[i];
+  h->spec.n_nets = n_nets;
+  if (dcfg) { h->spec.has_disc = 1; h->spec.dcfg = *dcfg; h->spec.disc = *disc; }
+  std::string why;
+  if (validate_spec(h->spec, &why) != 0) {
+    if (err) snprintf(err, err_len, "%s", why.c_str());
+    delete h;
+    return nullptr;
+  }
+  Bump measure;
+  Program tmp;
+  assemble(tmp, h->spec, measure);
+  h->scratch.assign(measure.off + 256, 0);
+  Bump mem;
+  mem.base = h->scratch.data();
+  if (assemble(h->prog, h->spec, mem) != 0) { delete h; return nullptr; }
+  DynState* d = h->prog.ctx.dyn;
+  memset(d, 0, sizeof(*d));
+  d->log_alpha = log(cfg->alpha);
+  d->alpha = (float)exp(d->log_alpha);
+  memset(h->t, 0, sizeof(h->t));
+  h->n_total = 0;
+  return h;
+}
+
+void hs_destroy(void* p) { delete (HostSim*)p; }
+
+int hs_train(void* p, const float* ring, int stride, int size, const float* ering, int estride, int esize, int n_steps,
+             const ilsw_inject* inj, const ilsw_batch* batch, uint64_t seed, int stats_step) {
+  HostSim* h = (HostSim*)p;
+  RunArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_steps = n_steps; a.step0 = h->n_total; a.stats_step = stats_step; a.seed = seed;
+  for (int i = 0; i < kMaxNets; ++i) a.t0[i] = h->t[i];
+  a.ring_policy = {ring, stride, size};
+  a.ring_expert = {ering, estride, esize};
+  if (inj) {
+    a.has_inject = 1;
+    a.inj.idx = inj->idx; a.inj.eps_next = inj->eps_next; a.inj.eps_cur = inj->eps_cur;
+    a.inj.idx_expert = inj->idx_expert; a.inj.idx_policy_d = inj->idx_policy_d; a.inj.gp_eps = inj->gp_eps;
+  }
+  if (batch) {
+    a.has_direct = 1;
+    a.direct = {batch->obs, batch->act, batch->rew, batch->term, batch->next_obs};
+  }
+  a.world = 1; a.rank = 0; a.loss_log_offset = 0;
+  const Program& P = h->prog;
+  for (int s = 0; s < n_steps; ++s)
+    for (int ph = 0; ph < P.n_phases; ++ph) {
+      const Phase& phs = P.phases[ph];
+      if (!phase_active(phs, P.ctx.hp, a, s)) continue;
+      for (int j = 0; j < phs.op_count; ++j) run_op(P, P.ops[phs.op_begin + j], a, s);
+    }
+  for (int slot = 0; slot < kMaxNets; ++slot) h->t[slot] = adam_t(a, P.ctx.hp, slot, n_steps - 1);
+  h->n_total += n_steps;
+  return 0;
+}
+
+const float* hs_losses(void* p) { return ((HostSim*)p)->prog.ctx.loss_log; }
+const float* hs_stats(void* p) { return ((HostSim*)p)->prog.ctx.stats; }
+int hs_stats_floats(void* p) { return ((HostSim*)p)->prog.ctx.stats_floats; }
+double hs_log_alpha(void* p) { return ((HostSim*)p)->prog.ctx.dyn->log_alpha; }
+int hs_num_phases(void* p) { return ((HostSim*)p)->prog.n_phases; }
+int hs_describe(void* p, char* buf, int n) {
+  std::string s = describe_program(((HostSim*)p)->prog);
+  snprintf(buf, n, "%s", s.c_str());
+  return (int)s.size();
+}
+// access to a gradient arena for formula tests: which = 0 policy, 1 qf1, 2 qf2, 3 disc
+const float* hs_grad(void* p, int which, int* n) {
+  const Ctx& c = ((HostSim*)p)->prog.ctx;
+  const MlpPtrs* m = which == 0 ? &c.policy : which == 1 ? &c.qf[0] : which == 2 ? &c.qf[1] : &c.disc;
+  *n = m->n_params;
+  return m->g;
+}
+}
