@@ -1,0 +1,518 @@
+// ilswiss_b200 -- C ABI (include/ilswiss_b200.h) over the sm_100a kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ilswiss_b200.h"
+#include "ilsw_engine.cuh"
+#include "ilsw_program.h"
+
+using namespace ilsw;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(ILSW_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" int ilsw_abi_version(void) { return ILSW_ABI_VERSION; }
+extern "C" const char* ilsw_last_error(void) { return g_err; }
+
+extern "C" int ilsw_device_info(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len) {
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  CU(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (name && name_len > 0) snprintf(name, name_len, "%s", p.name);
+  return ILSW_OK;
+}
+
+extern "C" int ilsw_mlp_num_params(int in_dim, int hidden, int out_dim, int log_std_head) {
+  return mlp_num_params(in_dim, hidden, out_dim, log_std_head);
+}
+
+// ==========================================================================================
+// Replay ring (R1-R4)
+// ==========================================================================================
+struct ilsw_rb {
+  int64_t capacity;
+  int O, A, stride, host_w;
+  float* rows;      // [capacity x stride]
+  float* cold;      // [capacity x 4]
+  int64_t top, size;
+  float* staging;   // device staging [staging_cap x host_w]
+  int64_t staging_cap, pending;
+  cudaEvent_t staged;
+  bool staged_valid;
+};
+
+// one warp per staged transition: staging row -> hot row at (top+i) % capacity, cold row
+__global__ void __launch_bounds__(256) rb_scatter_kernel(const float* __restrict__ staging, int64_t n, float* rows,
+                                                          float* cold, int64_t top, int64_t capacity, int O, int A,
+                                                          int stride, int host_w) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const float* src = staging + i * host_w;
+  const int64_t slot = (top + i) % capacity;
+  float* dst = rows + slot * stride;
+  const int hot = 2 * O + A + 2;
+  for (int k = lane; k < stride; k += 32) dst[k] = k < hot ? src[k] : 0.f;
+  if (lane < 4) cold[slot * 4 + lane] = lane < 3 ? src[hot + lane] : 0.f;
+}
+
+// one warp per sampled row, 128-bit loads/stores (stride is a multiple of 4 floats)
+__global__ void __launch_bounds__(256) rb_gather_kernel(const float* __restrict__ rows, const float* __restrict__ cold,
+                                                         const int32_t* __restrict__ idx, int B, int stride,
+                                                         float* out_hot, float* out_cold, int64_t size, uint64_t seed,
+                                                         uint64_t counter, int32_t* idx_out) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  int64_t r;
+  if (idx) r = idx[b];
+  else {
+    r = philox_index(seed, (uint32_t)counter, (uint32_t)b, (uint32_t)(counter >> 32) + 0x51u, (int)size);
+    if (idx_out && lane == 0) idx_out[b] = (int32_t)r;
+  }
+  const float4* src = reinterpret_cast<const float4*>(rows + r * stride);
+  float4* dst = reinterpret_cast<float4*>(out_hot + (size_t)b * stride);
+  for (int k = lane; k < (stride >> 2); k += 32) dst[k] = __ldg(src + k);
+  if (out_cold && lane == 0)
+    reinterpret_cast<float4*>(out_cold)[b] = __ldg(reinterpret_cast<const float4*>(cold) + r);
+}
+
+extern "C" int ilsw_rb_create(ilsw_rb** out, int64_t capacity, int obs_dim, int act_dim) {
+  if (!out || capacity <= 0 || obs_dim <= 0 || act_dim <= 0) return fail(ILSW_ERR_ARG, "rb_create: bad arguments");
+  if (capacity > 0x7fffffffLL) return fail(ILSW_ERR_ARG, "rb_create: capacity must fit int32 indices");
+  ilsw_rb* rb = new ilsw_rb();
+  memset(rb, 0, sizeof(*rb));
+  rb->capacity = capacity; rb->O = obs_dim; rb->A = act_dim;
+  rb->stride = round_up(2 * obs_dim + act_dim + 2, 4);
+  rb->host_w = 2 * obs_dim + act_dim + 5;
+  cudaError_t e = cudaMalloc(&rb->rows, (size_t)capacity * rb->stride * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&rb->cold, (size_t)capacity * 4 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(rb->cold, 0, (size_t)capacity * 4 * sizeof(float));
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rb->staged, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    int code = fail(ILSW_ERR_CUDA, "rb_create: %s (capacity %lld x %d floats)", cudaGetErrorString(e), (long long)capacity, rb->stride);
+    if (rb->rows) cudaFree(rb->rows);
+    if (rb->cold) cudaFree(rb->cold);
+    delete rb;
+    return code;
+  }
+  *out = rb;
+  return ILSW_OK;
+}
+extern "C" int ilsw_rb_destroy(ilsw_rb* rb) {
+  if (!rb) return ILSW_OK;
+  cudaFree(rb->rows); cudaFree(rb->cold);
+  if (rb->staging) cudaFree(rb->staging);
+  cudaEventDestroy(rb->staged);
+  delete rb;
+  return ILSW_OK;
+}
+extern "C" int ilsw_rb_host_row_floats(const ilsw_rb* rb) { return rb ? rb->host_w : ILSW_ERR_ARG; }
+extern "C" int ilsw_rb_row_stride(const ilsw_rb* rb) { return rb ? rb->stride : ILSW_ERR_ARG; }
+extern "C" int64_t ilsw_rb_capacity(const ilsw_rb* rb) { return rb ? rb->capacity : ILSW_ERR_ARG; }
+extern "C" int64_t ilsw_rb_size(const ilsw_rb* rb) { return rb ? rb->size + 0 : ILSW_ERR_ARG; }
+extern "C" int64_t ilsw_rb_top(const ilsw_rb* rb) { return rb ? rb->top : ILSW_ERR_ARG; }
+extern "C" float* ilsw_rb_rows_ptr(ilsw_rb* rb) { return rb ? rb->rows : nullptr; }
+extern "C" int ilsw_rb_clear(ilsw_rb* rb) {
+  if (!rb) return fail(ILSW_ERR_ARG, "rb_clear: null");
+  rb->top = rb->size = rb->pending = 0;
+  return ILSW_OK;
+}
+
+extern "C" int ilsw_rb_append(ilsw_rb* rb, const float* host_rows, int64_t n, void* copy_stream) {
+  if (!rb || (!host_rows && n > 0) || n < 0) return fail(ILSW_ERR_ARG, "rb_append: bad arguments");
+  if (n == 0) return ILSW_OK;
+  if (n > rb->capacity) return fail(ILSW_ERR_ARG, "rb_append: burst larger than the ring");
+  cudaStream_t cs = (cudaStream_t)copy_stream;
+  if (rb->pending == 0 && rb->staged_valid) CU(cudaStreamWaitEvent(cs, rb->staged, 0));  // staging reuse after the scatter
+  if (rb->pending + n > rb->staging_cap) {
+    // grow staging (rare; flushes what is pending first so no data is lost)
+    if (rb->pending > 0) {
+      int rc = ilsw_rb_commit(rb, copy_stream);
+      if (rc) return rc;
+      CU(cudaStreamSynchronize(cs));
+    }
+    int64_t cap = rb->staging_cap ? rb->staging_cap : 1024;
+    while (cap < n) cap *= 2;
+    if (cap != rb->staging_cap) {
+      if (rb->staging) { CU(cudaDeviceSynchronize()); CU(cudaFree(rb->staging)); }
+      CU(cudaMalloc(&rb->staging, (size_t)cap * rb->host_w * sizeof(float)));
+      rb->staging_cap = cap;
+    }
+  }
+  CU(cudaMemcpyAsync(rb->staging + rb->pending * rb->host_w, host_rows, (size_t)n * rb->host_w * sizeof(float),
+                     cudaMemcpyHostToDevice, cs));
+  CU(cudaEventRecord(rb->staged, cs));
+  rb->staged_valid = true;
+  rb->pending += n;
+  return ILSW_OK;
+}
+
+extern "C" int ilsw_rb_commit(ilsw_rb* rb, void* stream) {
+  if (!rb) return fail(ILSW_ERR_ARG, "rb_commit: null");
+  if (rb->pending == 0) return ILSW_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rb->staged_valid) CU(cudaStreamWaitEvent(st, rb->staged, 0));
+  const int64_t n = rb->pending;
+  const int wpb = 8;
+  rb_scatter_kernel<<<(unsigned)((n + wpb - 1) / wpb), 256, 0, st>>>(rb->staging, n, rb->rows, rb->cold, rb->top,
+                                                                     rb->capacity, rb->O, rb->A, rb->stride, rb->host_w);
+  CU(cudaGetLastError());
+  // the staging area may be overwritten by the next append on the copy stream only after this
+  // scatter has run: make later copies wait on it
+  CU(cudaEventRecord(rb->staged, st));
+  rb->top = (rb->top + n) % rb->capacity;
+  rb->size = rb->size + n > rb->capacity ? rb->capacity : rb->size + n;
+  rb->pending = 0;
+  return ILSW_OK;
+}
+
+extern "C" int ilsw_rb_load_device(ilsw_rb* rb, const float* dev_hot_rows, int64_t n, void* stream) {
+  if (!rb || !dev_hot_rows || n < 0 || n > rb->capacity) return fail(ILSW_ERR_ARG, "rb_load_device: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ilsw_rb_commit(rb, stream);
+  if (rc) return rc;
+  const size_t rowb = (size_t)rb->stride * sizeof(float);
+  int64_t first = n < rb->capacity - rb->top ? n : rb->capacity - rb->top;
+  CU(cudaMemcpyAsync(rb->rows + rb->top * rb->stride, dev_hot_rows, (size_t)first * rowb, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemsetAsync(rb->cold + rb->top * 4, 0, (size_t)first * 16, st));
+  if (n > first) {
+    CU(cudaMemcpyAsync(rb->rows, dev_hot_rows + first * rb->stride, (size_t)(n - first) * rowb, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemsetAsync(rb->cold, 0, (size_t)(n - first) * 16, st));
+  }
+  rb->top = (rb->top + n) % rb->capacity;
+  rb->size = rb->size + n > rb->capacity ? rb->capacity : rb->size + n;
+  return ILSW_OK;
+}
+
+extern "C" int ilsw_rb_gather(ilsw_rb* rb, const int32_t* idx_dev, int B, float* out_hot, float* out_cold, void* stream) {
+  if (!rb || !idx_dev || !out_hot || B <= 0) return fail(ILSW_ERR_ARG, "rb_gather: bad arguments");
+  int rc = ilsw_rb_commit(rb, stream);
+  if (rc) return rc;
+  if (rb->size == 0) return fail(ILSW_ERR_STATE, "rb_gather: empty ring");
+  rb_gather_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(rb->rows, rb->cold, idx_dev, B, rb->stride, out_hot,
+                                                                   out_cold, rb->size, 0, 0, nullptr);
+  CU(cudaGetLastError());
+  return ILSW_OK;
+}
+
+extern "C" int ilsw_rb_sample(ilsw_rb* rb, int B, uint64_t seed, uint64_t counter, int32_t* idx_out_dev, float* out_hot,
+                              void* stream) {
+  if (!rb || !out_hot || B <= 0) return fail(ILSW_ERR_ARG, "rb_sample: bad arguments");
+  int rc = ilsw_rb_commit(rb, stream);
+  if (rc) return rc;
+  if (rb->size == 0) return fail(ILSW_ERR_STATE, "rb_sample: empty ring");
+  rb_gather_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(rb->rows, rb->cold, nullptr, B, rb->stride, out_hot,
+                                                                   nullptr, rb->size, seed, counter, idx_out_dev);
+  CU(cudaGetLastError());
+  return ILSW_OK;
+}
+
+// ==========================================================================================
+// Trainer
+// ==========================================================================================
+struct ilsw_trainer {
+  TrainerSpec spec;
+  Program host_prog;      // device pointers inside
+  Program* dev_prog;
+  char* scratch;
+  size_t scratch_bytes;
+  BarrierState* bar;
+  int grid;
+  int t[kMaxNets];
+  int n_total;
+  int last_steps;
+  int64_t launches;
+  // replicas
+  char* ipc_buf;          // [flags 256B][recv 2*8*n floats]
+  size_t ipc_bytes;
+  Replica rep;
+  unsigned seq;
+  void* peer_bases[8];
+};
+
+static int trainer_build(ilsw_trainer* tr) {
+  std::string why;
+  int rc = validate_spec(tr->spec, &why);
+  if (rc) return fail(rc, "trainer spec invalid: %s", why.c_str());
+  Bump measure;
+  Program* tmp = new Program();
+  rc = assemble(*tmp, tr->spec, measure);
+  delete tmp;
+  if (rc) return fail(rc, "program assembly failed (too many phases/ops?)");
+  if (tr->scratch) { CU(cudaDeviceSynchronize()); CU(cudaFree(tr->scratch)); tr->scratch = nullptr; }
+  tr->scratch_bytes = measure.off + 256;
+  CU(cudaMalloc(&tr->scratch, tr->scratch_bytes));
+  CU(cudaMemset(tr->scratch, 0, tr->scratch_bytes));
+  Bump mem;
+  mem.base = tr->scratch;
+  rc = assemble(tr->host_prog, tr->spec, mem);
+  if (rc) return fail(rc, "program assembly failed");
+  if (!tr->dev_prog) CU(cudaMalloc(&tr->dev_prog, sizeof(Program)));
+  CU(cudaMemcpy(tr->dev_prog, &tr->host_prog, sizeof(Program), cudaMemcpyHostToDevice));
+  DynState d;
+  memset(&d, 0, sizeof(d));
+  d.log_alpha = log(tr->spec.cfg.alpha > 0 ? tr->spec.cfg.alpha : 1.0);
+  d.alpha = (float)exp(d.log_alpha);
+  CU(cudaMemcpy(tr->host_prog.ctx.dyn, &d, sizeof(d), cudaMemcpyHostToDevice));
+  return ILSW_OK;
+}
+
+extern "C" int ilsw_trainer_create(ilsw_trainer** out, const ilsw_trainer_config* cfg, const ilsw_mlp* nets, int n_nets) {
+  if (!out || !cfg || !nets || n_nets <= 0 || n_nets > 6) return fail(ILSW_ERR_ARG, "trainer_create: bad arguments");
+  int dev = 0, coop = 0, sms = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (!coop) return fail(ILSW_ERR_UNSUPPORTED, "device lacks cooperative launch");
+  ilsw_trainer* tr = new ilsw_trainer();
+  memset(tr, 0, sizeof(*tr));
+  tr->spec.cfg = *cfg;
+  for (int i = 0; i < n_nets; ++i) tr->spec.nets[i] = nets[i];
+  tr->spec.n_nets = n_nets;
+  int rc = trainer_build(tr);
+  if (rc) { ilsw_trainer_destroy(tr); return rc; }
+  cudaError_t e = cudaMalloc(&tr->bar, sizeof(BarrierState));
+  if (e == cudaSuccess) e = cudaMemset(tr->bar, 0, sizeof(BarrierState));
+  if (e != cudaSuccess) { ilsw_trainer_destroy(tr); return fail(ILSW_ERR_CUDA, "barrier alloc: %s", cudaGetErrorString(e)); }
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ilsw_engine_kernel, kThreads, 0);
+  if (e != cudaSuccess || per_sm < 1) { ilsw_trainer_destroy(tr); return fail(ILSW_ERR_CUDA, "engine kernel cannot be resident (%s)", cudaGetErrorString(e)); }
+  tr->grid = sms;  // persistent: one CTA per SM
+  const char* g = getenv("ILSW_GRID");
+  if (g && atoi(g) > 0 && atoi(g) <= sms * per_sm) tr->grid = atoi(g);
+  tr->rep.world = 1;
+  *out = tr;
+  return ILSW_OK;
+}
+
+extern "C" int ilsw_trainer_attach_disc(ilsw_trainer* tr, const ilsw_disc_config* cfg, const ilsw_mlp* disc) {
+  if (!tr || !cfg || !disc) return fail(ILSW_ERR_ARG, "attach_disc: bad arguments");
+  tr->spec.has_disc = 1;
+  tr->spec.dcfg = *cfg;
+  tr->spec.disc = *disc;
+  return trainer_build(tr);
+}
+
+extern "C" int ilsw_trainer_destroy(ilsw_trainer* tr) {
+  if (!tr) return ILSW_OK;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < 8; ++r)
+    if (tr->peer_bases[r] && r != tr->rep.rank) cudaIpcCloseMemHandle(tr->peer_bases[r]);
+  if (tr->ipc_buf) cudaFree(tr->ipc_buf);
+  if (tr->scratch) cudaFree(tr->scratch);
+  if (tr->dev_prog) cudaFree(tr->dev_prog);
+  if (tr->bar) cudaFree(tr->bar);
+  delete tr;
+  return ILSW_OK;
+}
+
+extern "C" int ilsw_train(ilsw_trainer* tr, ilsw_rb* policy_rb, ilsw_rb* expert_rb, int n_steps, const ilsw_inject* inject,
+                          const ilsw_batch* batch, uint64_t seed, int stats_step, void* stream) {
+  if (!tr || n_steps <= 0) return fail(ILSW_ERR_ARG, "train: bad arguments");
+  const ilsw_trainer_config& cfg = tr->spec.cfg;
+  if (n_steps > cfg.max_steps_per_call) return fail(ILSW_ERR_ARG, "train: n_steps %d > max_steps_per_call %d", n_steps, cfg.max_steps_per_call);
+  if (batch && n_steps != 1) return fail(ILSW_ERR_ARG, "train: a caller-provided batch implies n_steps == 1");
+  if (batch && tr->spec.has_disc) return fail(ILSW_ERR_UNSUPPORTED, "train: direct batches are not supported with a discriminator");
+  if (!batch && !policy_rb) return fail(ILSW_ERR_ARG, "train: no replay ring and no batch");
+  if (tr->spec.has_disc && !expert_rb) return fail(ILSW_ERR_ARG, "train: AdvIRL engine needs the expert ring");
+  cudaStream_t st = (cudaStream_t)stream;
+  RunArgs a;
+  memset(&a, 0, sizeof(a));
+  if (policy_rb) {
+    if (policy_rb->O != cfg.obs_dim || policy_rb->A != cfg.act_dim) return fail(ILSW_ERR_ARG, "train: ring dims != trainer dims");
+    int rc = ilsw_rb_commit(policy_rb, stream);
+    if (rc) return rc;
+    if (!batch && policy_rb->size <= 0) return fail(ILSW_ERR_STATE, "train: replay ring is empty");
+    a.ring_policy.rows = policy_rb->rows; a.ring_policy.stride = policy_rb->stride; a.ring_policy.size = (int)policy_rb->size;
+  }
+  if (expert_rb) {
+    if (expert_rb->O != cfg.obs_dim || expert_rb->A != cfg.act_dim) return fail(ILSW_ERR_ARG, "train: expert ring dims != trainer dims");
+    int rc = ilsw_rb_commit(expert_rb, stream);
+    if (rc) return rc;
+    if (tr->spec.has_disc && expert_rb->size <= 0) return fail(ILSW_ERR_STATE, "train: expert ring is empty");
+    a.ring_expert.rows = expert_rb->rows; a.ring_expert.stride = expert_rb->stride; a.ring_expert.size = (int)expert_rb->size;
+  }
+  a.n_steps = n_steps; a.step0 = tr->n_total; a.stats_step = stats_step; a.seed = seed;
+  for (int i = 0; i < kMaxNets; ++i) a.t0[i] = tr->t[i];
+  if (inject) {
+    if (!inject->idx || !inject->eps_next) return fail(ILSW_ERR_ARG, "train: inject needs idx and eps_next");
+    if (cfg.algo == ILSW_ALGO_SAC_ALPHA && !inject->eps_cur) return fail(ILSW_ERR_ARG, "train: inject needs eps_cur for SAC");
+    if (tr->spec.has_disc && (!inject->idx_expert || !inject->idx_policy_d || (tr->spec.dcfg.use_grad_pen && !inject->gp_eps)))
+      return fail(ILSW_ERR_ARG, "train: inject needs idx_expert/idx_policy_d/gp_eps for the discriminator step");
+    a.has_inject = 1;
+    a.inj.idx = inject->idx; a.inj.eps_next = inject->eps_next; a.inj.eps_cur = inject->eps_cur;
+    a.inj.idx_expert = inject->idx_expert; a.inj.idx_policy_d = inject->idx_policy_d; a.inj.gp_eps = inject->gp_eps;
+  }
+  if (batch) {
+    if (!batch->obs || !batch->act || !batch->rew || !batch->term || !batch->next_obs) return fail(ILSW_ERR_ARG, "train: incomplete batch");
+    a.has_direct = 1;
+    a.direct.obs = batch->obs; a.direct.act = batch->act; a.direct.rew = batch->rew; a.direct.term = batch->term;
+    a.direct.next_obs = batch->next_obs;
+    if (!inject) a.has_inject = 0;
+  }
+  a.world = tr->rep.world; a.rank = tr->rep.rank; a.loss_log_offset = 0;
+  Replica rp = tr->rep;
+  rp.seq0 = tr->seq;
+  const Program* dp = tr->dev_prog;
+  BarrierState* bar = tr->bar;
+  void* args[] = {(void*)&dp, (void*)&a, (void*)&bar, (void*)&rp};
+  CU(cudaLaunchCooperativeKernel((void*)ilsw_engine_kernel, dim3(tr->grid), dim3(kThreads), args, 0, st));
+  tr->launches += 1;
+  // host mirrors of the on-device counters
+  tr->seq += (unsigned)(adam_t(a, tr->host_prog.ctx.hp, SLOT_POLICY, n_steps - 1) - a.t0[SLOT_POLICY]);
+  for (int slot = 0; slot < kMaxNets; ++slot) tr->t[slot] = adam_t(a, tr->host_prog.ctx.hp, slot, n_steps - 1);
+  tr->n_total += n_steps;
+  tr->last_steps = n_steps;
+  return ILSW_OK;
+}
+
+static int check_abort(ilsw_trainer* tr, cudaStream_t st) {
+  DynState d;
+  CU(cudaMemcpyAsync(&d, tr->host_prog.ctx.dyn, sizeof(d), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (d.abort_flag) return fail(ILSW_ERR_ABORTED, "engine launch aborted (barrier/replica wait timed out)");
+  return ILSW_OK;
+}
+
+extern "C" int ilsw_read_losses(ilsw_trainer* tr, float* host_out, int n_steps, void* stream) {
+  if (!tr || !host_out || n_steps <= 0 || n_steps > tr->spec.cfg.max_steps_per_call) return fail(ILSW_ERR_ARG, "read_losses: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemcpyAsync(host_out, tr->host_prog.ctx.loss_log, (size_t)n_steps * kLossSlots * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return check_abort(tr, st);
+}
+extern "C" int ilsw_read_losses_async(ilsw_trainer* tr, float* pinned_out, int n_steps, void* stream) {
+  if (!tr || !pinned_out || n_steps <= 0 || n_steps > tr->spec.cfg.max_steps_per_call) return fail(ILSW_ERR_ARG, "read_losses_async: bad arguments");
+  CU(cudaMemcpyAsync(pinned_out, tr->host_prog.ctx.loss_log, (size_t)n_steps * kLossSlots * sizeof(float), cudaMemcpyDeviceToHost,
+                     (cudaStream_t)stream));
+  return ILSW_OK;
+}
+extern "C" int ilsw_stats_floats(const ilsw_trainer* tr) { return tr ? tr->host_prog.ctx.stats_floats : ILSW_ERR_ARG; }
+extern "C" int ilsw_read_stats(ilsw_trainer* tr, float* host_out, int n_floats, void* stream) {
+  if (!tr || !host_out || n_floats <= 0 || n_floats > tr->host_prog.ctx.stats_floats) return fail(ILSW_ERR_ARG, "read_stats: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemcpyAsync(host_out, tr->host_prog.ctx.stats, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return check_abort(tr, st);
+}
+
+extern "C" int ilsw_get_state(ilsw_trainer* tr, ilsw_state* out, void* stream) {
+  if (!tr || !out) return fail(ILSW_ERR_ARG, "get_state: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  DynState d;
+  CU(cudaMemcpyAsync(&d, tr->host_prog.ctx.dyn, sizeof(d), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  memset(out, 0, sizeof(*out));
+  out->log_alpha = d.log_alpha; out->alpha_exp_avg = d.alpha_m; out->alpha_exp_avg_sq = d.alpha_v; out->alpha_step = d.alpha_t;
+  for (int i = 0; i < 8; ++i) out->adam_step[i] = tr->t[i];
+  out->n_train_steps_total = tr->n_total;
+  if (d.abort_flag) return fail(ILSW_ERR_ABORTED, "engine launch aborted");
+  return ILSW_OK;
+}
+extern "C" int ilsw_set_state(ilsw_trainer* tr, const ilsw_state* in, void* stream) {
+  if (!tr || !in) return fail(ILSW_ERR_ARG, "set_state: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  DynState d;
+  memset(&d, 0, sizeof(d));
+  d.log_alpha = in->log_alpha; d.alpha_m = in->alpha_exp_avg; d.alpha_v = in->alpha_exp_avg_sq; d.alpha_t = in->alpha_step;
+  d.alpha = (float)exp(d.log_alpha);
+  CU(cudaMemcpyAsync(tr->host_prog.ctx.dyn, &d, sizeof(d), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  for (int i = 0; i < 8; ++i) tr->t[i] = in->adam_step[i];
+  tr->n_total = in->n_train_steps_total;
+  return ILSW_OK;
+}
+
+extern "C" int ilsw_describe_program(const ilsw_trainer* tr, char* buf, int buf_len) {
+  if (!tr || !buf || buf_len <= 0) return fail(ILSW_ERR_ARG, "describe_program: bad arguments");
+  std::string s = describe_program(tr->host_prog);
+  snprintf(buf, buf_len, "%s", s.c_str());
+  return (int)s.size();
+}
+extern "C" int ilsw_num_phases(const ilsw_trainer* tr) { return tr ? tr->host_prog.n_phases : ILSW_ERR_ARG; }
+extern "C" int64_t ilsw_kernel_launches(const ilsw_trainer* tr) { return tr ? tr->launches : ILSW_ERR_ARG; }
+
+extern "C" int ilsw_policy_act(ilsw_trainer* tr, const float* obs_dev, int n, int deterministic, uint64_t seed, float* act_dev,
+                               void* stream) {
+  if (!tr || !obs_dev || !act_dev || n <= 0 || n > 4096) return fail(ILSW_ERR_ARG, "policy_act: bad arguments");
+  const MlpPtrs& P = tr->host_prog.ctx.policy;
+  const Hyper& hp = tr->host_prog.ctx.hp;
+  size_t sh = (size_t)(P.in_dim + 2 * P.hid) * sizeof(float);
+  ilsw_policy_act_kernel<<<n, 256, sh, (cudaStream_t)stream>>>(P, hp.algo, hp.max_act, hp.policy_noise, hp.noise_clip, obs_dev, n,
+                                                               deterministic, seed, act_dev);
+  CU(cudaGetLastError());
+  return ILSW_OK;
+}
+
+// ==========================================================================================
+// Replicas: CUDA-IPC mapped receive buffers + flags, exchanged inside the engine kernel
+// ==========================================================================================
+static const size_t kFlagBytes = 256;
+
+extern "C" int ilsw_replica_export(ilsw_trainer* tr, void* handle_out) {
+  if (!tr || !handle_out) return fail(ILSW_ERR_ARG, "replica_export: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= ILSW_IPC_HANDLE_BYTES, "handle size");
+  const int n = tr->host_prog.ctx.policy.n_params;
+  if (!tr->ipc_buf) {
+    tr->ipc_bytes = kFlagBytes + (size_t)2 * 8 * n * sizeof(float);
+    CU(cudaMalloc(&tr->ipc_buf, tr->ipc_bytes));
+    CU(cudaMemset(tr->ipc_buf, 0, tr->ipc_bytes));
+    CU(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, tr->ipc_buf));
+  memset(handle_out, 0, ILSW_IPC_HANDLE_BYTES);
+  memcpy(handle_out, &h, sizeof(h));
+  return ILSW_OK;
+}
+
+extern "C" int ilsw_replica_connect(ilsw_trainer* tr, int rank, int world, const void* all_handles) {
+  if (!tr || !all_handles || world < 1 || world > 8 || rank < 0 || rank >= world) return fail(ILSW_ERR_ARG, "replica_connect: bad arguments");
+  if (!tr->ipc_buf) return fail(ILSW_ERR_STATE, "replica_connect: call ilsw_replica_export first");
+  const int n = tr->host_prog.ctx.policy.n_params;
+  Replica& rp = tr->rep;
+  memset(&rp, 0, sizeof(rp));
+  rp.world = world; rp.rank = rank; rp.n = n;
+  rp.grad = tr->host_prog.ctx.policy.g;
+  for (int r = 0; r < world; ++r) {
+    void* base = nullptr;
+    if (r == rank) base = tr->ipc_buf;
+    else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char*)all_handles + (size_t)r * ILSW_IPC_HANDLE_BYTES, sizeof(h));
+      CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    tr->peer_bases[r] = base;
+    rp.flags_peer[r] = reinterpret_cast<unsigned*>(base);
+    rp.recv_peer[r] = reinterpret_cast<float*>((char*)base + kFlagBytes);
+  }
+  rp.flags_local = rp.flags_peer[rank];
+  rp.recv_local = rp.recv_peer[rank];
+  tr->seq = 0;
+  return ILSW_OK;
+}

@@ -170,8 +170,7 @@ ILSW_HD AdamCoef adam_coef(const AdamOp& o, int t, int world) {
   return c;
 }
 
-ILSW_HD void adam_elem(const AdamOp& o, const AdamCoef& c, int i) {
-  float g = ldg(o.g + i) * c.gscale;
+ILSW_HD void adam_elem_g(const AdamOp& o, const AdamCoef& c, int i, float g) {
   float m = o.m[i], v = o.v[i], p = o.p[i];
   // exp_avg.lerp_(grad, 1-beta1)
   m = (c.w1 < 0.5f) ? m + c.w1 * (g - m) : g - (g - m) * c.one_m_w1;
@@ -184,6 +183,7 @@ ILSW_HD void adam_elem(const AdamOp& o, const AdamCoef& c, int i) {
   o.p[i] = p;
   if (o.target) o.target[i] = o.target[i] * c.one_m_tau + p * c.tau;
 }
+ILSW_HD void adam_elem(const AdamOp& o, const AdamCoef& c, int i) { adam_elem_g(o, c, i, ldg(o.g + i) * c.gscale); }
 
 ILSW_HD void polyak_elem(const PolyakOp& o, int i) {
   float om = (float)(1.0 - (double)o.tau);

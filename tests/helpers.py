@@ -241,3 +241,49 @@ def assert_params_close(got, ref, steps, lr=3e-4, msg=""):
     bad = int((diff > 1e-5).sum())
     assert bad <= max(1, int(1e-4 * diff.size)), (msg, bad, diff.size, float(diff.max()))
     assert float(diff.max()) <= 2.0 * lr * steps + 1e-6, (msg, float(diff.max()))
+
+
+# ---------------------------------------------------------------------------------------------
+# device runner (the product path, through the C ABI)
+# ---------------------------------------------------------------------------------------------
+class DeviceRun:
+    """Runs one parity case on the GPU through ilswiss_b200.engine (C ABI) with injected randomness."""
+
+    def __init__(self, case, max_steps=64):
+        from ilswiss_b200 import engine
+
+        self.case = case
+        self.engine_mod = engine
+        arenas = initial_arenas(case)
+        self.nets = {}
+        order = net_order(case)
+        for n in order:
+            i_d, h_d, o_d, ls = mlp_dims(case, n)
+            self.nets[n] = engine.NetArena(i_d, h_d, o_d, ls, trainable=not n.startswith("target"), init=arenas[n])
+        dcfg = dnet = None
+        if case["algo"] == "adv_irl":
+            i_d, h_d, o_d, ls = mlp_dims(case, "disc")
+            dnet = engine.NetArena(i_d, h_d, o_d, ls, init=arenas["disc"])
+            self.nets["disc"] = dnet
+            dcfg = disc_config(case)
+        self.eng = engine.StepEngine(trainer_config(case, max_steps), [self.nets[n] for n in order], dcfg, dnet)
+        data, edata = case_data(case)
+        O, A = case["obs_dim"], case["act_dim"]
+        self.ring = engine.ReplayRing(case["n_fill"], O, A)
+        self.ring.load_device(torch.from_numpy(layout.pack_hot_rows(**data)).cuda())
+        self.ering = None
+        if edata is not None:
+            self.ering = engine.ReplayRing(case["n_fill"], O, A)
+            self.ering.load_device(torch.from_numpy(layout.pack_hot_rows(**edata)).cuda())
+
+    def train(self, n_steps, inj, stats_step=-1, t_offset=0, seed=0):
+        dev = {k: torch.from_numpy(np.ascontiguousarray(v[t_offset:t_offset + n_steps])).cuda() for k, v in inj.items()}
+        self.eng.train(self.ring, n_steps, expert_ring=self.ering, inject=dev, stats_step=stats_step, seed=seed)
+        return self.eng.losses(n_steps)
+
+    def train_philox(self, n_steps, seed=1, stats_step=-1):
+        self.eng.train(self.ring, n_steps, expert_ring=self.ering, seed=seed, stats_step=stats_step)
+        return self.eng.losses(n_steps)
+
+    def arena(self, name):
+        return self.nets[name].p.detach().cpu().numpy()
