@@ -76,6 +76,7 @@ PROTOTYPES = {
     "ilsw_rb_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ilsw_rb_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ilsw_rb_clear": (C.c_int, [C.c_void_p]),
+    "ilsw_rb_set_cursor": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
     "ilsw_mlp_num_params": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ilsw_trainer_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(TrainerConfig), C.POINTER(Mlp), C.c_int]),
     "ilsw_trainer_attach_disc": (C.c_int, [C.c_void_p, C.POINTER(DiscConfig), C.POINTER(Mlp)]),
@@ -90,6 +91,7 @@ PROTOTYPES = {
     "ilsw_set_state": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p]),
     "ilsw_describe_program": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "ilsw_num_phases": (C.c_int, [C.c_void_p]),
+    "ilsw_read_phase_ns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ilsw_kernel_launches": (C.c_int64, [C.c_void_p]),
     "ilsw_policy_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "ilsw_replica_export": (C.c_int, [C.c_void_p, C.c_void_p]),

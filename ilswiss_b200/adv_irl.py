@@ -1,0 +1,162 @@
+"""AdvIRL (GAIL / AIRL / FAIRL) on the fused engine.
+
+    AdvIRLEngine            <->  the learner half of rlkit/torch/algorithms/adv_irl/adv_irl.py:
+                                 _do_training (:126-131), _do_reward_training (:133-236),
+                                 _do_policy_training (:238-314)
+    DeviceAdvIRLMixin       mixin for the reference's AdvIRL class
+    DeviceTorchRLAlgorithmMixin   same for TorchRLAlgorithm (torch_rl_algorithm.py:16-34)
+
+One engine step = one loop iteration with ONE discriminator update (BCE + gradient penalty,
+Adam) followed by ONE policy update (discriminator reward relabel + SAC-alpha step), which is what
+every shipped exp_spec uses (num_disc_updates_per_loop_iter = num_policy_updates_per_loop_iter = 1).
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.optim as optim
+
+from . import _abi
+from .trainers import SoftActorCritic, adopt_module, module_dims
+
+
+class AdvIRLEngine:
+    def __init__(self, mode, discriminator, policy_trainer, expert_replay_buffer, replay_buffer,
+                 state_only=False, disc_optim_batch_size=1024, policy_optim_batch_size=1024,
+                 policy_optim_batch_size_from_expert=0, num_update_loops_per_train_call=1,
+                 num_disc_updates_per_loop_iter=100, num_policy_updates_per_loop_iter=100,
+                 disc_lr=1e-3, disc_momentum=0.0, disc_optimizer_class=optim.Adam, use_grad_pen=True,
+                 grad_pen_weight=10, rew_clip_min=None, rew_clip_max=None, wrap_absorbing=False, **kwargs):
+        assert mode in ("airl", "gail", "fairl", "gail2"), "Invalid adversarial irl algorithm!"   # adv_irl.py:56-61
+        if not isinstance(policy_trainer, SoftActorCritic):
+            raise NotImplementedError("the fused AdvIRL engine drives ilswiss_b200.SoftActorCritic (as adv_irl_exp_script.py does)")
+        unsupported = []
+        if state_only:
+            unsupported.append("state_only")
+        if wrap_absorbing:
+            unsupported.append("wrap_absorbing")
+        if policy_optim_batch_size_from_expert:
+            unsupported.append("policy_optim_batch_size_from_expert>0")
+        if num_disc_updates_per_loop_iter != 1 or num_policy_updates_per_loop_iter != 1:
+            unsupported.append("num_{disc,policy}_updates_per_loop_iter != 1")
+        if disc_optim_batch_size != policy_optim_batch_size or disc_optim_batch_size != policy_trainer._cfg.batch:
+            unsupported.append("disc/policy batch sizes must equal the trainer batch")
+        if disc_optimizer_class is not optim.Adam:
+            unsupported.append("non-Adam disc optimizer")
+        if unsupported:
+            raise NotImplementedError("fused AdvIRL engine (SURVEY.md 8f rank 4): " + ", ".join(unsupported))
+        in_dim, H, out_dim, ls = module_dims(discriminator)
+        if out_dim != 1 or ls or getattr(discriminator, "clamp_magnitude", None) is None:
+            raise NotImplementedError("expects MLPDisc(num_layer_blocks=2, hid_act='tanh', use_bn=False)")
+        self.mode, self.discriminator, self.policy_trainer = mode, discriminator, policy_trainer
+        self.expert_replay_buffer, self.replay_buffer = expert_replay_buffer, replay_buffer
+        self.use_grad_pen, self.grad_pen_weight = use_grad_pen, grad_pen_weight
+        self.num_update_loops_per_train_call = num_update_loops_per_train_call
+        self.disc_arena = adopt_module(discriminator)
+        self.disc_optimizer = optim.Adam(self.discriminator.parameters(), lr=disc_lr, betas=(disc_momentum, 0.999))
+        dc = _abi.DiscConfig()
+        dc.mode, dc.batch = _abi.DISC_MODES[mode], int(disc_optim_batch_size)
+        dc.disc_lr, dc.disc_momentum = disc_lr, disc_momentum
+        dc.use_grad_pen, dc.grad_pen_weight = int(bool(use_grad_pen)), float(grad_pen_weight)
+        dc.clamp_magnitude = float(discriminator.clamp_magnitude)
+        dc.rew_clip_min_on, dc.rew_clip_max_on = int(rew_clip_min is not None), int(rew_clip_max is not None)
+        dc.rew_clip_min, dc.rew_clip_max = float(rew_clip_min or 0.0), float(rew_clip_max or 0.0)
+        self._dc = dc
+        eng = policy_trainer.engine
+        d = self.disc_arena.desc()
+        import ctypes as C
+        from ._lib import check
+        check(eng.lib.ilsw_trainer_attach_disc(eng.h, C.byref(dc), C.byref(d)), "attach_disc")
+        eng.disc = self.disc_arena
+        self.disc_eval_statistics = None
+
+    def do_training(self, n_loops=None, inject=None):
+        """AdvIRL._do_training: n_loops iterations (default num_update_loops_per_train_call) in one launch."""
+        tr = self.policy_trainer
+        n = self.num_update_loops_per_train_call if n_loops is None else n_loops
+        self.replay_buffer.flush()
+        self.expert_replay_buffer.flush()
+        done = 0
+        while done < n:
+            k = min(n - done, tr._cfg.max_steps_per_call)
+            want = (self.disc_eval_statistics is None or tr.eval_statistics is None) and done == 0
+            tr._launch += 1
+            sub = None if inject is None else {kk: v[done:done + k].contiguous() for kk, v in inject.items()}
+            tr.engine.train(self.replay_buffer.ring, k, expert_ring=self.expert_replay_buffer.ring, inject=sub,
+                            seed=tr._seed + tr._launch, stats_step=0 if want else -1)
+            L = tr.engine.losses(k) if (want or done + k >= n) else None
+            if want:
+                if tr.eval_statistics is None:
+                    tr.eval_statistics = tr._build_stats(L[0], tr.engine.stats())
+                if self.disc_eval_statistics is None:
+                    st = OrderedDict()
+                    st["Disc CE Loss"] = float(L[0, _abi.L_DISC_CE])
+                    st["Disc Acc"] = float(L[0, _abi.L_DISC_ACC])
+                    if self.use_grad_pen:
+                        st["Grad Pen"] = float(L[0, _abi.L_GRAD_PEN])
+                        st["Grad Pen W"] = np.mean(self.grad_pen_weight)
+                    self.disc_eval_statistics = st
+            if done + k >= n and self.disc_eval_statistics is not None:
+                # adv_irl.py:303-314 rewrites these after EVERY policy step: last write wins
+                self.disc_eval_statistics["Disc Rew Mean"] = float(L[-1, _abi.L_REW_MEAN])
+                self.disc_eval_statistics["Disc Rew Std"] = float(L[-1, _abi.L_REW_STD])
+                self.disc_eval_statistics["Disc Rew Max"] = float(L[-1, _abi.L_REW_MAX])
+                self.disc_eval_statistics["Disc Rew Min"] = float(L[-1, _abi.L_REW_MIN])
+            done += k
+
+    def end_epoch(self):
+        self.policy_trainer.end_epoch()
+        self.disc_eval_statistics = None
+
+    def get_disc_snapshot(self):
+        st = self.policy_trainer.engine.get_state()
+        self.policy_trainer._sync_optimizer(self.disc_optimizer, self.disc_arena, st.adam_step[4])
+        return dict(disc=self.discriminator, disc_optimizer=self.disc_optimizer)
+
+
+class DeviceTorchRLAlgorithmMixin:
+    """Put in front of rlkit's TorchRLAlgorithm: `class Alg(DeviceTorchRLAlgorithmMixin, TorchRLAlgorithm)`.
+    Requires replay_buffer=DeviceReplayBuffer(...) and an ilswiss_b200 trainer."""
+
+    def get_batch(self):
+        # torch_rl_algorithm.py:16-18 without the host round trip
+        return self.replay_buffer.random_batch_device(self.batch_size)
+
+    def _do_training(self, epoch):
+        # torch_rl_algorithm.py:28-34: num_train_steps_per_train_call steps in one launch
+        self.trainer.train_from_buffer(self.replay_buffer, self.num_train_steps_per_train_call)
+
+
+class DeviceAdvIRLMixin:
+    """Put in front of rlkit's AdvIRL: `class AdvIRL(DeviceAdvIRLMixin, RefAdvIRL)`."""
+
+    def _ilsw_engine(self):
+        eng = getattr(self, "_ilsw_eng", None)
+        if eng is None:
+            eng = AdvIRLEngine(
+                self.mode, self.discriminator, self.policy_trainer, self.expert_replay_buffer, self.replay_buffer,
+                state_only=self.state_only, disc_optim_batch_size=self.disc_optim_batch_size,
+                policy_optim_batch_size=self.policy_optim_batch_size,
+                policy_optim_batch_size_from_expert=self.policy_optim_batch_size_from_expert,
+                num_update_loops_per_train_call=self.num_update_loops_per_train_call,
+                num_disc_updates_per_loop_iter=self.num_disc_updates_per_loop_iter,
+                num_policy_updates_per_loop_iter=self.num_policy_updates_per_loop_iter,
+                disc_lr=self.disc_optimizer.param_groups[0]["lr"],
+                disc_momentum=self.disc_optimizer.param_groups[0]["betas"][0],
+                use_grad_pen=self.use_grad_pen, grad_pen_weight=self.grad_pen_weight,
+                rew_clip_min=self.rew_clip_min, rew_clip_max=self.rew_clip_max,
+                wrap_absorbing=getattr(self, "wrap_absorbing", False))
+            self.disc_optimizer = eng.disc_optimizer
+            self._ilsw_eng = eng
+        return eng
+
+    def get_batch(self, batch_size, from_expert, keys=None):
+        buf = self.expert_replay_buffer if from_expert else self.replay_buffer
+        b = buf.random_batch_device(batch_size)
+        return b if keys is None else {k: v for k, v in b.items() if k in keys}
+
+    def _do_training(self, epoch):
+        eng = self._ilsw_engine()
+        eng.disc_eval_statistics = self.disc_eval_statistics
+        eng.do_training()
+        self.disc_eval_statistics = eng.disc_eval_statistics

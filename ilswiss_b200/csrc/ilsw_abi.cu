@@ -145,6 +145,13 @@ extern "C" int ilsw_rb_clear(ilsw_rb* rb) {
   return ILSW_OK;
 }
 
+extern "C" int ilsw_rb_set_cursor(ilsw_rb* rb, int64_t top, int64_t size) {
+  if (!rb || top < 0 || top >= rb->capacity || size < 0 || size > rb->capacity) return fail(ILSW_ERR_ARG, "rb_set_cursor: bad arguments");
+  if (rb->pending) return fail(ILSW_ERR_STATE, "rb_set_cursor: pending appends");
+  rb->top = top; rb->size = size;
+  return ILSW_OK;
+}
+
 extern "C" int ilsw_rb_append(ilsw_rb* rb, const float* host_rows, int64_t n, void* copy_stream) {
   if (!rb || (!host_rows && n > 0) || n < 0) return fail(ILSW_ERR_ARG, "rb_append: bad arguments");
   if (n == 0) return ILSW_OK;
@@ -453,6 +460,13 @@ extern "C" int ilsw_describe_program(const ilsw_trainer* tr, char* buf, int buf_
   std::string s = describe_program(tr->host_prog);
   snprintf(buf, buf_len, "%s", s.c_str());
   return (int)s.size();
+}
+extern "C" int ilsw_read_phase_ns(ilsw_trainer* tr, unsigned long long* host_out, int n, void* stream) {
+  if (!tr || !host_out || n <= 0 || n > kMaxPhases + 1) return fail(ILSW_ERR_ARG, "read_phase_ns: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemcpyAsync(host_out, tr->host_prog.ctx.phase_ns, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return ILSW_OK;
 }
 extern "C" int ilsw_num_phases(const ilsw_trainer* tr) { return tr ? tr->host_prog.n_phases : ILSW_ERR_ARG; }
 extern "C" int64_t ilsw_kernel_launches(const ilsw_trainer* tr) { return tr ? tr->launches : ILSW_ERR_ARG; }

@@ -40,6 +40,12 @@ __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 constexpr long long kSpinLimit = 4000000000LL;  // ~2 s at 2 GHz: a hung peer/CTA aborts the launch
 
 // Sense-reversal grid barrier (all CTAs are co-resident: cooperative launch, 1 CTA / SM).
@@ -296,9 +302,11 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   for (int s = 0; s < a.n_steps; ++s) {
+    const bool stamp = (s == a.n_steps - 1) && blockIdx.x == 0 && threadIdx.x == 0;
+    if (stamp) c.phase_ns[0] = globaltimer_ns();
     for (int ph = 0; ph < prog->n_phases; ++ph) {
       const Phase& P = prog->phases[ph];
-      if (!phase_active(P, c.hp, a, s)) continue;
+      if (!phase_active(P, c.hp, a, s)) { if (stamp) c.phase_ns[ph + 1] = c.phase_ns[ph]; continue; }
       const bool exchange = P.collective && rp.world > 1;
       // exchange sequence number = number of policy updates so far (parity double-buffers the slots)
       const unsigned xseq = rp.seq0 + (unsigned)(adam_t(a, c.hp, SLOT_POLICY, s) - a.t0[SLOT_POLICY]);
@@ -329,6 +337,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
         }
       }
       if (!grid_barrier(bar, gridDim.x, gen, abort_flag)) return;
+      if (stamp) c.phase_ns[ph + 1] = globaltimer_ns();
     }
   }
 }

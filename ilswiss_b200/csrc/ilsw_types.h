@@ -165,6 +165,7 @@ struct Ctx {            // everything a row kernel needs
   float* loss_log;      // [max_steps x kLossSlots]
   float* stats;         // snapshot area (see ilsw_stats layout in include/ilswiss_b200.h)
   int stats_floats;
+  unsigned long long* phase_ns;  // [kMaxPhases+1] globaltimer stamps of the LAST step of a launch (profiling)
 };
 
 struct RingView {       // replay ring as seen by the gather row kernel

@@ -111,6 +111,9 @@ class ReplayRing:
         check(self.lib.ilsw_rb_clear(self.h), "rb_clear")
         self.pending = 0
 
+    def set_cursor(self, top, size):
+        check(self.lib.ilsw_rb_set_cursor(self.h, int(top), int(size)), "rb_set_cursor")
+
     def rows_view(self):
         """Zero-copy torch view of the whole ring (debug / snapshots)."""
         ptr = self.lib.ilsw_rb_rows_ptr(self.h)
@@ -223,6 +226,13 @@ class StepEngine:
         buf = C.create_string_buffer(1 << 15)
         check(self.lib.ilsw_describe_program(self.h, buf, len(buf)), "describe_program")
         return buf.value.decode()
+
+    def phase_times_us(self):
+        """Per-phase durations (us, barrier included) of the last step of the last launch."""
+        n = self.num_phases + 1
+        out = np.zeros(n, dtype=np.uint64)
+        check(self.lib.ilsw_read_phase_ns(self.h, out.ctypes.data_as(C.c_void_p), n, _stream_ptr()), "read_phase_ns")
+        return np.diff(out.astype(np.int64)) / 1000.0
 
     @property
     def num_phases(self):

@@ -1,0 +1,218 @@
+"""Device replay buffer with the reference's ReplayBuffer interface.
+
+Drop-in for rlkit.data_management.simple_replay_buffer.SimpleReplayBuffer /
+env_replay_buffer.EnvReplayBuffer (flat observations): same constructor arguments, same
+method names, argument meaning and return types -- but the transitions live in HBM
+(ilswiss_b200.engine.ReplayRing) and `random_batch` is one gather kernel.
+
+Inject it through the reference's own, supported constructor argument
+`BaseAlgorithm(replay_buffer=...)` (rlkit/core/base_algorithm.py:36,116-123).
+"""
+import numpy as np
+import torch
+
+from . import layout
+from .engine import ReplayRing
+
+ALL_KEYS = ("observations", "actions", "rewards", "terminals", "next_observations", "absorbing")
+
+
+class DeviceReplayBuffer:
+    """simple_replay_buffer.py:17-323 (int observation_dim only; dict/image observations are
+    outside the hot path and raise)."""
+
+    def __init__(self, max_replay_buffer_size, observation_dim, action_dim, random_seed=1995,
+                 flush_threshold=4096):
+        if not isinstance(observation_dim, (int, np.integer)):
+            raise NotImplementedError("DeviceReplayBuffer supports flat (int) observation_dim only")
+        self._np_rand_state = np.random.RandomState(random_seed)   # :20 -- same index stream
+        self._observation_dim = int(observation_dim)
+        self._action_dim = int(action_dim)
+        self._max_replay_buffer_size = int(max_replay_buffer_size)
+        self.ring = ReplayRing(self._max_replay_buffer_size, self._observation_dim, self._action_dim)
+        self._pending = []            # host rows not yet staged (episode-burst appends)
+        self._flush_threshold = flush_threshold
+        self._top = 0
+        self._size = 0
+        self._trajs = 0
+        self._cur_start = 0
+        self._traj_endpoints = {}
+        self._philox_counter = 0
+
+    # -- append side (R2) ----------------------------------------------------------------
+    def add_sample(self, observation, action, reward, terminal, next_observation, timeout=False, **kwargs):
+        """:78-108.  Values are rounded to float32 here exactly as the reference rounds them at
+        sample time (np_to_pytorch_batch, rlkit/torch/core.py:124-143)."""
+        O, A = self._observation_dim, self._action_dim
+        row = np.empty(layout.host_row_floats(O, A), dtype=np.float32)
+        row[:O] = np.asarray(observation, dtype=np.float64).reshape(O)
+        row[O:O + A] = np.asarray(action, dtype=np.float64).reshape(A)
+        row[O + A] = float(np.asarray(reward).reshape(-1)[0])
+        term = bool(np.asarray(terminal).reshape(-1)[0])
+        row[O + A + 1] = 1.0 if term else 0.0
+        row[O + A + 2:2 * O + A + 2] = np.asarray(next_observation, dtype=np.float64).reshape(O)
+        ab = kwargs.get("absorbing")
+        row[2 * O + A + 2:2 * O + A + 4] = 0.0 if ab is None else np.asarray(ab, dtype=np.float64).reshape(2)
+        row[2 * O + A + 4] = 1.0 if timeout else 0.0
+        self._pending.append(row)
+        if term:
+            next_start = (self._top + 1) % self._max_replay_buffer_size
+            self._traj_endpoints[self._cur_start] = next_start
+            self._cur_start = next_start
+        self._advance()
+        if len(self._pending) >= self._flush_threshold:
+            self.flush()
+
+    def add_samples(self, observations, actions, rewards, terminals, next_observations, absorbing=None, timeouts=None):
+        """Vectorised append of n transitions (not in the reference; same result as n add_sample
+        calls without terminal bookkeeping side effects other than sizes)."""
+        self.flush()
+        rows = layout.pack_host_rows(observations, actions, rewards, terminals, next_observations, absorbing, timeouts)
+        n = rows.shape[0]
+        self.ring.append_host(rows)
+        self._top = (self._top + n) % self._max_replay_buffer_size
+        self._size = min(self._size + n, self._max_replay_buffer_size)
+
+    def load_device_rows(self, hot_rows):
+        """Bulk fill from a CUDA tensor already in the hot-row layout [n, stride] (synthetic
+        benchmarks, snapshot restore): one D2D copy, no host involvement."""
+        self.flush()
+        n = hot_rows.shape[0]
+        self.ring.load_device(hot_rows)
+        self._top = (self._top + n) % self._max_replay_buffer_size
+        self._size = min(self._size + n, self._max_replay_buffer_size)
+
+    def _advance(self):
+        # :228-237
+        if self._top in self._traj_endpoints:
+            del self._traj_endpoints[self._top]
+        self._top = (self._top + 1) % self._max_replay_buffer_size
+        if self._size < self._max_replay_buffer_size:
+            self._size += 1
+
+    def terminate_episode(self):
+        # :125-132, plus: the finished episode is staged to the GPU on the side stream
+        if self._cur_start != self._top:
+            self._traj_endpoints[self._cur_start] = self._top
+            self._cur_start = self._top
+        self.flush()
+
+    def add_path(self, path, absorbing=False, env=None):
+        # :134-216
+        if absorbing:
+            raise NotImplementedError("wrap_absorbing is rejected by the reference itself (base_algorithm.py:137-139)")
+        for ob, action, reward, next_ob, terminal in zip(path["observations"], path["actions"], path["rewards"],
+                                                          path["next_observations"], path["terminals"]):
+            self.add_sample(observation=ob, action=action, reward=reward, terminal=terminal, next_observation=next_ob)
+        self.terminate_episode()
+        self._trajs += 1
+
+    def get_traj_num(self):
+        return self._trajs
+
+    def flush(self):
+        """Stage pending host rows: pinned cudaMemcpyAsync on the ring's side stream; they enter
+        the ring (scatter kernel on the compute stream) right before the next sample / train call."""
+        if self._pending:
+            self.ring.append_host(np.stack(self._pending))
+            self._pending = []
+
+    # -- sample side (R3/R4) -------------------------------------------------------------
+    def num_steps_can_sample(self):
+        return self._size
+
+    def sample_indices(self, batch_size):
+        """:242 -- RandomState.randint(0, size, B): uniform WITH replacement, same stream as the reference."""
+        return self._np_rand_state.randint(0, self._size, batch_size)
+
+    def random_batch(self, batch_size, keys=None, multi_step=False, step_num=1, **kwargs):
+        """:239-293.  Returns the reference's dict of numpy arrays (float64 / uint8 dtypes); the
+        values are the float32-rounded ones the reference feeds to its nets."""
+        if multi_step:
+            raise NotImplementedError("multi_step sampling is not on the hot path")
+        return self._get_batch_using_indices(self.sample_indices(batch_size), keys=keys)
+
+    def _get_batch_using_indices(self, indices, keys=None, **kwargs):
+        if keys is None:
+            keys = set(ALL_KEYS)
+        self.flush()
+        idx = torch.as_tensor(np.asarray(indices, dtype=np.int32), device="cuda")
+        hot, cold = self.ring.gather(idx)
+        full = layout.unpack_hot_rows(hot.cpu().numpy(), self._observation_dim, self._action_dim)
+        full["absorbing"] = cold[:, :2].cpu().numpy().astype(np.float64)
+        return {k: v for k, v in full.items() if k in keys}
+
+    def random_batch_device(self, batch_size, indices=None):
+        """Device-resident batch (dict of CUDA float32 tensors, reference key names): what
+        np_to_pytorch_batch(random_batch(B)) yields in the reference, without leaving HBM."""
+        self.flush()
+        if indices is None:
+            indices = self.sample_indices(batch_size)
+        idx = torch.as_tensor(np.asarray(indices, dtype=np.int32), device="cuda")
+        hot, cold = self.ring.gather(idx)
+        O, A = self._observation_dim, self._action_dim
+        return {
+            "observations": hot[:, :O], "actions": hot[:, O:O + A], "rewards": hot[:, O + A:O + A + 1],
+            "terminals": hot[:, O + A + 1:O + A + 2], "next_observations": hot[:, O + A + 2:2 * O + A + 2],
+            "absorbing": cold[:, :2],
+        }
+
+    def get_all(self, keys=None, **kwargs):
+        return self._get_batch_using_indices(np.arange(self._size), keys=keys)
+
+    def clear(self):
+        self._pending = []
+        self.ring.clear()
+        self._top = self._size = self._cur_start = 0
+        self._traj_endpoints = {}
+
+    # -- snapshots (base_algorithm.py:562-580 save_replay_buffer) ---------------------------
+    def __getstate__(self):
+        """Downloads to the reference's numpy field layout so `extra_data.pkl` stays readable."""
+        self.flush()
+        self.ring.commit()
+        rows = self.ring.rows_view()[: self._max_replay_buffer_size].cpu().numpy()
+        d = layout.unpack_hot_rows(rows, self._observation_dim, self._action_dim)
+        return dict(
+            _observation_dim=self._observation_dim, _action_dim=self._action_dim,
+            _max_replay_buffer_size=self._max_replay_buffer_size, _observations=d["observations"],
+            _next_obs=d["next_observations"], _actions=d["actions"], _rewards=d["rewards"],
+            _terminals=d["terminals"], _top=self._top, _size=self._size, _trajs=self._trajs,
+            _cur_start=self._cur_start, _traj_endpoints=dict(self._traj_endpoints),
+            _np_rand_state=self._np_rand_state,
+        )
+
+    def __setstate__(self, d):
+        self.__init__(d["_max_replay_buffer_size"], d["_observation_dim"], d["_action_dim"])
+        self._np_rand_state = d["_np_rand_state"]
+        n = d["_size"]
+        hot = layout.pack_hot_rows(d["_observations"], d["_actions"], d["_rewards"], d["_terminals"], d["_next_obs"])
+        # restore the physical layout (slot i holds row i), then the ring cursor
+        self.ring.load_device(torch.from_numpy(hot[: self._max_replay_buffer_size]).cuda())
+        self.ring.set_cursor(d["_top"], n)
+        self._top, self._size, self._trajs = d["_top"], n, d["_trajs"]
+        self._cur_start, self._traj_endpoints = d["_cur_start"], dict(d["_traj_endpoints"])
+
+
+class DeviceEnvReplayBuffer(DeviceReplayBuffer):
+    """env_replay_buffer.py:7-49: dims taken from env.observation_space / env.action_space."""
+
+    def __init__(self, max_replay_buffer_size, env, random_seed=1995):
+        self._ob_space = env.observation_space
+        self._action_space = env.action_space
+        super().__init__(max_replay_buffer_size, get_dim(self._ob_space), get_dim(self._action_space), random_seed)
+
+
+def get_dim(space):
+    """env_replay_buffer.py:35-49 for Box / Discrete spaces (duck-typed, no gym import)."""
+    name = type(space).__name__
+    if name == "Discrete":
+        return 1
+    if hasattr(space, "low"):
+        low = np.asarray(space.low)
+        if low.ndim > 1:
+            raise NotImplementedError("image observations are not on the hot path")
+        return int(low.size)
+    if hasattr(space, "flat_dim"):
+        return int(space.flat_dim)
+    raise TypeError("Unknown space: {}".format(space))

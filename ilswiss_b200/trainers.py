@@ -1,0 +1,360 @@
+"""Drop-in Trainer classes (rlkit/core/trainer.py:4-28 interface) backed by the fused engine.
+
+    SoftActorCritic  <->  rlkit/torch/algorithms/sac/sac_alpha.py:13-284
+    TD3              <->  rlkit/torch/algorithms/td3/td3.py:13-223
+
+Same constructor signatures, same attributes read from outside (.policy, .networks,
+.eval_statistics, get_eval_statistics(), end_epoch(), get_snapshot(), load_snapshot(), to()),
+same eval-statistics keys.  The nn.Modules passed in stay valid: their Parameters are re-pointed
+to views of the device parameter arenas the kernels update in place, so exploration /
+evaluation policies and pickled snapshots keep seeing the trained weights.
+"""
+import copy
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.optim as optim
+
+from . import _abi
+from .engine import NetArena, StepEngine, require_cuda
+
+
+def _stats(name, data):
+    """rlkit/core/eval_util.py:91-142 create_stats_ordered_dict for ndarray data."""
+    data = np.asarray(data)
+    return OrderedDict([(name + " Mean", np.mean(data)), (name + " Std", np.std(data)),
+                        (name + " Max", np.max(data)), (name + " Min", np.min(data))])
+
+
+def module_dims(module):
+    """(in_dim, hidden, out_dim, log_std_head) of a 2-hidden-layer reference MLP from its
+    parameter list (networks.py:23-83 / policies.py:191-243 / simple_disc_models.py:8-41)."""
+    ps = list(module.parameters())
+    if len(ps) not in (6, 8):
+        raise NotImplementedError("fused engine supports MLPs with exactly two hidden layers (got %d parameter tensors)" % len(ps))
+    H, in_dim = ps[0].shape
+    if tuple(ps[2].shape) != (H, H) or ps[4].shape[1] != H:
+        raise NotImplementedError("fused engine needs equal hidden widths")
+    out_dim = ps[4].shape[0]
+    if len(ps) == 8 and tuple(ps[6].shape) != (out_dim, H):
+        raise NotImplementedError("unexpected log-std head shape")
+    for flag in ("layer_norm", "batch_norm"):
+        if getattr(module, flag, False):
+            raise NotImplementedError("%s is not supported by the fused engine" % flag)
+    return int(in_dim), int(H), int(out_dim), len(ps) == 8
+
+
+def adopt_module(module, trainable=True):
+    """Moves a module's parameters into a flat device arena and re-points them at views of it."""
+    in_dim, H, out_dim, ls = module_dims(module)
+    arena = NetArena(in_dim, H, out_dim, ls, trainable=trainable)
+    with torch.no_grad():
+        for p, view in zip(module.parameters(), arena.views("p")):
+            view.copy_(p.detach().to(device="cuda", dtype=torch.float32))
+            p.data = view
+    module._ilsw_arena = arena
+    return arena
+
+
+def clone_module(module):
+    """PyTorchModule.copy() (rlkit/torch/core.py:32-35) when available, else deepcopy."""
+    if hasattr(module, "copy") and callable(module.copy) and not isinstance(module, dict):
+        try:
+            return module.copy()
+        except Exception:
+            pass
+    return copy.deepcopy(module)
+
+
+class _FusedTrainer:
+    eval_statistics = None
+
+    def _finish_init(self, cfg, nets):
+        require_cuda()
+        self.engine = StepEngine(cfg, nets)
+        self._cfg = cfg
+        self._seed = int(np.random.randint(1, 2 ** 31 - 1))
+        self._launch = 0
+
+    # -- the two ways to run gradient steps ------------------------------------------------
+    def train_step(self, batch):
+        """Trainer.train_step(batch): batch = dict of (B,.) float tensors with the reference's keys
+        (np_to_pytorch_batch output).  Runs ONE fused step on that batch."""
+        B = self._cfg.batch
+        b = {}
+        for key, name in (("observations", "obs"), ("actions", "act"), ("rewards", "rew"), ("terminals", "term"),
+                          ("next_observations", "next_obs")):
+            t = batch[key]
+            if not torch.is_tensor(t):
+                t = torch.as_tensor(np.asarray(t))
+            t = t.to(device="cuda", dtype=torch.float32).contiguous()
+            if t.shape[0] != B:
+                raise ValueError("batch size %d != trainer batch %d (fixed at construction: kwargs['batch_size'])" % (t.shape[0], B))
+            b[name] = t
+        want = self.eval_statistics is None
+        self._launch += 1
+        self.engine.train(None, 1, batch=b, seed=self._seed + self._launch, stats_step=0 if want else -1)
+        self._after_launch(1, want)
+
+    def train_from_buffer(self, replay_buffer, n_steps, inject=None):
+        """n_steps gradient steps, each on a fresh uniform sample of `replay_buffer`
+        (a DeviceReplayBuffer), in ONE kernel launch -- TorchRLAlgorithm._do_training
+        (torch_rl_algorithm.py:28-34) without the per-step host round trips."""
+        replay_buffer.flush()
+        want = self.eval_statistics is None
+        done = 0
+        while done < n_steps:
+            k = min(n_steps - done, self._cfg.max_steps_per_call)
+            self._launch += 1
+            sub = None if inject is None else {kk: v[done:done + k].contiguous() for kk, v in inject.items()}
+            self.engine.train(replay_buffer.ring, k, inject=sub, seed=self._seed + self._launch,
+                              stats_step=0 if (want and done == 0) else -1)
+            if want and done == 0:
+                self._after_launch(k, True)
+            done += k
+
+    def _after_launch(self, n_steps, want_stats):
+        if want_stats:
+            self.eval_statistics = self._build_stats(self.engine.losses(n_steps)[0], self.engine.stats())
+
+    # -- Trainer interface -----------------------------------------------------------------
+    def get_eval_statistics(self):
+        return self.eval_statistics
+
+    def end_epoch(self):
+        self.eval_statistics = None
+
+    def to(self, device):
+        # parameters already live on the GPU inside the arenas; nothing to move
+        return self
+
+    def _sync_optimizer(self, opt, arena, step):
+        opt.state.clear()
+        for p, m, v in zip(opt.param_groups[0]["params"], arena.views("m"), arena.views("v")):
+            opt.state[p] = dict(step=torch.tensor(float(step)), exp_avg=m, exp_avg_sq=v)
+
+    def _load_optimizer(self, opt, arena):
+        step = 0
+        for p, m, v in zip(opt.param_groups[0]["params"], arena.views("m"), arena.views("v")):
+            st = opt.state.get(p)
+            if st:
+                m.copy_(st["exp_avg"].to(m.device))
+                v.copy_(st["exp_avg_sq"].to(v.device))
+                step = int(float(st["step"]))
+        return step
+
+
+class SoftActorCritic(_FusedTrainer):
+    """sac_alpha.py:13-284 (reparameterised SAC, twin Q, auto-tuned alpha)."""
+
+    def __init__(self, policy, qf1, qf2, reward_scale=1.0, discount=0.99, policy_lr=1e-3, qf_lr=1e-3,
+                 alpha_lr=3e-4, soft_target_tau=1e-2, alpha=0.2, train_alpha=True,
+                 policy_mean_reg_weight=1e-3, policy_std_reg_weight=1e-3, optimizer_class=optim.Adam,
+                 beta_1=0.9, target_entropy=None, batch_size=256, max_steps_per_call=1000, **kwargs):
+        if optimizer_class is not optim.Adam:
+            raise NotImplementedError("the fused step implements torch.optim.Adam only")
+        self.policy, self.qf1, self.qf2 = policy, qf1, qf2
+        self.reward_scale, self.discount, self.soft_target_tau = reward_scale, discount, soft_target_tau
+        self.policy_mean_reg_weight, self.policy_std_reg_weight = policy_mean_reg_weight, policy_std_reg_weight
+        self.train_alpha = train_alpha
+        in_dim, H, act_dim, ls = module_dims(policy)
+        if not ls:
+            raise NotImplementedError("SAC needs a ReparamTanhMultivariateGaussianPolicy (conditioned_std=True)")
+        self.target_entropy = target_entropy
+        if target_entropy is None:   # sac_alpha.py:55-58
+            if "env" in kwargs:
+                self.target_entropy = -np.prod(kwargs["env"].action_space.shape) / 2.0
+            else:
+                self.target_entropy = -act_dim / 2.0
+        self.target_qf1, self.target_qf2 = clone_module(qf1), clone_module(qf2)   # :60-61
+        self._arenas = OrderedDict(
+            policy=adopt_module(policy), qf1=adopt_module(qf1), qf2=adopt_module(qf2),
+            target_qf1=adopt_module(self.target_qf1, False), target_qf2=adopt_module(self.target_qf2, False))
+        self.policy_optimizer = optim.Adam(self.policy.parameters(), lr=policy_lr, betas=(beta_1, 0.999))
+        self.qf1_optimizer = optim.Adam(self.qf1.parameters(), lr=qf_lr, betas=(beta_1, 0.999))
+        self.qf2_optimizer = optim.Adam(self.qf2.parameters(), lr=qf_lr, betas=(beta_1, 0.999))
+        self._log_alpha0 = float(np.log(alpha))
+        self._log_alpha_param = torch.tensor(np.log(alpha), requires_grad=train_alpha, device="cuda")
+        self.alpha_optimizer = optim.Adam([self._log_alpha_param], lr=alpha_lr, betas=(beta_1, 0.999))
+        cfg = _abi.TrainerConfig()
+        cfg.algo = _abi.ALGO_SAC_ALPHA
+        cfg.obs_dim, cfg.act_dim, cfg.batch = in_dim, act_dim, int(batch_size)
+        cfg.max_steps_per_call = int(max_steps_per_call)
+        cfg.reward_scale, cfg.discount, cfg.soft_target_tau = reward_scale, discount, soft_target_tau
+        cfg.policy_lr, cfg.qf_lr, cfg.alpha_lr = policy_lr, qf_lr, alpha_lr
+        cfg.beta_1, cfg.beta_2, cfg.adam_eps = beta_1, 0.999, 1e-8
+        cfg.alpha, cfg.train_alpha = alpha, int(bool(train_alpha))
+        cfg.target_entropy = float(self.target_entropy)
+        cfg.policy_mean_reg_weight, cfg.policy_std_reg_weight = policy_mean_reg_weight, policy_std_reg_weight
+        cfg.max_act = 1.0
+        self._finish_init(cfg, list(self._arenas.values()))
+        self.eval_statistics = None
+
+    @property
+    def log_alpha(self):
+        """float64 0-dim tensor like sac_alpha.py:51-53, refreshed from the device state."""
+        with torch.no_grad():
+            self._log_alpha_param.fill_(self.engine.get_state().log_alpha)
+        return self._log_alpha_param
+
+    @property
+    def alpha(self):
+        return self.log_alpha.detach().exp()
+
+    @property
+    def networks(self):
+        return [self.policy, self.qf1, self.qf2, self.target_qf1, self.target_qf2]
+
+    def _build_stats(self, L, vec):
+        B, A = self._cfg.batch, self._cfg.act_dim
+        st = OrderedDict()
+        st["Reward Scale"] = self.reward_scale
+        st["QF1 Loss"] = float(L[_abi.L_QF1])
+        st["QF2 Loss"] = float(L[_abi.L_QF2])
+        if self.train_alpha:
+            st["Alpha Loss"] = float(L[_abi.L_ALPHA_LOSS])
+        st["Policy Loss"] = float(L[_abi.L_POLICY])
+        st.update(_stats("Q1 Predictions", vec[0:B]))
+        st.update(_stats("Q2 Predictions", vec[B:2 * B]))
+        st.update(_stats("Alpha", [float(L[_abi.L_ALPHA])]))
+        o = 6 * B
+        st.update(_stats("Log Pis", vec[o:o + B]))
+        st.update(_stats("Policy mu", vec[o + B:o + B + B * A]))
+        st.update(_stats("Policy log std", vec[o + B + B * A:o + B + 2 * B * A]))
+        return st
+
+    def get_snapshot(self):
+        st = self.engine.get_state()
+        self._sync_optimizer(self.policy_optimizer, self._arenas["policy"], st.adam_step[2])
+        self._sync_optimizer(self.qf1_optimizer, self._arenas["qf1"], st.adam_step[0])
+        self._sync_optimizer(self.qf2_optimizer, self._arenas["qf2"], st.adam_step[1])
+        la = self.log_alpha
+        self.alpha_optimizer.state.clear()
+        self.alpha_optimizer.state[la] = dict(step=torch.tensor(float(st.alpha_step)),
+                                              exp_avg=torch.tensor(st.alpha_exp_avg, dtype=torch.float64),
+                                              exp_avg_sq=torch.tensor(st.alpha_exp_avg_sq, dtype=torch.float64))
+        return dict(qf1=self.qf1, qf2=self.qf2, policy=self.policy, target_qf1=self.target_qf1,
+                    target_qf2=self.target_qf2, log_alpha=la, policy_optimizer=self.policy_optimizer,
+                    qf1_optimizer=self.qf1_optimizer, qf2_optimizer=self.qf2_optimizer,
+                    alpha_optimizer=self.alpha_optimizer)
+
+    def load_snapshot(self, snapshot):
+        """sac_alpha.py:262-272 -- values are copied INTO the arenas (the modules keep their identity)."""
+        with torch.no_grad():
+            for name in ("policy", "qf1", "qf2", "target_qf1", "target_qf2"):
+                for dst, src in zip(getattr(self, name).parameters(), snapshot[name].parameters()):
+                    dst.copy_(src.to(dst.device))
+        st = self.engine.get_state()
+        for slot, key, arena in ((2, "policy_optimizer", "policy"), (0, "qf1_optimizer", "qf1"), (1, "qf2_optimizer", "qf2")):
+            src = snapshot[key]
+            mine = getattr(self, key)
+            for p_dst, p_src in zip(mine.param_groups[0]["params"], src.param_groups[0]["params"]):
+                if p_src in src.state:
+                    mine.state[p_dst] = src.state[p_src]
+            st.adam_step[slot] = self._load_optimizer(mine, self._arenas[arena])
+        st.log_alpha = float(snapshot["log_alpha"].detach().cpu())
+        a_src = snapshot["alpha_optimizer"]
+        for p_src in a_src.param_groups[0]["params"]:
+            if p_src in a_src.state:
+                s = a_src.state[p_src]
+                st.alpha_exp_avg, st.alpha_exp_avg_sq = float(s["exp_avg"]), float(s["exp_avg_sq"])
+                st.alpha_step = int(float(s["step"]))
+        self.engine.set_state(st)
+
+
+class TD3(_FusedTrainer):
+    """td3.py:13-223.  The target-action noise is the policy MODULE's (policy.noise /
+    policy.noise_clip, policies.py:150-152); the trainer arguments target_policy_noise* are stored
+    but unused, exactly as in the reference (td3.py:46-47,82-83)."""
+
+    def __init__(self, policy, qf1, qf2, reward_scale=1.0, discount=0.99, target_policy_noise=0.2,
+                 target_policy_noise_clip=0.5, policy_lr=1e-3, qf_lr=1e-3, policy_and_target_update_period=2,
+                 soft_target_tau=0.005, qf_criterion=None, optimizer_class=optim.Adam, batch_size=256,
+                 max_steps_per_call=1000, **kwargs):
+        if optimizer_class is not optim.Adam:
+            raise NotImplementedError("the fused step implements torch.optim.Adam only")
+        if qf_criterion is not None and not isinstance(qf_criterion, torch.nn.MSELoss):
+            raise NotImplementedError("the fused step implements the default MSELoss criterion")
+        self.qf1, self.qf2, self.policy = qf1, qf2, policy
+        self.reward_scale, self.discount = reward_scale, discount
+        self.target_policy_noise, self.target_policy_noise_clip = target_policy_noise, target_policy_noise_clip
+        self.policy_and_target_update_period, self.soft_target_tau = policy_and_target_update_period, soft_target_tau
+        in_dim, H, act_dim, ls = module_dims(policy)
+        if ls:
+            raise NotImplementedError("TD3 needs a deterministic MlpGaussianNoisePolicy")
+        self.target_policy = clone_module(policy)
+        self.target_qf1, self.target_qf2 = clone_module(qf1), clone_module(qf2)
+        self._arenas = OrderedDict(
+            policy=adopt_module(policy), qf1=adopt_module(qf1), qf2=adopt_module(qf2),
+            target_qf1=adopt_module(self.target_qf1, False), target_qf2=adopt_module(self.target_qf2, False),
+            target_policy=adopt_module(self.target_policy, False))
+        self.qf1_optimizer = optim.Adam(self.qf1.parameters(), lr=qf_lr)
+        self.qf2_optimizer = optim.Adam(self.qf2.parameters(), lr=qf_lr)
+        self.policy_optimizer = optim.Adam(self.policy.parameters(), lr=policy_lr)
+        cfg = _abi.TrainerConfig()
+        cfg.algo = _abi.ALGO_TD3
+        cfg.obs_dim, cfg.act_dim, cfg.batch = in_dim, act_dim, int(batch_size)
+        cfg.max_steps_per_call = int(max_steps_per_call)
+        cfg.reward_scale, cfg.discount, cfg.soft_target_tau = reward_scale, discount, soft_target_tau
+        cfg.policy_lr, cfg.qf_lr = policy_lr, qf_lr
+        cfg.beta_1, cfg.beta_2, cfg.adam_eps, cfg.alpha = 0.9, 0.999, 1e-8, 1.0
+        cfg.policy_and_target_update_period = int(policy_and_target_update_period)
+        cfg.policy_noise = float(getattr(policy, "noise", 0.1))
+        cfg.policy_noise_clip = float(getattr(policy, "noise_clip", 0.5))
+        cfg.max_act = float(getattr(policy, "max_act", 1.0))
+        self._finish_init(cfg, list(self._arenas.values()))
+        self.eval_statistics = None
+
+    @property
+    def _n_train_steps_total(self):
+        return self.engine.get_state().n_train_steps_total
+
+    @property
+    def networks(self):
+        return [self.policy, self.qf1, self.qf2, self.target_policy, self.target_qf1, self.target_qf2]
+
+    def _build_stats(self, L, vec):
+        B, A = self._cfg.batch, self._cfg.act_dim
+        st = OrderedDict()
+        st["QF1 Loss"] = float(L[_abi.L_QF1])
+        st["QF2 Loss"] = float(L[_abi.L_QF2])
+        # on non-policy steps the reference evaluates a stats-only policy loss (td3.py:131-136);
+        # the engine reports the loss of the most recent policy update instead
+        pl = float(L[_abi.L_POLICY])
+        self._last_policy_loss = pl if not np.isnan(pl) else getattr(self, "_last_policy_loss", float("nan"))
+        st["Policy Loss"] = self._last_policy_loss
+        st.update(_stats("Q1 Predictions", vec[0:B]))
+        st.update(_stats("Q2 Predictions", vec[B:2 * B]))
+        st.update(_stats("Q Targets", vec[2 * B:3 * B]))
+        st.update(_stats("Bellman Errors 1", vec[3 * B:4 * B]))
+        st.update(_stats("Bellman Errors 2", vec[4 * B:5 * B]))
+        st.update(_stats("Policy Action", self._cfg.max_act * vec[6 * B:6 * B + B * A]))
+        return st
+
+    def get_snapshot(self):
+        st = self.engine.get_state()
+        self._sync_optimizer(self.policy_optimizer, self._arenas["policy"], st.adam_step[2])
+        self._sync_optimizer(self.qf1_optimizer, self._arenas["qf1"], st.adam_step[0])
+        self._sync_optimizer(self.qf2_optimizer, self._arenas["qf2"], st.adam_step[1])
+        return dict(qf1=self.qf1, qf2=self.qf2, policy=self.policy, target_policy=self.target_policy,
+                    target_qf1=self.target_qf1, target_qf2=self.target_qf2, policy_optimizer=self.policy_optimizer,
+                    qf1_optimizer=self.qf1_optimizer, qf2_optimizer=self.qf2_optimizer)
+
+    def load_snapshot(self, snapshot):
+        """td3.py:198-206 (whose 'self.qf2_optimizer' key typo is NOT reproduced)."""
+        with torch.no_grad():
+            for name in ("policy", "qf1", "qf2", "target_qf1", "target_qf2", "target_policy"):
+                if name in snapshot:
+                    for dst, src in zip(getattr(self, name).parameters(), snapshot[name].parameters()):
+                        dst.copy_(src.to(dst.device))
+        st = self.engine.get_state()
+        for slot, key, arena in ((2, "policy_optimizer", "policy"), (0, "qf1_optimizer", "qf1"), (1, "qf2_optimizer", "qf2")):
+            if key not in snapshot:
+                continue
+            src, mine = snapshot[key], getattr(self, key)
+            for p_dst, p_src in zip(mine.param_groups[0]["params"], src.param_groups[0]["params"]):
+                if p_src in src.state:
+                    mine.state[p_dst] = src.state[p_src]
+            st.adam_step[slot] = self._load_optimizer(mine, self._arenas[arena])
+        self.engine.set_state(st)

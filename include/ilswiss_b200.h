@@ -71,6 +71,8 @@ int ilsw_rb_gather(ilsw_rb* rb, const int32_t* idx_dev, int B, float* out_hot, f
 int ilsw_rb_sample(ilsw_rb* rb, int B, uint64_t seed, uint64_t counter, int32_t* idx_out_dev,
                    float* out_hot, void* stream);
 int ilsw_rb_clear(ilsw_rb* rb);
+/* snapshot restore: set the write cursor / fill level after a physical-layout load */
+int ilsw_rb_set_cursor(ilsw_rb* rb, int64_t top, int64_t size);
 
 /* ---------------------------------------------------------------------------------------
  * Networks: one flat fp32 arena per network in nn.Module.parameters() order of the reference
@@ -196,6 +198,9 @@ int ilsw_set_state(ilsw_trainer* tr, const ilsw_state* in, void* stream);
 /* human-readable phase table of the compiled step program (host only; no GPU work) */
 int ilsw_describe_program(const ilsw_trainer* tr, char* buf, int buf_len);
 int ilsw_num_phases(const ilsw_trainer* tr);
+/* profiling: %globaltimer (ns) at the start and after every phase barrier of the LAST step of the
+ * most recent launch: out[0..n_phases] */
+int ilsw_read_phase_ns(ilsw_trainer* tr, unsigned long long* host_out, int n, void* stream);
 int64_t ilsw_kernel_launches(const ilsw_trainer* tr);   /* engine launches so far */
 
 /* A1: sampler-side policy inference for <= 64 env rows (policies.py:245-246, core.py:74-89).

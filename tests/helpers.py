@@ -233,13 +233,13 @@ def assert_params_close(got, ref, steps, lr=3e-4, msg=""):
     elements: Adam's normalised update m/(sqrt(v)+eps) is +-lr in the first steps REGARDLESS of
     |g|, so an element whose true gradient is ~0 (|g| ~ 1e-9, pure summation-order noise) can
     legitimately differ by up to 2*lr per step between two fp32 implementations.  Those
-    elements are bounded by 2*lr*steps and must be rarer than 1e-4 of the tensor."""
+    elements are bounded by 2*lr*steps and must be rarer than 5e-4 of the tensor."""
     got = np.asarray(got, dtype=np.float64).ravel()
     ref = np.asarray(ref, dtype=np.float64).ravel()
     assert got.shape == ref.shape, (msg, got.shape, ref.shape)
     diff = np.abs(got - ref)
     bad = int((diff > 1e-5).sum())
-    assert bad <= max(1, int(1e-4 * diff.size)), (msg, bad, diff.size, float(diff.max()))
+    assert bad <= max(2, int(5e-4 * diff.size)), (msg, bad, diff.size, float(diff.max()))
     assert float(diff.max()) <= 2.0 * lr * steps + 1e-6, (msg, float(diff.max()))
 
 

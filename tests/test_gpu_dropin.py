@@ -1,0 +1,207 @@
+"""-m gpu: the reference-facing drop-in classes (Trainer / ReplayBuffer / AdvIRL interfaces)."""
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import CFG, G, R, STAT_TO_SLOT, case_data, case_injection, layout
+
+pytestmark = pytest.mark.gpu
+
+
+def build_modules(case):
+    """Parameter containers (ilswiss_b200.modules) loaded with the seed-reproducible oracle init."""
+    from ilswiss_b200 import modules
+
+    O, A = case["obs_dim"], case["act_dim"]
+    nets = G.build_oracle_nets(case)
+    mods = {"qf1": modules.FlattenMlp([256, 256], 1, O + A), "qf2": modules.FlattenMlp([256, 256], 1, O + A)}
+    if case["algo"] == "td3":
+        mods["policy"] = modules.DeterministicNoisePolicy([256, 256], O, A, policy_noise=case["policy_noise"],
+                                                          policy_noise_clip=case["policy_noise_clip"])
+    else:
+        mods["policy"] = modules.TanhGaussianPolicy([256, 256], O, A)
+    if case["algo"] == "adv_irl":
+        mods["disc"] = modules.MLPDisc(O + A, 128)
+    for k, m in mods.items():
+        with torch.no_grad():
+            for p, v in zip(m.parameters(), nets[k].p.values()):
+                assert tuple(p.shape) == tuple(v.shape), (k, p.shape, v.shape)
+                p.copy_(v)
+    return mods, nets
+
+
+def fill(buf, data):
+    buf.add_samples(**data)
+
+
+def test_sac_trainer_dropin_train_step_and_stats_keys():
+    from ilswiss_b200.replay_buffer import DeviceReplayBuffer
+    from ilswiss_b200.trainers import SoftActorCritic
+
+    torch.set_num_threads(1)
+    case = CFG.CASES["sac_hopper"]
+    mods, nets = build_modules(case)
+    policy_ref = mods["policy"]
+    tr = SoftActorCritic(mods["policy"], mods["qf1"], mods["qf2"], batch_size=case["batch"], **case["sac"])
+    assert tr.policy is policy_ref and len(tr.networks) == 5
+    assert all(p.is_cuda for p in tr.policy.parameters())
+    data, _ = case_data(case)
+    buf = DeviceReplayBuffer(case["n_fill"], case["obs_dim"], case["act_dim"], random_seed=CFG.BUFFER_SEED)
+    fill(buf, data)
+    assert buf.num_steps_can_sample() == case["n_fill"] and buf._max_replay_buffer_size == case["n_fill"]
+    # reference-side oracle on identical indices / eps
+    ora = R.SacAlphaOracle(nets["policy"], nets["qf1"], nets["qf2"], case["act_dim"], **case["sac"])
+    obuf = R.ReplayOracle(case["n_fill"], case["obs_dim"], case["act_dim"], random_seed=CFG.BUFFER_SEED)
+    obuf.load_bulk(data)
+    inj = case_injection(case)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in inj.items()}
+    tr.train_from_buffer(buf, case["steps"], inject=dev)
+    L = tr.engine.losses(case["steps"])
+    for t in range(case["steps"]):
+        torch.manual_seed(CFG.EPS_SEED0 + t)
+        batch = R.np_to_torch_batch(obuf.random_batch(case["batch"]))
+        s = ora.train_step(batch, torch.randn(case["batch"], case["act_dim"]), torch.randn(case["batch"], case["act_dim"]))
+        assert abs(L[t, 0] - s["qf1_loss"]) <= 1e-4 * max(abs(s["qf1_loss"]), 1e-2)
+        assert abs(L[t, 2] - s["policy_loss"]) <= 1e-4
+    # the SAME nn.Module objects now hold the trained weights (exploration policy stays valid)
+    got = np.concatenate([p.detach().cpu().numpy().ravel() for p in policy_ref.parameters()])
+    assert np.max(np.abs(got - nets["policy"].flat())) < 5e-4
+    st = tr.get_eval_statistics()
+    expect = ["Reward Scale", "QF1 Loss", "QF2 Loss", "Alpha Loss", "Policy Loss"]
+    for name in ("Q1 Predictions", "Q2 Predictions", "Alpha", "Log Pis", "Policy mu", "Policy log std"):
+        expect += [name + s for s in (" Mean", " Std", " Max", " Min")]
+    assert list(st.keys()) == expect                       # sac_alpha.py:186-233 key set and order
+    tr.end_epoch()
+    assert tr.get_eval_statistics() is None
+    # Trainer.train_step(batch) with a dict of device tensors (np_to_pytorch_batch equivalent)
+    tr.train_step(buf.random_batch_device(case["batch"]))
+    assert set(tr.get_eval_statistics().keys()) == set(expect)
+    # snapshot: picklable, optimizer state populated, log_alpha float64 0-dim
+    snap = tr.get_snapshot()
+    assert set(snap.keys()) == {"qf1", "qf2", "policy", "target_qf1", "target_qf2", "log_alpha", "policy_optimizer",
+                                "qf1_optimizer", "qf2_optimizer", "alpha_optimizer"}
+    assert snap["log_alpha"].dtype == torch.float64 and snap["log_alpha"].dim() == 0
+    osd = snap["qf1_optimizer"].state_dict()
+    assert len(osd["state"]) == 6 and float(osd["state"][0]["step"]) == case["steps"] + 1
+    pickle.loads(pickle.dumps({k: v for k, v in snap.items() if "optimizer" not in k}))
+
+
+def test_snapshot_round_trip_resumes_bit_identically():
+    from ilswiss_b200.replay_buffer import DeviceReplayBuffer
+    from ilswiss_b200.trainers import SoftActorCritic
+
+    case = CFG.CASES["sac_hopper"]
+    inj = {k: torch.from_numpy(v).cuda() for k, v in case_injection(case).items()}
+    data, _ = case_data(case)
+
+    def mk():
+        mods, _ = build_modules(case)
+        tr = SoftActorCritic(mods["policy"], mods["qf1"], mods["qf2"], batch_size=case["batch"], **case["sac"])
+        buf = DeviceReplayBuffer(case["n_fill"], case["obs_dim"], case["act_dim"], random_seed=1)
+        fill(buf, data)
+        tr.eval_statistics = {}
+        return tr, buf
+
+    a, abuf = mk()
+    a.train_from_buffer(abuf, 6, inject=inj)
+    b, bbuf = mk()
+    b.train_from_buffer(bbuf, 3, inject={k: v[:3] for k, v in inj.items()})
+    snap = b.get_snapshot()
+    c, cbuf = mk()
+    c.load_snapshot(snap)
+    c.train_from_buffer(cbuf, 3, inject={k: v[3:] for k, v in inj.items()})
+    for name in ("policy", "qf1", "target_qf2"):
+        pa = torch.cat([p.flatten() for p in getattr(a, name).parameters()])
+        pc = torch.cat([p.flatten() for p in getattr(c, name).parameters()])
+        assert torch.equal(pa, pc), name
+    assert float(a.log_alpha) == float(c.log_alpha)
+
+
+def test_td3_trainer_dropin():
+    from ilswiss_b200.replay_buffer import DeviceReplayBuffer
+    from ilswiss_b200.trainers import TD3
+
+    case = CFG.CASES["td3_hopper"]
+    mods, nets = build_modules(case)
+    tr = TD3(mods["policy"], mods["qf1"], mods["qf2"], batch_size=case["batch"], **case["td3"])
+    assert len(tr.networks) == 6
+    data, _ = case_data(case)
+    buf = DeviceReplayBuffer(case["n_fill"], case["obs_dim"], case["act_dim"], random_seed=1)
+    fill(buf, data)
+    inj = {k: torch.from_numpy(v).cuda() for k, v in case_injection(case).items()}
+    tr.train_from_buffer(buf, case["steps"], inject=inj)
+    rows, final, _ = G.run_oracle(case)
+    L = tr.engine.losses(case["steps"])
+    for t, row in enumerate(rows):
+        assert abs(L[t, 0] - row["QF1 Loss"]) <= 1e-4 * max(abs(row["QF1 Loss"]), 1e-2)
+    st = tr.get_eval_statistics()
+    assert list(st.keys())[:3] == ["QF1 Loss", "QF2 Loss", "Policy Loss"]
+    for name in ("Q1 Predictions", "Q2 Predictions", "Q Targets", "Bellman Errors 1", "Bellman Errors 2", "Policy Action"):
+        assert name + " Mean" in st
+    assert tr._n_train_steps_total == case["steps"]
+
+
+def test_replay_buffer_dropin_matches_reference_semantics():
+    from ilswiss_b200.replay_buffer import DeviceReplayBuffer
+
+    rs = np.random.RandomState(0)
+    O, A, cap = 5, 2, 40
+    buf = DeviceReplayBuffer(cap, O, A, random_seed=11)
+    ora = R.ReplayOracle(cap, O, A, random_seed=11)
+    for ep in range(5):                       # episode bursts through the per-transition API
+        n = 13
+        path = dict(observations=rs.randn(n, O), actions=rs.uniform(-1, 1, (n, A)), rewards=rs.randn(n, 1),
+                    next_observations=rs.randn(n, O), terminals=np.array([[i == n - 1] for i in range(n)]))
+        buf.add_path(path)
+        ora.add_path(path)
+        assert buf.num_steps_can_sample() == ora.num_steps_can_sample()
+        assert buf._top == ora._top and buf._traj_endpoints == ora._traj_endpoints
+        got, ref = buf.random_batch(32), ora.random_batch(32)       # same RandomState stream
+        assert set(got.keys()) == set(ref.keys())
+        for k in ref:
+            assert got[k].dtype == ref[k].dtype and got[k].shape == ref[k].shape, k
+            np.testing.assert_array_equal(got[k].astype(np.float32), ref[k].astype(np.float32), err_msg=k)
+        sub = buf.random_batch(8, keys=["observations", "actions"])
+        ora.random_batch(8, keys=["observations", "actions"])
+        assert set(sub.keys()) == {"observations", "actions"}
+    clone = pickle.loads(pickle.dumps(buf))   # save_replay_buffer: true round trip
+    idx = np.arange(cap)
+    a, b = buf._get_batch_using_indices(idx), clone._get_batch_using_indices(idx)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+    assert clone._top == buf._top and clone._size == buf._size
+
+
+def test_adv_irl_engine_matches_oracle_and_stats_keys():
+    from ilswiss_b200.adv_irl import AdvIRLEngine
+    from ilswiss_b200.replay_buffer import DeviceReplayBuffer
+    from ilswiss_b200.trainers import SoftActorCritic
+
+    torch.set_num_threads(1)
+    case = CFG.CASES["gail_walker"]
+    mods, _ = build_modules(case)
+    tr = SoftActorCritic(mods["policy"], mods["qf1"], mods["qf2"], batch_size=case["batch"], **case["sac"])
+    data, edata = case_data(case)
+    buf = DeviceReplayBuffer(case["n_fill"], case["obs_dim"], case["act_dim"], random_seed=1)
+    ebuf = DeviceReplayBuffer(case["n_fill"], case["obs_dim"], case["act_dim"], random_seed=3)
+    fill(buf, data)
+    fill(ebuf, edata)
+    irl = AdvIRLEngine(case["mode"], mods["disc"], tr, ebuf, buf, disc_optim_batch_size=case["batch"],
+                       policy_optim_batch_size=case["batch"], num_update_loops_per_train_call=case["steps"],
+                       num_disc_updates_per_loop_iter=1, num_policy_updates_per_loop_iter=1, **case["disc"])
+    inj = {k: torch.from_numpy(v).cuda() for k, v in case_injection(case).items()}
+    irl.do_training(inject=inj)
+    rows, final, _ = G.run_oracle(case)
+    st = irl.disc_eval_statistics
+    assert list(st.keys()) == ["Disc CE Loss", "Disc Acc", "Grad Pen", "Grad Pen W", "Disc Rew Mean", "Disc Rew Std",
+                               "Disc Rew Max", "Disc Rew Min"]
+    assert abs(st["Disc CE Loss"] - rows[0]["Disc CE Loss"]) < 1e-4 * abs(rows[0]["Disc CE Loss"])
+    assert abs(st["Grad Pen"] - rows[0]["Grad Pen"]) < 1e-4 * max(abs(rows[0]["Grad Pen"]), 1e-2)
+    assert abs(st["Disc Rew Mean"] - rows[-1]["Disc Rew Mean"]) < 1e-4 * abs(rows[-1]["Disc Rew Mean"])   # last write wins
+    got = np.concatenate([p.detach().cpu().numpy().ravel() for p in mods["disc"].parameters()])
+    assert np.max(np.abs(got - final["disc"])) < 1e-4
+    with pytest.raises(NotImplementedError):
+        AdvIRLEngine("gail", mods["disc"], tr, ebuf, buf, state_only=True, disc_optim_batch_size=256,
+                     policy_optim_batch_size=256, num_disc_updates_per_loop_iter=1, num_policy_updates_per_loop_iter=1)

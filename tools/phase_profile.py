@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Per-phase timing of the persistent engine kernel (in-kernel %globaltimer stamps of the last
+step of a launch).  Usage: python tools/phase_profile.py [workload ...]   (needs a GPU)"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    names = sys.argv[1:] or ["sac_hopper"]
+    for name in names:
+        w = bench.WORKLOADS[name]
+        tr, buf, irl = bench.build_ours(w, seed=1, steps_per_launch=200)
+        tr.eval_statistics = {}
+        if irl is not None:
+            irl.disc_eval_statistics = {}
+        for _ in range(3):
+            bench.run_steps(tr, buf, irl, 200)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        bench.run_steps(tr, buf, irl, 200)
+        e1.record()
+        torch.cuda.synchronize()
+        us = tr.engine.phase_times_us()
+        desc = tr.engine.describe().strip().split("\n")
+        print("== %s: %.1f us/step (launch avg), last-step phase sum %.1f us, %d phases" %
+              (name, e0.elapsed_time(e1) * 1000 / 200, us.sum(), len(us)))
+        for t, d in zip(us, desc):
+            print("  %7.2f us  %s" % (t, d))
+
+
+if __name__ == "__main__":
+    main()
