@@ -229,7 +229,10 @@ def main():
     ap.add_argument("--workload", default="sac_hopper", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", type=int, default=None, help="GEMM mode: 0 fp32 SIMT, 1 TF32, 3 3xTF32 (default: library default)")
     args = ap.parse_args()
+    if args.precision is not None:
+        os.environ["ILSW_GEMM_PRECISION"] = str(args.precision)
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -25,7 +25,7 @@ class Mlp(C.Structure):
 
 class TrainerConfig(C.Structure):
     _fields_ = [("algo", C.c_int), ("obs_dim", C.c_int), ("act_dim", C.c_int), ("batch", C.c_int),
-                ("max_steps_per_call", C.c_int),
+                ("max_steps_per_call", C.c_int), ("gemm_precision", C.c_int),
                 ("reward_scale", C.c_double), ("discount", C.c_double), ("soft_target_tau", C.c_double),
                 ("policy_lr", C.c_double), ("qf_lr", C.c_double), ("vf_lr", C.c_double), ("alpha_lr", C.c_double),
                 ("beta_1", C.c_double), ("beta_2", C.c_double), ("adam_eps", C.c_double),

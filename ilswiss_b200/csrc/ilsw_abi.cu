@@ -252,6 +252,7 @@ struct ilsw_trainer {
   size_t scratch_bytes;
   BarrierState* bar;
   int grid;
+  size_t smem_bytes;
   int t[kMaxNets];
   int n_total;
   int last_steps;
@@ -287,6 +288,7 @@ static int trainer_build(ilsw_trainer* tr) {
   memset(&d, 0, sizeof(d));
   d.log_alpha = log(tr->spec.cfg.alpha > 0 ? tr->spec.cfg.alpha : 1.0);
   d.alpha = (float)exp(d.log_alpha);
+  d.alpha_p1 = d.alpha_p2 = 1.0;
   CU(cudaMemcpy(tr->host_prog.ctx.dyn, &d, sizeof(d), cudaMemcpyHostToDevice));
   return ILSW_OK;
 }
@@ -309,7 +311,11 @@ extern "C" int ilsw_trainer_create(ilsw_trainer** out, const ilsw_trainer_config
   if (e == cudaSuccess) e = cudaMemset(tr->bar, 0, sizeof(BarrierState));
   if (e != cudaSuccess) { ilsw_trainer_destroy(tr); return fail(ILSW_ERR_CUDA, "barrier alloc: %s", cudaGetErrorString(e)); }
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ilsw_engine_kernel, kThreads, 0);
+  tr->smem_bytes = (size_t)kTcSmemFloats * sizeof(float) + ((sizeof(Phase) * kMaxPhases + 15) & ~size_t(15)) +
+                   ((sizeof(Op) * (size_t)kMaxOps + 15) & ~size_t(15)) + sizeof(Ctx) + 64;
+  e = cudaFuncSetAttribute(ilsw_engine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr->smem_bytes);
+  if (e != cudaSuccess) { ilsw_trainer_destroy(tr); return fail(ILSW_ERR_CUDA, "engine smem opt-in (%zu B): %s", tr->smem_bytes, cudaGetErrorString(e)); }
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ilsw_engine_kernel, kThreads, tr->smem_bytes);
   if (e != cudaSuccess || per_sm < 1) { ilsw_trainer_destroy(tr); return fail(ILSW_ERR_CUDA, "engine kernel cannot be resident (%s)", cudaGetErrorString(e)); }
   tr->grid = sms;  // persistent: one CTA per SM
   const char* g = getenv("ILSW_GRID");
@@ -390,7 +396,9 @@ extern "C" int ilsw_train(ilsw_trainer* tr, ilsw_rb* policy_rb, ilsw_rb* expert_
   const Program* dp = tr->dev_prog;
   BarrierState* bar = tr->bar;
   void* args[] = {(void*)&dp, (void*)&a, (void*)&bar, (void*)&rp};
-  CU(cudaLaunchCooperativeKernel((void*)ilsw_engine_kernel, dim3(tr->grid), dim3(kThreads), args, 0, st));
+  const size_t smem = (size_t)kTcSmemFloats * sizeof(float) + ((sizeof(Phase) * kMaxPhases + 15) & ~size_t(15)) +
+                      ((sizeof(Op) * (size_t)tr->host_prog.n_ops + 15) & ~size_t(15)) + sizeof(Ctx) + 64;
+  CU(cudaLaunchCooperativeKernel((void*)ilsw_engine_kernel, dim3(tr->grid), dim3(kThreads), args, smem, st));
   tr->launches += 1;
   // host mirrors of the on-device counters
   tr->seq += (unsigned)(adam_t(a, tr->host_prog.ctx.hp, SLOT_POLICY, n_steps - 1) - a.t0[SLOT_POLICY]);
@@ -448,6 +456,8 @@ extern "C" int ilsw_set_state(ilsw_trainer* tr, const ilsw_state* in, void* stre
   memset(&d, 0, sizeof(d));
   d.log_alpha = in->log_alpha; d.alpha_m = in->alpha_exp_avg; d.alpha_v = in->alpha_exp_avg_sq; d.alpha_t = in->alpha_step;
   d.alpha = (float)exp(d.log_alpha);
+  d.alpha_p1 = pow(tr->host_prog.ctx.hp.beta1, (double)d.alpha_t);
+  d.alpha_p2 = pow(tr->host_prog.ctx.hp.beta2, (double)d.alpha_t);
   CU(cudaMemcpyAsync(tr->host_prog.ctx.dyn, &d, sizeof(d), cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));
   for (int i = 0; i < 8; ++i) tr->t[i] = in->adam_step[i];

@@ -49,30 +49,45 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 constexpr long long kSpinLimit = 4000000000LL;  // ~2 s at 2 GHz: a hung peer/CTA aborts the launch
 
 // Sense-reversal grid barrier (all CTAs are co-resident: cooperative launch, 1 CTA / SM).
+// Arrival is ONE atom.add.acq_rel.gpu (release of this CTA's phase writes, cumulative over the
+// preceding bar.sync), departure ONE ld.acquire.gpu poll loop: two L2 round trips, no membar.sc.
 // Returns false if the launch was aborted (timeout); every thread of every CTA then exits.
+__device__ __forceinline__ unsigned atom_add_acq_rel_gpu(unsigned* p, unsigned v) {
+  unsigned r;
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ bool grid_barrier(BarrierState* bar, unsigned nblocks, unsigned& gen, int* abort_flag) {
   __shared__ int s_ok;
   __syncthreads();
   if (threadIdx.x == 0) {
     int ok = 1;
     const unsigned target = gen + 1;
-    __threadfence();  // release this CTA's writes (also invalidates L1 on sm_100)
-    unsigned prev = atomicAdd(&bar->count, 1u);
+    unsigned prev = atom_add_acq_rel_gpu(&bar->count, 1u);
     if (prev == nblocks - 1) {
-      atomicExch(&bar->count, 0u);
-      __threadfence();
-      atomicExch(&bar->gen, target);
+      st_relaxed_gpu(&bar->count, 0u);
+      st_release_gpu(&bar->gen, target);
     } else {
-      long long t0 = clock64();
+      long long t0 = 0;
+      unsigned spins = 0;
       while (ld_acquire_gpu(&bar->gen) != target) {
-        long long dt = clock64() - t0;
-        if (dt > kSpinLimit) {
-          if (*(volatile int*)abort_flag) { ok = 0; break; }
-          if (dt > 2 * kSpinLimit) { atomicExch(abort_flag, 1); ok = 0; break; }
+        if ((++spins & 1023u) == 0u) {
+          if (t0 == 0) t0 = clock64();
+          long long dt = clock64() - t0;
+          if (dt > kSpinLimit) {
+            if (*(volatile int*)abort_flag) { ok = 0; break; }
+            if (dt > 2 * kSpinLimit) { atomicExch(abort_flag, 1); ok = 0; break; }
+          }
         }
       }
     }
-    __threadfence();
     s_ok = ok;
   }
   __syncthreads();
@@ -242,6 +257,161 @@ __device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* 
 }
 
 // ------------------------------------------------------------------------------------------
+// TF32 tensor-core GEMM tile (speed mode; mma.sync.m16n8k8, fp32 accumulate).
+// 32x32 outputs per CTA job; the WHOLE K panel (<=256 per stage) of both operands is brought
+// from L2 into shared memory with 16-byte cp.async.cg in one shot (one L2 round trip per
+// stage instead of one per 32-wide chunk), double-buffered when K > 256.  Each of the 8 warps
+// owns a 16x8 accumulator fragment over the full K.  Shared layouts are chosen per operand so
+// that BOTH the 128-bit fill and the fragment reads are bank-conflict free:
+//   k-contiguous operand  -> [32 rows][260]   (fragment bank = 4*row + k  = lane)
+//   m/n-contiguous operand -> [256 k][40]     (fragment bank = 8*k  + row = lane-permutation)
+// mode 1: single-pass TF32 (operands rounded with cvt.rna);  mode 3: 3xTF32 split
+// (hi/lo, small terms first) which recovers fp32-level accuracy on the tensor cores.
+// ------------------------------------------------------------------------------------------
+constexpr int kKC = 256;                      // K per stage
+constexpr int kKS = kKC + 4;                  // row stride of a k-contiguous panel
+constexpr int kMS = 40;                       // row stride of an m/n-contiguous panel
+constexpr int kOperandFloats = kKC * kMS;     // 10240 floats (>= 32*kKS = 8320)
+constexpr int kTcStageFloats = 2 * kOperandFloats;
+constexpr int kTcSmemFloats = 2 * kTcStageFloats;   // 2 stages x (A,B) = 160 KB
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t cvt_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// Fill one K stage of operand A (rows = m) or B (rows = n) into shared memory.
+//   contig_k: element(row, k) = base[row*ld + k]  -> smem[row*kKS + k]
+//   else    : element(row, k) = base[k*ld + row]  -> smem[k*kMS + row]
+// vec: 16-byte cp.async path allowed (aligned base, ld % 4 == 0, dims % 4 == 0, no aug column)
+template <bool IS_B>
+__device__ __forceinline__ void tc_fill(const GemmOp& o, float* sm, int row0, int k0, int klen, bool vec) {
+  const int tid = threadIdx.x;
+  const bool contig_k = IS_B ? !o.b_nc : !o.a_mc;
+  const float* base = IS_B ? o.B : o.A;
+  const int ld = IS_B ? o.ldb : o.lda;
+  const int R = IS_B ? o.N : o.M;           // real rows (aug column handled by the scalar path)
+  if (vec) {
+    if (contig_k) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int v = tid + i * kThreads, r = v >> 6, k = (v & 63) << 2;
+        const bool in = (row0 + r < R) && (k < klen);
+        const float* src = in ? base + (size_t)(row0 + r) * ld + k0 + k : base;
+        cp_async16(sm + r * kKS + k, src, in ? 16 : 0);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int v = tid + i * kThreads, k = v >> 3, r = (v & 7) << 2;
+        const bool in = (k < klen) && (row0 + r < R);
+        const float* src = in ? base + (size_t)(k0 + k) * ld + row0 + r : base;
+        cp_async16(sm + k * kMS + r, src, in ? 16 : 0);
+      }
+    }
+  } else {
+    const int Rt = IS_B ? o.N + o.aug_ones : o.M;
+    const int kpad = (klen + 7) & ~7;      // zero padded to the MMA k granularity
+    if (contig_k) {
+      for (int e = tid; e < 32 * kpad; e += kThreads) {
+        const int r = e / kpad, k = e - r * kpad;
+        float v = 0.f;
+        if (row0 + r < Rt && k < klen) v = IS_B ? gemm_B(o, k0 + k, row0 + r) : gemm_A(o, row0 + r, k0 + k);
+        sm[r * kKS + k] = v;
+      }
+    } else {
+      for (int e = tid; e < 32 * kpad; e += kThreads) {
+        const int k = e >> 5, r = e & 31;
+        float v = 0.f;
+        if (row0 + r < Rt && k < klen) v = IS_B ? gemm_B(o, k0 + k, row0 + r) : gemm_A(o, row0 + r, k0 + k);
+        sm[k * kMS + r] = v;
+      }
+    }
+  }
+}
+
+__device__ __noinline__ void gemm_tile_tc(const GemmOp& o, int tile, float* smem, int mode) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tm = tile / o.tiles_n, tn = tile - tm * o.tiles_n;
+  const int m0 = tm * 32, n0 = tn * 32;
+  const int mb = warp >> 2, nb = warp & 3;
+  const int g = lane >> 2, q = lane & 3;
+  const bool a_kc = !o.a_mc, b_kc = !o.b_nc;
+  const bool vecA = ((o.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(o.A) & 15) == 0) && ((o.K & 3) == 0) && ((o.M & 3) == 0);
+  const bool vecB = ((o.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(o.B) & 15) == 0) && ((o.K & 3) == 0) && ((o.N & 3) == 0) &&
+                    !(o.aug_ones && n0 + 32 > o.N);
+  const int nstages = (o.K + kKC - 1) / kKC;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  // prologue: stage 0
+  tc_fill<false>(o, smem, m0, 0, min(kKC, o.K), vecA);
+  tc_fill<true>(o, smem + kOperandFloats, n0, 0, min(kKC, o.K), vecB);
+  cp_async_commit();
+  for (int st = 0; st < nstages; ++st) {
+    float* As = smem + (st & 1) * kTcStageFloats;
+    float* Bs = As + kOperandFloats;
+    if (st + 1 < nstages) {
+      float* An = smem + ((st + 1) & 1) * kTcStageFloats;
+      const int k0 = (st + 1) * kKC, klen = min(kKC, o.K - k0);
+      tc_fill<false>(o, An, m0, k0, klen, vecA);
+      tc_fill<true>(o, An + kOperandFloats, n0, k0, klen, vecB);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int klen = min(kKC, o.K - st * kKC);
+    const int ksteps = (klen + 7) >> 3;       // panel is zero padded up to the stage length
+    // fragment base addresses
+    const float* a_lo = a_kc ? As + (mb * 16 + g) * kKS + q : As + q * kMS + mb * 16 + g;
+    const float* b_p = b_kc ? Bs + (nb * 8 + g) * kKS + q : Bs + q * kMS + nb * 8 + g;
+    const int a_row8 = a_kc ? 8 * kKS : 8, a_k4 = a_kc ? 4 : 4 * kMS, a_k8 = a_kc ? 8 : 8 * kMS;
+    const int b_k4 = b_kc ? 4 : 4 * kMS, b_k8 = b_kc ? 8 : 8 * kMS;
+#pragma unroll 4
+    for (int ks = 0; ks < ksteps; ++ks) {
+      float af[4], bf[2];
+      af[0] = a_lo[0]; af[1] = a_lo[a_row8]; af[2] = a_lo[a_k4]; af[3] = a_lo[a_row8 + a_k4];
+      bf[0] = b_p[0]; bf[1] = b_p[b_k4];
+      a_lo += a_k8; b_p += b_k8;
+      uint32_t ah[4], bh[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ah[i] = cvt_tf32(af[i]);
+      bh[0] = cvt_tf32(bf[0]); bh[1] = cvt_tf32(bf[1]);
+      if (mode == 3) {
+        uint32_t al[4], bl[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) al[i] = cvt_tf32(af[i] - __uint_as_float(ah[i]));
+        bl[0] = cvt_tf32(bf[0] - __uint_as_float(bh[0])); bl[1] = cvt_tf32(bf[1] - __uint_as_float(bh[1]));
+        mma_tf32(acc, al, bh);
+        mma_tf32(acc, ah, bl);
+      }
+      mma_tf32(acc, ah, bh);
+    }
+    __syncthreads();   // stage buffer may be refilled by the next iteration's prefetch
+  }
+  const int Nt = o.N + o.aug_ones;
+  const int r0 = m0 + mb * 16 + g, c0 = n0 + nb * 8 + 2 * q;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = r0 + ((i & 2) ? 8 : 0), n = c0 + (i & 1);
+    if (m < o.M && n < Nt) gemm_epilogue(o, m, n, acc[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // replica exchange: every rank PUSHES its policy gradient into every rank's receive slot over
 // NVLink peer stores, then publishes a sequence number; the Adam job sums the slots in rank
 // order (bit-identical on all ranks) -- no NCCL call, no host round trip, fused into the step.
@@ -289,23 +459,63 @@ __device__ __forceinline__ float replica_reduced_grad(const Replica& rp, unsigne
 // ------------------------------------------------------------------------------------------
 // the engine
 // ------------------------------------------------------------------------------------------
+// Dynamic shared memory: [GEMM staging (kTcSmemFloats)] [program copy: phases, ops, ctx].
+// The program is immutable during a launch; keeping it in shared memory removes every L2 round
+// trip from job dispatch (the L1 is invalidated at each grid barrier).
+struct SmemProgram { const Phase* phases; const Op* ops; const Ctx* ctx; int n_phases; };
+
+__device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
 __global__ void __launch_bounds__(kThreads, 1)
 ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* bar, Replica rp) {
-  __shared__ __align__(16) float smem[kGemmSmemFloats];
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  float* smem = reinterpret_cast<float*>(dyn_smem);
   __shared__ AdamCoef s_coef;
   __shared__ unsigned s_gen;
-  const Ctx& c = prog->ctx;
-  int* abort_flag = &c.dyn->abort_flag;
+  __shared__ double s_p1[kMaxNets], s_p2[kMaxNets], s_b1[kMaxNets], s_b2[kMaxNets];   // running beta^t per Adam slot
+  __shared__ int s_pt[kMaxNets];
+  const int n_phases = prog->n_phases, n_ops = prog->n_ops;
+  unsigned char* pbase = dyn_smem + (size_t)kTcSmemFloats * sizeof(float);
+  Phase* s_phases = reinterpret_cast<Phase*>(pbase);
+  Op* s_ops = reinterpret_cast<Op*>(pbase + align16(sizeof(Phase) * kMaxPhases));
+  Ctx* s_ctx = reinterpret_cast<Ctx*>(reinterpret_cast<unsigned char*>(s_ops) + align16(sizeof(Op) * (size_t)n_ops));
+  {
+    const int* src; int* dst; int n;
+    src = reinterpret_cast<const int*>(prog->phases); dst = reinterpret_cast<int*>(s_phases); n = (int)(sizeof(Phase) * n_phases / 4);
+    for (int i = threadIdx.x; i < n; i += kThreads) dst[i] = src[i];
+    src = reinterpret_cast<const int*>(prog->ops); dst = reinterpret_cast<int*>(s_ops); n = (int)(sizeof(Op) * n_ops / 4);
+    for (int i = threadIdx.x; i < n; i += kThreads) dst[i] = src[i];
+    src = reinterpret_cast<const int*>(&prog->ctx); dst = reinterpret_cast<int*>(s_ctx); n = (int)(sizeof(Ctx) / 4);
+    for (int i = threadIdx.x; i < n; i += kThreads) dst[i] = src[i];
+  }
   if (threadIdx.x == 0) s_gen = ld_acquire_gpu(&bar->gen);
+  if (threadIdx.x < kMaxNets) { s_pt[threadIdx.x] = -1; }
   __syncthreads();
+  if (threadIdx.x == 0) {   // one pow() per optimiser per LAUNCH; afterwards beta^t is a running product
+    for (int i = 0; i < n_ops; ++i)
+      if (s_ops[i].kind == OP_ADAM) {
+        const AdamOp& ao = s_ops[i].adam;
+        s_b1[ao.slot] = ao.beta1; s_b2[ao.slot] = ao.beta2; s_pt[ao.slot] = a.t0[ao.slot];
+        s_p1[ao.slot] = pow(ao.beta1, (double)a.t0[ao.slot]); s_p2[ao.slot] = pow(ao.beta2, (double)a.t0[ao.slot]);
+      }
+  }
+  __syncthreads();
+  const Ctx& c = *s_ctx;
+  int* abort_flag = &c.dyn->abort_flag;
   unsigned gen = s_gen;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int prec = c.hp.gemm_precision;
 
   for (int s = 0; s < a.n_steps; ++s) {
     const bool stamp = (s == a.n_steps - 1) && blockIdx.x == 0 && threadIdx.x == 0;
     if (stamp) c.phase_ns[0] = globaltimer_ns();
-    for (int ph = 0; ph < prog->n_phases; ++ph) {
-      const Phase& P = prog->phases[ph];
+    if (threadIdx.x < kMaxNets && s_pt[threadIdx.x] >= 0) {
+      const int tn = adam_t(a, c.hp, threadIdx.x, s);
+      while (s_pt[threadIdx.x] < tn) { s_p1[threadIdx.x] *= s_b1[threadIdx.x]; s_p2[threadIdx.x] *= s_b2[threadIdx.x]; s_pt[threadIdx.x]++; }
+    }
+    __syncthreads();
+    for (int ph = 0; ph < n_phases; ++ph) {
+      const Phase& P = s_phases[ph];
       if (!phase_active(P, c.hp, a, s)) { if (stamp) c.phase_ns[ph + 1] = c.phase_ns[ph]; continue; }
       const bool exchange = P.collective && rp.world > 1;
       // exchange sequence number = number of policy updates so far (parity double-buffers the slots)
@@ -313,16 +523,17 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
       if (exchange && !replica_exchange(rp, xseq, bar, gen, abort_flag)) return;
       for (int job = blockIdx.x; job < P.total_jobs; job += gridDim.x) {
         int j = job, oi = P.op_begin;
-        while (j >= prog->ops[oi].n_jobs) { j -= prog->ops[oi].n_jobs; ++oi; }
-        const Op& o = prog->ops[oi];
+        while (j >= s_ops[oi].n_jobs) { j -= s_ops[oi].n_jobs; ++oi; }
+        const Op& o = s_ops[oi];
         if (o.kind == OP_GEMM) {
-          gemm_tile_device(o.gemm, j, smem);
+          if (prec == 0) gemm_tile_device(o.gemm, j, smem);
+          else gemm_tile_tc(o.gemm, j, smem, prec);
         } else if (o.kind == OP_ROW) {
           const int row = j * kRowsPerJob + warp;
           if (row < o.row.rows) run_row(c, a, o.row.kind, s, row, lane, 32);
         } else if (o.kind == OP_ADAM) {
           __syncthreads();
-          if (threadIdx.x == 0) s_coef = adam_coef(o.adam, adam_t(a, c.hp, o.adam.slot, s), a.world);
+          if (threadIdx.x == 0) s_coef = adam_coef_pw(o.adam, s_p1[o.adam.slot], s_p2[o.adam.slot], a.world);
           __syncthreads();
           const AdamCoef cf = s_coef;
           const int beg = j * kAdamChunk, end = min(o.adam.n, beg + kAdamChunk);

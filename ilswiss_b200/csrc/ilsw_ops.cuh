@@ -106,6 +106,19 @@ ILSW_HD float philox_uniform(uint64_t seed, uint32_t gstep, uint32_t row, uint32
 }
 
 // ------------------------------------------------------------------------------------------
+// operand rounding of the tensor-core modes (the host simulator applies the same rounding so
+// the precision of a mode can be evaluated against the oracle without a GPU)
+ILSW_HD float round_tf32(float x) {   // cvt.rna.tf32.f32: nearest, ties away, 10-bit mantissa
+  union { float f; uint32_t u; } v; v.f = x;
+  v.u = (v.u + 0x1000u) & 0xFFFFE000u;
+  return v.f;
+}
+ILSW_HD float round_bf16(float x) {   // cvt.rn.bf16.f32
+  union { float f; uint32_t u; } v; v.f = x;
+  v.u = (v.u + 0x7FFFu + ((v.u >> 16) & 1u)) & 0xFFFF0000u;
+  return v.f;
+}
+
 // GEMM operand accessors + epilogue (shared by the device tile kernel and the host simulator)
 // ------------------------------------------------------------------------------------------
 ILSW_HD float gemm_A(const GemmOp& o, int m, int k) {
@@ -152,11 +165,12 @@ ILSW_HD int adam_t(const RunArgs& a, const Hyper& hp, int slot, int s) {
   return a.t0[slot] + s + 1;
 }
 
-ILSW_HD AdamCoef adam_coef(const AdamOp& o, int t, int world) {
+// p1 = beta1^t, p2 = beta2^t
+ILSW_HD AdamCoef adam_coef_pw(const AdamOp& o, double p1, double p2, int world) {
   AdamCoef c;
   double b1 = o.beta1, b2 = o.beta2;
-  double bc1 = 1.0 - pow(b1, (double)t);
-  double bc2 = 1.0 - pow(b2, (double)t);
+  double bc1 = 1.0 - p1;
+  double bc2 = 1.0 - p2;
   c.w1 = (float)(1.0 - b1);
   c.one_m_w1 = 1.0f - c.w1;
   c.beta2 = (float)b2;
@@ -168,6 +182,9 @@ ILSW_HD AdamCoef adam_coef(const AdamOp& o, int t, int world) {
   c.tau = o.tau;
   c.one_m_tau = (float)(1.0 - (double)o.tau);
   return c;
+}
+ILSW_HD AdamCoef adam_coef(const AdamOp& o, int t, int world) {
+  return adam_coef_pw(o, pow(o.beta1, (double)t), pow(o.beta2, (double)t), world);
 }
 
 ILSW_HD void adam_elem_g(const AdamOp& o, const AdamCoef& c, int i, float g) {
@@ -368,9 +385,9 @@ ILSW_HD void row_sac_pibwd(const Ctx& c, const RunArgs& a, int s, int b, int lan
   const float invB = 1.0f / (float)B, invBA = 1.0f / (float)(B * A);
   for (int j = lane; j < A; j += nl) {
     float gA = ldg(S.dA[0] + (size_t)b * A + j) + ldg(S.dA[1] + (size_t)b * A + j);
-    float t = S.act[(size_t)r * A + j];
-    float mu = S.mean[(size_t)r * A + j], ls = S.lstd[(size_t)r * A + j], lr = S.lraw[(size_t)r * A + j];
-    float ep = S.eps[(size_t)r * A + j];
+    float t = ldg(S.act + (size_t)r * A + j);
+    float mu = ldg(S.mean + (size_t)r * A + j), ls = ldg(S.lstd + (size_t)r * A + j), lr = ldg(S.lraw + (size_t)r * A + j);
+    float ep = ldg(S.eps + (size_t)r * A + j);
     float om = 1.0f - t * t;
     float J = 2.0f * t * om / (om + 1e-6f);           // d/dz of -log(1 - tanh(z)^2 + 1e-6)
     float dz = gA * om + alpha * invB * J;
@@ -453,7 +470,8 @@ ILSW_HD void row_sac_final(const Ctx& c, const RunArgs& a, int s, int r, int lan
       double w = 1.0 - b1;
       d->alpha_m = (w < 0.5) ? d->alpha_m + w * (g - d->alpha_m) : g - (g - d->alpha_m) * (1.0 - w);
       d->alpha_v = d->alpha_v * b2 + (1.0 - b2) * g * g;
-      double bc1 = 1.0 - pow(b1, (double)d->alpha_t), bc2 = 1.0 - pow(b2, (double)d->alpha_t);
+      d->alpha_p1 *= b1; d->alpha_p2 *= b2;
+      double bc1 = 1.0 - d->alpha_p1, bc2 = 1.0 - d->alpha_p2;
       double denom = sqrt(d->alpha_v) / sqrt(bc2) + c.hp.adam_eps;
       d->log_alpha = d->log_alpha + (-(c.hp.alpha_lr / bc1)) * d->alpha_m / denom;
       d->alpha = (float)exp(d->log_alpha);
@@ -514,7 +532,7 @@ ILSW_HD void row_td3_pibwd(const Ctx& c, const RunArgs& a, int s, int b, int lan
   const MlpPtrs& P = c.policy;
   const int Hd = S.Hd, A = S.A;
   for (int j = lane; j < A; j += nl) {
-    float t = S.act[(size_t)b * A + j];
+    float t = ldg(S.act + (size_t)b * A + j);
     S.dmean[(size_t)b * A + j] = ldg(S.dA[0] + (size_t)b * A + j) * c.hp.max_act * (1.0f - t * t);
   }
   wsync();

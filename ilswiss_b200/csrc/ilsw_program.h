@@ -351,6 +351,7 @@ inline void build_td3(Builder& b, const Ctx& c) {
 inline Hyper make_hyper(const ilsw_trainer_config& cfg) {
   Hyper h; memset(&h, 0, sizeof(h));
   h.algo = cfg.algo;
+  h.gemm_precision = cfg.gemm_precision;
   h.reward_scale = (float)cfg.reward_scale; h.discount = (float)cfg.discount; h.tau = (float)cfg.soft_target_tau;
   h.policy_lr = cfg.policy_lr; h.qf_lr = cfg.qf_lr; h.vf_lr = cfg.vf_lr; h.alpha_lr = cfg.alpha_lr;
   h.beta1 = cfg.beta_1; h.beta2 = cfg.beta_2 > 0 ? cfg.beta_2 : 0.999; h.adam_eps = cfg.adam_eps > 0 ? cfg.adam_eps : 1e-8;

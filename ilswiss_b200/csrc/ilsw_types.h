@@ -135,6 +135,7 @@ struct DiscBufs {
 
 struct DynState {       // device-resident mutable scalars (persist across launches)
   double log_alpha, alpha_m, alpha_v;
+  double alpha_p1, alpha_p2;   // running beta1^t, beta2^t of the alpha optimiser (avoids pow() on the device)
   int alpha_t;
   float alpha;          // exp(log_alpha) as used by the fp32 graph
   int abort_flag;
@@ -143,6 +144,7 @@ struct DynState {       // device-resident mutable scalars (persist across launc
 
 struct Hyper {
   int algo;             // 1 sac_alpha, 2 td3, 3 sac_v
+  int gemm_precision;   // 0 fp32 (SIMT, parity gate), 1 tf32 tensor cores, 2 bf16 tensor cores, 3 3xtf32
   float reward_scale, discount, tau;
   double policy_lr, qf_lr, vf_lr, alpha_lr, beta1, beta2, adam_eps;
   float mean_reg, std_reg, target_entropy;

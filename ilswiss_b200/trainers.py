@@ -10,6 +10,7 @@ to views of the device parameter arenas the kernels update in place, so explorat
 evaluation policies and pickled snapshots keep seeing the trained weights.
 """
 import copy
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -18,6 +19,12 @@ import torch.optim as optim
 
 from . import _abi
 from .engine import NetArena, StepEngine, require_cuda
+
+
+def default_gemm_precision():
+    """0: fp32 SIMT tiles (exact parity gate); 1: TF32 tensor cores; 3: 3xTF32 tensor cores
+    (fp32-level accuracy).  Override with ILSW_GEMM_PRECISION or the trainers' gemm_precision=."""
+    return int(os.environ.get("ILSW_GEMM_PRECISION", "3"))
 
 
 def _stats(name, data):
@@ -151,7 +158,8 @@ class SoftActorCritic(_FusedTrainer):
     def __init__(self, policy, qf1, qf2, reward_scale=1.0, discount=0.99, policy_lr=1e-3, qf_lr=1e-3,
                  alpha_lr=3e-4, soft_target_tau=1e-2, alpha=0.2, train_alpha=True,
                  policy_mean_reg_weight=1e-3, policy_std_reg_weight=1e-3, optimizer_class=optim.Adam,
-                 beta_1=0.9, target_entropy=None, batch_size=256, max_steps_per_call=1000, **kwargs):
+                 beta_1=0.9, target_entropy=None, batch_size=256, max_steps_per_call=1000, gemm_precision=None,
+                 **kwargs):
         if optimizer_class is not optim.Adam:
             raise NotImplementedError("the fused step implements torch.optim.Adam only")
         self.policy, self.qf1, self.qf2 = policy, qf1, qf2
@@ -179,6 +187,7 @@ class SoftActorCritic(_FusedTrainer):
         self.alpha_optimizer = optim.Adam([self._log_alpha_param], lr=alpha_lr, betas=(beta_1, 0.999))
         cfg = _abi.TrainerConfig()
         cfg.algo = _abi.ALGO_SAC_ALPHA
+        cfg.gemm_precision = default_gemm_precision() if gemm_precision is None else int(gemm_precision)
         cfg.obs_dim, cfg.act_dim, cfg.batch = in_dim, act_dim, int(batch_size)
         cfg.max_steps_per_call = int(max_steps_per_call)
         cfg.reward_scale, cfg.discount, cfg.soft_target_tau = reward_scale, discount, soft_target_tau
@@ -271,7 +280,7 @@ class TD3(_FusedTrainer):
     def __init__(self, policy, qf1, qf2, reward_scale=1.0, discount=0.99, target_policy_noise=0.2,
                  target_policy_noise_clip=0.5, policy_lr=1e-3, qf_lr=1e-3, policy_and_target_update_period=2,
                  soft_target_tau=0.005, qf_criterion=None, optimizer_class=optim.Adam, batch_size=256,
-                 max_steps_per_call=1000, **kwargs):
+                 max_steps_per_call=1000, gemm_precision=None, **kwargs):
         if optimizer_class is not optim.Adam:
             raise NotImplementedError("the fused step implements torch.optim.Adam only")
         if qf_criterion is not None and not isinstance(qf_criterion, torch.nn.MSELoss):
@@ -294,6 +303,7 @@ class TD3(_FusedTrainer):
         self.policy_optimizer = optim.Adam(self.policy.parameters(), lr=policy_lr)
         cfg = _abi.TrainerConfig()
         cfg.algo = _abi.ALGO_TD3
+        cfg.gemm_precision = default_gemm_precision() if gemm_precision is None else int(gemm_precision)
         cfg.obs_dim, cfg.act_dim, cfg.batch = in_dim, act_dim, int(batch_size)
         cfg.max_steps_per_call = int(max_steps_per_call)
         cfg.reward_scale, cfg.discount, cfg.soft_target_tau = reward_scale, discount, soft_target_tau

@@ -98,6 +98,7 @@ typedef struct {
   int algo;                 /* ilsw_algo */
   int obs_dim, act_dim, batch;
   int max_steps_per_call;   /* capacity of the per-step loss log */
+  int gemm_precision;       /* 0: fp32 SIMT (exact parity gate); 1: TF32 tensor cores; 3: 3xTF32 (fp32-level) */
   /* SoftActorCritic.__init__ (sac_alpha.py:21-40) / TD3.__init__ (td3.py:20-36) */
   double reward_scale, discount, soft_target_tau;
   double policy_lr, qf_lr, vf_lr, alpha_lr;

@@ -63,9 +63,10 @@ def case_injection(case, steps=None):
     return out
 
 
-def trainer_config(case, max_steps=64):
+def trainer_config(case, max_steps=64, precision=0):
     algo = case["algo"]
     cfg = _abi.TrainerConfig()
+    cfg.gemm_precision = precision
     cfg.obs_dim, cfg.act_dim, cfg.batch = case["obs_dim"], case["act_dim"], case["batch"]
     cfg.max_steps_per_call = max_steps
     cfg.beta_2, cfg.adam_eps = 0.999, 1e-8
@@ -228,7 +229,7 @@ class HostSimRun:
         self.lib.hs_destroy(self.h)
 
 
-def assert_params_close(got, ref, steps, lr=3e-4, msg=""):
+def assert_params_close(got, ref, steps, lr=3e-4, msg="", frac=5e-4):
     """Parameter parity bar.  <=1e-5 abs for all but a vanishing fraction of
     elements: Adam's normalised update m/(sqrt(v)+eps) is +-lr in the first steps REGARDLESS of
     |g|, so an element whose true gradient is ~0 (|g| ~ 1e-9, pure summation-order noise) can
@@ -239,7 +240,7 @@ def assert_params_close(got, ref, steps, lr=3e-4, msg=""):
     assert got.shape == ref.shape, (msg, got.shape, ref.shape)
     diff = np.abs(got - ref)
     bad = int((diff > 1e-5).sum())
-    assert bad <= max(2, int(5e-4 * diff.size)), (msg, bad, diff.size, float(diff.max()))
+    assert bad <= max(2, int(frac * diff.size)), (msg, bad, diff.size, float(diff.max()))
     assert float(diff.max()) <= 2.0 * lr * steps + 1e-6, (msg, float(diff.max()))
 
 
@@ -249,7 +250,7 @@ def assert_params_close(got, ref, steps, lr=3e-4, msg=""):
 class DeviceRun:
     """Runs one parity case on the GPU through ilswiss_b200.engine (C ABI) with injected randomness."""
 
-    def __init__(self, case, max_steps=64):
+    def __init__(self, case, max_steps=64, precision=0):
         from ilswiss_b200 import engine
 
         self.case = case
@@ -266,7 +267,7 @@ class DeviceRun:
             dnet = engine.NetArena(i_d, h_d, o_d, ls, init=arenas["disc"])
             self.nets["disc"] = dnet
             dcfg = disc_config(case)
-        self.eng = engine.StepEngine(trainer_config(case, max_steps), [self.nets[n] for n in order], dcfg, dnet)
+        self.eng = engine.StepEngine(trainer_config(case, max_steps, precision), [self.nets[n] for n in order], dcfg, dnet)
         data, edata = case_data(case)
         O, A = case["obs_dim"], case["act_dim"]
         self.ring = engine.ReplayRing(case["n_fill"], O, A)

@@ -31,7 +31,13 @@ static void run_op(const Program& P, const Op& o, const RunArgs& a, int s) {
     for (int m = 0; m < g.M; ++m)
       for (int n = 0; n < Nt; ++n) {
         float acc = 0.f;
-        for (int k = 0; k < g.K; ++k) acc += gemm_A(g, m, k) * gemm_B(g, k, n);
+        const int prec = c.hp.gemm_precision;
+        for (int k = 0; k < g.K; ++k) {
+          float x = gemm_A(g, m, k), y = gemm_B(g, k, n);
+          if (prec == 1) { x = round_tf32(x); y = round_tf32(y); }
+          else if (prec == 2) { x = round_bf16(x); y = round_bf16(y); }
+          acc += x * y;
+        }
         gemm_epilogue(g, m, n, acc);
       }
   } else if (o.kind == OP_ROW) {
@@ -71,6 +77,7 @@ void* hs_create(const ilsw_trainer_config* cfg, const ilsw_mlp* nets, int n_nets
   memset(d, 0, sizeof(*d));
   d->log_alpha = log(cfg->alpha);
   d->alpha = (float)exp(d->log_alpha);
+  d->alpha_p1 = d->alpha_p2 = 1.0;
   memset(h->t, 0, sizeof(h->t));
   h->n_total = 0;
   return h;
@@ -109,6 +116,7 @@ int hs_train(void* p, const float* ring, int stride, int size, const float* erin
   return 0;
 }
 
+void hs_set_precision(void* p, int prec) { ((HostSim*)p)->prog.ctx.hp.gemm_precision = prec; }
 const float* hs_losses(void* p) { return ((HostSim*)p)->prog.ctx.loss_log; }
 const float* hs_stats(void* p) { return ((HostSim*)p)->prog.ctx.stats; }
 int hs_stats_floats(void* p) { return ((HostSim*)p)->prog.ctx.stats_floats; }

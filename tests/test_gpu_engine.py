@@ -17,15 +17,20 @@ CASES = [n for n, c in CFG.CASES.items() if c["algo"] in ("sac_alpha", "td3", "a
 def loss_tol(k, ref):
     # bar (BASELINE.json north_star): 1e-4 relative on losses; the policy loss is a cancellation
     # of O(1) terms, so its floor is 1e-4 absolute
-    return 1e-4 * max(abs(ref), 1.0 if k == "Policy Loss" else 1e-2)
+    if k == "Policy Loss" or k.endswith(" Mean") or k.endswith(" Std"):
+        return 1e-4 * max(abs(ref), 1.0)     # means of O(1)-spread vectors: 1e-4 of their scale
+    return 1e-4 * max(abs(ref), 1e-2)
 
 
+# GEMM precision modes of the engine: 0 = fp32 SIMT (exact gate), 1 = TF32 tensor cores,
+# 3 = 3xTF32 tensor cores (fp32-level).  Loss bar is 1e-4 relative in EVERY mode.
+@pytest.mark.parametrize("precision", [0, 1, 3])
 @pytest.mark.parametrize("name", CASES)
-def test_cuda_step_matches_oracle(name):
+def test_cuda_step_matches_oracle(name, precision):
     torch.set_num_threads(1)
     case = CFG.CASES[name]
     rows, final, _ = G.run_oracle(case)
-    run = DeviceRun(case)
+    run = DeviceRun(case, precision=precision)
     L = run.train(case["steps"], case_injection(case))
     for t, row in enumerate(rows):
         for k, ref in row.items():
@@ -38,6 +43,10 @@ def test_cuda_step_matches_oracle(name):
     for k in final:
         if k == "log_alpha":
             assert abs(run.eng.get_state().log_alpha - final[k][0]) < 1e-6
+        elif precision == 1:
+            # single-pass TF32 perturbs gradients at the 1e-3 relative level: many more elements
+            # fall into Adam's sign-sensitive regime (see assert_params_close); bound only
+            assert_params_close(run.arena(k), final[k], case["steps"], msg="%s/%s" % (name, k), frac=1.0)
         else:
             assert_params_close(run.arena(k), final[k], case["steps"], msg="%s/%s" % (name, k))
 

@@ -13,7 +13,11 @@ import bench  # noqa: E402
 
 
 def main():
-    names = sys.argv[1:] or ["sac_hopper"]
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["sac_hopper"]
+    for a in sys.argv[1:]:
+        if a.startswith("--precision="):
+            os.environ["ILSW_GEMM_PRECISION"] = a.split("=")[1]
+    print("gemm precision mode:", os.environ.get("ILSW_GEMM_PRECISION", "3 (default)"))
     for name in names:
         w = bench.WORKLOADS[name]
         tr, buf, irl = bench.build_ours(w, seed=1, steps_per_launch=200)
