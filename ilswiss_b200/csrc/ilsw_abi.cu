@@ -503,7 +503,7 @@ extern "C" int ilsw_replica_export(ilsw_trainer* tr, void* handle_out) {
   static_assert(sizeof(cudaIpcMemHandle_t) <= ILSW_IPC_HANDLE_BYTES, "handle size");
   const int n = tr->host_prog.ctx.policy.n_params;
   if (!tr->ipc_buf) {
-    tr->ipc_bytes = kFlagBytes + (size_t)2 * 8 * n * sizeof(float);
+    tr->ipc_bytes = kFlagBytes + (size_t)2 * 8 * round_up(n, 4) * sizeof(float);
     CU(cudaMalloc(&tr->ipc_buf, tr->ipc_bytes));
     CU(cudaMemset(tr->ipc_buf, 0, tr->ipc_bytes));
     CU(cudaDeviceSynchronize());
@@ -521,7 +521,7 @@ extern "C" int ilsw_replica_connect(ilsw_trainer* tr, int rank, int world, const
   const int n = tr->host_prog.ctx.policy.n_params;
   Replica& rp = tr->rep;
   memset(&rp, 0, sizeof(rp));
-  rp.world = world; rp.rank = rank; rp.n = n;
+  rp.world = world; rp.rank = rank; rp.n = n; rp.nstride = round_up(n, 4);
   rp.grad = tr->host_prog.ctx.policy.g;
   for (int r = 0; r < world; ++r) {
     void* base = nullptr;

@@ -18,6 +18,7 @@ struct BarrierState { unsigned count; unsigned gen; unsigned pad[30]; };
 struct Replica {
   int world, rank;
   int n;                      // policy parameter count
+  int nstride;                // slot stride (n rounded up to 4 floats: 16-byte aligned slots)
   const float* grad;          // local policy gradient arena
   float* recv_local;          // [2][world][n]  (parity, source rank)
   float* recv_peer[8];        // recv_local of every rank (self included)
@@ -418,7 +419,7 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& o, int tile, float* smem
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool replica_exchange(const Replica& rp, unsigned seq, BarrierState* bar, unsigned& gen, int* abort_flag) {
   const int parity = (int)(seq & 1u);
-  const size_t slot = ((size_t)parity * rp.world + rp.rank) * (size_t)rp.n;
+  const size_t slot = ((size_t)parity * rp.world + rp.rank) * (size_t)rp.nstride;
   const int n4 = rp.n >> 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     float4 v = __ldcg(reinterpret_cast<const float4*>(rp.grad) + i);
@@ -450,9 +451,9 @@ __device__ __forceinline__ bool replica_exchange(const Replica& rp, unsigned seq
 }
 
 __device__ __forceinline__ float replica_reduced_grad(const Replica& rp, unsigned seq, int i) {
-  const size_t base = (size_t)(seq & 1u) * rp.world * (size_t)rp.n;
+  const size_t base = (size_t)(seq & 1u) * rp.world * (size_t)rp.nstride;
   float g = 0.f;
-  for (int r = 0; r < rp.world; ++r) g += __ldcv(rp.recv_local + base + (size_t)r * rp.n + i);
+  for (int r = 0; r < rp.world; ++r) g += __ldcv(rp.recv_local + base + (size_t)r * rp.nstride + i);
   return g;
 }
 
