@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include "ilsw_ops.cuh"
+#include "ilsw_rows_fast.cuh"
 
 namespace ilsw {
 
@@ -246,13 +247,24 @@ __device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* 
   __syncthreads();
   const int Nt = o.N + o.aug_ones;
   const int m = m0 + ty * 4 + kg;
+  EpiIn ein[4];
+  float vout[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + tx * 4 + j;
+    if (m < o.M && n < Nt) ein[j] = epi_load(o, m, n);
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float v = 0.f;
 #pragma unroll
     for (int g = 0; g < 4; ++g) v += red[(g * 64 + t) * 17 + kg * 4 + j];
+    vout[j] = v;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
     const int n = n0 + tx * 4 + j;
-    if (m < o.M && n < Nt) gemm_epilogue(o, m, n, v);
+    if (m < o.M && n < Nt) epi_store(o, m, n, vout[j], ein[j]);
   }
   __syncthreads();
 }
@@ -360,6 +372,15 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& o, int tile, float* smem
   tc_fill<false>(o, smem, m0, 0, min(kKC, o.K), vecA);
   tc_fill<true>(o, smem + kOperandFloats, n0, 0, min(kKC, o.K), vecB);
   cp_async_commit();
+  // epilogue inputs (bias / mask source / previous value) are fetched while the panels are in flight
+  const int Nt = o.N + o.aug_ones;
+  const int r0 = m0 + mb * 16 + g, c0 = n0 + nb * 8 + 2 * q;
+  EpiIn ein[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = r0 + ((i & 2) ? 8 : 0), n = c0 + (i & 1);
+    if (m < o.M && n < Nt) ein[i] = epi_load(o, m, n);
+  }
   for (int st = 0; st < nstages; ++st) {
     float* As = smem + (st & 1) * kTcStageFloats;
     float* Bs = As + kOperandFloats;
@@ -403,12 +424,10 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& o, int tile, float* smem
     }
     __syncthreads();   // stage buffer may be refilled by the next iteration's prefetch
   }
-  const int Nt = o.N + o.aug_ones;
-  const int r0 = m0 + mb * 16 + g, c0 = n0 + nb * 8 + 2 * q;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = r0 + ((i & 2) ? 8 : 0), n = c0 + (i & 1);
-    if (m < o.M && n < Nt) gemm_epilogue(o, m, n, acc[i]);
+    if (m < o.M && n < Nt) epi_store(o, m, n, acc[i], ein[i]);
   }
 }
 
@@ -506,6 +525,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
   unsigned gen = s_gen;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int prec = c.hp.gemm_precision;
+  const bool fast_rows = fast_rows_ok(c);
 
   for (int s = 0; s < a.n_steps; ++s) {
     const bool stamp = (s == a.n_steps - 1) && blockIdx.x == 0 && threadIdx.x == 0;
@@ -530,8 +550,11 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
           if (prec == 0) gemm_tile_device(o.gemm, j, smem);
           else gemm_tile_tc(o.gemm, j, smem, prec);
         } else if (o.kind == OP_ROW) {
-          const int row = j * kRowsPerJob + warp;
-          if (row < o.row.rows) run_row(c, a, o.row.kind, s, row, lane, 32);
+          RowEnv env; env.lane = lane; env.nl = 32; env.warp = warp; env.sm = smem;
+          if (!(fast_rows && run_row_job_fast(c, a, o.row.kind, o.row.rows, s, j, env))) {
+            const int row = j * kRowsPerJob + warp;
+            if (row < o.row.rows) run_row(c, a, o.row.kind, s, row, lane, 32);
+          }
         } else if (o.kind == OP_ADAM) {
           __syncthreads();
           if (threadIdx.x == 0) s_coef = adam_coef_pw(o.adam, s_p1[o.adam.slot], s_p2[o.adam.slot], a.world);
@@ -539,13 +562,47 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
           const AdamCoef cf = s_coef;
           const int beg = j * kAdamChunk, end = min(o.adam.n, beg + kAdamChunk);
           const bool reduced = exchange && o.adam.grad_scale_world;
-          for (int i = beg + threadIdx.x; i < end; i += kThreads) {
-            float g = reduced ? replica_reduced_grad(rp, xseq, i) : __ldcg(o.adam.g + i);
-            adam_elem_g(o.adam, cf, i, g * cf.gscale);
+          {  // 8 elements per thread: ALL loads first, then the arithmetic, then the stores
+            constexpr int E = kAdamChunk / kThreads;
+            float g[E], m[E], v[E], p[E], tg[E];
+            const AdamOp& ao = o.adam;
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+              const int i = beg + threadIdx.x + u * kThreads;
+              if (i < end) {
+                g[u] = (reduced ? replica_reduced_grad(rp, xseq, i) : __ldcg(ao.g + i)) * cf.gscale;
+                m[u] = ao.m[i]; v[u] = ao.v[i]; p[u] = ao.p[i];
+                tg[u] = ao.target ? ao.target[i] : 0.f;
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+              const int i = beg + threadIdx.x + u * kThreads;
+              if (i < end) {
+                float mm = (cf.w1 < 0.5f) ? m[u] + cf.w1 * (g[u] - m[u]) : g[u] - (g[u] - m[u]) * cf.one_m_w1;
+                float vv = v[u] * cf.beta2 + cf.one_m_beta2 * g[u] * g[u];
+                float denom = sqrtf(vv) / cf.bc2_sqrt + cf.eps;
+                float pp = p[u] + cf.neg_step * mm / denom;
+                ao.m[i] = mm; ao.v[i] = vv; ao.p[i] = pp;
+                if (ao.target) ao.target[i] = tg[u] * cf.one_m_tau + pp * cf.tau;
+              }
+            }
           }
         } else if (o.kind == OP_POLYAK) {
           const int beg = j * kAdamChunk, end = min(o.polyak.n, beg + kAdamChunk);
-          for (int i = beg + threadIdx.x; i < end; i += kThreads) polyak_elem(o.polyak, i);
+          constexpr int E = kAdamChunk / kThreads;
+          float tv[E], sv[E];
+          const float om = (float)(1.0 - (double)o.polyak.tau);
+#pragma unroll
+          for (int u = 0; u < E; ++u) {
+            const int i = beg + threadIdx.x + u * kThreads;
+            if (i < end) { tv[u] = o.polyak.target[i]; sv[u] = __ldcg(o.polyak.src + i); }
+          }
+#pragma unroll
+          for (int u = 0; u < E; ++u) {
+            const int i = beg + threadIdx.x + u * kThreads;
+            if (i < end) o.polyak.target[i] = tv[u] * om + sv[u] * o.polyak.tau;
+          }
         }
       }
       if (!grid_barrier(bar, gridDim.x, gen, abort_flag)) return;

@@ -128,26 +128,37 @@ ILSW_HD float gemm_B(const GemmOp& o, int k, int n) {
   if (o.aug_ones && n == o.N) return 1.0f;
   return ldg(o.B + (o.b_nc ? (size_t)k * o.ldb + n : (size_t)n * o.ldb + k));
 }
-ILSW_HD void gemm_epilogue(const GemmOp& o, int m, int n, float v) {
+// The epilogue is split into a LOAD half and a STORE half so that a tile can issue the loads of
+// all its outputs (bias, mask source, previous value) before any store: a store between two
+// loads would serialise them into separate L2 round trips.
+struct EpiIn { float bias, h, prev; };
+ILSW_HD EpiIn epi_load(const GemmOp& o, int m, int n) {
+  EpiIn e; e.bias = 0.f; e.h = 0.f; e.prev = 0.f;
   if (o.aug_ones && n == o.N) {
-    if (o.accumulate) v += ldg(o.bias_out + m);
-    o.bias_out[m] = v;
+    if (o.accumulate) e.prev = ldg(o.bias_out + m);
+    return e;
+  }
+  if (o.bias) e.bias = ldg(o.bias + n);
+  if (o.mask != ACT_NONE) e.h = ldg(o.H + (size_t)m * o.ldh + n);
+  if (o.accumulate) e.prev = ldg(o.C + (size_t)m * o.ldc + n);
+  return e;
+}
+ILSW_HD void epi_store(const GemmOp& o, int m, int n, float v, const EpiIn& e) {
+  if (o.aug_ones && n == o.N) {
+    o.bias_out[m] = o.accumulate ? v + e.prev : v;
     return;
   }
-  if (o.bias) v += ldg(o.bias + n);
+  if (o.bias) v += e.bias;
   if (o.act == ACT_RELU) v = v > 0.f ? v : 0.f;
   else if (o.act == ACT_TANH) v = tanhf(v);
-  size_t ci = (size_t)m * o.ldc + n;
+  const size_t ci = (size_t)m * o.ldc + n;
   if (o.C2) o.C2[ci] = v;
-  if (o.mask == ACT_RELU) {
-    v = ldg(o.H + (size_t)m * o.ldh + n) > 0.f ? v : 0.f;
-  } else if (o.mask == ACT_TANH) {
-    float h = ldg(o.H + (size_t)m * o.ldh + n);
-    v *= (1.0f - h * h);
-  }
-  if (o.accumulate) v += ldg(o.C + ci);
+  if (o.mask == ACT_RELU) v = e.h > 0.f ? v : 0.f;
+  else if (o.mask == ACT_TANH) v *= (1.0f - e.h * e.h);
+  if (o.accumulate) v += e.prev;
   o.C[ci] = v;
 }
+ILSW_HD void gemm_epilogue(const GemmOp& o, int m, int n, float v) { epi_store(o, m, n, v, epi_load(o, m, n)); }
 
 // ------------------------------------------------------------------------------------------
 // Adam / Polyak element kernels
@@ -730,7 +741,7 @@ ILSW_HD void row_disc_reward_final(const Ctx& c, const RunArgs& a, int s, int r,
 }
 
 // ---- dispatcher --------------------------------------------------------------------------
-ILSW_HD void run_row(const Ctx& c, const RunArgs& a, int kind, int s, int r, int lane, int nl) {
+ILSW_HDN void run_row(const Ctx& c, const RunArgs& a, int kind, int s, int r, int lane, int nl) {
   switch (kind) {
     case ROW_SAC_GATHER: case ROW_TD3_GATHER: row_sac_gather(c, a, s, r, lane, nl); break;
     case ROW_SAC_HEADS: row_sac_heads(c, a, s, r, lane, nl); break;

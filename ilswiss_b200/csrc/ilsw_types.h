@@ -11,8 +11,10 @@
 
 #if defined(__CUDACC__)
 #define ILSW_HD __host__ __device__ __forceinline__
+#define ILSW_HDN __host__ __device__ __noinline__
 #else
 #define ILSW_HD inline
+#define ILSW_HDN inline
 #endif
 
 namespace ilsw {

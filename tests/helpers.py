@@ -148,7 +148,7 @@ def load_hostsim():
     d = os.path.join(ROOT, "tests", "hostsim")
     so = os.path.join(d, "libilsw_hostsim.so")
     srcs = [os.path.join(d, "hostsim.cpp")] + [
-        os.path.join(ROOT, "ilswiss_b200", "csrc", f) for f in ("ilsw_ops.cuh", "ilsw_program.h", "ilsw_types.h")]
+        os.path.join(ROOT, "ilswiss_b200", "csrc", f) for f in ("ilsw_ops.cuh", "ilsw_rows_fast.cuh", "ilsw_program.h", "ilsw_types.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, srcs[0]])
     lib = C.CDLL(so)

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../ilswiss_b200/csrc/ilsw_ops.cuh"
+#include "../../ilswiss_b200/csrc/ilsw_rows_fast.cuh"
 #include "../../ilswiss_b200/csrc/ilsw_program.h"
 
 using namespace ilsw;
@@ -21,9 +22,11 @@ struct HostSim {
   TrainerSpec spec;
   int t[kMaxNets];
   int n_total;
+  int generic_rows;     // 1: force the generic per-row kernels (cross-check of the fast row jobs)
+  std::vector<float> rowbuf;
 };
 
-static void run_op(const Program& P, const Op& o, const RunArgs& a, int s) {
+static void run_op(HostSim* hs, const Program& P, const Op& o, const RunArgs& a, int s) {
   const Ctx& c = P.ctx;
   if (o.kind == OP_GEMM) {
     const GemmOp& g = o.gemm;
@@ -41,7 +44,14 @@ static void run_op(const Program& P, const Op& o, const RunArgs& a, int s) {
         gemm_epilogue(g, m, n, acc);
       }
   } else if (o.kind == OP_ROW) {
-    for (int r = 0; r < o.row.rows; ++r) run_row(c, a, o.row.kind, s, r, 0, 1);
+    const bool fast = !hs->generic_rows && fast_rows_ok(c);
+    for (int job = 0; job < o.n_jobs; ++job)
+      for (int w = 0; w < kRowsPerJob; ++w) {
+        RowEnv env; env.lane = 0; env.nl = 1; env.warp = w; env.sm = hs->rowbuf.data();
+        if (fast && run_row_job_fast(c, a, o.row.kind, o.row.rows, s, job, env)) continue;
+        const int r = job * kRowsPerJob + w;
+        if (r < o.row.rows) run_row(c, a, o.row.kind, s, r, 0, 1);
+      }
   } else if (o.kind == OP_ADAM) {
     AdamCoef cf = adam_coef(o.adam, adam_t(a, c.hp, o.adam.slot, s), a.world);
     for (int i = 0; i < o.adam.n; ++i) adam_elem(o.adam, cf, i);
@@ -80,6 +90,8 @@ void* hs_create(const ilsw_trainer_config* cfg, const ilsw_mlp* nets, int n_nets
   d->alpha_p1 = d->alpha_p2 = 1.0;
   memset(h->t, 0, sizeof(h->t));
   h->n_total = 0;
+  h->generic_rows = 0;
+  h->rowbuf.assign(kRowStageFloats + 8 * kRowScratchPerWarp + 64, 0.f);
   return h;
 }
 
@@ -109,13 +121,14 @@ int hs_train(void* p, const float* ring, int stride, int size, const float* erin
     for (int ph = 0; ph < P.n_phases; ++ph) {
       const Phase& phs = P.phases[ph];
       if (!phase_active(phs, P.ctx.hp, a, s)) continue;
-      for (int j = 0; j < phs.op_count; ++j) run_op(P, P.ops[phs.op_begin + j], a, s);
+      for (int j = 0; j < phs.op_count; ++j) run_op(h, P, P.ops[phs.op_begin + j], a, s);
     }
   for (int slot = 0; slot < kMaxNets; ++slot) h->t[slot] = adam_t(a, P.ctx.hp, slot, n_steps - 1);
   h->n_total += n_steps;
   return 0;
 }
 
+void hs_set_generic_rows(void* p, int flag) { ((HostSim*)p)->generic_rows = flag; }
 void hs_set_precision(void* p, int prec) { ((HostSim*)p)->prog.ctx.hp.gemm_precision = prec; }
 const float* hs_losses(void* p) { return ((HostSim*)p)->prog.ctx.loss_log; }
 const float* hs_stats(void* p) { return ((HostSim*)p)->prog.ctx.stats; }

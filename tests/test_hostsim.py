@@ -76,3 +76,22 @@ def test_program_shape(lib):
     assert lib.hs_num_phases(run.h) == text.count("phase ")
     assert "replica-exchange" in text and "ADAM" in text
     run.close()
+
+
+@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper", "gail_walker"])
+def test_fast_row_jobs_equal_generic_row_kernels(lib, name):
+    """Two independent implementations of every row kernel (latency-optimised job form vs the
+    generic per-row form) must agree bit for bit on the host."""
+    import ctypes as C
+
+    lib.hs_set_generic_rows.argtypes = [C.c_void_p, C.c_int]
+    case = CFG.CASES[name]
+    inj = case_injection(case)
+    a = HostSimRun(lib, case)
+    b = HostSimRun(lib, case)
+    lib.hs_set_generic_rows(b.h, 1)
+    La, Lb = a.train(case["steps"], inj), b.train(case["steps"], inj)
+    np.testing.assert_array_equal(np.nan_to_num(La), np.nan_to_num(Lb))
+    for k in a.arenas:
+        np.testing.assert_array_equal(a.arenas[k], b.arenas[k], err_msg=k)
+    a.close(); b.close()
