@@ -355,6 +355,30 @@ def main():
                 "h2d_bytes_per_step": buf.ring.host_w * 4, "d2h_bytes_per_step": 16 * 4,
                 "mode": "per train call: %d-transition burst H2D -> %d-step launch -> loss log D2H" % (launch, launch)}
 
+    # ---- the same metric in the other GEMM precision modes (short runs, same timing method)
+    by_prec = {}
+    if world == 1 and args.precision is None:
+        cur = int(os.environ.get("ILSW_GEMM_PRECISION", "1"))
+        by_prec[{0: "fp32_simt", 1: "tf32", 3: "tf32x3"}[cur]] = value
+        for pm in (0, 3, 1):
+            if pm == cur:
+                continue
+            os.environ["ILSW_GEMM_PRECISION"] = str(pm)
+            tr2, buf2, irl2 = build_ours(w, seed=100, steps_per_launch=launch)
+            tr2.eval_statistics = {}
+            if irl2 is not None:
+                irl2.disc_eval_statistics = {}
+            run_steps(tr2, buf2, irl2, launch)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(3):
+                run_steps(tr2, buf2, irl2, launch)
+            a1.record()
+            torch.cuda.synchronize()
+            by_prec[{0: "fp32_simt", 1: "tf32", 3: "tf32x3"}[pm]] = 3 * launch / (a0.elapsed_time(a1) / 1000.0)
+            del tr2, buf2, irl2
+        os.environ["ILSW_GEMM_PRECISION"] = str(cur)
     if rank != 0:
         return
     peaks, peak_src = {}, "fallback"
@@ -372,7 +396,10 @@ def main():
     except Exception:
         pass
     line = {"metric": metric, "value": value, "unit": "gradient-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {0: "f32", 1: "tf32 (tensor-core GEMM operands, f32 accumulate; f32 everywhere else)",
+                      3: "f32 via 3xTF32 split on tensor cores"}[int(os.environ.get("ILSW_GEMM_PRECISION", "1"))],
+            "value_by_gemm_precision": by_prec,
             "data": "synthetic", "config": dict(config, l2="flushed between timed launches (256 MiB write, untimed)",
                                                 sampling="in-kernel Philox, uniform with replacement"),
             "e2e": e2e, "e2e_train_call": e2e_call, "gpu_launches": int(launches),

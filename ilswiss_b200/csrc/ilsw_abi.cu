@@ -395,6 +395,7 @@ extern "C" int ilsw_train(ilsw_trainer* tr, ilsw_rb* policy_rb, ilsw_rb* expert_
   rp.seq0 = tr->seq;
   const Program* dp = tr->dev_prog;
   BarrierState* bar = tr->bar;
+  CU(cudaMemsetAsync(bar, 0, sizeof(BarrierState), st));   // monotonic barrier counter restarts at 0
   void* args[] = {(void*)&dp, (void*)&a, (void*)&bar, (void*)&rp};
   const size_t smem = (size_t)kTcSmemFloats * sizeof(float) + ((sizeof(Phase) * kMaxPhases + 15) & ~size_t(15)) +
                       ((sizeof(Op) * (size_t)tr->host_prog.n_ops + 15) & ~size_t(15)) + sizeof(Ctx) + 64;
@@ -472,7 +473,7 @@ extern "C" int ilsw_describe_program(const ilsw_trainer* tr, char* buf, int buf_
   return (int)s.size();
 }
 extern "C" int ilsw_read_phase_ns(ilsw_trainer* tr, unsigned long long* host_out, int n, void* stream) {
-  if (!tr || !host_out || n <= 0 || n > kMaxPhases + 1) return fail(ILSW_ERR_ARG, "read_phase_ns: bad arguments");
+  if (!tr || !host_out || n <= 0 || n > 2 * (kMaxPhases + 1)) return fail(ILSW_ERR_ARG, "read_phase_ns: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaMemcpyAsync(host_out, tr->host_prog.ctx.phase_ns, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));

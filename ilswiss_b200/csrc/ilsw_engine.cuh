@@ -66,27 +66,29 @@ __device__ __forceinline__ void st_relaxed_gpu(unsigned* p, unsigned v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void red_add_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// `gen` counts the barriers passed; bar->count is monotonic (never reset): barrier k is complete
+// when count >= (k+1)*nblocks.  Arrival = one fire-and-forget red.release (no return value to wait
+// for), departure = ld.acquire polling: measured 1.25 us on 148 SMs vs 1.9 us for the
+// atom+generation variant (tools/microbench.cu, profiles/r1_microbench.txt).
 __device__ __forceinline__ bool grid_barrier(BarrierState* bar, unsigned nblocks, unsigned& gen, int* abort_flag) {
   __shared__ int s_ok;
   __syncthreads();
   if (threadIdx.x == 0) {
     int ok = 1;
-    const unsigned target = gen + 1;
-    unsigned prev = atom_add_acq_rel_gpu(&bar->count, 1u);
-    if (prev == nblocks - 1) {
-      st_relaxed_gpu(&bar->count, 0u);
-      st_release_gpu(&bar->gen, target);
-    } else {
-      long long t0 = 0;
-      unsigned spins = 0;
-      while (ld_acquire_gpu(&bar->gen) != target) {
-        if ((++spins & 1023u) == 0u) {
-          if (t0 == 0) t0 = clock64();
-          long long dt = clock64() - t0;
-          if (dt > kSpinLimit) {
-            if (*(volatile int*)abort_flag) { ok = 0; break; }
-            if (dt > 2 * kSpinLimit) { atomicExch(abort_flag, 1); ok = 0; break; }
-          }
+    const unsigned target = (gen + 1u) * nblocks;
+    red_add_release_gpu(&bar->count, 1u);
+    long long t0 = 0;
+    unsigned spins = 0;
+    while ((int)(ld_acquire_gpu(&bar->count) - target) < 0) {
+      if ((++spins & 1023u) == 0u) {
+        if (t0 == 0) t0 = clock64();
+        long long dt = clock64() - t0;
+        if (dt > kSpinLimit) {
+          if (*(volatile int*)abort_flag) { ok = 0; break; }
+          if (dt > 2 * kSpinLimit) { atomicExch(abort_flag, 1); ok = 0; break; }
         }
       }
     }
@@ -306,57 +308,70 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// Fill one K stage of operand A (rows = m) or B (rows = n) into shared memory.
-//   contig_k: element(row, k) = base[row*ld + k]  -> smem[row*kKS + k]
-//   else    : element(row, k) = base[k*ld + row]  -> smem[k*kMS + row]
-// vec: 16-byte cp.async path allowed (aligned base, ld % 4 == 0, dims % 4 == 0, no aug column)
-template <bool IS_B>
-__device__ __forceinline__ void tc_fill(const GemmOp& o, float* sm, int row0, int k0, int klen, bool vec) {
+// fragment loads: typed shared array indexed by byte offset from the dynamic-smem base
+__device__ __forceinline__ float lds_u32(unsigned byte_off) { return ilsw_dyn_smem_f[byte_off >> 2]; }
+__device__ __forceinline__ void cp_async4(unsigned smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void sts_u32(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// Fill one K stage of BOTH operands into shared memory (single, compact routine: code size
+// matters -- the engine's instruction working set must stay cache resident).
+//   k-contiguous operand: element(row,k) = base[row*ld + k] -> smem[row*kKS + k]
+//   otherwise           : element(row,k) = base[k*ld + row] -> smem[k*kMS + row]
+// vec   : 16-byte cp.async.cg (aligned base, ld % 4 == 0, dims % 4 == 0, no aug column in the tile)
+// !vec  : 4-byte cp.async.ca per element (unaligned rows such as W0[H x 14], ragged edges, the
+//         ones column of the bias gradient).  Nothing is staged through registers, so all copies
+//         of a stage are in flight together.  (.ca allocates in L1: safe because every grid
+//         barrier's ld.acquire.gpu invalidates the L1 -- CCTL.IVALL -- before a new phase reads.)
+__device__ __noinline__ void tc_fill_stage(const GemmOp& o, float* stage, int m0, int n0, int k0, int klen, bool vecA, bool vecB) {
   const int tid = threadIdx.x;
-  const bool contig_k = IS_B ? !o.b_nc : !o.a_mc;
-  const float* base = IS_B ? o.B : o.A;
-  const int ld = IS_B ? o.ldb : o.lda;
-  const int R = IS_B ? o.N : o.M;           // real rows (aug column handled by the scalar path)
-  if (vec) {
-    if (contig_k) {
-#pragma unroll
+  const int kpad = (klen + 7) & ~7;      // zero padded to the MMA k granularity
+#pragma unroll 1
+  for (int op = 0; op < 2; ++op) {
+    const bool isB = op != 0;
+    const bool contig_k = isB ? !o.b_nc : !o.a_mc;
+    const float* base = isB ? o.B : o.A;
+    const int ld = isB ? o.ldb : o.lda;
+    const int R = isB ? o.N : o.M;
+    const int row0 = isB ? n0 : m0;
+    const bool vec = isB ? vecB : vecA;
+    float* sm = stage + op * kOperandFloats;
+    const int sr = contig_k ? ld : 1, sk = contig_k ? 1 : ld;        // source strides
+    const int dr = contig_k ? kKS : 1, dk = contig_k ? 1 : kMS;      // shared strides
+    if (vec) {
+#pragma unroll 2
       for (int i = 0; i < 8; ++i) {
-        const int v = tid + i * kThreads, r = v >> 6, k = (v & 63) << 2;
+        const int v = tid + i * kThreads;
+        const int r = contig_k ? (v >> 6) : ((v & 7) << 2);
+        const int k = contig_k ? ((v & 63) << 2) : (v >> 3);
         const bool in = (row0 + r < R) && (k < klen);
-        const float* src = in ? base + (size_t)(row0 + r) * ld + k0 + k : base;
-        cp_async16(sm + r * kKS + k, src, in ? 16 : 0);
+        const float* src = in ? base + (size_t)(row0 + r) * sr + (size_t)(k0 + k) * sk : base;
+        cp_async16(sm + r * dr + k * dk, src, in ? 16 : 0);
       }
     } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int v = tid + i * kThreads, k = v >> 3, r = (v & 7) << 2;
-        const bool in = (k < klen) && (row0 + r < R);
-        const float* src = in ? base + (size_t)(k0 + k) * ld + row0 + r : base;
-        cp_async16(sm + k * kMS + r, src, in ? 16 : 0);
-      }
-    }
-  } else {
-    const int Rt = IS_B ? o.N + o.aug_ones : o.M;
-    const int kpad = (klen + 7) & ~7;      // zero padded to the MMA k granularity
-    if (contig_k) {
-      for (int e = tid; e < 32 * kpad; e += kThreads) {
-        const int r = e / kpad, k = e - r * kpad;
-        float v = 0.f;
-        if (row0 + r < Rt && k < klen) v = IS_B ? gemm_B(o, k0 + k, row0 + r) : gemm_A(o, row0 + r, k0 + k);
-        sm[r * kKS + k] = v;
-      }
-    } else {
-      for (int e = tid; e < 32 * kpad; e += kThreads) {
-        const int k = e >> 5, r = e & 31;
-        float v = 0.f;
-        if (row0 + r < Rt && k < klen) v = IS_B ? gemm_B(o, k0 + k, row0 + r) : gemm_A(o, row0 + r, k0 + k);
-        sm[k * kMS + r] = v;
+      const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
+      const bool aug = isB && o.aug_ones;
+      // only rows that exist (plus the ones column) and kpad k's are touched; the rest of the
+      // 32-row fragment range is zeroed so the MMA sees exact zeros
+      const int nelem = 32 * kpad;
+#pragma unroll 2
+      for (int e = tid; e < nelem; e += kThreads) {
+        const int r = contig_k ? e / kpad : (e & 31);
+        const int k = contig_k ? e - r * kpad : (e >> 5);
+        const unsigned dst = sbase + 4u * (unsigned)(r * dr + k * dk);
+        const int gr = row0 + r;
+        if (gr < R && k < klen) cp_async4(dst, base + (size_t)gr * sr + (size_t)(k0 + k) * sk);
+        else sts_u32(dst, (aug && gr == R && k < klen) ? 1.0f : 0.f);
       }
     }
   }
 }
 
-__device__ __noinline__ void gemm_tile_tc(const GemmOp& o, int tile, float* smem, int mode) {
+__device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* smem, int mode) {
+  const GemmOp o = og;                       // registers / local copy: the op descriptor lives in shared memory
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tm = tile / o.tiles_n, tn = tile - tm * o.tiles_n;
   const int m0 = tm * 32, n0 = tn * 32;
@@ -367,60 +382,68 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& o, int tile, float* smem
   const bool vecB = ((o.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(o.B) & 15) == 0) && ((o.K & 3) == 0) && ((o.N & 3) == 0) &&
                     !(o.aug_ones && n0 + 32 > o.N);
   const int nstages = (o.K + kKC - 1) / kKC;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  // prologue: stage 0
-  tc_fill<false>(o, smem, m0, 0, min(kKC, o.K), vecA);
-  tc_fill<true>(o, smem + kOperandFloats, n0, 0, min(kKC, o.K), vecB);
-  cp_async_commit();
-  // epilogue inputs (bias / mask source / previous value) are fetched while the panels are in flight
   const int Nt = o.N + o.aug_ones;
   const int r0 = m0 + mb * 16 + g, c0 = n0 + nb * 8 + 2 * q;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   EpiIn ein[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = r0 + ((i & 2) ? 8 : 0), n = c0 + (i & 1);
-    if (m < o.M && n < Nt) ein[i] = epi_load(o, m, n);
-  }
-  for (int st = 0; st < nstages; ++st) {
-    float* As = smem + (st & 1) * kTcStageFloats;
-    float* Bs = As + kOperandFloats;
+  // fragment addressing (32-bit shared addresses, bytes)
+  const unsigned sbase = 4u * (unsigned)(smem - ilsw_dyn_smem_f);   // byte offset inside dynamic shared memory
+  const unsigned a_off = 4u * (a_kc ? (mb * 16 + g) * kKS + q : q * kMS + mb * 16 + g);
+  const unsigned b_off = 4u * (b_kc ? (nb * 8 + g) * kKS + q : q * kMS + nb * 8 + g);
+  const unsigned a_row8 = 4u * (a_kc ? 8 * kKS : 8), a_k4 = 4u * (a_kc ? 4 : 4 * kMS), a_k8 = 2u * a_k4;
+  const unsigned b_k4 = 4u * (b_kc ? 4 : 4 * kMS), b_k8 = 2u * b_k4;
+  // does this warp's 16x8 fragment intersect the valid output at all?  (ragged tiles: N = 3, 14, 1 ...)
+  const bool warp_live = (m0 + mb * 16 < o.M) && (n0 + nb * 8 < Nt);
+#pragma unroll 1
+  for (int st = -1; st < nstages; ++st) {
     if (st + 1 < nstages) {
-      float* An = smem + ((st + 1) & 1) * kTcStageFloats;
-      const int k0 = (st + 1) * kKC, klen = min(kKC, o.K - k0);
-      tc_fill<false>(o, An, m0, k0, klen, vecA);
-      tc_fill<true>(o, An + kOperandFloats, n0, k0, klen, vecB);
+      const int k0 = (st + 1) * kKC;
+      tc_fill_stage(og, smem + ((st + 1) & 1) * kTcStageFloats, m0, n0, k0, min(kKC, o.K - k0), vecA, vecB);
       cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
     }
-    __syncthreads();
-    const int klen = min(kKC, o.K - st * kKC);
-    const int ksteps = (klen + 7) >> 3;       // panel is zero padded up to the stage length
-    // fragment base addresses
-    const float* a_lo = a_kc ? As + (mb * 16 + g) * kKS + q : As + q * kMS + mb * 16 + g;
-    const float* b_p = b_kc ? Bs + (nb * 8 + g) * kKS + q : Bs + q * kMS + nb * 8 + g;
-    const int a_row8 = a_kc ? 8 * kKS : 8, a_k4 = a_kc ? 4 : 4 * kMS, a_k8 = a_kc ? 8 : 8 * kMS;
-    const int b_k4 = b_kc ? 4 : 4 * kMS, b_k8 = b_kc ? 8 : 8 * kMS;
-#pragma unroll 4
-    for (int ks = 0; ks < ksteps; ++ks) {
-      float af[4], bf[2];
-      af[0] = a_lo[0]; af[1] = a_lo[a_row8]; af[2] = a_lo[a_k4]; af[3] = a_lo[a_row8 + a_k4];
-      bf[0] = b_p[0]; bf[1] = b_p[b_k4];
-      a_lo += a_k8; b_p += b_k8;
-      uint32_t ah[4], bh[2];
+    if (st < 0) {
+      // epilogue inputs (bias / mask source / previous value) are fetched while the panels are in flight
 #pragma unroll
-      for (int i = 0; i < 4; ++i) ah[i] = cvt_tf32(af[i]);
-      bh[0] = cvt_tf32(bf[0]); bh[1] = cvt_tf32(bf[1]);
-      if (mode == 3) {
-        uint32_t al[4], bl[2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) al[i] = cvt_tf32(af[i] - __uint_as_float(ah[i]));
-        bl[0] = cvt_tf32(bf[0] - __uint_as_float(bh[0])); bl[1] = cvt_tf32(bf[1] - __uint_as_float(bh[1]));
-        mma_tf32(acc, al, bh);
-        mma_tf32(acc, ah, bl);
+      for (int i = 0; i < 4; ++i) {
+        const int m = r0 + ((i & 2) ? 8 : 0), n = c0 + (i & 1);
+        if (m < o.M && n < Nt) ein[i] = epi_load(o, m, n);
       }
-      mma_tf32(acc, ah, bh);
+      continue;
+    }
+    if (st + 1 < nstages) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+    if (warp_live) {
+      const int klen = min(kKC, o.K - st * kKC);
+      const int ksteps = (klen + 7) >> 3;       // panels are zero padded up to a multiple of 8
+      unsigned ap = sbase + 4u * (unsigned)((st & 1) * kTcStageFloats) + a_off;
+      unsigned bp = sbase + 4u * (unsigned)((st & 1) * kTcStageFloats + kOperandFloats) + b_off;
+      if (mode == 3) {
+#pragma unroll 2
+        for (int ks = 0; ks < ksteps; ++ks) {
+          float af[4], bf[2];
+          af[0] = lds_u32(ap); af[1] = lds_u32(ap + a_row8); af[2] = lds_u32(ap + a_k4); af[3] = lds_u32(ap + a_row8 + a_k4);
+          bf[0] = lds_u32(bp); bf[1] = lds_u32(bp + b_k4);
+          ap += a_k8; bp += b_k8;
+          uint32_t ah[4], bh[2], al[4], bl[2];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { ah[i] = cvt_tf32(af[i]); al[i] = cvt_tf32(af[i] - __uint_as_float(ah[i])); }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) { bh[i] = cvt_tf32(bf[i]); bl[i] = cvt_tf32(bf[i] - __uint_as_float(bh[i])); }
+          mma_tf32(acc, al, bh);
+          mma_tf32(acc, ah, bl);
+          mma_tf32(acc, ah, bh);
+        }
+      } else {
+#pragma unroll 4
+        for (int ks = 0; ks < ksteps; ++ks) {
+          uint32_t ah[4], bh[2];
+          ah[0] = cvt_tf32(lds_u32(ap)); ah[1] = cvt_tf32(lds_u32(ap + a_row8));
+          ah[2] = cvt_tf32(lds_u32(ap + a_k4)); ah[3] = cvt_tf32(lds_u32(ap + a_row8 + a_k4));
+          bh[0] = cvt_tf32(lds_u32(bp)); bh[1] = cvt_tf32(lds_u32(bp + b_k4));
+          ap += a_k8; bp += b_k8;
+          mma_tf32(acc, ah, bh);
+        }
+      }
     }
     __syncthreads();   // stage buffer may be refilled by the next iteration's prefetch
   }
@@ -488,8 +511,8 @@ __device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~size_t(
 
 __global__ void __launch_bounds__(kThreads, 1)
 ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* bar, Replica rp) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  float* smem = reinterpret_cast<float*>(dyn_smem);
+  unsigned char* dyn_smem = reinterpret_cast<unsigned char*>(ilsw_dyn_smem_f);
+  float* smem = ilsw_dyn_smem_f;
   __shared__ AdamCoef s_coef;
   __shared__ unsigned s_gen;
   __shared__ double s_p1[kMaxNets], s_p2[kMaxNets], s_b1[kMaxNets], s_b2[kMaxNets];   // running beta^t per Adam slot
@@ -508,7 +531,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
     src = reinterpret_cast<const int*>(&prog->ctx); dst = reinterpret_cast<int*>(s_ctx); n = (int)(sizeof(Ctx) / 4);
     for (int i = threadIdx.x; i < n; i += kThreads) dst[i] = src[i];
   }
-  if (threadIdx.x == 0) s_gen = ld_acquire_gpu(&bar->gen);
+  if (threadIdx.x == 0) s_gen = 0u;          // the host zeroes the barrier state before every launch
   if (threadIdx.x < kMaxNets) { s_pt[threadIdx.x] = -1; }
   __syncthreads();
   if (threadIdx.x == 0) {   // one pow() per optimiser per LAUNCH; afterwards beta^t is a running product
@@ -605,6 +628,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
           }
         }
       }
+      if (stamp) c.phase_ns[kMaxPhases + 1 + ph] = globaltimer_ns();
       if (!grid_barrier(bar, gridDim.x, gen, abort_flag)) return;
       if (stamp) c.phase_ns[ph + 1] = globaltimer_ns();
     }

@@ -66,7 +66,7 @@ ILSW_HD int ldgi(const int* p) {
 #endif
 }
 
-ILSW_HD float wdot(const float* h, const float* w, int n, int lane, int nl) {
+ILSW_HDN float wdot(const float* h, const float* w, int n, int lane, int nl) {
   float s = 0.f;
   for (int k = lane; k < n; k += nl) s += ldg(h + k) * ldg(w + k);
   return wsum(s);
@@ -77,7 +77,7 @@ ILSW_HD float wdot(const float* h, const float* w, int n, int lane, int nl) {
 // ------------------------------------------------------------------------------------------
 struct U4 { uint32_t x, y, z, w; };
 ILSW_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
-ILSW_HD U4 philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+ILSW_HDN U4 philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   U4 c = {c0, c1, c2, c3};
   for (int r = 0; r < 10; ++r) {
@@ -91,7 +91,7 @@ ILSW_HD U4 philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t
   return c;
 }
 ILSW_HD float u01(uint32_t u) { return ((float)(u >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
-ILSW_HD float philox_normal(uint64_t seed, uint32_t gstep, uint32_t row, uint32_t col, uint32_t stream) {
+ILSW_HDN float philox_normal(uint64_t seed, uint32_t gstep, uint32_t row, uint32_t col, uint32_t stream) {
   U4 r = philox(seed, gstep, row, col, stream);
   float u1 = u01(r.x), u2 = u01(r.y);
   return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
@@ -225,7 +225,7 @@ ILSW_HD const float* ring_row(const RingView& rv, int idx) { return rv.rows + (s
 
 // ---- SAC-alpha -------------------------------------------------------------------------
 // R3/R4: sample index -> packed batch tiles.  Ring row layout: [obs(O) | act(A) | rew | term | next_obs(O)].
-ILSW_HD void row_sac_gather(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_sac_gather(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   const SacBufs& S = c.s;
   const int O = S.O, A = S.A, B = S.B;
   const bool td3 = (c.hp.algo == 2);
@@ -280,7 +280,7 @@ ILSW_HD void row_sac_gather(const Ctx& c, const RunArgs& a, int s, int b, int la
 }
 
 // N2: policy heads on 2B rows (rows [0,B) = next_obs, [B,2B) = obs).
-ILSW_HD void row_sac_heads(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
+ILSW_HDN void row_sac_heads(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
   const SacBufs& S = c.s;
   const MlpPtrs& P = c.policy;
   const int A = S.A, Hd = S.Hd, B = S.B, O = S.O;
@@ -319,7 +319,7 @@ ILSW_HD void row_sac_heads(const Ctx& c, const RunArgs& a, int s, int r, int lan
 }
 
 // shared by SAC and TD3: target value, critic loss terms, output-layer backward of both critics
-ILSW_HD void row_critic_target(const Ctx& c, int b, int lane, int nl, bool use_entropy, float loss_grad_factor) {
+ILSW_HDN void row_critic_target(const Ctx& c, int b, int lane, int nl, bool use_entropy, float loss_grad_factor) {
   const SacBufs& S = c.s;
   const int Hd = S.Hd;
   float tq0 = wdot(S.h1t[0] + (size_t)b * Hd, c.tqf[0].p + c.tqf[0].oW2, Hd, lane, nl) + ldg(c.tqf[0].p + c.tqf[0].ob2);
@@ -347,12 +347,12 @@ ILSW_HD void row_critic_target(const Ctx& c, int b, int lane, int nl, bool use_e
   if (lane == 0) { S.tq[0][b] = tq0; S.tq[1][b] = tq1; S.y[b] = y; }
 }
 
-ILSW_HD void row_sac_target(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_sac_target(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   row_critic_target(c, b, lane, nl, true, 1.0f);  // d/dq of 0.5*mean((q-y)^2)
 }
 
 // policy loss terms + output-layer backward through min(Q1,Q2)(obs, a~) with UPDATED critics
-ILSW_HD void row_sac_ploss(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_sac_ploss(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   const SacBufs& S = c.s;
   const int Hd = S.Hd, A = S.A, B = S.B;
   float q[2];
@@ -387,7 +387,7 @@ ILSW_HD void row_sac_ploss(const Ctx& c, const RunArgs& a, int s, int b, int lan
 }
 
 // backward through the tanh-Gaussian head; produces dmean, dlraw and delta of the last hidden layer
-ILSW_HD void row_sac_pibwd(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_sac_pibwd(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   const SacBufs& S = c.s;
   const MlpPtrs& P = c.policy;
   const int Hd = S.Hd, A = S.A, B = S.B;
@@ -421,18 +421,18 @@ ILSW_HD void row_sac_pibwd(const Ctx& c, const RunArgs& a, int s, int b, int lan
   if (lane == 0) S.aterm[b] = ldg(S.logpi + r) + c.hp.target_entropy;
 }
 
-ILSW_HD float wmean(const float* x, int n, int lane, int nl) {
+ILSW_HDN float wmean(const float* x, int n, int lane, int nl) {
   float s = 0.f;
   for (int i = lane; i < n; i += nl) s += ldg(x + i);
   return wsum(s) / (float)n;
 }
 
-ILSW_HD void stats_copy(float* dst, const float* src, int n, int lane, int nl) {
+ILSW_HDN void stats_copy(float* dst, const float* src, int n, int lane, int nl) {
   for (int i = lane; i < n; i += nl) dst[i] = ldg(src + i);
 }
 
 // stats snapshot layout (floats): see ilsw_stats_offsets() in ilsw_program.h
-ILSW_HD void snapshot_sac(const Ctx& c, int lane, int nl) {
+ILSW_HDN void snapshot_sac(const Ctx& c, int lane, int nl) {
   const SacBufs& S = c.s;
   const int B = S.B, A = S.A;
   const bool td3 = c.hp.algo == 2;
@@ -453,7 +453,7 @@ ILSW_HD void snapshot_sac(const Ctx& c, int lane, int nl) {
 }
 
 // losses, alpha update (float64 scalar Adam), loss log, optional stats snapshot.  Single warp.
-ILSW_HD void row_sac_final(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
+ILSW_HDN void row_sac_final(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
   if (r != 0) return;
   const SacBufs& S = c.s;
   const int B = S.B, A = S.A;
@@ -495,7 +495,7 @@ ILSW_HD void row_sac_final(const Ctx& c, const RunArgs& a, int s, int r, int lan
 
 // ---- TD3 -------------------------------------------------------------------------------
 // target policy head with the policy module's clipped noise (policies.py:176-186, td3.py:82-83)
-ILSW_HD void row_td3_thead(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_td3_thead(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   const SacBufs& S = c.s;
   const MlpPtrs& P = c.tpolicy;
   const int A = S.A, Hd = S.Hd, O = S.O;
@@ -510,10 +510,10 @@ ILSW_HD void row_td3_thead(const Ctx& c, const RunArgs& a, int s, int b, int lan
     }
   }
 }
-ILSW_HD void row_td3_target(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_td3_target(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   row_critic_target(c, b, lane, nl, false, 2.0f);  // d/dq of mean((q-y)^2), no 1/2 (td3.py:93-98)
 }
-ILSW_HD void row_td3_phead(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_td3_phead(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   const SacBufs& S = c.s;
   const MlpPtrs& P = c.policy;
   const int A = S.A, Hd = S.Hd, O = S.O;
@@ -527,7 +527,7 @@ ILSW_HD void row_td3_phead(const Ctx& c, const RunArgs& a, int s, int b, int lan
     }
   }
 }
-ILSW_HD void row_td3_ploss(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_td3_ploss(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   const SacBufs& S = c.s;
   const MlpPtrs& Q = c.qf[0];
   const int Hd = S.Hd;
@@ -538,7 +538,7 @@ ILSW_HD void row_td3_ploss(const Ctx& c, const RunArgs& a, int s, int b, int lan
   float* e1 = S.e1[0] + (size_t)b * Hd;
   for (int k = lane; k < Hd; k += nl) e1[k] = (ldg(h + k) > 0.f) ? dq * ldg(Q.p + Q.oW2 + k) : 0.f;
 }
-ILSW_HD void row_td3_pibwd(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_td3_pibwd(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   const SacBufs& S = c.s;
   const MlpPtrs& P = c.policy;
   const int Hd = S.Hd, A = S.A;
@@ -555,7 +555,7 @@ ILSW_HD void row_td3_pibwd(const Ctx& c, const RunArgs& a, int s, int b, int lan
     d1[k] = (ldg(h + k) > 0.f) ? acc : 0.f;
   }
 }
-ILSW_HD void row_td3_final(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
+ILSW_HDN void row_td3_final(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
   if (r != 0) return;
   const SacBufs& S = c.s;
   const int B = S.B;
@@ -570,14 +570,14 @@ ILSW_HD void row_td3_final(const Ctx& c, const RunArgs& a, int s, int r, int lan
   }
   if (s == a.stats_step) snapshot_sac(c, lane, nl);
 }
-ILSW_HD void row_td3_final_policy(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
+ILSW_HDN void row_td3_final_policy(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
   if (r != 0) return;
   float pl = wmean(c.s.plterm, c.s.B, lane, nl);
   if (lane == 0) c.loss_log[(size_t)(a.loss_log_offset + s) * kLossSlots + L_POLICY] = pl;
 }
 
 // ---- AdvIRL discriminator --------------------------------------------------------------
-ILSW_HD void row_disc_gather(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_disc_gather(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   const DiscBufs& Dd = c.d;
   const int B = Dd.B, D = Dd.D;
   int ie = a.has_inject ? a.inj.idx_expert[(size_t)s * B + b]
@@ -603,7 +603,7 @@ ILSW_HD void row_disc_gather(const Ctx& c, const RunArgs& a, int s, int b, int l
 
 // output layer on all rows; BCE-with-logits terms + CE output backward (rows < 2B);
 // clamp mask and GP delta2 = c * w3 * (1-h2^2) for the interpolated rows (>= 2B)
-ILSW_HD void row_disc_head(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
+ILSW_HDN void row_disc_head(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
   const DiscBufs& Dd = c.d;
   const MlpPtrs& N = c.disc;
   const int B = Dd.B, Hd = Dd.Hd;
@@ -643,7 +643,7 @@ ILSW_HD void row_disc_head(const Ctx& c, const RunArgs& a, int s, int r, int lan
 }
 
 // Gulrajani penalty: n = ||g||, term (n-1)^2, gbar = dL/dg = (2*lambda/B)(n-1) g/n  (0 at n=0)
-ILSW_HD void row_disc_gnorm(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_disc_gnorm(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   const DiscBufs& Dd = c.d;
   const int D = Dd.D;
   const float* g = Dd.g + (size_t)b * Dd.ld_d;
@@ -657,7 +657,7 @@ ILSW_HD void row_disc_gnorm(const Ctx& c, const RunArgs& a, int s, int b, int la
   if (lane == 0) { Dd.nrm[b] = n; Dd.gpterm[b] = (n - 1.0f) * (n - 1.0f); }
 }
 // ubar1 = dbar1 * s1 ; sbar1 = dbar1 * u1
-ILSW_HD void row_disc_ew1(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_disc_ew1(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   const DiscBufs& Dd = c.d;
   const int Hd = Dd.Hd, B = Dd.B;
   for (int k = lane; k < Hd; k += nl) {
@@ -669,7 +669,7 @@ ILSW_HD void row_disc_ew1(const Ctx& c, const RunArgs& a, int s, int b, int lane
   }
 }
 // t3 = c*dbar2*s2 ; sbar2 = dbar2*(c*w3) ; zbar2 = (-2 h2 sbar2) * s2
-ILSW_HD void row_disc_ew2(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_disc_ew2(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   const DiscBufs& Dd = c.d;
   const int Hd = Dd.Hd, B = Dd.B;
   const float* w3 = c.disc.p + c.disc.oW2;
@@ -685,7 +685,7 @@ ILSW_HD void row_disc_ew2(const Ctx& c, const RunArgs& a, int s, int b, int lane
   }
 }
 // zbar1 = (hbar1_raw - 2 h1 sbar1) * s1
-ILSW_HD void row_disc_ew3(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_disc_ew3(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   const DiscBufs& Dd = c.d;
   const int Hd = Dd.Hd, B = Dd.B;
   for (int k = lane; k < Hd; k += nl) {
@@ -694,7 +694,7 @@ ILSW_HD void row_disc_ew3(const Ctx& c, const RunArgs& a, int s, int b, int lane
     Dd.zb1[i] = (ldg(Dd.hb1 + i) - 2.0f * h1 * ldg(Dd.sb1 + i)) * (1.0f - h1 * h1);
   }
 }
-ILSW_HD void row_disc_final(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
+ILSW_HDN void row_disc_final(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
   if (r != 0) return;
   const DiscBufs& Dd = c.d;
   float ce = wmean(Dd.ceterm, 2 * Dd.B, lane, nl);
@@ -706,7 +706,7 @@ ILSW_HD void row_disc_final(const Ctx& c, const RunArgs& a, int s, int r, int la
   }
 }
 // D2: reward relabel of the policy batch (adv_irl.py:266-298); overwrites the SAC batch reward
-ILSW_HD void row_disc_reward(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+ILSW_HDN void row_disc_reward(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   const DiscBufs& Dd = c.d;
   const MlpPtrs& N = c.disc;
   const int Hd = Dd.Hd;
@@ -723,7 +723,7 @@ ILSW_HD void row_disc_reward(const Ctx& c, const RunArgs& a, int s, int b, int l
   if (c.hp.clip_min_on) r = fmaxf(r, c.hp.rew_clip_min);
   if (lane == 0) { c.s.rew[b] = r; Dd.rewraw[b] = r; }
 }
-ILSW_HD void row_disc_reward_final(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
+ILSW_HDN void row_disc_reward_final(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
   if (r != 0) return;
   const DiscBufs& Dd = c.d;
   const int B = Dd.B;

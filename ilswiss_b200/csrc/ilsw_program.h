@@ -425,7 +425,7 @@ inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem) {
   c.loss_log = mem.f((size_t)cfg.max_steps_per_call * kLossSlots);
   c.stats_floats = stats_floats_for(cfg.algo, B, A);
   c.stats = mem.f(c.stats_floats);
-  c.phase_ns = mem.take<unsigned long long>(kMaxPhases + 1);
+  c.phase_ns = mem.take<unsigned long long>(2 * (kMaxPhases + 1));
   alloc_sac_bufs(mem, c.s, cfg.algo, B, O, A, Hd);
   auto grad = [&](const ilsw_mlp& n) { return mem.f(mlp_num_params(n.in_dim, n.hidden, n.out_dim, n.log_std_head)); };
   c.policy = make_mlp(sp.nets[0], grad(sp.nets[0]));

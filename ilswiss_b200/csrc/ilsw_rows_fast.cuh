@@ -31,6 +31,27 @@ struct RowEnv {
 
 struct Vec { float v[ILSW_VL]; };
 
+// Staged data lives in the CTA's dynamic SHARED memory on the device.  Accesses go through the
+// typed extern array (plain LDS/STS with ordinary memory semantics: the compiler may batch them
+// but never moves them across __syncthreads), addressed by the float offset of the generic pointer.
+#if defined(__CUDACC__)
+extern __shared__ __align__(16) float ilsw_dyn_smem_f[];
+#endif
+ILSW_HD float lds(const float* p) {
+#ifdef __CUDA_ARCH__
+  return ilsw_dyn_smem_f[(int)(p - ilsw_dyn_smem_f)];
+#else
+  return *p;
+#endif
+}
+ILSW_HD void sts(float* p, float v) {
+#ifdef __CUDA_ARCH__
+  ilsw_dyn_smem_f[(int)(p - ilsw_dyn_smem_f)] = v;
+#else
+  *p = v;
+#endif
+}
+
 ILSW_HD void vload(Vec& x, const float* p, int n, int lane, int nl) {
 #pragma unroll
   for (int i = 0; i < ILSW_VL; ++i) { const int k = lane + i * nl; x.v[i] = k < n ? ldg(p + k) : 0.f; }
@@ -42,7 +63,7 @@ ILSW_HD void vload_plain(Vec& x, const float* p, int n, int lane, int nl) {   //
 ILSW_HD float vdot_s(const Vec& h, const float* w, int n, int lane, int nl) {   // w staged/plain
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < ILSW_VL; ++i) { const int k = lane + i * nl; if (k < n) s += h.v[i] * w[k]; }
+  for (int i = 0; i < ILSW_VL; ++i) { const int k = lane + i * nl; if (k < n) s += h.v[i] * lds(w + k); }
   return wsum(s);
 }
 
@@ -50,7 +71,15 @@ ILSW_HD float vdot_s(const Vec& h, const float* w, int n, int lane, int nl) {   
 ILSW_HD const float* cta_stage(const RowEnv& e, const float* src, int n, int off) {
 #ifdef __CUDA_ARCH__
   float* dst = e.sm + off;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldcg(src + i);
+  // batches of 4 loads per thread are issued together (a store between two loads would
+  // serialise them into separate L2 round trips), then stored
+  for (int base = 0; base < n; base += 4 * (int)blockDim.x) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = base + u * (int)blockDim.x + (int)threadIdx.x; v[u] = i < n ? __ldcg(src + i) : 0.f; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = base + u * (int)blockDim.x + (int)threadIdx.x; if (i < n) sts(dst + i, v[u]); }
+  }
   return dst;
 #else
   (void)e; (void)n; (void)off;
@@ -85,15 +114,16 @@ ILSW_HDN void job_sac_heads(const Ctx& c, int job, const RowEnv& e) {
   cta_sync();
   if (r < 2 * B) {
     float* sc = warp_scratch(e);
+#pragma unroll 1
     for (int j = 0; j < A; ++j) {
-      float mu = vdot_s(h, Wm + (size_t)j * Hd, Hd, lane, nl) + bm[j];
-      float lr = vdot_s(h, Ws + (size_t)j * Hd, Hd, lane, nl) + bs[j];
-      if (lane == 0) { sc[j] = mu; sc[A + j] = lr; }
+      float mu = vdot_s(h, Wm + (size_t)j * Hd, Hd, lane, nl) + lds(bm + j);
+      float lr = vdot_s(h, Ws + (size_t)j * Hd, Hd, lane, nl) + lds(bs + j);
+      if (lane == 0) { sts(sc + j, mu); sts(sc + A + j, lr); }
     }
     wsync();
     float s1 = 0.f, s2 = 0.f, s3 = 0.f;
     for (int j = lane; j < A; j += nl) {
-      const float mu = sc[j], lraw = sc[A + j];
+      const float mu = lds(sc + j), lraw = lds(sc + A + j);
       const float ls = fminf(fmaxf(lraw, -20.0f), 2.0f);
       const float sig = expf(ls), cov = expf(2.0f * ls);
       const float z = ldg(S.eps + (size_t)r * A + j) * sig + mu;
@@ -158,7 +188,7 @@ ILSW_HDN void job_critic_target(const Ctx& c, int job, const RowEnv& e, bool use
 #pragma unroll
       for (int x = 0; x < ILSW_VL; ++x) {
         const int k = lane + x * nl;
-        if (k < Hd) d1[k] = hq[i].v[x] > 0.f ? dq * qw[i][k] : 0.f;
+        if (k < Hd) d1[k] = hq[i].v[x] > 0.f ? dq * lds(qw[i] + k) : 0.f;
       }
     }
     if (lane == 0) { S.tq[0][b] = tq0; S.tq[1][b] = tq1; S.y[b] = y; }
@@ -204,7 +234,7 @@ ILSW_HDN void job_sac_ploss(const Ctx& c, int job, const RowEnv& e) {
 #pragma unroll
       for (int x = 0; x < ILSW_VL; ++x) {
         const int k = lane + x * nl;
-        if (k < Hd) e1[k] = h[i].v[x] > 0.f ? dq * qw[i][k] : 0.f;
+        if (k < Hd) e1[k] = h[i].v[x] > 0.f ? dq * lds(qw[i] + k) : 0.f;
       }
     }
   }
@@ -241,19 +271,20 @@ ILSW_HDN void job_sac_pibwd(const Ctx& c, int job, const RowEnv& e) {
       const float dmu = dz + 2.0f * c.hp.mean_reg * mu * invBA;
       const float dl = dz * ep * expf(ls) - alpha * invB + 2.0f * c.hp.std_reg * ls * invBA;
       const float dlr = (lr >= -20.0f && lr <= 2.0f) ? dl : 0.f;
-      sc[j] = dmu; sc[A + j] = dlr;
+      sts(sc + j, dmu); sts(sc + A + j, dlr);
     }
   }
   cta_sync();   // staged heads visible; also orders the scratch writes inside each warp
   if (b < B) {
-    for (int j = lane; j < A; j += nl) { S.dmean[(size_t)b * A + j] = sc[j]; S.dlraw[(size_t)b * A + j] = sc[A + j]; }
+    for (int j = lane; j < A; j += nl) { S.dmean[(size_t)b * A + j] = lds(sc + j); S.dlraw[(size_t)b * A + j] = lds(sc + A + j); }
     float* d1 = S.d1p + (size_t)b * Hd;
 #pragma unroll
     for (int x = 0; x < ILSW_VL; ++x) {
       const int k = lane + x * nl;
       if (k < Hd) {
         float acc = 0.f;
-        for (int j = 0; j < A; ++j) acc += sc[j] * Wm[(size_t)j * Hd + k] + sc[A + j] * Ws[(size_t)j * Hd + k];
+#pragma unroll 1
+        for (int j = 0; j < A; ++j) acc += lds(sc + j) * lds(Wm + (size_t)j * Hd + k) + lds(sc + A + j) * lds(Ws + (size_t)j * Hd + k);
         d1[k] = h.v[x] > 0.f ? acc : 0.f;
       }
     }
@@ -278,12 +309,12 @@ ILSW_HDN void job_td3_head(const Ctx& c, int job, const RowEnv& e, bool target) 
   if (b < S.B) {
     float* sc = warp_scratch(e);
     for (int j = 0; j < A; ++j) {
-      const float pre = vdot_s(h, W + (size_t)j * Hd, Hd, lane, nl) + bb[j];
-      if (lane == 0) sc[j] = pre;
+      const float pre = vdot_s(h, W + (size_t)j * Hd, Hd, lane, nl) + lds(bb + j);
+      if (lane == 0) sts(sc + j, pre);
     }
     wsync();
     for (int j = lane; j < A; j += nl) {
-      const float t = tanhf(sc[j]);
+      const float t = tanhf(lds(sc + j));
       if (target) {
         float nz = c.hp.policy_noise * ldg(S.noise + (size_t)b * A + j);
         nz = fminf(fmaxf(nz, -c.hp.noise_clip), c.hp.noise_clip);
@@ -315,7 +346,7 @@ ILSW_HDN void job_td3_ploss(const Ctx& c, int job, const RowEnv& e) {
 #pragma unroll
     for (int x = 0; x < ILSW_VL; ++x) {
       const int k = lane + x * nl;
-      if (k < Hd) e1[k] = h.v[x] > 0.f ? dq * qw[k] : 0.f;
+      if (k < Hd) e1[k] = h.v[x] > 0.f ? dq * lds(qw + k) : 0.f;
     }
   }
   cta_sync();
@@ -333,19 +364,20 @@ ILSW_HDN void job_td3_pibwd(const Ctx& c, int job, const RowEnv& e) {
     vload(h, S.h1p + (size_t)b * Hd, Hd, lane, nl);
     for (int j = lane; j < A; j += nl) {
       const float t = ldg(S.act + (size_t)b * A + j);
-      sc[j] = ldg(S.dA[0] + (size_t)b * A + j) * c.hp.max_act * (1.0f - t * t);
+      sts(sc + j, ldg(S.dA[0] + (size_t)b * A + j) * c.hp.max_act * (1.0f - t * t));
     }
   }
   cta_sync();
   if (b < S.B) {
-    for (int j = lane; j < A; j += nl) S.dmean[(size_t)b * A + j] = sc[j];
+    for (int j = lane; j < A; j += nl) S.dmean[(size_t)b * A + j] = lds(sc + j);
     float* d1 = S.d1p + (size_t)b * Hd;
 #pragma unroll
     for (int x = 0; x < ILSW_VL; ++x) {
       const int k = lane + x * nl;
       if (k < Hd) {
         float acc = 0.f;
-        for (int j = 0; j < A; ++j) acc += sc[j] * W[(size_t)j * Hd + k];
+#pragma unroll 1
+        for (int j = 0; j < A; ++j) acc += lds(sc + j) * lds(W + (size_t)j * Hd + k);
         d1[k] = h.v[x] > 0.f ? acc : 0.f;
       }
     }
@@ -385,7 +417,7 @@ ILSW_HDN void job_disc_head(const Ctx& c, int job, const RowEnv& e, int rows) {
 #pragma unroll
       for (int xx = 0; xx < ILSW_VL; ++xx) {
         const int k = lane + xx * nl;
-        if (k < Hd) d2[k] = dl * w3[k] * (1.0f - h2.v[xx] * h2.v[xx]);
+        if (k < Hd) d2[k] = dl * lds(w3 + k) * (1.0f - h2.v[xx] * h2.v[xx]);
       }
     } else {
       const int b = r - 2 * B;
@@ -394,7 +426,7 @@ ILSW_HDN void job_disc_head(const Ctx& c, int job, const RowEnv& e, int rows) {
 #pragma unroll
       for (int xx = 0; xx < ILSW_VL; ++xx) {
         const int k = lane + xx * nl;
-        if (k < Hd) dl2[k] = pass * w3[k] * (1.0f - h2.v[xx] * h2.v[xx]);
+        if (k < Hd) dl2[k] = pass * lds(w3 + k) * (1.0f - h2.v[xx] * h2.v[xx]);
       }
     }
   }

@@ -169,7 +169,8 @@ struct Ctx {            // everything a row kernel needs
   float* loss_log;      // [max_steps x kLossSlots]
   float* stats;         // snapshot area (see ilsw_stats layout in include/ilswiss_b200.h)
   int stats_floats;
-  unsigned long long* phase_ns;  // [kMaxPhases+1] globaltimer stamps of the LAST step of a launch (profiling)
+  unsigned long long* phase_ns;  // [2*(kMaxPhases+1)] globaltimer stamps of the LAST step of a launch (profiling):
+                                 // [i] = after the barrier of phase i-1; [kMaxPhases+1+i] = CTA 0 finished its jobs of phase i
 };
 
 struct RingView {       // replay ring as seen by the gather row kernel

@@ -22,9 +22,10 @@ from .engine import NetArena, StepEngine, require_cuda
 
 
 def default_gemm_precision():
-    """0: fp32 SIMT tiles (exact parity gate); 1: TF32 tensor cores; 3: 3xTF32 tensor cores
-    (fp32-level accuracy).  Override with ILSW_GEMM_PRECISION or the trainers' gemm_precision=."""
-    return int(os.environ.get("ILSW_GEMM_PRECISION", "3"))
+    """0: fp32 SIMT tiles (exact parity gate); 1: TF32 tensor cores (default speed mode: losses within
+    1e-4 relative of the reference, see tests/test_gpu_engine.py); 3: 3xTF32 tensor cores (fp32-level
+    accuracy).  Override with ILSW_GEMM_PRECISION or the trainers' gemm_precision= argument."""
+    return int(os.environ.get("ILSW_GEMM_PRECISION", "1"))
 
 
 def _stats(name, data):

@@ -44,7 +44,7 @@ def test_sac_trainer_dropin_train_step_and_stats_keys():
     case = CFG.CASES["sac_hopper"]
     mods, nets = build_modules(case)
     policy_ref = mods["policy"]
-    tr = SoftActorCritic(mods["policy"], mods["qf1"], mods["qf2"], batch_size=case["batch"], **case["sac"])
+    tr = SoftActorCritic(mods["policy"], mods["qf1"], mods["qf2"], batch_size=case["batch"], gemm_precision=3, **case["sac"])
     assert tr.policy is policy_ref and len(tr.networks) == 5
     assert all(p.is_cuda for p in tr.policy.parameters())
     data, _ = case_data(case)
@@ -98,7 +98,7 @@ def test_snapshot_round_trip_resumes_bit_identically():
 
     def mk():
         mods, _ = build_modules(case)
-        tr = SoftActorCritic(mods["policy"], mods["qf1"], mods["qf2"], batch_size=case["batch"], **case["sac"])
+        tr = SoftActorCritic(mods["policy"], mods["qf1"], mods["qf2"], batch_size=case["batch"], gemm_precision=3, **case["sac"])
         buf = DeviceReplayBuffer(case["n_fill"], case["obs_dim"], case["act_dim"], random_seed=1)
         fill(buf, data)
         tr.eval_statistics = {}
@@ -125,7 +125,7 @@ def test_td3_trainer_dropin():
 
     case = CFG.CASES["td3_hopper"]
     mods, nets = build_modules(case)
-    tr = TD3(mods["policy"], mods["qf1"], mods["qf2"], batch_size=case["batch"], **case["td3"])
+    tr = TD3(mods["policy"], mods["qf1"], mods["qf2"], batch_size=case["batch"], gemm_precision=3, **case["td3"])
     assert len(tr.networks) == 6
     data, _ = case_data(case)
     buf = DeviceReplayBuffer(case["n_fill"], case["obs_dim"], case["act_dim"], random_seed=1)
@@ -182,7 +182,7 @@ def test_adv_irl_engine_matches_oracle_and_stats_keys():
     torch.set_num_threads(1)
     case = CFG.CASES["gail_walker"]
     mods, _ = build_modules(case)
-    tr = SoftActorCritic(mods["policy"], mods["qf1"], mods["qf2"], batch_size=case["batch"], **case["sac"])
+    tr = SoftActorCritic(mods["policy"], mods["qf1"], mods["qf2"], batch_size=case["batch"], gemm_precision=3, **case["sac"])
     data, edata = case_data(case)
     buf = DeviceReplayBuffer(case["n_fill"], case["obs_dim"], case["act_dim"], random_seed=1)
     ebuf = DeviceReplayBuffer(case["n_fill"], case["obs_dim"], case["act_dim"], random_seed=3)

@@ -14,7 +14,19 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 CASES = [n for n, c in CFG.CASES.items() if c["algo"] in ("sac_alpha", "td3", "adv_irl")]
 
 
-def loss_tol(k, ref):
+def loss_tol(k, ref, precision=0, n_rows=512):
+    if precision == 1:
+        # single-pass TF32 (10-bit mantissa operands): the 1e-4 bar is a bar on LOSSES (means over the
+        # batch, where rounding noise averages out).  Element-level statistics carry the per-element
+        # TF32 error (~1e-3 relative), and Disc Acc is a count of sign decisions: allow 2 flips.
+        if k == "Disc Acc":
+            return 2.0 / n_rows + 1e-9
+        if k.endswith(" Max") or k.endswith(" Min"):
+            return 2e-3 * max(abs(ref), 1.0)
+    return _loss_tol(k, ref)
+
+
+def _loss_tol(k, ref):
     # bar (BASELINE.json north_star): 1e-4 relative on losses; the policy loss is a cancellation
     # of O(1) terms, so its floor is 1e-4 absolute
     if k == "Policy Loss" or k.endswith(" Mean") or k.endswith(" Std"):
@@ -39,16 +51,16 @@ def test_cuda_step_matches_oracle(name, precision):
             got = float(L[t, STAT_TO_SLOT[k]])
             if np.isnan(got):
                 continue
-            assert abs(got - ref) <= loss_tol(k, ref), (name, t, k, got, ref)
+            assert abs(got - ref) <= loss_tol(k, ref, precision, 2 * case["batch"]), (name, t, k, got, ref)
     for k in final:
         if k == "log_alpha":
             assert abs(run.eng.get_state().log_alpha - final[k][0]) < 1e-6
-        elif precision == 1:
-            # single-pass TF32 perturbs gradients at the 1e-3 relative level: many more elements
-            # fall into Adam's sign-sensitive regime (see assert_params_close); bound only
-            assert_params_close(run.arena(k), final[k], case["steps"], msg="%s/%s" % (name, k), frac=1.0)
         else:
-            assert_params_close(run.arena(k), final[k], case["steps"], msg="%s/%s" % (name, k))
+            # tensor-core modes perturb gradients (TF32: 1e-3 relative, 3xTF32: ~5e-7 + the tensor
+            # core's truncating fp32 accumulation): more elements fall into Adam's sign-sensitive
+            # regime (see assert_params_close); the 2*lr*steps bound holds in every mode
+            frac = {0: 5e-4, 3: 0.1, 1: 1.0}[precision]
+            assert_params_close(run.arena(k), final[k], case["steps"], msg="%s/%s" % (name, k), frac=frac)
 
 
 @pytest.mark.parametrize("name", CASES)

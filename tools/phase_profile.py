@@ -36,8 +36,8 @@ def main():
         desc = tr.engine.describe().strip().split("\n")
         print("== %s: %.1f us/step (launch avg), last-step phase sum %.1f us, %d phases" %
               (name, e0.elapsed_time(e1) * 1000 / 200, us.sum(), len(us)))
-        for t, d in zip(us, desc):
-            print("  %7.2f us  %s" % (t, d))
+        for t, j, d in zip(us, tr.engine.last_job_us, desc):
+            print("  %7.2f us (cta0 jobs %6.2f, barrier+wait %6.2f)  %s" % (t, j, t - j, d))
 
 
 if __name__ == "__main__":
