@@ -252,6 +252,7 @@ struct ilsw_trainer {
   size_t scratch_bytes;
   BarrierState* bar;
   int grid;
+  int ctas;
   size_t smem_bytes;
   int t[kMaxNets];
   int n_total;
@@ -311,15 +312,21 @@ extern "C" int ilsw_trainer_create(ilsw_trainer** out, const ilsw_trainer_config
   if (e == cudaSuccess) e = cudaMemset(tr->bar, 0, sizeof(BarrierState));
   if (e != cudaSuccess) { ilsw_trainer_destroy(tr); return fail(ILSW_ERR_CUDA, "barrier alloc: %s", cudaGetErrorString(e)); }
   int per_sm = 0;
-  tr->smem_bytes = (size_t)kTcSmemFloats * sizeof(float) + ((sizeof(Phase) * kMaxPhases + 15) & ~size_t(15)) +
+  // occupancy variant: 2 CTAs/SM pays off when the GEMM phases have more than 2 tiles per SM (B >= 512)
+  tr->ctas = cfg->batch >= 512 ? 2 : 1;
+  const char* cv = getenv("ILSW_CTAS_PER_SM");
+  if (cv && (atoi(cv) == 1 || atoi(cv) == 2)) tr->ctas = atoi(cv);
+  tr->smem_bytes = (size_t)tc_smem_floats(tr->ctas) * sizeof(float) + ((sizeof(Phase) * kMaxPhases + 15) & ~size_t(15)) +
                    ((sizeof(Op) * (size_t)kMaxOps + 15) & ~size_t(15)) + sizeof(Ctx) + 64;
-  e = cudaFuncSetAttribute(ilsw_engine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr->smem_bytes);
+  const void* kfn = tr->ctas == 2 ? (const void*)ilsw_engine_kernel<2> : (const void*)ilsw_engine_kernel<1>;
+  e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr->smem_bytes);
   if (e != cudaSuccess) { ilsw_trainer_destroy(tr); return fail(ILSW_ERR_CUDA, "engine smem opt-in (%zu B): %s", tr->smem_bytes, cudaGetErrorString(e)); }
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ilsw_engine_kernel, kThreads, tr->smem_bytes);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kThreads, tr->smem_bytes);
   if (e != cudaSuccess || per_sm < 1) { ilsw_trainer_destroy(tr); return fail(ILSW_ERR_CUDA, "engine kernel cannot be resident (%s)", cudaGetErrorString(e)); }
-  tr->grid = sms;  // persistent: one CTA per SM
+  if (per_sm < tr->ctas) { ilsw_trainer_destroy(tr); return fail(ILSW_ERR_CUDA, "engine kernel: only %d CTA/SM resident, need %d", per_sm, tr->ctas); }
+  tr->grid = sms * tr->ctas;  // persistent: all CTAs co-resident (cooperative launch)
   const char* g = getenv("ILSW_GRID");
-  if (g && atoi(g) > 0 && atoi(g) <= sms * per_sm) tr->grid = atoi(g);
+  if (g && atoi(g) > 0 && atoi(g) <= sms * tr->ctas) tr->grid = atoi(g);
   tr->rep.world = 1;
   *out = tr;
   return ILSW_OK;
@@ -397,9 +404,9 @@ extern "C" int ilsw_train(ilsw_trainer* tr, ilsw_rb* policy_rb, ilsw_rb* expert_
   BarrierState* bar = tr->bar;
   CU(cudaMemsetAsync(bar, 0, sizeof(BarrierState), st));   // monotonic barrier counter restarts at 0
   void* args[] = {(void*)&dp, (void*)&a, (void*)&bar, (void*)&rp};
-  const size_t smem = (size_t)kTcSmemFloats * sizeof(float) + ((sizeof(Phase) * kMaxPhases + 15) & ~size_t(15)) +
+  const size_t smem = (size_t)tc_smem_floats(tr->ctas) * sizeof(float) + ((sizeof(Phase) * kMaxPhases + 15) & ~size_t(15)) +
                       ((sizeof(Op) * (size_t)tr->host_prog.n_ops + 15) & ~size_t(15)) + sizeof(Ctx) + 64;
-  CU(cudaLaunchCooperativeKernel((void*)ilsw_engine_kernel, dim3(tr->grid), dim3(kThreads), args, smem, st));
+  CU(cudaLaunchCooperativeKernel(tr->ctas == 2 ? (void*)ilsw_engine_kernel<2> : (void*)ilsw_engine_kernel<1>, dim3(tr->grid), dim3(kThreads), args, smem, st));
   tr->launches += 1;
   // host mirrors of the on-device counters
   tr->seq += (unsigned)(adam_t(a, tr->host_prog.ctx.hp, SLOT_POLICY, n_steps - 1) - a.t0[SLOT_POLICY]);

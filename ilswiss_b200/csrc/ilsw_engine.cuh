@@ -273,9 +273,9 @@ __device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* 
 
 // ------------------------------------------------------------------------------------------
 // TF32 tensor-core GEMM tile (speed mode; mma.sync.m16n8k8, fp32 accumulate).
-// 32x32 outputs per CTA job; the WHOLE K panel (<=256 per stage) of both operands is brought
-// from L2 into shared memory with 16-byte cp.async.cg in one shot (one L2 round trip per
-// stage instead of one per 32-wide chunk), double-buffered when K > 256.  Each of the 8 warps
+// 32x32 outputs per CTA job; K panels of 128 of both operands are brought from L2 into shared
+// memory with 16-byte cp.async.cg (one L2 round trip per 128-deep stage instead of one per
+// 32-wide chunk), two stages in flight.  Each of the 8 warps
 // owns a 16x8 accumulator fragment over the full K.  Shared layouts are chosen per operand so
 // that BOTH the 128-bit fill and the fragment reads are bank-conflict free:
 //   k-contiguous operand  -> [32 rows][260]   (fragment bank = 4*row + k  = lane)
@@ -283,12 +283,18 @@ __device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* 
 // mode 1: single-pass TF32 (operands rounded with cvt.rna);  mode 3: 3xTF32 split
 // (hi/lo, small terms first) which recovers fp32-level accuracy on the tensor cores.
 // ------------------------------------------------------------------------------------------
-constexpr int kKC = 256;                      // K per stage
-constexpr int kKS = kKC + 4;                  // row stride of a k-contiguous panel
+// K per stage is a template parameter: 256 (one CTA per SM, 160 KB staging: a K=256 GEMM is a single
+// stage) or 128 (two CTAs per SM, 80 KB staging each).
 constexpr int kMS = 40;                       // row stride of an m/n-contiguous panel
-constexpr int kOperandFloats = kKC * kMS;     // 10240 floats (>= 32*kKS = 8320)
-constexpr int kTcStageFloats = 2 * kOperandFloats;
-constexpr int kTcSmemFloats = 2 * kTcStageFloats;   // 2 stages x (A,B) = 160 KB
+template <int KC> struct TcGeom {
+  static constexpr int kKS = KC + 4;                    // row stride of a k-contiguous panel
+  static constexpr int kOperandFloats = KC * kMS;       // >= 32 * kKS
+  static constexpr int kStageFloats = 2 * kOperandFloats;
+  static constexpr int kSmemFloats = 2 * kStageFloats;  // 2 stages x (A,B): 160 KB (KC=256) / 80 KB (KC=128)
+};
+constexpr int tc_smem_floats(int ctas) { return ctas == 2 ? TcGeom<128>::kSmemFloats : TcGeom<256>::kSmemFloats; }
+// The engine is compiled in two occupancy variants: CTAS=1 (255 registers/thread, lowest single-job
+// latency: B=256 workloads) and CTAS=2 (128 registers, twice the tile parallelism per SM: B=1024).
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -326,7 +332,10 @@ __device__ __forceinline__ void sts_u32(unsigned addr, float v) {
 //         ones column of the bias gradient).  Nothing is staged through registers, so all copies
 //         of a stage are in flight together.  (.ca allocates in L1: safe because every grid
 //         barrier's ld.acquire.gpu invalidates the L1 -- CCTL.IVALL -- before a new phase reads.)
+template <int KC>
 __device__ __noinline__ void tc_fill_stage(const GemmOp& o, float* stage, int m0, int n0, int k0, int klen, bool vecA, bool vecB) {
+  constexpr int kKS = TcGeom<KC>::kKS, kOperandFloats = TcGeom<KC>::kOperandFloats;
+  constexpr int kVecPerRow = KC / 4, kVecShift = (KC == 256 ? 6 : 5), kVecIters = 32 * KC / 4 / kThreads;
   const int tid = threadIdx.x;
   const int kpad = (klen + 7) & ~7;      // zero padded to the MMA k granularity
 #pragma unroll 1
@@ -343,10 +352,10 @@ __device__ __noinline__ void tc_fill_stage(const GemmOp& o, float* stage, int m0
     const int dr = contig_k ? kKS : 1, dk = contig_k ? 1 : kMS;      // shared strides
     if (vec) {
 #pragma unroll 2
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kVecIters; ++i) {                    // 32 x KC floats = 8*KC vectors
         const int v = tid + i * kThreads;
-        const int r = contig_k ? (v >> 6) : ((v & 7) << 2);
-        const int k = contig_k ? ((v & 63) << 2) : (v >> 3);
+        const int r = contig_k ? (v >> kVecShift) : ((v & 7) << 2);
+        const int k = contig_k ? ((v & (kVecPerRow - 1)) << 2) : (v >> 3);
         const bool in = (row0 + r < R) && (k < klen);
         const float* src = in ? base + (size_t)(row0 + r) * sr + (size_t)(k0 + k) * sk : base;
         cp_async16(sm + r * dr + k * dk, src, in ? 16 : 0);
@@ -370,7 +379,9 @@ __device__ __noinline__ void tc_fill_stage(const GemmOp& o, float* stage, int m0
   }
 }
 
+template <int KC>
 __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* smem, int mode) {
+  constexpr int kKC = KC, kKS = TcGeom<KC>::kKS, kOperandFloats = TcGeom<KC>::kOperandFloats, kTcStageFloats = TcGeom<KC>::kStageFloats;
   const GemmOp o = og;                       // registers / local copy: the op descriptor lives in shared memory
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tm = tile / o.tiles_n, tn = tile - tm * o.tiles_n;
@@ -398,7 +409,7 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
   for (int st = -1; st < nstages; ++st) {
     if (st + 1 < nstages) {
       const int k0 = (st + 1) * kKC;
-      tc_fill_stage(og, smem + ((st + 1) & 1) * kTcStageFloats, m0, n0, k0, min(kKC, o.K - k0), vecA, vecB);
+      tc_fill_stage<KC>(og, smem + ((st + 1) & 1) * kTcStageFloats, m0, n0, k0, min(kKC, o.K - k0), vecA, vecB);
       cp_async_commit();
     }
     if (st < 0) {
@@ -509,7 +520,8 @@ struct SmemProgram { const Phase* phases; const Op* ops; const Ctx* ctx; int n_p
 
 __device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CTAS>
+__global__ void __launch_bounds__(kThreads, CTAS)
 ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* bar, Replica rp) {
   unsigned char* dyn_smem = reinterpret_cast<unsigned char*>(ilsw_dyn_smem_f);
   float* smem = ilsw_dyn_smem_f;
@@ -518,7 +530,8 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
   __shared__ double s_p1[kMaxNets], s_p2[kMaxNets], s_b1[kMaxNets], s_b2[kMaxNets];   // running beta^t per Adam slot
   __shared__ int s_pt[kMaxNets];
   const int n_phases = prog->n_phases, n_ops = prog->n_ops;
-  unsigned char* pbase = dyn_smem + (size_t)kTcSmemFloats * sizeof(float);
+  constexpr int KC = CTAS == 2 ? 128 : 256;
+  unsigned char* pbase = dyn_smem + (size_t)TcGeom<KC>::kSmemFloats * sizeof(float);
   Phase* s_phases = reinterpret_cast<Phase*>(pbase);
   Op* s_ops = reinterpret_cast<Op*>(pbase + align16(sizeof(Phase) * kMaxPhases));
   Ctx* s_ctx = reinterpret_cast<Ctx*>(reinterpret_cast<unsigned char*>(s_ops) + align16(sizeof(Op) * (size_t)n_ops));
@@ -571,12 +584,13 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
         const Op& o = s_ops[oi];
         if (o.kind == OP_GEMM) {
           if (prec == 0) gemm_tile_device(o.gemm, j, smem);
-          else gemm_tile_tc(o.gemm, j, smem, prec);
+          else gemm_tile_tc<KC>(o.gemm, j, smem, prec);
         } else if (o.kind == OP_ROW) {
           RowEnv env; env.lane = lane; env.nl = 32; env.warp = warp; env.sm = smem;
-          if (!(fast_rows && run_row_job_fast(c, a, o.row.kind, o.row.rows, s, j, env))) {
+          const int s_row = s + o.row.arg0;          // arg0 = 1: prefetch job for the next step
+          if (s_row < a.n_steps && !(fast_rows && run_row_job_fast(c, a, o.row.kind, o.row.rows, s_row, j, env))) {
             const int row = j * kRowsPerJob + warp;
-            if (row < o.row.rows) run_row(c, a, o.row.kind, s, row, lane, 32);
+            if (row < o.row.rows) run_row(c, a, o.row.kind, s_row, row, lane, 32);
           }
         } else if (o.kind == OP_ADAM) {
           __syncthreads();

@@ -442,7 +442,7 @@ ILSW_HDN void snapshot_sac(const Ctx& c, int lane, int nl) {
   stats_copy(st, S.y, B, lane, nl); st += B;
   stats_copy(st, S.lossterm[0], B, lane, nl); st += B;
   stats_copy(st, S.lossterm[1], B, lane, nl); st += B;
-  stats_copy(st, S.rew, B, lane, nl); st += B;
+  st += B;   // (reward slot: unused -- the batch reward buffer may already hold the prefetched next batch)
   if (td3) {
     stats_copy(st, S.act, B * A, lane, nl); st += B * A;
   } else {
@@ -740,6 +740,31 @@ ILSW_HDN void row_disc_reward_final(const Ctx& c, const RunArgs& a, int s, int r
   }
 }
 
+// generic form of the fused "dA = e0 . W0[:, O:O+A]" + head backward rows (the fast jobs are in
+// ilsw_rows_fast.cuh); used for shapes outside the fast path and as cross-check in the host simulator
+ILSW_HDN void row_da(const Ctx& c, int b, int nets, int lane, int nl) {
+  const SacBufs& S = c.s;
+  const int Hd = S.Hd, A = S.A, O = S.O, K0 = O + A;
+  for (int i = 0; i < nets; ++i) {
+    const MlpPtrs& Q = c.qf[i];
+    for (int j = 0; j < A; ++j) {
+      float acc = 0.f;
+      for (int n = lane; n < Hd; n += nl) acc += ldg(S.e0[i] + (size_t)b * Hd + n) * ldg(Q.p + Q.oW0 + (size_t)n * K0 + O + j);
+      acc = wsum(acc);
+      if (lane == 0) S.dA[i][(size_t)b * A + j] = acc;
+    }
+  }
+  wsync();
+}
+ILSW_HDN void row_sac_pibwd_da(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+  row_da(c, b, 2, lane, nl);
+  row_sac_pibwd(c, a, s, b, lane, nl);
+}
+ILSW_HDN void row_td3_pibwd_da(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+  row_da(c, b, 1, lane, nl);
+  row_td3_pibwd(c, a, s, b, lane, nl);
+}
+
 // ---- dispatcher --------------------------------------------------------------------------
 ILSW_HDN void run_row(const Ctx& c, const RunArgs& a, int kind, int s, int r, int lane, int nl) {
   switch (kind) {
@@ -748,6 +773,8 @@ ILSW_HDN void run_row(const Ctx& c, const RunArgs& a, int kind, int s, int r, in
     case ROW_SAC_TARGET: row_sac_target(c, a, s, r, lane, nl); break;
     case ROW_SAC_PLOSS: row_sac_ploss(c, a, s, r, lane, nl); break;
     case ROW_SAC_PIBWD: row_sac_pibwd(c, a, s, r, lane, nl); break;
+    case ROW_SAC_PIBWD_DA: row_sac_pibwd_da(c, a, s, r, lane, nl); break;
+    case ROW_TD3_PIBWD_DA: row_td3_pibwd_da(c, a, s, r, lane, nl); break;
     case ROW_SAC_FINAL: row_sac_final(c, a, s, r, lane, nl); break;
     case ROW_TD3_THEAD: row_td3_thead(c, a, s, r, lane, nl); break;
     case ROW_TD3_TARGET: row_td3_target(c, a, s, r, lane, nl); break;
@@ -770,6 +797,7 @@ ILSW_HDN void run_row(const Ctx& c, const RunArgs& a, int kind, int s, int r, in
 }
 
 ILSW_HD bool phase_active(const Phase& ph, const Hyper& hp, const RunArgs& a, int s) {
+  if (ph.cond == COND_FIRST_STEP) return s == 0;
   if (ph.cond == COND_TD3_POLICY) {
     int per = hp.period > 0 ? hp.period : 1;
     return ((a.step0 + s) % per) == 0;

@@ -99,9 +99,9 @@ struct Builder {
     g.C = G; g.ldc = Nin; g.aug_ones = gbias ? 1 : 0; g.bias_out = gbias; g.accumulate = accumulate;
     gemm(g);
   }
-  void row(int kind, int rows) {
+  void row(int kind, int rows, int next_step = 0) {
     Op* o = add(OP_ROW, (rows + kRowsPerJob - 1) / kRowsPerJob);
-    if (o) { o->row.kind = kind; o->row.rows = rows; }
+    if (o) { o->row.kind = kind; o->row.rows = rows; o->row.arg0 = next_step; }
   }
   void adam(const MlpPtrs& n, const MlpPtrs* target, double lr, double b1, double b2, double eps, float tau, int slot,
             int world_scale = 0) {
@@ -239,7 +239,9 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
   const float* h0p_obs = S.h0p + (size_t)B * Hd;
   const float* h1p_obs = S.h1p + (size_t)B * Hd;
 
-  b.phase(); b.row(ROW_SAC_GATHER, B);
+  // the batch of step s+1 is gathered in the LAST phase of step s (independent of everything that
+  // phase does); only the first step of a launch needs a gather phase of its own
+  b.phase(COND_FIRST_STEP); b.row(ROW_SAC_GATHER, B);
   b.phase();
   for (int i = 0; i < 2; ++i) b.fwd(S.Xoa, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0q[i], Hd, ACT_RELU);
   b.fwd(S.Xpi, S.ld_o, 2 * B, O, P.p + P.oW0, P.p + P.ob0, Hd, S.h0p, Hd, ACT_RELU);
@@ -276,9 +278,7 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
   b.phase(); b.row(ROW_SAC_PLOSS, B);
   b.phase();
   for (int i = 0; i < 2; ++i) b.dx(S.e1[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0n[i], Hd, ACT_RELU, S.e0[i], Hd);
-  b.phase();
-  for (int i = 0; i < 2; ++i) b.dx(S.e0[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW0 + O, K0, A, nullptr, 0, ACT_NONE, S.dA[i], A);
-  b.phase(); b.row(ROW_SAC_PIBWD, B);
+  b.phase(); b.row(ROW_SAC_PIBWD_DA, B);      // dA = e0 . W0[:, O:O+A] fused into the head backward rows
   b.phase();
   b.dx(S.d1p, Hd, B, Hd, P.p + P.oW1, Hd, Hd, h0p_obs, Hd, ACT_RELU, S.d0p, Hd);
   b.dw(S.d1p, Hd, Hd, h0p_obs, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);
@@ -289,6 +289,7 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
   b.phase(COND_ALWAYS, 1);
   b.adam(P, nullptr, c.hp.policy_lr, b1, b2, eps, 0.f, SLOT_POLICY, 1);
   b.row(ROW_SAC_FINAL, 1);
+  b.row(ROW_SAC_GATHER, B, /*next_step=*/1);
 }
 
 // S3
@@ -333,8 +334,7 @@ inline void build_td3(Builder& b, const Ctx& c) {
   b.phase(PC); b.fwd(S.h0n[0], Hd, B, Hd, c.qf[0].p + c.qf[0].oW1, c.qf[0].p + c.qf[0].ob1, Hd, S.h1n[0], Hd, ACT_RELU);
   b.phase(PC); b.row(ROW_TD3_PLOSS, B);
   b.phase(PC); b.dx(S.e1[0], Hd, B, Hd, c.qf[0].p + c.qf[0].oW1, Hd, Hd, S.h0n[0], Hd, ACT_RELU, S.e0[0], Hd);
-  b.phase(PC); b.dx(S.e0[0], Hd, B, Hd, c.qf[0].p + c.qf[0].oW0 + O, K0, A, nullptr, 0, ACT_NONE, S.dA[0], A);
-  b.phase(PC); b.row(ROW_TD3_PIBWD, B);
+  b.phase(PC); b.row(ROW_TD3_PIBWD_DA, B);
   b.phase(PC);
   b.dx(S.d1p, Hd, B, Hd, P.p + P.oW1, Hd, Hd, S.h0p, Hd, ACT_RELU, S.d0p, Hd);
   b.dw(S.d1p, Hd, Hd, S.h0p, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);

@@ -20,8 +20,8 @@ namespace ilsw {
 #define ILSW_VL 256      // host simulator: one lane owns the whole vector
 #endif
 constexpr int kFastMaxHid = 256;
-constexpr int kFastMaxAct = 64;
-constexpr int kRowStageFloats = 2 * kFastMaxAct * kFastMaxHid + 4 * kFastMaxHid;   // staged weights
+constexpr int kFastMaxAct = 32;
+constexpr int kRowStageFloats = 2 * kFastMaxAct * kFastMaxHid + 4 * kFastMaxHid;   // staged weights (68 KB + scratch <= the 80 KB GEMM staging area of the 2-CTA/SM variant)
 constexpr int kRowScratchPerWarp = 4 * kFastMaxAct;                                // per-warp exchange area
 
 struct RowEnv {
@@ -86,6 +86,36 @@ ILSW_HD const float* cta_stage(const RowEnv& e, const float* src, int n, int off
   return src;
 #endif
 }
+// stages W0[:, O:O+A] of a critic TRANSPOSED: dst[j*Hd + n] = W0[n*K0 + O + j]
+ILSW_HD const float* cta_stage_w0a(const RowEnv& e, const MlpPtrs& Q, int O, int A, int Hd, int off) {
+#ifdef __CUDA_ARCH__
+  float* dst = e.sm + off;
+  const int K0 = O + A, n = A * Hd;
+  for (int base = 0; base < n; base += 4 * (int)blockDim.x) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * (int)blockDim.x + (int)threadIdx.x;      // i = j*Hd + nn
+      v[u] = i < n ? __ldcg(Q.p + Q.oW0 + (size_t)(i % Hd) * K0 + O + i / Hd) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = base + u * (int)blockDim.x + (int)threadIdx.x; if (i < n) sts(dst + i, v[u]); }
+  }
+  return dst;
+#else
+  (void)e; (void)Q; (void)O; (void)A; (void)Hd; (void)off;
+  return nullptr;   // host: read the strided weights directly (see w0a())
+#endif
+}
+ILSW_HD float w0a(const float* staged, const MlpPtrs& Q, int O, int A, int Hd, int j, int n) {
+#ifdef __CUDA_ARCH__
+  (void)Q; (void)O; (void)A;
+  return lds(staged + (size_t)j * Hd + n);
+#else
+  (void)staged; (void)Hd;
+  return Q.p[Q.oW0 + (size_t)n * (O + A) + O + j];
+#endif
+}
 ILSW_HD void cta_sync() {
 #ifdef __CUDA_ARCH__
   __syncthreads();
@@ -94,7 +124,8 @@ ILSW_HD void cta_sync() {
 ILSW_HD float* warp_scratch(const RowEnv& e) { return e.sm + kRowStageFloats + e.warp * kRowScratchPerWarp; }
 
 ILSW_HD bool fast_rows_ok(const Ctx& c) {
-  return c.s.Hd <= kFastMaxHid && c.s.A <= kFastMaxAct && (!c.hp.has_disc || c.d.Hd <= kFastMaxHid);
+  return c.s.Hd <= kFastMaxHid && c.s.A <= kFastMaxAct && 4 * c.s.A * c.s.Hd <= kRowStageFloats &&
+         (!c.hp.has_disc || c.d.Hd <= kFastMaxHid);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -244,24 +275,46 @@ ILSW_HDN void job_sac_ploss(const Ctx& c, int job, const RowEnv& e) {
 // ---------------------------------------------------------------------------------------------
 // backward through the tanh-Gaussian head
 // ---------------------------------------------------------------------------------------------
-ILSW_HDN void job_sac_pibwd(const Ctx& c, int job, const RowEnv& e) {
+ILSW_HDN void job_sac_pibwd(const Ctx& c, int job, const RowEnv& e, bool with_da) {
   const SacBufs& S = c.s;
   const MlpPtrs& P = c.policy;
   const int Hd = S.Hd, A = S.A, B = S.B, lane = e.lane, nl = e.nl;
   const float* Wm = cta_stage(e, P.p + P.oW2, A * Hd, 0);
   const float* Ws = cta_stage(e, P.p + P.oW3, A * Hd, A * Hd);
+  const float* Wa[2] = {nullptr, nullptr};
+  if (with_da) for (int i = 0; i < 2; ++i) Wa[i] = cta_stage_w0a(e, c.qf[i], S.O, A, Hd, (2 + i) * A * Hd);
   const int b = job * kRowsPerJob + e.warp;
   const int r = B + b;
   Vec h;
   float* sc = warp_scratch(e);
   float lpi = 0.f;
+  if (with_da) {
+    // dA[b,j] = sum_n e0_i[b,n] * W0_i[n, O+j], both critics (formerly a GEMM phase of its own)
+    Vec e0[2];
+    if (b < B) for (int i = 0; i < 2; ++i) vload(e0[i], S.e0[i] + (size_t)b * Hd, Hd, lane, nl);
+    cta_sync();
+    if (b < B) {
+#pragma unroll 1
+      for (int j = 0; j < A; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int x = 0; x < ILSW_VL; ++x) {
+          const int n = lane + x * nl;
+          if (n < Hd) acc += e0[0].v[x] * w0a(Wa[0], c.qf[0], S.O, A, Hd, j, n) + e0[1].v[x] * w0a(Wa[1], c.qf[1], S.O, A, Hd, j, n);
+        }
+        acc = wsum(acc);
+        if (lane == 0) sts(sc + 2 * A + j, acc);
+      }
+    }
+    wsync();
+  }
   if (b < B) {
     vload(h, S.h1p + (size_t)r * Hd, Hd, lane, nl);
     const float alpha = ldg(&c.dyn->alpha);
     lpi = ldg(S.logpi + r);
     const float invB = 1.0f / (float)B, invBA = 1.0f / (float)(B * A);
     for (int j = lane; j < A; j += nl) {
-      const float gA = ldg(S.dA[0] + (size_t)b * A + j) + ldg(S.dA[1] + (size_t)b * A + j);
+      const float gA = with_da ? lds(sc + 2 * A + j) : ldg(S.dA[0] + (size_t)b * A + j) + ldg(S.dA[1] + (size_t)b * A + j);
       const float t = ldg(S.act + (size_t)r * A + j);
       const float mu = ldg(S.mean + (size_t)r * A + j), ls = ldg(S.lstd + (size_t)r * A + j), lr = ldg(S.lraw + (size_t)r * A + j);
       const float ep = ldg(S.eps + (size_t)r * A + j);
@@ -352,19 +405,40 @@ ILSW_HDN void job_td3_ploss(const Ctx& c, int job, const RowEnv& e) {
   cta_sync();
 }
 
-ILSW_HDN void job_td3_pibwd(const Ctx& c, int job, const RowEnv& e) {
+ILSW_HDN void job_td3_pibwd(const Ctx& c, int job, const RowEnv& e, bool with_da) {
   const SacBufs& S = c.s;
   const MlpPtrs& P = c.policy;
   const int Hd = S.Hd, A = S.A, lane = e.lane, nl = e.nl;
   const float* W = cta_stage(e, P.p + P.oW2, A * Hd, 0);
+  const float* Wa = with_da ? cta_stage_w0a(e, c.qf[0], S.O, A, Hd, A * Hd) : nullptr;
   const int b = job * kRowsPerJob + e.warp;
   Vec h;
   float* sc = warp_scratch(e);
+  if (with_da) {
+    Vec e0;
+    if (b < S.B) vload(e0, S.e0[0] + (size_t)b * Hd, Hd, lane, nl);
+    cta_sync();
+    if (b < S.B) {
+#pragma unroll 1
+      for (int j = 0; j < A; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int x = 0; x < ILSW_VL; ++x) {
+          const int n = lane + x * nl;
+          if (n < Hd) acc += e0.v[x] * w0a(Wa, c.qf[0], S.O, A, Hd, j, n);
+        }
+        acc = wsum(acc);
+        if (lane == 0) sts(sc + A + j, acc);
+      }
+    }
+    wsync();
+  }
   if (b < S.B) {
     vload(h, S.h1p + (size_t)b * Hd, Hd, lane, nl);
     for (int j = lane; j < A; j += nl) {
       const float t = ldg(S.act + (size_t)b * A + j);
-      sts(sc + j, ldg(S.dA[0] + (size_t)b * A + j) * c.hp.max_act * (1.0f - t * t));
+      const float gA = with_da ? lds(sc + A + j) : ldg(S.dA[0] + (size_t)b * A + j);
+      sts(sc + j, gA * c.hp.max_act * (1.0f - t * t));
     }
   }
   cta_sync();
@@ -510,11 +584,13 @@ ILSW_HD bool run_row_job_fast(const Ctx& c, const RunArgs& a, int kind, int rows
     case ROW_SAC_TARGET: job_critic_target(c, job, e, true, 1.0f); return true;
     case ROW_TD3_TARGET: job_critic_target(c, job, e, false, 2.0f); return true;
     case ROW_SAC_PLOSS: job_sac_ploss(c, job, e); return true;
-    case ROW_SAC_PIBWD: job_sac_pibwd(c, job, e); return true;
+    case ROW_SAC_PIBWD: job_sac_pibwd(c, job, e, false); return true;
+    case ROW_SAC_PIBWD_DA: job_sac_pibwd(c, job, e, true); return true;
     case ROW_TD3_THEAD: job_td3_head(c, job, e, true); return true;
     case ROW_TD3_PHEAD: job_td3_head(c, job, e, false); return true;
     case ROW_TD3_PLOSS: job_td3_ploss(c, job, e); return true;
-    case ROW_TD3_PIBWD: job_td3_pibwd(c, job, e); return true;
+    case ROW_TD3_PIBWD: job_td3_pibwd(c, job, e, false); return true;
+    case ROW_TD3_PIBWD_DA: job_td3_pibwd(c, job, e, true); return true;
     case ROW_DISC_HEAD: job_disc_head(c, job, e, rows); return true;
     case ROW_DISC_EW1: case ROW_DISC_EW2: case ROW_DISC_EW3: job_disc_ew(c, kind, job, e); return true;
     case ROW_DISC_REWARD: job_disc_reward(c, job, e); return true;

@@ -20,7 +20,7 @@
 namespace ilsw {
 
 constexpr int kMaxPhases = 96;
-constexpr int kMaxOps = 256;
+constexpr int kMaxOps = 128;
 constexpr int kMaxNets = 8;       // Adam step-counter slots
 constexpr int kLossSlots = 16;    // floats per step in the loss log
 constexpr int kThreads = 256;     // CTA size of the engine kernel
@@ -32,7 +32,7 @@ enum OpKind : int { OP_GEMM = 1, OP_ADAM = 2, OP_ROW = 3, OP_POLYAK = 4 };
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 
 // phase conditions
-enum Cond : int { COND_ALWAYS = 0, COND_TD3_POLICY = 1 };
+enum Cond : int { COND_ALWAYS = 0, COND_TD3_POLICY = 1, COND_FIRST_STEP = 2 };
 
 // loss-log slots (per step)
 enum LossSlot : int {
@@ -72,7 +72,7 @@ struct PolyakOp { float* target; const float* src; int n; float tau; };
 struct RowOp {
   int kind;             // algorithm-specific row kernel id
   int rows;             // number of rows (jobs = ceil(rows / kRowsPerJob))
-  int arg0, arg1;
+  int arg0, arg1;       // arg0 = 1: the job works for step s+1 (batch prefetch), skipped on the last step
 };
 
 struct Op {
@@ -221,7 +221,8 @@ enum RowKind : int {
   ROW_TD3_FINAL, ROW_TD3_FINAL_POLICY,
   ROW_DISC_GATHER, ROW_DISC_HEAD, ROW_DISC_GNORM, ROW_DISC_EW1, ROW_DISC_EW2, ROW_DISC_EW3,
   ROW_DISC_FINAL, ROW_DISC_REWARD, ROW_DISC_REWARD_FINAL,
-  ROW_SACV_HEADS, ROW_SACV_TARGET, ROW_SACV_VTARGET, ROW_SACV_PLOSS, ROW_SACV_FINAL
+  ROW_SACV_HEADS, ROW_SACV_TARGET, ROW_SACV_VTARGET, ROW_SACV_PLOSS, ROW_SACV_FINAL,
+  ROW_SAC_PIBWD_DA, ROW_TD3_PIBWD_DA      // policy-head backward fused with dA = e0 . W0[:, O:O+A]
 };
 
 }  // namespace ilsw

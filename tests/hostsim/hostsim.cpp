@@ -45,6 +45,8 @@ static void run_op(HostSim* hs, const Program& P, const Op& o, const RunArgs& a,
       }
   } else if (o.kind == OP_ROW) {
     const bool fast = !hs->generic_rows && fast_rows_ok(c);
+    s += o.row.arg0;                               // arg0 = 1: prefetch job for the next step
+    if (s >= a.n_steps) return;
     for (int job = 0; job < o.n_jobs; ++job)
       for (int w = 0; w < kRowsPerJob; ++w) {
         RowEnv env; env.lane = 0; env.nl = 1; env.warp = w; env.sm = hs->rowbuf.data();

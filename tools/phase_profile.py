@@ -17,7 +17,9 @@ def main():
     for a in sys.argv[1:]:
         if a.startswith("--precision="):
             os.environ["ILSW_GEMM_PRECISION"] = a.split("=")[1]
-    print("gemm precision mode:", os.environ.get("ILSW_GEMM_PRECISION", "3 (default)"))
+        if a.startswith("--ctas="):
+            os.environ["ILSW_CTAS_PER_SM"] = a.split("=")[1]
+    print("gemm precision mode:", os.environ.get("ILSW_GEMM_PRECISION", "default"), " ctas/SM:", os.environ.get("ILSW_CTAS_PER_SM", "auto"))
     for name in names:
         w = bench.WORKLOADS[name]
         tr, buf, irl = bench.build_ours(w, seed=1, steps_per_launch=200)
@@ -37,6 +39,8 @@ def main():
         print("== %s: %.1f us/step (launch avg), last-step phase sum %.1f us, %d phases" %
               (name, e0.elapsed_time(e1) * 1000 / 200, us.sum(), len(us)))
         for t, j, d in zip(us, tr.engine.last_job_us, desc):
+            if t == 0:
+                continue
             print("  %7.2f us (cta0 jobs %6.2f, barrier+wait %6.2f)  %s" % (t, j, t - j, d))
 
 
