@@ -486,6 +486,11 @@ extern "C" int ilsw_read_phase_ns(ilsw_trainer* tr, unsigned long long* host_out
   CU(cudaStreamSynchronize(st));
   return ILSW_OK;
 }
+extern "C" int ilsw_read_tile_ns(unsigned long long* host_out /* [kMaxPhases][8] */) {
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(host_out, g_tile_ns, sizeof(unsigned long long) * kMaxPhases * 8));
+  return ILSW_OK;
+}
 extern "C" int ilsw_num_phases(const ilsw_trainer* tr) { return tr ? tr->host_prog.n_phases : ILSW_ERR_ARG; }
 extern "C" int64_t ilsw_kernel_launches(const ilsw_trainer* tr) { return tr ? tr->launches : ILSW_ERR_ARG; }
 

@@ -303,19 +303,54 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, i
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ uint32_t cvt_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// fp32 -> tf32 with round-to-nearest (ties away) done in INTEGER arithmetic (IADD + LOP3 on the fast
+// pipes).  cvt.rna.tf32.f32 issues on the 16-lane/clk conversion pipe: with 6-12 conversions per
+// MMA it, not the tensor core, paced the tile (measured 2.9 us for 32 k-steps).  Same result as
+// cvt.rna for finite values.
+__device__ __forceinline__ uint32_t cvt_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// fragment loads: typed shared array indexed by byte offset from the dynamic-smem base
-__device__ __forceinline__ float lds_u32(unsigned byte_off) { return ilsw_dyn_smem_f[byte_off >> 2]; }
+// profiling: CTA 0 / thread 0 stamps the stages of its LAST tile of every phase (read with
+// ilsw_read_tile_ns): [phase][0..4] = tile start, panels issued, panels landed, MMA done, epilogue done
+__device__ unsigned long long g_tile_ns[kMaxPhases][8];
+__device__ int g_dbg_phase;
+#define ILSW_TSTAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_tile_ns[g_dbg_phase][i] = globaltimer_ns(); } while (0)
+
+// the 6 fragment words of one k-step (A: rows g,g+8 x k q,q+4; B: k q,q+4) with explicit 32-bit shared
+// addresses, issued back to back by one asm block
+struct Frag { float a[4]; float b[2]; };
+__device__ __forceinline__ void frag_load(Frag& f, unsigned ap, unsigned a_row8, unsigned a_k4, unsigned bp, unsigned b_k4) {
+  asm volatile(
+      "ld.shared.f32 %0, [%6];\n\t"
+      "ld.shared.f32 %1, [%7];\n\t"
+      "ld.shared.f32 %2, [%8];\n\t"
+      "ld.shared.f32 %3, [%9];\n\t"
+      "ld.shared.f32 %4, [%10];\n\t"
+      "ld.shared.f32 %5, [%11];"
+      : "=f"(f.a[0]), "=f"(f.a[1]), "=f"(f.a[2]), "=f"(f.a[3]), "=f"(f.b[0]), "=f"(f.b[1])
+      : "r"(ap), "r"(ap + a_row8), "r"(ap + a_k4), "r"(ap + a_row8 + a_k4), "r"(bp), "r"(bp + b_k4)
+      : "memory");
+}
+__device__ __forceinline__ void frag_mma(float (&acc)[4], const Frag& f, int mode) {
+  uint32_t ah[4], bh[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ah[i] = cvt_tf32(f.a[i]);
+  bh[0] = cvt_tf32(f.b[0]); bh[1] = cvt_tf32(f.b[1]);
+  if (mode == 3) {
+    uint32_t al[4], bl[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) al[i] = cvt_tf32(f.a[i] - __uint_as_float(ah[i]));
+#pragma unroll
+    for (int i = 0; i < 2; ++i) bl[i] = cvt_tf32(f.b[i] - __uint_as_float(bh[i]));
+    mma_tf32(acc, al, bh);
+    mma_tf32(acc, ah, bl);
+  }
+  mma_tf32(acc, ah, bh);
+}
 __device__ __forceinline__ void cp_async4(unsigned smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
@@ -337,7 +372,7 @@ __device__ __noinline__ void tc_fill_stage(const GemmOp& o, float* stage, int m0
   constexpr int kKS = TcGeom<KC>::kKS, kOperandFloats = TcGeom<KC>::kOperandFloats;
   constexpr int kVecPerRow = KC / 4, kVecShift = (KC == 256 ? 6 : 5), kVecIters = 32 * KC / 4 / kThreads;
   const int tid = threadIdx.x;
-  const int kpad = (klen + 7) & ~7;      // zero padded to the MMA k granularity
+  const int kpad = (klen + 15) & ~15;    // zero padded to TWO MMA k-steps (the k loop is unrolled by 2, unguarded)
 #pragma unroll 1
   for (int op = 0; op < 2; ++op) {
     const bool isB = op != 0;
@@ -395,10 +430,15 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
   const int nstages = (o.K + kKC - 1) / kKC;
   const int Nt = o.N + o.aug_ones;
   const int r0 = m0 + mb * 16 + g, c0 = n0 + nb * 8 + 2 * q;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float accs[2][4];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) accs[u][i] = 0.f;
   EpiIn ein[4];
+  ILSW_TSTAMP(0);
   // fragment addressing (32-bit shared addresses, bytes)
-  const unsigned sbase = 4u * (unsigned)(smem - ilsw_dyn_smem_f);   // byte offset inside dynamic shared memory
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
   const unsigned a_off = 4u * (a_kc ? (mb * 16 + g) * kKS + q : q * kMS + mb * 16 + g);
   const unsigned b_off = 4u * (b_kc ? (nb * 8 + g) * kKS + q : q * kMS + nb * 8 + g);
   const unsigned a_row8 = 4u * (a_kc ? 8 * kKS : 8), a_k4 = 4u * (a_kc ? 4 : 4 * kMS), a_k8 = 2u * a_k4;
@@ -419,50 +459,44 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
         const int m = r0 + ((i & 2) ? 8 : 0), n = c0 + (i & 1);
         if (m < o.M && n < Nt) ein[i] = epi_load(o, m, n);
       }
+      ILSW_TSTAMP(1);
       continue;
     }
     if (st + 1 < nstages) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
+    if (st == 0) ILSW_TSTAMP(2);
     if (warp_live) {
       const int klen = min(kKC, o.K - st * kKC);
-      const int ksteps = (klen + 7) >> 3;       // panels are zero padded up to a multiple of 8
+      const int ksteps = ((klen + 15) >> 4) << 1;   // panels are zero padded up to a multiple of 16
       unsigned ap = sbase + 4u * (unsigned)((st & 1) * kTcStageFloats) + a_off;
       unsigned bp = sbase + 4u * (unsigned)((st & 1) * kTcStageFloats + kOperandFloats) + b_off;
-      if (mode == 3) {
-#pragma unroll 2
-        for (int ks = 0; ks < ksteps; ++ks) {
-          float af[4], bf[2];
-          af[0] = lds_u32(ap); af[1] = lds_u32(ap + a_row8); af[2] = lds_u32(ap + a_k4); af[3] = lds_u32(ap + a_row8 + a_k4);
-          bf[0] = lds_u32(bp); bf[1] = lds_u32(bp + b_k4);
-          ap += a_k8; bp += b_k8;
-          uint32_t ah[4], bh[2], al[4], bl[2];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { ah[i] = cvt_tf32(af[i]); al[i] = cvt_tf32(af[i] - __uint_as_float(ah[i])); }
-#pragma unroll
-          for (int i = 0; i < 2; ++i) { bh[i] = cvt_tf32(bf[i]); bl[i] = cvt_tf32(bf[i] - __uint_as_float(bh[i])); }
-          mma_tf32(acc, al, bh);
-          mma_tf32(acc, ah, bl);
-          mma_tf32(acc, ah, bh);
-        }
-      } else {
-#pragma unroll 4
-        for (int ks = 0; ks < ksteps; ++ks) {
-          uint32_t ah[4], bh[2];
-          ah[0] = cvt_tf32(lds_u32(ap)); ah[1] = cvt_tf32(lds_u32(ap + a_row8));
-          ah[2] = cvt_tf32(lds_u32(ap + a_k4)); ah[3] = cvt_tf32(lds_u32(ap + a_row8 + a_k4));
-          bh[0] = cvt_tf32(lds_u32(bp)); bh[1] = cvt_tf32(lds_u32(bp + b_k4));
-          ap += a_k8; bp += b_k8;
-          mma_tf32(acc, ah, bh);
-        }
+      // Software-pipelined k loop, unrolled by two with ping-pong fragment registers and two
+      // independent accumulator sets: the loads of step k+1 are issued before the MMA of step k, there
+      // is no per-step guard (panels are zero padded to an even number of steps; the last prefetch
+      // reads one step past the panel, inside the shared allocation, and is never used).
+      Frag f0, f1;
+      frag_load(f0, ap, a_row8, a_k4, bp, b_k4);
+      ap += a_k8; bp += b_k8;
+#pragma unroll 1
+      for (int k2 = 0; k2 < ksteps; k2 += 2) {
+        frag_load(f1, ap, a_row8, a_k4, bp, b_k4);
+        ap += a_k8; bp += b_k8;
+        frag_mma(accs[0], f0, mode);
+        frag_load(f0, ap, a_row8, a_k4, bp, b_k4);
+        ap += a_k8; bp += b_k8;
+        frag_mma(accs[1], f1, mode);
       }
     }
     __syncthreads();   // stage buffer may be refilled by the next iteration's prefetch
   }
+  ILSW_TSTAMP(3);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = r0 + ((i & 2) ? 8 : 0), n = c0 + (i & 1);
-    if (m < o.M && n < Nt) epi_store(o, m, n, acc[i], ein[i]);
+    const float accv = accs[0][i] + accs[1][i];
+    if (m < o.M && n < Nt) epi_store(o, m, n, accv, ein[i]);
   }
+  ILSW_TSTAMP(4);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -573,6 +607,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
     __syncthreads();
     for (int ph = 0; ph < n_phases; ++ph) {
       const Phase& P = s_phases[ph];
+      if (blockIdx.x == 0 && threadIdx.x == 0) g_dbg_phase = ph;
       if (!phase_active(P, c.hp, a, s)) { if (stamp) c.phase_ns[ph + 1] = c.phase_ns[ph]; continue; }
       const bool exchange = P.collective && rp.world > 1;
       // exchange sequence number = number of policy updates so far (parity double-buffers the slots)

@@ -26,29 +26,38 @@ constexpr int kRowScratchPerWarp = 4 * kFastMaxAct;                             
 
 struct RowEnv {
   int lane, nl, warp;
-  float* sm;            // device: CTA shared memory (>= kRowStageFloats + 8*kRowScratchPerWarp floats); host: scratch
+  float* sm;            // host simulator: scratch buffer (>= kRowStageFloats + 8*kRowScratchPerWarp floats); device: the
+                        // dynamic shared memory base (staging always starts at offset 0)
 };
 
 struct Vec { float v[ILSW_VL]; };
 
-// Staged data lives in the CTA's dynamic SHARED memory on the device.  Accesses go through the
-// typed extern array (plain LDS/STS with ordinary memory semantics: the compiler may batch them
-// but never moves them across __syncthreads), addressed by the float offset of the generic pointer.
+// Staged data lives in the CTA's dynamic SHARED memory on the device.  SPtr is a "shared pointer":
+// on the device it is a float OFFSET into the typed extern shared array (plain LDS/STS with an
+// immediate/register offset: no generic-address conversion per access, ordinary memory semantics so
+// the compiler batches loads but never moves them across __syncthreads); on the host simulator it
+// is an ordinary pointer.
 #if defined(__CUDACC__)
 extern __shared__ __align__(16) float ilsw_dyn_smem_f[];
 #endif
-ILSW_HD float lds(const float* p) {
+struct SPtr {
+  const float* p;   // host
+  int off;          // device
+  ILSW_HD SPtr operator+(size_t i) const { SPtr r; r.p = p ? p + i : p; r.off = off + (int)i; return r; }
+};
+ILSW_HD SPtr sptr_null() { SPtr r; r.p = nullptr; r.off = 0; return r; }
+ILSW_HD float lds(const SPtr& s) {
 #ifdef __CUDA_ARCH__
-  return ilsw_dyn_smem_f[(int)(p - ilsw_dyn_smem_f)];
+  return ilsw_dyn_smem_f[s.off];
 #else
-  return *p;
+  return *s.p;
 #endif
 }
-ILSW_HD void sts(float* p, float v) {
+ILSW_HD void sts(const SPtr& s, float v) {
 #ifdef __CUDA_ARCH__
-  ilsw_dyn_smem_f[(int)(p - ilsw_dyn_smem_f)] = v;
+  ilsw_dyn_smem_f[s.off] = v;
 #else
-  *p = v;
+  *const_cast<float*>(s.p) = v;
 #endif
 }
 
@@ -60,7 +69,7 @@ ILSW_HD void vload_plain(Vec& x, const float* p, int n, int lane, int nl) {   //
 #pragma unroll
   for (int i = 0; i < ILSW_VL; ++i) { const int k = lane + i * nl; x.v[i] = k < n ? p[k] : 0.f; }
 }
-ILSW_HD float vdot_s(const Vec& h, const float* w, int n, int lane, int nl) {   // w staged/plain
+ILSW_HD float vdot_s(const Vec& h, const SPtr& w, int n, int lane, int nl) {   // w staged/plain
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < ILSW_VL; ++i) { const int k = lane + i * nl; if (k < n) s += h.v[i] * lds(w + k); }
@@ -68,9 +77,11 @@ ILSW_HD float vdot_s(const Vec& h, const float* w, int n, int lane, int nl) {   
 }
 
 // CTA-cooperative staging (device) / passthrough (host).  All threads of the CTA must call.
-ILSW_HD const float* cta_stage(const RowEnv& e, const float* src, int n, int off) {
+ILSW_HD SPtr cta_stage(const RowEnv& e, const float* src, int n, int off) {
+  SPtr r;
 #ifdef __CUDA_ARCH__
-  float* dst = e.sm + off;
+  (void)e;
+  r.p = nullptr; r.off = off;
   // batches of 4 loads per thread are issued together (a store between two loads would
   // serialise them into separate L2 round trips), then stored
   for (int base = 0; base < n; base += 4 * (int)blockDim.x) {
@@ -78,18 +89,20 @@ ILSW_HD const float* cta_stage(const RowEnv& e, const float* src, int n, int off
 #pragma unroll
     for (int u = 0; u < 4; ++u) { const int i = base + u * (int)blockDim.x + (int)threadIdx.x; v[u] = i < n ? __ldcg(src + i) : 0.f; }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int i = base + u * (int)blockDim.x + (int)threadIdx.x; if (i < n) sts(dst + i, v[u]); }
+    for (int u = 0; u < 4; ++u) { const int i = base + u * (int)blockDim.x + (int)threadIdx.x; if (i < n) ilsw_dyn_smem_f[off + i] = v[u]; }
   }
-  return dst;
 #else
   (void)e; (void)n; (void)off;
-  return src;
+  r.p = src; r.off = 0;
 #endif
+  return r;
 }
 // stages W0[:, O:O+A] of a critic TRANSPOSED: dst[j*Hd + n] = W0[n*K0 + O + j]
-ILSW_HD const float* cta_stage_w0a(const RowEnv& e, const MlpPtrs& Q, int O, int A, int Hd, int off) {
+ILSW_HD SPtr cta_stage_w0a(const RowEnv& e, const MlpPtrs& Q, int O, int A, int Hd, int off) {
+  SPtr r;
 #ifdef __CUDA_ARCH__
-  float* dst = e.sm + off;
+  (void)e;
+  r.p = nullptr; r.off = off;
   const int K0 = O + A, n = A * Hd;
   for (int base = 0; base < n; base += 4 * (int)blockDim.x) {
     float v[4];
@@ -99,18 +112,18 @@ ILSW_HD const float* cta_stage_w0a(const RowEnv& e, const MlpPtrs& Q, int O, int
       v[u] = i < n ? __ldcg(Q.p + Q.oW0 + (size_t)(i % Hd) * K0 + O + i / Hd) : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int i = base + u * (int)blockDim.x + (int)threadIdx.x; if (i < n) sts(dst + i, v[u]); }
+    for (int u = 0; u < 4; ++u) { const int i = base + u * (int)blockDim.x + (int)threadIdx.x; if (i < n) ilsw_dyn_smem_f[off + i] = v[u]; }
   }
-  return dst;
 #else
   (void)e; (void)Q; (void)O; (void)A; (void)Hd; (void)off;
-  return nullptr;   // host: read the strided weights directly (see w0a())
+  r.p = nullptr; r.off = 0;   // host: read the strided weights directly (see w0a())
 #endif
+  return r;
 }
-ILSW_HD float w0a(const float* staged, const MlpPtrs& Q, int O, int A, int Hd, int j, int n) {
+ILSW_HD float w0a(const SPtr& staged, const MlpPtrs& Q, int O, int A, int Hd, int j, int n) {
 #ifdef __CUDA_ARCH__
   (void)Q; (void)O; (void)A;
-  return lds(staged + (size_t)j * Hd + n);
+  return ilsw_dyn_smem_f[staged.off + j * Hd + n];
 #else
   (void)staged; (void)Hd;
   return Q.p[Q.oW0 + (size_t)n * (O + A) + O + j];
@@ -121,7 +134,12 @@ ILSW_HD void cta_sync() {
   __syncthreads();
 #endif
 }
-ILSW_HD float* warp_scratch(const RowEnv& e) { return e.sm + kRowStageFloats + e.warp * kRowScratchPerWarp; }
+ILSW_HD SPtr warp_scratch(const RowEnv& e) {
+  SPtr r;
+  r.p = e.sm + kRowStageFloats + e.warp * kRowScratchPerWarp;   // host: scratch buffer; device: unused
+  r.off = kRowStageFloats + e.warp * kRowScratchPerWarp;
+  return r;
+}
 
 ILSW_HD bool fast_rows_ok(const Ctx& c) {
   return c.s.Hd <= kFastMaxHid && c.s.A <= kFastMaxAct && 4 * c.s.A * c.s.Hd <= kRowStageFloats &&
@@ -135,16 +153,16 @@ ILSW_HDN void job_sac_heads(const Ctx& c, int job, const RowEnv& e) {
   const SacBufs& S = c.s;
   const MlpPtrs& P = c.policy;
   const int A = S.A, Hd = S.Hd, B = S.B, O = S.O, lane = e.lane, nl = e.nl;
-  const float* Wm = cta_stage(e, P.p + P.oW2, A * Hd, 0);
-  const float* Ws = cta_stage(e, P.p + P.oW3, A * Hd, A * Hd);
-  const float* bm = cta_stage(e, P.p + P.ob2, A, 2 * A * Hd);
-  const float* bs = cta_stage(e, P.p + P.ob3, A, 2 * A * Hd + A);
+  const SPtr Wm = cta_stage(e, P.p + P.oW2, A * Hd, 0);
+  const SPtr Ws = cta_stage(e, P.p + P.oW3, A * Hd, A * Hd);
+  const SPtr bm = cta_stage(e, P.p + P.ob2, A, 2 * A * Hd);
+  const SPtr bs = cta_stage(e, P.p + P.ob3, A, 2 * A * Hd + A);
   const int r = job * kRowsPerJob + e.warp;
   Vec h;
   if (r < 2 * B) vload(h, S.h1p + (size_t)r * Hd, Hd, lane, nl);
   cta_sync();
   if (r < 2 * B) {
-    float* sc = warp_scratch(e);
+    const SPtr sc = warp_scratch(e);
 #pragma unroll 1
     for (int j = 0; j < A; ++j) {
       float mu = vdot_s(h, Wm + (size_t)j * Hd, Hd, lane, nl) + lds(bm + j);
@@ -183,7 +201,7 @@ ILSW_HDN void job_sac_heads(const Ctx& c, int job, const RowEnv& e) {
 ILSW_HDN void job_critic_target(const Ctx& c, int job, const RowEnv& e, bool use_entropy, float loss_grad_factor) {
   const SacBufs& S = c.s;
   const int Hd = S.Hd, lane = e.lane, nl = e.nl;
-  const float* tw[2]; const float* qw[2];
+  SPtr tw[2], qw[2];
   for (int i = 0; i < 2; ++i) {
     tw[i] = cta_stage(e, c.tqf[i].p + c.tqf[i].oW2, Hd, i * Hd);
     qw[i] = cta_stage(e, c.qf[i].p + c.qf[i].oW2, Hd, (2 + i) * Hd);
@@ -233,7 +251,7 @@ ILSW_HDN void job_critic_target(const Ctx& c, int job, const RowEnv& e, bool use
 ILSW_HDN void job_sac_ploss(const Ctx& c, int job, const RowEnv& e) {
   const SacBufs& S = c.s;
   const int Hd = S.Hd, A = S.A, B = S.B, lane = e.lane, nl = e.nl;
-  const float* qw[2];
+  SPtr qw[2];
   for (int i = 0; i < 2; ++i) qw[i] = cta_stage(e, c.qf[i].p + c.qf[i].oW2, Hd, i * Hd);
   const int b = job * kRowsPerJob + e.warp;
   Vec h[2];
@@ -279,14 +297,14 @@ ILSW_HDN void job_sac_pibwd(const Ctx& c, int job, const RowEnv& e, bool with_da
   const SacBufs& S = c.s;
   const MlpPtrs& P = c.policy;
   const int Hd = S.Hd, A = S.A, B = S.B, lane = e.lane, nl = e.nl;
-  const float* Wm = cta_stage(e, P.p + P.oW2, A * Hd, 0);
-  const float* Ws = cta_stage(e, P.p + P.oW3, A * Hd, A * Hd);
-  const float* Wa[2] = {nullptr, nullptr};
+  const SPtr Wm = cta_stage(e, P.p + P.oW2, A * Hd, 0);
+  const SPtr Ws = cta_stage(e, P.p + P.oW3, A * Hd, A * Hd);
+  SPtr Wa[2] = {sptr_null(), sptr_null()};
   if (with_da) for (int i = 0; i < 2; ++i) Wa[i] = cta_stage_w0a(e, c.qf[i], S.O, A, Hd, (2 + i) * A * Hd);
   const int b = job * kRowsPerJob + e.warp;
   const int r = B + b;
   Vec h;
-  float* sc = warp_scratch(e);
+  const SPtr sc = warp_scratch(e);
   float lpi = 0.f;
   if (with_da) {
     // dA[b,j] = sum_n e0_i[b,n] * W0_i[n, O+j], both critics (formerly a GEMM phase of its own)
@@ -353,14 +371,14 @@ ILSW_HDN void job_td3_head(const Ctx& c, int job, const RowEnv& e, bool target) 
   const SacBufs& S = c.s;
   const MlpPtrs& P = target ? c.tpolicy : c.policy;
   const int A = S.A, Hd = S.Hd, O = S.O, lane = e.lane, nl = e.nl;
-  const float* W = cta_stage(e, P.p + P.oW2, A * Hd, 0);
-  const float* bb = cta_stage(e, P.p + P.ob2, A, A * Hd);
+  const SPtr W = cta_stage(e, P.p + P.oW2, A * Hd, 0);
+  const SPtr bb = cta_stage(e, P.p + P.ob2, A, A * Hd);
   const int b = job * kRowsPerJob + e.warp;
   Vec h;
   if (b < S.B) vload(h, (target ? S.h1tp : S.h1p) + (size_t)b * Hd, Hd, lane, nl);
   cta_sync();
   if (b < S.B) {
-    float* sc = warp_scratch(e);
+    const SPtr sc = warp_scratch(e);
     for (int j = 0; j < A; ++j) {
       const float pre = vdot_s(h, W + (size_t)j * Hd, Hd, lane, nl) + lds(bb + j);
       if (lane == 0) sts(sc + j, pre);
@@ -385,7 +403,7 @@ ILSW_HDN void job_td3_ploss(const Ctx& c, int job, const RowEnv& e) {
   const SacBufs& S = c.s;
   const MlpPtrs& Q = c.qf[0];
   const int Hd = S.Hd, lane = e.lane, nl = e.nl;
-  const float* qw = cta_stage(e, Q.p + Q.oW2, Hd, 0);
+  const SPtr qw = cta_stage(e, Q.p + Q.oW2, Hd, 0);
   const int b = job * kRowsPerJob + e.warp;
   Vec h;
   float qb = 0.f;
@@ -409,11 +427,12 @@ ILSW_HDN void job_td3_pibwd(const Ctx& c, int job, const RowEnv& e, bool with_da
   const SacBufs& S = c.s;
   const MlpPtrs& P = c.policy;
   const int Hd = S.Hd, A = S.A, lane = e.lane, nl = e.nl;
-  const float* W = cta_stage(e, P.p + P.oW2, A * Hd, 0);
-  const float* Wa = with_da ? cta_stage_w0a(e, c.qf[0], S.O, A, Hd, A * Hd) : nullptr;
+  const SPtr W = cta_stage(e, P.p + P.oW2, A * Hd, 0);
+  SPtr Wa = sptr_null();
+  if (with_da) Wa = cta_stage_w0a(e, c.qf[0], S.O, A, Hd, A * Hd);
   const int b = job * kRowsPerJob + e.warp;
   Vec h;
-  float* sc = warp_scratch(e);
+  const SPtr sc = warp_scratch(e);
   if (with_da) {
     Vec e0;
     if (b < S.B) vload(e0, S.e0[0] + (size_t)b * Hd, Hd, lane, nl);
@@ -466,7 +485,7 @@ ILSW_HDN void job_disc_head(const Ctx& c, int job, const RowEnv& e, int rows) {
   const DiscBufs& Dd = c.d;
   const MlpPtrs& N = c.disc;
   const int B = Dd.B, Hd = Dd.Hd, lane = e.lane, nl = e.nl;
-  const float* w3 = cta_stage(e, N.p + N.oW2, Hd, 0);
+  const SPtr w3 = cta_stage(e, N.p + N.oW2, Hd, 0);
   const int r = job * kRowsPerJob + e.warp;
   Vec h2;
   float b3 = 0.f;
@@ -550,7 +569,7 @@ ILSW_HDN void job_disc_reward(const Ctx& c, int job, const RowEnv& e) {
   const DiscBufs& Dd = c.d;
   const MlpPtrs& N = c.disc;
   const int Hd = Dd.Hd, lane = e.lane, nl = e.nl;
-  const float* w3 = cta_stage(e, N.p + N.oW2, Hd, 0);
+  const SPtr w3 = cta_stage(e, N.p + N.oW2, Hd, 0);
   const int b = job * kRowsPerJob + e.warp;
   Vec h;
   float b3 = 0.f;

@@ -202,6 +202,8 @@ int ilsw_num_phases(const ilsw_trainer* tr);
 /* profiling: %globaltimer (ns) at the start and after every phase barrier of the LAST step of the
  * most recent launch: out[0..n_phases] */
 int ilsw_read_phase_ns(ilsw_trainer* tr, unsigned long long* host_out, int n, void* stream);
+/* profiling: stage stamps of CTA 0's last tensor-core GEMM tile in every phase: out[96][8] (ns) */
+int ilsw_read_tile_ns(unsigned long long* host_out);
 int64_t ilsw_kernel_launches(const ilsw_trainer* tr);   /* engine launches so far */
 
 /* A1: sampler-side policy inference for <= 64 env rows (policies.py:245-246, core.py:74-89).

@@ -38,9 +38,16 @@ def main():
         desc = tr.engine.describe().strip().split("\n")
         print("== %s: %.1f us/step (launch avg), last-step phase sum %.1f us, %d phases" %
               (name, e0.elapsed_time(e1) * 1000 / 200, us.sum(), len(us)))
-        for t, j, d in zip(us, tr.engine.last_job_us, desc):
+        import ctypes as C
+        tile = np.zeros((96, 8), dtype=np.uint64)
+        tr.engine.lib.ilsw_read_tile_ns(tile.ctypes.data_as(C.c_void_p))
+        tile = tile.astype(np.int64)
+        for i, (t, j, d) in enumerate(zip(us, tr.engine.last_job_us, desc)):
             if t == 0:
                 continue
+            if "GEMM" in d and tile[i, 4] > 0:
+                st = np.diff(tile[i, :5]) / 1000.0
+                d += "   [last tile of cta0: issue %.2f  land %.2f  mma %.2f  epi %.2f us]" % tuple(st)
             print("  %7.2f us (cta0 jobs %6.2f, barrier+wait %6.2f)  %s" % (t, j, t - j, d))
 
 
