@@ -623,8 +623,8 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
         } else if (o.kind == OP_ROW) {
           RowEnv env; env.lane = lane; env.nl = 32; env.warp = warp; env.sm = smem;
           const int s_row = s + o.row.arg0;          // arg0 = 1: prefetch job for the next step
-          if (s_row < a.n_steps && !(fast_rows && run_row_job_fast(c, a, o.row.kind, o.row.rows, s_row, j, env))) {
-            const int row = j * kRowsPerJob + warp;
+          if (s_row < a.n_steps && !(fast_rows && run_row_job_fast(c, a, o.row.kind, o.row.rows, s_row, j + o.row.arg1 / kRowsPerJob, env))) {
+            const int row = o.row.arg1 + j * kRowsPerJob + warp;     // arg1: first row of the job range
             if (row < o.row.rows) run_row(c, a, o.row.kind, s_row, row, lane, 32);
           }
         } else if (o.kind == OP_ADAM) {

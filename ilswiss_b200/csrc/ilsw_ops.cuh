@@ -442,7 +442,8 @@ ILSW_HDN void snapshot_sac(const Ctx& c, int lane, int nl) {
   stats_copy(st, S.y, B, lane, nl); st += B;
   stats_copy(st, S.lossterm[0], B, lane, nl); st += B;
   stats_copy(st, S.lossterm[1], B, lane, nl); st += B;
-  st += B;   // (reward slot: unused -- the batch reward buffer may already hold the prefetched next batch)
+  if (c.hp.algo == 3) stats_copy(st, S.vp, B, lane, nl);   // SAC-V: V predictions (slot unused otherwise)
+  st += B;
   if (td3) {
     stats_copy(st, S.act, B * A, lane, nl); st += B * A;
   } else {
@@ -740,6 +741,54 @@ ILSW_HDN void row_disc_reward_final(const Ctx& c, const RunArgs& a, int s, int r
   }
 }
 
+// ---- SAC, V-function variant (sac.py:70-179) ------------------------------------------------
+// q_target from the TARGET V net; V regression target = min Q(obs, a~) - alpha*log pi with the
+// PRE-update critics; output-layer backward of Q1, Q2 and V.
+ILSW_HDN void row_sacv_target(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
+  const SacBufs& S = c.s;
+  const int Hd = S.Hd, B = S.B;
+  const float invB = 1.0f / (float)B;
+  const float tv = wdot(S.h1tv + (size_t)b * Hd, c.tvf.p + c.tvf.oW2, Hd, lane, nl) + ldg(c.tvf.p + c.tvf.ob2);
+  const float y = c.hp.reward_scale * ldg(S.rew + b) + (1.0f - ldg(S.term + b)) * c.hp.discount * tv;
+  float qold[2];
+  for (int i = 0; i < 2; ++i) {
+    const MlpPtrs& Q = c.qf[i];
+    qold[i] = wdot(S.h1n[i] + (size_t)b * Hd, Q.p + Q.oW2, Hd, lane, nl) + ldg(Q.p + Q.ob2);
+    const float* h = S.h1q[i] + (size_t)b * Hd;
+    const float q = wdot(h, Q.p + Q.oW2, Hd, lane, nl) + ldg(Q.p + Q.ob2);
+    const float diff = q - y, dq = diff * invB;
+    if (lane == 0) { S.qp[i][b] = q; S.dq[i][b] = dq; S.lossterm[i][b] = diff * diff; S.qn_old[i][b] = qold[i]; }
+    float* d1 = S.d1q[i] + (size_t)b * Hd;
+    for (int k = lane; k < Hd; k += nl) d1[k] = (ldg(h + k) > 0.f) ? dq * ldg(Q.p + Q.oW2 + k) : 0.f;
+  }
+  const float vtarget = fminf(qold[0], qold[1]) - ldg(&c.dyn->alpha) * ldg(S.logpi + B + b);
+  const float* hv = S.h1v + (size_t)b * Hd;
+  const float v = wdot(hv, c.vf.p + c.vf.oW2, Hd, lane, nl) + ldg(c.vf.p + c.vf.ob2);
+  const float dvd = v - vtarget, dv = dvd * invB;
+  if (lane == 0) { S.vp[b] = v; S.dv[b] = dv; S.lossterm_v[b] = dvd * dvd; S.tv[b] = tv; S.y[b] = y; }
+  float* d1 = S.d1v + (size_t)b * Hd;
+  for (int k = lane; k < Hd; k += nl) d1[k] = (ldg(hv + k) > 0.f) ? dv * ldg(c.vf.p + c.vf.oW2 + k) : 0.f;
+}
+ILSW_HDN void row_sacv_final(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {
+  if (r != 0) return;
+  const SacBufs& S = c.s;
+  const int B = S.B, A = S.A;
+  float l1 = 0.5f * wmean(S.lossterm[0], B, lane, nl);
+  float l2 = 0.5f * wmean(S.lossterm[1], B, lane, nl);
+  float lv = 0.5f * wmean(S.lossterm_v, B, lane, nl);
+  float pl = wmean(S.plterm, B, lane, nl);
+  float rm = wmean(S.regmu, B, lane, nl) / (float)A;
+  float rl = wmean(S.regls, B, lane, nl) / (float)A;
+  pl = pl + (c.hp.mean_reg * rm + c.hp.std_reg * rl);
+  float q1m = wmean(S.qp[0], B, lane, nl), lpm = wmean(S.logpi + B, B, lane, nl), ytm = wmean(S.y, B, lane, nl);
+  if (lane == 0) {
+    float* L = c.loss_log + (size_t)(a.loss_log_offset + s) * kLossSlots;
+    L[L_QF1] = l1; L[L_QF2] = l2; L[L_VF] = lv; L[L_POLICY] = pl; L[L_ALPHA] = c.dyn->alpha; L[L_ALPHA_LOSS] = 0.f;
+    L[L_Q1_MEAN] = q1m; L[L_LOGPI_MEAN] = lpm; L[L_QT_MEAN] = ytm;
+  }
+  if (s == a.stats_step) snapshot_sac(c, lane, nl);
+}
+
 // generic form of the fused "dA = e0 . W0[:, O:O+A]" + head backward rows (the fast jobs are in
 // ilsw_rows_fast.cuh); used for shapes outside the fast path and as cross-check in the host simulator
 ILSW_HDN void row_da(const Ctx& c, int b, int nets, int lane, int nl) {
@@ -774,6 +823,8 @@ ILSW_HDN void run_row(const Ctx& c, const RunArgs& a, int kind, int s, int r, in
     case ROW_SAC_PLOSS: row_sac_ploss(c, a, s, r, lane, nl); break;
     case ROW_SAC_PIBWD: row_sac_pibwd(c, a, s, r, lane, nl); break;
     case ROW_SAC_PIBWD_DA: row_sac_pibwd_da(c, a, s, r, lane, nl); break;
+    case ROW_SACV_TARGET: row_sacv_target(c, a, s, r, lane, nl); break;
+    case ROW_SACV_FINAL: row_sacv_final(c, a, s, r, lane, nl); break;
     case ROW_TD3_PIBWD_DA: row_td3_pibwd_da(c, a, s, r, lane, nl); break;
     case ROW_SAC_FINAL: row_sac_final(c, a, s, r, lane, nl); break;
     case ROW_TD3_THEAD: row_td3_thead(c, a, s, r, lane, nl); break;

@@ -99,9 +99,9 @@ struct Builder {
     g.C = G; g.ldc = Nin; g.aug_ones = gbias ? 1 : 0; g.bias_out = gbias; g.accumulate = accumulate;
     gemm(g);
   }
-  void row(int kind, int rows, int next_step = 0) {
+  void row(int kind, int rows, int next_step = 0, int row_offset = 0) {
     Op* o = add(OP_ROW, (rows + kRowsPerJob - 1) / kRowsPerJob);
-    if (o) { o->row.kind = kind; o->row.rows = rows; o->row.arg0 = next_step; }
+    if (o) { o->row.kind = kind; o->row.rows = rows + row_offset; o->row.arg0 = next_step; o->row.arg1 = row_offset; }
   }
   void adam(const MlpPtrs& n, const MlpPtrs* target, double lr, double b1, double b2, double eps, float tau, int slot,
             int world_scale = 0) {
@@ -153,6 +153,11 @@ inline void alloc_sac_bufs(Bump& mem, SacBufs& S, int algo, int B, int O, int A,
   S.plterm = mem.f(B); S.regmu = mem.f(B); S.regls = mem.f(B); S.aterm = mem.f(B);
   S.h0tp = mem.f((size_t)B * Hd); S.h1tp = mem.f((size_t)B * Hd);
   S.h0v = S.h1v = S.h0tv = S.h1tv = S.vp = S.tv = S.dv = S.d1v = S.d0v = S.lossterm_v = nullptr;
+  if (algo == ILSW_ALGO_SAC_V) {
+    S.h0v = mem.f((size_t)B * Hd); S.h1v = mem.f((size_t)B * Hd); S.h0tv = mem.f((size_t)B * Hd); S.h1tv = mem.f((size_t)B * Hd);
+    S.vp = mem.f(B); S.tv = mem.f(B); S.dv = mem.f(B); S.lossterm_v = mem.f(B);
+    S.d1v = mem.f((size_t)B * Hd); S.d0v = mem.f((size_t)B * Hd);
+  }
 }
 
 inline void alloc_disc_bufs(Bump& mem, DiscBufs& D, int B, int Din, int Hd) {
@@ -172,7 +177,7 @@ inline void alloc_disc_bufs(Bump& mem, DiscBufs& D, int B, int Din, int Hd) {
 }
 
 inline int stats_floats_for(int algo, int B, int A) {
-  return algo == ILSW_ALGO_TD3 ? 6 * B + B * A : 7 * B + 2 * B * A;
+  return algo == ILSW_ALGO_TD3 ? 6 * B + B * A : 7 * B + 2 * B * A;   // SAC-alpha and SAC-V share a layout
 }
 
 // ------------------------------------------------------------------------------------------
@@ -348,6 +353,69 @@ inline void build_td3(Builder& b, const Ctx& c) {
   b.row(ROW_TD3_FINAL_POLICY, 1);
 }
 
+// S2: SAC with a V function and a fixed entropy coefficient (sac.py:70-179, 242-243)
+inline void build_sac_v(Builder& b, const Ctx& c) {
+  const SacBufs& S = c.s;
+  const int B = S.B, O = S.O, A = S.A, Hd = S.Hd, K0 = O + A;
+  const MlpPtrs& P = c.policy; const MlpPtrs& V = c.vf; const MlpPtrs& TV = c.tvf;
+  const double b1 = c.hp.beta1, b2 = c.hp.beta2, eps = c.hp.adam_eps;
+  float* h0p_obs = S.h0p + (size_t)B * Hd;      // the policy runs on the obs rows [B,2B) of the 2B layout
+  float* h1p_obs = S.h1p + (size_t)B * Hd;
+  const float* obs_rows = S.Xpi + (size_t)B * S.ld_o;
+  b.phase(); b.row(ROW_SAC_GATHER, B);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.fwd(S.Xoa, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0q[i], Hd, ACT_RELU);
+  b.fwd(S.Xna, S.ld_oa, B, O, TV.p + TV.oW0, TV.p + TV.ob0, Hd, S.h0tv, Hd, ACT_RELU);
+  b.fwd(S.Xoa, S.ld_oa, B, O, V.p + V.oW0, V.p + V.ob0, Hd, S.h0v, Hd, ACT_RELU);
+  b.fwd(obs_rows, S.ld_o, B, O, P.p + P.oW0, P.p + P.ob0, Hd, h0p_obs, Hd, ACT_RELU);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.fwd(S.h0q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1q[i], Hd, ACT_RELU);
+  b.fwd(S.h0tv, Hd, B, Hd, TV.p + TV.oW1, TV.p + TV.ob1, Hd, S.h1tv, Hd, ACT_RELU);
+  b.fwd(S.h0v, Hd, B, Hd, V.p + V.oW1, V.p + V.ob1, Hd, S.h1v, Hd, ACT_RELU);
+  b.fwd(h0p_obs, Hd, B, Hd, P.p + P.oW1, P.p + P.ob1, Hd, h1p_obs, Hd, ACT_RELU);
+  b.phase(); b.row(ROW_SAC_HEADS, B, 0, /*row_offset=*/B);          // one eps draw: a~, log pi on the obs rows
+  b.phase();   // min Q(obs, a~) with the PRE-update critics (V regression target, sac.py:121-129)
+  for (int i = 0; i < 2; ++i) b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0n[i], Hd, ACT_RELU);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.fwd(S.h0n[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1n[i], Hd, ACT_RELU);
+  b.phase(); b.row(ROW_SACV_TARGET, B);
+  b.phase();
+  for (int i = 0; i < 2; ++i) {
+    const MlpPtrs& Q = c.qf[i];
+    b.dx(S.d1q[i], Hd, B, Hd, Q.p + Q.oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
+    b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, Q.g + Q.oW1, Q.g + Q.ob1);
+    b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, Q.g + Q.oW2, Q.g + Q.ob2);
+  }
+  b.dx(S.d1v, Hd, B, Hd, V.p + V.oW1, Hd, Hd, S.h0v, Hd, ACT_RELU, S.d0v, Hd);
+  b.dw(S.d1v, Hd, Hd, S.h0v, Hd, Hd, B, V.g + V.oW1, V.g + V.ob1);
+  b.dw(S.dv, 1, 1, S.h1v, Hd, Hd, B, V.g + V.oW2, V.g + V.ob2);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0);
+  b.dw(S.d0v, Hd, Hd, S.Xoa, S.ld_oa, O, B, V.g + V.oW0, V.g + V.ob0);
+  b.phase();   // all three backward passes first, then the three Adam steps (sac.py:132-139)
+  b.adam(c.qf[0], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF1);
+  b.adam(c.qf[1], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF2);
+  b.adam(V, &c.tvf, c.hp.vf_lr, b1, b2, eps, c.hp.tau, SLOT_VF);           // + Polyak of the target V (:242-243)
+  b.phase();   // policy loss re-evaluates the UPDATED critics on the SAME action sample (:150-153)
+  for (int i = 0; i < 2; ++i) b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0n[i], Hd, ACT_RELU);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.fwd(S.h0n[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1n[i], Hd, ACT_RELU);
+  b.phase(); b.row(ROW_SAC_PLOSS, B);
+  b.phase();
+  for (int i = 0; i < 2; ++i) b.dx(S.e1[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0n[i], Hd, ACT_RELU, S.e0[i], Hd);
+  b.phase(); b.row(ROW_SAC_PIBWD_DA, B);
+  b.phase();
+  b.dx(S.d1p, Hd, B, Hd, P.p + P.oW1, Hd, Hd, h0p_obs, Hd, ACT_RELU, S.d0p, Hd);
+  b.dw(S.d1p, Hd, Hd, h0p_obs, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);
+  b.dw(S.dmean, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2);
+  b.dw(S.dlraw, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW3, P.g + P.ob3);
+  b.phase();
+  b.dw(S.d0p, Hd, Hd, obs_rows, S.ld_o, O, B, P.g + P.oW0, P.g + P.ob0);
+  b.phase(COND_ALWAYS, 1);
+  b.adam(P, nullptr, c.hp.policy_lr, b1, b2, eps, 0.f, SLOT_POLICY, 1);
+  b.row(ROW_SACV_FINAL, 1);
+}
+
 inline Hyper make_hyper(const ilsw_trainer_config& cfg) {
   Hyper h; memset(&h, 0, sizeof(h));
   h.algo = cfg.algo;
@@ -387,7 +455,7 @@ inline int validate_spec(const TrainerSpec& sp, std::string* why) {
   if (c.obs_dim <= 0 || c.act_dim <= 0 || c.batch <= 0) return fail("obs_dim/act_dim/batch must be positive");
   if (c.act_dim > 64) return fail("act_dim > 64 unsupported");
   if (c.max_steps_per_call <= 0) return fail("max_steps_per_call must be positive");
-  int need = c.algo == ILSW_ALGO_SAC_ALPHA ? 5 : (c.algo == ILSW_ALGO_TD3 ? 6 : -1);
+  int need = c.algo == ILSW_ALGO_SAC_ALPHA ? 5 : (c.algo == ILSW_ALGO_TD3 ? 6 : (c.algo == ILSW_ALGO_SAC_V ? 5 : -1));
   if (need < 0) return fail("unsupported algo");
   if (sp.n_nets != need) return fail("wrong number of networks for this algorithm");
   const int Hd = sp.nets[0].hidden;
@@ -396,11 +464,12 @@ inline int validate_spec(const TrainerSpec& sp, std::string* why) {
     if (!n.p) return fail("null parameter arena");
     if (n.hidden != Hd || Hd <= 0) return fail("all networks must share one hidden width");
     bool is_policy = (i == 0) || (c.algo == ILSW_ALGO_TD3 && i == 5);
-    int in_dim = is_policy ? c.obs_dim : c.obs_dim + c.act_dim;
+    bool is_vnet = c.algo == ILSW_ALGO_SAC_V && i >= 3;          // vf, target_vf: obs -> 1
+    int in_dim = (is_policy || is_vnet) ? c.obs_dim : c.obs_dim + c.act_dim;
     int out_dim = is_policy ? c.act_dim : 1;
     if (n.in_dim != in_dim || n.out_dim != out_dim) return fail("network in/out dims do not match obs/act dims");
     if ((n.log_std_head != 0) != (is_policy && c.algo != ILSW_ALGO_TD3)) return fail("log_std_head mismatch");
-    bool trainable = i < 3;
+    bool trainable = i < 3 || (c.algo == ILSW_ALGO_SAC_V && i == 3);
     if (trainable && (!n.m || !n.v)) return fail("trainable network needs Adam moment arenas");
   }
   if (sp.has_disc) {
@@ -431,8 +500,13 @@ inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem) {
   c.policy = make_mlp(sp.nets[0], grad(sp.nets[0]));
   c.qf[0] = make_mlp(sp.nets[1], grad(sp.nets[1]));
   c.qf[1] = make_mlp(sp.nets[2], grad(sp.nets[2]));
-  c.tqf[0] = make_mlp(sp.nets[3], nullptr);
-  c.tqf[1] = make_mlp(sp.nets[4], nullptr);
+  if (cfg.algo == ILSW_ALGO_SAC_V) {
+    c.vf = make_mlp(sp.nets[3], grad(sp.nets[3]));
+    c.tvf = make_mlp(sp.nets[4], nullptr);
+  } else {
+    c.tqf[0] = make_mlp(sp.nets[3], nullptr);
+    c.tqf[1] = make_mlp(sp.nets[4], nullptr);
+  }
   if (cfg.algo == ILSW_ALGO_TD3) c.tpolicy = make_mlp(sp.nets[5], nullptr);
   if (sp.has_disc) {
     alloc_disc_bufs(mem, c.d, B, O + A, sp.disc.hidden);
@@ -448,6 +522,7 @@ inline int build_program(Program& P) {
   if (c.hp.has_disc) build_disc_step(b, c);
   if (c.hp.algo == ILSW_ALGO_SAC_ALPHA) build_sac_alpha(b, c);
   else if (c.hp.algo == ILSW_ALGO_TD3) build_td3(b, c);
+  else if (c.hp.algo == ILSW_ALGO_SAC_V) build_sac_v(b, c);
   else return ILSW_ERR_UNSUPPORTED;
   return b.overflow ? ILSW_ERR_STATE : ILSW_OK;
 }

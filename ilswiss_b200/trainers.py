@@ -274,6 +274,92 @@ class SoftActorCritic(_FusedTrainer):
         self.engine.set_state(st)
 
 
+class SoftActorCriticV(_FusedTrainer):
+    """sac.py:12-273 -- the older SAC with a V function, a target V and a FIXED entropy coefficient
+    (what run_scripts/sac_exp_script.py instantiates)."""
+
+    def __init__(self, policy, qf1, qf2, vf, reward_scale=1.0, discount=0.99, alpha=1.0, policy_lr=1e-3, qf_lr=1e-3,
+                 vf_lr=1e-3, soft_target_tau=1e-2, policy_mean_reg_weight=1e-3, policy_std_reg_weight=1e-3,
+                 optimizer_class=optim.Adam, beta_1=0.9, batch_size=256, max_steps_per_call=1000, gemm_precision=None,
+                 **kwargs):
+        if optimizer_class is not optim.Adam:
+            raise NotImplementedError("the fused step implements torch.optim.Adam only")
+        self.policy, self.qf1, self.qf2, self.vf = policy, qf1, qf2, vf
+        self.reward_scale, self.discount, self.soft_target_tau = reward_scale, discount, soft_target_tau
+        self.policy_mean_reg_weight, self.policy_std_reg_weight = policy_mean_reg_weight, policy_std_reg_weight
+        self.alpha = alpha
+        in_dim, H, act_dim, ls = module_dims(policy)
+        if not ls:
+            raise NotImplementedError("SAC needs a ReparamTanhMultivariateGaussianPolicy (conditioned_std=True)")
+        self.target_vf = clone_module(vf)
+        self._arenas = OrderedDict(policy=adopt_module(policy), qf1=adopt_module(qf1), qf2=adopt_module(qf2),
+                                   vf=adopt_module(vf), target_vf=adopt_module(self.target_vf, False))
+        self.policy_optimizer = optim.Adam(self.policy.parameters(), lr=policy_lr, betas=(beta_1, 0.999))
+        self.qf1_optimizer = optim.Adam(self.qf1.parameters(), lr=qf_lr, betas=(beta_1, 0.999))
+        self.qf2_optimizer = optim.Adam(self.qf2.parameters(), lr=qf_lr, betas=(beta_1, 0.999))
+        self.vf_optimizer = optim.Adam(self.vf.parameters(), lr=vf_lr, betas=(beta_1, 0.999))
+        cfg = _abi.TrainerConfig()
+        cfg.algo = _abi.ALGO_SAC_V
+        cfg.gemm_precision = default_gemm_precision() if gemm_precision is None else int(gemm_precision)
+        cfg.obs_dim, cfg.act_dim, cfg.batch = in_dim, act_dim, int(batch_size)
+        cfg.max_steps_per_call = int(max_steps_per_call)
+        cfg.reward_scale, cfg.discount, cfg.soft_target_tau = reward_scale, discount, soft_target_tau
+        cfg.policy_lr, cfg.qf_lr, cfg.vf_lr = policy_lr, qf_lr, vf_lr
+        cfg.beta_1, cfg.beta_2, cfg.adam_eps = beta_1, 0.999, 1e-8
+        cfg.alpha, cfg.train_alpha = alpha, 0
+        cfg.policy_mean_reg_weight, cfg.policy_std_reg_weight = policy_mean_reg_weight, policy_std_reg_weight
+        cfg.max_act = 1.0
+        self._finish_init(cfg, list(self._arenas.values()))
+        self.eval_statistics = None
+
+    @property
+    def networks(self):
+        return [self.policy, self.qf1, self.qf2, self.vf, self.target_vf]
+
+    def _build_stats(self, L, vec):
+        B, A = self._cfg.batch, self._cfg.act_dim
+        st = OrderedDict()
+        st["Reward Scale"] = self.reward_scale
+        st["QF1 Loss"] = float(L[_abi.L_QF1])
+        st["QF2 Loss"] = float(L[_abi.L_QF2])
+        st["VF Loss"] = float(L[_abi.L_VF])
+        st["Policy Loss"] = float(L[_abi.L_POLICY])
+        st.update(_stats("Q1 Predictions", vec[0:B]))
+        st.update(_stats("Q2 Predictions", vec[B:2 * B]))
+        st.update(_stats("V Predictions", vec[5 * B:6 * B]))
+        o = 6 * B
+        st.update(_stats("Log Pis", vec[o:o + B]))
+        st.update(_stats("Policy mu", vec[o + B:o + B + B * A]))
+        st.update(_stats("Policy log std", vec[o + B + B * A:o + B + 2 * B * A]))
+        return st
+
+    def get_snapshot(self):
+        st = self.engine.get_state()
+        for slot, name in ((2, "policy"), (0, "qf1"), (1, "qf2"), (3, "vf")):
+            self._sync_optimizer(getattr(self, name + "_optimizer"), self._arenas[name], st.adam_step[slot])
+        return dict(qf1=self.qf1, qf2=self.qf2, policy=self.policy, vf=self.vf, target_vf=self.target_vf,
+                    policy_optimizer=self.policy_optimizer, qf1_optimizer=self.qf1_optimizer,
+                    qf2_optimizer=self.qf2_optimizer, vf_optimizer=self.vf_optimizer)
+
+    def load_snapshot(self, snapshot):
+        """sac.py:258-268 (whose 'self.vf_optimizer' key typo is NOT reproduced)."""
+        with torch.no_grad():
+            for name in ("policy", "qf1", "qf2", "vf", "target_vf"):
+                for dst, src in zip(getattr(self, name).parameters(), snapshot[name].parameters()):
+                    dst.copy_(src.to(dst.device))
+        st = self.engine.get_state()
+        for slot, name in ((2, "policy"), (0, "qf1"), (1, "qf2"), (3, "vf")):
+            key = name + "_optimizer"
+            if key not in snapshot:
+                continue
+            src, mine = snapshot[key], getattr(self, key)
+            for p_dst, p_src in zip(mine.param_groups[0]["params"], src.param_groups[0]["params"]):
+                if p_src in src.state:
+                    mine.state[p_dst] = src.state[p_src]
+            st.adam_step[slot] = self._load_optimizer(mine, self._arenas[name])
+        self.engine.set_state(st)
+
+
 class TD3(_FusedTrainer):
     """td3.py:13-223.  The target-action noise is the policy MODULE's (policy.noise /
     policy.noise_clip, policies.py:150-152); the trainer arguments target_policy_noise* are stored

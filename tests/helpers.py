@@ -23,7 +23,7 @@ STAT_TO_SLOT = {
     "Disc Acc": _abi.L_DISC_ACC, "Grad Pen": _abi.L_GRAD_PEN, "Disc Rew Mean": _abi.L_REW_MEAN,
     "Disc Rew Std": _abi.L_REW_STD, "Disc Rew Max": _abi.L_REW_MAX, "Disc Rew Min": _abi.L_REW_MIN,
     "Q1 Predictions Mean": _abi.L_Q1_MEAN, "Log Pis Mean": _abi.L_LOGPI_MEAN,
-    "Q Targets Mean": _abi.L_QT_MEAN,
+    "Q Targets Mean": _abi.L_QT_MEAN, "VF Loss": _abi.L_VF,
 }
 
 
@@ -95,6 +95,17 @@ def trainer_config(case, max_steps=64, precision=0):
         cfg.alpha = 1.0
         cfg.policy_and_target_update_period = kw["policy_and_target_update_period"]
         cfg.policy_noise, cfg.policy_noise_clip = case["policy_noise"], case["policy_noise_clip"]
+    elif algo == "sac_v":
+        kw = case["sac"]
+        cfg.algo = _abi.ALGO_SAC_V
+        cfg.reward_scale, cfg.discount = kw["reward_scale"], kw["discount"]
+        cfg.soft_target_tau = kw["soft_target_tau"]
+        cfg.policy_lr, cfg.qf_lr, cfg.vf_lr = kw["policy_lr"], kw["qf_lr"], kw["vf_lr"]
+        cfg.beta_1 = kw.get("beta_1", 0.9)
+        cfg.alpha = kw.get("alpha", 1.0)
+        cfg.train_alpha = 0
+        cfg.policy_mean_reg_weight = kw["policy_mean_reg_weight"]
+        cfg.policy_std_reg_weight = kw["policy_std_reg_weight"]
     else:
         raise NotImplementedError(algo)
     return cfg
@@ -119,6 +130,8 @@ def net_order(case):
     """Order of networks expected by ilsw_trainer_create."""
     if case["algo"] == "td3":
         return ["policy", "qf1", "qf2", "target_qf1", "target_qf2", "target_policy"]
+    if case["algo"] == "sac_v":
+        return ["policy", "qf1", "qf2", "vf", "target_vf"]
     return ["policy", "qf1", "qf2", "target_qf1", "target_qf2"]
 
 
@@ -127,6 +140,8 @@ def initial_arenas(case):
     nets = G.build_oracle_nets(case)
     flat = {k: n.flat().astype(np.float32) for k, n in nets.items()}
     flat["target_qf1"], flat["target_qf2"] = flat["qf1"].copy(), flat["qf2"].copy()
+    if case["algo"] == "sac_v":
+        flat["target_vf"] = flat["vf"].copy()
     if case["algo"] == "td3":
         flat["target_policy"] = flat["policy"].copy()
     return flat
@@ -138,6 +153,8 @@ def mlp_dims(case, name):
         return O, CFG.HIDDEN[0], A, int(case["algo"] != "td3")
     if name == "disc":
         return O + A, CFG.DISC_HID, 1, 0
+    if name in ("vf", "target_vf"):
+        return O, CFG.HIDDEN[0], 1, 0
     return O + A, CFG.HIDDEN[0], 1, 0
 
 

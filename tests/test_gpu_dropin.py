@@ -205,3 +205,38 @@ def test_adv_irl_engine_matches_oracle_and_stats_keys():
     with pytest.raises(NotImplementedError):
         AdvIRLEngine("gail", mods["disc"], tr, ebuf, buf, state_only=True, disc_optim_batch_size=256,
                      policy_optim_batch_size=256, num_disc_updates_per_loop_iter=1, num_policy_updates_per_loop_iter=1)
+
+
+def test_sac_v_trainer_dropin():
+    from ilswiss_b200 import modules
+    from ilswiss_b200.replay_buffer import DeviceReplayBuffer
+    from ilswiss_b200.trainers import SoftActorCriticV
+
+    torch.set_num_threads(1)
+    case = CFG.CASES["sacv_hopper"]
+    O, A = case["obs_dim"], case["act_dim"]
+    nets = G.build_oracle_nets(case)
+    mods = {"qf1": modules.FlattenMlp([256, 256], 1, O + A), "qf2": modules.FlattenMlp([256, 256], 1, O + A),
+            "vf": modules.FlattenMlp([256, 256], 1, O), "policy": modules.TanhGaussianPolicy([256, 256], O, A)}
+    for k, m in mods.items():
+        with torch.no_grad():
+            for p, v in zip(m.parameters(), nets[k].p.values()):
+                p.copy_(v)
+    tr = SoftActorCriticV(mods["policy"], mods["qf1"], mods["qf2"], mods["vf"], batch_size=case["batch"],
+                          gemm_precision=3, **case["sac"])
+    assert len(tr.networks) == 5
+    data, _ = case_data(case)
+    buf = DeviceReplayBuffer(case["n_fill"], O, A, random_seed=1)
+    fill(buf, data)
+    inj = {k: torch.from_numpy(v).cuda() for k, v in case_injection(case).items()}
+    tr.train_from_buffer(buf, case["steps"], inject=inj)
+    rows, final, _ = G.run_oracle(case)
+    L = tr.engine.losses(case["steps"])
+    for t, row in enumerate(rows):
+        for key, slot in (("QF1 Loss", 0), ("QF2 Loss", 1), ("VF Loss", 5), ("Policy Loss", 2)):
+            assert abs(L[t, slot] - row[key]) <= 1e-4 * max(abs(row[key]), 1.0 if key == "Policy Loss" else 1e-2), (t, key)
+    st = tr.get_eval_statistics()
+    assert list(st.keys())[:5] == ["Reward Scale", "QF1 Loss", "QF2 Loss", "VF Loss", "Policy Loss"]
+    assert "V Predictions Mean" in st and "Policy log std Min" in st
+    snap = tr.get_snapshot()
+    assert set(snap) == {"qf1", "qf2", "policy", "vf", "target_vf", "policy_optimizer", "qf1_optimizer", "qf2_optimizer", "vf_optimizer"}

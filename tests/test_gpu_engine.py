@@ -11,7 +11,7 @@ from helpers import CFG, G, DeviceRun, STAT_TO_SLOT, assert_params_close, case_i
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-CASES = [n for n, c in CFG.CASES.items() if c["algo"] in ("sac_alpha", "td3", "adv_irl")]
+CASES = [n for n, c in CFG.CASES.items() if c["algo"] in ("sac_alpha", "sac_v", "td3", "adv_irl")]
 
 
 def loss_tol(k, ref, precision=0, n_rows=512):

@@ -7,7 +7,7 @@ import torch
 
 from helpers import CFG, G, HostSimRun, STAT_TO_SLOT, assert_params_close, case_injection, load_hostsim
 
-CASES = [n for n, c in CFG.CASES.items() if c["algo"] in ("sac_alpha", "td3", "adv_irl")]
+CASES = [n for n, c in CFG.CASES.items() if c["algo"] in ("sac_alpha", "sac_v", "td3", "adv_irl")]
 
 
 @pytest.fixture(scope="module")
