@@ -240,3 +240,98 @@ def test_sac_v_trainer_dropin():
     assert "V Predictions Mean" in st and "Policy log std Min" in st
     snap = tr.get_snapshot()
     assert set(snap) == {"qf1", "qf2", "policy", "vf", "target_vf", "policy_optimizer", "qf1_optimizer", "qf2_optimizer", "vf_optimizer"}
+
+
+def test_policy_act_kernel_matches_module_forward():
+    """A1: sampler-side inference kernel == the nn.Module's own deterministic forward."""
+    from ilswiss_b200 import modules
+    from ilswiss_b200.trainers import TD3, SoftActorCritic
+
+    torch.manual_seed(0)
+    O, A = 17, 6
+    pol = modules.TanhGaussianPolicy([256, 256], O, A)
+    tr = SoftActorCritic(pol, modules.FlattenMlp([256, 256], 1, O + A), modules.FlattenMlp([256, 256], 1, O + A), batch_size=64)
+    obs = torch.randn(10, O, device="cuda")
+    got = tr.engine.policy_act(obs, deterministic=True)
+    with torch.no_grad():
+        ref = pol(obs, deterministic=True)[0]
+    assert torch.allclose(got, ref, atol=2e-6, rtol=1e-5)
+    sto = tr.engine.policy_act(obs, deterministic=False, seed=3)
+    assert sto.abs().max() <= 1.0 and not torch.allclose(sto, ref)
+    assert torch.equal(sto, tr.engine.policy_act(obs, deterministic=False, seed=3))
+    # the module is still a live view of the trained parameters: get_actions works on numpy input
+    act = pol.get_actions(obs.cpu().numpy(), deterministic=True)
+    assert act.shape == (10, A) and np.allclose(act, ref.cpu().numpy(), atol=1e-6)
+    dpol = modules.DeterministicNoisePolicy([256, 256], O, A, policy_noise=0.2, policy_noise_clip=0.5)
+    t3 = TD3(dpol, modules.FlattenMlp([256, 256], 1, O + A), modules.FlattenMlp([256, 256], 1, O + A), batch_size=64)
+    with torch.no_grad():
+        ref3 = dpol(obs, deterministic=True)[0]
+    assert torch.allclose(t3.engine.policy_act(obs, deterministic=True), ref3, atol=2e-6, rtol=1e-5)
+
+
+def test_algorithm_mixins_drive_one_launch_per_train_call():
+    """DeviceTorchRLAlgorithmMixin / DeviceAdvIRLMixin in front of minimal stand-ins of the reference
+    algorithm classes (same attribute names as torch_rl_algorithm.py:8-34 and adv_irl.py:34-131)."""
+    from ilswiss_b200 import modules
+    from ilswiss_b200.adv_irl import DeviceAdvIRLMixin, DeviceTorchRLAlgorithmMixin
+    from ilswiss_b200.replay_buffer import DeviceReplayBuffer
+    from ilswiss_b200.trainers import SoftActorCritic
+
+    O, A, B = 11, 3, 64
+    rs = np.random.RandomState(0)
+
+    def mk_buf(seed):
+        buf = DeviceReplayBuffer(5000, O, A, random_seed=seed)
+        buf.add_samples(rs.randn(3000, O), rs.uniform(-1, 1, (3000, A)), rs.randn(3000, 1), np.zeros((3000, 1)), rs.randn(3000, O))
+        return buf
+
+    def mk_trainer():
+        return SoftActorCritic(modules.TanhGaussianPolicy([256, 256], O, A), modules.FlattenMlp([256, 256], 1, O + A),
+                               modules.FlattenMlp([256, 256], 1, O + A), batch_size=B, max_steps_per_call=50)
+
+    class RefRL:                                   # stand-in for rlkit TorchRLAlgorithm
+        def __init__(self, trainer, replay_buffer):
+            self.trainer, self.replay_buffer = trainer, replay_buffer
+            self.batch_size, self.num_train_steps_per_train_call = B, 37
+
+        def _do_training(self, epoch):
+            raise AssertionError("reference path must be overridden")
+
+    class Alg(DeviceTorchRLAlgorithmMixin, RefRL):
+        pass
+
+    alg = Alg(mk_trainer(), mk_buf(1))
+    n0 = alg.trainer.engine.kernel_launches
+    alg._do_training(0)
+    assert alg.trainer.engine.kernel_launches == n0 + 1                      # 37 gradient steps, one launch
+    assert alg.trainer.engine.get_state().n_train_steps_total == 37
+    b = alg.get_batch()
+    assert b["observations"].is_cuda and b["observations"].shape == (B, O) and b["rewards"].shape == (B, 1)
+    assert "QF1 Loss" in alg.trainer.get_eval_statistics()
+
+    class RefIRL:                                  # stand-in for rlkit AdvIRL (attribute names of adv_irl.py:63-104)
+        def __init__(self):
+            self.mode, self.state_only = "gail2", False
+            self.discriminator = modules.MLPDisc(O + A, 128)
+            self.policy_trainer = mk_trainer()
+            self.expert_replay_buffer, self.replay_buffer = mk_buf(3), mk_buf(1)
+            self.disc_optim_batch_size = self.policy_optim_batch_size = B
+            self.policy_optim_batch_size_from_expert = 0
+            self.num_update_loops_per_train_call = 21
+            self.num_disc_updates_per_loop_iter = self.num_policy_updates_per_loop_iter = 1
+            self.disc_optimizer = torch.optim.Adam(self.discriminator.parameters(), lr=3e-4, betas=(0.9, 0.999))
+            self.use_grad_pen, self.grad_pen_weight = True, 8.0
+            self.rew_clip_min = self.rew_clip_max = None
+            self.wrap_absorbing = False
+            self.disc_eval_statistics = None
+
+    class IRL(DeviceAdvIRLMixin, RefIRL):
+        pass
+
+    irl = IRL()
+    irl._do_training(0)
+    st = irl.disc_eval_statistics
+    assert st is not None and "Disc CE Loss" in st and "Disc Rew Mean" in st and np.isfinite(st["Grad Pen"])
+    assert irl.policy_trainer.engine.get_state().adam_step[4] == 21          # 21 discriminator updates
+    eb = irl.get_batch(B, True, keys=["observations", "actions"])
+    assert set(eb.keys()) == {"observations", "actions"}
