@@ -535,10 +535,7 @@ extern "C" int ilsw_replica_connect(ilsw_trainer* tr, int rank, int world, const
   Replica& rp = tr->rep;
   memset(&rp, 0, sizeof(rp));
   rp.world = world; rp.rank = rank; rp.n = n; rp.nstride = round_up(n, 4);
-  {
-    const MlpPtrs& pol = tr->host_prog.ctx.policy;
-    rp.gs.g = pol.g; rp.gs.gpart = pol.gpart; rp.gs.gp_tiles = pol.gp_tiles; rp.gs.gp_rows = pol.hid; rp.gs.gp_k0 = pol.in_dim; rp.gs.gp_ldp = pol.gp_ldp;
-  }
+  rp.grad = tr->host_prog.ctx.policy.g;
   for (int r = 0; r < world; ++r) {
     void* base = nullptr;
     if (r == rank) base = tr->ipc_buf;

@@ -20,7 +20,7 @@ struct Replica {
   int world, rank;
   int n;                      // policy parameter count
   int nstride;                // slot stride (n rounded up to 4 floats: 16-byte aligned slots)
-  GradSrc gs;                 // local policy gradient (arena, or arena + fused first-layer partials)
+  const float* grad;          // local policy gradient arena
   float* recv_local;          // [2][world][n]  (parity, source rank)
   float* recv_peer[8];        // recv_local of every rank (self included)
   unsigned* flags_local;      // [8] sequence numbers written by the peers
@@ -47,8 +47,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-
-__device__ void dw0_partials_from_tile(const GemmOp& o, int tm, int m0, int n0, float* tile_sm);
 
 constexpr long long kSpinLimit = 4000000000LL;  // ~2 s at 2 GHz: a hung peer/CTA aborts the launch
 
@@ -271,17 +269,6 @@ __device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* 
     if (m < o.M && n < Nt) epi_store(o, m, n, vout[j], ein[j]);
   }
   __syncthreads();
-  if (o.dwp) {   // fused first-layer gradient (see dw0_partials_from_tile); `red` is no longer needed
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      float dv = 0.f;
-      if (m < o.M && n < Nt) dv = (o.mask == ACT_RELU) ? (ein[j].h > 0.f ? vout[j] : 0.f) : vout[j];
-      smem[(m - m0) * 33 + (n - n0)] = dv;
-    }
-    __syncthreads();
-    dw0_partials_from_tile(o, tm, m0, n0, smem);
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -508,40 +495,8 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
     const int m = r0 + ((i & 2) ? 8 : 0), n = c0 + (i & 1);
     const float accv = accs[0][i] + accs[1][i];
     if (m < o.M && n < Nt) epi_store(o, m, n, accv, ein[i]);
-    if (o.dwp) {   // keep the finished delta0 value (after the mask) for the fused first-layer gradient
-      float dv = 0.f;
-      if (m < o.M && n < Nt) dv = (o.mask == ACT_RELU) ? (ein[i].h > 0.f ? accv : 0.f) : accv;
-      smem[(m - m0) * 33 + (n - n0)] = dv;
-    }
   }
-  if (o.dwp) { __syncthreads(); dw0_partials_from_tile(o, tm, m0, n0, smem); }
   ILSW_TSTAMP(4);
-}
-
-// Fused first-layer weight gradient: after a delta0 tile [32 rows x 32 hidden cols] has been written,
-// the same CTA forms P[tm][n][k'] = sum_r delta0[r,n] * [X | 1][r,k'] for its 32 rows (k' <= 31) from
-// shared-memory copies of the tile and of the 32 input rows.  `tile_sm` holds delta0[r*33 + n].
-__device__ __noinline__ void dw0_partials_from_tile(const GemmOp& o, int tm, int m0, int n0, float* tile_sm) {
-  const int tid = threadIdx.x;
-  const int k0 = o.dw_k0, ldx = 33;
-  float* xs = tile_sm + 32 * 33;                 // [32 rows][33]: X rows of this tile, column k0 = 1
-  for (int e = tid; e < 32 * (k0 + 1); e += kThreads) {
-    const int r = e / (k0 + 1), k = e - r * (k0 + 1);
-    float v = 0.f;
-    if (m0 + r < o.M) v = k < k0 ? __ldcg(o.dwX + (size_t)(m0 + r) * o.dw_ldx + k) : 1.0f;
-    xs[r * ldx + k] = v;
-  }
-  __syncthreads();
-  const int n = tid & 31;
-  if (n0 + n < o.N) {
-    for (int k = tid >> 5; k <= k0; k += kThreads / 32) {
-      float acc = 0.f;
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) acc = fmaf(tile_sm[r * 33 + n], xs[r * ldx + k], acc);
-      o.dwp[((size_t)tm * o.N + n0 + n) * o.dw_ldp + k] = acc;
-    }
-  }
-  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -554,13 +509,11 @@ __device__ __forceinline__ bool replica_exchange(const Replica& rp, unsigned seq
   const size_t slot = ((size_t)parity * rp.world + rp.rank) * (size_t)rp.nstride;
   const int n4 = rp.n >> 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-    float4 v;
-    if (rp.gs.gpart) { v.x = grad_at(rp.gs, 4 * i); v.y = grad_at(rp.gs, 4 * i + 1); v.z = grad_at(rp.gs, 4 * i + 2); v.w = grad_at(rp.gs, 4 * i + 3); }
-    else v = __ldcg(reinterpret_cast<const float4*>(rp.gs.g) + i);
+    float4 v = __ldcg(reinterpret_cast<const float4*>(rp.grad) + i);
     for (int r = 0; r < rp.world; ++r) reinterpret_cast<float4*>(rp.recv_peer[r] + slot)[i] = v;
   }
   for (int i = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < rp.n; i += gridDim.x * blockDim.x) {
-    float v = grad_at(rp.gs, i);
+    float v = __ldcg(rp.grad + i);
     for (int r = 0; r < rp.world; ++r) rp.recv_peer[r][slot + i] = v;
   }
   __threadfence_system();
@@ -689,7 +642,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
             for (int u = 0; u < E; ++u) {
               const int i = beg + threadIdx.x + u * kThreads;
               if (i < end) {
-                g[u] = (reduced ? replica_reduced_grad(rp, xseq, i) : grad_at(ao.gs, i)) * cf.gscale;
+                g[u] = (reduced ? replica_reduced_grad(rp, xseq, i) : __ldcg(ao.g + i)) * cf.gscale;
                 m[u] = ao.m[i]; v[u] = ao.v[i]; p[u] = ao.p[i];
                 tg[u] = ao.target ? ao.target[i] : 0.f;
               }

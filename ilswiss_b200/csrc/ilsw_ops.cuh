@@ -160,35 +160,9 @@ ILSW_HD void epi_store(const GemmOp& o, int m, int n, float v, const EpiIn& e) {
 }
 ILSW_HD void gemm_epilogue(const GemmOp& o, int m, int n, float v) { epi_store(o, m, n, v, epi_load(o, m, n)); }
 
-// host-side (simulator) form of the fused first-layer weight-gradient partials of one row tile
-ILSW_HD void gemm_dw0_partials_tile(const GemmOp& o, int tm) {
-  const int m0 = tm * 32, m1 = (m0 + 32 < o.M) ? m0 + 32 : o.M;
-  for (int n = 0; n < o.N; ++n)
-    for (int k = 0; k <= o.dw_k0; ++k) {
-      float acc = 0.f;
-      for (int r = m0; r < m1; ++r) acc += o.C[(size_t)r * o.ldc + n] * (k < o.dw_k0 ? ldg(o.dwX + (size_t)r * o.dw_ldx + k) : 1.0f);
-      o.dwp[((size_t)tm * o.N + n) * o.dw_ldp + k] = acc;
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // Adam / Polyak element kernels
 // ------------------------------------------------------------------------------------------
-// gradient of parameter i (see GradSrc)
-ILSW_HD float grad_at(const GradSrc& gs, int i) {
-  if (gs.gpart) {
-    const int nW = gs.gp_rows * gs.gp_k0;
-    if (i < nW + gs.gp_rows) {
-      const int n = i < nW ? i / gs.gp_k0 : i - nW;
-      const int k = i < nW ? i - n * gs.gp_k0 : gs.gp_k0;
-      float acc = 0.f;
-      for (int t = 0; t < gs.gp_tiles; ++t) acc += ldg(gs.gpart + ((size_t)t * gs.gp_rows + n) * gs.gp_ldp + k);
-      return acc;
-    }
-  }
-  return ldg(gs.g + i);
-}
-
 struct AdamCoef { float w1, one_m_w1, beta2, one_m_beta2, neg_step, bc2_sqrt, eps, gscale, tau, one_m_tau; };
 
 // Adam step count of `slot` for step index `s` of this launch (1-based count AFTER the update).
@@ -237,7 +211,7 @@ ILSW_HD void adam_elem_g(const AdamOp& o, const AdamCoef& c, int i, float g) {
   o.p[i] = p;
   if (o.target) o.target[i] = o.target[i] * c.one_m_tau + p * c.tau;
 }
-ILSW_HD void adam_elem(const AdamOp& o, const AdamCoef& c, int i) { adam_elem_g(o, c, i, grad_at(o.gs, i) * c.gscale); }
+ILSW_HD void adam_elem(const AdamOp& o, const AdamCoef& c, int i) { adam_elem_g(o, c, i, ldg(o.g + i) * c.gscale); }
 
 ILSW_HD void polyak_elem(const PolyakOp& o, int i) {
   float om = (float)(1.0 - (double)o.tau);

@@ -48,17 +48,7 @@ inline MlpPtrs make_mlp(const ilsw_mlp& n, float* grad) {
   m.oW3 = m.ob2 + n.out_dim;
   m.ob3 = m.oW3 + (n.log_std_head ? n.out_dim * n.hidden : 0);
   m.n_params = mlp_num_params(n.in_dim, n.hidden, n.out_dim, n.log_std_head);
-  m.gpart = nullptr; m.gp_tiles = 0; m.gp_ldp = 0;
   return m;
-}
-
-// fused first-layer gradient is used for input widths up to 31 (Hopper 14/11, Walker 23/17)
-inline bool fuse_dw0(int in_dim) { return in_dim + 1 <= 32; }
-inline void attach_dw0_partials(Bump& mem, MlpPtrs& m, int batch) {
-  if (!fuse_dw0(m.in_dim)) return;
-  m.gp_tiles = (batch + 31) / 32;
-  m.gp_ldp = round_up(m.in_dim + 1, 4);
-  m.gpart = mem.f((size_t)m.gp_tiles * m.hid * m.gp_ldp);
 }
 
 struct Builder {
@@ -101,26 +91,6 @@ struct Builder {
     g.C = out; g.ldc = ldo; g.C2 = raw; g.H = Hm; g.ldh = ldh; g.mask = mask;
     gemm(g);
   }
-  // backward-data through layer 1 that ALSO emits the first-layer weight-gradient partials
-  // (net.gpart): replaces the separate dW0 GEMM phase when the input width is small
-  void dx_fused_dw0(const float* D, int ldd, int M, const MlpPtrs& net, const float* Hm, float* out, const float* X, int ldx) {
-    GemmOp g; memset(&g, 0, sizeof(g));
-    g.A = D; g.lda = ldd; g.a_mc = 0; g.B = net.p + net.oW1; g.ldb = net.hid; g.b_nc = 1; g.M = M; g.N = net.hid; g.K = net.hid;
-    g.C = out; g.ldc = net.hid; g.H = Hm; g.ldh = net.hid; g.mask = ACT_RELU;
-    g.dwp = net.gpart; g.dwX = X; g.dw_ldx = ldx; g.dw_k0 = net.in_dim; g.dw_ldp = net.gp_ldp;
-    gemm(g);
-  }
-  // layer-1 backward-data of `net`: fused with the first-layer gradient partials when available
-  void dx_l1(const float* D, int M, const MlpPtrs& net, const float* Hm, float* out, const float* X, int ldx) {
-    if (net.gpart) dx_fused_dw0(D, net.hid, M, net, Hm, out, X, ldx);
-    else dx(D, net.hid, M, net.hid, net.p + net.oW1, net.hid, net.hid, Hm, net.hid, ACT_RELU, out, net.hid);
-  }
-  // first-layer weight gradient as a GEMM of its own (only when it was not fused into dx_l1)
-  void dw0(const float* D0, const MlpPtrs& net, const float* X, int ldx, int Kb) {
-    if (!net.gpart) dw(D0, net.hid, net.hid, X, ldx, net.in_dim, Kb, net.g + net.oW0, net.g + net.ob0);
-  }
-  bool phase_empty() const { return P.n_phases > 0 && P.phases[P.n_phases - 1].op_count == 0; }
-  void drop_empty_phase() { if (phase_empty()) P.n_phases--; }
   // G[Mout,Nin] (+)= D[Kb,Mout]^T X[Kb,Nin] ; gbias[Mout] (+)= colsum(D)   (weight gradient)
   void dw(const float* D, int ldd, int Mout, const float* X, int ldx, int Nin, int Kb, float* G, float* gbias,
           int accumulate = 0) {
@@ -137,8 +107,7 @@ struct Builder {
             int world_scale = 0) {
     Op* o = add(OP_ADAM, (n.n_params + kAdamChunk - 1) / kAdamChunk);
     if (!o) return;
-    o->adam.p = n.p; o->adam.gs.g = n.g; o->adam.gs.gpart = nullptr; o->adam.m = n.m; o->adam.v = n.v;
-    if (n.gpart) { o->adam.gs.gpart = n.gpart; o->adam.gs.gp_tiles = n.gp_tiles; o->adam.gs.gp_rows = n.hid; o->adam.gs.gp_k0 = n.in_dim; o->adam.gs.gp_ldp = n.gp_ldp; }
+    o->adam.p = n.p; o->adam.g = n.g; o->adam.m = n.m; o->adam.v = n.v;
     o->adam.target = target ? target->p : nullptr;
     o->adam.n = n.n_params; o->adam.lr = lr; o->adam.beta1 = b1; o->adam.beta2 = b2; o->adam.eps = eps;
     o->adam.tau = tau; o->adam.slot = slot; o->adam.grad_scale_world = world_scale;
@@ -298,13 +267,12 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
   b.phase();
   for (int i = 0; i < 2; ++i) {
     const MlpPtrs& Q = c.qf[i];
-    b.dx_l1(S.d1q[i], B, Q, S.h0q[i], S.d0q[i], S.Xoa, S.ld_oa);
+    b.dx(S.d1q[i], Hd, B, Hd, Q.p + Q.oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
     b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, Q.g + Q.oW1, Q.g + Q.ob1);
     b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, Q.g + Q.oW2, Q.g + Q.ob2);
   }
   b.phase();
-  for (int i = 0; i < 2; ++i) b.dw0(S.d0q[i], c.qf[i], S.Xoa, S.ld_oa, B);
-  b.drop_empty_phase();
+  for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0);
   b.phase();
   b.adam(c.qf[0], &c.tqf[0], c.hp.qf_lr, b1, b2, eps, c.hp.tau, SLOT_QF1);   // Adam + Polyak of the target
   b.adam(c.qf[1], &c.tqf[1], c.hp.qf_lr, b1, b2, eps, c.hp.tau, SLOT_QF2);
@@ -317,13 +285,12 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
   for (int i = 0; i < 2; ++i) b.dx(S.e1[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0n[i], Hd, ACT_RELU, S.e0[i], Hd);
   b.phase(); b.row(ROW_SAC_PIBWD_DA, B);      // dA = e0 . W0[:, O:O+A] fused into the head backward rows
   b.phase();
-  b.dx_l1(S.d1p, B, P, h0p_obs, S.d0p, obs_rows, S.ld_o);
+  b.dx(S.d1p, Hd, B, Hd, P.p + P.oW1, Hd, Hd, h0p_obs, Hd, ACT_RELU, S.d0p, Hd);
   b.dw(S.d1p, Hd, Hd, h0p_obs, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);
   b.dw(S.dmean, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2);
   b.dw(S.dlraw, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW3, P.g + P.ob3);
   b.phase();
-  b.dw0(S.d0p, P, obs_rows, S.ld_o, B);
-  b.drop_empty_phase();
+  b.dw(S.d0p, Hd, Hd, obs_rows, S.ld_o, O, B, P.g + P.oW0, P.g + P.ob0);
   b.phase(COND_ALWAYS, 1);
   b.adam(P, nullptr, c.hp.policy_lr, b1, b2, eps, 0.f, SLOT_POLICY, 1);
   b.row(ROW_SAC_FINAL, 1);
@@ -353,13 +320,12 @@ inline void build_td3(Builder& b, const Ctx& c) {
   b.phase();
   for (int i = 0; i < 2; ++i) {
     const MlpPtrs& Q = c.qf[i];
-    b.dx_l1(S.d1q[i], B, Q, S.h0q[i], S.d0q[i], S.Xoa, S.ld_oa);
+    b.dx(S.d1q[i], Hd, B, Hd, Q.p + Q.oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
     b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, Q.g + Q.oW1, Q.g + Q.ob1);
     b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, Q.g + Q.oW2, Q.g + Q.ob2);
   }
   b.phase();
-  for (int i = 0; i < 2; ++i) b.dw0(S.d0q[i], c.qf[i], S.Xoa, S.ld_oa, B);
-  b.drop_empty_phase();
+  for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0);
   b.phase();
   b.adam(c.qf[0], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF1);
   b.adam(c.qf[1], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF2);
@@ -375,12 +341,11 @@ inline void build_td3(Builder& b, const Ctx& c) {
   b.phase(PC); b.dx(S.e1[0], Hd, B, Hd, c.qf[0].p + c.qf[0].oW1, Hd, Hd, S.h0n[0], Hd, ACT_RELU, S.e0[0], Hd);
   b.phase(PC); b.row(ROW_TD3_PIBWD_DA, B);
   b.phase(PC);
-  b.dx_l1(S.d1p, B, P, S.h0p, S.d0p, S.Xoa, S.ld_oa);
+  b.dx(S.d1p, Hd, B, Hd, P.p + P.oW1, Hd, Hd, S.h0p, Hd, ACT_RELU, S.d0p, Hd);
   b.dw(S.d1p, Hd, Hd, S.h0p, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);
   b.dw(S.dmean, A, A, S.h1p, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2);
   b.phase(PC);
-  b.dw0(S.d0p, P, S.Xoa, S.ld_oa, B);
-  b.drop_empty_phase();
+  b.dw(S.d0p, Hd, Hd, S.Xoa, S.ld_oa, O, B, P.g + P.oW0, P.g + P.ob0);
   b.phase(PC, 1);
   b.adam(P, &c.tpolicy, c.hp.policy_lr, b1, b2, eps, c.hp.tau, SLOT_POLICY, 1);
   b.polyak(c.qf[0], c.tqf[0], c.hp.tau);
@@ -417,17 +382,16 @@ inline void build_sac_v(Builder& b, const Ctx& c) {
   b.phase();
   for (int i = 0; i < 2; ++i) {
     const MlpPtrs& Q = c.qf[i];
-    b.dx_l1(S.d1q[i], B, Q, S.h0q[i], S.d0q[i], S.Xoa, S.ld_oa);
+    b.dx(S.d1q[i], Hd, B, Hd, Q.p + Q.oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
     b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, Q.g + Q.oW1, Q.g + Q.ob1);
     b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, Q.g + Q.oW2, Q.g + Q.ob2);
   }
-  b.dx_l1(S.d1v, B, V, S.h0v, S.d0v, S.Xoa, S.ld_oa);
+  b.dx(S.d1v, Hd, B, Hd, V.p + V.oW1, Hd, Hd, S.h0v, Hd, ACT_RELU, S.d0v, Hd);
   b.dw(S.d1v, Hd, Hd, S.h0v, Hd, Hd, B, V.g + V.oW1, V.g + V.ob1);
   b.dw(S.dv, 1, 1, S.h1v, Hd, Hd, B, V.g + V.oW2, V.g + V.ob2);
   b.phase();
-  for (int i = 0; i < 2; ++i) b.dw0(S.d0q[i], c.qf[i], S.Xoa, S.ld_oa, B);
-  b.dw0(S.d0v, V, S.Xoa, S.ld_oa, B);
-  b.drop_empty_phase();
+  for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0);
+  b.dw(S.d0v, Hd, Hd, S.Xoa, S.ld_oa, O, B, V.g + V.oW0, V.g + V.ob0);
   b.phase();   // all three backward passes first, then the three Adam steps (sac.py:132-139)
   b.adam(c.qf[0], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF1);
   b.adam(c.qf[1], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF2);
@@ -441,13 +405,12 @@ inline void build_sac_v(Builder& b, const Ctx& c) {
   for (int i = 0; i < 2; ++i) b.dx(S.e1[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0n[i], Hd, ACT_RELU, S.e0[i], Hd);
   b.phase(); b.row(ROW_SAC_PIBWD_DA, B);
   b.phase();
-  b.dx_l1(S.d1p, B, P, h0p_obs, S.d0p, obs_rows, S.ld_o);
+  b.dx(S.d1p, Hd, B, Hd, P.p + P.oW1, Hd, Hd, h0p_obs, Hd, ACT_RELU, S.d0p, Hd);
   b.dw(S.d1p, Hd, Hd, h0p_obs, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);
   b.dw(S.dmean, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2);
   b.dw(S.dlraw, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW3, P.g + P.ob3);
   b.phase();
-  b.dw0(S.d0p, P, obs_rows, S.ld_o, B);
-  b.drop_empty_phase();
+  b.dw(S.d0p, Hd, Hd, obs_rows, S.ld_o, O, B, P.g + P.oW0, P.g + P.ob0);
   b.phase(COND_ALWAYS, 1);
   b.adam(P, nullptr, c.hp.policy_lr, b1, b2, eps, 0.f, SLOT_POLICY, 1);
   b.row(ROW_SACV_FINAL, 1);
@@ -537,12 +500,8 @@ inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem) {
   c.policy = make_mlp(sp.nets[0], grad(sp.nets[0]));
   c.qf[0] = make_mlp(sp.nets[1], grad(sp.nets[1]));
   c.qf[1] = make_mlp(sp.nets[2], grad(sp.nets[2]));
-  attach_dw0_partials(mem, c.policy, B);
-  attach_dw0_partials(mem, c.qf[0], B);
-  attach_dw0_partials(mem, c.qf[1], B);
   if (cfg.algo == ILSW_ALGO_SAC_V) {
     c.vf = make_mlp(sp.nets[3], grad(sp.nets[3]));
-    attach_dw0_partials(mem, c.vf, B);
     c.tvf = make_mlp(sp.nets[4], nullptr);
   } else {
     c.tqf[0] = make_mlp(sp.nets[3], nullptr);

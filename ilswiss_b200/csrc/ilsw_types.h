@@ -56,21 +56,10 @@ struct GemmOp {
   int mask;             // backward mask: ACT_RELU -> (H>0), ACT_TANH -> (1-H^2)
   int accumulate;       // C += value (and bias_out +=)
   int tiles_m, tiles_n;
-  // fused first-layer weight gradient (small input widths): the tile that produces delta0[32 rows, 32 cols]
-  // also emits the partial sums  P[tm][n][k'] = sum_{rows of the tile} delta0[r,n] * [X | 1][r,k']
-  float* dwp; const float* dwX; int dw_ldx, dw_k0, dw_ldp;
-};
-
-// where a gradient element comes from: the gradient arena, or (first-layer region) the sum over the
-// row tiles of the partials written by the fused delta0 tiles
-struct GradSrc {
-  const float* g;
-  const float* gpart;   // nullptr: plain arena
-  int gp_tiles, gp_rows, gp_k0, gp_ldp;   // partial layout [tiles][rows][ldp]; W0 is [rows x k0], b0 follows
 };
 
 struct AdamOp {
-  float* p; GradSrc gs; float* m; float* v;
+  float* p; const float* g; float* m; float* v;
   float* target;        // optional Polyak target updated from the NEW p (nullptr: none)
   int n;
   double lr, beta1, beta2, eps; float tau;
@@ -112,7 +101,6 @@ struct MlpPtrs {        // canonical 2-hidden-layer layout inside one flat arena
   int n_params;
   // element offsets
   int oW0, ob0, oW1, ob1, oW2, ob2, oW3, ob3;
-  float* gpart; int gp_tiles, gp_ldp;       // fused first-layer gradient partials [tiles][hid][ldp] (nullptr: none)
 };
 
 struct SacBufs {        // SAC-alpha / TD3 / SAC-V scratch (all fp32, row-major)

@@ -43,8 +43,6 @@ static void run_op(HostSim* hs, const Program& P, const Op& o, const RunArgs& a,
         }
         gemm_epilogue(g, m, n, acc);
       }
-    if (g.dwp)
-      for (int tm = 0; tm < g.tiles_m; ++tm) gemm_dw0_partials_tile(g, tm);
   } else if (o.kind == OP_ROW) {
     const bool fast = !hs->generic_rows && fast_rows_ok(c);
     s += o.row.arg0;                               // arg0 = 1: prefetch job for the next step
