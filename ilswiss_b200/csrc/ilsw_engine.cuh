@@ -526,7 +526,8 @@ __device__ __forceinline__ bool replica_exchange(const Replica& rp, unsigned seq
     long long t0 = clock64();
     while ((int)(ld_acquire_sys(rp.flags_local + threadIdx.x) - seq) < 0) {
       long long dt = clock64() - t0;
-      if (dt > kSpinLimit && (*(volatile int*)abort_flag || dt > 2 * kSpinLimit)) {
+      // peers may start their launch seconds later (module load, host jitter): be patient (~20 s)
+      if (dt > kSpinLimit && (*(volatile int*)abort_flag || dt > 10 * kSpinLimit)) {
         atomicExch(abort_flag, 1);
         s_ok2 = 0;
         break;

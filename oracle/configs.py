@@ -50,6 +50,17 @@ CASES = {
                         disc=dict(disc_lr=3e-4, disc_momentum=0.9, use_grad_pen=True,
                                   grad_pen_weight=4.0),
                         sac=dict(SAC_KW, reward_scale=1.0, alpha=0.2), seed=20),
+    # ragged shapes: batch not a multiple of the 32-row tile / of 4, odd hidden widths, tiny dims
+    "sac_ragged": dict(algo="sac_alpha", obs_dim=5, act_dim=2, batch=70, n_fill=300, steps=3, hidden=64,
+                       sac=dict(SAC_KW, alpha=0.2), seed=21),
+    "td3_ragged": dict(algo="td3", obs_dim=7, act_dim=3, batch=72, n_fill=500, steps=4, hidden=96,
+                       td3=dict(reward_scale=1.0, discount=0.99, soft_target_tau=0.005, policy_lr=3e-4,
+                                qf_lr=3e-4, policy_and_target_update_period=2),
+                       policy_noise=0.2, policy_noise_clip=0.5, seed=22),
+    "gail_ragged": dict(algo="adv_irl", obs_dim=5, act_dim=2, batch=40, n_fill=400, n_expert=90, steps=3,
+                        mode="gail2", hidden=64, disc_hid=48,
+                        disc=dict(disc_lr=3e-4, disc_momentum=0.9, use_grad_pen=True, grad_pen_weight=8.0),
+                        sac=dict(SAC_KW, reward_scale=2.0, beta_1=0.25, alpha=0.2), seed=23),
 }
 
 HIDDEN = (256, 256)

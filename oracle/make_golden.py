@@ -40,18 +40,20 @@ def build_oracle_nets(case):
     O, A = case["obs_dim"], case["act_dim"]
     nets = OrderedDict()
     algo = case["algo"]
+    HID = (case.get("hidden", C.HIDDEN[0]),) * 2
+    DH = case.get("disc_hid", C.DISC_HID)
     if algo in ("sac_alpha", "sac_v", "adv_irl"):
-        nets["qf1"] = R.Net(R.init_mlp(rs, O + A, C.HIDDEN, 1))
-        nets["qf2"] = R.Net(R.init_mlp(rs, O + A, C.HIDDEN, 1))
+        nets["qf1"] = R.Net(R.init_mlp(rs, O + A, HID, 1))
+        nets["qf2"] = R.Net(R.init_mlp(rs, O + A, HID, 1))
         if algo == "sac_v":
-            nets["vf"] = R.Net(R.init_mlp(rs, O, C.HIDDEN, 1))
-        nets["policy"] = R.Net(R.init_mlp(rs, O, C.HIDDEN, A, init_w=1e-3, log_std_head=True))
+            nets["vf"] = R.Net(R.init_mlp(rs, O, HID, 1))
+        nets["policy"] = R.Net(R.init_mlp(rs, O, HID, A, init_w=1e-3, log_std_head=True))
         if algo == "adv_irl":
-            nets["disc"] = R.Net(R.init_disc(rs, O + A, C.DISC_HID))
+            nets["disc"] = R.Net(R.init_disc(rs, O + A, DH))
     elif algo == "td3":
-        nets["qf1"] = R.Net(R.init_mlp(rs, O + A, C.HIDDEN, 1))
-        nets["qf2"] = R.Net(R.init_mlp(rs, O + A, C.HIDDEN, 1))
-        nets["policy"] = R.Net(R.init_mlp(rs, O, C.HIDDEN, A, init_w=1e-3))
+        nets["qf1"] = R.Net(R.init_mlp(rs, O + A, HID, 1))
+        nets["qf2"] = R.Net(R.init_mlp(rs, O + A, HID, 1))
+        nets["policy"] = R.Net(R.init_mlp(rs, O, HID, A, init_w=1e-3))
     # perturb so that nothing sits exactly on the tiny U(+-3e-3) last-layer init: makes
     # log_std clamps, relu masks and min(q1,q2) selections non-trivial in the fixtures
     for name, net in nets.items():
@@ -117,22 +119,24 @@ def run_reference(case):
     env = ref_shim.FakeEnv(O, A)
     algo = case["algo"]
     mods = OrderedDict()
+    HID = [case.get("hidden", C.HIDDEN[0])] * 2
+    DH = case.get("disc_hid", C.DISC_HID)
 
     def mk_q():
-        return ref.FlattenMlp(hidden_sizes=list(C.HIDDEN), input_size=O + A, output_size=1)
+        return ref.FlattenMlp(hidden_sizes=list(HID), input_size=O + A, output_size=1)
 
     mods["qf1"], mods["qf2"] = mk_q(), mk_q()
     if algo == "sac_v":
-        mods["vf"] = ref.FlattenMlp(hidden_sizes=list(C.HIDDEN), input_size=O, output_size=1)
+        mods["vf"] = ref.FlattenMlp(hidden_sizes=list(HID), input_size=O, output_size=1)
     if algo == "td3":
         mods["policy"] = ref.MlpGaussianNoisePolicy(
-            hidden_sizes=list(C.HIDDEN), obs_dim=O, action_dim=A, output_activation=torch.tanh,
+            hidden_sizes=list(HID), obs_dim=O, action_dim=A, output_activation=torch.tanh,
             policy_noise=case["policy_noise"], policy_noise_clip=case["policy_noise_clip"])
     else:
         mods["policy"] = ref.ReparamTanhMultivariateGaussianPolicy(
-            hidden_sizes=list(C.HIDDEN), obs_dim=O, action_dim=A)
+            hidden_sizes=list(HID), obs_dim=O, action_dim=A)
     if algo == "adv_irl":
-        mods["disc"] = ref.MLPDisc(O + A, num_layer_blocks=2, hid_dim=C.DISC_HID, hid_act="tanh",
+        mods["disc"] = ref.MLPDisc(O + A, num_layer_blocks=2, hid_dim=DH, hid_act="tanh",
                                    use_bn=False, clamp_magnitude=10.0)
     for k, m in mods.items():
         _load_into_module(m, nets[k])
@@ -153,7 +157,7 @@ def run_reference(case):
             num_disc_updates_per_loop_iter=1, num_policy_updates_per_loop_iter=1,
             rew_clip_min=case.get("rew_clip_min"), rew_clip_max=case.get("rew_clip_max"),
             env=env, exploration_policy=mods["policy"], training_env=None, replay_buffer=buf,
-            max_path_length=100, no_terminal=True, **case["disc"])
+            max_path_length=min(100, case["n_fill"] - 1), no_terminal=True, **case["disc"])
 
     rows = []
     for t in range(case["steps"]):

@@ -149,13 +149,14 @@ def initial_arenas(case):
 
 def mlp_dims(case, name):
     O, A = case["obs_dim"], case["act_dim"]
+    H = case.get("hidden", CFG.HIDDEN[0])
     if name in ("policy", "target_policy"):
-        return O, CFG.HIDDEN[0], A, int(case["algo"] != "td3")
+        return O, H, A, int(case["algo"] != "td3")
     if name == "disc":
-        return O + A, CFG.DISC_HID, 1, 0
+        return O + A, case.get("disc_hid", CFG.DISC_HID), 1, 0
     if name in ("vf", "target_vf"):
-        return O, CFG.HIDDEN[0], 1, 0
-    return O + A, CFG.HIDDEN[0], 1, 0
+        return O, H, 1, 0
+    return O + A, H, 1, 0
 
 
 # ---------------------------------------------------------------------------------------------
