@@ -93,6 +93,8 @@ PROTOTYPES = {
     "ilsw_num_phases": (C.c_int, [C.c_void_p]),
     "ilsw_read_phase_ns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ilsw_read_tile_ns": (C.c_int, [C.c_void_p]),
+    "ilsw_trainer_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "ilsw_read_cta_ns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ilsw_kernel_launches": (C.c_int64, [C.c_void_p]),
     "ilsw_policy_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "ilsw_replica_export": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -8,7 +8,8 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libilswiss_b200.so")
+# ILSW_LIB: development override used to A/B kernel variants on one GPU box (tools/ab.sh)
+LIB_PATH = os.environ.get("ILSW_LIB") or os.path.join(_HERE, "csrc", "libilswiss_b200.so")
 _lib = None
 
 

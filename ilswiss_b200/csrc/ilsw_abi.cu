@@ -258,6 +258,7 @@ struct ilsw_trainer {
   int n_total;
   int last_steps;
   int64_t launches;
+  int profile;
   // replicas
   char* ipc_buf;          // [flags 256B][recv 2*8*n floats]
   size_t ipc_bytes;
@@ -398,6 +399,7 @@ extern "C" int ilsw_train(ilsw_trainer* tr, ilsw_rb* policy_rb, ilsw_rb* expert_
     if (!inject) a.has_inject = 0;
   }
   a.world = tr->rep.world; a.rank = tr->rep.rank; a.loss_log_offset = 0;
+  a.profile = tr->profile;
   Replica rp = tr->rep;
   rp.seq0 = tr->seq;
   const Program* dp = tr->dev_prog;
@@ -486,9 +488,21 @@ extern "C" int ilsw_read_phase_ns(ilsw_trainer* tr, unsigned long long* host_out
   CU(cudaStreamSynchronize(st));
   return ILSW_OK;
 }
+extern "C" int ilsw_read_cta_ns(ilsw_trainer* tr, unsigned long long* host_out /* [96][304] */, void* stream) {
+  if (!tr || !host_out) return fail(ILSW_ERR_ARG, "read_cta_ns: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemcpyAsync(host_out, tr->host_prog.ctx.cta_ns, sizeof(unsigned long long) * kMaxPhases * kMaxGrid, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return ILSW_OK;
+}
 extern "C" int ilsw_read_tile_ns(unsigned long long* host_out /* [kMaxPhases][8] */) {
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpyFromSymbol(host_out, g_tile_ns, sizeof(unsigned long long) * kMaxPhases * 8));
+  return ILSW_OK;
+}
+extern "C" int ilsw_trainer_set_profiling(ilsw_trainer* tr, int on) {
+  if (!tr) return fail(ILSW_ERR_ARG, "set_profiling: null");
+  tr->profile = on ? 1 : 0;
   return ILSW_OK;
 }
 extern "C" int ilsw_num_phases(const ilsw_trainer* tr) { return tr ? tr->host_prog.n_phases : ILSW_ERR_ARG; }

@@ -196,7 +196,12 @@ __device__ __forceinline__ void tile_store_B(const GemmOp& o, float* Bs, const f
   }
 }
 
-__device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* smem) {
+// fused optimiser step on gradient element gi (value g) -- the tile epilogues' Adam(+Polyak)
+__device__ __forceinline__ void adam_fused_elem(const AdamOp& ad, const AdamCoef& cf, int gi, float g) {
+  adam_elem_g(ad, cf, gi, g);
+}
+
+__device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* smem, const AdamOp* ad, const AdamCoef* cf) {
   const int tid = threadIdx.x;
   const int tm = tile / o.tiles_n, tn = tile - tm * o.tiles_n;
   const int m0 = tm * kTM, n0 = tn * kTN;
@@ -247,7 +252,7 @@ __device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* 
 #pragma unroll
     for (int j = 0; j < 4; ++j) red[(kg * 64 + t) * 17 + i * 4 + j] = acc[i][j];
   __syncthreads();
-  const int Nt = o.N + o.aug_ones;
+  const int Nt = o.N;      // the aug column (n == N) is produced below from column sums of A
   const int m = m0 + ty * 4 + kg;
   EpiIn ein[4];
   float vout[4];
@@ -266,7 +271,18 @@ __device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* 
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int n = n0 + tx * 4 + j;
-    if (m < o.M && n < Nt) epi_store(o, m, n, vout[j], ein[j]);
+    if (m < o.M && n < Nt) {
+      epi_store(o, m, n, vout[j], ein[j]);
+      if (ad) adam_fused_elem(*ad, *cf, gemm_grad_index(o, *ad, m, n), o.accumulate ? vout[j] + ein[j].prev : vout[j]);
+    }
+  }
+  if (o.aug_ones && tn == 0 && tid < 32 && m0 + tid < o.M) {     // bias gradient: bias_out[m] = sum_k A(m,k)
+    const int mm = m0 + tid;
+    float ssum = 0.f;
+    for (int k = 0; k < o.K; ++k) ssum += gemm_A(o, mm, k);
+    const EpiIn e = epi_load(o, mm, o.N);
+    epi_store(o, mm, o.N, ssum, e);
+    if (ad) adam_fused_elem(*ad, *cf, gemm_grad_index(o, *ad, mm, o.N), o.accumulate ? ssum + e.prev : ssum);
   }
   __syncthreads();
 }
@@ -300,6 +316,9 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, i
   unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16s(unsigned smem_dst, const float* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -314,42 +333,82 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// profiling: CTA 0 / thread 0 stamps the stages of its LAST tile of every phase (read with
-// ilsw_read_tile_ns): [phase][0..4] = tile start, panels issued, panels landed, MMA done, epilogue done
+// profiling (opt-in, ilsw_trainer_set_profiling): thread 0 of CTA 0 stamps the stages of its LAST tile of
+// every phase (read with ilsw_read_tile_ns): [phase][0..4] = tile start, panels issued, panels landed, MMA
+// done, epilogue done.  `prof_phase` < 0 (the production setting) compiles to one predictable branch per
+// stamp: no global traffic on the critical path of CTA 0.
 __device__ unsigned long long g_tile_ns[kMaxPhases][8];
-__device__ int g_dbg_phase;
-#define ILSW_TSTAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_tile_ns[g_dbg_phase][i] = globaltimer_ns(); } while (0)
+#define ILSW_TSTAMP(i) do { if (prof_phase >= 0 && threadIdx.x == 0) g_tile_ns[prof_phase][i] = globaltimer_ns(); } while (0)
 
-// the 6 fragment words of one k-step (A: rows g,g+8 x k q,q+4; B: k q,q+4) with explicit 32-bit shared
-// addresses, issued back to back by one asm block
-struct Frag { float a[4]; float b[2]; };
-__device__ __forceinline__ void frag_load(Frag& f, unsigned ap, unsigned a_row8, unsigned a_k4, unsigned bp, unsigned b_k4) {
+// Fragment words of ONE k-step (k8) for the whole 32x32 tile: A = 2 m16 tiles x 4 words, B = 4 n8 tiles
+// x 2 words (m16n8k8 TF32 fragment layout: a0 (g,q) a1 (g+8,q) a2 (g,q+4) a3 (g+8,q+4); b0 (q,g) b1 (q+4,g)).
+// Explicit 32-bit shared addresses, the 16 loads issued back to back.
+struct FragSet { float a[8]; float b[8]; };
+__device__ __forceinline__ void fragset_load(FragSet& f, unsigned ap, unsigned a_row8, unsigned a_k4, unsigned a_mt,
+                                             unsigned bp, unsigned b_k4, unsigned b_nt) {
   asm volatile(
-      "ld.shared.f32 %0, [%6];\n\t"
-      "ld.shared.f32 %1, [%7];\n\t"
-      "ld.shared.f32 %2, [%8];\n\t"
-      "ld.shared.f32 %3, [%9];\n\t"
-      "ld.shared.f32 %4, [%10];\n\t"
-      "ld.shared.f32 %5, [%11];"
-      : "=f"(f.a[0]), "=f"(f.a[1]), "=f"(f.a[2]), "=f"(f.a[3]), "=f"(f.b[0]), "=f"(f.b[1])
-      : "r"(ap), "r"(ap + a_row8), "r"(ap + a_k4), "r"(ap + a_row8 + a_k4), "r"(bp), "r"(bp + b_k4)
+      "ld.shared.f32 %0, [%8];\n\t"
+      "ld.shared.f32 %1, [%9];\n\t"
+      "ld.shared.f32 %2, [%10];\n\t"
+      "ld.shared.f32 %3, [%11];\n\t"
+      "ld.shared.f32 %4, [%12];\n\t"
+      "ld.shared.f32 %5, [%13];\n\t"
+      "ld.shared.f32 %6, [%14];\n\t"
+      "ld.shared.f32 %7, [%15];"
+      : "=f"(f.a[0]), "=f"(f.a[1]), "=f"(f.a[2]), "=f"(f.a[3]), "=f"(f.a[4]), "=f"(f.a[5]), "=f"(f.a[6]), "=f"(f.a[7])
+      : "r"(ap), "r"(ap + a_row8), "r"(ap + a_k4), "r"(ap + a_row8 + a_k4),
+        "r"(ap + a_mt), "r"(ap + a_mt + a_row8), "r"(ap + a_mt + a_k4), "r"(ap + a_mt + a_row8 + a_k4)
+      : "memory");
+  asm volatile(
+      "ld.shared.f32 %0, [%8];\n\t"
+      "ld.shared.f32 %1, [%9];\n\t"
+      "ld.shared.f32 %2, [%10];\n\t"
+      "ld.shared.f32 %3, [%11];\n\t"
+      "ld.shared.f32 %4, [%12];\n\t"
+      "ld.shared.f32 %5, [%13];\n\t"
+      "ld.shared.f32 %6, [%14];\n\t"
+      "ld.shared.f32 %7, [%15];"
+      : "=f"(f.b[0]), "=f"(f.b[1]), "=f"(f.b[2]), "=f"(f.b[3]), "=f"(f.b[4]), "=f"(f.b[5]), "=f"(f.b[6]), "=f"(f.b[7])
+      : "r"(bp), "r"(bp + b_k4), "r"(bp + b_nt), "r"(bp + b_nt + b_k4),
+        "r"(bp + 2u * b_nt), "r"(bp + 2u * b_nt + b_k4), "r"(bp + 3u * b_nt), "r"(bp + 3u * b_nt + b_k4)
       : "memory");
 }
-__device__ __forceinline__ void frag_mma(float (&acc)[4], const Frag& f, int mode) {
-  uint32_t ah[4], bh[2];
+__device__ __forceinline__ void mma_tf32p(float* d, const uint32_t* a, const uint32_t* b) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// all MMAs of one k-step: 8 independent accumulator tiles, so consecutive MMAs never depend on each
+// other (mode 3: the 8 lo*hi products, then the 8 hi*lo, then the 8 hi*hi -- small terms first per
+// accumulator).  n_mt / n_nt: live m16 / n8 tiles of a ragged output tile (warp-uniform).
+template <bool FULL>
+__device__ __forceinline__ void fragset_mma(float (&acc)[8][4], const FragSet& f, int mode, int n_mt, int n_nt) {
+  uint32_t ah[8], bh[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) ah[i] = cvt_tf32(f.a[i]);
-  bh[0] = cvt_tf32(f.b[0]); bh[1] = cvt_tf32(f.b[1]);
+  for (int i = 0; i < 8; ++i) { ah[i] = cvt_tf32(f.a[i]); bh[i] = cvt_tf32(f.b[i]); }
   if (mode == 3) {
-    uint32_t al[4], bl[2];
+    uint32_t al[8], bl[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) al[i] = cvt_tf32(f.a[i] - __uint_as_float(ah[i]));
+    for (int i = 0; i < 8; ++i) {
+      al[i] = cvt_tf32(f.a[i] - __uint_as_float(ah[i]));
+      bl[i] = cvt_tf32(f.b[i] - __uint_as_float(bh[i]));
+    }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) bl[i] = cvt_tf32(f.b[i] - __uint_as_float(bh[i]));
-    mma_tf32(acc, al, bh);
-    mma_tf32(acc, ah, bl);
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        if (FULL || (mt < n_mt && nt < n_nt)) mma_tf32p(acc[mt * 4 + nt], al + 4 * mt, bh + 2 * nt);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        if (FULL || (mt < n_mt && nt < n_nt)) mma_tf32p(acc[mt * 4 + nt], ah + 4 * mt, bl + 2 * nt);
   }
-  mma_tf32(acc, ah, bh);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      if (FULL || (mt < n_mt && nt < n_nt)) mma_tf32p(acc[mt * 4 + nt], ah + 4 * mt, bh + 2 * nt);
 }
 __device__ __forceinline__ void cp_async4(unsigned smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
@@ -386,65 +445,91 @@ __device__ __noinline__ void tc_fill_stage(const GemmOp& o, float* stage, int m0
     const int sr = contig_k ? ld : 1, sk = contig_k ? 1 : ld;        // source strides
     const int dr = contig_k ? kKS : 1, dk = contig_k ? 1 : kMS;      // shared strides
     if (vec) {
-#pragma unroll 2
+      // thread -> one 16-byte vector per iteration; (row, k) advance by constant steps, so the loop body is
+      // predicate + cp.async + 4 adds (the step engine is instruction-latency bound: every instruction
+      // removed from a tile's prologue is ~5 cycles off the critical path)
+      int r = contig_k ? (tid >> kVecShift) : ((tid & 7) << 2);
+      int k = contig_k ? ((tid & (kVecPerRow - 1)) << 2) : (tid >> 3);
+      const int rstep = contig_k ? (kThreads >> kVecShift) : 0, kstep = contig_k ? 0 : (kThreads >> 3);
+      const int rlim = R - row0;
+      const float* src = base + (size_t)(row0 + r) * sr + (size_t)(k0 + k) * sk;
+      const size_t sstep = (size_t)rstep * sr + (size_t)kstep * sk;
+      unsigned dst = (unsigned)__cvta_generic_to_shared(sm + r * dr + k * dk);
+      const unsigned dstep = 4u * (unsigned)(rstep * dr + kstep * dk);
+#pragma unroll 4
       for (int i = 0; i < kVecIters; ++i) {                    // 32 x KC floats = 8*KC vectors
-        const int v = tid + i * kThreads;
-        const int r = contig_k ? (v >> kVecShift) : ((v & 7) << 2);
-        const int k = contig_k ? ((v & (kVecPerRow - 1)) << 2) : (v >> 3);
-        const bool in = (row0 + r < R) && (k < klen);
-        const float* src = in ? base + (size_t)(row0 + r) * sr + (size_t)(k0 + k) * sk : base;
-        cp_async16(sm + r * dr + k * dk, src, in ? 16 : 0);
+        const bool in = (r < rlim) && (k < klen);
+        cp_async16s(dst, in ? src : base, in ? 16 : 0);
+        src += sstep; dst += dstep; r += rstep; k += kstep;
       }
     } else {
       const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
-      const bool aug = isB && o.aug_ones;
       // only rows that exist (plus the ones column) and kpad k's are touched; the rest of the
-      // 32-row fragment range is zeroed so the MMA sees exact zeros
+      // 32-row fragment range is zeroed so the MMA sees exact zeros.  Element e = tid + j*256 maps to
+      // (r, k) = (e / kpad, e % kpad) [k contiguous] or (e % 32, e / 32); both advance incrementally.
       const int nelem = 32 * kpad;
+      int r, k, rq, kq;
+      if (contig_k) { r = tid / kpad; k = tid - r * kpad; rq = kThreads / kpad; kq = kThreads - rq * kpad; }
+      else { r = tid & 31; k = tid >> 5; rq = 0; kq = kThreads >> 5; }
+      const int rlim = R - row0;
 #pragma unroll 2
       for (int e = tid; e < nelem; e += kThreads) {
-        const int r = contig_k ? e / kpad : (e & 31);
-        const int k = contig_k ? e - r * kpad : (e >> 5);
         const unsigned dst = sbase + 4u * (unsigned)(r * dr + k * dk);
-        const int gr = row0 + r;
-        if (gr < R && k < klen) cp_async4(dst, base + (size_t)gr * sr + (size_t)(k0 + k) * sk);
-        else sts_u32(dst, (aug && gr == R && k < klen) ? 1.0f : 0.f);
+        if (r < rlim && k < klen) cp_async4(dst, base + (size_t)(row0 + r) * sr + (size_t)(k0 + k) * sk);
+        else sts_u32(dst, 0.f);
+        r += rq; k += kq;
+        if (contig_k && k >= kpad) { k -= kpad; r += 1; }
       }
     }
   }
 }
 
+constexpr int kRedLd = 36;                    // row stride of a per-warp partial tile (floats; 16-byte aligned rows)
+constexpr int kRedFloats = 8 * 32 * kRedLd;   // 36 KB: fits one staging stage of either occupancy variant
+
+// 32x32 output tile.  The K range of every stage is split over the 8 warps (warp w owns k-steps w, w+8,
+// ...): each warp accumulates the WHOLE 32x32 tile for its k-steps in 8 independent m16n8 accumulators
+// (24 independent MMAs per k-step in 3xTF32 mode -> the loop is issue bound, not MMA-latency bound; one
+// fragment word feeds 2-4 MMAs), then the 8 partial tiles are summed through shared memory in warp order
+// (fixed order: bit-reproducible).  Measured predecessor (one 16x8 accumulator per warp over the full K,
+// 96 dependent MMAs): 3.3 us of a 5.9 us tile.
 template <int KC>
-__device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* smem, int mode) {
+__device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* smem, int mode, int prof_phase, const AdamOp* ad, const AdamCoef* cf) {
   constexpr int kKC = KC, kKS = TcGeom<KC>::kKS, kOperandFloats = TcGeom<KC>::kOperandFloats, kTcStageFloats = TcGeom<KC>::kStageFloats;
+  static_assert(kRedFloats <= TcGeom<KC>::kStageFloats, "partial tiles must fit one stage");
   const GemmOp o = og;                       // registers / local copy: the op descriptor lives in shared memory
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tm = tile / o.tiles_n, tn = tile - tm * o.tiles_n;
   const int m0 = tm * 32, n0 = tn * 32;
-  const int mb = warp >> 2, nb = warp & 3;
   const int g = lane >> 2, q = lane & 3;
   const bool a_kc = !o.a_mc, b_kc = !o.b_nc;
   const bool vecA = ((o.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(o.A) & 15) == 0) && ((o.K & 3) == 0) && ((o.M & 3) == 0);
-  const bool vecB = ((o.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(o.B) & 15) == 0) && ((o.K & 3) == 0) && ((o.N & 3) == 0) &&
-                    !(o.aug_ones && n0 + 32 > o.N);
+  const bool vecB = ((o.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(o.B) & 15) == 0) && ((o.K & 3) == 0) && ((o.N & 3) == 0);
   const int nstages = (o.K + kKC - 1) / kKC;
-  const int Nt = o.N + o.aug_ones;
-  const int r0 = m0 + mb * 16 + g, c0 = n0 + nb * 8 + 2 * q;
-  float accs[2][4];
+  const int Nt = o.N;
+  // bias gradient (aug_ones): bias_out[m] = sum_k A(m,k), taken from the A panels (m-contiguous layout) by the tn == 0 tile
+  const bool do_aug = o.aug_ones && tn == 0;
+  float colsum = 0.f;
+  // live fragment tiles of a ragged output tile (N = 3, 14, 1 ...): warp-uniform
+  const int n_mt = min(2, (o.M - m0 + 15) >> 4), n_nt = min(4, (Nt - n0 + 7) >> 3);
+  const bool full = (n_mt == 2) && (n_nt == 4);
+  // epilogue mapping: thread -> (row = tid / 8, 4 consecutive columns)
+  const int er = m0 + (tid >> 3), ec = n0 + ((tid & 7) << 2);
+  float acc[8][4];
 #pragma unroll
-  for (int u = 0; u < 2; ++u)
+  for (int u = 0; u < 8; ++u)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) accs[u][i] = 0.f;
+    for (int i = 0; i < 4; ++i) acc[u][i] = 0.f;
   EpiIn ein[4];
   ILSW_TSTAMP(0);
   // fragment addressing (32-bit shared addresses, bytes)
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
-  const unsigned a_off = 4u * (a_kc ? (mb * 16 + g) * kKS + q : q * kMS + mb * 16 + g);
-  const unsigned b_off = 4u * (b_kc ? (nb * 8 + g) * kKS + q : q * kMS + nb * 8 + g);
+  const unsigned a_off = 4u * (a_kc ? g * kKS + q : q * kMS + g);
+  const unsigned b_off = 4u * (b_kc ? g * kKS + q : q * kMS + g);
   const unsigned a_row8 = 4u * (a_kc ? 8 * kKS : 8), a_k4 = 4u * (a_kc ? 4 : 4 * kMS), a_k8 = 2u * a_k4;
+  const unsigned a_mt = 2u * a_row8;                                   // next m16 tile
   const unsigned b_k4 = 4u * (b_kc ? 4 : 4 * kMS), b_k8 = 2u * b_k4;
-  // does this warp's 16x8 fragment intersect the valid output at all?  (ragged tiles: N = 3, 14, 1 ...)
-  const bool warp_live = (m0 + mb * 16 < o.M) && (n0 + nb * 8 < Nt);
+  const unsigned b_nt = 4u * (b_kc ? 8 * kKS : 8);                     // next n8 tile
 #pragma unroll 1
   for (int st = -1; st < nstages; ++st) {
     if (st + 1 < nstages) {
@@ -455,49 +540,179 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
     if (st < 0) {
       // epilogue inputs (bias / mask source / previous value) are fetched while the panels are in flight
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = r0 + ((i & 2) ? 8 : 0), n = c0 + (i & 1);
-        if (m < o.M && n < Nt) ein[i] = epi_load(o, m, n);
-      }
+      for (int i = 0; i < 4; ++i)
+        if (er < o.M && ec + i < Nt) ein[i] = epi_load(o, er, ec + i);
       ILSW_TSTAMP(1);
       continue;
     }
     if (st + 1 < nstages) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
     if (st == 0) ILSW_TSTAMP(2);
-    if (warp_live) {
+    {
       const int klen = min(kKC, o.K - st * kKC);
-      const int ksteps = ((klen + 15) >> 4) << 1;   // panels are zero padded up to a multiple of 16
-      unsigned ap = sbase + 4u * (unsigned)((st & 1) * kTcStageFloats) + a_off;
-      unsigned bp = sbase + 4u * (unsigned)((st & 1) * kTcStageFloats + kOperandFloats) + b_off;
-      // Software-pipelined k loop, unrolled by two with ping-pong fragment registers and two
-      // independent accumulator sets: the loads of step k+1 are issued before the MMA of step k, there
-      // is no per-step guard (panels are zero padded to an even number of steps; the last prefetch
-      // reads one step past the panel, inside the shared allocation, and is never used).
-      Frag f0, f1;
-      frag_load(f0, ap, a_row8, a_k4, bp, b_k4);
-      ap += a_k8; bp += b_k8;
+      const int ksteps = (klen + 7) >> 3;            // panels are zero padded up to a multiple of 16
+      const unsigned a0 = sbase + 4u * (unsigned)((st & 1) * kTcStageFloats) + a_off;
+      const unsigned b0 = sbase + 4u * (unsigned)((st & 1) * kTcStageFloats + kOperandFloats) + b_off;
+      // software pipeline over this warp's k-steps: the fragment loads of the next k-step are issued
+      // before the MMAs of the current one (ping-pong fragment registers)
+      FragSet f0, f1;
+      int ks = warp;
+      if (ks < ksteps) fragset_load(f0, a0 + (unsigned)ks * a_k8, a_row8, a_k4, a_mt, b0 + (unsigned)ks * b_k8, b_k4, b_nt);
+      if (full) {          // all 8 fragment tiles live: straight-line MMAs, no guards
 #pragma unroll 1
-      for (int k2 = 0; k2 < ksteps; k2 += 2) {
-        frag_load(f1, ap, a_row8, a_k4, bp, b_k4);
-        ap += a_k8; bp += b_k8;
-        frag_mma(accs[0], f0, mode);
-        frag_load(f0, ap, a_row8, a_k4, bp, b_k4);
-        ap += a_k8; bp += b_k8;
-        frag_mma(accs[1], f1, mode);
+        while (ks < ksteps) {
+          int kn = ks + 8;
+          if (kn < ksteps) fragset_load(f1, a0 + (unsigned)kn * a_k8, a_row8, a_k4, a_mt, b0 + (unsigned)kn * b_k8, b_k4, b_nt);
+          fragset_mma<true>(acc, f0, mode, 2, 4);
+          ks = kn;
+          if (ks >= ksteps) break;
+          kn = ks + 8;
+          if (kn < ksteps) fragset_load(f0, a0 + (unsigned)kn * a_k8, a_row8, a_k4, a_mt, b0 + (unsigned)kn * b_k8, b_k4, b_nt);
+          fragset_mma<true>(acc, f1, mode, 2, 4);
+          ks = kn;
+        }
+      } else {             // ragged output tile (N = 3, 14, 1 ...): skip the dead fragment tiles
+#pragma unroll 1
+        for (; ks < ksteps; ks += 8) {
+          fragset_mma<false>(acc, f0, mode, n_mt, n_nt);
+          if (ks + 8 < ksteps) fragset_load(f0, a0 + (unsigned)(ks + 8) * a_k8, a_row8, a_k4, a_mt, b0 + (unsigned)(ks + 8) * b_k8, b_k4, b_nt);
+        }
       }
     }
-    __syncthreads();   // stage buffer may be refilled by the next iteration's prefetch
+    if (do_aug) {      // thread -> (m = tid % 32, k = tid / 32 + 8 i): conflict-free reads of the [k][kMS] panel
+      const int klen = min(kKC, o.K - st * kKC);
+      const float* As = smem + (st & 1) * kTcStageFloats + (tid >> 5) * kMS + (tid & 31);
+      float sacc = 0.f;
+      for (int k = tid >> 5; k < klen; k += 8, As += 8 * kMS) sacc += *As;
+      colsum += sacc;
+    }
+    __syncthreads();   // stage buffer may be refilled by the next iteration's prefetch / reused for the partials
+  }
+  // cross-warp reduction of the partial tiles (stage 0 area; all warps are past their MMAs)
+  const int nred = min(8, (min(kKC, o.K) + 7) >> 3);      // warps that own at least one k-step (stage 0 is the longest)
+  if (warp < nred) {
+    float* red = smem + warp * (32 * kRedLd);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float* r0p = red + (mt * 16 + g) * kRedLd + nt * 8 + 2 * q;
+        *reinterpret_cast<float2*>(r0p) = make_float2(acc[mt * 4 + nt][0], acc[mt * 4 + nt][1]);
+        *reinterpret_cast<float2*>(r0p + 8 * kRedLd) = make_float2(acc[mt * 4 + nt][2], acc[mt * 4 + nt][3]);
+      }
+  }
+  if (do_aug) smem[kRedFloats + tid] = colsum;
+  __syncthreads();
+  float4 sum = *reinterpret_cast<const float4*>(smem + (tid >> 3) * kRedLd + ((tid & 7) << 2));
+  for (int w = 1; w < nred; ++w) {
+    const float4 v = *reinterpret_cast<const float4*>(smem + w * (32 * kRedLd) + (tid >> 3) * kRedLd + ((tid & 7) << 2));
+    sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
   }
   ILSW_TSTAMP(3);
+  const float outv[4] = {sum.x, sum.y, sum.z, sum.w};
+  if (ad) {
+    // weight-gradient tile with the optimiser fused: all Adam-state loads of the 4 elements first (one L2 round trip)
+    int gi[4]; float am[4], av[4], ap[4], at[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = r0 + ((i & 2) ? 8 : 0), n = c0 + (i & 1);
-    const float accv = accs[0][i] + accs[1][i];
-    if (m < o.M && n < Nt) epi_store(o, m, n, accv, ein[i]);
+    for (int i = 0; i < 4; ++i) {
+      gi[i] = -1;
+      if (er < o.M && ec + i < Nt) {
+        gi[i] = gemm_grad_index(o, *ad, er, ec + i);
+        am[i] = __ldcg(ad->m + gi[i]); av[i] = __ldcg(ad->v + gi[i]); ap[i] = __ldcg(ad->p + gi[i]);
+        at[i] = ad->target ? __ldcg(ad->target + gi[i]) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (gi[i] >= 0) {
+        const float gv = o.accumulate ? outv[i] + ein[i].prev : outv[i];
+        o.C[(size_t)er * o.ldc + ec + i] = gv;
+        adam_math_store(*ad, *cf, gi[i], gv, am[i], av[i], ap[i], at[i]);
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (er < o.M && ec + i < Nt) epi_store(o, er, ec + i, outv[i], ein[i]);
   }
+  if (do_aug && tid < 32 && m0 + tid < o.M) {
+    float bsum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) bsum += smem[kRedFloats + w * 32 + tid];
+    const EpiIn e = epi_load(o, m0 + tid, o.N);
+    epi_store(o, m0 + tid, o.N, bsum, e);
+    if (ad) adam_fused_elem(*ad, *cf, gemm_grad_index(o, *ad, m0 + tid, o.N), o.accumulate ? bsum + e.prev : bsum);
+  }
+  __syncthreads();     // the partial tiles are read before the next job's panels overwrite them
   ILSW_TSTAMP(4);
 }
+
+// Skinny weight-gradient tile: M <= 8 output rows (critic output layer M = 1, policy heads M = A), a_mc && b_nc.
+//   C[m, n0+col] = sum_k A[k*lda + m] * B[k*ldb + n0 + col]   (+ bias_out[m] = sum_k A[k*lda + m])
+// Exact fp32 on the SIMT pipes, straight from L2 (no panels, no MMA): thread -> (col = tid % 32, k = tid / 32 + 8 i), 8 k's
+// of loads in flight per thread; the 8 k-groups are summed through shared memory in a fixed order.  A ragged MMA tile
+// for these shapes costs a full tile (5 us); this is ~1.5 us.
+__device__ __noinline__ void gemm_tile_skinny(const GemmOp& og, int tile, float* smem, const AdamOp* ad, const AdamCoef* cf) {
+  const GemmOp o = og;
+  const int tid = threadIdx.x, col = tid & 31, kg = tid >> 5;
+  const int n = tile * 32 + col;
+  const int M = o.M;
+  const bool nv = n < o.N;
+  float acc[8], asum[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) { acc[m] = 0.f; asum[m] = 0.f; }
+  const float* Bp = o.B + n;
+#pragma unroll 1
+  for (int k0 = kg; k0 < o.K; k0 += 64) {
+    float bv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + 8 * u;
+      bv[u] = (k < o.K && nv) ? __ldcg(Bp + (size_t)k * o.ldb) : 0.f;
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      if (m < M) {
+        float av[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = k0 + 8 * u;
+          av[u] = k < o.K ? __ldcg(o.A + (size_t)k * o.lda + m) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { acc[m] = fmaf(av[u], bv[u], acc[m]); asum[m] += av[u]; }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 8; ++m)
+    if (m < M) {
+      smem[(kg * 8 + m) * 32 + col] = acc[m];
+      if (col == 0) smem[2048 + kg * 8 + m] = asum[m];
+    }
+  __syncthreads();
+  {
+    const int m = tid >> 5;                       // thread -> output (m, col)
+    if (m < M && nv) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += smem[(w * 8 + m) * 32 + col];
+      const EpiIn e = epi_load(o, m, n);
+      epi_store(o, m, n, v, e);
+      if (ad) adam_fused_elem(*ad, *cf, gemm_grad_index(o, *ad, m, n), o.accumulate ? v + e.prev : v);
+    }
+    if (o.aug_ones && tile == 0 && tid < M) {     // bias gradient
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += smem[2048 + w * 8 + tid];
+      const EpiIn e = epi_load(o, tid, o.N);
+      epi_store(o, tid, o.N, v, e);
+      if (ad) adam_fused_elem(*ad, *cf, gemm_grad_index(o, *ad, tid, o.N), o.accumulate ? v + e.prev : v);
+    }
+  }
+  __syncthreads();
+}
+ILSW_HD bool gemm_is_skinny(const GemmOp& o) { return o.M <= 8 && o.a_mc && o.b_nc && o.tiles_m == 1; }
+
 
 // ------------------------------------------------------------------------------------------
 // replica exchange: every rank PUSHES its policy gradient into every rank's receive slot over
@@ -555,12 +770,40 @@ struct SmemProgram { const Phase* phases; const Op* ops; const Ctx* ctx; int n_p
 
 __device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
+// one flat Adam(+Polyak) chunk of kAdamChunk elements: ALL loads first, then the arithmetic, then the stores
+__device__ __noinline__ void adam_job(const AdamOp& ao, const AdamCoef& cfs, int j, bool reduced, const Replica& rp, unsigned xseq, int world) {
+  const AdamCoef cf = cfs;
+  const float gscale = (ao.grad_scale_world && world > 1) ? 1.0f / (float)world : 1.0f;
+  const int beg = ao.begin + j * kAdamChunk, end = min(ao.n, beg + kAdamChunk);
+  constexpr int E = kAdamChunk / kThreads;
+  float g[E], m[E], v[E], p[E], tg[E];
+#pragma unroll
+  for (int u = 0; u < E; ++u) {
+    const int i = beg + threadIdx.x + u * kThreads;
+    if (i < end) {
+      g[u] = (reduced ? replica_reduced_grad(rp, xseq, i) : __ldcg(ao.g + i)) * gscale;
+      m[u] = ao.m[i]; v[u] = ao.v[i]; p[u] = ao.p[i];
+      tg[u] = ao.target ? ao.target[i] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < E; ++u) {
+    const int i = beg + threadIdx.x + u * kThreads;
+    if (i < end) adam_math_store(ao, cf, i, g[u], m[u], v[u], p[u], tg[u]);
+  }
+}
+
 template <int CTAS>
 __global__ void __launch_bounds__(kThreads, CTAS)
-ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* bar, Replica rp) {
+ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierState* bar, Replica rp_param) {
   unsigned char* dyn_smem = reinterpret_cast<unsigned char*>(ilsw_dyn_smem_f);
   float* smem = ilsw_dyn_smem_f;
-  __shared__ AdamCoef s_coef;
+  // launch arguments live in shared memory: row kernels take them by reference and the replica tables are indexed
+  // dynamically -- from the parameter bank either would force a per-thread local-memory copy
+  __shared__ RunArgs s_a;
+  __shared__ Replica s_rp;
+  __shared__ AdamCoef s_coefs[kMaxNets];       // this step's Adam coefficients per optimiser slot
+  __shared__ int s_adam_op[kMaxNets];
   __shared__ unsigned s_gen;
   __shared__ double s_p1[kMaxNets], s_p2[kMaxNets], s_b1[kMaxNets], s_b2[kMaxNets];   // running beta^t per Adam slot
   __shared__ int s_pt[kMaxNets];
@@ -579,13 +822,16 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
     src = reinterpret_cast<const int*>(&prog->ctx); dst = reinterpret_cast<int*>(s_ctx); n = (int)(sizeof(Ctx) / 4);
     for (int i = threadIdx.x; i < n; i += kThreads) dst[i] = src[i];
   }
-  if (threadIdx.x == 0) s_gen = 0u;          // the host zeroes the barrier state before every launch
-  if (threadIdx.x < kMaxNets) { s_pt[threadIdx.x] = -1; }
+  if (threadIdx.x == 0) { s_gen = 0u; s_a = a_param; s_rp = rp_param; }   // the host zeroes the barrier state before every launch
+  if (threadIdx.x < kMaxNets) { s_pt[threadIdx.x] = -1; s_adam_op[threadIdx.x] = -1; }
   __syncthreads();
+  const RunArgs& a = s_a;
+  const Replica& rp = s_rp;
   if (threadIdx.x == 0) {   // one pow() per optimiser per LAUNCH; afterwards beta^t is a running product
     for (int i = 0; i < n_ops; ++i)
       if (s_ops[i].kind == OP_ADAM) {
         const AdamOp& ao = s_ops[i].adam;
+        if (s_adam_op[ao.slot] < 0) s_adam_op[ao.slot] = i;
         s_b1[ao.slot] = ao.beta1; s_b2[ao.slot] = ao.beta2; s_pt[ao.slot] = a.t0[ao.slot];
         s_p1[ao.slot] = pow(ao.beta1, (double)a.t0[ao.slot]); s_p2[ao.slot] = pow(ao.beta2, (double)a.t0[ao.slot]);
       }
@@ -604,11 +850,11 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
     if (threadIdx.x < kMaxNets && s_pt[threadIdx.x] >= 0) {
       const int tn = adam_t(a, c.hp, threadIdx.x, s);
       while (s_pt[threadIdx.x] < tn) { s_p1[threadIdx.x] *= s_b1[threadIdx.x]; s_p2[threadIdx.x] *= s_b2[threadIdx.x]; s_pt[threadIdx.x]++; }
+      s_coefs[threadIdx.x] = adam_coef_pw(s_ops[s_adam_op[threadIdx.x]].adam, s_p1[threadIdx.x], s_p2[threadIdx.x], 1);
     }
     __syncthreads();
     for (int ph = 0; ph < n_phases; ++ph) {
       const Phase& P = s_phases[ph];
-      if (blockIdx.x == 0 && threadIdx.x == 0) g_dbg_phase = ph;
       if (!phase_active(P, c.hp, a, s)) { if (stamp) c.phase_ns[ph + 1] = c.phase_ns[ph]; continue; }
       const bool exchange = P.collective && rp.world > 1;
       // exchange sequence number = number of policy updates so far (parity double-buffers the slots)
@@ -619,8 +865,11 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
         while (j >= s_ops[oi].n_jobs) { j -= s_ops[oi].n_jobs; ++oi; }
         const Op& o = s_ops[oi];
         if (o.kind == OP_GEMM) {
-          if (prec == 0) gemm_tile_device(o.gemm, j, smem);
-          else gemm_tile_tc<KC>(o.gemm, j, smem, prec);
+          const AdamOp* ad = o.gemm.adam ? &s_ops[o.gemm.adam - 1].adam : nullptr;
+          const AdamCoef* cf = ad ? &s_coefs[ad->slot] : nullptr;
+          if (gemm_is_skinny(o.gemm)) gemm_tile_skinny(o.gemm, j, smem, ad, cf);
+          else if (prec == 0) gemm_tile_device(o.gemm, j, smem, ad, cf);
+          else gemm_tile_tc<KC>(o.gemm, j, smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, ad, cf);
         } else if (o.kind == OP_ROW) {
           RowEnv env; env.lane = lane; env.nl = 32; env.warp = warp; env.sm = smem;
           const int s_row = s + o.row.arg0;          // arg0 = 1: prefetch job for the next step
@@ -629,38 +878,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
             if (row < o.row.rows) run_row(c, a, o.row.kind, s_row, row, lane, 32);
           }
         } else if (o.kind == OP_ADAM) {
-          __syncthreads();
-          if (threadIdx.x == 0) s_coef = adam_coef_pw(o.adam, s_p1[o.adam.slot], s_p2[o.adam.slot], a.world);
-          __syncthreads();
-          const AdamCoef cf = s_coef;
-          const int beg = j * kAdamChunk, end = min(o.adam.n, beg + kAdamChunk);
-          const bool reduced = exchange && o.adam.grad_scale_world;
-          {  // 8 elements per thread: ALL loads first, then the arithmetic, then the stores
-            constexpr int E = kAdamChunk / kThreads;
-            float g[E], m[E], v[E], p[E], tg[E];
-            const AdamOp& ao = o.adam;
-#pragma unroll
-            for (int u = 0; u < E; ++u) {
-              const int i = beg + threadIdx.x + u * kThreads;
-              if (i < end) {
-                g[u] = (reduced ? replica_reduced_grad(rp, xseq, i) : __ldcg(ao.g + i)) * cf.gscale;
-                m[u] = ao.m[i]; v[u] = ao.v[i]; p[u] = ao.p[i];
-                tg[u] = ao.target ? ao.target[i] : 0.f;
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < E; ++u) {
-              const int i = beg + threadIdx.x + u * kThreads;
-              if (i < end) {
-                float mm = (cf.w1 < 0.5f) ? m[u] + cf.w1 * (g[u] - m[u]) : g[u] - (g[u] - m[u]) * cf.one_m_w1;
-                float vv = v[u] * cf.beta2 + cf.one_m_beta2 * g[u] * g[u];
-                float denom = sqrtf(vv) / cf.bc2_sqrt + cf.eps;
-                float pp = p[u] + cf.neg_step * mm / denom;
-                ao.m[i] = mm; ao.v[i] = vv; ao.p[i] = pp;
-                if (ao.target) ao.target[i] = tg[u] * cf.one_m_tau + pp * cf.tau;
-              }
-            }
-          }
+          adam_job(o.adam, s_coefs[o.adam.slot], j, exchange && o.adam.grad_scale_world, rp, xseq, a.world);
         } else if (o.kind == OP_POLYAK) {
           const int beg = j * kAdamChunk, end = min(o.polyak.n, beg + kAdamChunk);
           constexpr int E = kAdamChunk / kThreads;
@@ -679,6 +897,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a, BarrierState* ba
         }
       }
       if (stamp) c.phase_ns[kMaxPhases + 1 + ph] = globaltimer_ns();
+      if (a.profile && s == a.n_steps - 1 && threadIdx.x == 0 && blockIdx.x < kMaxGrid) c.cta_ns[ph * kMaxGrid + blockIdx.x] = globaltimer_ns();
       if (!grid_barrier(bar, gridDim.x, gen, abort_flag)) return;
       if (stamp) c.phase_ns[ph + 1] = globaltimer_ns();
     }

@@ -198,8 +198,9 @@ ILSW_HD AdamCoef adam_coef(const AdamOp& o, int t, int world) {
   return adam_coef_pw(o, pow(o.beta1, (double)t), pow(o.beta2, (double)t), world);
 }
 
-ILSW_HD void adam_elem_g(const AdamOp& o, const AdamCoef& c, int i, float g) {
-  float m = o.m[i], v = o.v[i], p = o.p[i];
+// one element of torch.optim.Adam (+ the Polyak update of a target network from the NEW parameter) with the
+// state already in registers: shared by the flat Adam jobs and the fused GEMM epilogues (identical arithmetic)
+ILSW_HD void adam_math_store(const AdamOp& o, const AdamCoef& c, int i, float g, float m, float v, float p, float tg) {
   // exp_avg.lerp_(grad, 1-beta1)
   m = (c.w1 < 0.5f) ? m + c.w1 * (g - m) : g - (g - m) * c.one_m_w1;
   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
@@ -209,9 +210,18 @@ ILSW_HD void adam_elem_g(const AdamOp& o, const AdamCoef& c, int i, float g) {
   o.m[i] = m;
   o.v[i] = v;
   o.p[i] = p;
-  if (o.target) o.target[i] = o.target[i] * c.one_m_tau + p * c.tau;
+  if (o.target) o.target[i] = tg * c.one_m_tau + p * c.tau;
+}
+ILSW_HD void adam_elem_g(const AdamOp& o, const AdamCoef& c, int i, float g) {
+  adam_math_store(o, c, i, g, o.m[i], o.v[i], o.p[i], o.target ? o.target[i] : 0.f);
 }
 ILSW_HD void adam_elem(const AdamOp& o, const AdamCoef& c, int i) { adam_elem_g(o, c, i, ldg(o.g + i) * c.gscale); }
+
+// fused optimiser epilogue: element (m,n) of GEMM `o` is gradient element `gi` of the arena described by `ad`
+ILSW_HD int gemm_grad_index(const GemmOp& o, const AdamOp& ad, int m, int n) {
+  if (o.aug_ones && n == o.N) return (int)(o.bias_out - ad.g) + m;
+  return (int)(o.C - ad.g) + m * o.ldc + n;
+}
 
 ILSW_HD void polyak_elem(const PolyakOp& o, int i) {
   float om = (float)(1.0 - (double)o.tau);
@@ -848,8 +858,10 @@ ILSW_HDN void run_row(const Ctx& c, const RunArgs& a, int kind, int s, int r, in
 }
 
 ILSW_HD bool phase_active(const Phase& ph, const Hyper& hp, const RunArgs& a, int s) {
-  if (ph.cond == COND_FIRST_STEP) return s == 0;
-  if (ph.cond == COND_TD3_POLICY) {
+  if ((ph.cond & COND_FIRST_STEP) && s != 0) return false;
+  if ((ph.cond & COND_WORLD_1) && a.world > 1) return false;
+  if ((ph.cond & COND_WORLD_N) && a.world <= 1) return false;
+  if (ph.cond & COND_TD3_POLICY) {
     int per = hp.period > 0 ? hp.period : 1;
     return ((a.step0 + s) % per) == 0;
   }

@@ -72,7 +72,7 @@ struct Builder {
   }
   void gemm(GemmOp g) {
     g.tiles_m = (g.M + 31) / 32;
-    g.tiles_n = (g.N + g.aug_ones + 31) / 32;
+    g.tiles_n = (g.N + 31) / 32;      // the aug (bias-gradient) column is produced by the tn==0 tiles
     Op* o = add(OP_GEMM, g.tiles_m * g.tiles_n);
     if (o) o->gemm = g;
   }
@@ -92,16 +92,29 @@ struct Builder {
     gemm(g);
   }
   // G[Mout,Nin] (+)= D[Kb,Mout]^T X[Kb,Nin] ; gbias[Mout] (+)= colsum(D)   (weight gradient)
+  // adam_op >= 0: index of an adam_desc() op -- the epilogue applies the optimiser step to what it produces
   void dw(const float* D, int ldd, int Mout, const float* X, int ldx, int Nin, int Kb, float* G, float* gbias,
-          int accumulate = 0) {
+          int accumulate = 0, int adam_op = -1) {
     GemmOp g; memset(&g, 0, sizeof(g));
     g.A = D; g.lda = ldd; g.a_mc = 1; g.B = X; g.ldb = ldx; g.b_nc = 1; g.M = Mout; g.N = Nin; g.K = Kb;
     g.C = G; g.ldc = Nin; g.aug_ones = gbias ? 1 : 0; g.bias_out = gbias; g.accumulate = accumulate;
+    g.adam = adam_op >= 0 ? adam_op + 1 : 0;
     gemm(g);
   }
   void row(int kind, int rows, int next_step = 0, int row_offset = 0) {
     Op* o = add(OP_ROW, (rows + kRowsPerJob - 1) / kRowsPerJob);
     if (o) { o->row.kind = kind; o->row.rows = rows + row_offset; o->row.arg0 = next_step; o->row.arg1 = row_offset; }
+  }
+  // descriptor for fused GEMM epilogues (no jobs of its own); returns its op index
+  int adam_desc(const MlpPtrs& n, const MlpPtrs* target, double lr, double b1, double b2, double eps, float tau, int slot) {
+    const int idx = P.n_ops;
+    Op* o = add(OP_ADAM, 0);
+    if (!o) return -1;
+    o->adam.p = n.p; o->adam.g = n.g; o->adam.m = n.m; o->adam.v = n.v;
+    o->adam.target = target ? target->p : nullptr;
+    o->adam.n = n.n_params; o->adam.lr = lr; o->adam.beta1 = b1; o->adam.beta2 = b2; o->adam.eps = eps;
+    o->adam.tau = tau; o->adam.slot = slot; o->adam.grad_scale_world = 0; o->adam.begin = 0; o->adam.fused_only = 1;
+    return idx;
   }
   void adam(const MlpPtrs& n, const MlpPtrs* target, double lr, double b1, double b2, double eps, float tau, int slot,
             int world_scale = 0) {
@@ -264,18 +277,17 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
   b.phase();
   for (int i = 0; i < 2; ++i) b.fwd(S.h0t[i], Hd, B, Hd, c.tqf[i].p + c.tqf[i].oW1, c.tqf[i].p + c.tqf[i].ob1, Hd, S.h1t[i], Hd, ACT_RELU);
   b.phase(); b.row(ROW_SAC_TARGET, B);
-  b.phase();
-  for (int i = 0; i < 2; ++i) {
-    const MlpPtrs& Q = c.qf[i];
-    b.dx(S.d1q[i], Hd, B, Hd, Q.p + Q.oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
-    b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, Q.g + Q.oW1, Q.g + Q.ob1);
-    b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, Q.g + Q.oW2, Q.g + Q.ob2);
+  b.phase();   // backward-data of both critics: one full tile per CTA
+  for (int i = 0; i < 2; ++i)
+    b.dx(S.d1q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
+  b.phase();   // all weight gradients of both critics; Adam + Polyak of the targets fused into the tile epilogues
+  {
+    int ad[2];
+    for (int i = 0; i < 2; ++i) ad[i] = b.adam_desc(c.qf[i], &c.tqf[i], c.hp.qf_lr, b1, b2, eps, c.hp.tau, i == 0 ? SLOT_QF1 : SLOT_QF2);
+    for (int i = 0; i < 2; ++i) b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW1, c.qf[i].g + c.qf[i].ob1, 0, ad[i]);
+    for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0, 0, ad[i]);
+    for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);   // skinny: cheap, last
   }
-  b.phase();
-  for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0);
-  b.phase();
-  b.adam(c.qf[0], &c.tqf[0], c.hp.qf_lr, b1, b2, eps, c.hp.tau, SLOT_QF1);   // Adam + Polyak of the target
-  b.adam(c.qf[1], &c.tqf[1], c.hp.qf_lr, b1, b2, eps, c.hp.tau, SLOT_QF2);
   b.phase();
   for (int i = 0; i < 2; ++i) b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0n[i], Hd, ACT_RELU);
   b.phase();
@@ -286,12 +298,25 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
   b.phase(); b.row(ROW_SAC_PIBWD_DA, B);      // dA = e0 . W0[:, O:O+A] fused into the head backward rows
   b.phase();
   b.dx(S.d1p, Hd, B, Hd, P.p + P.oW1, Hd, Hd, h0p_obs, Hd, ACT_RELU, S.d0p, Hd);
+  // one replica: the policy's Adam step is fused into its weight-gradient tiles
+  b.phase(COND_WORLD_1);
+  {
+    const int ad = b.adam_desc(P, nullptr, c.hp.policy_lr, b1, b2, eps, 0.f, SLOT_POLICY);
+    b.dw(S.d1p, Hd, Hd, h0p_obs, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1, 0, ad);
+    b.dw(S.d0p, Hd, Hd, obs_rows, S.ld_o, O, B, P.g + P.oW0, P.g + P.ob0, 0, ad);
+    b.dw(S.dmean, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2, 0, ad);
+    b.dw(S.dlraw, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW3, P.g + P.ob3, 0, ad);
+  }
+  b.phase(COND_WORLD_1);
+  b.row(ROW_SAC_FINAL, 1);
+  b.row(ROW_SAC_GATHER, B, /*next_step=*/1);
+  // replicas: gradients first, then exchange + Adam of the averaged gradient
+  b.phase(COND_WORLD_N);
   b.dw(S.d1p, Hd, Hd, h0p_obs, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);
+  b.dw(S.d0p, Hd, Hd, obs_rows, S.ld_o, O, B, P.g + P.oW0, P.g + P.ob0);
   b.dw(S.dmean, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2);
   b.dw(S.dlraw, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW3, P.g + P.ob3);
-  b.phase();
-  b.dw(S.d0p, Hd, Hd, obs_rows, S.ld_o, O, B, P.g + P.oW0, P.g + P.ob0);
-  b.phase(COND_ALWAYS, 1);
+  b.phase(COND_WORLD_N, 1);
   b.adam(P, nullptr, c.hp.policy_lr, b1, b2, eps, 0.f, SLOT_POLICY, 1);
   b.row(ROW_SAC_FINAL, 1);
   b.row(ROW_SAC_GATHER, B, /*next_step=*/1);
@@ -318,17 +343,16 @@ inline void build_td3(Builder& b, const Ctx& c) {
   for (int i = 0; i < 2; ++i) b.fwd(S.h0t[i], Hd, B, Hd, c.tqf[i].p + c.tqf[i].oW1, c.tqf[i].p + c.tqf[i].ob1, Hd, S.h1t[i], Hd, ACT_RELU);
   b.phase(); b.row(ROW_TD3_TARGET, B);
   b.phase();
-  for (int i = 0; i < 2; ++i) {
-    const MlpPtrs& Q = c.qf[i];
-    b.dx(S.d1q[i], Hd, B, Hd, Q.p + Q.oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
-    b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, Q.g + Q.oW1, Q.g + Q.ob1);
-    b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, Q.g + Q.oW2, Q.g + Q.ob2);
+  for (int i = 0; i < 2; ++i)
+    b.dx(S.d1q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
+  b.phase();   // weight gradients of both critics with the Adam step fused into the tile epilogues
+  {
+    int ad[2];
+    for (int i = 0; i < 2; ++i) ad[i] = b.adam_desc(c.qf[i], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, i == 0 ? SLOT_QF1 : SLOT_QF2);
+    for (int i = 0; i < 2; ++i) b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW1, c.qf[i].g + c.qf[i].ob1, 0, ad[i]);
+    for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0, 0, ad[i]);
+    for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
   }
-  b.phase();
-  for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0);
-  b.phase();
-  b.adam(c.qf[0], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF1);
-  b.adam(c.qf[1], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF2);
   b.row(ROW_TD3_FINAL, 1);
   // delayed policy + target update (td3.py:113-124), steps with (n_train_steps_total % period)==0
   const int PC = COND_TD3_POLICY;
@@ -342,11 +366,21 @@ inline void build_td3(Builder& b, const Ctx& c) {
   b.phase(PC); b.row(ROW_TD3_PIBWD_DA, B);
   b.phase(PC);
   b.dx(S.d1p, Hd, B, Hd, P.p + P.oW1, Hd, Hd, S.h0p, Hd, ACT_RELU, S.d0p, Hd);
+  b.phase(PC | COND_WORLD_1);
+  {
+    const int ad = b.adam_desc(P, &c.tpolicy, c.hp.policy_lr, b1, b2, eps, c.hp.tau, SLOT_POLICY);
+    b.dw(S.d1p, Hd, Hd, S.h0p, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1, 0, ad);
+    b.dw(S.d0p, Hd, Hd, S.Xoa, S.ld_oa, O, B, P.g + P.oW0, P.g + P.ob0, 0, ad);
+    b.dw(S.dmean, A, A, S.h1p, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2, 0, ad);
+  }
+  b.polyak(c.qf[0], c.tqf[0], c.hp.tau);
+  b.polyak(c.qf[1], c.tqf[1], c.hp.tau);
+  b.row(ROW_TD3_FINAL_POLICY, 1);
+  b.phase(PC | COND_WORLD_N);
   b.dw(S.d1p, Hd, Hd, S.h0p, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);
-  b.dw(S.dmean, A, A, S.h1p, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2);
-  b.phase(PC);
   b.dw(S.d0p, Hd, Hd, S.Xoa, S.ld_oa, O, B, P.g + P.oW0, P.g + P.ob0);
-  b.phase(PC, 1);
+  b.dw(S.dmean, A, A, S.h1p, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2);
+  b.phase(PC | COND_WORLD_N, 1);
   b.adam(P, &c.tpolicy, c.hp.policy_lr, b1, b2, eps, c.hp.tau, SLOT_POLICY, 1);
   b.polyak(c.qf[0], c.tqf[0], c.hp.tau);
   b.polyak(c.qf[1], c.tqf[1], c.hp.tau);
@@ -380,22 +414,25 @@ inline void build_sac_v(Builder& b, const Ctx& c) {
   for (int i = 0; i < 2; ++i) b.fwd(S.h0n[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1n[i], Hd, ACT_RELU);
   b.phase(); b.row(ROW_SACV_TARGET, B);
   b.phase();
-  for (int i = 0; i < 2; ++i) {
-    const MlpPtrs& Q = c.qf[i];
-    b.dx(S.d1q[i], Hd, B, Hd, Q.p + Q.oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
-    b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, Q.g + Q.oW1, Q.g + Q.ob1);
-    b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, Q.g + Q.oW2, Q.g + Q.ob2);
-  }
+  for (int i = 0; i < 2; ++i)
+    b.dx(S.d1q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
   b.dx(S.d1v, Hd, B, Hd, V.p + V.oW1, Hd, Hd, S.h0v, Hd, ACT_RELU, S.d0v, Hd);
-  b.dw(S.d1v, Hd, Hd, S.h0v, Hd, Hd, B, V.g + V.oW1, V.g + V.ob1);
-  b.dw(S.dv, 1, 1, S.h1v, Hd, Hd, B, V.g + V.oW2, V.g + V.ob2);
+  // all three backward passes first, then the three Adam steps (sac.py:132-139): the weight-gradient tiles read
+  // only deltas and activations computed above, so fusing each Adam (+ Polyak of the target V, :242-243) into
+  // their epilogues keeps that order
   b.phase();
-  for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0);
-  b.dw(S.d0v, Hd, Hd, S.Xoa, S.ld_oa, O, B, V.g + V.oW0, V.g + V.ob0);
-  b.phase();   // all three backward passes first, then the three Adam steps (sac.py:132-139)
-  b.adam(c.qf[0], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF1);
-  b.adam(c.qf[1], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF2);
-  b.adam(V, &c.tvf, c.hp.vf_lr, b1, b2, eps, c.hp.tau, SLOT_VF);           // + Polyak of the target V (:242-243)
+  {
+    const int aq0 = b.adam_desc(c.qf[0], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF1);
+    const int aq1 = b.adam_desc(c.qf[1], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF2);
+    const int av = b.adam_desc(V, &c.tvf, c.hp.vf_lr, b1, b2, eps, c.hp.tau, SLOT_VF);
+    const int ad[2] = {aq0, aq1};
+    for (int i = 0; i < 2; ++i) b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW1, c.qf[i].g + c.qf[i].ob1, 0, ad[i]);
+    b.dw(S.d1v, Hd, Hd, S.h0v, Hd, Hd, B, V.g + V.oW1, V.g + V.ob1, 0, av);
+    for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0, 0, ad[i]);
+    b.dw(S.d0v, Hd, Hd, S.Xoa, S.ld_oa, O, B, V.g + V.oW0, V.g + V.ob0, 0, av);
+    for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
+    b.dw(S.dv, 1, 1, S.h1v, Hd, Hd, B, V.g + V.oW2, V.g + V.ob2, 0, av);
+  }
   b.phase();   // policy loss re-evaluates the UPDATED critics on the SAME action sample (:150-153)
   for (int i = 0; i < 2; ++i) b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0n[i], Hd, ACT_RELU);
   b.phase();
@@ -406,12 +443,21 @@ inline void build_sac_v(Builder& b, const Ctx& c) {
   b.phase(); b.row(ROW_SAC_PIBWD_DA, B);
   b.phase();
   b.dx(S.d1p, Hd, B, Hd, P.p + P.oW1, Hd, Hd, h0p_obs, Hd, ACT_RELU, S.d0p, Hd);
+  b.phase(COND_WORLD_1);
+  {
+    const int ad = b.adam_desc(P, nullptr, c.hp.policy_lr, b1, b2, eps, 0.f, SLOT_POLICY);
+    b.dw(S.d1p, Hd, Hd, h0p_obs, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1, 0, ad);
+    b.dw(S.d0p, Hd, Hd, obs_rows, S.ld_o, O, B, P.g + P.oW0, P.g + P.ob0, 0, ad);
+    b.dw(S.dmean, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2, 0, ad);
+    b.dw(S.dlraw, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW3, P.g + P.ob3, 0, ad);
+  }
+  b.row(ROW_SACV_FINAL, 1);
+  b.phase(COND_WORLD_N);
   b.dw(S.d1p, Hd, Hd, h0p_obs, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);
+  b.dw(S.d0p, Hd, Hd, obs_rows, S.ld_o, O, B, P.g + P.oW0, P.g + P.ob0);
   b.dw(S.dmean, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2);
   b.dw(S.dlraw, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW3, P.g + P.ob3);
-  b.phase();
-  b.dw(S.d0p, Hd, Hd, obs_rows, S.ld_o, O, B, P.g + P.oW0, P.g + P.ob0);
-  b.phase(COND_ALWAYS, 1);
+  b.phase(COND_WORLD_N, 1);
   b.adam(P, nullptr, c.hp.policy_lr, b1, b2, eps, 0.f, SLOT_POLICY, 1);
   b.row(ROW_SACV_FINAL, 1);
 }
@@ -495,6 +541,7 @@ inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem) {
   c.stats_floats = stats_floats_for(cfg.algo, B, A);
   c.stats = mem.f(c.stats_floats);
   c.phase_ns = mem.take<unsigned long long>(2 * (kMaxPhases + 1));
+  c.cta_ns = mem.take<unsigned long long>((size_t)kMaxPhases * kMaxGrid);
   alloc_sac_bufs(mem, c.s, cfg.algo, B, O, A, Hd);
   auto grad = [&](const ilsw_mlp& n) { return mem.f(mlp_num_params(n.in_dim, n.hidden, n.out_dim, n.log_std_head)); };
   c.policy = make_mlp(sp.nets[0], grad(sp.nets[0]));
@@ -533,16 +580,19 @@ inline std::string describe_program(const Program& P) {
   static const char* kinds[] = {"?", "GEMM", "ADAM", "ROW", "POLYAK"};
   for (int i = 0; i < P.n_phases; ++i) {
     const Phase& ph = P.phases[i];
-    snprintf(line, sizeof(line), "phase %2d jobs=%4d%s%s:", i, ph.total_jobs, ph.cond ? " [td3-policy-step]" : "",
-             ph.collective ? " [replica-exchange]" : "");
+    snprintf(line, sizeof(line), "phase %2d jobs=%4d%s%s%s%s%s:", i, ph.total_jobs, (ph.cond & COND_TD3_POLICY) ? " [td3-policy-step]" : "",
+             (ph.cond & COND_FIRST_STEP) ? " [first-step]" : "", (ph.cond & COND_WORLD_1) ? " [1-replica]" : "",
+             (ph.cond & COND_WORLD_N) ? " [n-replicas]" : "", ph.collective ? " [replica-exchange]" : "");
     out += line;
     for (int j = 0; j < ph.op_count; ++j) {
       const Op& o = P.ops[ph.op_begin + j];
       if (o.kind == OP_GEMM)
-        snprintf(line, sizeof(line), " GEMM(%dx%dx%d%s%s)", o.gemm.M, o.gemm.N, o.gemm.K, o.gemm.aug_ones ? "+1" : "",
-                 o.gemm.accumulate ? ",acc" : "");
+        snprintf(line, sizeof(line), " GEMM(%dx%dx%d%s%s%s)", o.gemm.M, o.gemm.N, o.gemm.K, o.gemm.aug_ones ? "+1" : "",
+                 o.gemm.accumulate ? ",acc" : "", o.gemm.adam ? ",adam" : "");
       else if (o.kind == OP_ROW)
         snprintf(line, sizeof(line), " ROW(k%d,%d)", o.row.kind, o.row.rows);
+      else if (o.kind == OP_ADAM && o.adam.fused_only)
+        line[0] = 0;
       else if (o.kind == OP_ADAM)
         snprintf(line, sizeof(line), " ADAM(%d%s)", o.adam.n, o.adam.target ? ",polyak" : "");
       else

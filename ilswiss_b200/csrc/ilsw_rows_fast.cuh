@@ -593,12 +593,77 @@ ILSW_HDN void job_disc_reward(const Ctx& c, int job, const RowEnv& e) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// SAC-alpha step epilogue: the 9 batch means are reduced by the 8 warps in parallel (one L2 round trip each
+// instead of 9 in sequence on one warp), then lane 0 of warp 0 does the scalar work (loss log, float64 Adam of
+// log alpha).  Same arithmetic as row_sac_final (ilsw_ops.cuh), which remains the generic fallback.
+// ---------------------------------------------------------------------------------------------
+ILSW_HDN void job_sac_final(const Ctx& c, const RunArgs& a, int s, const RowEnv& e) {
+  const SacBufs& S = c.s;
+  const int B = S.B, A = S.A, lane = e.lane, nl = e.nl;
+#ifdef __CUDA_ARCH__
+  const int nw = 8;
+#else
+  const int nw = 1;                 // host simulator: warps run one after the other -> warp 0 does everything
+  if (e.warp != 0) return;
+#endif
+  const SPtr sc = warp_scratch(e) + (size_t)0;
+  SPtr res; res.p = e.sm + kRowStageFloats; res.off = kRowStageFloats;      // 9 means (scratch of warp 0)
+  (void)sc;
+  for (int v = e.warp; v < 9; v += nw) {
+    const float* x = v == 0 ? S.lossterm[0] : v == 1 ? S.lossterm[1] : v == 2 ? S.plterm : v == 3 ? S.regmu : v == 4 ? S.regls
+                   : v == 5 ? S.aterm : v == 6 ? S.qp[0] : v == 7 ? S.logpi + B : S.y;
+    float acc = 0.f;
+    for (int i0 = lane; i0 < B; i0 += 8 * nl) {
+      float t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int i = i0 + u * nl; t[u] = i < B ? ldg(x + i) : 0.f; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += t[u];
+    }
+    acc = wsum(acc) / (float)B;
+    if (lane == 0) sts(res + v, acc);
+  }
+  cta_sync();
+  if (e.warp == 0) {
+    DynState* d = c.dyn;
+    if (lane == 0) {
+      const float l1 = 0.5f * lds(res + 0), l2 = 0.5f * lds(res + 1);
+      const float rm = lds(res + 3) / (float)A, rl = lds(res + 4) / (float)A;
+      const float pl = lds(res + 2) + (c.hp.mean_reg * rm + c.hp.std_reg * rl);
+      const float am = lds(res + 5);
+      float alpha_loss = 0.f;
+      float* L = c.loss_log + (size_t)(a.loss_log_offset + s) * kLossSlots;
+      L[L_QF1] = l1; L[L_QF2] = l2; L[L_POLICY] = pl;
+      L[L_Q1_MEAN] = lds(res + 6); L[L_LOGPI_MEAN] = lds(res + 7); L[L_QT_MEAN] = lds(res + 8);
+      if (c.hp.train_alpha) {
+        alpha_loss = -((float)d->log_alpha * am);
+        double g = (double)(-am);
+        double b1 = c.hp.beta1, b2 = c.hp.beta2;
+        d->alpha_t += 1;
+        double w = 1.0 - b1;
+        d->alpha_m = (w < 0.5) ? d->alpha_m + w * (g - d->alpha_m) : g - (g - d->alpha_m) * (1.0 - w);
+        d->alpha_v = d->alpha_v * b2 + (1.0 - b2) * g * g;
+        d->alpha_p1 *= b1; d->alpha_p2 *= b2;
+        double bc1 = 1.0 - d->alpha_p1, bc2 = 1.0 - d->alpha_p2;
+        double denom = sqrt(d->alpha_v) / sqrt(bc2) + c.hp.adam_eps;
+        d->log_alpha = d->log_alpha + (-(c.hp.alpha_lr / bc1)) * d->alpha_m / denom;
+        d->alpha = (float)exp(d->log_alpha);
+      }
+      L[L_ALPHA_LOSS] = alpha_loss;
+      L[L_ALPHA] = d->alpha;
+    }
+    if (s == a.stats_step) snapshot_sac(c, lane, nl);
+  }
+  cta_sync();
+}
+
+// ---------------------------------------------------------------------------------------------
 // job-level dispatcher: returns true if a fast implementation handled the job
 // (called by ALL threads of the CTA on the device; by each emulated warp on the host)
 // ---------------------------------------------------------------------------------------------
 ILSW_HD bool run_row_job_fast(const Ctx& c, const RunArgs& a, int kind, int rows, int s, int job, const RowEnv& e) {
-  (void)a; (void)s;
   switch (kind) {
+    case ROW_SAC_FINAL: job_sac_final(c, a, s, e); return true;
     case ROW_SAC_HEADS: job_sac_heads(c, job, e); return true;
     case ROW_SAC_TARGET: job_critic_target(c, job, e, true, 1.0f); return true;
     case ROW_TD3_TARGET: job_critic_target(c, job, e, false, 2.0f); return true;

@@ -21,6 +21,7 @@ namespace ilsw {
 
 constexpr int kMaxPhases = 96;
 constexpr int kMaxOps = 128;
+constexpr int kMaxGrid = 304;     // CTAs of the persistent grid (148 SMs x 2)
 constexpr int kMaxNets = 8;       // Adam step-counter slots
 constexpr int kLossSlots = 16;    // floats per step in the loss log
 constexpr int kThreads = 256;     // CTA size of the engine kernel
@@ -31,8 +32,8 @@ enum OpKind : int { OP_GEMM = 1, OP_ADAM = 2, OP_ROW = 3, OP_POLYAK = 4 };
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 
-// phase conditions
-enum Cond : int { COND_ALWAYS = 0, COND_TD3_POLICY = 1, COND_FIRST_STEP = 2 };
+// phase conditions (bit mask: every set condition must hold)
+enum Cond : int { COND_ALWAYS = 0, COND_TD3_POLICY = 1, COND_FIRST_STEP = 2, COND_WORLD_1 = 4, COND_WORLD_N = 8 };
 
 // loss-log slots (per step)
 enum LossSlot : int {
@@ -46,7 +47,9 @@ struct GemmOp {
   const float* A; int lda; int a_mc;  // a_mc=0: A(m,k)=A[m*lda+k] (k contiguous); 1: A[k*lda+m]
   const float* B; int ldb; int b_nc;  // b_nc=0: B(k,n)=B[n*ldb+k] (k contiguous); 1: B[k*ldb+n]
   int M, N, K;
-  int aug_ones;         // 1: logical extra column n==N with B(k,N)=1, routed to bias_out[m]
+  int aug_ones;         // 1: logical extra column n==N with B(k,N)=1, routed to bias_out[m] (= sum_k A(m,k): the bias
+                        // gradient of a weight-gradient GEMM; requires a_mc).  The device tiles produce it in their
+                        // tn==0 tile from the A panel -- it costs no extra column tile.
   float* C; int ldc;
   float* C2;            // optional second output: value BEFORE the mask (ldc shared)
   float* bias_out;      // aug_ones destination (bias gradient)
@@ -56,6 +59,10 @@ struct GemmOp {
   int mask;             // backward mask: ACT_RELU -> (H>0), ACT_TANH -> (1-H^2)
   int accumulate;       // C += value (and bias_out +=)
   int tiles_m, tiles_n;
+  int adam;             // 0: none; k+1: ops[k] is an OP_ADAM descriptor (fused_only) covering this GEMM's outputs --
+                        // the epilogue applies the Adam (+Polyak) update to every gradient element it produces, so the
+                        // weight-gradient phase needs no separate optimiser phase (valid only without accumulate
+                        // partners and without a cross-replica exchange)
 };
 
 struct AdamOp {
@@ -65,6 +72,8 @@ struct AdamOp {
   double lr, beta1, beta2, eps; float tau;
   int slot;             // Adam step-counter slot
   int grad_scale_world; // 1: divide g by world size (replica-averaged policy gradient)
+  int begin;            // first element of the flat job range [begin, n)
+  int fused_only;       // 1: descriptor for GEMM epilogues (GemmOp::adam); owns no jobs
 };
 
 struct PolyakOp { float* target; const float* src; int n; float tau; };
@@ -171,6 +180,7 @@ struct Ctx {            // everything a row kernel needs
   int stats_floats;
   unsigned long long* phase_ns;  // [2*(kMaxPhases+1)] globaltimer stamps of the LAST step of a launch (profiling):
                                  // [i] = after the barrier of phase i-1; [kMaxPhases+1+i] = CTA 0 finished its jobs of phase i
+  unsigned long long* cta_ns;    // [kMaxPhases x kMaxGrid] (profiling on): every CTA's jobs-done time per phase, last step
 };
 
 struct RingView {       // replay ring as seen by the gather row kernel
@@ -202,6 +212,7 @@ struct RunArgs {
   // replicas
   int world, rank;
   int loss_log_offset;  // first row of loss_log to write
+  int profile;          // 1: CTA 0 stamps the stages of its GEMM tiles (tools/phase_profile.py); 0 in production
 };
 
 struct Program {

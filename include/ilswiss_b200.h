@@ -202,8 +202,13 @@ int ilsw_num_phases(const ilsw_trainer* tr);
 /* profiling: %globaltimer (ns) at the start and after every phase barrier of the LAST step of the
  * most recent launch: out[0..n_phases] */
 int ilsw_read_phase_ns(ilsw_trainer* tr, unsigned long long* host_out, int n, void* stream);
-/* profiling: stage stamps of CTA 0's last tensor-core GEMM tile in every phase: out[96][8] (ns) */
+/* profiling: stage stamps of CTA 0's last tensor-core GEMM tile in every phase: out[96][8] (ns);
+ * only recorded after ilsw_trainer_set_profiling(tr, 1) (off by default: the stamps cost CTA 0 an L2
+ * round trip per tile) */
 int ilsw_read_tile_ns(unsigned long long* host_out);
+int ilsw_trainer_set_profiling(ilsw_trainer* tr, int on);
+/* profiling on: jobs-done time (ns) of every CTA in every phase of the last step: out[96][304] */
+int ilsw_read_cta_ns(ilsw_trainer* tr, unsigned long long* host_out, void* stream);
 int64_t ilsw_kernel_launches(const ilsw_trainer* tr);   /* engine launches so far */
 
 /* A1: sampler-side policy inference for <= 64 env rows (policies.py:245-246, core.py:74-89).

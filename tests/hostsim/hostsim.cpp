@@ -31,6 +31,9 @@ static void run_op(HostSim* hs, const Program& P, const Op& o, const RunArgs& a,
   if (o.kind == OP_GEMM) {
     const GemmOp& g = o.gemm;
     int Nt = g.N + g.aug_ones;
+    const AdamOp* ad = g.adam ? &P.ops[g.adam - 1].adam : nullptr;     // fused optimiser epilogue
+    AdamCoef acf;
+    if (ad) acf = adam_coef(*ad, adam_t(a, c.hp, ad->slot, s), a.world);
     for (int m = 0; m < g.M; ++m)
       for (int n = 0; n < Nt; ++n) {
         float acc = 0.f;
@@ -42,6 +45,10 @@ static void run_op(HostSim* hs, const Program& P, const Op& o, const RunArgs& a,
           acc += x * y;
         }
         gemm_epilogue(g, m, n, acc);
+        if (ad) {
+          const int gi = gemm_grad_index(g, *ad, m, n);
+          adam_elem_g(*ad, acf, gi, ad->g[gi] * acf.gscale);
+        }
       }
   } else if (o.kind == OP_ROW) {
     const bool fast = !hs->generic_rows && fast_rows_ok(c);
@@ -55,8 +62,9 @@ static void run_op(HostSim* hs, const Program& P, const Op& o, const RunArgs& a,
         if (r < o.row.rows) run_row(c, a, o.row.kind, s, r, 0, 1);
       }
   } else if (o.kind == OP_ADAM) {
+    if (o.adam.fused_only) return;                 // applied by the GEMM epilogues that reference it
     AdamCoef cf = adam_coef(o.adam, adam_t(a, c.hp, o.adam.slot, s), a.world);
-    for (int i = 0; i < o.adam.n; ++i) adam_elem(o.adam, cf, i);
+    for (int i = o.adam.begin; i < o.adam.n; ++i) adam_elem(o.adam, cf, i);
   } else if (o.kind == OP_POLYAK) {
     for (int i = 0; i < o.polyak.n; ++i) polyak_elem(o.polyak, i);
   }

@@ -24,6 +24,21 @@ def main():
         w = bench.WORKLOADS[name]
         tr, buf, irl = bench.build_ours(w, seed=1, steps_per_launch=200)
         tr.eval_statistics = {}
+        has_prof = hasattr(tr.engine.lib, "ilsw_trainer_set_profiling")
+        # production timing first (tile stamps off): best of 5 launches of 200 steps
+        best = 1e9
+        for i in range(8):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            bench.run_steps(tr, buf, irl, 200)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                best = min(best, e0.elapsed_time(e1) * 1000 / 200)
+        print("== %s: %.2f us/step production (best of 5 x 200-step launches, tile stamps off)" % (name, best))
+        if has_prof:
+            tr.engine.lib.ilsw_trainer_set_profiling(tr.engine.h, 0 if "--no-tile-stamps" in sys.argv else 1)
         if irl is not None:
             irl.disc_eval_statistics = {}
         for _ in range(3):
@@ -42,13 +57,28 @@ def main():
         tile = np.zeros((96, 8), dtype=np.uint64)
         tr.engine.lib.ilsw_read_tile_ns(tile.ctypes.data_as(C.c_void_p))
         tile = tile.astype(np.int64)
+        cta = np.zeros((96, 304), dtype=np.uint64)
+        grid = 148
+        if hasattr(tr.engine.lib, "ilsw_read_cta_ns"):
+            tr.engine.lib.ilsw_read_cta_ns(tr.engine.h, cta.ctypes.data_as(C.c_void_p), None)
+        cta = cta.astype(np.int64)
+        pn = np.zeros(2 * 97, dtype=np.uint64)
+        tr.engine.lib.ilsw_read_phase_ns(tr.engine.h, pn.ctypes.data_as(C.c_void_p), 2 * 97, None)
+        pn = pn.astype(np.int64)
         for i, (t, j, d) in enumerate(zip(us, tr.engine.last_job_us, desc)):
             if t == 0:
                 continue
             if "GEMM" in d and tile[i, 4] > 0:
                 st = np.diff(tile[i, :5]) / 1000.0
                 d += "   [last tile of cta0: issue %.2f  land %.2f  mma %.2f  epi %.2f us]" % tuple(st)
-            print("  %7.2f us (cta0 jobs %6.2f, barrier+wait %6.2f)  %s" % (t, j, t - j, d))
+            slow = ""
+            if cta[i].max() > 0:
+                done = (cta[i] - pn[i]) / 1000.0
+                done[cta[i] == 0] = 0
+                w = int(done.argmax())
+                srt = np.sort(done[done > 0])
+                slow = " slowest cta %3d %5.2f, median %5.2f |" % (w, done[w], srt[len(srt) // 2])
+            print("  %7.2f us (cta0 jobs %6.2f, barrier+wait %6.2f)%s  %s" % (t, j, t - j, slow, d))
 
 
 if __name__ == "__main__":
