@@ -324,21 +324,35 @@ def main():
     rs = np.random.RandomState(5)
     host_obs, host_act = rs.randn(Ke, O), rs.uniform(-1, 1, (Ke, A))
     host_nobs, host_rew = rs.randn(Ke, O), rs.randn(Ke)
-    sync_all()
-    t0 = time.perf_counter()
-    for i in range(Ke):
-        buf.add_sample(host_obs[i], host_act[i], host_rew[i], False, host_nobs[i])
-        buf.flush()
-        run_steps(tr, buf, irl, 1)
-        tr.engine.losses(1)
-    torch.cuda.synchronize()
-    e2e_dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
+    def e2e_loop(pipelined):
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            buf.add_sample(host_obs[i], host_act[i], host_rew[i], False, host_nobs[i])
+            buf.flush()                          # pinned H2D of this step's transition (side stream)
+            run_steps(tr, buf, irl, 1)           # one fused gradient step (one kernel launch)
+            if pipelined:
+                tr.engine.losses_async(1)        # D2H of this step's losses into a pinned ring, no host sync
+            else:
+                tr.engine.losses(1)              # D2H + host sync every step
+        if pipelined:
+            got = tr.engine.losses_collect()     # one sync; every step's losses are on the host now
+            assert got.shape[0] == Ke and np.isfinite(got[:, :2]).all(), got.shape
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    e2e_sync_dt = e2e_loop(False)
+    e2e_dt = e2e_loop(True)
     e2e = {"value": world * Ke / e2e_dt, "unit": "gradient-steps/s", "h2d_bytes_per_step": buf.ring.host_w * 4,
-           "d2h_bytes_per_step": 16 * 4, "steps": Ke, "mode": "per-step API calls: add_sample+flush (pinned H2D) -> 1-step launch -> loss D2H"}
+           "d2h_bytes_per_step": 16 * 4, "steps": Ke,
+           "mode": "per-step API calls with host buffers: add_sample+flush (pinned H2D, side stream) -> 1-step launch -> "
+                   "loss D2H into a pinned ring (stream-ordered, collected once at the end)",
+           "value_with_host_sync_every_step": world * Ke / e2e_sync_dt}
     # train-call granularity (what _do_training does): burst of `launch` transitions + `launch` steps + loss log D2H
     reps = 3
     burst = dict(observations=rs.randn(launch, O), actions=rs.uniform(-1, 1, (launch, A)), rewards=rs.randn(launch, 1),

@@ -85,6 +85,7 @@ PROTOTYPES = {
                              C.c_uint64, C.c_int, C.c_void_p]),
     "ilsw_read_losses": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ilsw_read_losses_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ilsw_check_abort": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ilsw_stats_floats": (C.c_int, [C.c_void_p]),
     "ilsw_read_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ilsw_get_state": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p]),

@@ -284,6 +284,16 @@ static int trainer_build(ilsw_trainer* tr) {
   mem.base = tr->scratch;
   rc = assemble(tr->host_prog, tr->spec, mem);
   if (rc) return fail(rc, "program assembly failed");
+  // development aid (tools/phase_profile.py): ILSW_DEBUG_DUP_PHASE=k runs phase k twice in a row -- only meaningful for
+  // idempotent phases (forward / row phases); the second run shows the phase's warm-code, warm-data time
+  if (const char* dp = getenv("ILSW_DEBUG_DUP_PHASE")) {
+    Program& P = tr->host_prog;
+    const int k = atoi(dp);
+    if (k >= 0 && k < P.n_phases && P.n_phases < kMaxPhases) {
+      for (int i = P.n_phases; i > k; --i) P.phases[i] = P.phases[i - 1];
+      P.n_phases++;
+    }
+  }
   if (!tr->dev_prog) CU(cudaMalloc(&tr->dev_prog, sizeof(Program)));
   CU(cudaMemcpy(tr->dev_prog, &tr->host_prog, sizeof(Program), cudaMemcpyHostToDevice));
   DynState d;
@@ -437,6 +447,10 @@ extern "C" int ilsw_read_losses_async(ilsw_trainer* tr, float* pinned_out, int n
   CU(cudaMemcpyAsync(pinned_out, tr->host_prog.ctx.loss_log, (size_t)n_steps * kLossSlots * sizeof(float), cudaMemcpyDeviceToHost,
                      (cudaStream_t)stream));
   return ILSW_OK;
+}
+extern "C" int ilsw_check_abort(ilsw_trainer* tr, void* stream) {
+  if (!tr) return fail(ILSW_ERR_ARG, "check_abort: null");
+  return check_abort(tr, (cudaStream_t)stream);
 }
 extern "C" int ilsw_stats_floats(const ilsw_trainer* tr) { return tr ? tr->host_prog.ctx.stats_floats : ILSW_ERR_ARG; }
 extern "C" int ilsw_read_stats(ilsw_trainer* tr, float* host_out, int n_floats, void* stream) {

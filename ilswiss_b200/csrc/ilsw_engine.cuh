@@ -42,12 +42,6 @@ __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
 constexpr long long kSpinLimit = 4000000000LL;  // ~2 s at 2 GHz: a hung peer/CTA aborts the launch
 
 // Sense-reversal grid barrier (all CTAs are co-resident: cooperative launch, 1 CTA / SM).
@@ -337,7 +331,6 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 // every phase (read with ilsw_read_tile_ns): [phase][0..4] = tile start, panels issued, panels landed, MMA
 // done, epilogue done.  `prof_phase` < 0 (the production setting) compiles to one predictable branch per
 // stamp: no global traffic on the critical path of CTA 0.
-__device__ unsigned long long g_tile_ns[kMaxPhases][8];
 #define ILSW_TSTAMP(i) do { if (prof_phase >= 0 && threadIdx.x == 0) g_tile_ns[prof_phase][i] = globaltimer_ns(); } while (0)
 
 // Fragment words of ONE k-step (k8) for the whole 32x32 tile: A = 2 m16 tiles x 4 words, B = 4 n8 tiles
@@ -872,6 +865,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
           else gemm_tile_tc<KC>(o.gemm, j, smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, ad, cf);
         } else if (o.kind == OP_ROW) {
           RowEnv env; env.lane = lane; env.nl = 32; env.warp = warp; env.sm = smem;
+          env.prof = (a.profile && blockIdx.x == 0) ? ph : -1;
           const int s_row = s + o.row.arg0;          // arg0 = 1: prefetch job for the next step
           if (s_row < a.n_steps && !(fast_rows && run_row_job_fast(c, a, o.row.kind, o.row.rows, s_row, j + o.row.arg1 / kRowsPerJob, env))) {
             const int row = o.row.arg1 + j * kRowsPerJob + warp;     // arg1: first row of the job range

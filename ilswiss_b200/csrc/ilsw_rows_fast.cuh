@@ -24,8 +24,24 @@ constexpr int kFastMaxAct = 32;
 constexpr int kRowStageFloats = 2 * kFastMaxAct * kFastMaxHid + 4 * kFastMaxHid;   // staged weights (68 KB + scratch <= the 80 KB GEMM staging area of the 2-CTA/SM variant)
 constexpr int kRowScratchPerWarp = 4 * kFastMaxAct;                                // per-warp exchange area
 
+// profiling (opt-in): thread 0 of CTA 0 stamps the stages of its last row job / GEMM tile of every phase
+#if defined(__CUDACC__)
+__device__ unsigned long long g_tile_ns[kMaxPhases][8];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+#ifdef __CUDA_ARCH__
+#define ILSW_RSTAMP(e, i) do { if ((e).prof >= 0 && threadIdx.x == 0) g_tile_ns[(e).prof][i] = globaltimer_ns(); } while (0)
+#else
+#define ILSW_RSTAMP(e, i) do { } while (0)
+#endif
+
 struct RowEnv {
   int lane, nl, warp;
+  int prof;             // phase index when CTA 0 profiles this job, else -1
   float* sm;            // host simulator: scratch buffer (>= kRowStageFloats + 8*kRowScratchPerWarp floats); device: the
                         // dynamic shared memory base (staging always starts at offset 0)
 };
@@ -61,72 +77,153 @@ ILSW_HD void sts(const SPtr& s, float v) {
 #endif
 }
 
-ILSW_HD void vload(Vec& x, const float* p, int n, int lane, int nl) {
-#pragma unroll
-  for (int i = 0; i < ILSW_VL; ++i) { const int k = lane + i * nl; x.v[i] = k < n ? ldg(p + k) : 0.f; }
+// Element k of a row vector owned by (lane, slot x).  Device: lane owns two groups of 4 CONSECUTIVE floats
+// (k = 128 c + 4 lane + i): every global / shared access of a row is a fully coalesced 128-bit instruction, a
+// quarter of the instructions of the element-strided mapping (the step is bound by the instruction count of the
+// one warp that owns a row).  Needs width % 4 == 0 (fast_rows_ok).  Host simulator: one lane owns the whole vector.
+ILSW_HD int vk(int lane, int x, int nl) {
+#ifdef __CUDA_ARCH__
+  (void)nl;
+  return ((x >> 2) << 7) + (lane << 2) + (x & 3);
+#else
+  return lane + x * nl;
+#endif
 }
-ILSW_HD void vload_plain(Vec& x, const float* p, int n, int lane, int nl) {   // staged (shared) or immutable data
+ILSW_HD void vzero(Vec& x) {
 #pragma unroll
+  for (int i = 0; i < ILSW_VL; ++i) x.v[i] = 0.f;
+}
+ILSW_HD void vload(Vec& x, const float* p, int n, int lane, int nl) {     // data written by other CTAs: through L2
+#ifdef __CUDA_ARCH__
+  (void)nl;
+#pragma unroll
+  for (int c = 0; c < ILSW_VL / 4; ++c) {
+    const int k = (c << 7) + (lane << 2);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < n) v = __ldcg(reinterpret_cast<const float4*>(p + k));
+    x.v[4 * c] = v.x; x.v[4 * c + 1] = v.y; x.v[4 * c + 2] = v.z; x.v[4 * c + 3] = v.w;
+  }
+#else
   for (int i = 0; i < ILSW_VL; ++i) { const int k = lane + i * nl; x.v[i] = k < n ? p[k] : 0.f; }
+#endif
 }
-ILSW_HD float vdot_s(const Vec& h, const SPtr& w, int n, int lane, int nl) {   // w staged/plain
+ILSW_HD void vstore(float* p, const Vec& x, int n, int lane, int nl) {
+#ifdef __CUDA_ARCH__
+  (void)nl;
+#pragma unroll
+  for (int c = 0; c < ILSW_VL / 4; ++c) {
+    const int k = (c << 7) + (lane << 2);
+    if (k < n) *reinterpret_cast<float4*>(p + k) = make_float4(x.v[4 * c], x.v[4 * c + 1], x.v[4 * c + 2], x.v[4 * c + 3]);
+  }
+#else
+  for (int i = 0; i < ILSW_VL; ++i) { const int k = lane + i * nl; if (k < n) p[k] = x.v[i]; }
+#endif
+}
+ILSW_HD void vload_s(Vec& x, const SPtr& w, int n, int lane, int nl) {    // staged (shared) data; offsets are multiples of 4
+#ifdef __CUDA_ARCH__
+  (void)nl;
+#pragma unroll
+  for (int c = 0; c < ILSW_VL / 4; ++c) {
+    const int k = (c << 7) + (lane << 2);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < n) v = *reinterpret_cast<const float4*>(ilsw_dyn_smem_f + w.off + k);
+    x.v[4 * c] = v.x; x.v[4 * c + 1] = v.y; x.v[4 * c + 2] = v.z; x.v[4 * c + 3] = v.w;
+  }
+#else
+  for (int i = 0; i < ILSW_VL; ++i) { const int k = lane + i * nl; x.v[i] = k < n ? w.p[k] : 0.f; }
+#endif
+}
+ILSW_HD float vdot_part(const Vec& a, const Vec& b) {      // this lane's share of <a, b> (padding slots are zero)
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < ILSW_VL; ++i) { const int k = lane + i * nl; if (k < n) s += h.v[i] * lds(w + k); }
-  return wsum(s);
+  for (int i = 0; i < ILSW_VL; ++i) s += a.v[i] * b.v[i];
+  return s;
+}
+ILSW_HD float vdot_s(const Vec& h, const SPtr& w, int n, int lane, int nl) {   // w staged
+  Vec wv;
+  vload_s(wv, w, n, lane, nl);
+  return wsum(vdot_part(h, wv));
 }
 
-// CTA-cooperative staging (device) / passthrough (host).  All threads of the CTA must call.
-ILSW_HD SPtr cta_stage(const RowEnv& e, const float* src, int n, int off) {
-  SPtr r;
-#ifdef __CUDA_ARCH__
-  (void)e;
-  r.p = nullptr; r.off = off;
-  // batches of 4 loads per thread are issued together (a store between two loads would
-  // serialise them into separate L2 round trips), then stored
-  for (int base = 0; base < n; base += 4 * (int)blockDim.x) {
-    float v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const int i = base + u * (int)blockDim.x + (int)threadIdx.x; v[u] = i < n ? __ldcg(src + i) : 0.f; }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const int i = base + u * (int)blockDim.x + (int)threadIdx.x; if (i < n) ilsw_dyn_smem_f[off + i] = v[u]; }
-  }
-#else
-  (void)e; (void)n; (void)off;
-  r.p = src; r.off = 0;
-#endif
-  return r;
+// CTA-cooperative staging of up to N small blocks in ONE batch: all global loads of a thread are issued before its
+// first shared store (one L2 round trip for the whole set; separate loops would serialise them).  Element i of a
+// block comes from src[(i % inner) * s_inner + (i / inner)] (inner == n: a plain copy; the strided form stages
+// W0[:, O:O+A] of a critic transposed).  Device: all threads of the CTA must call.  Host: passthrough pointers
+// (strided blocks are read in place by w0a()).
+struct StageReq { const float* src; int n; int off; int inner; int s_inner; };
+ILSW_HD StageReq stage_plain(const float* src, int n, int off) { StageReq r; r.src = src; r.n = n; r.off = off; r.inner = n > 0 ? n : 1; r.s_inner = 1; return r; }
+// dst[j*Hd + nn] = W0[nn*K0 + O + j]
+ILSW_HD StageReq stage_w0a(const MlpPtrs& Q, int O, int A, int Hd, int off) {
+  StageReq r; r.src = Q.p + Q.oW0 + O; r.n = A * Hd; r.off = off; r.inner = Hd; r.s_inner = O + A; return r;
 }
-// stages W0[:, O:O+A] of a critic TRANSPOSED: dst[j*Hd + n] = W0[n*K0 + O + j]
-ILSW_HD SPtr cta_stage_w0a(const RowEnv& e, const MlpPtrs& Q, int O, int A, int Hd, int off) {
-  SPtr r;
-#ifdef __CUDA_ARCH__
+template <int N, int STRIDED_MASK = 0>      // bit r of STRIDED_MASK: request r uses the strided source form
+ILSW_HD void cta_stage_multi(const RowEnv& e, const StageReq (&rq)[N], SPtr (&out)[N]) {
   (void)e;
-  r.p = nullptr; r.off = off;
-  const int K0 = O + A, n = A * Hd;
-  for (int base = 0; base < n; base += 4 * (int)blockDim.x) {
-    float v[4];
+#ifdef __CUDA_ARCH__
+  constexpr int U = 8, T = kThreads;          // first pass: up to U elements per thread and request, all in flight together
+  const int tid = (int)threadIdx.x;
+  float v[N][U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = base + u * (int)blockDim.x + (int)threadIdx.x;      // i = j*Hd + nn
-      v[u] = i < n ? __ldcg(Q.p + Q.oW0 + (size_t)(i % Hd) * K0 + O + i / Hd) : 0.f;
+  for (int r = 0; r < N; ++r) {
+    out[r].p = nullptr; out[r].off = rq[r].off;
+    const float* src = rq[r].src;
+    const int n = rq[r].n;
+    if ((STRIDED_MASK >> r) & 1) {
+      const int inner = rq[r].inner, si = rq[r].s_inner;
+      int j = tid / inner, nn = tid - j * inner;
+      const int dj = T / inner, dn = T - dj * inner;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u * T < n) {          // warp-uniform: dead batches cost one branch
+          v[r][u] = (tid + u * T < n) ? __ldcg(src + (size_t)nn * si + j) : 0.f;
+          nn += dn; j += dj;
+          if (nn >= inner) { nn -= inner; ++j; }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (u * T < n) v[r][u] = (tid + u * T < n) ? __ldcg(src + tid + u * T) : 0.f;
     }
+  }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int i = base + u * (int)blockDim.x + (int)threadIdx.x; if (i < n) ilsw_dyn_smem_f[off + i] = v[u]; }
+  for (int r = 0; r < N; ++r) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u * T < rq[r].n && tid + u * T < rq[r].n) ilsw_dyn_smem_f[rq[r].off + tid + u * T] = v[r][u];
+  }
+  // blocks larger than U*T elements (wide action spaces): the rest in plain loops
+#pragma unroll
+  for (int r = 0; r < N; ++r) {
+    for (int i = U * T + tid; i < rq[r].n; i += T) {
+      const int inner = rq[r].inner;
+      const size_t idx = ((STRIDED_MASK >> r) & 1) ? (size_t)(i % inner) * rq[r].s_inner + i / inner : (size_t)i;
+      ilsw_dyn_smem_f[rq[r].off + i] = __ldcg(rq[r].src + idx);
+    }
   }
 #else
-  (void)e; (void)Q; (void)O; (void)A; (void)Hd; (void)off;
-  r.p = nullptr; r.off = 0;   // host: read the strided weights directly (see w0a())
+  for (int r = 0; r < N; ++r) { out[r].p = ((STRIDED_MASK >> r) & 1) ? nullptr : rq[r].src; out[r].off = 0; }
 #endif
-  return r;
 }
-ILSW_HD float w0a(const SPtr& staged, const MlpPtrs& Q, int O, int A, int Hd, int j, int n) {
+// single-block convenience form
+ILSW_HD SPtr cta_stage(const RowEnv& e, const float* src, int n, int off) {
+  StageReq rq[1] = {stage_plain(src, n, off)};
+  SPtr out[1];
+  cta_stage_multi(e, rq, out);
+  return out[0];
+}
+// this lane's share of sum_n e0[n] * W0[n, O+j]  (staged transposed on the device, read in place on the host)
+ILSW_HD float vdot_w0a_part(const Vec& e0, const SPtr& staged, const MlpPtrs& Q, int O, int A, int Hd, int j, int lane, int nl) {
 #ifdef __CUDA_ARCH__
   (void)Q; (void)O; (void)A;
-  return ilsw_dyn_smem_f[staged.off + j * Hd + n];
+  Vec wv;
+  vload_s(wv, staged + (size_t)j * Hd, Hd, lane, nl);
+  return vdot_part(e0, wv);
 #else
-  (void)staged; (void)Hd;
-  return Q.p[Q.oW0 + (size_t)n * (O + A) + O + j];
+  (void)staged;
+  float s = 0.f;
+  for (int x = 0; x < ILSW_VL; ++x) { const int n = lane + x * nl; if (n < Hd) s += e0.v[x] * Q.p[Q.oW0 + (size_t)n * (O + A) + O + j]; }
+  return s;
 #endif
 }
 ILSW_HD void cta_sync() {
@@ -142,9 +239,17 @@ ILSW_HD SPtr warp_scratch(const RowEnv& e) {
 }
 
 ILSW_HD bool fast_rows_ok(const Ctx& c) {
-  return c.s.Hd <= kFastMaxHid && c.s.A <= kFastMaxAct && 4 * c.s.A * c.s.Hd <= kRowStageFloats &&
-         (!c.hp.has_disc || c.d.Hd <= kFastMaxHid);
+  return c.s.Hd <= kFastMaxHid && (c.s.Hd & 3) == 0 && c.s.A <= kFastMaxAct && 4 * c.s.A * c.s.Hd <= kRowStageFloats &&
+         (!c.hp.has_disc || (c.d.Hd <= kFastMaxHid && (c.d.Hd & 3) == 0));
 }
+
+// per-lane slots of a per-action (A-wide) vector: the device handles A <= 32 with one slot per lane, the host
+// simulator's single lane owns all of them
+#ifdef __CUDA_ARCH__
+#define ILSW_AL 1
+#else
+#define ILSW_AL kFastMaxAct
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // SAC policy heads (N2) on 2B rows
@@ -153,14 +258,21 @@ ILSW_HDN void job_sac_heads(const Ctx& c, int job, const RowEnv& e) {
   const SacBufs& S = c.s;
   const MlpPtrs& P = c.policy;
   const int A = S.A, Hd = S.Hd, B = S.B, O = S.O, lane = e.lane, nl = e.nl;
-  const SPtr Wm = cta_stage(e, P.p + P.oW2, A * Hd, 0);
-  const SPtr Ws = cta_stage(e, P.p + P.oW3, A * Hd, A * Hd);
-  const SPtr bm = cta_stage(e, P.p + P.ob2, A, 2 * A * Hd);
-  const SPtr bs = cta_stage(e, P.p + P.ob3, A, 2 * A * Hd + A);
+  ILSW_RSTAMP(e, 0);
   const int r = job * kRowsPerJob + e.warp;
   Vec h;
-  if (r < 2 * B) vload(h, S.h1p + (size_t)r * Hd, Hd, lane, nl);
+  float ep[ILSW_AL];
+  if (r < 2 * B) {
+    vload(h, S.h1p + (size_t)r * Hd, Hd, lane, nl);
+    for (int j = lane, q = 0; j < A; j += nl, ++q) ep[q] = ldg(S.eps + (size_t)r * A + j);
+  }
+  const StageReq rq[4] = {stage_plain(P.p + P.oW2, A * Hd, 0), stage_plain(P.p + P.oW3, A * Hd, A * Hd),
+                          stage_plain(P.p + P.ob2, A, 2 * A * Hd), stage_plain(P.p + P.ob3, A, 2 * A * Hd + A)};
+  SPtr sp[4];
+  cta_stage_multi(e, rq, sp);
+  const SPtr Wm = sp[0], Ws = sp[1], bm = sp[2], bs = sp[3];
   cta_sync();
+  ILSW_RSTAMP(e, 1);
   if (r < 2 * B) {
     const SPtr sc = warp_scratch(e);
 #pragma unroll 1
@@ -170,12 +282,13 @@ ILSW_HDN void job_sac_heads(const Ctx& c, int job, const RowEnv& e) {
       if (lane == 0) { sts(sc + j, mu); sts(sc + A + j, lr); }
     }
     wsync();
+    ILSW_RSTAMP(e, 2);
     float s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    for (int j = lane; j < A; j += nl) {
+    for (int j = lane, q = 0; j < A; j += nl, ++q) {
       const float mu = lds(sc + j), lraw = lds(sc + A + j);
       const float ls = fminf(fmaxf(lraw, -20.0f), 2.0f);
       const float sig = expf(ls), cov = expf(2.0f * ls);
-      const float z = ldg(S.eps + (size_t)r * A + j) * sig + mu;
+      const float z = ep[q] * sig + mu;
       const float t = tanhf(z);
       const float d = mu - z;
       s1 += d * d / cov; s2 += ls; s3 += logf(1.0f - t * t + 1e-6f);
@@ -192,6 +305,7 @@ ILSW_HDN void job_sac_heads(const Ctx& c, int job, const RowEnv& e) {
       S.logpi[r] = lp;
     }
   }
+  ILSW_RSTAMP(e, 3);
   cta_sync();
 }
 
@@ -201,15 +315,12 @@ ILSW_HDN void job_sac_heads(const Ctx& c, int job, const RowEnv& e) {
 ILSW_HDN void job_critic_target(const Ctx& c, int job, const RowEnv& e, bool use_entropy, float loss_grad_factor) {
   const SacBufs& S = c.s;
   const int Hd = S.Hd, lane = e.lane, nl = e.nl;
-  SPtr tw[2], qw[2];
-  for (int i = 0; i < 2; ++i) {
-    tw[i] = cta_stage(e, c.tqf[i].p + c.tqf[i].oW2, Hd, i * Hd);
-    qw[i] = cta_stage(e, c.qf[i].p + c.qf[i].oW2, Hd, (2 + i) * Hd);
-  }
+  ILSW_RSTAMP(e, 0);
   const int b = job * kRowsPerJob + e.warp;
   Vec ht[2], hq[2];
   float rew = 0.f, term = 0.f, lp = 0.f, alpha = 0.f, tb[2] = {0.f, 0.f}, qb[2] = {0.f, 0.f};
   if (b < S.B) {
+#pragma unroll
     for (int i = 0; i < 2; ++i) {
       vload(ht[i], S.h1t[i] + (size_t)b * Hd, Hd, lane, nl);
       vload(hq[i], S.h1q[i] + (size_t)b * Hd, Hd, lane, nl);
@@ -219,29 +330,35 @@ ILSW_HDN void job_critic_target(const Ctx& c, int job, const RowEnv& e, bool use
     rew = ldg(S.rew + b); term = ldg(S.term + b);
     if (use_entropy) { lp = ldg(S.logpi + b); alpha = ldg(&c.dyn->alpha); }
   }
+  const StageReq rq[4] = {stage_plain(c.tqf[0].p + c.tqf[0].oW2, Hd, 0), stage_plain(c.tqf[1].p + c.tqf[1].oW2, Hd, Hd),
+                          stage_plain(c.qf[0].p + c.qf[0].oW2, Hd, 2 * Hd), stage_plain(c.qf[1].p + c.qf[1].oW2, Hd, 3 * Hd)};
+  SPtr sp[4];
+  cta_stage_multi(e, rq, sp);
   cta_sync();
+  ILSW_RSTAMP(e, 1);
   if (b < S.B) {
-    const float tq0 = vdot_s(ht[0], tw[0], Hd, lane, nl) + tb[0];
-    const float tq1 = vdot_s(ht[1], tw[1], Hd, lane, nl) + tb[1];
+    const float tq0 = vdot_s(ht[0], sp[0], Hd, lane, nl) + tb[0];
+    const float tq1 = vdot_s(ht[1], sp[1], Hd, lane, nl) + tb[1];
     const float tmin = fminf(tq0, tq1);
     const float rs = c.hp.reward_scale * rew;
     const float inner = use_entropy ? tmin - alpha * lp : tmin;
     const float y = rs + (1.0f - term) * c.hp.discount * inner;
     const float invB = 1.0f / (float)S.B;
+#pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const float q = vdot_s(hq[i], qw[i], Hd, lane, nl) + qb[i];
+      Vec w;
+      vload_s(w, sp[2 + i], Hd, lane, nl);
+      const float q = wsum(vdot_part(hq[i], w)) + qb[i];
       const float diff = q - y;
       const float dq = loss_grad_factor * diff * invB;
       if (lane == 0) { S.qp[i][b] = q; S.dq[i][b] = dq; S.lossterm[i][b] = diff * diff; }
-      float* d1 = S.d1q[i] + (size_t)b * Hd;
 #pragma unroll
-      for (int x = 0; x < ILSW_VL; ++x) {
-        const int k = lane + x * nl;
-        if (k < Hd) d1[k] = hq[i].v[x] > 0.f ? dq * lds(qw[i] + k) : 0.f;
-      }
+      for (int x = 0; x < ILSW_VL; ++x) w.v[x] = hq[i].v[x] > 0.f ? dq * w.v[x] : 0.f;
+      vstore(S.d1q[i] + (size_t)b * Hd, w, Hd, lane, nl);
     }
     if (lane == 0) { S.tq[0][b] = tq0; S.tq[1][b] = tq1; S.y[b] = y; }
   }
+  ILSW_RSTAMP(e, 2);
   cta_sync();
 }
 
@@ -251,12 +368,12 @@ ILSW_HDN void job_critic_target(const Ctx& c, int job, const RowEnv& e, bool use
 ILSW_HDN void job_sac_ploss(const Ctx& c, int job, const RowEnv& e) {
   const SacBufs& S = c.s;
   const int Hd = S.Hd, A = S.A, B = S.B, lane = e.lane, nl = e.nl;
-  SPtr qw[2];
-  for (int i = 0; i < 2; ++i) qw[i] = cta_stage(e, c.qf[i].p + c.qf[i].oW2, Hd, i * Hd);
+  ILSW_RSTAMP(e, 0);
   const int b = job * kRowsPerJob + e.warp;
   Vec h[2];
   float qb[2] = {0.f, 0.f}, lp = 0.f, alpha = 0.f, smu = 0.f, sls = 0.f;
   if (b < B) {
+#pragma unroll
     for (int i = 0; i < 2; ++i) { vload(h[i], S.h1n[i] + (size_t)b * Hd, Hd, lane, nl); qb[i] = ldg(c.qf[i].p + c.qf[i].ob2); }
     lp = ldg(S.logpi + B + b); alpha = ldg(&c.dyn->alpha);
     for (int j = lane; j < A; j += nl) {
@@ -264,10 +381,16 @@ ILSW_HDN void job_sac_ploss(const Ctx& c, int job, const RowEnv& e) {
       smu += mu * mu; sls += ls * ls;
     }
   }
+  const StageReq rq[2] = {stage_plain(c.qf[0].p + c.qf[0].oW2, Hd, 0), stage_plain(c.qf[1].p + c.qf[1].oW2, Hd, Hd)};
+  SPtr qw[2];
+  cta_stage_multi(e, rq, qw);
   cta_sync();
+  ILSW_RSTAMP(e, 1);
   if (b < B) {
+    Vec w[2];
     float q[2];
-    for (int i = 0; i < 2; ++i) q[i] = vdot_s(h[i], qw[i], Hd, lane, nl) + qb[i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { vload_s(w[i], qw[i], Hd, lane, nl); q[i] = wsum(vdot_part(h[i], w[i])) + qb[i]; }
     smu = wsum(smu); sls = wsum(sls);
     const float invB = 1.0f / (float)B;
     const float w0 = q[0] < q[1] ? 1.f : (q[0] == q[1] ? 0.5f : 0.f);
@@ -277,16 +400,15 @@ ILSW_HDN void job_sac_ploss(const Ctx& c, int job, const RowEnv& e) {
       S.plterm[b] = alpha * lp - fminf(q[0], q[1]);
       S.regmu[b] = smu; S.regls[b] = sls;
     }
+#pragma unroll
     for (int i = 0; i < 2; ++i) {
       const float dq = -invB * wq[i];
-      float* e1 = S.e1[i] + (size_t)b * Hd;
 #pragma unroll
-      for (int x = 0; x < ILSW_VL; ++x) {
-        const int k = lane + x * nl;
-        if (k < Hd) e1[k] = h[i].v[x] > 0.f ? dq * lds(qw[i] + k) : 0.f;
-      }
+      for (int x = 0; x < ILSW_VL; ++x) w[i].v[x] = h[i].v[x] > 0.f ? dq * w[i].v[x] : 0.f;
+      vstore(S.e1[i] + (size_t)b * Hd, w[i], Hd, lane, nl);
     }
   }
+  ILSW_RSTAMP(e, 2);
   cta_sync();
 }
 
@@ -297,70 +419,81 @@ ILSW_HDN void job_sac_pibwd(const Ctx& c, int job, const RowEnv& e, bool with_da
   const SacBufs& S = c.s;
   const MlpPtrs& P = c.policy;
   const int Hd = S.Hd, A = S.A, B = S.B, lane = e.lane, nl = e.nl;
-  const SPtr Wm = cta_stage(e, P.p + P.oW2, A * Hd, 0);
-  const SPtr Ws = cta_stage(e, P.p + P.oW3, A * Hd, A * Hd);
-  SPtr Wa[2] = {sptr_null(), sptr_null()};
-  if (with_da) for (int i = 0; i < 2; ++i) Wa[i] = cta_stage_w0a(e, c.qf[i], S.O, A, Hd, (2 + i) * A * Hd);
+  ILSW_RSTAMP(e, 0);
   const int b = job * kRowsPerJob + e.warp;
   const int r = B + b;
-  Vec h;
+  // every global load of the row first (one L2 round trip), then the staging batch
+  Vec h, e0[2];
+  float alpha = 0.f, lpi = 0.f;
+  float t_[ILSW_AL], mu_[ILSW_AL], ls_[ILSW_AL], lr_[ILSW_AL], ep_[ILSW_AL], ga_[ILSW_AL];
+  if (b < B) {
+    if (with_da) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) vload(e0[i], S.e0[i] + (size_t)b * Hd, Hd, lane, nl);
+    }
+    vload(h, S.h1p + (size_t)r * Hd, Hd, lane, nl);
+    alpha = ldg(&c.dyn->alpha);
+    lpi = ldg(S.logpi + r);
+    for (int j = lane, q = 0; j < A; j += nl, ++q) {
+      t_[q] = ldg(S.act + (size_t)r * A + j);
+      mu_[q] = ldg(S.mean + (size_t)r * A + j); ls_[q] = ldg(S.lstd + (size_t)r * A + j); lr_[q] = ldg(S.lraw + (size_t)r * A + j);
+      ep_[q] = ldg(S.eps + (size_t)r * A + j);
+      ga_[q] = with_da ? 0.f : ldg(S.dA[0] + (size_t)b * A + j) + ldg(S.dA[1] + (size_t)b * A + j);
+    }
+  }
+  const StageReq rq[4] = {stage_plain(P.p + P.oW2, A * Hd, 0), stage_plain(P.p + P.oW3, A * Hd, A * Hd),
+                          with_da ? stage_w0a(c.qf[0], S.O, A, Hd, 2 * A * Hd) : stage_plain(nullptr, 0, 0),
+                          with_da ? stage_w0a(c.qf[1], S.O, A, Hd, 3 * A * Hd) : stage_plain(nullptr, 0, 0)};
+  SPtr sp[4];
+  cta_stage_multi<4, 0xC>(e, rq, sp);
+  const SPtr Wm = sp[0], Ws = sp[1];
   const SPtr sc = warp_scratch(e);
-  float lpi = 0.f;
-  if (with_da) {
-    // dA[b,j] = sum_n e0_i[b,n] * W0_i[n, O+j], both critics (formerly a GEMM phase of its own)
-    Vec e0[2];
-    if (b < B) for (int i = 0; i < 2; ++i) vload(e0[i], S.e0[i] + (size_t)b * Hd, Hd, lane, nl);
-    cta_sync();
-    if (b < B) {
+  cta_sync();
+  ILSW_RSTAMP(e, 1);
+  if (b < B) {
+    if (with_da) {
+      // dA[b,j] = sum_n e0_i[b,n] * W0_i[n, O+j], both critics (formerly a GEMM phase of its own)
 #pragma unroll 1
       for (int j = 0; j < A; ++j) {
-        float acc = 0.f;
-#pragma unroll
-        for (int x = 0; x < ILSW_VL; ++x) {
-          const int n = lane + x * nl;
-          if (n < Hd) acc += e0[0].v[x] * w0a(Wa[0], c.qf[0], S.O, A, Hd, j, n) + e0[1].v[x] * w0a(Wa[1], c.qf[1], S.O, A, Hd, j, n);
-        }
-        acc = wsum(acc);
+        const float acc = wsum(vdot_w0a_part(e0[0], sp[2], c.qf[0], S.O, A, Hd, j, lane, nl) +
+                               vdot_w0a_part(e0[1], sp[3], c.qf[1], S.O, A, Hd, j, lane, nl));
         if (lane == 0) sts(sc + 2 * A + j, acc);
       }
+      wsync();
     }
-    wsync();
-  }
-  if (b < B) {
-    vload(h, S.h1p + (size_t)r * Hd, Hd, lane, nl);
-    const float alpha = ldg(&c.dyn->alpha);
-    lpi = ldg(S.logpi + r);
+    ILSW_RSTAMP(e, 2);
     const float invB = 1.0f / (float)B, invBA = 1.0f / (float)(B * A);
-    for (int j = lane; j < A; j += nl) {
-      const float gA = with_da ? lds(sc + 2 * A + j) : ldg(S.dA[0] + (size_t)b * A + j) + ldg(S.dA[1] + (size_t)b * A + j);
-      const float t = ldg(S.act + (size_t)r * A + j);
-      const float mu = ldg(S.mean + (size_t)r * A + j), ls = ldg(S.lstd + (size_t)r * A + j), lr = ldg(S.lraw + (size_t)r * A + j);
-      const float ep = ldg(S.eps + (size_t)r * A + j);
+    for (int j = lane, q = 0; j < A; j += nl, ++q) {
+      const float gA = with_da ? lds(sc + 2 * A + j) : ga_[q];
+      const float t = t_[q], mu = mu_[q], ls = ls_[q], lr = lr_[q];
       const float om = 1.0f - t * t;
       const float J = 2.0f * t * om / (om + 1e-6f);
       const float dz = gA * om + alpha * invB * J;
       const float dmu = dz + 2.0f * c.hp.mean_reg * mu * invBA;
-      const float dl = dz * ep * expf(ls) - alpha * invB + 2.0f * c.hp.std_reg * ls * invBA;
+      const float dl = dz * ep_[q] * expf(ls) - alpha * invB + 2.0f * c.hp.std_reg * ls * invBA;
       const float dlr = (lr >= -20.0f && lr <= 2.0f) ? dl : 0.f;
       sts(sc + j, dmu); sts(sc + A + j, dlr);
+      S.dmean[(size_t)b * A + j] = dmu; S.dlraw[(size_t)b * A + j] = dlr;
     }
-  }
-  cta_sync();   // staged heads visible; also orders the scratch writes inside each warp
-  if (b < B) {
-    for (int j = lane; j < A; j += nl) { S.dmean[(size_t)b * A + j] = lds(sc + j); S.dlraw[(size_t)b * A + j] = lds(sc + A + j); }
-    float* d1 = S.d1p + (size_t)b * Hd;
-#pragma unroll
-    for (int x = 0; x < ILSW_VL; ++x) {
-      const int k = lane + x * nl;
-      if (k < Hd) {
-        float acc = 0.f;
+    wsync();
+    ILSW_RSTAMP(e, 3);
+    Vec acc;
+    vzero(acc);
 #pragma unroll 1
-        for (int j = 0; j < A; ++j) acc += lds(sc + j) * lds(Wm + (size_t)j * Hd + k) + lds(sc + A + j) * lds(Ws + (size_t)j * Hd + k);
-        d1[k] = h.v[x] > 0.f ? acc : 0.f;
-      }
+    for (int j = 0; j < A; ++j) {
+      const float dm = lds(sc + j), dl = lds(sc + A + j);
+      Vec wm, ws;
+      vload_s(wm, Wm + (size_t)j * Hd, Hd, lane, nl);
+      vload_s(ws, Ws + (size_t)j * Hd, Hd, lane, nl);
+#pragma unroll
+      for (int x = 0; x < ILSW_VL; ++x) acc.v[x] += dm * wm.v[x] + dl * ws.v[x];
     }
+#pragma unroll
+    for (int x = 0; x < ILSW_VL; ++x) acc.v[x] = h.v[x] > 0.f ? acc.v[x] : 0.f;
+    vstore(S.d1p + (size_t)b * Hd, acc, Hd, lane, nl);
     if (lane == 0) S.aterm[b] = lpi + c.hp.target_entropy;
   }
+  ILSW_RSTAMP(e, 4);
   cta_sync();
 }
 
@@ -371,23 +504,30 @@ ILSW_HDN void job_td3_head(const Ctx& c, int job, const RowEnv& e, bool target) 
   const SacBufs& S = c.s;
   const MlpPtrs& P = target ? c.tpolicy : c.policy;
   const int A = S.A, Hd = S.Hd, O = S.O, lane = e.lane, nl = e.nl;
-  const SPtr W = cta_stage(e, P.p + P.oW2, A * Hd, 0);
-  const SPtr bb = cta_stage(e, P.p + P.ob2, A, A * Hd);
   const int b = job * kRowsPerJob + e.warp;
   Vec h;
-  if (b < S.B) vload(h, (target ? S.h1tp : S.h1p) + (size_t)b * Hd, Hd, lane, nl);
+  float nz_[ILSW_AL];
+  if (b < S.B) {
+    vload(h, (target ? S.h1tp : S.h1p) + (size_t)b * Hd, Hd, lane, nl);
+    if (target) for (int j = lane, q = 0; j < A; j += nl, ++q) nz_[q] = ldg(S.noise + (size_t)b * A + j);
+  }
+  const StageReq rq[2] = {stage_plain(P.p + P.oW2, A * Hd, 0), stage_plain(P.p + P.ob2, A, A * Hd)};
+  SPtr sp[2];
+  cta_stage_multi(e, rq, sp);
+  const SPtr W = sp[0], bb = sp[1];
   cta_sync();
   if (b < S.B) {
     const SPtr sc = warp_scratch(e);
+#pragma unroll 1
     for (int j = 0; j < A; ++j) {
       const float pre = vdot_s(h, W + (size_t)j * Hd, Hd, lane, nl) + lds(bb + j);
       if (lane == 0) sts(sc + j, pre);
     }
     wsync();
-    for (int j = lane; j < A; j += nl) {
+    for (int j = lane, q = 0; j < A; j += nl, ++q) {
       const float t = tanhf(lds(sc + j));
       if (target) {
-        float nz = c.hp.policy_noise * ldg(S.noise + (size_t)b * A + j);
+        float nz = c.hp.policy_noise * nz_[q];
         nz = fminf(fmaxf(nz, -c.hp.noise_clip), c.hp.noise_clip);
         S.Xna[(size_t)b * S.ld_oa + O + j] = c.hp.max_act * t + nz;
       } else {
@@ -403,22 +543,21 @@ ILSW_HDN void job_td3_ploss(const Ctx& c, int job, const RowEnv& e) {
   const SacBufs& S = c.s;
   const MlpPtrs& Q = c.qf[0];
   const int Hd = S.Hd, lane = e.lane, nl = e.nl;
-  const SPtr qw = cta_stage(e, Q.p + Q.oW2, Hd, 0);
   const int b = job * kRowsPerJob + e.warp;
   Vec h;
   float qb = 0.f;
   if (b < S.B) { vload(h, S.h1n[0] + (size_t)b * Hd, Hd, lane, nl); qb = ldg(Q.p + Q.ob2); }
+  const SPtr qw = cta_stage(e, Q.p + Q.oW2, Hd, 0);
   cta_sync();
   if (b < S.B) {
-    const float q = vdot_s(h, qw, Hd, lane, nl) + qb;
+    Vec w;
+    vload_s(w, qw, Hd, lane, nl);
+    const float q = wsum(vdot_part(h, w)) + qb;
     const float dq = -1.0f / (float)S.B;
     if (lane == 0) { S.qn[0][b] = q; S.plterm[b] = -q; }
-    float* e1 = S.e1[0] + (size_t)b * Hd;
 #pragma unroll
-    for (int x = 0; x < ILSW_VL; ++x) {
-      const int k = lane + x * nl;
-      if (k < Hd) e1[k] = h.v[x] > 0.f ? dq * lds(qw + k) : 0.f;
-    }
+    for (int x = 0; x < ILSW_VL; ++x) w.v[x] = h.v[x] > 0.f ? dq * w.v[x] : 0.f;
+    vstore(S.e1[0] + (size_t)b * Hd, w, Hd, lane, nl);
   }
   cta_sync();
 }
@@ -427,53 +566,54 @@ ILSW_HDN void job_td3_pibwd(const Ctx& c, int job, const RowEnv& e, bool with_da
   const SacBufs& S = c.s;
   const MlpPtrs& P = c.policy;
   const int Hd = S.Hd, A = S.A, lane = e.lane, nl = e.nl;
-  const SPtr W = cta_stage(e, P.p + P.oW2, A * Hd, 0);
-  SPtr Wa = sptr_null();
-  if (with_da) Wa = cta_stage_w0a(e, c.qf[0], S.O, A, Hd, A * Hd);
   const int b = job * kRowsPerJob + e.warp;
-  Vec h;
-  const SPtr sc = warp_scratch(e);
-  if (with_da) {
-    Vec e0;
-    if (b < S.B) vload(e0, S.e0[0] + (size_t)b * Hd, Hd, lane, nl);
-    cta_sync();
-    if (b < S.B) {
-#pragma unroll 1
-      for (int j = 0; j < A; ++j) {
-        float acc = 0.f;
-#pragma unroll
-        for (int x = 0; x < ILSW_VL; ++x) {
-          const int n = lane + x * nl;
-          if (n < Hd) acc += e0.v[x] * w0a(Wa, c.qf[0], S.O, A, Hd, j, n);
-        }
-        acc = wsum(acc);
-        if (lane == 0) sts(sc + A + j, acc);
-      }
-    }
-    wsync();
-  }
+  Vec h, e0;
+  float t_[ILSW_AL], ga_[ILSW_AL];
   if (b < S.B) {
+    if (with_da) vload(e0, S.e0[0] + (size_t)b * Hd, Hd, lane, nl);
     vload(h, S.h1p + (size_t)b * Hd, Hd, lane, nl);
-    for (int j = lane; j < A; j += nl) {
-      const float t = ldg(S.act + (size_t)b * A + j);
-      const float gA = with_da ? lds(sc + A + j) : ldg(S.dA[0] + (size_t)b * A + j);
-      sts(sc + j, gA * c.hp.max_act * (1.0f - t * t));
+    for (int j = lane, q = 0; j < A; j += nl, ++q) {
+      t_[q] = ldg(S.act + (size_t)b * A + j);
+      ga_[q] = with_da ? 0.f : ldg(S.dA[0] + (size_t)b * A + j);
     }
   }
+  const StageReq rq[2] = {stage_plain(P.p + P.oW2, A * Hd, 0),
+                          with_da ? stage_w0a(c.qf[0], S.O, A, Hd, A * Hd) : stage_plain(nullptr, 0, 0)};
+  SPtr sp[2];
+  cta_stage_multi<2, 0x2>(e, rq, sp);
+  const SPtr W = sp[0];
+  const SPtr sc = warp_scratch(e);
   cta_sync();
   if (b < S.B) {
-    for (int j = lane; j < A; j += nl) S.dmean[(size_t)b * A + j] = lds(sc + j);
-    float* d1 = S.d1p + (size_t)b * Hd;
-#pragma unroll
-    for (int x = 0; x < ILSW_VL; ++x) {
-      const int k = lane + x * nl;
-      if (k < Hd) {
-        float acc = 0.f;
+    if (with_da) {
 #pragma unroll 1
-        for (int j = 0; j < A; ++j) acc += lds(sc + j) * lds(W + (size_t)j * Hd + k);
-        d1[k] = h.v[x] > 0.f ? acc : 0.f;
+      for (int j = 0; j < A; ++j) {
+        const float acc = wsum(vdot_w0a_part(e0, sp[1], c.qf[0], S.O, A, Hd, j, lane, nl));
+        if (lane == 0) sts(sc + A + j, acc);
       }
+      wsync();
     }
+    for (int j = lane, q = 0; j < A; j += nl, ++q) {
+      const float t = t_[q];
+      const float gA = with_da ? lds(sc + A + j) : ga_[q];
+      const float dm = gA * c.hp.max_act * (1.0f - t * t);
+      sts(sc + j, dm);
+      S.dmean[(size_t)b * A + j] = dm;
+    }
+    wsync();
+    Vec acc;
+    vzero(acc);
+#pragma unroll 1
+    for (int j = 0; j < A; ++j) {
+      const float dm = lds(sc + j);
+      Vec w;
+      vload_s(w, W + (size_t)j * Hd, Hd, lane, nl);
+#pragma unroll
+      for (int x = 0; x < ILSW_VL; ++x) acc.v[x] += dm * w.v[x];
+    }
+#pragma unroll
+    for (int x = 0; x < ILSW_VL; ++x) acc.v[x] = h.v[x] > 0.f ? acc.v[x] : 0.f;
+    vstore(S.d1p + (size_t)b * Hd, acc, Hd, lane, nl);
   }
   cta_sync();
 }
@@ -485,14 +625,16 @@ ILSW_HDN void job_disc_head(const Ctx& c, int job, const RowEnv& e, int rows) {
   const DiscBufs& Dd = c.d;
   const MlpPtrs& N = c.disc;
   const int B = Dd.B, Hd = Dd.Hd, lane = e.lane, nl = e.nl;
-  const SPtr w3 = cta_stage(e, N.p + N.oW2, Hd, 0);
   const int r = job * kRowsPerJob + e.warp;
   Vec h2;
   float b3 = 0.f;
   if (r < rows) { vload(h2, Dd.h2 + (size_t)r * Hd, Hd, lane, nl); b3 = ldg(N.p + N.ob2); }
+  const SPtr w3 = cta_stage(e, N.p + N.oW2, Hd, 0);
   cta_sync();
   if (r < rows) {
-    const float y = vdot_s(h2, w3, Hd, lane, nl) + b3;
+    Vec w;
+    vload_s(w, w3, Hd, lane, nl);
+    const float y = wsum(vdot_part(h2, w)) + b3;
     const float cm = c.hp.disc_clamp;
     const float pass = (y >= -cm && y <= cm) ? 1.f : 0.f;
     if (r < 2 * B) {
@@ -506,21 +648,15 @@ ILSW_HDN void job_disc_head(const Ctx& c, int job, const RowEnv& e, int rows) {
         Dd.y[r] = x; Dd.dlogit[r] = dl; Dd.ceterm[r] = ce;
         Dd.accterm[r] = ((x > 0.f ? 1.f : 0.f) == t) ? 1.f : 0.f;
       }
-      float* d2 = Dd.d2 + (size_t)r * Hd;
 #pragma unroll
-      for (int xx = 0; xx < ILSW_VL; ++xx) {
-        const int k = lane + xx * nl;
-        if (k < Hd) d2[k] = dl * lds(w3 + k) * (1.0f - h2.v[xx] * h2.v[xx]);
-      }
+      for (int xx = 0; xx < ILSW_VL; ++xx) w.v[xx] = dl * w.v[xx] * (1.0f - h2.v[xx] * h2.v[xx]);
+      vstore(Dd.d2 + (size_t)r * Hd, w, Hd, lane, nl);
     } else {
       const int b = r - 2 * B;
       if (lane == 0) Dd.cmask[b] = pass;
-      float* dl2 = Dd.dl2 + (size_t)b * Hd;
 #pragma unroll
-      for (int xx = 0; xx < ILSW_VL; ++xx) {
-        const int k = lane + xx * nl;
-        if (k < Hd) dl2[k] = pass * lds(w3 + k) * (1.0f - h2.v[xx] * h2.v[xx]);
-      }
+      for (int xx = 0; xx < ILSW_VL; ++xx) w.v[xx] = pass * w.v[xx] * (1.0f - h2.v[xx] * h2.v[xx]);
+      vstore(Dd.dl2 + (size_t)b * Hd, w, Hd, lane, nl);
     }
   }
   cta_sync();
@@ -536,32 +672,28 @@ ILSW_HDN void job_disc_ew(const Ctx& c, int kind, int job, const RowEnv& e) {
     Vec h1, db, u1;
     vload(h1, Dd.h1 + ri, Hd, lane, nl); vload(db, Dd.db1 + ro, Hd, lane, nl); vload(u1, Dd.u1 + ro, Hd, lane, nl);
 #pragma unroll
-    for (int x = 0; x < ILSW_VL; ++x) {
-      const int k = lane + x * nl;
-      if (k < Hd) { Dd.ub1[ro + k] = db.v[x] * (1.0f - h1.v[x] * h1.v[x]); Dd.sb1[ro + k] = db.v[x] * u1.v[x]; }
-    }
+    for (int x = 0; x < ILSW_VL; ++x) { h1.v[x] = db.v[x] * (1.0f - h1.v[x] * h1.v[x]); u1.v[x] = db.v[x] * u1.v[x]; }
+    vstore(Dd.ub1 + ro, h1, Hd, lane, nl);
+    vstore(Dd.sb1 + ro, u1, Hd, lane, nl);
   } else if (kind == ROW_DISC_EW2) {
     Vec h2, db, w3;
     vload(h2, Dd.h2 + ri, Hd, lane, nl); vload(db, Dd.db2 + ro, Hd, lane, nl); vload(w3, c.disc.p + c.disc.oW2, Hd, lane, nl);
     const float cmk = ldg(Dd.cmask + b);
 #pragma unroll
     for (int x = 0; x < ILSW_VL; ++x) {
-      const int k = lane + x * nl;
-      if (k < Hd) {
-        const float s2 = 1.0f - h2.v[x] * h2.v[x];
-        Dd.t3[ro + k] = db.v[x] * s2;
-        const float sb2 = db.v[x] * (cmk * w3.v[x]);
-        Dd.zb2[ro + k] = (-2.0f * h2.v[x] * sb2) * s2;
-      }
+      const float s2 = 1.0f - h2.v[x] * h2.v[x];
+      const float sb2 = db.v[x] * (cmk * w3.v[x]);
+      w3.v[x] = (-2.0f * h2.v[x] * sb2) * s2;
+      db.v[x] = db.v[x] * s2;
     }
+    vstore(Dd.t3 + ro, db, Hd, lane, nl);
+    vstore(Dd.zb2 + ro, w3, Hd, lane, nl);
   } else {
     Vec h1, hb, sb;
     vload(h1, Dd.h1 + ri, Hd, lane, nl); vload(hb, Dd.hb1 + ro, Hd, lane, nl); vload(sb, Dd.sb1 + ro, Hd, lane, nl);
 #pragma unroll
-    for (int x = 0; x < ILSW_VL; ++x) {
-      const int k = lane + x * nl;
-      if (k < Hd) Dd.zb1[ro + k] = (hb.v[x] - 2.0f * h1.v[x] * sb.v[x]) * (1.0f - h1.v[x] * h1.v[x]);
-    }
+    for (int x = 0; x < ILSW_VL; ++x) hb.v[x] = (hb.v[x] - 2.0f * h1.v[x] * sb.v[x]) * (1.0f - h1.v[x] * h1.v[x]);
+    vstore(Dd.zb1 + ro, hb, Hd, lane, nl);
   }
 }
 
@@ -569,11 +701,11 @@ ILSW_HDN void job_disc_reward(const Ctx& c, int job, const RowEnv& e) {
   const DiscBufs& Dd = c.d;
   const MlpPtrs& N = c.disc;
   const int Hd = Dd.Hd, lane = e.lane, nl = e.nl;
-  const SPtr w3 = cta_stage(e, N.p + N.oW2, Hd, 0);
   const int b = job * kRowsPerJob + e.warp;
   Vec h;
   float b3 = 0.f;
   if (b < Dd.B) { vload(h, Dd.rh2 + (size_t)b * Hd, Hd, lane, nl); b3 = ldg(N.p + N.ob2); }
+  const SPtr w3 = cta_stage(e, N.p + N.oW2, Hd, 0);
   cta_sync();
   if (b < Dd.B) {
     const float y = vdot_s(h, w3, Hd, lane, nl) + b3;

@@ -69,11 +69,20 @@ class ReplayRing:
         rows = np.ascontiguousarray(rows, dtype=np.float32)
         n = rows.shape[0]
         assert rows.shape[1] == self.host_w, (rows.shape, self.host_w)
+        # pinned ring: a slot is rewritten only after the copy stream has drained (once per lap), so
+        # back-to-back appends never block the host on the previous H2D copy
         if self._pinned is None or self._pinned.shape[0] < n:
-            self._pinned = torch.empty((max(n, 1024), self.host_w), dtype=torch.float32).pin_memory()
-        self._copy_stream.synchronize()  # previous staging copy out of the pinned buffer is done
-        self._pinned[:n].copy_(torch.from_numpy(rows))
-        check(self.lib.ilsw_rb_append(self.h, C.c_void_p(self._pinned.data_ptr()), n,
+            self._copy_stream.synchronize()
+            self._pinned = torch.empty((max(2 * n, 4096), self.host_w), dtype=torch.float32).pin_memory()
+            self._pinned_np = self._pinned.numpy()
+            self._pin_cur = 0
+        if self._pin_cur + n > self._pinned.shape[0]:
+            self._copy_stream.synchronize()
+            self._pin_cur = 0
+        c = self._pin_cur
+        self._pinned_np[c:c + n] = rows
+        self._pin_cur = c + n
+        check(self.lib.ilsw_rb_append(self.h, C.c_void_p(self._pinned.data_ptr() + c * self.host_w * 4), n,
                                       C.c_void_p(self._copy_stream.cuda_stream)), "rb_append")
         self.pending += n
         if self.pending > self.capacity:
@@ -206,6 +215,40 @@ class StepEngine:
         n = n_steps or self.last_steps
         out = np.empty((n, _abi.LOSS_SLOTS), dtype=np.float32)
         check(self.lib.ilsw_read_losses(self.h, out.ctypes.data_as(C.c_void_p), n, _stream_ptr()), "read_losses")
+        return out
+
+    # -- asynchronous loss read-back: the D2H copy of a launch's loss log is queued behind the launch into a
+    # pinned ring; the host only synchronises when it collects (per-step API use without a host sync per step)
+    _loss_ring = None
+
+    def losses_async(self, n_steps=None):
+        n = n_steps or self.last_steps
+        if self._loss_ring is None:
+            self._loss_ring = torch.empty((max(4096, self.cfg.max_steps_per_call), _abi.LOSS_SLOTS), dtype=torch.float32).pin_memory()
+            self._loss_np = self._loss_ring.numpy()
+            self._loss_cur = 0
+            self._loss_done = []
+        if self._loss_cur + n > self._loss_ring.shape[0]:
+            self._drain_losses()
+        c = self._loss_cur
+        check(self.lib.ilsw_read_losses_async(self.h, C.c_void_p(self._loss_ring.data_ptr() + c * _abi.LOSS_SLOTS * 4), n,
+                                              _stream_ptr()), "read_losses_async")
+        self._loss_cur = c + n
+
+    def _drain_losses(self):
+        torch.cuda.current_stream().synchronize()
+        if self._loss_cur:
+            self._loss_done.append(self._loss_np[:self._loss_cur].copy())
+        self._loss_cur = 0
+
+    def losses_collect(self):
+        """All losses queued with losses_async() since the last collect: [n_total_steps, LOSS_SLOTS]."""
+        if self._loss_ring is None:
+            return np.zeros((0, _abi.LOSS_SLOTS), dtype=np.float32)
+        self._drain_losses()
+        check(self.lib.ilsw_check_abort(self.h, _stream_ptr()), "check_abort")
+        out = np.concatenate(self._loss_done) if self._loss_done else np.zeros((0, _abi.LOSS_SLOTS), dtype=np.float32)
+        self._loss_done = []
         return out
 
     def stats(self):

@@ -179,6 +179,9 @@ enum {
 int ilsw_read_losses(ilsw_trainer* tr, float* host_out, int n_steps, void* stream);
 /* asynchronous variant: enqueue D2H of the last `n_steps` rows into pinned host memory */
 int ilsw_read_losses_async(ilsw_trainer* tr, float* pinned_out, int n_steps, void* stream);
+/* synchronises `stream` and reports ILSW_ERR_ABORTED if any launch since the last check hit the in-kernel watchdog
+ * (the synchronous readers check on every call; users of the async variant call this when they collect) */
+int ilsw_check_abort(ilsw_trainer* tr, void* stream);
 
 /* eval-statistics snapshot (sac_alpha.py:186-233, td3.py:126-177): vectors of the batch of
  * `stats_step`.  Layout (floats): q1_pred[B] q2_pred[B] q_target[B] err1[B] err2[B] reward[B]

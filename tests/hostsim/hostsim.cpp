@@ -56,7 +56,7 @@ static void run_op(HostSim* hs, const Program& P, const Op& o, const RunArgs& a,
     if (s >= a.n_steps) return;
     for (int job = 0; job < o.n_jobs; ++job)
       for (int w = 0; w < kRowsPerJob; ++w) {
-        RowEnv env; env.lane = 0; env.nl = 1; env.warp = w; env.sm = hs->rowbuf.data();
+        RowEnv env; env.lane = 0; env.nl = 1; env.warp = w; env.sm = hs->rowbuf.data(); env.prof = -1;
         if (fast && run_row_job_fast(c, a, o.row.kind, o.row.rows, s, job + o.row.arg1 / kRowsPerJob, env)) continue;
         const int r = o.row.arg1 + job * kRowsPerJob + w;
         if (r < o.row.rows) run_row(c, a, o.row.kind, s, r, 0, 1);

@@ -68,6 +68,11 @@ def main():
         for i, (t, j, d) in enumerate(zip(us, tr.engine.last_job_us, desc)):
             if t == 0:
                 continue
+            if "ROW" in d and "GEMM" not in d and tile[i, 0] > 0:
+                ts = tile[i, :8]
+                n = int((ts > 0).sum())
+                d += "   [cta0 row job stages: %s us; job start %.2f us after phase start]" % (
+                    " ".join("%.2f" % x for x in np.diff(ts[:n]) / 1000.0), (ts[0] - pn[i]) / 1000.0)
             if "GEMM" in d and tile[i, 4] > 0:
                 st = np.diff(tile[i, :5]) / 1000.0
                 d += "   [last tile of cta0: issue %.2f  land %.2f  mma %.2f  epi %.2f us]" % tuple(st)
