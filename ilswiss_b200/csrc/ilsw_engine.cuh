@@ -11,6 +11,17 @@
 #include "ilsw_ops.cuh"
 #include "ilsw_rows_fast.cuh"
 
+// experiment switches of the tensor-core tile (see DESIGN.md 4.4 for the measurements behind the defaults)
+#ifndef ILSW_ADAM_PREFETCH
+#define ILSW_ADAM_PREFETCH 0
+#endif
+#ifndef ILSW_EIN_FIRST
+#define ILSW_EIN_FIRST 0
+#endif
+#ifndef ILSW_VECRAG
+#define ILSW_VECRAG 1
+#endif
+
 namespace ilsw {
 
 struct BarrierState { unsigned count; unsigned gen; unsigned pad[30]; };
@@ -414,7 +425,7 @@ __device__ __forceinline__ void sts_u32(unsigned addr, float v) {
 // matters -- the engine's instruction working set must stay cache resident).
 //   k-contiguous operand: element(row,k) = base[row*ld + k] -> smem[row*kKS + k]
 //   otherwise           : element(row,k) = base[k*ld + row] -> smem[k*kMS + row]
-// vec   : 16-byte cp.async.cg (aligned base, ld % 4 == 0, dims % 4 == 0, no aug column in the tile)
+// vec   : 16-byte cp.async.cg (aligned base, ld % 4 == 0; ragged extents copy partial vectors, zero filled)
 // !vec  : 4-byte cp.async.ca per element (unaligned rows such as W0[H x 14], ragged edges, the
 //         ones column of the bias gradient).  Nothing is staged through registers, so all copies
 //         of a stage are in flight together.  (.ca allocates in L1: safe because every grid
@@ -449,10 +460,21 @@ __device__ __noinline__ void tc_fill_stage(const GemmOp& o, float* stage, int m0
       const size_t sstep = (size_t)rstep * sr + (size_t)kstep * sk;
       unsigned dst = (unsigned)__cvta_generic_to_shared(sm + r * dr + k * dk);
       const unsigned dstep = 4u * (unsigned)(rstep * dr + kstep * dk);
+      // a vector at a ragged edge (N = 11, 14 ... or K % 4 != 0) copies only its live floats: cp.async zero-fills the
+      // rest.  The live count along the vector direction is loop invariant (k is fixed per thread in the k-contiguous
+      // layout, r in the other), so the loop body stays predicate + cp.async + 4 adds.
+#if ILSW_VECRAG
+      const int vbytes = 4 * min(max(contig_k ? klen - k : rlim - r, 0), 4);
+#endif
 #pragma unroll 4
       for (int i = 0; i < kVecIters; ++i) {                    // 32 x KC floats = 8*KC vectors
+#if ILSW_VECRAG
+        const int nb = (contig_k ? (r < rlim) : (k < klen)) ? vbytes : 0;
+        cp_async16s(dst, nb ? src : base, nb);
+#else
         const bool in = (r < rlim) && (k < klen);
         cp_async16s(dst, in ? src : base, in ? 16 : 0);
+#endif
         src += sstep; dst += dstep; r += rstep; k += kstep;
       }
     } else {
@@ -496,8 +518,14 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
   const int m0 = tm * 32, n0 = tn * 32;
   const int g = lane >> 2, q = lane & 3;
   const bool a_kc = !o.a_mc, b_kc = !o.b_nc;
+  // 16-byte panel copies need 16-byte aligned source vectors: aligned base and leading dimension (ragged extents are fine)
+#if ILSW_VECRAG
+  const bool vecA = ((o.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(o.A) & 15) == 0);
+  const bool vecB = ((o.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(o.B) & 15) == 0);
+#else
   const bool vecA = ((o.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(o.A) & 15) == 0) && ((o.K & 3) == 0) && ((o.M & 3) == 0);
   const bool vecB = ((o.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(o.B) & 15) == 0) && ((o.K & 3) == 0) && ((o.N & 3) == 0);
+#endif
   const int nstages = (o.K + kKC - 1) / kKC;
   const int Nt = o.N;
   // bias gradient (aug_ones): bias_out[m] = sum_k A(m,k), taken from the A panels (m-contiguous layout) by the tn == 0 tile
@@ -514,7 +542,38 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[u][i] = 0.f;
   EpiIn ein[4];
+  // fused-optimiser tiles: the Adam state of this thread's 4 elements (and of the bias element of a tn == 0 tile) is
+  // fetched while the panels are in flight -- no L2 round trip left in the epilogue
+#if ILSW_ADAM_PREFETCH
+  int gi[4] = {-1, -1, -1, -1}, gib = -1;
+  float am[4], av[4], ap[4], at[4], bm = 0.f, bv = 0.f, bp = 0.f, bt = 0.f;
+#endif
   ILSW_TSTAMP(0);
+  // epilogue inputs (bias / mask source / previous value, Adam state) are requested BEFORE the panel copies: behind
+  // 64 KB of cp.async traffic in the load/store queue they would return last
+#if ILSW_EIN_FIRST
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (er < o.M && ec + i < Nt) ein[i] = epi_load(o, er, ec + i);
+#endif
+#define ILSW_ADAM_STATE_LOADS() \
+  if (ad) { \
+    _Pragma("unroll") \
+    for (int i = 0; i < 4; ++i) \
+      if (er < o.M && ec + i < Nt) { \
+        gi[i] = gemm_grad_index(o, *ad, er, ec + i); \
+        am[i] = __ldcg(ad->m + gi[i]); av[i] = __ldcg(ad->v + gi[i]); ap[i] = __ldcg(ad->p + gi[i]); \
+        at[i] = ad->target ? __ldcg(ad->target + gi[i]) : 0.f; \
+      } \
+    if (do_aug && tid < 32 && m0 + tid < o.M) { \
+      gib = gemm_grad_index(o, *ad, m0 + tid, o.N); \
+      bm = __ldcg(ad->m + gib); bv = __ldcg(ad->v + gib); bp = __ldcg(ad->p + gib); \
+      bt = ad->target ? __ldcg(ad->target + gib) : 0.f; \
+    } \
+  }
+#if ILSW_ADAM_PREFETCH
+  ILSW_ADAM_STATE_LOADS();
+#endif
   // fragment addressing (32-bit shared addresses, bytes)
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
   const unsigned a_off = 4u * (a_kc ? g * kKS + q : q * kMS + g);
@@ -531,10 +590,11 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
       cp_async_commit();
     }
     if (st < 0) {
-      // epilogue inputs (bias / mask source / previous value) are fetched while the panels are in flight
+#if !ILSW_EIN_FIRST
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         if (er < o.M && ec + i < Nt) ein[i] = epi_load(o, er, ec + i);
+#endif
       ILSW_TSTAMP(1);
       continue;
     }
@@ -603,18 +663,13 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
   }
   ILSW_TSTAMP(3);
   const float outv[4] = {sum.x, sum.y, sum.z, sum.w};
+#if !ILSW_ADAM_PREFETCH
+  int gi[4] = {-1, -1, -1, -1}, gib = -1;
+  float am[4], av[4], ap[4], at[4], bm = 0.f, bv = 0.f, bp = 0.f, bt = 0.f;
+  ILSW_ADAM_STATE_LOADS();
+#endif
   if (ad) {
-    // weight-gradient tile with the optimiser fused: all Adam-state loads of the 4 elements first (one L2 round trip)
-    int gi[4]; float am[4], av[4], ap[4], at[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      gi[i] = -1;
-      if (er < o.M && ec + i < Nt) {
-        gi[i] = gemm_grad_index(o, *ad, er, ec + i);
-        am[i] = __ldcg(ad->m + gi[i]); av[i] = __ldcg(ad->v + gi[i]); ap[i] = __ldcg(ad->p + gi[i]);
-        at[i] = ad->target ? __ldcg(ad->target + gi[i]) : 0.f;
-      }
-    }
+    // weight-gradient tile with the optimiser fused (Adam state prefetched in the prologue)
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (gi[i] >= 0) {
@@ -633,7 +688,7 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
     for (int w = 0; w < 8; ++w) bsum += smem[kRedFloats + w * 32 + tid];
     const EpiIn e = epi_load(o, m0 + tid, o.N);
     epi_store(o, m0 + tid, o.N, bsum, e);
-    if (ad) adam_fused_elem(*ad, *cf, gemm_grad_index(o, *ad, m0 + tid, o.N), o.accumulate ? bsum + e.prev : bsum);
+    if (ad) adam_math_store(*ad, *cf, gib, o.accumulate ? bsum + e.prev : bsum, bm, bv, bp, bt);
   }
   __syncthreads();     // the partial tiles are read before the next job's panels overwrite them
   ILSW_TSTAMP(4);

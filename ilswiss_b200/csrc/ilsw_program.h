@@ -247,6 +247,12 @@ inline void build_disc_step(Builder& b, const Ctx& c) {
 }
 
 // S1 (+ D2 reward relabel when a discriminator is attached)
+// Two critics' backward-data tiles plus their skinny output-layer gradient tiles fit one wave of a 148-SM grid?
+inline bool early_out_layer_grad(int B, int Hd) {
+  const int dx_tiles = 2 * ((B + 31) / 32) * ((Hd + 31) / 32), skinny_tiles = 2 * ((Hd + 31) / 32);
+  return dx_tiles + skinny_tiles <= 148;
+}
+
 inline void build_sac_alpha(Builder& b, const Ctx& c) {
   const SacBufs& S = c.s;
   const int B = S.B, O = S.O, A = S.A, Hd = S.Hd, K0 = O + A;
@@ -278,15 +284,22 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
   for (int i = 0; i < 2; ++i) b.fwd(S.h0t[i], Hd, B, Hd, c.tqf[i].p + c.tqf[i].oW1, c.tqf[i].p + c.tqf[i].ob1, Hd, S.h1t[i], Hd, ACT_RELU);
   b.phase(); b.row(ROW_SAC_TARGET, B);
   b.phase();   // backward-data of both critics: one full tile per CTA
-  for (int i = 0; i < 2; ++i)
-    b.dx(S.d1q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
-  b.phase();   // all weight gradients of both critics; Adam + Polyak of the targets fused into the tile epilogues
   {
     int ad[2];
     for (int i = 0; i < 2; ++i) ad[i] = b.adam_desc(c.qf[i], &c.tqf[i], c.hp.qf_lr, b1, b2, eps, c.hp.tau, i == 0 ? SLOT_QF1 : SLOT_QF2);
+    for (int i = 0; i < 2; ++i)
+      b.dx(S.d1q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
+    // the output-layer gradient (+ Adam/Polyak of W2, b2) needs only dq and h1 and nothing reads W2 any more this
+    // step: when the backward-data phase leaves CTAs idle its skinny tiles run there, which keeps the weight-gradient
+    // phase within one wave of the grid (160 -> 144 jobs at B = 256)
+    const bool early_w2 = early_out_layer_grad(B, Hd);
+    if (early_w2)
+      for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
+    b.phase();   // the other weight gradients of both critics; Adam + Polyak of the targets fused into the tile epilogues
     for (int i = 0; i < 2; ++i) b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW1, c.qf[i].g + c.qf[i].ob1, 0, ad[i]);
     for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0, 0, ad[i]);
-    for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);   // skinny: cheap, last
+    if (!early_w2)
+      for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
   }
   b.phase();
   for (int i = 0; i < 2; ++i) b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0n[i], Hd, ACT_RELU);
@@ -343,15 +356,19 @@ inline void build_td3(Builder& b, const Ctx& c) {
   for (int i = 0; i < 2; ++i) b.fwd(S.h0t[i], Hd, B, Hd, c.tqf[i].p + c.tqf[i].oW1, c.tqf[i].p + c.tqf[i].ob1, Hd, S.h1t[i], Hd, ACT_RELU);
   b.phase(); b.row(ROW_TD3_TARGET, B);
   b.phase();
-  for (int i = 0; i < 2; ++i)
-    b.dx(S.d1q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
-  b.phase();   // weight gradients of both critics with the Adam step fused into the tile epilogues
   {
     int ad[2];
     for (int i = 0; i < 2; ++i) ad[i] = b.adam_desc(c.qf[i], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, i == 0 ? SLOT_QF1 : SLOT_QF2);
+    for (int i = 0; i < 2; ++i)
+      b.dx(S.d1q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
+    const bool early_w2 = early_out_layer_grad(B, Hd);      // see build_sac_alpha
+    if (early_w2)
+      for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
+    b.phase();   // weight gradients of both critics with the Adam step fused into the tile epilogues
     for (int i = 0; i < 2; ++i) b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW1, c.qf[i].g + c.qf[i].ob1, 0, ad[i]);
     for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0, 0, ad[i]);
-    for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
+    if (!early_w2)
+      for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
   }
   b.row(ROW_TD3_FINAL, 1);
   // delayed policy + target update (td3.py:113-124), steps with (n_train_steps_total % period)==0
