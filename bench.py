@@ -369,6 +369,29 @@ def main():
                 "h2d_bytes_per_step": buf.ring.host_w * 4, "d2h_bytes_per_step": 16 * 4,
                 "mode": "per train call: %d-transition burst H2D -> %d-step launch -> loss log D2H" % (launch, launch)}
 
+    # ---- sampler coupling: the per-env-step get_actions round trip with host buffers, env_num = 4,
+    # through ilsw_policy_act_host (one kernel, one sync) next to the eager torch module path the reference uses
+    sampler = None
+    if world == 1:
+        from ilswiss_b200.sampler import DevicePolicy
+        dp = DevicePolicy(tr, seed=1)
+        obs4 = rs.randn(4, O)
+        for _ in range(20):
+            dp.get_actions(obs4)
+            tr.policy.get_actions(obs4)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(500):
+            dp.get_actions(obs4)
+        ours_us = (time.perf_counter() - t0) / 500 * 1e6
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            for _ in range(500):
+                tr.policy.get_actions(obs4)
+        eager_us = (time.perf_counter() - t0) / 500 * 1e6
+        sampler = {"get_actions_us": ours_us, "eager_module_get_actions_us": eager_us, "env_num": 4,
+                   "note": "host numpy obs -> host numpy actions, stochastic; eager = the nn.Module forward the reference's eval_np runs on the same GPU"}
+
     # ---- the same metric in the other GEMM precision modes (short runs, same timing method)
     by_prec = {}
     if world == 1 and args.precision is None:
@@ -416,7 +439,7 @@ def main():
             "value_by_gemm_precision": by_prec,
             "data": "synthetic", "config": dict(config, l2="flushed between timed launches (256 MiB write, untimed)",
                                                 sampling="in-kernel Philox, uniform with replacement"),
-            "e2e": e2e, "e2e_train_call": e2e_call, "gpu_launches": int(launches),
+            "e2e": e2e, "e2e_train_call": e2e_call, "sampler": sampler, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "ilsw_engine_kernel",
                          "algorithmic_bytes_per_launch": bytes_step * launch, "launch_ms": ms_per_launch},

@@ -4,6 +4,7 @@ Pure declarations: importing this module does not load the library (see _lib.py)
 import ctypes as C
 
 ABI_VERSION = 1
+UPDATE_BOTH, UPDATE_DISC_ONLY, UPDATE_POLICY_ONLY = 0, 1, 2
 LOSS_SLOTS = 16
 IPC_HANDLE_BYTES = 64
 
@@ -80,6 +81,7 @@ PROTOTYPES = {
     "ilsw_mlp_num_params": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ilsw_trainer_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(TrainerConfig), C.POINTER(Mlp), C.c_int]),
     "ilsw_trainer_attach_disc": (C.c_int, [C.c_void_p, C.POINTER(DiscConfig), C.POINTER(Mlp)]),
+    "ilsw_trainer_set_update_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "ilsw_trainer_destroy": (C.c_int, [C.c_void_p]),
     "ilsw_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Inject), C.POINTER(Batch),
                              C.c_uint64, C.c_int, C.c_void_p]),
@@ -98,6 +100,7 @@ PROTOTYPES = {
     "ilsw_read_cta_ns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ilsw_kernel_launches": (C.c_int64, [C.c_void_p]),
     "ilsw_policy_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "ilsw_policy_act_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "ilsw_replica_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ilsw_replica_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
 }

@@ -8,7 +8,9 @@
 
 One engine step = one loop iteration with ONE discriminator update (BCE + gradient penalty,
 Adam) followed by ONE policy update (discriminator reward relabel + SAC-alpha step), which is what
-every shipped exp_spec uses (num_disc_updates_per_loop_iter = num_policy_updates_per_loop_iter = 1).
+the shipped exp_specs use (num_disc_updates_per_loop_iter = num_policy_updates_per_loop_iter = 1) -- all but
+gail_humanoid.yaml (100 / 100), which runs as alternating disc-only / policy-only launches of the same program
+(`_do_training_split`, `ilsw_trainer_set_update_mode`).
 """
 from collections import OrderedDict
 
@@ -37,8 +39,8 @@ class AdvIRLEngine:
             unsupported.append("wrap_absorbing")
         if policy_optim_batch_size_from_expert:
             unsupported.append("policy_optim_batch_size_from_expert>0")
-        if num_disc_updates_per_loop_iter != 1 or num_policy_updates_per_loop_iter != 1:
-            unsupported.append("num_{disc,policy}_updates_per_loop_iter != 1")
+        if num_disc_updates_per_loop_iter < 1 or num_policy_updates_per_loop_iter < 1:
+            unsupported.append("num_{disc,policy}_updates_per_loop_iter < 1")
         if disc_optim_batch_size != policy_optim_batch_size or disc_optim_batch_size != policy_trainer._cfg.batch:
             unsupported.append("disc/policy batch sizes must equal the trainer batch")
         if disc_optimizer_class is not optim.Adam:
@@ -52,6 +54,8 @@ class AdvIRLEngine:
         self.expert_replay_buffer, self.replay_buffer = expert_replay_buffer, replay_buffer
         self.use_grad_pen, self.grad_pen_weight = use_grad_pen, grad_pen_weight
         self.num_update_loops_per_train_call = num_update_loops_per_train_call
+        self.num_disc_updates_per_loop_iter = int(num_disc_updates_per_loop_iter)
+        self.num_policy_updates_per_loop_iter = int(num_policy_updates_per_loop_iter)
         self.disc_arena = adopt_module(discriminator)
         self.disc_optimizer = optim.Adam(self.discriminator.parameters(), lr=disc_lr, betas=(disc_momentum, 0.999))
         dc = _abi.DiscConfig()
@@ -76,6 +80,8 @@ class AdvIRLEngine:
         n = self.num_update_loops_per_train_call if n_loops is None else n_loops
         self.replay_buffer.flush()
         self.expert_replay_buffer.flush()
+        if self.num_disc_updates_per_loop_iter != 1 or self.num_policy_updates_per_loop_iter != 1:
+            return self._do_training_split(n, inject)
         done = 0
         while done < n:
             k = min(n - done, tr._cfg.max_steps_per_call)
@@ -103,6 +109,58 @@ class AdvIRLEngine:
                 self.disc_eval_statistics["Disc Rew Max"] = float(L[-1, _abi.L_REW_MAX])
                 self.disc_eval_statistics["Disc Rew Min"] = float(L[-1, _abi.L_REW_MIN])
             done += k
+
+    def _do_training_split(self, n_loops, inject=None):
+        """adv_irl.py:126-131 with num_disc_updates_per_loop_iter / num_policy_updates_per_loop_iter != 1
+        (exp_specs/gail/gail_humanoid.yaml: 100/100): per loop iteration one launch of n_disc discriminator-only
+        steps, then one launch of n_policy policy-only steps (reward relabel with the current discriminator).
+        inject (parity mode): idx_expert / idx_policy_d / gp_eps hold n_loops*n_disc rows, idx / eps_next /
+        eps_cur n_loops*n_policy rows, in the order the reference consumes them."""
+        tr, eng = self.policy_trainer, self.policy_trainer.engine
+        nd, npol = self.num_disc_updates_per_loop_iter, self.num_policy_updates_per_loop_iter
+        cap = tr._cfg.max_steps_per_call
+
+        def launches(total, mode, keys, row0, stats_ok):
+            eng.set_update_mode(mode)
+            done, first = 0, None
+            while done < total:
+                k = min(total - done, cap)
+                tr._launch += 1
+                sub = None
+                if inject is not None:
+                    sub = {kk: inject[kk][row0 + done:row0 + done + k].contiguous() for kk in keys}
+                want_stats = stats_ok and done == 0
+                eng.train(self.replay_buffer.ring, k, expert_ring=self.expert_replay_buffer.ring, inject=sub,
+                          seed=tr._seed + tr._launch, stats_step=0 if want_stats else -1)
+                L = eng.losses(k)
+                if first is None:
+                    first = (L[0].copy(), eng.stats() if want_stats else None)
+                last = L[-1].copy()
+                done += k
+            return first, last
+
+        try:
+            for it in range(n_loops):
+                (L0, _), _ = launches(nd, _abi.UPDATE_DISC_ONLY, ("idx_expert", "idx_policy_d", "gp_eps"), it * nd, False)
+                if self.disc_eval_statistics is None:
+                    st = OrderedDict()
+                    st["Disc CE Loss"] = float(L0[_abi.L_DISC_CE])
+                    st["Disc Acc"] = float(L0[_abi.L_DISC_ACC])
+                    if self.use_grad_pen:
+                        st["Grad Pen"] = float(L0[_abi.L_GRAD_PEN])
+                        st["Grad Pen W"] = np.mean(self.grad_pen_weight)
+                    self.disc_eval_statistics = st
+                want = tr.eval_statistics is None
+                (P0, vec), Pl = launches(npol, _abi.UPDATE_POLICY_ONLY, ("idx", "eps_next", "eps_cur"), it * npol, want)
+                if want:
+                    tr.eval_statistics = tr._build_stats(P0, vec)
+                # adv_irl.py:303-314 rewrites these after EVERY policy step: last write wins
+                self.disc_eval_statistics["Disc Rew Mean"] = float(Pl[_abi.L_REW_MEAN])
+                self.disc_eval_statistics["Disc Rew Std"] = float(Pl[_abi.L_REW_STD])
+                self.disc_eval_statistics["Disc Rew Max"] = float(Pl[_abi.L_REW_MAX])
+                self.disc_eval_statistics["Disc Rew Min"] = float(Pl[_abi.L_REW_MIN])
+        finally:
+            eng.set_update_mode(_abi.UPDATE_BOTH)
 
     def end_epoch(self):
         self.policy_trainer.end_epoch()

@@ -265,7 +265,11 @@ struct ilsw_trainer {
   Replica rep;
   unsigned seq;
   void* peer_bases[8];
+  // sampler-side inference with host buffers (ilsw_policy_act_host): pinned + device staging, allocated on first use
+  float *act_pin, *act_dev;     // [kMaxActRows x (in_dim + act_dim)] each: observations first, actions after
+  int update_mode;              // UpdateMode of the next launches (AdvIRL programs)
 };
+static const int kMaxActRows = 4096;
 
 static int trainer_build(ilsw_trainer* tr) {
   std::string why;
@@ -351,12 +355,22 @@ extern "C" int ilsw_trainer_attach_disc(ilsw_trainer* tr, const ilsw_disc_config
   return trainer_build(tr);
 }
 
+extern "C" int ilsw_trainer_set_update_mode(ilsw_trainer* tr, int mode) {
+  if (!tr || mode < UPDATE_BOTH || mode > UPDATE_POLICY_ONLY) return fail(ILSW_ERR_ARG, "set_update_mode: bad arguments");
+  if (mode != UPDATE_BOTH && !tr->spec.has_disc) return fail(ILSW_ERR_STATE, "set_update_mode: no discriminator attached");
+  if (mode != UPDATE_BOTH && tr->rep.world > 1) return fail(ILSW_ERR_UNSUPPORTED, "set_update_mode: split launches are single-replica");
+  tr->update_mode = mode;
+  return ILSW_OK;
+}
+
 extern "C" int ilsw_trainer_destroy(ilsw_trainer* tr) {
   if (!tr) return ILSW_OK;
   cudaDeviceSynchronize();
   for (int r = 0; r < 8; ++r)
     if (tr->peer_bases[r] && r != tr->rep.rank) cudaIpcCloseMemHandle(tr->peer_bases[r]);
   if (tr->ipc_buf) cudaFree(tr->ipc_buf);
+  if (tr->act_pin) cudaFreeHost(tr->act_pin);
+  if (tr->act_dev) cudaFree(tr->act_dev);
   if (tr->scratch) cudaFree(tr->scratch);
   if (tr->dev_prog) cudaFree(tr->dev_prog);
   if (tr->bar) cudaFree(tr->bar);
@@ -393,9 +407,11 @@ extern "C" int ilsw_train(ilsw_trainer* tr, ilsw_rb* policy_rb, ilsw_rb* expert_
   a.n_steps = n_steps; a.step0 = tr->n_total; a.stats_step = stats_step; a.seed = seed;
   for (int i = 0; i < kMaxNets; ++i) a.t0[i] = tr->t[i];
   if (inject) {
-    if (!inject->idx || !inject->eps_next) return fail(ILSW_ERR_ARG, "train: inject needs idx and eps_next");
-    if (cfg.algo == ILSW_ALGO_SAC_ALPHA && !inject->eps_cur) return fail(ILSW_ERR_ARG, "train: inject needs eps_cur for SAC");
-    if (tr->spec.has_disc && (!inject->idx_expert || !inject->idx_policy_d || (tr->spec.dcfg.use_grad_pen && !inject->gp_eps)))
+    const bool policy_part = tr->update_mode != UPDATE_DISC_ONLY;
+    if (policy_part && (!inject->idx || !inject->eps_next)) return fail(ILSW_ERR_ARG, "train: inject needs idx and eps_next");
+    if (policy_part && cfg.algo == ILSW_ALGO_SAC_ALPHA && !inject->eps_cur) return fail(ILSW_ERR_ARG, "train: inject needs eps_cur for SAC");
+    if (tr->spec.has_disc && tr->update_mode != UPDATE_POLICY_ONLY &&
+        (!inject->idx_expert || !inject->idx_policy_d || (tr->spec.dcfg.use_grad_pen && !inject->gp_eps)))
       return fail(ILSW_ERR_ARG, "train: inject needs idx_expert/idx_policy_d/gp_eps for the discriminator step");
     a.has_inject = 1;
     a.inj.idx = inject->idx; a.inj.eps_next = inject->eps_next; a.inj.eps_cur = inject->eps_cur;
@@ -410,6 +426,8 @@ extern "C" int ilsw_train(ilsw_trainer* tr, ilsw_rb* policy_rb, ilsw_rb* expert_
   }
   a.world = tr->rep.world; a.rank = tr->rep.rank; a.loss_log_offset = 0;
   a.profile = tr->profile;
+  a.update_mode = tr->spec.has_disc ? tr->update_mode : UPDATE_BOTH;
+  if (a.update_mode == UPDATE_DISC_ONLY && batch) return fail(ILSW_ERR_ARG, "train: a disc-only launch samples from the rings (no direct batch)");
   Replica rp = tr->rep;
   rp.seq0 = tr->seq;
   const Program* dp = tr->dev_prog;
@@ -421,9 +439,9 @@ extern "C" int ilsw_train(ilsw_trainer* tr, ilsw_rb* policy_rb, ilsw_rb* expert_
   CU(cudaLaunchCooperativeKernel(tr->ctas == 2 ? (void*)ilsw_engine_kernel<2> : (void*)ilsw_engine_kernel<1>, dim3(tr->grid), dim3(kThreads), args, smem, st));
   tr->launches += 1;
   // host mirrors of the on-device counters
-  tr->seq += (unsigned)(adam_t(a, tr->host_prog.ctx.hp, SLOT_POLICY, n_steps - 1) - a.t0[SLOT_POLICY]);
-  for (int slot = 0; slot < kMaxNets; ++slot) tr->t[slot] = adam_t(a, tr->host_prog.ctx.hp, slot, n_steps - 1);
-  tr->n_total += n_steps;
+  if (a.update_mode != UPDATE_DISC_ONLY)
+    tr->seq += (unsigned)(adam_t(a, tr->host_prog.ctx.hp, SLOT_POLICY, n_steps - 1) - a.t0[SLOT_POLICY]);
+  commit_counters(tr->t, tr->n_total, a, tr->host_prog.ctx.hp, n_steps);
   tr->last_steps = n_steps;
   return ILSW_OK;
 }
@@ -531,6 +549,32 @@ extern "C" int ilsw_policy_act(ilsw_trainer* tr, const float* obs_dev, int n, in
   ilsw_policy_act_kernel<<<n, 256, sh, (cudaStream_t)stream>>>(P, hp.algo, hp.max_act, hp.policy_noise, hp.noise_clip, obs_dev, n,
                                                                deterministic, seed, act_dev);
   CU(cudaGetLastError());
+  return ILSW_OK;
+}
+
+// A1 with HOST buffers -- what exploration_policy.get_actions(obs_np) does every env step (rlkit/torch/core.py:74-89,
+// base_algorithm.py:369-380): pinned H2D of the observations, ONE kernel, pinned D2H of the actions, ONE host sync.
+// Stream ordered behind the gradient steps already queued on `stream`, so it always sees the latest policy.
+extern "C" int ilsw_policy_act_host(ilsw_trainer* tr, const float* obs_host, int n, int deterministic, uint64_t seed,
+                                    float* act_host, void* stream) {
+  if (!tr || !obs_host || !act_host || n <= 0 || n > kMaxActRows) return fail(ILSW_ERR_ARG, "policy_act_host: bad arguments");
+  const MlpPtrs& P = tr->host_prog.ctx.policy;
+  const int O = P.in_dim, A = tr->spec.cfg.act_dim;
+  if (!tr->act_pin) {
+    const size_t bytes = (size_t)kMaxActRows * (O + A) * sizeof(float);
+    CU(cudaMallocHost(&tr->act_pin, bytes));
+    CU(cudaMalloc(&tr->act_dev, bytes));
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* pin_obs = tr->act_pin; float* pin_act = tr->act_pin + (size_t)kMaxActRows * O;
+  float* dev_obs = tr->act_dev; float* dev_act = tr->act_dev + (size_t)kMaxActRows * O;
+  memcpy(pin_obs, obs_host, (size_t)n * O * sizeof(float));
+  CU(cudaMemcpyAsync(dev_obs, pin_obs, (size_t)n * O * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = ilsw_policy_act(tr, dev_obs, n, deterministic, seed, dev_act, stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(pin_act, dev_act, (size_t)n * A * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  memcpy(act_host, pin_act, (size_t)n * A * sizeof(float));
   return ILSW_OK;
 }
 

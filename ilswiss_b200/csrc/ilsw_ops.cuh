@@ -858,6 +858,8 @@ ILSW_HDN void run_row(const Ctx& c, const RunArgs& a, int kind, int s, int r, in
 }
 
 ILSW_HD bool phase_active(const Phase& ph, const Hyper& hp, const RunArgs& a, int s) {
+  if ((ph.cond & COND_DISC_PART) && a.update_mode == UPDATE_POLICY_ONLY) return false;
+  if ((ph.cond & COND_POLICY_PART) && a.update_mode == UPDATE_DISC_ONLY) return false;
   if ((ph.cond & COND_FIRST_STEP) && s != 0) return false;
   if ((ph.cond & COND_WORLD_1) && a.world > 1) return false;
   if ((ph.cond & COND_WORLD_N) && a.world <= 1) return false;
@@ -866,6 +868,18 @@ ILSW_HD bool phase_active(const Phase& ph, const Hyper& hp, const RunArgs& a, in
     return ((a.step0 + s) % per) == 0;
   }
   return true;
+}
+
+// Host mirror of the counters a launch of n_steps advanced (shared by the C ABI and the test-only host simulator):
+// a disc-only launch steps only the discriminator's Adam, a policy-only launch everything else.
+inline void commit_counters(int (&t)[kMaxNets], int& n_total, const RunArgs& a, const Hyper& hp, int n_steps) {
+  for (int slot = 0; slot < kMaxNets; ++slot) {
+    const bool disc_slot = slot == SLOT_DISC;
+    if (a.update_mode == UPDATE_DISC_ONLY && !disc_slot) continue;
+    if (a.update_mode == UPDATE_POLICY_ONLY && disc_slot) continue;
+    t[slot] = adam_t(a, hp, slot, n_steps - 1);
+  }
+  n_total += n_steps;
 }
 
 }  // namespace ilsw

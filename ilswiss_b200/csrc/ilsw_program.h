@@ -55,11 +55,12 @@ struct Builder {
   Program& P;
   explicit Builder(Program& p) : P(p) { P.n_phases = 0; P.n_ops = 0; }
   bool overflow = false;
+  int base_cond = COND_ALWAYS;   // OR-ed into every phase (COND_DISC_PART / COND_POLICY_PART of AdvIRL programs)
 
   void phase(int cond = COND_ALWAYS, int collective = 0) {
     if (P.n_phases >= kMaxPhases) { overflow = true; return; }
     Phase& ph = P.phases[P.n_phases++];
-    ph.op_begin = P.n_ops; ph.op_count = 0; ph.total_jobs = 0; ph.cond = cond; ph.collective = collective;
+    ph.op_begin = P.n_ops; ph.op_count = 0; ph.total_jobs = 0; ph.cond = cond | base_cond; ph.collective = collective;
   }
   Op* add(int kind, int n_jobs) {
     if (P.n_ops >= kMaxOps || P.n_phases == 0) { overflow = true; return nullptr; }
@@ -583,7 +584,7 @@ inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem) {
 inline int build_program(Program& P) {
   Builder b(P);
   const Ctx& c = P.ctx;
-  if (c.hp.has_disc) build_disc_step(b, c);
+  if (c.hp.has_disc) { b.base_cond = COND_DISC_PART; build_disc_step(b, c); b.base_cond = COND_POLICY_PART; }
   if (c.hp.algo == ILSW_ALGO_SAC_ALPHA) build_sac_alpha(b, c);
   else if (c.hp.algo == ILSW_ALGO_TD3) build_td3(b, c);
   else if (c.hp.algo == ILSW_ALGO_SAC_V) build_sac_v(b, c);

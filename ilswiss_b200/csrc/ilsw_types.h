@@ -33,7 +33,12 @@ enum OpKind : int { OP_GEMM = 1, OP_ADAM = 2, OP_ROW = 3, OP_POLYAK = 4 };
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 
 // phase conditions (bit mask: every set condition must hold)
-enum Cond : int { COND_ALWAYS = 0, COND_TD3_POLICY = 1, COND_FIRST_STEP = 2, COND_WORLD_1 = 4, COND_WORLD_N = 8 };
+enum Cond : int { COND_ALWAYS = 0, COND_TD3_POLICY = 1, COND_FIRST_STEP = 2, COND_WORLD_1 = 4, COND_WORLD_N = 8,
+                  COND_DISC_PART = 16,      // phase of the discriminator update (D1); skipped by policy-only launches
+                  COND_POLICY_PART = 32 };  // phase of the policy update (D2 + S1) of an AdvIRL program; skipped by disc-only launches
+// AdvIRL launches (adv_irl.py:126-131): one engine step = one disc update + one policy update (UPDATE_BOTH, the
+// num_*_updates_per_loop_iter = 1 case of every shipped yaml but one), or n disc-only / n policy-only steps
+enum UpdateMode : int { UPDATE_BOTH = 0, UPDATE_DISC_ONLY = 1, UPDATE_POLICY_ONLY = 2 };
 
 // loss-log slots (per step)
 enum LossSlot : int {
@@ -213,6 +218,7 @@ struct RunArgs {
   int world, rank;
   int loss_log_offset;  // first row of loss_log to write
   int profile;          // 1: CTA 0 stamps the stages of its GEMM tiles (tools/phase_profile.py); 0 in production
+  int update_mode;      // UpdateMode (AdvIRL programs only)
 };
 
 struct Program {

@@ -211,6 +211,10 @@ class StepEngine:
                                   C.c_uint64(seed), stats_step, _stream_ptr()), "train")
         self.last_steps = n_steps
 
+    def set_update_mode(self, mode):
+        """AdvIRL engines: 0 = fused disc+policy iteration, 1 = disc-only steps, 2 = policy-only steps."""
+        check(self.lib.ilsw_trainer_set_update_mode(self.h, int(mode)), "set_update_mode")
+
     def losses(self, n_steps=None):
         n = n_steps or self.last_steps
         out = np.empty((n, _abi.LOSS_SLOTS), dtype=np.float32)
@@ -292,6 +296,16 @@ class StepEngine:
         out = torch.empty((obs.shape[0], self.cfg.act_dim), dtype=torch.float32, device=obs.device)
         check(self.lib.ilsw_policy_act(self.h, _ptr(obs), obs.shape[0], int(deterministic), C.c_uint64(seed), _ptr(out),
                                        _stream_ptr()), "policy_act")
+        return out
+
+    def policy_act_host(self, obs_np, deterministic=False, seed=0):
+        """get_actions with host buffers: numpy [n,O] -> numpy [n,A]; one kernel, one host sync."""
+        obs = np.ascontiguousarray(obs_np, dtype=np.float32)
+        if obs.ndim != 2 or obs.shape[1] != self.cfg.obs_dim:
+            raise ValueError("observations must be [n, %d], got %s" % (self.cfg.obs_dim, obs.shape))
+        out = np.empty((obs.shape[0], self.cfg.act_dim), dtype=np.float32)
+        check(self.lib.ilsw_policy_act_host(self.h, obs.ctypes.data_as(C.c_void_p), obs.shape[0], int(deterministic),
+                                            C.c_uint64(seed), out.ctypes.data_as(C.c_void_p), _stream_ptr()), "policy_act_host")
         return out
 
     def replica_export(self):

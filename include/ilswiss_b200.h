@@ -133,6 +133,12 @@ int ilsw_trainer_create(ilsw_trainer** out, const ilsw_trainer_config* cfg, cons
 /* Turns a SAC-alpha trainer into an AdvIRL engine: one engine step = one loop iteration of
  * adv_irl.py:126-131 with 1 discriminator update + 1 policy update. */
 int ilsw_trainer_attach_disc(ilsw_trainer* tr, const ilsw_disc_config* cfg, const ilsw_mlp* disc);
+/* num_disc_updates_per_loop_iter / num_policy_updates_per_loop_iter != 1 (adv_irl.py:126-131; exp_specs/gail/
+ * gail_humanoid.yaml uses 100/100): subsequent ilsw_train calls run n_steps discriminator updates only (mode 1:
+ * _do_reward_training, :133-236) or n_steps policy updates only (mode 2: _do_policy_training, :238-314, rewards from the
+ * current discriminator); mode 0 restores the fused 1+1 iteration.  Adam step counts advance only for the part run. */
+enum { ILSW_UPDATE_BOTH = 0, ILSW_UPDATE_DISC_ONLY = 1, ILSW_UPDATE_POLICY_ONLY = 2 };
+int ilsw_trainer_set_update_mode(ilsw_trainer* tr, int mode);
 int ilsw_trainer_destroy(ilsw_trainer* tr);
 
 /* Injected randomness for parity runs (all DEVICE pointers, T = n_steps of the call):
@@ -214,10 +220,15 @@ int ilsw_trainer_set_profiling(ilsw_trainer* tr, int on);
 int ilsw_read_cta_ns(ilsw_trainer* tr, unsigned long long* host_out, void* stream);
 int64_t ilsw_kernel_launches(const ilsw_trainer* tr);   /* engine launches so far */
 
-/* A1: sampler-side policy inference for <= 64 env rows (policies.py:245-246, core.py:74-89).
+/* A1: sampler-side policy inference for <= 4096 env rows (policies.py:245-246, core.py:74-89).
  * obs_dev [n,O] -> act_dev [n,A]; deterministic: tanh(mean) (SAC) / no noise (TD3). */
 int ilsw_policy_act(ilsw_trainer* tr, const float* obs_dev, int n, int deterministic,
                     uint64_t seed, float* act_dev, void* stream);
+/* the same with HOST buffers -- replaces the per-env-step round trip of exploration_policy.get_actions
+ * (rlkit/torch/core.py:74-89 eval_np: torch_ify -> forward -> np_ify; caller base_algorithm.py:369-380):
+ * pinned H2D of obs_host [n,O], one kernel, pinned D2H into act_host [n,A], one stream synchronisation. */
+int ilsw_policy_act_host(ilsw_trainer* tr, const float* obs_host, int n, int deterministic,
+                         uint64_t seed, float* act_host, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Replicas: one process per GPU; policy gradients are averaged across ranks

@@ -63,6 +63,15 @@ CASES = {
                         sac=dict(SAC_KW, reward_scale=2.0, beta_1=0.25, alpha=0.2), seed=23),
 }
 
+# adv_irl.py:126-131 with num_disc_updates_per_loop_iter / num_policy_updates_per_loop_iter != 1 (gail_humanoid.yaml uses
+# 100/100): one case "step" = one _do_training call = n_disc discriminator updates, then n_policy policy updates
+LOOP_CASES = {
+    "gail_nd2_np3": dict(algo="adv_irl", obs_dim=11, act_dim=3, batch=128, n_fill=5000, n_expert=2000, steps=2,
+                         n_disc=2, n_policy=3, mode="gail",
+                         disc=dict(disc_lr=3e-4, disc_momentum=0.9, use_grad_pen=True, grad_pen_weight=4.0),
+                         sac=dict(SAC_KW, reward_scale=2.0, alpha=0.2), seed=24),
+}
+
 HIDDEN = (256, 256)
 DISC_HID = 128
 BUFFER_SEED = 1      # policy replay buffer index RNG

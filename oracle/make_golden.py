@@ -154,7 +154,7 @@ def run_reference(case):
             mode=case["mode"], discriminator=mods["disc"], policy_trainer=trainer,
             expert_replay_buffer=ebuf, state_only=False, disc_optim_batch_size=B,
             policy_optim_batch_size=B, num_update_loops_per_train_call=1,
-            num_disc_updates_per_loop_iter=1, num_policy_updates_per_loop_iter=1,
+            num_disc_updates_per_loop_iter=case.get("n_disc", 1), num_policy_updates_per_loop_iter=case.get("n_policy", 1),
             rew_clip_min=case.get("rew_clip_min"), rew_clip_max=case.get("rew_clip_max"),
             env=env, exploration_policy=mods["policy"], training_env=None, replay_buffer=buf,
             max_path_length=min(100, case["n_fill"] - 1), no_terminal=True, **case["disc"])
@@ -222,16 +222,23 @@ def run_oracle(case):
         torch.manual_seed(C.EPS_SEED0 + t)
         row = OrderedDict()
         if algo == "adv_irl":
-            eb = R.np_to_torch_batch(ebuf.random_batch(B, keys=["observations", "actions"]))
-            pb = R.np_to_torch_batch(buf.random_batch(B, keys=["observations", "actions"]))
-            gp_eps = torch.rand(B, 1) if case["disc"]["use_grad_pen"] else None
-            d = disc.reward_step(torch.cat([eb["observations"], eb["actions"]], 1),
-                                 torch.cat([pb["observations"], pb["actions"]], 1), gp_eps)
-            batch = R.np_to_torch_batch(buf.random_batch(B))
-            rew = disc.rewards(batch["observations"], batch["actions"], case["mode"],
-                               case.get("rew_clip_min"), case.get("rew_clip_max"))
-            batch["rewards"] = rew
-            s = tr.train_step(batch, torch.randn(B, A), torch.randn(B, A))
+            # adv_irl.py:126-131: n_disc reward updates, then n_policy policy updates; the logged statistics are those of
+            # the FIRST update of each kind in the call (eval_statistics is filled once), reward stats of the LAST (:303-314)
+            d = s = None
+            for _ in range(case.get("n_disc", 1)):
+                eb = R.np_to_torch_batch(ebuf.random_batch(B, keys=["observations", "actions"]))
+                pb = R.np_to_torch_batch(buf.random_batch(B, keys=["observations", "actions"]))
+                gp_eps = torch.rand(B, 1) if case["disc"]["use_grad_pen"] else None
+                di = disc.reward_step(torch.cat([eb["observations"], eb["actions"]], 1),
+                                      torch.cat([pb["observations"], pb["actions"]], 1), gp_eps)
+                d = d or di
+            for _ in range(case.get("n_policy", 1)):
+                batch = R.np_to_torch_batch(buf.random_batch(B))
+                rew = disc.rewards(batch["observations"], batch["actions"], case["mode"],
+                                   case.get("rew_clip_min"), case.get("rew_clip_max"))
+                batch["rewards"] = rew
+                si = tr.train_step(batch, torch.randn(B, A), torch.randn(B, A))
+                s = s or si
             rn = rew.numpy()
             row.update({"Disc CE Loss": d["disc_ce_loss"], "Disc Acc": d["disc_acc"]})
             if case["disc"]["use_grad_pen"]:
@@ -298,9 +305,10 @@ def compare_rows(ref_rows, ora_rows, rtol):
 def main():
     torch.set_num_threads(1)
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    names = sys.argv[1:] or list(C.CASES.keys())
+    all_cases = dict(C.CASES, **C.LOOP_CASES)
+    names = sys.argv[1:] or list(all_cases.keys())
     for name in names:
-        case = C.CASES[name]
+        case = all_cases[name]
         ref_rows, ref_final, ref_dig = run_reference(case)
         ora_rows, ora_final, ora_dig = run_oracle(case)
         worst = compare_rows(ref_rows, ora_rows, 2e-5)

@@ -63,6 +63,62 @@ def case_injection(case, steps=None):
     return out
 
 
+def loop_case_injection(case):
+    """Injection streams of a LOOP_CASES case (n_disc / n_policy updates per _do_training call), in the order the
+    reference consumes its RNGs: per call t (torch.manual_seed(EPS_SEED0 + t)): n_disc x [expert randint, policy
+    randint, torch.rand(B,1)], then n_policy x [policy randint, randn(B,A), randn(B,A)].  Disc arrays have
+    steps*n_disc rows, policy arrays steps*n_policy rows."""
+    B, A, T = case["batch"], case["act_dim"], case["steps"]
+    nd, npol = case["n_disc"], case["n_policy"]
+    rs = np.random.RandomState(CFG.BUFFER_SEED)
+    ers = np.random.RandomState(CFG.EXPERT_SEED)
+    out = dict(idx=np.zeros((T * npol, B), np.int32), eps_next=np.zeros((T * npol, B, A), np.float32),
+               eps_cur=np.zeros((T * npol, B, A), np.float32), idx_expert=np.zeros((T * nd, B), np.int32),
+               idx_policy_d=np.zeros((T * nd, B), np.int32), gp_eps=np.zeros((T * nd, B), np.float32))
+    for t in range(T):
+        torch.manual_seed(CFG.EPS_SEED0 + t)
+        for i in range(nd):
+            out["idx_expert"][t * nd + i] = ers.randint(0, case["n_expert"], B)
+            out["idx_policy_d"][t * nd + i] = rs.randint(0, case["n_fill"], B)
+            if case["disc"]["use_grad_pen"]:
+                out["gp_eps"][t * nd + i] = torch.rand(B, 1).numpy().ravel()
+        for j in range(npol):
+            out["idx"][t * npol + j] = rs.randint(0, case["n_fill"], B)
+            out["eps_next"][t * npol + j] = torch.randn(B, A).numpy()
+            out["eps_cur"][t * npol + j] = torch.randn(B, A).numpy()
+    return out
+
+
+DISC_STATS = ("Disc CE Loss", "Disc Acc", "Grad Pen")
+REW_STATS = ("Disc Rew Mean", "Disc Rew Std", "Disc Rew Max", "Disc Rew Min")
+
+
+def run_loop_case(run, case, set_mode):
+    """Drives a HostSimRun / DeviceRun through a LOOP_CASES case with alternating disc-only / policy-only launches
+    (set_mode(1|2|0)) and returns one statistics row per _do_training call with the reference's logging rules: first
+    disc update, first policy update, reward statistics of the last policy update."""
+    inj = loop_case_injection(case)
+    nd, npol = case["n_disc"], case["n_policy"]
+    disc_keys, pol_keys = ("idx_expert", "idx_policy_d", "gp_eps"), ("idx", "eps_next", "eps_cur")
+    rows = []
+    for t in range(case["steps"]):
+        set_mode(1)
+        Ld = run.train(nd, {k: inj[k] for k in disc_keys}, t_offset=t * nd)
+        set_mode(2)
+        Lp = run.train(npol, {k: inj[k] for k in pol_keys}, t_offset=t * npol)
+        row = {}
+        for k, slot in STAT_TO_SLOT.items():
+            if k in DISC_STATS:
+                row[k] = float(Ld[0, slot])
+            elif k in REW_STATS:
+                row[k] = float(Lp[-1, slot])
+            else:
+                row[k] = float(Lp[0, slot])
+        rows.append(row)
+    set_mode(0)
+    return rows
+
+
 def trainer_config(case, max_steps=64, precision=0):
     algo = case["algo"]
     cfg = _abi.TrainerConfig()
@@ -189,6 +245,7 @@ def load_hostsim():
     lib.hs_num_phases.argtypes = [C.c_void_p]
     lib.hs_describe.restype = C.c_int
     lib.hs_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    lib.hs_set_update_mode.argtypes = [C.c_void_p, C.c_int]
     lib.hs_grad.restype = C.POINTER(C.c_float)
     lib.hs_grad.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     return lib
@@ -233,8 +290,8 @@ class HostSimRun:
 
     def train(self, n_steps, inj, stats_step=-1, t_offset=0, seed=0):
         keep = {k: np.ascontiguousarray(v[t_offset:t_offset + n_steps]) for k, v in inj.items()}
-        ij = _abi.Inject(np_ptr(keep["idx"]), np_ptr(keep["eps_next"]), np_ptr(keep["eps_cur"]),
-                         np_ptr(keep["idx_expert"]), np_ptr(keep["idx_policy_d"]), np_ptr(keep["gp_eps"]))
+        ptr = lambda k: np_ptr(keep[k]) if k in keep else None       # split launches inject only their own streams
+        ij = _abi.Inject(ptr("idx"), ptr("eps_next"), ptr("eps_cur"), ptr("idx_expert"), ptr("idx_policy_d"), ptr("gp_eps"))
         er = self.ering
         rc = self.lib.hs_train(self.h, np_ptr(self.ring), self.ring.shape[1], self.ring.shape[0],
                                np_ptr(er) if er is not None else None, er.shape[1] if er is not None else 0,

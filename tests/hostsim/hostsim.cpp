@@ -23,6 +23,7 @@ struct HostSim {
   int t[kMaxNets];
   int n_total;
   int generic_rows;     // 1: force the generic per-row kernels (cross-check of the fast row jobs)
+  int update_mode = 0;  // UpdateMode of the next hs_train calls
   std::vector<float> rowbuf;
 };
 
@@ -126,6 +127,7 @@ int hs_train(void* p, const float* ring, int stride, int size, const float* erin
     a.direct = {batch->obs, batch->act, batch->rew, batch->term, batch->next_obs};
   }
   a.world = 1; a.rank = 0; a.loss_log_offset = 0;
+  a.update_mode = h->update_mode;
   const Program& P = h->prog;
   for (int s = 0; s < n_steps; ++s)
     for (int ph = 0; ph < P.n_phases; ++ph) {
@@ -133,12 +135,12 @@ int hs_train(void* p, const float* ring, int stride, int size, const float* erin
       if (!phase_active(phs, P.ctx.hp, a, s)) continue;
       for (int j = 0; j < phs.op_count; ++j) run_op(h, P, P.ops[phs.op_begin + j], a, s);
     }
-  for (int slot = 0; slot < kMaxNets; ++slot) h->t[slot] = adam_t(a, P.ctx.hp, slot, n_steps - 1);
-  h->n_total += n_steps;
+  commit_counters(h->t, h->n_total, a, P.ctx.hp, n_steps);
   return 0;
 }
 
 void hs_set_generic_rows(void* p, int flag) { ((HostSim*)p)->generic_rows = flag; }
+void hs_set_update_mode(void* p, int mode) { ((HostSim*)p)->update_mode = mode; }
 void hs_set_precision(void* p, int prec) { ((HostSim*)p)->prog.ctx.hp.gemm_precision = prec; }
 const float* hs_losses(void* p) { return ((HostSim*)p)->prog.ctx.loss_log; }
 const float* hs_stats(void* p) { return ((HostSim*)p)->prog.ctx.stats; }

@@ -207,6 +207,45 @@ def test_adv_irl_engine_matches_oracle_and_stats_keys():
                      policy_optim_batch_size=256, num_disc_updates_per_loop_iter=1, num_policy_updates_per_loop_iter=1)
 
 
+def test_adv_irl_engine_multiple_updates_per_loop_iter():
+    """num_disc_updates_per_loop_iter / num_policy_updates_per_loop_iter != 1 (gail_humanoid.yaml) through the drop-in
+    engine: statistics follow the reference's logging rules, parameters follow the oracle's nested loops."""
+    from helpers import loop_case_injection
+    from ilswiss_b200.adv_irl import AdvIRLEngine
+    from ilswiss_b200.replay_buffer import DeviceReplayBuffer
+    from ilswiss_b200.trainers import SoftActorCritic
+
+    torch.set_num_threads(1)
+    case = CFG.LOOP_CASES["gail_nd2_np3"]
+    mods, _ = build_modules(case)
+    tr = SoftActorCritic(mods["policy"], mods["qf1"], mods["qf2"], batch_size=case["batch"], gemm_precision=3, **case["sac"])
+    data, edata = case_data(case)
+    buf = DeviceReplayBuffer(case["n_fill"], case["obs_dim"], case["act_dim"], random_seed=1)
+    ebuf = DeviceReplayBuffer(case["n_fill"], case["obs_dim"], case["act_dim"], random_seed=3)
+    fill(buf, data)
+    fill(ebuf, edata)
+    irl = AdvIRLEngine(case["mode"], mods["disc"], tr, ebuf, buf, disc_optim_batch_size=case["batch"],
+                       policy_optim_batch_size=case["batch"], num_update_loops_per_train_call=case["steps"],
+                       num_disc_updates_per_loop_iter=case["n_disc"], num_policy_updates_per_loop_iter=case["n_policy"],
+                       **case["disc"])
+    inj = {k: torch.from_numpy(v).cuda() for k, v in loop_case_injection(case).items()}
+    irl.do_training(inject=inj)          # steps loop iterations in one train call: stats of the FIRST updates, rewards of the LAST
+    rows, final, _ = G.run_oracle(case)
+    st = irl.disc_eval_statistics
+    assert abs(st["Disc CE Loss"] - rows[0]["Disc CE Loss"]) < 1e-4 * abs(rows[0]["Disc CE Loss"])
+    assert abs(st["Disc Rew Mean"] - rows[-1]["Disc Rew Mean"]) < 1e-4 * max(abs(rows[-1]["Disc Rew Mean"]), 1.0)
+    assert abs(tr.eval_statistics["QF1 Loss"] - rows[0]["QF1 Loss"]) < 1e-4 * abs(rows[0]["QF1 Loss"])
+    got = np.concatenate([p.detach().cpu().numpy().ravel() for p in mods["disc"].parameters()])
+    assert np.max(np.abs(got - final["disc"])) < 1e-4
+    gotp = np.concatenate([p.detach().cpu().numpy().ravel() for p in mods["policy"].parameters()])
+    assert np.max(np.abs(gotp - final["policy"])) < 2 * 3e-4 * 6 + 1e-6
+    state = tr.engine.get_state()
+    assert state.adam_step[4] == case["steps"] * case["n_disc"] and state.adam_step[2] == case["steps"] * case["n_policy"]
+    # speed mode (in-kernel Philox) runs too
+    irl.do_training(n_loops=1)
+    assert np.isfinite(irl.disc_eval_statistics["Disc Rew Mean"])
+
+
 def test_sac_v_trainer_dropin():
     from ilswiss_b200 import modules
     from ilswiss_b200.replay_buffer import DeviceReplayBuffer

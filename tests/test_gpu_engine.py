@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import CFG, G, DeviceRun, STAT_TO_SLOT, assert_params_close, case_injection
+from helpers import CFG, G, DeviceRun, STAT_TO_SLOT, assert_params_close, case_injection, run_loop_case
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -129,3 +129,49 @@ def test_direct_batch_equals_ring_batch():
     b.eng.train(None, 1, inject=dev, batch=batch)
     np.testing.assert_array_equal(La[:, :5], b.eng.losses(1)[:, :5])
     np.testing.assert_array_equal(a.arena("qf1"), b.arena("qf1"))
+
+
+@pytest.mark.parametrize("precision", [0, 3])
+@pytest.mark.parametrize("name", list(CFG.LOOP_CASES.keys()))
+def test_cuda_split_disc_policy_launches_match_oracle_and_golden(name, precision):
+    """adv_irl.py:126-131 with n_disc / n_policy != 1 (gail_humanoid.yaml): alternating disc-only / policy-only launches
+    (ilsw_trainer_set_update_mode) vs the oracle's nested loops AND vs the executed reference's transcript."""
+    torch.set_num_threads(1)
+    case = CFG.LOOP_CASES[name]
+    rows, final, _ = G.run_oracle(case)
+    run = DeviceRun(case, precision=precision)
+    got_rows = run_loop_case(run, case, run.eng.set_update_mode)
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    keys = [str(k) for k in gold["stat_keys"]]
+    for t, (row, got) in enumerate(zip(rows, got_rows)):
+        for k, ref in row.items():
+            if k in STAT_TO_SLOT and ref is not None:
+                assert abs(got[k] - ref) <= loss_tol(k, ref, precision, 2 * case["batch"]), (name, t, k, got[k], ref)
+        for j, k in enumerate(keys):
+            ref = gold["stats"][t, j]
+            if k in STAT_TO_SLOT and not np.isnan(ref):
+                assert abs(got[k] - ref) <= loss_tol(k, ref, precision, 2 * case["batch"]), (name, t, k, got[k], ref)
+    n_updates = case["steps"] * max(case["n_disc"], case["n_policy"])
+    for k in final:
+        if k == "log_alpha":
+            assert abs(run.eng.get_state().log_alpha - final[k][0]) < 1e-6
+        else:
+            assert_params_close(run.arena(k), final[k], n_updates, msg="%s/%s" % (name, k), frac={0: 5e-4, 3: 0.1}[precision])
+
+
+def test_cuda_fused_iteration_equals_split_launches():
+    """One fused disc+policy step == a disc-only launch followed by a policy-only launch, bit for bit."""
+    case = CFG.CASES["gail_hopper"]
+    inj = case_injection(case)
+    a = DeviceRun(case, precision=3)
+    a.train(case["steps"], inj)
+    b = DeviceRun(case, precision=3)
+    for t in range(case["steps"]):
+        b.eng.set_update_mode(1)
+        b.train(1, inj, t_offset=t)
+        b.eng.set_update_mode(2)
+        b.train(1, inj, t_offset=t)
+    for k in ("policy", "qf1", "qf2", "target_qf1", "disc"):
+        np.testing.assert_array_equal(a.arena(k), b.arena(k), err_msg=k)
+    sa, sb = a.eng.get_state(), b.eng.get_state()
+    assert list(sa.adam_step) == list(sb.adam_step) and sa.log_alpha == sb.log_alpha

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import CFG, G, HostSimRun, STAT_TO_SLOT, assert_params_close, case_injection, load_hostsim
+from helpers import CFG, G, HostSimRun, STAT_TO_SLOT, assert_params_close, case_injection, load_hostsim, run_loop_case
 
 CASES = [n for n, c in CFG.CASES.items() if c["algo"] in ("sac_alpha", "sac_v", "td3", "adv_irl")]
 
@@ -92,6 +92,49 @@ def test_fast_row_jobs_equal_generic_row_kernels(lib, name):
     lib.hs_set_generic_rows(b.h, 1)
     La, Lb = a.train(case["steps"], inj), b.train(case["steps"], inj)
     np.testing.assert_array_equal(np.nan_to_num(La), np.nan_to_num(Lb))
+    for k in a.arenas:
+        np.testing.assert_array_equal(a.arenas[k], b.arenas[k], err_msg=k)
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("name", list(CFG.LOOP_CASES.keys()))
+def test_hostsim_split_disc_policy_launches_match_oracle(lib, name):
+    """adv_irl.py:126-131 with n_disc / n_policy != 1: alternating disc-only / policy-only launches of the SAME program
+    (phase conditions COND_DISC_PART / COND_POLICY_PART) reproduce the oracle's nested loops."""
+    torch.set_num_threads(1)
+    case = CFG.LOOP_CASES[name]
+    rows, final, _ = G.run_oracle(case)
+    run = HostSimRun(lib, case)
+    got_rows = run_loop_case(run, case, lambda m: lib.hs_set_update_mode(run.h, m))
+    for t, (row, got) in enumerate(zip(rows, got_rows)):
+        for k, ref in row.items():
+            if k not in STAT_TO_SLOT or ref is None:
+                continue
+            tol = 1e-4 * max(abs(ref), 1e-3) if k != "Policy Loss" else 1e-4 * max(abs(ref), 1.0)
+            assert abs(got[k] - ref) <= tol, (name, t, k, got[k], ref)
+    n_updates = case["steps"] * max(case["n_disc"], case["n_policy"])
+    for k in final:
+        if k == "log_alpha":
+            assert abs(lib.hs_log_alpha(run.h) - final[k][0]) < 1e-6
+            continue
+        assert_params_close(run.arenas[k], final[k], n_updates, msg="%s/%s" % (name, k))
+    run.close()
+
+
+def test_hostsim_fused_iteration_equals_split_launches(lib):
+    """One fused disc+policy engine step == one disc-only launch followed by one policy-only launch, bit for bit."""
+    case = CFG.CASES["gail_hopper"]
+    inj = case_injection(case)
+    a = HostSimRun(lib, case)
+    La = a.train(case["steps"], inj)
+    b = HostSimRun(lib, case)
+    for t in range(case["steps"]):
+        lib.hs_set_update_mode(b.h, 1)
+        Ld = b.train(1, inj, t_offset=t)
+        lib.hs_set_update_mode(b.h, 2)
+        Lp = b.train(1, inj, t_offset=t)
+        assert Ld[0, STAT_TO_SLOT["Disc CE Loss"]] == La[t, STAT_TO_SLOT["Disc CE Loss"]]
+        assert Lp[0, STAT_TO_SLOT["QF1 Loss"]] == La[t, STAT_TO_SLOT["QF1 Loss"]]
     for k in a.arenas:
         np.testing.assert_array_equal(a.arenas[k], b.arenas[k], err_msg=k)
     a.close(); b.close()

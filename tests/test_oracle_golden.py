@@ -12,10 +12,13 @@ from oracle import make_golden as G
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.mark.parametrize("name", list(C.CASES.keys()))
+ALL_CASES = dict(C.CASES, **C.LOOP_CASES)
+
+
+@pytest.mark.parametrize("name", list(ALL_CASES.keys()))
 def test_oracle_reproduces_reference_transcript(name):
     torch.set_num_threads(1)
-    case = C.CASES[name]
+    case = ALL_CASES[name]
     gold = np.load(os.path.join(GOLDEN, name + ".npz"))
     keys = [str(k) for k in gold["stat_keys"]]
     rows, final, digests = G.run_oracle(case)
