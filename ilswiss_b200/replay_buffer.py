@@ -101,11 +101,38 @@ class DeviceReplayBuffer:
         # :134-216
         if absorbing:
             raise NotImplementedError("wrap_absorbing is rejected by the reference itself (base_algorithm.py:137-139)")
-        for ob, action, reward, next_ob, terminal in zip(path["observations"], path["actions"], path["rewards"],
-                                                          path["next_observations"], path["terminals"]):
-            self.add_sample(observation=ob, action=action, reward=reward, terminal=terminal, next_observation=next_ob)
+        # same result as the reference's per-transition add_sample loop; the rows of the whole path are packed in one
+        # vectorised pass and go to the GPU as ONE pinned copy when the episode is terminated
+        n = len(path["observations"])
+        if n:
+            terms = np.asarray(path["terminals"]).reshape(n).astype(bool)
+            rows = layout.pack_host_rows(np.asarray(path["observations"]).reshape(n, -1), np.asarray(path["actions"]).reshape(n, -1),
+                                         np.asarray(path["rewards"]).reshape(n), terms,
+                                         np.asarray(path["next_observations"]).reshape(n, -1))
+            self._pending.extend(rows)
+            for t in range(n):
+                if terms[t]:
+                    next_start = (self._top + 1) % self._max_replay_buffer_size
+                    self._traj_endpoints[self._cur_start] = next_start
+                    self._cur_start = next_start
+                self._advance()
         self.terminate_episode()
         self._trajs += 1
+
+    def save_data(self, save_name):
+        """:110-123 -- the reference's on-disk dump (fields up to _top), readable by its own tools."""
+        import pickle
+
+        d = self.__getstate__()
+        top = self._top
+        save_dict = {
+            "observations": d["_observations"][:top], "actions": d["_actions"][:top],
+            "next_observations": d["_next_obs"][:top], "terminals": d["_terminals"][:top],
+            "timeouts": np.zeros((top, 1), dtype="uint8"), "rewards": d["_rewards"][:top],
+            "agent_infos": [None] * top, "env_infos": [None] * top,
+        }
+        with open(save_name, "wb") as f:
+            pickle.dump(save_dict, f)
 
     def get_traj_num(self):
         return self._trajs

@@ -174,6 +174,44 @@ def test_replay_buffer_dropin_matches_reference_semantics():
     assert clone._top == buf._top and clone._size == buf._size
 
 
+def test_expert_demo_ingest_and_save_data(tmp_path):
+    """8f rank 3: pickled trajectory list -> normalised demos -> expert ring (adv_irl_exp_script.py:51-138), and the
+    reference's on-disk dump format (simple_replay_buffer.py:110-123)."""
+    from ilswiss_b200 import demos
+    from ilswiss_b200.replay_buffer import DeviceReplayBuffer
+
+    rs = np.random.RandomState(4)
+    O, A, T = 6, 2, 25
+    trajs = []
+    for i in range(5):
+        obs = rs.randn(T + 1, O) * (i + 1)
+        trajs.append(dict(observations=obs[:-1], next_observations=obs[1:], actions=rs.uniform(-1, 1, (T, A)),
+                          rewards=rs.randn(T, 1), terminals=np.zeros((T, 1), dtype=bool)))
+    path = str(tmp_path / "demos.pkl")
+    with open(path, "wb") as f:
+        pickle.dump(trajs, f)
+    buf = DeviceReplayBuffer(1000, O, A, random_seed=3)
+    ora = R.ReplayOracle(1000, O, A, random_seed=3)
+    import random
+    sel, st, name, kw = demos.ingest(path, buf, traj_num=4, scale_env_with_demo_stats=True, rng=random.Random(2))
+    for t in sel:
+        ora.add_path(t)
+    assert name == "ScaledEnv" and buf.num_steps_can_sample() == 4 * T == ora.num_steps_can_sample()
+    assert buf._traj_endpoints == ora._traj_endpoints and buf.get_traj_num() == 4
+    got, ref = buf.random_batch(64), ora.random_batch(64)
+    for k in ref:
+        np.testing.assert_array_equal(got[k].astype(np.float32), ref[k].astype(np.float32), err_msg=k)
+    allobs = buf.get_all(keys=["observations"])["observations"]
+    assert abs(allobs.mean()) < 1e-6 and abs(allobs.std(0).mean() - 1.0) < 1e-4       # demos were standardised
+    dump = str(tmp_path / "buffer.pkl")
+    buf.save_data(dump)
+    with open(dump, "rb") as f:
+        d = pickle.load(f)
+    assert set(d) == {"observations", "actions", "next_observations", "terminals", "timeouts", "rewards", "agent_infos", "env_infos"}
+    assert d["observations"].shape == (4 * T, O) and len(d["env_infos"]) == 4 * T
+    np.testing.assert_array_equal(d["observations"].astype(np.float32), ora._observations[:4 * T].astype(np.float32))
+
+
 def test_adv_irl_engine_matches_oracle_and_stats_keys():
     from ilswiss_b200.adv_irl import AdvIRLEngine
     from ilswiss_b200.replay_buffer import DeviceReplayBuffer
