@@ -33,7 +33,9 @@ class TrainerConfig(C.Structure):
                 ("alpha", C.c_double), ("train_alpha", C.c_int), ("target_entropy", C.c_double),
                 ("policy_mean_reg_weight", C.c_double), ("policy_std_reg_weight", C.c_double),
                 ("policy_and_target_update_period", C.c_int),
-                ("policy_noise", C.c_double), ("policy_noise_clip", C.c_double), ("max_act", C.c_double)]
+                ("policy_noise", C.c_double), ("policy_noise_clip", C.c_double), ("max_act", C.c_double),
+                ("her", C.c_int), ("her_sigma", C.c_double), ("min_act", C.c_double),
+                ("clip_return_l", C.c_double), ("clip_return_r", C.c_double)]
 
 
 class DiscConfig(C.Structure):

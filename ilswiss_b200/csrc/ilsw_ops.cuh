@@ -335,6 +335,7 @@ ILSW_HDN void row_critic_target(const Ctx& c, int b, int lane, int nl, bool use_
   float tq0 = wdot(S.h1t[0] + (size_t)b * Hd, c.tqf[0].p + c.tqf[0].oW2, Hd, lane, nl) + ldg(c.tqf[0].p + c.tqf[0].ob2);
   float tq1 = wdot(S.h1t[1] + (size_t)b * Hd, c.tqf[1].p + c.tqf[1].oW2, Hd, lane, nl) + ldg(c.tqf[1].p + c.tqf[1].ob2);
   float tmin = fminf(tq0, tq1);
+  if (c.hp.her) tmin = fminf(fmaxf(tmin, c.hp.clip_l), c.hp.clip_r);      // her/td3.py:116-120 (torch.clip)
   float rs = c.hp.reward_scale * ldg(S.rew + b);
   float inner = tmin;
   if (use_entropy) inner = tmin - ldg(&c.dyn->alpha) * ldg(S.logpi + b);
@@ -510,6 +511,13 @@ ILSW_HDN void row_td3_thead(const Ctx& c, const RunArgs& a, int s, int b, int la
   const SacBufs& S = c.s;
   const MlpPtrs& P = c.tpolicy;
   const int A = S.A, Hd = S.Hd, O = S.O;
+  if (c.hp.her) {     // her/td3.py:103-112: next action = clamp(sigma * N(0,1), min_act, max_act)
+    for (int j = lane; j < A; j += nl) {
+      float nz = c.hp.her_sigma * ldg(S.noise + (size_t)b * A + j);
+      S.Xna[(size_t)b * S.ld_oa + O + j] = fminf(fmaxf(nz, c.hp.min_act), c.hp.max_act);
+    }
+    return;
+  }
   const float* h = S.h1tp + (size_t)b * Hd;
   for (int j = 0; j < A; ++j) {
     float pre = wdot(h, P.p + P.oW2 + (size_t)j * Hd, Hd, lane, nl) + ldg(P.p + P.ob2 + j);
@@ -545,7 +553,12 @@ ILSW_HDN void row_td3_ploss(const Ctx& c, const RunArgs& a, int s, int b, int la
   const float* h = S.h1n[0] + (size_t)b * Hd;
   float q = wdot(h, Q.p + Q.oW2, Hd, lane, nl) + ldg(Q.p + Q.ob2);
   float dq = -1.0f / (float)S.B;
-  if (lane == 0) { S.qn[0][b] = q; S.plterm[b] = -q; }
+  float l2 = 0.f;
+  if (c.hp.her) {     // + mean(action^2) over B x A elements (her/td3.py:150-152)
+    for (int j = lane; j < S.A; j += nl) { float av = c.hp.max_act * ldg(S.act + (size_t)b * S.A + j); l2 += av * av; }
+    l2 = wsum(l2) / (float)S.A;
+  }
+  if (lane == 0) { S.qn[0][b] = q; S.plterm[b] = -q + l2; }
   float* e1 = S.e1[0] + (size_t)b * Hd;
   for (int k = lane; k < Hd; k += nl) e1[k] = (ldg(h + k) > 0.f) ? dq * ldg(Q.p + Q.oW2 + k) : 0.f;
 }
@@ -555,7 +568,9 @@ ILSW_HDN void row_td3_pibwd(const Ctx& c, const RunArgs& a, int s, int b, int la
   const int Hd = S.Hd, A = S.A;
   for (int j = lane; j < A; j += nl) {
     float t = ldg(S.act + (size_t)b * A + j);
-    S.dmean[(size_t)b * A + j] = ldg(S.dA[0] + (size_t)b * A + j) * c.hp.max_act * (1.0f - t * t);
+    float da = ldg(S.dA[0] + (size_t)b * A + j);
+    if (c.hp.her) da += 2.0f * c.hp.max_act * t / (float)(S.B * A);     // d mean(a^2) / da
+    S.dmean[(size_t)b * A + j] = da * c.hp.max_act * (1.0f - t * t);
   }
   wsync();
   const float* h = S.h1p + (size_t)b * Hd;

@@ -346,10 +346,12 @@ inline void build_td3(Builder& b, const Ctx& c) {
   b.phase(); b.row(ROW_TD3_GATHER, B);
   b.phase();
   for (int i = 0; i < 2; ++i) b.fwd(S.Xoa, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0q[i], Hd, ACT_RELU);
-  b.fwd(S.Xna, S.ld_oa, B, O, TP.p + TP.oW0, TP.p + TP.ob0, Hd, S.h0tp, Hd, ACT_RELU);
+  // HER-TD3 overwrites the target policy's action with clipped noise (her/td3.py:103-112): its forward pass is dead code
+  const bool her = c.hp.her != 0;
+  if (!her) b.fwd(S.Xna, S.ld_oa, B, O, TP.p + TP.oW0, TP.p + TP.ob0, Hd, S.h0tp, Hd, ACT_RELU);
   b.phase();
   for (int i = 0; i < 2; ++i) b.fwd(S.h0q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1q[i], Hd, ACT_RELU);
-  b.fwd(S.h0tp, Hd, B, Hd, TP.p + TP.oW1, TP.p + TP.ob1, Hd, S.h1tp, Hd, ACT_RELU);
+  if (!her) b.fwd(S.h0tp, Hd, B, Hd, TP.p + TP.oW1, TP.p + TP.ob1, Hd, S.h1tp, Hd, ACT_RELU);
   b.phase(); b.row(ROW_TD3_THEAD, B);
   b.phase();
   for (int i = 0; i < 2; ++i) b.fwd(S.Xna, S.ld_oa, B, K0, c.tqf[i].p + c.tqf[i].oW0, c.tqf[i].p + c.tqf[i].ob0, Hd, S.h0t[i], Hd, ACT_RELU);
@@ -492,6 +494,9 @@ inline Hyper make_hyper(const ilsw_trainer_config& cfg) {
   h.period = cfg.policy_and_target_update_period > 0 ? cfg.policy_and_target_update_period : 1;
   h.policy_noise = (float)cfg.policy_noise; h.noise_clip = (float)cfg.policy_noise_clip;
   h.max_act = cfg.max_act != 0 ? (float)cfg.max_act : 1.0f;
+  h.her = cfg.algo == ILSW_ALGO_TD3 ? cfg.her : 0;
+  h.her_sigma = (float)cfg.her_sigma; h.min_act = (float)cfg.min_act;
+  h.clip_l = (float)cfg.clip_return_l; h.clip_r = (float)cfg.clip_return_r;
   return h;
 }
 

@@ -239,6 +239,7 @@ ILSW_HD SPtr warp_scratch(const RowEnv& e) {
 }
 
 ILSW_HD bool fast_rows_ok(const Ctx& c) {
+  if (c.hp.her) return false;     // HER-TD3 rows exist in the generic form only (ilsw_ops.cuh)
   return c.s.Hd <= kFastMaxHid && (c.s.Hd & 3) == 0 && c.s.A <= kFastMaxAct && 4 * c.s.A * c.s.Hd <= kRowStageFloats &&
          (!c.hp.has_disc || (c.d.Hd <= kFastMaxHid && (c.d.Hd & 3) == 0));
 }

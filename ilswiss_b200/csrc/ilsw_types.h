@@ -168,6 +168,8 @@ struct Hyper {
   float fixed_alpha;
   // td3
   int period; float policy_noise, noise_clip, max_act;
+  // HER-TD3 (her/td3.py): see ilsw_trainer_config
+  int her; float her_sigma, min_act, clip_l, clip_r;
   // disc
   int has_disc; int disc_mode;    // 0 airl 1 gail 2 gail2 3 fairl
   double disc_lr, disc_beta1; float gp_weight, disc_clamp; int use_gp;

@@ -1,7 +1,9 @@
 """Drop-in Trainer classes (rlkit/core/trainer.py:4-28 interface) backed by the fused engine.
 
     SoftActorCritic  <->  rlkit/torch/algorithms/sac/sac_alpha.py:13-284
+    SoftActorCriticV <->  rlkit/torch/algorithms/sac/sac.py:13-243
     TD3              <->  rlkit/torch/algorithms/td3/td3.py:13-223
+    HerTD3           <->  rlkit/torch/algorithms/her/td3.py:14-245
 
 Same constructor signatures, same attributes read from outside (.policy, .networks,
 .eval_statistics, get_eval_statistics(), end_epoch(), get_snapshot(), load_snapshot(), to()),
@@ -401,8 +403,12 @@ class TD3(_FusedTrainer):
         cfg.policy_noise = float(getattr(policy, "noise", 0.1))
         cfg.policy_noise_clip = float(getattr(policy, "noise_clip", 0.5))
         cfg.max_act = float(getattr(policy, "max_act", 1.0))
+        self._configure(cfg, policy, kwargs)
         self._finish_init(cfg, list(self._arenas.values()))
         self.eval_statistics = None
+
+    def _configure(self, cfg, policy, kwargs):
+        pass
 
     @property
     def _n_train_steps_total(self):
@@ -456,3 +462,38 @@ class TD3(_FusedTrainer):
                     mine.state[p_dst] = src.state[p_src]
             st.adam_step[slot] = self._load_optimizer(mine, self._arenas[arena])
         self.engine.set_state(st)
+
+
+class HerTD3(TD3):
+    """rlkit/torch/algorithms/her/td3.py:14-245 -- goal-conditioned TD3 (exp_specs/her/her_*_td3.yaml through
+    run_scripts/her_td3_exp_script.py:69-88).  Networks take cat(observation, desired_goal); the three differences from
+    TD3 are those of the reference (her/td3.py:103-112, :116-120, :150-152): the next action is the clipped noise alone
+    (`clamp(sigma * N(0,1), min_act, max_act)` -- the target policy's output is overwritten there), the min target Q is
+    clipped to [clip_return_l, clip_return_r], and the policy loss carries + mean(action^2).
+
+    train_step(batch) takes the reference's goal-conditioned batch (keys desired_goals / next_desired_goals next to the
+    usual five) and concatenates on the device; train_from_buffer() works on a DeviceReplayBuffer whose rows already
+    hold cat(obs, goal) (observation_dim = obs_dim + goal_dim)."""
+
+    def __init__(self, policy, qf1, qf2, clip_return_l=None, clip_return_r=None, **kwargs):
+        self._her_clip = (clip_return_l, clip_return_r)
+        super().__init__(policy, qf1, qf2, **kwargs)
+        self.clip_return_l, self.clip_return_r = self._cfg.clip_return_l, self._cfg.clip_return_r
+
+    def _configure(self, cfg, policy, kwargs):
+        cl, cr = self._her_clip
+        gamma_sum = 1.0 / (1.0 - cfg.discount)                       # her/td3.py:81-85
+        cfg.her = 1
+        cfg.her_sigma = float(getattr(policy, "sigma", 0.2))         # target_policy.sigma (policies.py:506)
+        cfg.min_act = float(getattr(policy, "min_act", -1.0))
+        cfg.clip_return_l = -gamma_sum if cl is None else float(cl)
+        cfg.clip_return_r = 0.0 if cr is None else float(cr)
+
+    def train_step(self, batch):
+        if "desired_goals" in batch:
+            def dev(x):
+                return torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(device="cuda", dtype=torch.float32)
+            batch = dict(batch)
+            batch["observations"] = torch.cat([dev(batch["observations"]), dev(batch["desired_goals"])], dim=-1)
+            batch["next_observations"] = torch.cat([dev(batch["next_observations"]), dev(batch["next_desired_goals"])], dim=-1)
+        super().train_step(batch)

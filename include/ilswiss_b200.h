@@ -110,6 +110,11 @@ typedef struct {
   /* TD3: policy MODULE noise parameters (policies.py:150-152), td3.py:113 period */
   int policy_and_target_update_period;
   double policy_noise, policy_noise_clip, max_act;
+  /* HER-TD3 (rlkit/torch/algorithms/her/td3.py:88-160; observations are cat(obs, desired_goal)): target action =
+   * clamp(her_sigma * N(0,1), min_act, max_act) (:103-112 -- the target policy's output is overwritten), min target Q
+   * clipped to [clip_return_l, clip_return_r] (:116-120), policy loss + mean(action^2) (:150-152). */
+  int her;
+  double her_sigma, min_act, clip_return_l, clip_return_r;
 } ilsw_trainer_config;
 
 typedef struct {

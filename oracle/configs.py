@@ -28,6 +28,18 @@ CASES = {
                        td3=dict(reward_scale=1.0, discount=0.99, soft_target_tau=0.005,
                                 policy_lr=3e-4, qf_lr=3e-4, policy_and_target_update_period=2),
                        policy_noise=0.2, policy_noise_clip=0.5, seed=16),
+    # exp_specs/her/her_reach_td3.yaml -> her/td3.py: obs_dim = observation (10) + desired_goal (3); policy_lr 6e-4
+    "her_td3_reach": dict(algo="td3", obs_dim=13, act_dim=4, batch=256, n_fill=20000, steps=5,
+                          her=dict(goal_dim=3, sigma=0.2),
+                          td3=dict(reward_scale=1.0, discount=0.99, soft_target_tau=0.005, policy_lr=6e-4,
+                                   qf_lr=3e-4, policy_and_target_update_period=2),
+                          policy_noise=0.2, policy_noise_clip=0.5, seed=25),
+    # the yamls' net_size 300 (not a multiple of the 32-wide tile) and a narrow return clip
+    "her_td3_h300": dict(algo="td3", obs_dim=13, act_dim=4, batch=128, n_fill=4000, steps=4, hidden=300,
+                         her=dict(goal_dim=3, sigma=0.3, clip_return_l=-0.05, clip_return_r=0.02),
+                         td3=dict(reward_scale=1.0, discount=0.98, soft_target_tau=0.005, policy_lr=6e-4,
+                                  qf_lr=3e-4, policy_and_target_update_period=2),
+                         policy_noise=0.2, policy_noise_clip=0.5, seed=26),
     # exp_specs/gail/gail_walker.yaml (gail2, grad_pen 8, reward_scale 2, beta_1 0.25)
     "gail_walker": dict(algo="adv_irl", obs_dim=17, act_dim=6, batch=256, n_fill=20000,
                         n_expert=4000, steps=4, mode="gail2",

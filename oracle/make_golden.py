@@ -128,7 +128,13 @@ def run_reference(case):
     mods["qf1"], mods["qf2"] = mk_q(), mk_q()
     if algo == "sac_v":
         mods["vf"] = ref.FlattenMlp(hidden_sizes=list(HID), input_size=O, output_size=1)
-    if algo == "td3":
+    her = case.get("her")
+    if her:
+        mods["policy"] = ref.MlpGaussianAndEpsilonConditionPolicy(
+            hidden_sizes=list(HID), action_space=ref_shim.FakeEnv(O, A).action_space, obs_dim=O - her["goal_dim"],
+            condition_dim=her["goal_dim"], action_dim=A, output_activation=torch.tanh, max_sigma=her["sigma"],
+            min_sigma=her["sigma"])
+    elif algo == "td3":
         mods["policy"] = ref.MlpGaussianNoisePolicy(
             hidden_sizes=list(HID), obs_dim=O, action_dim=A, output_activation=torch.tanh,
             policy_noise=case["policy_noise"], policy_noise_clip=case["policy_noise_clip"])
@@ -145,6 +151,9 @@ def run_reference(case):
         trainer = ref.SacAlpha(policy=mods["policy"], qf1=mods["qf1"], qf2=mods["qf2"], env=env, **case["sac"])
     elif algo == "sac_v":
         trainer = ref.SacV(policy=mods["policy"], qf1=mods["qf1"], qf2=mods["qf2"], vf=mods["vf"], **case["sac"])
+    elif her:
+        trainer = ref.HerTD3(policy=mods["policy"], qf1=mods["qf1"], qf2=mods["qf2"], clip_return_l=her.get("clip_return_l"),
+                             clip_return_r=her.get("clip_return_r"), **case["td3"])
     else:
         trainer = ref.TD3(policy=mods["policy"], qf1=mods["qf1"], qf2=mods["qf2"], **case["td3"])
 
@@ -177,6 +186,12 @@ def run_reference(case):
         else:
             trainer.end_epoch()
             batch = ref.np_to_pytorch_batch(buf.random_batch(B))
+            if her:     # the relabel buffer hands goals over separately; the trainer concatenates them (her/td3.py:94-98)
+                G_ = her["goal_dim"]
+                batch["desired_goals"] = batch["observations"][:, O - G_:]
+                batch["next_desired_goals"] = batch["next_observations"][:, O - G_:]
+                batch["observations"] = batch["observations"][:, :O - G_]
+                batch["next_observations"] = batch["next_observations"][:, :O - G_]
             trainer.train_step(batch)
             st = trainer.get_eval_statistics()
             for k in ["QF1 Loss", "QF2 Loss", "VF Loss", "Policy Loss", "Alpha Loss", "Alpha Mean",
@@ -213,6 +228,10 @@ def run_oracle(case):
         tr = R.SacAlphaOracle(nets["policy"], nets["qf1"], nets["qf2"], A, **case["sac"])
     elif algo == "sac_v":
         tr = R.SacVOracle(nets["policy"], nets["qf1"], nets["qf2"], nets["vf"], **case["sac"])
+    elif case.get("her"):
+        h = case["her"]
+        tr = R.HerTD3Oracle(nets["policy"], nets["qf1"], nets["qf2"], sigma=h["sigma"], clip_return_l=h.get("clip_return_l"),
+                            clip_return_r=h.get("clip_return_r"), **case["td3"])
     else:
         tr = R.TD3Oracle(nets["policy"], nets["qf1"], nets["qf2"], policy_noise=case["policy_noise"],
                          policy_noise_clip=case["policy_noise_clip"], **case["td3"])

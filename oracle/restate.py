@@ -531,6 +531,58 @@ class TD3Oracle:
 
 
 # --------------------------------------------------------------------------------------
+# HER-TD3 (rlkit/torch/algorithms/her/td3.py:88-160).  Observations are cat(obs, desired_goal) /
+# cat(next_obs, next_desired_goal) (:97-98); everything else as TD3 except the three marked lines.
+# --------------------------------------------------------------------------------------
+class HerTD3Oracle(TD3Oracle):
+    def __init__(self, policy, qf1, qf2, sigma=0.2, min_act=-1.0, max_act=1.0, clip_return_l=None,
+                 clip_return_r=None, **kw):
+        kw.pop("policy_noise", None), kw.pop("policy_noise_clip", None)
+        super().__init__(policy, qf1, qf2, **kw)
+        self.sigma, self.min_act, self.max_act = sigma, min_act, max_act
+        gamma_sum = 1.0 / (1.0 - self.discount)                      # :81-85
+        self.clip_l = -gamma_sum if clip_return_l is None else clip_return_l
+        self.clip_r = 0.0 if clip_return_r is None else clip_return_r
+
+    def train_step(self, batch, noise):
+        rewards = self.reward_scale * batch["rewards"]
+        terminals, obs = batch["terminals"], batch["observations"]
+        actions, next_obs = batch["actions"], batch["next_observations"]
+        w1, w2, wp = self.qf1.leaves(), self.qf2.leaves(), self.policy.leaves()
+        with torch.no_grad():
+            tw1 = list(self.target_qf1.p.values())
+            tw2 = list(self.target_qf2.p.values())
+            # :103-112 -- `noisy_next_actions = clamp(noise, min_act, max_act)`: the target policy's action is
+            # overwritten, the next action is the clipped noise alone
+            na = torch.clamp(self.sigma * noise, self.min_act, self.max_act)
+            tq = torch.clip(torch.min(q_forward(tw1, next_obs, na), q_forward(tw2, next_obs, na)),
+                            self.clip_l, self.clip_r)                # :116-120
+            q_target = rewards + (1.0 - terminals) * self.discount * tq
+        q1_pred = q_forward(w1, obs, actions)
+        qf1_loss = ((q1_pred - q_target) ** 2).mean()
+        q2_pred = q_forward(w2, obs, actions)
+        qf2_loss = ((q2_pred - q_target) ** 2).mean()
+        g1 = torch.autograd.grad(qf1_loss, w1)
+        adam_update(self.qf1, g1, self.qf_lr, 0.9)
+        g2 = torch.autograd.grad(qf2_loss, w2)
+        adam_update(self.qf2, g2, self.qf_lr, 0.9)
+        policy_loss = None
+        if self.n_total % self.period == 0:
+            w1n = [t.detach() for t in self.qf1.p.values()]
+            pa = td3_policy_forward(wp, obs, None, max_act=self.max_act)
+            policy_loss = -q_forward(w1n, obs, pa).mean() + torch.square(pa).mean()      # :150-152
+            gp = torch.autograd.grad(policy_loss, wp)
+            adam_update(self.policy, gp, self.policy_lr, 0.9)
+            polyak(self.policy, self.target_policy, self.tau)
+            polyak(self.qf1, self.target_qf1, self.tau)
+            polyak(self.qf2, self.target_qf2, self.tau)
+        self.n_total += 1
+        return dict(qf1_loss=float(qf1_loss), qf2_loss=float(qf2_loss),
+                    policy_loss=None if policy_loss is None else float(policy_loss),
+                    q1_pred=q1_pred.detach().numpy().ravel(), q_target=q_target.numpy().ravel())
+
+
+# --------------------------------------------------------------------------------------
 # D1 + D2: AdvIRL discriminator step and reward relabel (adv_irl.py:133-314)
 # --------------------------------------------------------------------------------------
 def disc_reward(logits, mode, rew_clip_min=None, rew_clip_max=None):

@@ -151,6 +151,12 @@ def trainer_config(case, max_steps=64, precision=0):
         cfg.alpha = 1.0
         cfg.policy_and_target_update_period = kw["policy_and_target_update_period"]
         cfg.policy_noise, cfg.policy_noise_clip = case["policy_noise"], case["policy_noise_clip"]
+        if case.get("her"):
+            h = case["her"]
+            cfg.her, cfg.her_sigma, cfg.min_act = 1, h["sigma"], -1.0
+            cl, cr = h.get("clip_return_l"), h.get("clip_return_r")
+            cfg.clip_return_l = -1.0 / (1.0 - kw["discount"]) if cl is None else cl
+            cfg.clip_return_r = 0.0 if cr is None else cr
     elif algo == "sac_v":
         kw = case["sac"]
         cfg.algo = _abi.ALGO_SAC_V

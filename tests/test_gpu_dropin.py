@@ -143,6 +143,50 @@ def test_td3_trainer_dropin():
     assert tr._n_train_steps_total == case["steps"]
 
 
+def test_her_td3_trainer_dropin():
+    """her/td3.py through the drop-in class: goal-conditioned batches via train_step (desired_goals keys), and the
+    in-HBM path on a ring whose rows hold cat(obs, goal); both against the oracle (bit-identical to the reference)."""
+    from ilswiss_b200.replay_buffer import DeviceReplayBuffer
+    from ilswiss_b200.trainers import HerTD3
+
+    torch.set_num_threads(1)
+    case = CFG.CASES["her_td3_reach"]
+    her, O, A, B = case["her"], case["obs_dim"], case["act_dim"], case["batch"]
+    G_ = her["goal_dim"]
+    rows, final, _ = G.run_oracle(case)
+    inj_np = case_injection(case)
+    data, _ = case_data(case)
+
+    def make():
+        mods, _ = build_modules(case)
+        mods["policy"].sigma, mods["policy"].min_act = her["sigma"], -1.0
+        return HerTD3(mods["policy"], mods["qf1"], mods["qf2"], batch_size=B, gemm_precision=3, **case["td3"]), mods
+
+    # (a) in-HBM ring path, injected indices / noise
+    tr, mods = make()
+    assert tr.clip_return_l == pytest.approx(-100.0) and tr.clip_return_r == 0.0
+    buf = DeviceReplayBuffer(case["n_fill"], O, A, random_seed=1)
+    fill(buf, data)
+    tr.train_from_buffer(buf, case["steps"], inject={k: torch.from_numpy(v).cuda() for k, v in inj_np.items()})
+    L = tr.engine.losses(case["steps"])
+    for t, row in enumerate(rows):
+        assert abs(L[t, 0] - row["QF1 Loss"]) <= 1e-4 * max(abs(row["QF1 Loss"]), 1e-2)
+        if row.get("Policy Loss") is not None:
+            assert abs(L[t, 2] - row["Policy Loss"]) <= 1e-4 * max(abs(row["Policy Loss"]), 1.0)
+    got = np.concatenate([p.detach().cpu().numpy().ravel() for p in mods["policy"].parameters()])
+    assert np.max(np.abs(got - final["policy"])) < 2 * 6e-4 * case["steps"] + 1e-6
+    # (b) the reference's batch interface: goals handed over separately, one step per call (Philox target noise)
+    tr2, _ = make()
+    idx = inj_np["idx"][0]
+    b = dict(observations=data["observations"][idx][:, :O - G_], desired_goals=data["observations"][idx][:, O - G_:],
+             next_observations=data["next_observations"][idx][:, :O - G_], next_desired_goals=data["next_observations"][idx][:, O - G_:],
+             actions=data["actions"][idx], rewards=data["rewards"][idx].reshape(B, 1), terminals=data["terminals"][idx].reshape(B, 1))
+    tr2.train_step(b)
+    st = tr2.get_eval_statistics()
+    assert np.isfinite(st["QF1 Loss"]) and "Q Targets Mean" in st
+    assert st["Q Targets Max"] <= float(np.max(data["rewards"][idx])) + 1e-5          # min target Q is clipped to <= 0
+
+
 def test_replay_buffer_dropin_matches_reference_semantics():
     from ilswiss_b200.replay_buffer import DeviceReplayBuffer
 
