@@ -30,6 +30,8 @@ WORKLOADS = {
     "sac_ant": dict(algo="sac", O=111, A=8, B=256, N=1_000_000, target_entropy=-4.0, reward_scale=1.0, beta_1=0.9),
     "gail_walker": dict(algo="gail", O=17, A=6, B=256, N=20_000, NE=4000, target_entropy=None, reward_scale=2.0, beta_1=0.25),
     "td3_humanoid": dict(algo="td3", O=376, A=17, B=1024, N=2_000_000),
+    # exp_specs/her/her_pick_td3.yaml (her/td3.py): FetchPickAndPlace observation 25 + desired_goal 3, act 4, batch 4096, net_size 300
+    "her_td3_pick": dict(algo="td3", her=True, O=28, A=4, B=4096, N=1_000_000, H=300),
 }
 H, DH = 256, 128
 LAUNCH = 1000   # gradient steps per kernel launch (num_train_steps_per_train_call of sac_hopper.yaml:20)
@@ -38,6 +40,7 @@ LAUNCH = 1000   # gradient steps per kernel launch (num_train_steps_per_train_ca
 def algorithmic_bytes_per_step(w):
     """24*P_trainable_updated + 8*P_target_updated + 4*B*(2O+A+2) (+ disc)."""
     O, A, B = w["O"], w["A"], w["B"]
+    H = w.get("H", 256)
     Pq = (O + A) * H + H + H * H + H + H + 1
     if w["algo"] == "td3":
         Pp = O * H + H + H * H + H + H * A + A
@@ -92,13 +95,20 @@ def build_ours(w, seed, steps_per_launch):
 
     torch.manual_seed(seed)
     O, A, B = w["O"], w["A"], w["B"]
+    H = w.get("H", 256)
     qf1 = modules.FlattenMlp([H, H], 1, O + A)
     qf2 = modules.FlattenMlp([H, H], 1, O + A)
     if w["algo"] == "td3":
         policy = modules.DeterministicNoisePolicy([H, H], O, A, policy_noise=0.2, policy_noise_clip=0.5)
-        tr = trainers.TD3(policy, qf1, qf2, reward_scale=1.0, discount=0.99, policy_lr=3e-4, qf_lr=3e-4,
-                          policy_and_target_update_period=2, soft_target_tau=0.005, batch_size=B,
-                          max_steps_per_call=steps_per_launch)
+        if w.get("her"):
+            policy.sigma, policy.min_act = 0.2, -1.0
+            tr = trainers.HerTD3(policy, qf1, qf2, reward_scale=1.0, discount=0.99, policy_lr=6e-4, qf_lr=3e-4,
+                                 policy_and_target_update_period=2, soft_target_tau=0.005, batch_size=B,
+                                 max_steps_per_call=steps_per_launch)
+        else:
+            tr = trainers.TD3(policy, qf1, qf2, reward_scale=1.0, discount=0.99, policy_lr=3e-4, qf_lr=3e-4,
+                              policy_and_target_update_period=2, soft_target_tau=0.005, batch_size=B,
+                              max_steps_per_call=steps_per_launch)
     else:
         policy = modules.TanhGaussianPolicy([H, H], O, A)
         tr = trainers.SoftActorCritic(policy, qf1, qf2, reward_scale=w["reward_scale"], discount=0.99, policy_lr=3e-4,
@@ -153,6 +163,7 @@ def time_cpu_port(w, steps, warmup, threads):
 
     torch.set_num_threads(threads)
     O, A, B = w["O"], w["A"], w["B"]
+    H = w.get("H", 256)
     n = min(w["N"], 1_000_000)
     rs = np.random.RandomState(0)
     nets = dict(qf1=R.Net(R.init_mlp(rs, O + A, (H, H), 1)), qf2=R.Net(R.init_mlp(rs, O + A, (H, H), 1)))
@@ -162,7 +173,10 @@ def time_cpu_port(w, steps, warmup, threads):
     disc = ebuf = None
     if w["algo"] == "td3":
         nets["policy"] = R.Net(R.init_mlp(rs, O, (H, H), A, init_w=1e-3))
-        tr = R.TD3Oracle(nets["policy"], nets["qf1"], nets["qf2"], policy_lr=3e-4, qf_lr=3e-4)
+        if w.get("her"):
+            tr = R.HerTD3Oracle(nets["policy"], nets["qf1"], nets["qf2"], sigma=0.2, policy_lr=6e-4, qf_lr=3e-4)
+        else:
+            tr = R.TD3Oracle(nets["policy"], nets["qf1"], nets["qf2"], policy_lr=3e-4, qf_lr=3e-4)
     else:
         nets["policy"] = R.Net(R.init_mlp(rs, O, (H, H), A, init_w=1e-3, log_std_head=True))
         tr = R.SacAlphaOracle(nets["policy"], nets["qf1"], nets["qf2"], A, reward_scale=w["reward_scale"], policy_lr=3e-4,
@@ -238,9 +252,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     K, W = args.steps, max(args.warmup, 3)
-    metric = "%s gradient-steps/sec at batch %d" % ({"sac": "SAC", "gail": "GAIL (adv_irl)", "td3": "TD3"}[w["algo"]], w["B"])
+    metric = "%s gradient-steps/sec at batch %d" % ("HER-TD3" if w.get("her") else {"sac": "SAC", "gail": "GAIL (adv_irl)", "td3": "TD3"}[w["algo"]], w["B"])
     config = {"workload": "%s: obs=%d act=%d batch=%d, %d-transition HBM replay ring, 2x%d MLPs, %d gradient steps per kernel launch"
-              % (args.workload, w["O"], w["A"], w["B"], w["N"], H, LAUNCH), "parallelism": "replicas x%d" % max(world, args.gpus),
+              % (args.workload, w["O"], w["A"], w["B"], w["N"], w.get("H", 256), LAUNCH), "parallelism": "replicas x%d" % max(world, args.gpus),
               "global_batch": w["B"] * max(world, 1)}
 
     if args.impl == "reference":

@@ -82,26 +82,45 @@ __global__ void __launch_bounds__(256) rb_scatter_kernel(const float* __restrict
   if (lane < 4) cold[slot * 4 + lane] = lane < 3 ? src[hot + lane] : 0.f;
 }
 
-// one warp per sampled row, 128-bit loads/stores (stride is a multiple of 4 floats)
+// R3/R4: uniform sample + minibatch gather.  A group of LPR lanes (8 / 16 / 32, chosen from the row length) owns one sampled
+// row; rows are 16-byte aligned (stride % 4 == 0), so every access is a 128-bit ld.global.nc / st.global and the lanes
+// of a group read consecutive 16-byte vectors of the same row (coalesced 128..512-byte segments -- the rows themselves
+// are random HBM addresses).  Up to kGatherUnroll vectors per lane are loaded before the first store, so a 3 KB Humanoid row is
+// one round trip per lane instead of seven dependent ones.  Optional in-kernel Philox index (speed mode).
+constexpr int kGatherUnroll = 8;
+template <int LPR>
 __global__ void __launch_bounds__(256) rb_gather_kernel(const float* __restrict__ rows, const float* __restrict__ cold,
                                                          const int32_t* __restrict__ idx, int B, int stride,
                                                          float* out_hot, float* out_cold, int64_t size, uint64_t seed,
                                                          uint64_t counter, int32_t* idx_out) {
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  constexpr int kRowsPerCta = 256 / LPR;
+  const int sub = threadIdx.x % LPR;
+  const int b = blockIdx.x * kRowsPerCta + threadIdx.x / LPR;
   if (b >= B) return;
   int64_t r;
   if (idx) r = idx[b];
   else {
     r = philox_index(seed, (uint32_t)counter, (uint32_t)b, (uint32_t)(counter >> 32) + 0x51u, (int)size);
-    if (idx_out && lane == 0) idx_out[b] = (int32_t)r;
+    if (idx_out && sub == 0) idx_out[b] = (int32_t)r;
   }
   const float4* src = reinterpret_cast<const float4*>(rows + r * stride);
   float4* dst = reinterpret_cast<float4*>(out_hot + (size_t)b * stride);
-  for (int k = lane; k < (stride >> 2); k += 32) dst[k] = __ldg(src + k);
-  if (out_cold && lane == 0)
+  const int nv = stride >> 2;
+  for (int k0 = sub; k0 < nv; k0 += LPR * kGatherUnroll) {
+    float4 v[kGatherUnroll];
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; ++u)
+      if (k0 + u * LPR < nv) v[u] = __ldg(src + k0 + u * LPR);
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; ++u)
+      if (k0 + u * LPR < nv) dst[k0 + u * LPR] = v[u];
+  }
+  if (out_cold && sub == 0)
     reinterpret_cast<float4*>(out_cold)[b] = __ldg(reinterpret_cast<const float4*>(cold) + r);
 }
+
+static void launch_gather(const ilsw_rb* rb, const int32_t* idx, int B, float* out_hot, float* out_cold, uint64_t seed,
+                          uint64_t counter, int32_t* idx_out, cudaStream_t st);
 
 extern "C" int ilsw_rb_create(ilsw_rb** out, int64_t capacity, int obs_dim, int act_dim) {
   if (!out || capacity <= 0 || obs_dim <= 0 || act_dim <= 0) return fail(ILSW_ERR_ARG, "rb_create: bad arguments");
@@ -218,13 +237,23 @@ extern "C" int ilsw_rb_load_device(ilsw_rb* rb, const float* dev_hot_rows, int64
   return ILSW_OK;
 }
 
+static void launch_gather(const ilsw_rb* rb, const int32_t* idx, int B, float* out_hot, float* out_cold, uint64_t seed,
+                          uint64_t counter, int32_t* idx_out, cudaStream_t st) {
+  const int nv = rb->stride >> 2;           // 16-byte vectors per row: Hopper 7, Walker 11, Ant 58, Humanoid 193
+  if (nv <= 8)
+    rb_gather_kernel<8><<<(B + 31) / 32, 256, 0, st>>>(rb->rows, rb->cold, idx, B, rb->stride, out_hot, out_cold, rb->size, seed, counter, idx_out);
+  else if (nv <= 16)
+    rb_gather_kernel<16><<<(B + 15) / 16, 256, 0, st>>>(rb->rows, rb->cold, idx, B, rb->stride, out_hot, out_cold, rb->size, seed, counter, idx_out);
+  else
+    rb_gather_kernel<32><<<(B + 7) / 8, 256, 0, st>>>(rb->rows, rb->cold, idx, B, rb->stride, out_hot, out_cold, rb->size, seed, counter, idx_out);
+}
+
 extern "C" int ilsw_rb_gather(ilsw_rb* rb, const int32_t* idx_dev, int B, float* out_hot, float* out_cold, void* stream) {
   if (!rb || !idx_dev || !out_hot || B <= 0) return fail(ILSW_ERR_ARG, "rb_gather: bad arguments");
   int rc = ilsw_rb_commit(rb, stream);
   if (rc) return rc;
   if (rb->size == 0) return fail(ILSW_ERR_STATE, "rb_gather: empty ring");
-  rb_gather_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(rb->rows, rb->cold, idx_dev, B, rb->stride, out_hot,
-                                                                   out_cold, rb->size, 0, 0, nullptr);
+  launch_gather(rb, idx_dev, B, out_hot, out_cold, 0, 0, nullptr, (cudaStream_t)stream);
   CU(cudaGetLastError());
   return ILSW_OK;
 }
@@ -235,8 +264,7 @@ extern "C" int ilsw_rb_sample(ilsw_rb* rb, int B, uint64_t seed, uint64_t counte
   int rc = ilsw_rb_commit(rb, stream);
   if (rc) return rc;
   if (rb->size == 0) return fail(ILSW_ERR_STATE, "rb_sample: empty ring");
-  rb_gather_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(rb->rows, rb->cold, nullptr, B, rb->stride, out_hot,
-                                                                   nullptr, rb->size, seed, counter, idx_out_dev);
+  launch_gather(rb, nullptr, B, out_hot, nullptr, seed, counter, idx_out_dev, (cudaStream_t)stream);
   CU(cudaGetLastError());
   return ILSW_OK;
 }
