@@ -406,6 +406,26 @@ def main():
         sampler = {"get_actions_us": ours_us, "eager_module_get_actions_us": eager_us, "env_num": 4,
                    "note": "host numpy obs -> host numpy actions, stochastic; eager = the nn.Module forward the reference's eval_np runs on the same GPU"}
 
+    # ---- the replay ring's own kernel against the HBM roofline: in-kernel Philox sample + gather of a LARGE batch from this
+    # workload's ring (the per-step batch of B rows is gathered inside the engine kernel; this is what the kernel sustains)
+    replay = None
+    if world == 1:
+        rows_n = (1 << 20) if buf.ring.stride <= 64 else (1 << 18)
+        for _ in range(3):
+            buf.ring.sample(rows_n, 7, 1)
+        ts = []
+        for i in range(10):
+            flush.zero_()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(); out = buf.ring.sample(rows_n, 7, 2 + i); g1.record()
+            torch.cuda.synchronize()
+            ts.append(g0.elapsed_time(g1))
+            del out
+        gms = float(np.median(ts))
+        gby = rows_n * buf.ring.stride * 4 * 2 + rows_n * 4
+        replay = {"kernel": "rb_gather_kernel (Philox sample + gather)", "rows": rows_n, "row_bytes": buf.ring.stride * 4, "ms": gms,
+                  "algorithmic_bytes": gby, "achieved": gby / gms / 1e6, "unit": "GB/s", "l2": "flushed before every timed launch"}
+
     # ---- the same metric in the other GEMM precision modes (short runs, same timing method)
     by_prec = {}
     if world == 1 and args.precision is None:
@@ -458,6 +478,9 @@ def main():
                          "traffic": traffic, "peak_source": peak_src, "kernel": "ilsw_engine_kernel",
                          "algorithmic_bytes_per_launch": bytes_step * launch, "launch_ms": ms_per_launch},
             "clocks": clocks}
+    if replay is not None:
+        replay["peak"], replay["frac"] = peak, replay["achieved"] / peak
+        line["replay_roofline"] = replay
     if world == 1 and not args.no_cpu_baseline:
         cores = best_cpu_threads(w)
         n_cpu = 600 if w["algo"] != "td3" else 250

@@ -85,10 +85,8 @@ __global__ void __launch_bounds__(256) rb_scatter_kernel(const float* __restrict
 // R3/R4: uniform sample + minibatch gather.  A group of LPR lanes (8 / 16 / 32, chosen from the row length) owns one sampled
 // row; rows are 16-byte aligned (stride % 4 == 0), so every access is a 128-bit ld.global.nc / st.global and the lanes
 // of a group read consecutive 16-byte vectors of the same row (coalesced 128..512-byte segments -- the rows themselves
-// are random HBM addresses).  Up to kGatherUnroll vectors per lane are loaded before the first store, so a 3 KB Humanoid row is
-// one round trip per lane instead of seven dependent ones.  Optional in-kernel Philox index (speed mode).
-constexpr int kGatherUnroll = 8;
-template <int LPR>
+// are random HBM addresses).  Rows of 17..64 vectors (Ant) keep two loads per lane in flight before the first store.  Optional in-kernel Philox index (speed mode).
+template <int LPR, int kGatherUnroll>
 __global__ void __launch_bounds__(256) rb_gather_kernel(const float* __restrict__ rows, const float* __restrict__ cold,
                                                          const int32_t* __restrict__ idx, int B, int stride,
                                                          float* out_hot, float* out_cold, int64_t size, uint64_t seed,
@@ -240,12 +238,21 @@ extern "C" int ilsw_rb_load_device(ilsw_rb* rb, const float* dev_hot_rows, int64
 static void launch_gather(const ilsw_rb* rb, const int32_t* idx, int B, float* out_hot, float* out_cold, uint64_t seed,
                           uint64_t counter, int32_t* idx_out, cudaStream_t st) {
   const int nv = rb->stride >> 2;           // 16-byte vectors per row: Hopper 7, Walker 11, Ant 58, Humanoid 193
-  if (nv <= 8)
-    rb_gather_kernel<8><<<(B + 31) / 32, 256, 0, st>>>(rb->rows, rb->cold, idx, B, rb->stride, out_hot, out_cold, rb->size, seed, counter, idx_out);
+  static const bool v1 = getenv("ILSW_GATHER_V1") != nullptr;   // development aid (tools/replay_bench.py): warp per row, no batching
+  if (v1)
+    rb_gather_kernel<32, 1><<<(B + 7) / 8, 256, 0, st>>>(rb->rows, rb->cold, idx, B, rb->stride, out_hot, out_cold, rb->size, seed, counter, idx_out);
+  else if (nv <= 8)
+    rb_gather_kernel<8, 1><<<(B + 31) / 32, 256, 0, st>>>(rb->rows, rb->cold, idx, B, rb->stride, out_hot, out_cold, rb->size, seed, counter, idx_out);
   else if (nv <= 16)
-    rb_gather_kernel<16><<<(B + 15) / 16, 256, 0, st>>>(rb->rows, rb->cold, idx, B, rb->stride, out_hot, out_cold, rb->size, seed, counter, idx_out);
-  else
-    rb_gather_kernel<32><<<(B + 7) / 8, 256, 0, st>>>(rb->rows, rb->cold, idx, B, rb->stride, out_hot, out_cold, rb->size, seed, counter, idx_out);
+    rb_gather_kernel<16, 1><<<(B + 15) / 16, 256, 0, st>>>(rb->rows, rb->cold, idx, B, rb->stride, out_hot, out_cold, rb->size, seed, counter, idx_out);
+  else {
+    static const int un = getenv("ILSW_GATHER_UNROLL") ? atoi(getenv("ILSW_GATHER_UNROLL")) : 0;
+    const int u = un ? un : (nv <= 64 ? 2 : 1);   // measured (profiles/r1_replay_bench.txt): Ant rows (58 vectors) 2 loads in flight per lane, Humanoid 1
+    if (u == 1) rb_gather_kernel<32, 1><<<(B + 7) / 8, 256, 0, st>>>(rb->rows, rb->cold, idx, B, rb->stride, out_hot, out_cold, rb->size, seed, counter, idx_out);
+    else if (u == 2) rb_gather_kernel<32, 2><<<(B + 7) / 8, 256, 0, st>>>(rb->rows, rb->cold, idx, B, rb->stride, out_hot, out_cold, rb->size, seed, counter, idx_out);
+    else if (u == 4) rb_gather_kernel<32, 4><<<(B + 7) / 8, 256, 0, st>>>(rb->rows, rb->cold, idx, B, rb->stride, out_hot, out_cold, rb->size, seed, counter, idx_out);
+    else rb_gather_kernel<32, 8><<<(B + 7) / 8, 256, 0, st>>>(rb->rows, rb->cold, idx, B, rb->stride, out_hot, out_cold, rb->size, seed, counter, idx_out);
+  }
 }
 
 extern "C" int ilsw_rb_gather(ilsw_rb* rb, const int32_t* idx_dev, int B, float* out_hot, float* out_cold, void* stream) {

@@ -34,6 +34,7 @@ def main():
         chunk = 250_000
         for s in range(0, N, chunk):
             ring.load_device(torch.randn((min(chunk, N - s), ring.stride), generator=g, device="cuda"))
+        B = (1 << lg) * (4 if ring.stride <= 64 else 1)      # small rows: more of them, so the launch ramp does not dominate
         idx = torch.randint(0, N, (B,), generator=g, device="cuda", dtype=torch.int32)
         for label, fn in (("gather(idx)", lambda: ring.gather(idx)), ("sample(philox)", lambda: ring.sample(B, 7, 1))):
             for _ in range(3):
@@ -51,7 +52,7 @@ def main():
             print(json.dumps({"kernel": "rb_gather_kernel", "mode": label, "shape": name, "rows": B, "row_bytes": ring.stride * 4,
                               "ms": ms, "algorithmic_bytes": by, "achieved_gbs": by / ms / 1e6, "peak_gbs": peak,
                               "frac": by / ms / 1e6 / peak, "note": "includes the output allocation of the Python wrapper (cached allocator)"}))
-        n = 1 << 15
+        n = min(1 << 17, (64 << 20) // (ring.host_w * 4))
         host = np.random.RandomState(0).randn(n, ring.host_w).astype(np.float32)
         ts = []
         for _ in range(5):
