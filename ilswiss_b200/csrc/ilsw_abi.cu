@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) rb_scatter_kernel(const float* __restrict
 // of a group read consecutive 16-byte vectors of the same row (coalesced 128..512-byte segments -- the rows themselves
 // are random HBM addresses).  Rows of 17..64 vectors (Ant) keep two loads per lane in flight before the first store.  Optional in-kernel Philox index (speed mode).
 template <int LPR, int kGatherUnroll>
-__global__ void __launch_bounds__(256) rb_gather_kernel(const float* __restrict__ rows, const float* __restrict__ cold,
+__global__ void __launch_bounds__(256, 8) rb_gather_kernel(const float* __restrict__ rows, const float* __restrict__ cold,
                                                          const int32_t* __restrict__ idx, int B, int stride,
                                                          float* out_hot, float* out_cold, int64_t size, uint64_t seed,
                                                          uint64_t counter, int32_t* idx_out) {

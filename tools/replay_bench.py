@@ -3,7 +3,7 @@
 scatter, at the four BASELINE.json shapes, on large batches (the per-step batches of 256-1024 rows are launch-latency
 bound; this measures what the kernels sustain).  Prints one JSON line per (shape, kernel).
 
-    python tools/replay_bench.py [rows_log2=18]
+    python tools/replay_bench.py [rows_log2=18] [shape]
 Algorithmic bytes: gather = B * stride * 4 read (random rows) + B * stride * 4 written (+ 4 B index bytes);
 scatter = n * host_w * 4 read + n * (stride + 4) * 4 written."""
 import json
@@ -28,7 +28,10 @@ def main():
     except Exception:
         peak = 6650.0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    only = sys.argv[2] if len(sys.argv) > 2 else None
     for name, (O, A, N) in SHAPES.items():
+        if only and name != only:
+            continue
         ring = engine.ReplayRing(N, O, A)
         g = torch.Generator(device="cuda"); g.manual_seed(1)
         chunk = 250_000
