@@ -829,7 +829,10 @@ __device__ __noinline__ void adam_job(const AdamOp& ao, const AdamCoef& cfs, int
   for (int u = 0; u < E; ++u) {
     const int i = beg + threadIdx.x + u * kThreads;
     if (i < end) {
-      g[u] = (reduced ? replica_reduced_grad(rp, xseq, i) : __ldcg(ao.g + i)) * gscale;
+      // __fmul_rn: the scaled gradient must be ROUNDED before Adam consumes it -- a plain `* gscale` gets contracted into
+      // the first FMA of adam_math_store ((s * gscale) - m), which made R identical replicas differ from one replica by an
+      // ulp (tools/replica_check.py, test A: the single-replica program applies Adam in the weight-gradient epilogues)
+      g[u] = __fmul_rn(reduced ? replica_reduced_grad(rp, xseq, i) : __ldcg(ao.g + i), gscale);
       m[u] = ao.m[i]; v[u] = ao.v[i]; p[u] = ao.p[i];
       tg[u] = ao.target ? ao.target[i] : 0.f;
     }

@@ -200,17 +200,37 @@ ILSW_HD AdamCoef adam_coef(const AdamOp& o, int t, int world) {
 
 // one element of torch.optim.Adam (+ the Polyak update of a target network from the NEW parameter) with the
 // state already in registers: shared by the flat Adam jobs and the fused GEMM epilogues (identical arithmetic)
+// The element update is written with EXPLICIT roundings on the device: it is inlined into several call sites (flat Adam
+// jobs, three tile epilogues) and nvcc's FMA contraction picks a different fusion per site (a*b + c*d has two), which made
+// a single-replica run (Adam in the tile epilogues) differ from R identical replicas (flat Adam job after the exchange)
+// by an ulp.  With intrinsics every site executes the same sequence (tools/replica_check.py test A: bitwise equal).
+#ifdef __CUDA_ARCH__
+#define ILSW_MUL(a, b) __fmul_rn(a, b)
+#define ILSW_ADD(a, b) __fadd_rn(a, b)
+#define ILSW_SUB(a, b) __fsub_rn(a, b)
+#define ILSW_FMA(a, b, c) __fmaf_rn(a, b, c)
+#define ILSW_DIV(a, b) __fdiv_rn(a, b)
+#define ILSW_SQRT(a) __fsqrt_rn(a)
+#else
+#define ILSW_MUL(a, b) ((a) * (b))
+#define ILSW_ADD(a, b) ((a) + (b))
+#define ILSW_SUB(a, b) ((a) - (b))
+#define ILSW_FMA(a, b, c) fmaf(a, b, c)
+#define ILSW_DIV(a, b) ((a) / (b))
+#define ILSW_SQRT(a) sqrtf(a)
+#endif
 ILSW_HD void adam_math_store(const AdamOp& o, const AdamCoef& c, int i, float g, float m, float v, float p, float tg) {
   // exp_avg.lerp_(grad, 1-beta1)
-  m = (c.w1 < 0.5f) ? m + c.w1 * (g - m) : g - (g - m) * c.one_m_w1;
+  const float d = ILSW_SUB(g, m);
+  m = (c.w1 < 0.5f) ? ILSW_FMA(c.w1, d, m) : ILSW_SUB(g, ILSW_MUL(d, c.one_m_w1));
   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
-  v = v * c.beta2 + c.one_m_beta2 * g * g;
-  float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
-  p = p + c.neg_step * m / denom;  // addcdiv_(exp_avg, denom, value=-step_size)
+  v = ILSW_FMA(ILSW_MUL(c.one_m_beta2, g), g, ILSW_MUL(v, c.beta2));
+  const float denom = ILSW_ADD(ILSW_DIV(ILSW_SQRT(v), c.bc2_sqrt), c.eps);
+  p = ILSW_ADD(p, ILSW_DIV(ILSW_MUL(c.neg_step, m), denom));  // addcdiv_(exp_avg, denom, value=-step_size)
   o.m[i] = m;
   o.v[i] = v;
   o.p[i] = p;
-  if (o.target) o.target[i] = tg * c.one_m_tau + p * c.tau;
+  if (o.target) o.target[i] = ILSW_FMA(tg, c.one_m_tau, ILSW_MUL(p, c.tau));
 }
 ILSW_HD void adam_elem_g(const AdamOp& o, const AdamCoef& c, int i, float g) {
   adam_math_store(o, c, i, g, o.m[i], o.v[i], o.p[i], o.target ? o.target[i] : 0.f);

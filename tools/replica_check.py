@@ -48,7 +48,7 @@ def main():
         replicas.connect_replicas(_T(rep))
         Lr = rep.train(case["steps"], inj)
         torch.cuda.synchronize()
-        assert np.array_equal(Ls[:, :5], Lr[:, :5], equal_nan=True), (name, "A: losses differ", Ls[:, :3], Lr[:, :3])
+        assert np.array_equal(Ls[:, :5], Lr[:, :5], equal_nan=True), (name, "A: losses differ", Ls[:, :5] - Lr[:, :5], Ls[:, 3:5], Lr[:, 3:5])
         for k in ("policy", "qf1", "target_qf1"):
             assert np.array_equal(solo.arena(k), rep.arena(k)), (name, "A", k)
         # ---- B: distinct replicas (different index/eps streams per rank)
