@@ -18,6 +18,9 @@
 #ifndef ILSW_EIN_FIRST
 #define ILSW_EIN_FIRST 0
 #endif
+#ifndef ILSW_TC128_SIMPLE
+#define ILSW_TC128_SIMPLE 1
+#endif
 #ifndef ILSW_VECRAG
 #define ILSW_VECRAG 1
 #endif
@@ -611,7 +614,15 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
       FragSet f0, f1;
       int ks = warp;
       if (ks < ksteps) fragset_load(f0, a0 + (unsigned)ks * a_k8, a_row8, a_k4, a_mt, b0 + (unsigned)ks * b_k8, b_k4, b_nt);
-      if (full) {          // all 8 fragment tiles live: straight-line MMAs, no guards
+      if (full && KC == 128 && ILSW_TC128_SIMPLE) {
+        // two CTAs per SM (128-register cap): one fragment set, no ping-pong -- four warps per scheduler hide the shared
+        // memory latency, and the second fragment set is what pushed this variant into local-memory spills
+#pragma unroll 1
+        for (; ks < ksteps; ks += 8) {
+          fragset_mma<true>(acc, f0, mode, 2, 4);
+          if (ks + 8 < ksteps) fragset_load(f0, a0 + (unsigned)(ks + 8) * a_k8, a_row8, a_k4, a_mt, b0 + (unsigned)(ks + 8) * b_k8, b_k4, b_nt);
+        }
+      } else if (full) {          // all 8 fragment tiles live: straight-line MMAs, no guards
 #pragma unroll 1
         while (ks < ksteps) {
           int kn = ks + 8;
