@@ -4,6 +4,7 @@
     SoftActorCriticV <->  rlkit/torch/algorithms/sac/sac.py:13-243
     TD3              <->  rlkit/torch/algorithms/td3/td3.py:13-223
     HerTD3           <->  rlkit/torch/algorithms/her/td3.py:14-245
+    HerSAC           <->  rlkit/torch/algorithms/her/sac.py:12-251
 
 Same constructor signatures, same attributes read from outside (.policy, .networks,
 .eval_statistics, get_eval_statistics(), end_epoch(), get_snapshot(), load_snapshot(), to()),
@@ -490,10 +491,34 @@ class HerTD3(TD3):
         cfg.clip_return_r = 0.0 if cr is None else float(cr)
 
     def train_step(self, batch):
-        if "desired_goals" in batch:
-            def dev(x):
-                return torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(device="cuda", dtype=torch.float32)
-            batch = dict(batch)
-            batch["observations"] = torch.cat([dev(batch["observations"]), dev(batch["desired_goals"])], dim=-1)
-            batch["next_observations"] = torch.cat([dev(batch["next_observations"]), dev(batch["next_desired_goals"])], dim=-1)
-        super().train_step(batch)
+        super().train_step(_concat_goals(batch))
+
+
+def _concat_goals(batch):
+    """her/td3.py:94-98, her/sac.py:80-84: networks see cat(obs, desired_goal) / cat(next_obs, next_desired_goal)."""
+    if "desired_goals" not in batch:
+        return batch
+
+    def dev(x):
+        return torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(device="cuda", dtype=torch.float32)
+    batch = dict(batch)
+    batch["observations"] = torch.cat([dev(batch["observations"]), dev(batch["desired_goals"])], dim=-1)
+    batch["next_observations"] = torch.cat([dev(batch["next_observations"]), dev(batch["next_desired_goals"])], dim=-1)
+    return batch
+
+
+class HerSAC(SoftActorCritic):
+    """rlkit/torch/algorithms/her/sac.py:12-251 (run_scripts/her_sac_exp_script.py) -- goal-conditioned SAC with the
+    auto-tuned alpha.  The step is sac_alpha's on cat(observation, desired_goal) (her/sac.py:80-143); the one numeric
+    difference is the default target entropy: -prod(action_space.shape) (her/sac.py:52), not half of it."""
+
+    def __init__(self, policy, qf1, qf2, **kwargs):
+        if kwargs.get("target_entropy") is None:
+            if "env" in kwargs:
+                kwargs["target_entropy"] = -float(np.prod(kwargs["env"].action_space.shape))
+            else:
+                kwargs["target_entropy"] = -float(list(policy.parameters())[4].shape[0])
+        super().__init__(policy, qf1, qf2, **kwargs)
+
+    def train_step(self, batch):
+        super().train_step(_concat_goals(batch))

@@ -34,6 +34,9 @@ CASES = {
                           td3=dict(reward_scale=1.0, discount=0.99, soft_target_tau=0.005, policy_lr=6e-4,
                                    qf_lr=3e-4, policy_and_target_update_period=2),
                           policy_noise=0.2, policy_noise_clip=0.5, seed=25),
+    # run_scripts/her_sac_exp_script.py -> her/sac.py: sac_alpha on cat(obs, goal), target entropy -A (her/sac.py:52)
+    "her_sac_reach": dict(algo="sac_alpha", obs_dim=13, act_dim=4, batch=256, n_fill=20000, steps=4,
+                          her=dict(goal_dim=3), sac=dict(SAC_KW, alpha=0.2, target_entropy=-4.0), seed=27),
     # the yamls' net_size 300 (not a multiple of the 32-wide tile) and a narrow return clip
     "her_td3_h300": dict(algo="td3", obs_dim=13, act_dim=4, batch=128, n_fill=4000, steps=4, hidden=300,
                          her=dict(goal_dim=3, sigma=0.3, clip_return_l=-0.05, clip_return_r=0.02),

@@ -129,7 +129,10 @@ def run_reference(case):
     if algo == "sac_v":
         mods["vf"] = ref.FlattenMlp(hidden_sizes=list(HID), input_size=O, output_size=1)
     her = case.get("her")
-    if her:
+    if her and algo == "sac_alpha":
+        mods["policy"] = ref.ReparamTanhMultivariateGaussianConditionPolicy(
+            hidden_sizes=list(HID), obs_dim=O - her["goal_dim"], condition_dim=her["goal_dim"], action_dim=A)
+    elif her:
         mods["policy"] = ref.MlpGaussianAndEpsilonConditionPolicy(
             hidden_sizes=list(HID), action_space=ref_shim.FakeEnv(O, A).action_space, obs_dim=O - her["goal_dim"],
             condition_dim=her["goal_dim"], action_dim=A, output_activation=torch.tanh, max_sigma=her["sigma"],
@@ -147,7 +150,11 @@ def run_reference(case):
     for k, m in mods.items():
         _load_into_module(m, nets[k])
 
-    if algo in ("sac_alpha", "adv_irl"):
+    if algo == "sac_alpha" and her:
+        kw = {k: v for k, v in case["sac"].items() if k != "target_entropy"}     # her/sac.py takes none: -prod(action shape)
+        trainer = ref.HerSAC(policy=mods["policy"], qf1=mods["qf1"], qf2=mods["qf2"], env=env, **kw)
+        assert float(trainer.target_entropy) == case["sac"]["target_entropy"]
+    elif algo in ("sac_alpha", "adv_irl"):
         trainer = ref.SacAlpha(policy=mods["policy"], qf1=mods["qf1"], qf2=mods["qf2"], env=env, **case["sac"])
     elif algo == "sac_v":
         trainer = ref.SacV(policy=mods["policy"], qf1=mods["qf1"], qf2=mods["qf2"], vf=mods["vf"], **case["sac"])

@@ -104,7 +104,9 @@ def import_reference():
         MlpGaussianNoisePolicy,
         MlpGaussianAndEpsilonConditionPolicy,
     )
+    from rlkit.torch.common.policies import ReparamTanhMultivariateGaussianConditionPolicy
     from rlkit.torch.algorithms.her.td3 import TD3 as HerTD3
+    from rlkit.torch.algorithms.her.sac import SAC as HerSAC
     from rlkit.torch.algorithms.sac.sac_alpha import SoftActorCritic as SacAlpha
     from rlkit.torch.algorithms.sac.sac import SoftActorCritic as SacV
     from rlkit.torch.algorithms.td3.td3 import TD3

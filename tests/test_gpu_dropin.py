@@ -187,6 +187,38 @@ def test_her_td3_trainer_dropin():
     assert st["Q Targets Max"] <= float(np.max(data["rewards"][idx])) + 1e-5          # min target Q is clipped to <= 0
 
 
+def test_her_sac_trainer_dropin():
+    """her/sac.py: sac_alpha on cat(obs, goal) with target entropy -A; goal-conditioned batches through train_step."""
+    from ilswiss_b200.replay_buffer import DeviceReplayBuffer
+    from ilswiss_b200.trainers import HerSAC
+
+    torch.set_num_threads(1)
+    case = CFG.CASES["her_sac_reach"]
+    O, A, B, G_ = case["obs_dim"], case["act_dim"], case["batch"], case["her"]["goal_dim"]
+    mods, _ = build_modules(case)
+    kw = {k: v for k, v in case["sac"].items() if k != "target_entropy"}
+    tr = HerSAC(mods["policy"], mods["qf1"], mods["qf2"], batch_size=B, gemm_precision=3, **kw)
+    assert tr.target_entropy == -float(A)                           # her/sac.py:52, not -A/2
+    data, _ = case_data(case)
+    buf = DeviceReplayBuffer(case["n_fill"], O, A, random_seed=1)
+    fill(buf, data)
+    inj_np = case_injection(case)
+    tr.train_from_buffer(buf, case["steps"], inject={k: torch.from_numpy(v).cuda() for k, v in inj_np.items()})
+    rows, final, _ = G.run_oracle(case)
+    L = tr.engine.losses(case["steps"])
+    for t, row in enumerate(rows):
+        for key, slot in (("QF1 Loss", 0), ("QF2 Loss", 1), ("Policy Loss", 2), ("Alpha Loss", 3)):
+            assert abs(L[t, slot] - row[key]) <= 1e-4 * max(abs(row[key]), 1.0 if key == "Policy Loss" else 1e-2), (t, key)
+    assert abs(float(tr.log_alpha) - final["log_alpha"][0]) < 1e-6
+    idx = inj_np["idx"][0]
+    b = dict(observations=data["observations"][idx][:, :O - G_], desired_goals=data["observations"][idx][:, O - G_:],
+             next_observations=data["next_observations"][idx][:, :O - G_], next_desired_goals=data["next_observations"][idx][:, O - G_:],
+             actions=data["actions"][idx], rewards=data["rewards"][idx].reshape(B, 1), terminals=data["terminals"][idx].reshape(B, 1))
+    tr.end_epoch()
+    tr.train_step(b)
+    assert np.isfinite(tr.get_eval_statistics()["QF1 Loss"])
+
+
 def test_replay_buffer_dropin_matches_reference_semantics():
     from ilswiss_b200.replay_buffer import DeviceReplayBuffer
 
