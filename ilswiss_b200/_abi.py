@@ -42,7 +42,8 @@ class DiscConfig(C.Structure):
     _fields_ = [("mode", C.c_int), ("batch", C.c_int), ("disc_lr", C.c_double), ("disc_momentum", C.c_double),
                 ("use_grad_pen", C.c_int), ("grad_pen_weight", C.c_double), ("clamp_magnitude", C.c_double),
                 ("rew_clip_min_on", C.c_int), ("rew_clip_max_on", C.c_int),
-                ("rew_clip_min", C.c_double), ("rew_clip_max", C.c_double)]
+                ("rew_clip_min", C.c_double), ("rew_clip_max", C.c_double),
+                ("state_only", C.c_int), ("policy_batch_from_expert", C.c_int)]
 
 
 class Inject(C.Structure):

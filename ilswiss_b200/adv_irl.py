@@ -33,12 +33,10 @@ class AdvIRLEngine:
         if not isinstance(policy_trainer, SoftActorCritic):
             raise NotImplementedError("the fused AdvIRL engine drives ilswiss_b200.SoftActorCritic (as adv_irl_exp_script.py does)")
         unsupported = []
-        if state_only:
-            unsupported.append("state_only")
         if wrap_absorbing:
             unsupported.append("wrap_absorbing")
-        if policy_optim_batch_size_from_expert:
-            unsupported.append("policy_optim_batch_size_from_expert>0")
+        if not 0 <= policy_optim_batch_size_from_expert < policy_optim_batch_size:
+            unsupported.append("policy_optim_batch_size_from_expert must be in [0, policy_optim_batch_size)")
         if num_disc_updates_per_loop_iter < 1 or num_policy_updates_per_loop_iter < 1:
             unsupported.append("num_{disc,policy}_updates_per_loop_iter < 1")
         if disc_optim_batch_size != policy_optim_batch_size or disc_optim_batch_size != policy_trainer._cfg.batch:
@@ -50,6 +48,10 @@ class AdvIRLEngine:
         in_dim, H, out_dim, ls = module_dims(discriminator)
         if out_dim != 1 or ls or getattr(discriminator, "clamp_magnitude", None) is None:
             raise NotImplementedError("expects MLPDisc(num_layer_blocks=2, hid_act='tanh', use_bn=False)")
+        cfg = policy_trainer._cfg
+        want_in = 2 * cfg.obs_dim if state_only else cfg.obs_dim + cfg.act_dim      # adv_irl_exp_script.py:150-156
+        if in_dim != want_in:
+            raise ValueError("discriminator input dim %d != %d (%s)" % (in_dim, want_in, "2*obs_dim: state_only" if state_only else "obs_dim+act_dim"))
         self.mode, self.discriminator, self.policy_trainer = mode, discriminator, policy_trainer
         self.expert_replay_buffer, self.replay_buffer = expert_replay_buffer, replay_buffer
         self.use_grad_pen, self.grad_pen_weight = use_grad_pen, grad_pen_weight
@@ -65,6 +67,8 @@ class AdvIRLEngine:
         dc.clamp_magnitude = float(discriminator.clamp_magnitude)
         dc.rew_clip_min_on, dc.rew_clip_max_on = int(rew_clip_min is not None), int(rew_clip_max is not None)
         dc.rew_clip_min, dc.rew_clip_max = float(rew_clip_min or 0.0), float(rew_clip_max or 0.0)
+        dc.state_only, dc.policy_batch_from_expert = int(bool(state_only)), int(policy_optim_batch_size_from_expert)
+        self.state_only, self.policy_optim_batch_size_from_expert = bool(state_only), int(policy_optim_batch_size_from_expert)
         self._dc = dc
         eng = policy_trainer.engine
         d = self.disc_arena.desc()

@@ -269,10 +269,13 @@ ILSW_HDN void row_sac_gather(const Ctx& c, const RunArgs& a, int s, int b, int l
     term = a.direct.term[b];
     if (lane == 0) S.idx[b] = b;
   } else {
+    // adv_irl.py:239-255: the last n_from_expert rows of the policy batch are expert transitions
+    const bool from_expert = c.hp.has_disc && b >= B - c.hp.n_from_expert;
+    const RingView& rv = from_expert ? a.ring_expert : a.ring_policy;
     int idx = a.has_inject ? a.inj.idx[(size_t)s * B + b]
-                           : philox_index(a.seed, (uint32_t)(a.step0 + s), (uint32_t)b, 0u, a.ring_policy.size);
+                           : philox_index(a.seed, (uint32_t)(a.step0 + s), (uint32_t)b, 0u, rv.size);
     if (lane == 0) S.idx[b] = idx;
-    const float* src = ring_row(a.ring_policy, idx);
+    const float* src = ring_row(rv, idx);
     obs = src;
     act = src + O;
     rew = src[O + A];
@@ -285,6 +288,10 @@ ILSW_HDN void row_sac_gather(const Ctx& c, const RunArgs& a, int s, int b, int l
     S.Xoa[(size_t)b * S.ld_oa + k] = o;
     S.Xon[(size_t)b * S.ld_oa + k] = o;
     S.Xna[(size_t)b * S.ld_oa + k] = n;
+    if (c.hp.has_disc && c.hp.state_only) {          // reward relabel input cat(obs, next_obs) (adv_irl.py:265-269)
+      c.d.Xsn[(size_t)b * c.d.ld_sn + k] = o;
+      c.d.Xsn[(size_t)b * c.d.ld_sn + O + k] = n;
+    }
     if (!td3) {
       S.Xpi[(size_t)b * S.ld_o + k] = n;            // rows [0,B): next_obs
       S.Xpi[(size_t)(B + b) * S.ld_o + k] = o;      // rows [B,2B): obs
@@ -639,8 +646,10 @@ ILSW_HDN void row_disc_gather(const Ctx& c, const RunArgs& a, int s, int b, int 
                       : philox_uniform(a.seed, (uint32_t)(a.step0 + s), (uint32_t)b, 5u);
     if (lane == 0) Dd.gp_eps[b] = ep;
   }
+  const int O = c.s.O, skip = c.hp.state_only ? c.s.A + 2 : 0;     // state_only: [obs | next_obs] of the ring row
   for (int k = lane; k < D; k += nl) {
-    float e = xe[k], p = xp[k];
+    const int ks = k < O ? k : k + skip;
+    float e = xe[ks], p = xp[ks];
     Dd.X3[(size_t)b * Dd.ld_d + k] = e;
     Dd.X3[(size_t)(B + b) * Dd.ld_d + k] = p;
     if (c.hp.use_gp) Dd.X3[(size_t)(2 * B + b) * Dd.ld_d + k] = ep * e + (1.0f - ep) * p;  // adv_irl.py:191

@@ -188,6 +188,7 @@ inline void alloc_disc_bufs(Bump& mem, DiscBufs& D, int B, int Din, int Hd) {
   D.hb1 = mem.f((size_t)B * Hd); D.zb1 = mem.f((size_t)B * Hd);
   D.ceterm = mem.f(2 * B); D.accterm = mem.f(2 * B); D.gpterm = mem.f(B);
   D.rh1 = mem.f((size_t)B * Hd); D.rh2 = mem.f((size_t)B * Hd); D.rewraw = mem.f(B);
+  D.ld_sn = D.ld_d; D.Xsn = mem.f((size_t)B * D.ld_sn);
 }
 
 inline int stats_floats_for(int algo, int B, int A) {
@@ -270,7 +271,8 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
   b.phase();
   for (int i = 0; i < 2; ++i) b.fwd(S.Xoa, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0q[i], Hd, ACT_RELU);
   b.fwd(S.Xpi, S.ld_o, 2 * B, O, P.p + P.oW0, P.p + P.ob0, Hd, S.h0p, Hd, ACT_RELU);
-  if (disc) b.fwd(S.Xoa, S.ld_oa, B, K0, c.disc.p + c.disc.oW0, c.disc.p + c.disc.ob0, c.d.Hd, c.d.rh1, c.d.Hd, ACT_TANH);
+  if (disc && c.hp.state_only) b.fwd(c.d.Xsn, c.d.ld_sn, B, 2 * O, c.disc.p + c.disc.oW0, c.disc.p + c.disc.ob0, c.d.Hd, c.d.rh1, c.d.Hd, ACT_TANH);
+  else if (disc) b.fwd(S.Xoa, S.ld_oa, B, K0, c.disc.p + c.disc.oW0, c.disc.p + c.disc.ob0, c.d.Hd, c.d.rh1, c.d.Hd, ACT_TANH);
   b.phase();
   for (int i = 0; i < 2; ++i) b.fwd(S.h0q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1q[i], Hd, ACT_RELU);
   b.fwd(S.h0p, Hd, 2 * B, Hd, P.p + P.oW1, P.p + P.ob1, Hd, S.h1p, Hd, ACT_RELU);
@@ -505,6 +507,7 @@ inline void apply_disc_hyper(Hyper& h, const ilsw_disc_config& d) {
   h.gp_weight = (float)d.grad_pen_weight; h.disc_clamp = (float)d.clamp_magnitude; h.use_gp = d.use_grad_pen;
   h.clip_min_on = d.rew_clip_min_on; h.clip_max_on = d.rew_clip_max_on;
   h.rew_clip_min = (float)d.rew_clip_min; h.rew_clip_max = (float)d.rew_clip_max;
+  h.state_only = d.state_only; h.n_from_expert = d.policy_batch_from_expert;
 }
 
 inline int build_program(Program& P);
@@ -544,7 +547,9 @@ inline int validate_spec(const TrainerSpec& sp, std::string* why) {
   if (sp.has_disc) {
     if (c.algo != ILSW_ALGO_SAC_ALPHA) return fail("discriminator requires the SAC-alpha trainer");
     if (sp.dcfg.batch != c.batch) return fail("disc batch must equal policy batch");
-    if (sp.disc.in_dim != c.obs_dim + c.act_dim || sp.disc.out_dim != 1 || sp.disc.log_std_head) return fail("disc dims");
+    const int disc_in = sp.dcfg.state_only ? 2 * c.obs_dim : c.obs_dim + c.act_dim;
+    if (sp.disc.in_dim != disc_in || sp.disc.out_dim != 1 || sp.disc.log_std_head) return fail("disc dims");
+    if (sp.dcfg.policy_batch_from_expert < 0 || sp.dcfg.policy_batch_from_expert >= c.batch) return fail("policy_batch_from_expert must be in [0, batch)");
     if (!sp.disc.p || !sp.disc.m || !sp.disc.v) return fail("disc arenas");
     if (sp.dcfg.mode < 0 || sp.dcfg.mode > 3) return fail("disc mode");
   }
@@ -579,7 +584,7 @@ inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem) {
   }
   if (cfg.algo == ILSW_ALGO_TD3) c.tpolicy = make_mlp(sp.nets[5], nullptr);
   if (sp.has_disc) {
-    alloc_disc_bufs(mem, c.d, B, O + A, sp.disc.hidden);
+    alloc_disc_bufs(mem, c.d, B, sp.dcfg.state_only ? 2 * O : O + A, sp.disc.hidden);
     c.disc = make_mlp(sp.disc, grad(sp.disc));
   }
   return build_program(P);

@@ -147,6 +147,7 @@ struct DiscBufs {
   float *ceterm, *accterm, *gpterm;
   // reward relabel (D2)
   float *rh1, *rh2, *rewraw;
+  float *Xsn; int ld_sn;     // state_only: cat(obs, next_obs) rows of the policy batch (reward relabel input)
 };
 
 struct DynState {       // device-resident mutable scalars (persist across launches)
@@ -174,6 +175,8 @@ struct Hyper {
   int has_disc; int disc_mode;    // 0 airl 1 gail 2 gail2 3 fairl
   double disc_lr, disc_beta1; float gp_weight, disc_clamp; int use_gp;
   int clip_min_on, clip_max_on; float rew_clip_min, rew_clip_max;
+  int state_only;       // disc input = cat(obs, next_obs) (adv_irl.py:139-179)
+  int n_from_expert;    // last n rows of the policy batch come from the expert ring (adv_irl.py:239-255)
 };
 
 struct Ctx {            // everything a row kernel needs

@@ -126,6 +126,11 @@ typedef struct {
   double clamp_magnitude;   /* MLPDisc clamp (simple_disc_models.py:43-48) */
   int rew_clip_min_on, rew_clip_max_on;
   double rew_clip_min, rew_clip_max;
+  /* adv_irl.py:139-179,265-269: discriminator input cat(obs, next_obs) instead of cat(obs, act); disc.in_dim = 2*obs_dim */
+  int state_only;
+  /* adv_irl.py:239-255 policy_optim_batch_size_from_expert: the LAST n rows of every policy batch are sampled from the expert
+   * ring (injected idx rows >= batch - n index the expert ring) */
+  int policy_batch_from_expert;
 } ilsw_disc_config;
 
 typedef struct ilsw_trainer ilsw_trainer;

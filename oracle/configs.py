@@ -65,6 +65,15 @@ CASES = {
                         disc=dict(disc_lr=3e-4, disc_momentum=0.9, use_grad_pen=True,
                                   grad_pen_weight=4.0),
                         sac=dict(SAC_KW, reward_scale=1.0, alpha=0.2), seed=20),
+    # adv_irl.py:139-179,265-269 state_only (AIRL on cat(s, s')) and :239-255 expert transitions mixed into the policy batch
+    "airl_state_only": dict(algo="adv_irl", obs_dim=11, act_dim=3, batch=128, n_fill=5000, n_expert=2000, steps=3,
+                            mode="airl", state_only=True,
+                            disc=dict(disc_lr=3e-4, disc_momentum=0.9, use_grad_pen=True, grad_pen_weight=10.0),
+                            sac=dict(SAC_KW, reward_scale=1.0, alpha=0.2), seed=28),
+    "gail_expert_mix": dict(algo="adv_irl", obs_dim=11, act_dim=3, batch=128, n_fill=5000, n_expert=2000, steps=3,
+                            mode="gail", from_expert=32,
+                            disc=dict(disc_lr=3e-4, disc_momentum=0.9, use_grad_pen=True, grad_pen_weight=4.0),
+                            sac=dict(SAC_KW, reward_scale=1.0, alpha=0.2), seed=29),
     # ragged shapes: batch not a multiple of the 32-row tile / of 4, odd hidden widths, tiny dims
     "sac_ragged": dict(algo="sac_alpha", obs_dim=5, act_dim=2, batch=70, n_fill=300, steps=3, hidden=64,
                        sac=dict(SAC_KW, alpha=0.2), seed=21),

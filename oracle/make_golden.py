@@ -49,7 +49,7 @@ def build_oracle_nets(case):
             nets["vf"] = R.Net(R.init_mlp(rs, O, HID, 1))
         nets["policy"] = R.Net(R.init_mlp(rs, O, HID, A, init_w=1e-3, log_std_head=True))
         if algo == "adv_irl":
-            nets["disc"] = R.Net(R.init_disc(rs, O + A, DH))
+            nets["disc"] = R.Net(R.init_disc(rs, 2 * O if case.get("state_only") else O + A, DH))
     elif algo == "td3":
         nets["qf1"] = R.Net(R.init_mlp(rs, O + A, HID, 1))
         nets["qf2"] = R.Net(R.init_mlp(rs, O + A, HID, 1))
@@ -145,7 +145,7 @@ def run_reference(case):
         mods["policy"] = ref.ReparamTanhMultivariateGaussianPolicy(
             hidden_sizes=list(HID), obs_dim=O, action_dim=A)
     if algo == "adv_irl":
-        mods["disc"] = ref.MLPDisc(O + A, num_layer_blocks=2, hid_dim=DH, hid_act="tanh",
+        mods["disc"] = ref.MLPDisc(2 * O if case.get("state_only") else O + A, num_layer_blocks=2, hid_dim=DH, hid_act="tanh",
                                    use_bn=False, clamp_magnitude=10.0)
     for k, m in mods.items():
         _load_into_module(m, nets[k])
@@ -168,7 +168,8 @@ def run_reference(case):
     if algo == "adv_irl":
         alg = ref.AdvIRL(
             mode=case["mode"], discriminator=mods["disc"], policy_trainer=trainer,
-            expert_replay_buffer=ebuf, state_only=False, disc_optim_batch_size=B,
+            expert_replay_buffer=ebuf, state_only=case.get("state_only", False), disc_optim_batch_size=B,
+            policy_optim_batch_size_from_expert=case.get("from_expert", 0),
             policy_optim_batch_size=B, num_update_loops_per_train_call=1,
             num_disc_updates_per_loop_iter=case.get("n_disc", 1), num_policy_updates_per_loop_iter=case.get("n_policy", 1),
             rew_clip_min=case.get("rew_clip_min"), rew_clip_max=case.get("rew_clip_max"),
@@ -251,16 +252,23 @@ def run_oracle(case):
             # adv_irl.py:126-131: n_disc reward updates, then n_policy policy updates; the logged statistics are those of
             # the FIRST update of each kind in the call (eval_statistics is filled once), reward stats of the LAST (:303-314)
             d = s = None
+            second = "next_observations" if case.get("state_only") else "actions"     # adv_irl.py:139-143
+            E = case.get("from_expert", 0)
             for _ in range(case.get("n_disc", 1)):
-                eb = R.np_to_torch_batch(ebuf.random_batch(B, keys=["observations", "actions"]))
-                pb = R.np_to_torch_batch(buf.random_batch(B, keys=["observations", "actions"]))
+                eb = R.np_to_torch_batch(ebuf.random_batch(B, keys=["observations", second]))
+                pb = R.np_to_torch_batch(buf.random_batch(B, keys=["observations", second]))
                 gp_eps = torch.rand(B, 1) if case["disc"]["use_grad_pen"] else None
-                di = disc.reward_step(torch.cat([eb["observations"], eb["actions"]], 1),
-                                      torch.cat([pb["observations"], pb["actions"]], 1), gp_eps)
+                di = disc.reward_step(torch.cat([eb["observations"], eb[second]], 1),
+                                      torch.cat([pb["observations"], pb[second]], 1), gp_eps)
                 d = d or di
             for _ in range(case.get("n_policy", 1)):
-                batch = R.np_to_torch_batch(buf.random_batch(B))
-                rew = disc.rewards(batch["observations"], batch["actions"], case["mode"],
+                if E:       # adv_irl.py:239-255: B - E rows from the policy buffer, then E rows from the expert buffer
+                    bp = R.np_to_torch_batch(buf.random_batch(B - E))
+                    be = R.np_to_torch_batch(ebuf.random_batch(E))
+                    batch = {k: torch.cat([bp[k], be[k]], dim=0) for k in bp}
+                else:
+                    batch = R.np_to_torch_batch(buf.random_batch(B))
+                rew = disc.rewards(batch["observations"], batch[second], case["mode"],
                                    case.get("rew_clip_min"), case.get("rew_clip_max"))
                 batch["rewards"] = rew
                 si = tr.train_step(batch, torch.randn(B, A), torch.randn(B, A))

@@ -634,7 +634,7 @@ class DiscOracle:
                     grads=[g.numpy() for g in grads])
 
     def rewards(self, obs, act, mode, rew_clip_min=None, rew_clip_max=None):
-        """adv_irl.py:266-298 (disc in eval mode, logits detached)."""
+        """adv_irl.py:266-298 (disc in eval mode, logits detached).  `act` is next_obs in state_only mode (:265-269)."""
         with torch.no_grad():
             w = list(self.disc.p.values())
             return disc_reward(disc_forward(w, torch.cat([obs, act], dim=1), self.clamp), mode,

@@ -54,7 +54,10 @@ def case_injection(case, steps=None):
             out["idx_policy_d"][t] = rs.randint(0, case["n_fill"], B)
             if case["disc"]["use_grad_pen"]:
                 out["gp_eps"][t] = torch.rand(B, 1).numpy().ravel()
-        out["idx"][t] = rs.randint(0, case["n_fill"], B)
+        E = case.get("from_expert", 0)
+        out["idx"][t, :B - E] = rs.randint(0, case["n_fill"], B - E)
+        if E:       # adv_irl.py:239-255: policy-buffer draw first, then the expert-buffer draw
+            out["idx"][t, B - E:] = ers.randint(0, case["n_expert"], E)
         out["eps_next"][t] = torch.randn(B, A).numpy()
         if algo in ("sac_alpha", "adv_irl"):
             out["eps_cur"][t] = torch.randn(B, A).numpy()
@@ -185,6 +188,7 @@ def disc_config(case):
     dc.rew_clip_max_on = int(case.get("rew_clip_max") is not None)
     dc.rew_clip_min = case.get("rew_clip_min") or 0.0
     dc.rew_clip_max = case.get("rew_clip_max") or 0.0
+    dc.state_only, dc.policy_batch_from_expert = int(case.get("state_only", False)), case.get("from_expert", 0)
     return dc
 
 
@@ -215,7 +219,7 @@ def mlp_dims(case, name):
     if name in ("policy", "target_policy"):
         return O, H, A, int(case["algo"] != "td3")
     if name == "disc":
-        return O + A, case.get("disc_hid", CFG.DISC_HID), 1, 0
+        return (2 * O if case.get("state_only") else O + A), case.get("disc_hid", CFG.DISC_HID), 1, 0
     if name in ("vf", "target_vf"):
         return O, H, 1, 0
     return O + A, H, 1, 0

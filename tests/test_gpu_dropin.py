@@ -317,7 +317,7 @@ def test_adv_irl_engine_matches_oracle_and_stats_keys():
     got = np.concatenate([p.detach().cpu().numpy().ravel() for p in mods["disc"].parameters()])
     assert np.max(np.abs(got - final["disc"])) < 1e-4
     with pytest.raises(NotImplementedError):
-        AdvIRLEngine("gail", mods["disc"], tr, ebuf, buf, state_only=True, disc_optim_batch_size=256,
+        AdvIRLEngine("gail", mods["disc"], tr, ebuf, buf, wrap_absorbing=True, disc_optim_batch_size=256,
                      policy_optim_batch_size=256, num_disc_updates_per_loop_iter=1, num_policy_updates_per_loop_iter=1)
 
 
