@@ -186,6 +186,7 @@ class DeviceTorchRLAlgorithmMixin:
 
     def _do_training(self, epoch):
         # torch_rl_algorithm.py:28-34: num_train_steps_per_train_call steps in one launch
+        self.trainer.ensure_batch(self.batch_size, self.num_train_steps_per_train_call)
         self.trainer.train_from_buffer(self.replay_buffer, self.num_train_steps_per_train_call)
 
 
@@ -195,6 +196,7 @@ class DeviceAdvIRLMixin:
     def _ilsw_engine(self):
         eng = getattr(self, "_ilsw_eng", None)
         if eng is None:
+            self.policy_trainer.ensure_batch(self.policy_optim_batch_size, self.num_update_loops_per_train_call)
             eng = AdvIRLEngine(
                 self.mode, self.discriminator, self.policy_trainer, self.expert_replay_buffer, self.replay_buffer,
                 state_only=self.state_only, disc_optim_batch_size=self.disc_optim_batch_size,

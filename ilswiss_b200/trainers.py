@@ -85,9 +85,23 @@ class _FusedTrainer:
     def _finish_init(self, cfg, nets):
         require_cuda()
         self.engine = StepEngine(cfg, nets)
-        self._cfg = cfg
+        self._cfg, self._nets = cfg, list(nets)
         self._seed = int(np.random.randint(1, 2 ** 31 - 1))
         self._launch = 0
+
+    def ensure_batch(self, batch_size, max_steps_per_call=None):
+        """The step program is compiled for ONE batch size, but the reference hands `batch_size` to the ALGORITHM
+        (rl_alg_params, torch_rl_algorithm.py:16-18), not to the trainer: adopt the algorithm's value the first time it
+        is seen.  Rebuilds the engine (fresh optimiser counters), so it is only legal before the first gradient step."""
+        B = int(batch_size)
+        M = max(int(self._cfg.max_steps_per_call), int(max_steps_per_call or 0))
+        if B == self._cfg.batch and M == self._cfg.max_steps_per_call:
+            return
+        if self.engine.get_state().n_train_steps_total != 0 or getattr(self.engine, "disc", None) is not None:
+            raise ValueError("batch size %d != trainer batch %d, and the engine has already been used: construct the trainer "
+                             "with batch_size=%d" % (B, self._cfg.batch, B))
+        self._cfg.batch, self._cfg.max_steps_per_call = B, M
+        self.engine = StepEngine(self._cfg, self._nets)
 
     # -- the two ways to run gradient steps ------------------------------------------------
     def train_step(self, batch):
@@ -102,7 +116,8 @@ class _FusedTrainer:
                 t = torch.as_tensor(np.asarray(t))
             t = t.to(device="cuda", dtype=torch.float32).contiguous()
             if t.shape[0] != B:
-                raise ValueError("batch size %d != trainer batch %d (fixed at construction: kwargs['batch_size'])" % (t.shape[0], B))
+                self.ensure_batch(t.shape[0])          # first use only; raises once the engine has trained
+                B = self._cfg.batch
             b[name] = t
         want = self.eval_statistics is None
         self._launch += 1

@@ -461,6 +461,20 @@ def test_algorithm_mixins_drive_one_launch_per_train_call():
     b = alg.get_batch()
     assert b["observations"].is_cuda and b["observations"].shape == (B, O) and b["rewards"].shape == (B, 1)
     assert "QF1 Loss" in alg.trainer.get_eval_statistics()
+    # the reference gives batch_size to the ALGORITHM, not the trainer: a trainer built with the default batch adopts it
+    # on first use (ensure_batch) and refuses to change once it has trained
+    tr_default = SoftActorCritic(modules.TanhGaussianPolicy([256, 256], O, A), modules.FlattenMlp([256, 256], 1, O + A),
+                                 modules.FlattenMlp([256, 256], 1, O + A))
+    assert tr_default._cfg.batch == 256
+    alg2 = Alg(tr_default, mk_buf(1))
+    alg2._do_training(0)
+    assert tr_default._cfg.batch == B and tr_default.engine.get_state().n_train_steps_total == 37
+    with pytest.raises(ValueError):
+        tr_default.ensure_batch(2 * B)
+    tr_step = SoftActorCritic(modules.TanhGaussianPolicy([256, 256], O, A), modules.FlattenMlp([256, 256], 1, O + A),
+                              modules.FlattenMlp([256, 256], 1, O + A))
+    tr_step.train_step(alg.get_batch())                # Trainer.train_step(batch) with a 64-row batch
+    assert tr_step._cfg.batch == B and np.isfinite(tr_step.get_eval_statistics()["QF1 Loss"])
 
     class RefIRL:                                  # stand-in for rlkit AdvIRL (attribute names of adv_irl.py:63-104)
         def __init__(self):
