@@ -176,7 +176,34 @@ class AdvIRLEngine:
         return dict(disc=self.discriminator, disc_optimizer=self.disc_optimizer)
 
 
-class DeviceTorchRLAlgorithmMixin:
+class _DeviceSamplerMixin:
+    """Sampler coupling: BaseAlgorithm._get_action_and_info (base_algorithm.py:369-380) with the
+    per-env-step policy round trip going through sampler.DevicePolicy (one C-ABI call: pinned H2D, one kernel, pinned
+    D2H) whenever the exploration policy IS the trainer's policy module; anything else falls through to the reference."""
+
+    def _ilsw_device_policy(self):
+        dp = getattr(self, "_ilsw_dp", None)
+        if dp is None:
+            from .sampler import DevicePolicy
+
+            trainer = getattr(self, "trainer", None) or getattr(self, "policy_trainer", None)
+            pol = getattr(trainer, "policy", None)
+            ok = pol is not None and self.exploration_policy is pol and hasattr(trainer, "engine")
+            dp = DevicePolicy(trainer) if ok else False
+            self._ilsw_dp = dp
+        return dp
+
+    def _get_action_and_info(self, observation):
+        dp = self._ilsw_device_policy()
+        if dp is False:
+            return super()._get_action_and_info(observation)
+        self.exploration_policy.set_num_steps_total(self._n_env_steps_total)
+        if not self._can_train():
+            return [self.action_space.sample() for _ in range(len(observation))]
+        return dp.get_actions(observation)
+
+
+class DeviceTorchRLAlgorithmMixin(_DeviceSamplerMixin):
     """Put in front of rlkit's TorchRLAlgorithm: `class Alg(DeviceTorchRLAlgorithmMixin, TorchRLAlgorithm)`.
     Requires replay_buffer=DeviceReplayBuffer(...) and an ilswiss_b200 trainer."""
 
@@ -190,7 +217,7 @@ class DeviceTorchRLAlgorithmMixin:
         self.trainer.train_from_buffer(self.replay_buffer, self.num_train_steps_per_train_call)
 
 
-class DeviceAdvIRLMixin:
+class DeviceAdvIRLMixin(_DeviceSamplerMixin):
     """Put in front of rlkit's AdvIRL: `class AdvIRL(DeviceAdvIRLMixin, RefAdvIRL)`."""
 
     def _ilsw_engine(self):

@@ -453,6 +453,21 @@ def test_algorithm_mixins_drive_one_launch_per_train_call():
     class Alg(DeviceTorchRLAlgorithmMixin, RefRL):
         pass
 
+    # sampler coupling through the mixin: exploration_policy is the trainer's module -> DevicePolicy round trip
+    class _Space:
+        def sample(self):
+            return np.zeros(A)
+
+    samp = Alg(mk_trainer(), mk_buf(1))
+    samp.exploration_policy, samp._n_env_steps_total, samp.action_space = samp.trainer.policy, 0, _Space()
+    samp.trainer.policy.set_num_steps_total = lambda t: None
+    samp._can_train = lambda: True
+    obs4 = rs.randn(4, O)
+    acts = samp._get_action_and_info(obs4)
+    assert acts.shape == (4, A) and np.abs(acts).max() < 1.0 and samp._ilsw_dp is not False
+    samp._can_train = lambda: False
+    assert len(samp._get_action_and_info(obs4)) == 4            # warm-up: random actions (base_algorithm.py:376-377)
+
     alg = Alg(mk_trainer(), mk_buf(1))
     n0 = alg.trainer.engine.kernel_launches
     alg._do_training(0)
