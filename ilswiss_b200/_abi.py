@@ -46,6 +46,12 @@ class DiscConfig(C.Structure):
                 ("state_only", C.c_int), ("policy_batch_from_expert", C.c_int)]
 
 
+class HerSamplingDesc(C.Structure):
+    _fields_ = [("enabled", C.c_int), ("n_traj", C.c_int), ("traj_start", C.c_void_p), ("traj_len", C.c_void_p),
+                ("next_achieved_goal", C.c_void_p), ("goal_dim", C.c_int), ("relabel_num", C.c_int),
+                ("distance_threshold", C.c_float), ("inj_idx_her", C.c_void_p)]
+
+
 class Inject(C.Structure):
     _fields_ = [("idx", C.c_void_p), ("eps_next", C.c_void_p), ("eps_cur", C.c_void_p),
                 ("idx_expert", C.c_void_p), ("idx_policy_d", C.c_void_p), ("gp_eps", C.c_void_p)]
@@ -85,6 +91,7 @@ PROTOTYPES = {
     "ilsw_trainer_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(TrainerConfig), C.POINTER(Mlp), C.c_int]),
     "ilsw_trainer_attach_disc": (C.c_int, [C.c_void_p, C.POINTER(DiscConfig), C.POINTER(Mlp)]),
     "ilsw_trainer_set_update_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "ilsw_trainer_set_her": (C.c_int, [C.c_void_p, C.POINTER(HerSamplingDesc)]),
     "ilsw_trainer_destroy": (C.c_int, [C.c_void_p]),
     "ilsw_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Inject), C.POINTER(Batch),
                              C.c_uint64, C.c_int, C.c_void_p]),

@@ -303,6 +303,7 @@ struct ilsw_trainer {
   // sampler-side inference with host buffers (ilsw_policy_act_host): pinned + device staging, allocated on first use
   float *act_pin, *act_dev;     // [kMaxActRows x (in_dim + act_dim)] each: observations first, actions after
   int update_mode;              // UpdateMode of the next launches (AdvIRL programs)
+  HerSampling her;              // relabel-at-sample of the next launches (ilsw_trainer_set_her)
 };
 static const int kMaxActRows = 4096;
 
@@ -390,6 +391,22 @@ extern "C" int ilsw_trainer_attach_disc(ilsw_trainer* tr, const ilsw_disc_config
   return trainer_build(tr);
 }
 
+extern "C" int ilsw_trainer_set_her(ilsw_trainer* tr, const ilsw_her_sampling* her) {
+  if (!tr) return fail(ILSW_ERR_ARG, "set_her: null trainer");
+  memset(&tr->her, 0, sizeof(tr->her));
+  if (!her || !her->enabled) return ILSW_OK;
+  if (tr->spec.has_disc) return fail(ILSW_ERR_UNSUPPORTED, "set_her: not with a discriminator attached");
+  if (her->goal_dim <= 0 || her->goal_dim >= tr->spec.cfg.obs_dim || her->relabel_num < 0 || her->relabel_num > tr->spec.cfg.batch ||
+      !her->traj_start || !her->traj_len || !her->next_achieved_goal || her->n_traj < 0)
+    return fail(ILSW_ERR_ARG, "set_her: bad arguments");
+  tr->her.enabled = 1; tr->her.n_traj = her->n_traj;
+  tr->her.traj_start = her->traj_start; tr->her.traj_len = her->traj_len;
+  tr->her.ag_next = her->next_achieved_goal; tr->her.G = her->goal_dim;
+  tr->her.relabel_num = her->relabel_num; tr->her.threshold = her->distance_threshold;
+  tr->her.inj_idx_her = her->inj_idx_her;
+  return ILSW_OK;
+}
+
 extern "C" int ilsw_trainer_set_update_mode(ilsw_trainer* tr, int mode) {
   if (!tr || mode < UPDATE_BOTH || mode > UPDATE_POLICY_ONLY) return fail(ILSW_ERR_ARG, "set_update_mode: bad arguments");
   if (mode != UPDATE_BOTH && !tr->spec.has_disc) return fail(ILSW_ERR_STATE, "set_update_mode: no discriminator attached");
@@ -462,6 +479,12 @@ extern "C" int ilsw_train(ilsw_trainer* tr, ilsw_rb* policy_rb, ilsw_rb* expert_
   a.world = tr->rep.world; a.rank = tr->rep.rank; a.loss_log_offset = 0;
   a.profile = tr->profile;
   a.update_mode = tr->spec.has_disc ? tr->update_mode : UPDATE_BOTH;
+  a.her = tr->her;
+  if (a.her.enabled && !batch) {
+    if (!policy_rb) return fail(ILSW_ERR_ARG, "train: hindsight sampling needs the replay ring");
+    if (a.her.n_traj <= 0) return fail(ILSW_ERR_STATE, "train: hindsight sampling needs at least one finished trajectory");
+    if (inject && !a.her.inj_idx_her) return fail(ILSW_ERR_ARG, "train: inject needs inj_idx_her for hindsight sampling");
+  }
   if (a.update_mode == UPDATE_DISC_ONLY && batch) return fail(ILSW_ERR_ARG, "train: a disc-only launch samples from the rings (no direct batch)");
   Replica rp = tr->rep;
   rp.seq0 = tr->seq;

@@ -261,6 +261,7 @@ ILSW_HDN void row_sac_gather(const Ctx& c, const RunArgs& a, int s, int b, int l
   const bool td3 = (c.hp.algo == 2);
   const float *obs, *act, *nobs;
   float rew, term;
+  int idx = b, idx_her = -1;
   if (a.has_direct) {
     obs = a.direct.obs + (size_t)b * O;
     act = a.direct.act + (size_t)b * A;
@@ -272,8 +273,23 @@ ILSW_HDN void row_sac_gather(const Ctx& c, const RunArgs& a, int s, int b, int l
     // adv_irl.py:239-255: the last n_from_expert rows of the policy batch are expert transitions
     const bool from_expert = c.hp.has_disc && b >= B - c.hp.n_from_expert;
     const RingView& rv = from_expert ? a.ring_expert : a.ring_policy;
-    int idx = a.has_inject ? a.inj.idx[(size_t)s * B + b]
-                           : philox_index(a.seed, (uint32_t)(a.step0 + s), (uint32_t)b, 0u, rv.size);
+    if (a.her.enabled) {
+      // relabel_replay_buffer.py:70-95: uniform finished trajectory -> uniform step in it -> uniform FUTURE step [step, end)
+      if (a.has_inject) {
+        idx = a.inj.idx[(size_t)s * B + b];
+        idx_her = a.her.inj_idx_her[(size_t)s * B + b];
+      } else {
+        const int t = philox_index(a.seed, (uint32_t)(a.step0 + s), (uint32_t)b, 6u, a.her.n_traj);
+        const int st = a.her.traj_start[t], len = a.her.traj_len[t];
+        const int off = philox_index(a.seed, (uint32_t)(a.step0 + s), (uint32_t)b, 0u, len);
+        const int fut = off + philox_index(a.seed, (uint32_t)(a.step0 + s), (uint32_t)b, 7u, len - off);
+        idx = (st + off) % rv.size;
+        idx_her = (st + fut) % rv.size;
+      }
+    } else {
+      idx = a.has_inject ? a.inj.idx[(size_t)s * B + b]
+                         : philox_index(a.seed, (uint32_t)(a.step0 + s), (uint32_t)b, 0u, rv.size);
+    }
     if (lane == 0) S.idx[b] = idx;
     const float* src = ring_row(rv, idx);
     obs = src;
@@ -282,9 +298,26 @@ ILSW_HDN void row_sac_gather(const Ctx& c, const RunArgs& a, int s, int b, int l
     term = src[O + A + 1];
     nobs = src + O + A + 2;
   }
+  // hindsight relabel (relabel_replay_buffer.py:99-131): goal part of the first relabel_num rows <- next achieved goal of
+  // the future step; sparse goal reward recomputed for EVERY row from its next achieved goal and (new) desired goal
+  const bool her = a.her.enabled && !a.has_direct;
+  const int G = her ? a.her.G : 0, g0 = O - G;
+  const bool relabel = her && b < a.her.relabel_num;
+  const float* goal_src = relabel ? a.her.ag_next + (size_t)idx_her * G : nullptr;
+  if (her && a.her.relabel_num > 0) {
+    const float* ag = a.her.ag_next + (size_t)idx * G;
+    float ss = 0.f;
+    for (int k = lane; k < G; k += nl) {
+      const float d = ag[k] - (relabel ? goal_src[k] : obs[g0 + k]);
+      ss += d * d;
+    }
+    ss = wsum(ss);
+    rew = (sqrtf(ss) > a.her.threshold) ? -1.0f : -0.0f;
+  }
   if (lane == 0) { S.rew[b] = rew; S.term[b] = term; }
   for (int k = lane; k < O; k += nl) {
     float o = obs[k], n = nobs[k];
+    if (relabel && k >= g0) o = n = goal_src[k - g0];
     S.Xoa[(size_t)b * S.ld_oa + k] = o;
     S.Xon[(size_t)b * S.ld_oa + k] = o;
     S.Xna[(size_t)b * S.ld_oa + k] = n;

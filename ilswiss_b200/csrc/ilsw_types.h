@@ -206,6 +206,14 @@ struct Inject {         // optional injected randomness (parity mode); all devic
   const float* gp_eps;    // [T x B]
 };
 
+struct HerSampling {    // relabel-at-sample (see ilsw_her_sampling in include/ilswiss_b200.h)
+  int enabled, n_traj;
+  const int* traj_start; const int* traj_len;
+  const float* ag_next; int G;
+  int relabel_num; float threshold;
+  const int* inj_idx_her;
+};
+
 struct DirectBatch {    // optional: train on a caller-provided dense batch instead of the ring
   const float *obs, *act, *rew, *term, *next_obs;   // [B x O], [B x A], [B], [B], [B x O]
 };
@@ -224,6 +232,7 @@ struct RunArgs {
   int loss_log_offset;  // first row of loss_log to write
   int profile;          // 1: CTA 0 stamps the stages of its GEMM tiles (tools/phase_profile.py); 0 in production
   int update_mode;      // UpdateMode (AdvIRL programs only)
+  HerSampling her;
 };
 
 struct Program {

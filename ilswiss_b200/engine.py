@@ -211,6 +211,11 @@ class StepEngine:
                                   C.c_uint64(seed), stats_step, _stream_ptr()), "train")
         self.last_steps = n_steps
 
+    def set_her(self, desc=None):
+        """Hindsight relabel-at-sample for the next train() calls (desc: _abi.HerSamplingDesc; None switches it off)."""
+        self._her_keep = desc
+        check(self.lib.ilsw_trainer_set_her(self.h, C.byref(desc) if desc is not None else None), "set_her")
+
     def set_update_mode(self, mode):
         """AdvIRL engines: 0 = fused disc+policy iteration, 1 = disc-only steps, 2 = policy-only steps."""
         check(self.lib.ilsw_trainer_set_update_mode(self.h, int(mode)), "set_update_mode")

@@ -147,6 +147,26 @@ int ilsw_trainer_attach_disc(ilsw_trainer* tr, const ilsw_disc_config* cfg, cons
  * gail_humanoid.yaml uses 100/100): subsequent ilsw_train calls run n_steps discriminator updates only (mode 1:
  * _do_reward_training, :133-236) or n_steps policy updates only (mode 2: _do_policy_training, :238-314, rewards from the
  * current discriminator); mode 0 restores the fused 1+1 iteration.  Adam step counts advance only for the part run. */
+/* Hindsight relabel-at-sample (rlkit/data_management/relabel_replay_buffer.py:63-131, relabel_type "future"): ring rows hold
+ * obs = cat(observation, desired_goal); the gather of every step (i) samples a finished trajectory uniformly, a step in it,
+ * and a future step of the same trajectory, (ii) overwrites the goal part of obs / next_obs of the FIRST relabel_num rows of
+ * the batch with the next achieved goal of the future step (:103-118) and (iii) recomputes every row's reward as the
+ * sparse goal reward -(||next_achieved_goal - desired_goal|| > distance_threshold) (:127-131, Fetch envs' compute_reward).
+ * All pointers are DEVICE pointers that must stay valid while set; NULL / enabled = 0 switches it off.  With injected
+ * randomness (ilsw_inject.idx = step rows) inj_idx_her [T,B] supplies the future rows. */
+typedef struct {
+  int enabled;
+  int n_traj;                   /* finished trajectories */
+  const int32_t* traj_start;    /* [n_traj] ring index of the first transition */
+  const int32_t* traj_len;      /* [n_traj] transitions in the trajectory (may wrap around the ring) */
+  const float* next_achieved_goal;   /* [capacity, goal_dim] side array, same slot numbering as the ring */
+  int goal_dim;
+  int relabel_num;              /* int(her_ratio * batch) */
+  float distance_threshold;
+  const int32_t* inj_idx_her;   /* parity mode only */
+} ilsw_her_sampling;
+int ilsw_trainer_set_her(ilsw_trainer* tr, const ilsw_her_sampling* her);
+
 enum { ILSW_UPDATE_BOTH = 0, ILSW_UPDATE_DISC_ONLY = 1, ILSW_UPDATE_POLICY_ONLY = 2 };
 int ilsw_trainer_set_update_mode(ilsw_trainer* tr, int mode);
 int ilsw_trainer_destroy(ilsw_trainer* tr);

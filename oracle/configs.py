@@ -96,6 +96,15 @@ LOOP_CASES = {
                          sac=dict(SAC_KW, reward_scale=2.0, alpha=0.2), seed=24),
 }
 
+# HER relabel-at-sample (relabel_replay_buffer.py:63-131) feeding her/td3.py: observation 10 + goal 3, 12 episodes of 50 steps
+HER_RELABEL_CASES = {
+    "her_td3_relabel": dict(algo="td3", obs_dim=13, act_dim=4, batch=64, n_fill=800, steps=4,
+                            her=dict(goal_dim=3, sigma=0.2), her_ratio=0.8, threshold=0.05, n_episodes=12, T=50,
+                            td3=dict(reward_scale=1.0, discount=0.98, soft_target_tau=0.005, policy_lr=6e-4,
+                                     qf_lr=3e-4, policy_and_target_update_period=2),
+                            policy_noise=0.2, policy_noise_clip=0.5, seed=30),
+}
+
 HIDDEN = (256, 256)
 DISC_HID = 128
 BUFFER_SEED = 1      # policy replay buffer index RNG

@@ -48,6 +48,23 @@ class FakeEnv:
         self.action_space = gs.Box(act_dim)
 
 
+class FakeGoalEnv:
+    """Goal-environment stand-in for HindsightReplayBuffer (relabel_replay_buffer.py:27-48): Dict observation space and the
+    gym-robotics sparse compute_reward."""
+
+    def __init__(self, obs_dim, goal_dim, act_dim, distance_threshold=0.05):
+        import gym.spaces as gs
+
+        d = gs.Dict(1)
+        d.spaces = dict(observation=gs.Box(obs_dim), achieved_goal=gs.Box(goal_dim), desired_goal=gs.Box(goal_dim))
+        self.observation_space, self.action_space = d, gs.Box(act_dim)
+        self.distance_threshold = distance_threshold
+
+    def compute_reward(self, achieved_goal, goal, info):
+        d = np.linalg.norm(achieved_goal - goal, axis=-1)
+        return -(d > self.distance_threshold).astype(np.float32)
+
+
 _installed = False
 
 

@@ -165,6 +165,113 @@ class ReplayOracle:
         return ret
 
 
+# --------------------------------------------------------------------------------------
+# HER: HindsightReplayBuffer (rlkit/data_management/relabel_replay_buffer.py:12-131) on top of the dict-observation mode
+# of SimpleReplayBuffer (simple_replay_buffer.py:31-43,99-104,270-279).  Observations are dicts with the keys
+# observation / achieved_goal / desired_goal; the reward function is the goal environments' sparse compute_reward
+# (-(||achieved - desired|| > distance_threshold), e.g. gym robotics FetchEnv) that the reference takes from
+# env.compute_reward (:36-37).
+# --------------------------------------------------------------------------------------
+class HindsightOracle:
+    OBS_KEYS = ("observation", "achieved_goal", "desired_goal")
+
+    def __init__(self, max_replay_buffer_size, obs_dim, goal_dim, action_dim, random_seed=1995, relabel_type="future",
+                 her_ratio=0.8, distance_threshold=0.05):
+        self._np_rand_state = np.random.RandomState(random_seed)
+        N = self._max_replay_buffer_size = max_replay_buffer_size
+        dims = dict(observation=obs_dim, achieved_goal=goal_dim, desired_goal=goal_dim)
+        self._observations = {k: np.zeros((N, d)) for k, d in dims.items()}
+        self._next_obs = {k: np.zeros((N, d)) for k, d in dims.items()}
+        self._actions = np.zeros((N, action_dim))
+        self._rewards = np.zeros((N, 1))
+        self._terminals = np.zeros((N, 1), dtype="uint8")
+        self._top = self._size = self._cur_start = 0
+        self._traj_endpoints = {}
+        self.relabel_type, self.her_ratio, self.distance_threshold = relabel_type, her_ratio, distance_threshold
+
+    def compute_reward(self, achieved, goal, info=None):
+        d = np.linalg.norm(achieved - goal, axis=-1)
+        return -(d > self.distance_threshold).astype(np.float32)
+
+    def add_sample(self, observation, action, reward, terminal, next_observation, **kwargs):
+        # simple_replay_buffer.py:78-108
+        self._actions[self._top] = action
+        self._rewards[self._top] = reward
+        self._terminals[self._top] = terminal
+        if terminal:
+            next_start = (self._top + 1) % self._max_replay_buffer_size
+            self._traj_endpoints[self._cur_start] = next_start
+            self._cur_start = next_start
+        for k, v in observation.items():
+            self._observations[k][self._top] = v
+        for k, v in next_observation.items():
+            self._next_obs[k][self._top] = v
+        if self._top in self._traj_endpoints:              # _advance, :228-237
+            del self._traj_endpoints[self._top]
+        self._top = (self._top + 1) % self._max_replay_buffer_size
+        if self._size < self._max_replay_buffer_size:
+            self._size += 1
+
+    def terminate_episode(self):
+        if self._cur_start != self._top:                   # :125-132
+            self._traj_endpoints[self._cur_start] = self._top
+            self._cur_start = self._top
+
+    def sample_indices(self, batch_size):
+        """relabel_replay_buffer.py:70-95 -- the index draws of random_batch, in the reference's RNG order (the buffer's
+        RandomState for trajectory shuffle / trajectory / step, the GLOBAL numpy RNG for the future step)."""
+        relabel = (self.relabel_type is not None) and (self.her_ratio > 0)
+        keys_list = list(self._traj_endpoints.keys())
+        starts = self._np_rand_state.choice(keys_list, size=len(keys_list), replace=False)
+        ends = [self._traj_endpoints[k] for k in starts]
+        traj_indice = self._np_rand_state.randint(0, len(starts), batch_size)
+        indices, indices_relabel = [], []
+        for i in traj_indice:
+            traj_len = (ends[i] - starts[i]) % self._size
+            step = (self._np_rand_state.randint(0, traj_len, 1)[0] + starts[i]) % self._size
+            indices.append(step)
+            if relabel:
+                step_her = {"final": ends[i] - 1,
+                            "future": np.random.randint(step, (traj_len + starts[i])) % self._size}[self.relabel_type]
+                indices_relabel.append(step_her)
+        return np.asarray(indices), np.asarray(indices_relabel)
+
+    def batch_from_indices(self, indices, indices_relabel):
+        """:97-131 -- gather, relabel the first int(her_ratio * B) rows, recompute every reward."""
+        relabel = (self.relabel_type is not None) and (self.her_ratio > 0)
+        B = len(indices)
+        obs = {k: v[indices].copy() for k, v in self._observations.items()}
+        nobs = {k: v[indices].copy() for k, v in self._next_obs.items()}
+        out = dict(actions=self._actions[indices], rewards=self._rewards[indices], terminals=self._terminals[indices])
+        if relabel:
+            n = int(self.her_ratio * B)
+            src = self._next_obs["achieved_goal"][indices_relabel]
+            obs["desired_goal"][:n] = src[:n]
+            nobs["desired_goal"][:n] = src[:n]
+        out["achieved_goals"], out["desired_goals"] = obs["achieved_goal"], obs["desired_goal"]
+        out["next_achieved_goals"], out["next_desired_goals"] = nobs["achieved_goal"], nobs["desired_goal"]
+        out["observations"], out["next_observations"] = obs["observation"], nobs["observation"]
+        if relabel:
+            out["rewards"] = self.compute_reward(out["next_achieved_goals"], out["desired_goals"]).reshape(-1, 1)
+        return out
+
+    def random_batch(self, batch_size):
+        return self.batch_from_indices(*self.sample_indices(batch_size))
+
+
+def synth_goal_episodes(rs, n_episodes, T, O0, G, A):
+    """Synthetic goal-env episodes: random walks so that future achieved goals are sometimes within the threshold."""
+    eps = []
+    for _ in range(n_episodes):
+        goal = rs.randn(G) * 0.05
+        ag = np.cumsum(rs.randn(T + 1, G) * 0.02, axis=0)
+        ob = rs.randn(T + 1, O0)
+        eps.append([(dict(observation=ob[t], achieved_goal=ag[t], desired_goal=goal), rs.uniform(-1, 1, A), -1.0,
+                     t == T - 1 and rs.rand() < 0.5, dict(observation=ob[t + 1], achieved_goal=ag[t + 1], desired_goal=goal))
+                    for t in range(T)])
+    return eps
+
+
 def np_to_torch_batch(np_batch):
     """rlkit/torch/core.py:124-143 + pytorch_util.py:84-88: per key astype(float32)."""
     return {k: torch.from_numpy(v.astype(np.float32)) for k, v in np_batch.items()}

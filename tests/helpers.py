@@ -92,6 +92,69 @@ def loop_case_injection(case):
     return out
 
 
+def her_relabel_setup(case):
+    """A HER_RELABEL_CASES case: the oracle hindsight buffer filled with synthetic goal episodes, the device-side
+    views of it (ring rows with obs = cat(observation, desired_goal), next-achieved-goal side array, trajectory table) and,
+    per step, the index draws + the relabelled oracle batch (networks see cat(obs, goal), her/td3.py:94-98)."""
+    O, A, B, G_ = case["obs_dim"], case["act_dim"], case["batch"], case["her"]["goal_dim"]
+    N, T = case["n_fill"], case["steps"]
+    ora = R.HindsightOracle(N, O - G_, G_, A, random_seed=CFG.BUFFER_SEED, her_ratio=case["her_ratio"],
+                            distance_threshold=case["threshold"])
+    rs = np.random.RandomState(case["seed"])
+    for ep in R.synth_goal_episodes(rs, case["n_episodes"], case["T"], O - G_, G_, A):
+        for (o, a, r, d, no) in ep:
+            ora.add_sample(o, a, r, d, no)
+        ora.terminate_episode()
+    cat = lambda d: np.concatenate([d["observation"], d["desired_goal"]], axis=1)
+    ring = layout.pack_hot_rows(cat(ora._observations), ora._actions, ora._rewards, ora._terminals, cat(ora._next_obs))
+    starts = np.array(list(ora._traj_endpoints.keys()), dtype=np.int32)
+    lens = np.array([(ora._traj_endpoints[int(s)] - int(s)) % ora._size for s in starts], dtype=np.int32)
+    out = dict(oracle=ora, ring=ring, ring_size=ora._size, ag_next=np.ascontiguousarray(ora._next_obs["achieved_goal"], dtype=np.float32),
+               traj_start=starts, traj_len=lens, relabel_num=int(case["her_ratio"] * B), threshold=case["threshold"],
+               idx=np.zeros((T, B), np.int32), idx_her=np.zeros((T, B), np.int32),
+               eps_next=np.zeros((T, B, A), np.float32), batches=[])
+    for t in range(T):
+        np.random.seed(CFG.EPS_SEED0 + t)               # the future-step draw uses the GLOBAL numpy RNG (:88)
+        torch.manual_seed(CFG.EPS_SEED0 + t)
+        i, ih = ora.sample_indices(B)
+        out["idx"][t], out["idx_her"][t] = i, ih
+        b = ora.batch_from_indices(i, ih)
+        out["batches"].append(dict(
+            observations=np.concatenate([b["observations"], b["desired_goals"]], axis=1),
+            next_observations=np.concatenate([b["next_observations"], b["next_desired_goals"]], axis=1),
+            actions=b["actions"], rewards=b["rewards"], terminals=b["terminals"]))
+        out["eps_next"][t] = torch.randn(B, A).numpy()
+    return out
+
+
+def her_oracle_rows(case, setup):
+    """HerTD3Oracle driven by the relabelled oracle batches: per-step statistics + final parameters."""
+    nets = G.build_oracle_nets(case)
+    h = case["her"]
+    tr = R.HerTD3Oracle(nets["policy"], nets["qf1"], nets["qf2"], sigma=h["sigma"], clip_return_l=h.get("clip_return_l"),
+                        clip_return_r=h.get("clip_return_r"), **case["td3"])
+    rows = []
+    for t, b in enumerate(setup["batches"]):
+        s = tr.train_step(R.np_to_torch_batch(b), torch.from_numpy(setup["eps_next"][t]))
+        row = {"QF1 Loss": s["qf1_loss"], "QF2 Loss": s["qf2_loss"], "Q Targets Mean": float(s["q_target"].mean())}
+        if s["policy_loss"] is not None:
+            row["Policy Loss"] = s["policy_loss"]
+        rows.append(row)
+    final = {k: n.flat() for k, n in nets.items()}
+    final["target_qf1"], final["target_policy"] = tr.target_qf1.flat(), tr.target_policy.flat()
+    return rows, final
+
+
+def her_desc(setup, ptr, inj_offset=0, n=None):
+    """_abi.HerSamplingDesc over arrays / tensors addressed through `ptr` (np_ptr on the host, data_ptr on the device)."""
+    d = _abi.HerSamplingDesc()
+    d.enabled, d.n_traj = 1, len(setup["traj_start"])
+    d.traj_start, d.traj_len, d.next_achieved_goal = ptr("traj_start"), ptr("traj_len"), ptr("ag_next")
+    d.goal_dim, d.relabel_num, d.distance_threshold = setup["ag_next"].shape[1], setup["relabel_num"], setup["threshold"]
+    d.inj_idx_her = ptr("idx_her")
+    return d
+
+
 DISC_STATS = ("Disc CE Loss", "Disc Acc", "Grad Pen")
 REW_STATS = ("Disc Rew Mean", "Disc Rew Std", "Disc Rew Max", "Disc Rew Min")
 
@@ -256,6 +319,7 @@ def load_hostsim():
     lib.hs_describe.restype = C.c_int
     lib.hs_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.hs_set_update_mode.argtypes = [C.c_void_p, C.c_int]
+    lib.hs_set_her.argtypes = [C.c_void_p, C.POINTER(_abi.HerSamplingDesc)]
     lib.hs_grad.restype = C.POINTER(C.c_float)
     lib.hs_grad.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     return lib

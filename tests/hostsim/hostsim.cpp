@@ -24,6 +24,7 @@ struct HostSim {
   int n_total;
   int generic_rows;     // 1: force the generic per-row kernels (cross-check of the fast row jobs)
   int update_mode = 0;  // UpdateMode of the next hs_train calls
+  HerSampling her = {};  // relabel-at-sample of the next hs_train calls (hs_set_her)
   std::vector<float> rowbuf;
 };
 
@@ -128,6 +129,7 @@ int hs_train(void* p, const float* ring, int stride, int size, const float* erin
   }
   a.world = 1; a.rank = 0; a.loss_log_offset = 0;
   a.update_mode = h->update_mode;
+  a.her = h->her;
   const Program& P = h->prog;
   for (int s = 0; s < n_steps; ++s)
     for (int ph = 0; ph < P.n_phases; ++ph) {
@@ -141,6 +143,14 @@ int hs_train(void* p, const float* ring, int stride, int size, const float* erin
 
 void hs_set_generic_rows(void* p, int flag) { ((HostSim*)p)->generic_rows = flag; }
 void hs_set_update_mode(void* p, int mode) { ((HostSim*)p)->update_mode = mode; }
+void hs_set_her(void* p, const ilsw_her_sampling* her) {
+  HostSim* h = (HostSim*)p;
+  memset(&h->her, 0, sizeof(h->her));
+  if (!her || !her->enabled) return;
+  h->her.enabled = 1; h->her.n_traj = her->n_traj; h->her.traj_start = her->traj_start; h->her.traj_len = her->traj_len;
+  h->her.ag_next = her->next_achieved_goal; h->her.G = her->goal_dim; h->her.relabel_num = her->relabel_num;
+  h->her.threshold = her->distance_threshold; h->her.inj_idx_her = her->inj_idx_her;
+}
 void hs_set_precision(void* p, int prec) { ((HostSim*)p)->prog.ctx.hp.gemm_precision = prec; }
 const float* hs_losses(void* p) { return ((HostSim*)p)->prog.ctx.loss_log; }
 const float* hs_stats(void* p) { return ((HostSim*)p)->prog.ctx.stats; }

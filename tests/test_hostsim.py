@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import CFG, G, HostSimRun, STAT_TO_SLOT, assert_params_close, case_injection, load_hostsim, run_loop_case
+from helpers import CFG, G, HostSimRun, STAT_TO_SLOT, assert_params_close, case_injection, load_hostsim, run_loop_case, her_relabel_setup, her_oracle_rows, her_desc, np_ptr
 
 CASES = [n for n, c in CFG.CASES.items() if c["algo"] in ("sac_alpha", "sac_v", "td3", "adv_irl")]
 
@@ -138,3 +138,35 @@ def test_hostsim_fused_iteration_equals_split_launches(lib):
     for k in a.arenas:
         np.testing.assert_array_equal(a.arenas[k], b.arenas[k], err_msg=k)
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("name", list(CFG.HER_RELABEL_CASES.keys()))
+def test_hostsim_her_relabel_at_sample_matches_oracle(lib, name):
+    """relabel_replay_buffer.py:63-131 inside the step program's gather: goal substitution from the future step's next
+    achieved goal for the first int(her_ratio B) rows, sparse reward recomputed for every row -- against the oracle
+    hindsight buffer (pinned to the reference's) feeding the HER-TD3 oracle."""
+    import ctypes as C
+
+    torch.set_num_threads(1)
+    case = CFG.HER_RELABEL_CASES[name]
+    setup = her_relabel_setup(case)
+    rows, final = her_oracle_rows(case, setup)
+    run = HostSimRun(lib, case)
+    run.ring = np.ascontiguousarray(setup["ring"][:setup["ring_size"]])
+    desc = her_desc(setup, lambda k: np_ptr(setup[k]))
+    lib.hs_set_her(run.h, C.byref(desc))
+    L = run.train(case["steps"], dict(idx=setup["idx"], eps_next=setup["eps_next"]))
+    for t, row in enumerate(rows):
+        for k, ref in row.items():
+            got = L[t, STAT_TO_SLOT[k]]
+            tol = 1e-4 * max(abs(ref), 1e-3) if k != "Policy Loss" else 1e-4 * max(abs(ref), 1.0)
+            assert abs(got - ref) <= tol, (name, t, k, got, ref)
+    for k in ("policy", "qf1", "qf2", "target_qf1", "target_policy"):
+        assert_params_close(run.arenas[k], final[k], case["steps"], lr=6e-4, msg="%s/%s" % (name, k))
+    # speed mode: in-kernel Philox trajectory / step / future-step draws run and give finite, sparse-reward targets
+    lib.hs_set_her(run.h, C.byref(desc))
+    rc = run.lib.hs_train(run.h, np_ptr(run.ring), run.ring.shape[1], run.ring.shape[0], None, 0, 0, 2, None, None, 7, -1)
+    assert rc == 0
+    L2 = np.ctypeslib.as_array(lib.hs_losses(run.h), shape=(2, 16)).copy()
+    assert np.isfinite(L2[:, :2]).all()
+    run.close()

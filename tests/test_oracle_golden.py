@@ -66,3 +66,36 @@ def test_goldens_regenerate_from_reference():
         for j, k in enumerate(keys):
             if k in row:
                 assert row[k] == pytest.approx(gold["stats"][t, j], rel=1e-6, abs=1e-9)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/rlkit"), reason="reference checkout absent")
+def test_hindsight_oracle_matches_reference_buffer():
+    """Pins HindsightOracle to the executed rlkit HindsightReplayBuffer: same index draws, same relabelled batches
+    (bit-exact)."""
+    from oracle import ref_shim
+    from oracle.restate import HindsightOracle, synth_goal_episodes
+
+    ref_shim.install()
+    from rlkit.data_management.relabel_replay_buffer import HindsightReplayBuffer
+
+    O0, G, A, N = 10, 3, 4, 400
+    env = ref_shim.FakeGoalEnv(O0, G, A)
+    ref = HindsightReplayBuffer(N, env, random_seed=5, relabel_type="future", her_ratio=0.8)
+    ora = HindsightOracle(N, O0, G, A, random_seed=5, relabel_type="future", her_ratio=0.8)
+    rs = np.random.RandomState(0)
+    for ep in synth_goal_episodes(rs, 7, 50, O0, G, A):
+        for (o, a, r, d, no) in ep:
+            ref.add_sample(o, a, r, d, no)
+            ora.add_sample(o, a, r, d, no)
+        ref.terminate_episode()
+        ora.terminate_episode()
+    assert ref._traj_endpoints == ora._traj_endpoints and ref._top == ora._top and ref._size == ora._size
+    for trial in range(3):
+        np.random.seed(100 + trial)
+        want = ref.random_batch(64)
+        np.random.seed(100 + trial)
+        got = ora.random_batch(64)
+        assert set(got.keys()) == set(want.keys())
+        for k in want:
+            np.testing.assert_array_equal(np.asarray(got[k]), np.asarray(want[k]), err_msg=k)
+        assert (want["rewards"] == 0).any() and (want["rewards"] == -1).any()          # both reward values occur
