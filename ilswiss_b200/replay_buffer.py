@@ -243,3 +243,117 @@ def get_dim(space):
     if hasattr(space, "flat_dim"):
         return int(space.flat_dim)
     raise TypeError("Unknown space: {}".format(space))
+
+
+class DeviceHindsightReplayBuffer(DeviceReplayBuffer):
+    """rlkit/data_management/relabel_replay_buffer.py:12-131 (HindsightReplayBuffer, relabel_type "future" / her_ratio) with
+    the transitions in HBM: ring rows hold obs = cat(observation, desired_goal) / next_obs likewise, a device side array
+    holds every slot's next achieved goal, and the trajectory table of finished episodes is mirrored on the device, so that
+    the step program samples trajectory -> step -> future step, relabels and recomputes the sparse goal reward INSIDE its
+    gather phase (`HerTD3.train_from_buffer` / `ilsw_trainer_set_her`).
+
+    Observations are the goal environments' dicts (keys observation / achieved_goal / desired_goal).  The reward rule is
+    the sparse one every shipped HER yaml's environment uses, -(||achieved - desired|| > distance_threshold)
+    (gym robotics `compute_reward`, which the reference takes from `env.compute_reward`, :36-37).
+    random_batch() keeps the reference's host semantics (same RNG streams: the buffer's RandomState for the trajectory
+    shuffle / trajectory / step draws, the global numpy RNG for the future step, :70-95)."""
+
+    def __init__(self, max_replay_buffer_size, obs_dim, goal_dim, action_dim, random_seed=1995, relabel_type="future",
+                 her_ratio=0.8, distance_threshold=0.05, observation_key="observation", desired_goal_key="desired_goal",
+                 achieved_goal_key="achieved_goal"):
+        if relabel_type not in ("future", None):
+            raise NotImplementedError("relabel_type %r (the shipped yamls use 'future')" % (relabel_type,))
+        super().__init__(max_replay_buffer_size, int(obs_dim) + int(goal_dim), action_dim, random_seed)
+        self._obs0_dim, self._goal_dim = int(obs_dim), int(goal_dim)
+        self.relabel_type, self.her_ratio, self.distance_threshold = relabel_type, float(her_ratio), float(distance_threshold)
+        self.observation_key, self.desired_goal_key, self.achieved_goal_key = observation_key, desired_goal_key, achieved_goal_key
+        self._ag_next = torch.zeros((self._max_replay_buffer_size, self._goal_dim), dtype=torch.float32, device="cuda")
+        self._ag_pending = []         # (slot, next achieved goal) of rows not yet staged
+        self._traj_dev = None         # (starts, lens) int32 CUDA tensors, rebuilt when the table changes
+        self._traj_dirty = True
+
+    def _cat(self, obs):
+        return np.concatenate([np.asarray(obs[self.observation_key], dtype=np.float64).ravel(),
+                               np.asarray(obs[self.desired_goal_key], dtype=np.float64).ravel()])
+
+    def add_sample(self, observation, action, reward, terminal, next_observation, **kwargs):
+        assert isinstance(observation, dict), "Observation should be dict!"           # :53
+        self._ag_pending.append((self._top, np.asarray(next_observation[self.achieved_goal_key], dtype=np.float32).ravel()))
+        n_before = len(self._traj_endpoints)
+        super().add_sample(self._cat(observation), action, reward, terminal, self._cat(next_observation), **kwargs)
+        self._traj_dirty = self._traj_dirty or len(self._traj_endpoints) != n_before or bool(np.asarray(terminal).reshape(-1)[0])
+
+    def terminate_episode(self):
+        super().terminate_episode()
+        self._traj_dirty = True
+
+    def flush(self):
+        super().flush()
+        if self._ag_pending:
+            slots = torch.as_tensor(np.array([s for s, _ in self._ag_pending], dtype=np.int64), device="cuda")
+            vals = torch.as_tensor(np.stack([v for _, v in self._ag_pending]), device="cuda")
+            self._ag_next[slots] = vals
+            self._ag_pending = []
+
+    def trajectory_table(self):
+        """(starts, lens) of the finished trajectories as int32 CUDA tensors (:68-75: [start, end) modulo the fill level)."""
+        if self._traj_dirty or self._traj_dev is None:
+            starts = np.array(list(self._traj_endpoints.keys()), dtype=np.int32)
+            lens = np.array([(self._traj_endpoints[int(s)] - int(s)) % self._size for s in starts], dtype=np.int32)
+            keep = lens > 0
+            self._traj_dev = (torch.as_tensor(starts[keep], device="cuda"), torch.as_tensor(lens[keep], device="cuda"))
+            self._traj_dirty = False
+        return self._traj_dev
+
+    def her_desc(self, batch_size, inj_idx_her=None):
+        """The ilsw_her_sampling descriptor of this buffer for a trainer with `batch_size` rows per step."""
+        from . import _abi
+
+        self.flush()
+        starts, lens = self.trajectory_table()
+        d = _abi.HerSamplingDesc()
+        d.enabled, d.n_traj = 1, int(starts.numel())
+        d.traj_start, d.traj_len, d.next_achieved_goal = starts.data_ptr(), lens.data_ptr(), self._ag_next.data_ptr()
+        d.goal_dim, d.distance_threshold = self._goal_dim, self.distance_threshold
+        relabel = (self.relabel_type is not None) and (self.her_ratio > 0)
+        d.relabel_num = int(self.her_ratio * batch_size) if relabel else 0
+        d.inj_idx_her = inj_idx_her.data_ptr() if inj_idx_her is not None else None
+        self._desc_keep = (starts, lens, inj_idx_her)
+        return d
+
+    # -- host-facing sampling with the reference's semantics ---------------------------------
+    def sample_indices(self, batch_size):
+        relabel = (self.relabel_type is not None) and (self.her_ratio > 0)
+        keys_list = list(self._traj_endpoints.keys())
+        starts = self._np_rand_state.choice(keys_list, size=len(keys_list), replace=False)
+        ends = [self._traj_endpoints[k] for k in starts]
+        traj_indice = self._np_rand_state.randint(0, len(starts), batch_size)
+        indices, indices_relabel = [], []
+        for i in traj_indice:
+            traj_len = (ends[i] - starts[i]) % self._size
+            step = (self._np_rand_state.randint(0, traj_len, 1)[0] + starts[i]) % self._size
+            indices.append(step)
+            if relabel:
+                indices_relabel.append(np.random.randint(step, (traj_len + starts[i])) % self._size)
+        return np.asarray(indices), np.asarray(indices_relabel)
+
+    def random_batch(self, batch_size, keys=None, **kwargs):
+        """:63-131 -- the reference's goal-conditioned batch dict (observations / desired_goals / achieved_goals / next_* /
+        actions / rewards / terminals), relabelled."""
+        idx, idx_her = self.sample_indices(batch_size)
+        self.flush()
+        O0 = self._obs0_dim
+        full = self._get_batch_using_indices(idx, keys=None)
+        ag_next = self._ag_next[torch.as_tensor(idx, device="cuda", dtype=torch.long)].cpu().numpy().astype(np.float64)
+        out = dict(actions=full["actions"], terminals=full["terminals"], rewards=full["rewards"],
+                   observations=full["observations"][:, :O0], next_observations=full["next_observations"][:, :O0],
+                   desired_goals=full["observations"][:, O0:].copy(), next_desired_goals=full["next_observations"][:, O0:].copy(),
+                   next_achieved_goals=ag_next)
+        if len(idx_her):
+            n = int(self.her_ratio * batch_size)
+            src = self._ag_next[torch.as_tensor(idx_her, device="cuda", dtype=torch.long)].cpu().numpy().astype(np.float64)
+            out["desired_goals"][:n] = src[:n]
+            out["next_desired_goals"][:n] = src[:n]
+            d = np.linalg.norm(out["next_achieved_goals"] - out["desired_goals"], axis=-1)
+            out["rewards"] = (-(d > self.distance_threshold).astype(np.float32)).reshape(-1, 1)
+        return out

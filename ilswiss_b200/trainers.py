@@ -480,7 +480,33 @@ class TD3(_FusedTrainer):
         self.engine.set_state(st)
 
 
-class HerTD3(TD3):
+class _HindsightMixin:
+    """Goal-conditioned batches (desired_goals keys) for train_step; hindsight sampling inside the gather for
+    train_from_buffer on a DeviceHindsightReplayBuffer."""
+
+    def train_step(self, batch):
+        super().train_step(_concat_goals(batch))
+
+    def train_from_buffer(self, replay_buffer, n_steps, inject=None):
+        """With a DeviceHindsightReplayBuffer the hindsight sampling + relabel (relabel_replay_buffer.py:63-131) runs
+        inside the step program's gather phase; inject (parity mode) then also carries `idx_her` [T, B]."""
+        if hasattr(replay_buffer, "her_desc"):
+            her_idx = None
+            if inject is not None:
+                inject = dict(inject)
+                her_idx = inject.pop("idx_her").contiguous()
+            if her_idx is not None and n_steps > self._cfg.max_steps_per_call:
+                raise ValueError("injected hindsight runs must fit one launch")
+            self.engine.set_her(replay_buffer.her_desc(self._cfg.batch, her_idx))
+            try:
+                super().train_from_buffer(replay_buffer, n_steps, inject=inject)
+            finally:
+                self.engine.set_her(None)
+        else:
+            super().train_from_buffer(replay_buffer, n_steps, inject=inject)
+
+
+class HerTD3(_HindsightMixin, TD3):
     """rlkit/torch/algorithms/her/td3.py:14-245 -- goal-conditioned TD3 (exp_specs/her/her_*_td3.yaml through
     run_scripts/her_td3_exp_script.py:69-88).  Networks take cat(observation, desired_goal); the three differences from
     TD3 are those of the reference (her/td3.py:103-112, :116-120, :150-152): the next action is the clipped noise alone
@@ -505,9 +531,6 @@ class HerTD3(TD3):
         cfg.clip_return_l = -gamma_sum if cl is None else float(cl)
         cfg.clip_return_r = 0.0 if cr is None else float(cr)
 
-    def train_step(self, batch):
-        super().train_step(_concat_goals(batch))
-
 
 def _concat_goals(batch):
     """her/td3.py:94-98, her/sac.py:80-84: networks see cat(obs, desired_goal) / cat(next_obs, next_desired_goal)."""
@@ -522,7 +545,7 @@ def _concat_goals(batch):
     return batch
 
 
-class HerSAC(SoftActorCritic):
+class HerSAC(_HindsightMixin, SoftActorCritic):
     """rlkit/torch/algorithms/her/sac.py:12-251 (run_scripts/her_sac_exp_script.py) -- goal-conditioned SAC with the
     auto-tuned alpha.  The step is sac_alpha's on cat(observation, desired_goal) (her/sac.py:80-143); the one numeric
     difference is the default target entropy: -prod(action_space.shape) (her/sac.py:52), not half of it."""
@@ -534,6 +557,3 @@ class HerSAC(SoftActorCritic):
             else:
                 kwargs["target_entropy"] = -float(list(policy.parameters())[4].shape[0])
         super().__init__(policy, qf1, qf2, **kwargs)
-
-    def train_step(self, batch):
-        super().train_step(_concat_goals(batch))
