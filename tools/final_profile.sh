@@ -9,6 +9,9 @@ for w in gail_walker td3_humanoid sac_ant her_td3_pick; do
 done
 python bench.py --impl reference --steps 1500 --warmup 20 > $OUT/bench_reference_sac_hopper.json 2> $OUT/bench_reference.err
 python tools/phase_profile.py sac_hopper gail_walker td3_humanoid > $OUT/phase_profile.txt 2>&1
+if [ "${SKIP_NCU:-0}" = "1" ]; then ls $OUT; for f in $OUT/bench_*.json; do python -c "
+import json, sys
+d = json.load(open('$f')); print('$f'.split('/')[-1], d.get('value'), (d.get('e2e') or {}).get('value'), (d.get('cpu_baseline') or {}).get('value'))"; done; exit 0; fi
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/ncu_launches.csv \
     python bench.py --steps 3000 --warmup 1000 --e2e-steps 20 --no-cpu-baseline --precision 3 > $OUT/ncu_launches_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:ilsw_engine_kernel -s 2 -c 1 -f -o $OUT/engine_full \
