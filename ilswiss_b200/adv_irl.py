@@ -217,6 +217,28 @@ class DeviceTorchRLAlgorithmMixin(_DeviceSamplerMixin):
         self.trainer.train_from_buffer(self.replay_buffer, self.num_train_steps_per_train_call)
 
 
+class DeviceHERMixin:
+    """Put in front of rlkit's HER (rlkit/torch/algorithms/her/her.py:8-42): `class HER(DeviceHERMixin, RefHER)` with
+    replay_buffer=DeviceEnvHindsightReplayBuffer(...) and an ilswiss_b200 HerTD3 / HerSAC trainer.  A train call is one
+    launch whose gather phase does the hindsight sampling + relabel; get_batch keeps the reference's host semantics."""
+
+    def get_batch(self, keys=None):
+        from .replay_buffer import DeviceHindsightReplayBuffer
+
+        if not isinstance(self.replay_buffer, DeviceHindsightReplayBuffer):
+            return super().get_batch(keys=keys)
+        b = self.replay_buffer.random_batch(self.batch_size)
+        return {k: torch.as_tensor(np.asarray(v, dtype=np.float32), device="cuda") for k, v in b.items()}
+
+    def _do_training(self, epoch):
+        from .replay_buffer import DeviceHindsightReplayBuffer
+
+        if not isinstance(self.replay_buffer, DeviceHindsightReplayBuffer) or not hasattr(self.trainer, "ensure_batch"):
+            return super()._do_training(epoch)
+        self.trainer.ensure_batch(self.batch_size, self.num_train_steps_per_train_call)
+        self.trainer.train_from_buffer(self.replay_buffer, self.num_train_steps_per_train_call)
+
+
 class DeviceAdvIRLMixin(_DeviceSamplerMixin):
     """Put in front of rlkit's AdvIRL: `class AdvIRL(DeviceAdvIRLMixin, RefAdvIRL)`."""
 

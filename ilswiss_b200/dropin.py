@@ -16,9 +16,12 @@ SoftActorCritic`, sac_alpha_exp_script.py:21), so replacing the module attribute
     rlkit.torch.algorithms.adv_irl.adv_irl.AdvIRL               -> DeviceAdvIRLMixin in front of the original
     rlkit.data_management.env_replay_buffer.EnvReplayBuffer     -> replay_buffer.DeviceEnvReplayBuffer
       (also the name BaseAlgorithm bound at import time, base_algorithm.py:9,116-123)
+    rlkit.torch.algorithms.her.her.HER                          -> DeviceHERMixin in front of the original
+    rlkit.torch.algorithms.her.her.HindsightReplayBuffer        -> replay_buffer.DeviceEnvHindsightReplayBuffer
+      (the name HER.__init__ uses when no buffer is passed, her.py:16-25)
 
-`rlkit.torch.algorithms.her.her.HER` keeps the reference's host relabel buffer and per-step `train_step(batch)` calls
-(it subclasses the ORIGINAL TorchRLAlgorithm, bound when her.py was imported); HerTD3 / HerSAC take its batches.
+The HER class subclasses the ORIGINAL TorchRLAlgorithm (bound when her.py was imported); with any other replay buffer or
+trainer the mixin falls through to the reference's host relabel buffer and per-step `train_step(batch)` calls.
 The trainers adopt the algorithm's `batch_size` on first use (`ensure_batch`).  `uninstall()` restores everything.
 """
 import importlib
@@ -47,7 +50,13 @@ def install(reference_root=None):
     _patch("rlkit.torch.algorithms.her.td3", "TD3", trainers.HerTD3)
     _patch("rlkit.torch.algorithms.her.sac", "SAC", trainers.HerSAC)
     # her.py must bind the ORIGINAL TorchRLAlgorithm: import it before the class is replaced
-    importlib.import_module("rlkit.torch.algorithms.her.her")
+    ref_her = importlib.import_module("rlkit.torch.algorithms.her.her").HER
+
+    class HER(adv_irl.DeviceHERMixin, ref_her):
+        __doc__ = ref_her.__doc__
+
+    _patch("rlkit.torch.algorithms.her.her", "HindsightReplayBuffer", replay_buffer.DeviceEnvHindsightReplayBuffer)
+    _patch("rlkit.torch.algorithms.her.her", "HER", HER)
     ref_alg = importlib.import_module("rlkit.torch.algorithms.torch_rl_algorithm").TorchRLAlgorithm
     ref_irl = importlib.import_module("rlkit.torch.algorithms.adv_irl.adv_irl").AdvIRL
 

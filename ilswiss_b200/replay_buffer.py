@@ -357,3 +357,18 @@ class DeviceHindsightReplayBuffer(DeviceReplayBuffer):
             d = np.linalg.norm(out["next_achieved_goals"] - out["desired_goals"], axis=-1)
             out["rewards"] = (-(d > self.distance_threshold).astype(np.float32)).reshape(-1, 1)
         return out
+
+
+class DeviceEnvHindsightReplayBuffer(DeviceHindsightReplayBuffer):
+    """HindsightReplayBuffer's own constructor signature (relabel_replay_buffer.py:13-48): dims from the goal environment's
+    Dict observation space, the sparse-reward threshold from `env.distance_threshold` (gym robotics; default 0.05)."""
+
+    def __init__(self, max_replay_buffer_size, env, random_seed=1995, relabel_type="future", her_ratio=0.8,
+                 observation_key="observation", desired_goal_key="desired_goal", achieved_goal_key="achieved_goal"):
+        spaces = env.observation_space.spaces
+        self._ob_space, self._action_space = env.observation_space, env.action_space
+        thr = float(getattr(getattr(env, "unwrapped", env), "distance_threshold", getattr(env, "distance_threshold", 0.05)))
+        super().__init__(max_replay_buffer_size, get_dim(spaces[observation_key]), get_dim(spaces[desired_goal_key]),
+                         get_dim(self._action_space), random_seed=random_seed, relabel_type=relabel_type, her_ratio=her_ratio,
+                         distance_threshold=thr, observation_key=observation_key, desired_goal_key=desired_goal_key,
+                         achieved_goal_key=achieved_goal_key)

@@ -28,9 +28,11 @@ def test_install_replaces_the_classes_the_run_scripts_import():
         assert issubclass(m_irl.AdvIRL, adv_irl.DeviceAdvIRLMixin) and issubclass(m_irl.AdvIRL, ref_irl)
         assert m_alg.TorchRLAlgorithm._do_training is adv_irl.DeviceTorchRLAlgorithmMixin._do_training
         assert base.EnvReplayBuffer is replay_buffer.DeviceEnvReplayBuffer
-        # HER keeps the reference's algorithm class (host relabel buffer, per-step train_step)
-        from rlkit.torch.algorithms.her.her import HER
-        assert not issubclass(HER, adv_irl.DeviceTorchRLAlgorithmMixin) and issubclass(HER, ref_alg)
+        # HER: our mixin in front of the reference class, which itself still derives from the ORIGINAL TorchRLAlgorithm
+        import rlkit.torch.algorithms.her.her as m_her
+        assert issubclass(m_her.HER, adv_irl.DeviceHERMixin) and issubclass(m_her.HER, ref_alg)
+        assert not issubclass(m_her.HER, adv_irl.DeviceTorchRLAlgorithmMixin)
+        assert m_her.HindsightReplayBuffer is replay_buffer.DeviceEnvHindsightReplayBuffer
         dropin.install()                   # idempotent
     finally:
         dropin.uninstall()

@@ -83,3 +83,56 @@ def test_device_hindsight_buffer_random_batch_matches_oracle():
         for k in ("observations", "next_observations", "desired_goals", "next_desired_goals", "actions", "rewards", "terminals",
                   "next_achieved_goals"):
             np.testing.assert_array_equal(np.asarray(got[k], dtype=np.float32), np.asarray(want[k], dtype=np.float32), err_msg=k)
+
+
+def test_her_algorithm_mixin_and_env_buffer_constructor():
+    """DeviceHERMixin in front of a stand-in of rlkit's HER (her.py:8-33) with the buffer built from a goal env's spaces."""
+    from ilswiss_b200.adv_irl import DeviceHERMixin
+    from ilswiss_b200.replay_buffer import DeviceEnvHindsightReplayBuffer
+    from ilswiss_b200.trainers import HerTD3
+
+    case = CFG.HER_RELABEL_CASES["her_td3_relabel"]
+    O, A, G_ = case["obs_dim"], case["act_dim"], case["her"]["goal_dim"]
+
+    class Box:
+        def __init__(self, n):
+            self.low, self.shape = -np.ones(n), (n,)
+
+    class Dict:
+        def __init__(self, **spaces):
+            self.spaces = spaces
+
+    class Env:
+        observation_space = Dict(observation=Box(O - G_), achieved_goal=Box(G_), desired_goal=Box(G_))
+        action_space = Box(A)
+        distance_threshold = 0.05
+
+    buf = DeviceEnvHindsightReplayBuffer(case["n_fill"], Env(), random_seed=3, relabel_type="future", her_ratio=0.8)
+    assert buf._obs0_dim == O - G_ and buf._goal_dim == G_ and buf.distance_threshold == 0.05
+    rs = np.random.RandomState(1)
+    for ep in R.synth_goal_episodes(rs, 6, 40, O - G_, G_, A):
+        for (o, a, r, d, no) in ep:
+            buf.add_sample(o, a, r, d, no)
+        buf.terminate_episode()
+    mods = _modules(case)
+
+    class RefHER:                                   # attribute names of torch_rl_algorithm.py:8-34 / her.py
+        def __init__(self, trainer, replay_buffer):
+            self.trainer, self.replay_buffer = trainer, replay_buffer
+            self.batch_size, self.num_train_steps_per_train_call = 32, 25
+
+        def _do_training(self, epoch):
+            raise AssertionError("reference path must be overridden")
+
+    class HER(DeviceHERMixin, RefHER):
+        pass
+
+    alg = HER(HerTD3(mods["policy"], mods["qf1"], mods["qf2"], **case["td3"]), buf)
+    n0 = alg.trainer.engine.kernel_launches
+    alg._do_training(0)
+    assert alg.trainer._cfg.batch == 32                                       # adopted from the algorithm
+    assert alg.trainer.engine.kernel_launches == n0 + 1 and alg.trainer.engine.get_state().n_train_steps_total == 25
+    b = alg.get_batch()
+    assert b["observations"].shape == (32, O - G_) and b["desired_goals"].shape == (32, G_) and b["rewards"].is_cuda
+    alg.trainer.train_step(b)                                                 # the reference's per-step path works too
+    assert np.isfinite(alg.trainer.get_eval_statistics()["QF1 Loss"])
