@@ -44,7 +44,7 @@ def _loss_tol(k, ref):
 @pytest.mark.parametrize("precision", [0, 1, 3])
 @pytest.mark.parametrize("name", CASES)
 def test_cuda_step_matches_oracle(name, precision):
-    if precision == 1 and name in TF32_SINGLE_PASS_NOT_MEASURED:
+    if precision == 1 and name in TF32_SINGLE_PASS_NOT_MEASURED and not os.environ.get("ILSW_TF32_ALL"):
         pytest.skip("opt-in single-pass TF32 mode: tolerance not yet measured on a B200 for this case (modes 0 and 3 are)")
     torch.set_num_threads(1)
     case = CFG.CASES[name]
