@@ -103,6 +103,10 @@ HER_RELABEL_CASES = {
                             td3=dict(reward_scale=1.0, discount=0.98, soft_target_tau=0.005, policy_lr=6e-4,
                                      qf_lr=3e-4, policy_and_target_update_period=2),
                             policy_noise=0.2, policy_noise_clip=0.5, seed=30),
+    # the same buffer feeding her/sac.py (the SAC program gathers the NEXT step's batch in its last phase)
+    "her_sac_relabel": dict(algo="sac_alpha", obs_dim=13, act_dim=4, batch=64, n_fill=800, steps=4,
+                            her=dict(goal_dim=3), her_ratio=0.8, threshold=0.05, n_episodes=12, T=50,
+                            sac=dict(SAC_KW, alpha=0.2, target_entropy=-4.0), seed=31),
 }
 
 HIDDEN = (256, 256)

@@ -112,7 +112,7 @@ def her_relabel_setup(case):
     out = dict(oracle=ora, ring=ring, ring_size=ora._size, ag_next=np.ascontiguousarray(ora._next_obs["achieved_goal"], dtype=np.float32),
                traj_start=starts, traj_len=lens, relabel_num=int(case["her_ratio"] * B), threshold=case["threshold"],
                idx=np.zeros((T, B), np.int32), idx_her=np.zeros((T, B), np.int32),
-               eps_next=np.zeros((T, B, A), np.float32), batches=[])
+               eps_next=np.zeros((T, B, A), np.float32), eps_cur=np.zeros((T, B, A), np.float32), batches=[])
     for t in range(T):
         np.random.seed(CFG.EPS_SEED0 + t)               # the future-step draw uses the GLOBAL numpy RNG (:88)
         torch.manual_seed(CFG.EPS_SEED0 + t)
@@ -124,6 +124,7 @@ def her_relabel_setup(case):
             next_observations=np.concatenate([b["next_observations"], b["next_desired_goals"]], axis=1),
             actions=b["actions"], rewards=b["rewards"], terminals=b["terminals"]))
         out["eps_next"][t] = torch.randn(B, A).numpy()
+        out["eps_cur"][t] = torch.randn(B, A).numpy()
     return out
 
 
@@ -131,6 +132,16 @@ def her_oracle_rows(case, setup):
     """HerTD3Oracle driven by the relabelled oracle batches: per-step statistics + final parameters."""
     nets = G.build_oracle_nets(case)
     h = case["her"]
+    if case["algo"] == "sac_alpha":          # her/sac.py == sac_alpha on cat(obs, goal) with target entropy -A
+        tr = R.SacAlphaOracle(nets["policy"], nets["qf1"], nets["qf2"], case["act_dim"], **case["sac"])
+        rows = []
+        for t, b in enumerate(setup["batches"]):
+            s = tr.train_step(R.np_to_torch_batch(b), torch.from_numpy(setup["eps_next"][t]), torch.from_numpy(setup["eps_cur"][t]))
+            rows.append({"QF1 Loss": s["qf1_loss"], "QF2 Loss": s["qf2_loss"], "Policy Loss": s["policy_loss"],
+                         "Alpha Loss": s["alpha_loss"]})
+        final = {k: n.flat() for k, n in nets.items()}
+        final["target_qf1"] = tr.target_qf1.flat()
+        return rows, final
     tr = R.HerTD3Oracle(nets["policy"], nets["qf1"], nets["qf2"], sigma=h["sigma"], clip_return_l=h.get("clip_return_l"),
                         clip_return_r=h.get("clip_return_r"), **case["td3"])
     rows = []

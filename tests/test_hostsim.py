@@ -155,13 +155,13 @@ def test_hostsim_her_relabel_at_sample_matches_oracle(lib, name):
     run.ring = np.ascontiguousarray(setup["ring"][:setup["ring_size"]])
     desc = her_desc(setup, lambda k: np_ptr(setup[k]))
     lib.hs_set_her(run.h, C.byref(desc))
-    L = run.train(case["steps"], dict(idx=setup["idx"], eps_next=setup["eps_next"]))
+    L = run.train(case["steps"], dict(idx=setup["idx"], eps_next=setup["eps_next"], eps_cur=setup["eps_cur"]))
     for t, row in enumerate(rows):
         for k, ref in row.items():
             got = L[t, STAT_TO_SLOT[k]]
             tol = 1e-4 * max(abs(ref), 1e-3) if k != "Policy Loss" else 1e-4 * max(abs(ref), 1.0)
             assert abs(got - ref) <= tol, (name, t, k, got, ref)
-    for k in ("policy", "qf1", "qf2", "target_qf1", "target_policy"):
+    for k in final:
         assert_params_close(run.arenas[k], final[k], case["steps"], lr=6e-4, msg="%s/%s" % (name, k))
     # speed mode: in-kernel Philox trajectory / step / future-step draws run and give finite, sparse-reward targets
     lib.hs_set_her(run.h, C.byref(desc))
