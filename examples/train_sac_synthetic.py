@@ -26,7 +26,7 @@ class SyntheticVecEnv:
     def __init__(self, n, obs_dim=11, act_dim=3, seed=0):
         self.rs = np.random.RandomState(seed)
         self.n, self.O, self.A = n, obs_dim, act_dim
-        self.Amat = 0.95 * np.eye(obs_dim) + 0.02 * self.rs.randn(obs_dim, obs_dim)
+        self.Amat = 0.8 * np.eye(obs_dim) + 0.02 * self.rs.randn(obs_dim, obs_dim)       # spectral radius < 1: stable
         self.Bmat = 0.3 * self.rs.randn(obs_dim, act_dim)
         self.state = self.rs.randn(n, obs_dim)
 
@@ -35,7 +35,7 @@ class SyntheticVecEnv:
         return self.state.copy()
 
     def step(self, act):
-        nxt = self.state @ self.Amat.T + act @ self.Bmat.T + 0.05 * self.rs.randn(self.n, self.O)
+        nxt = np.clip(self.state @ self.Amat.T + act @ self.Bmat.T + 0.05 * self.rs.randn(self.n, self.O), -10.0, 10.0)
         rew = -(nxt ** 2).sum(1) * 0.1 - 0.01 * (act ** 2).sum(1)
         self.state = nxt
         return nxt.copy(), rew, np.zeros(self.n, dtype=bool)
