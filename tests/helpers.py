@@ -330,6 +330,7 @@ def load_hostsim():
     lib.hs_describe.restype = C.c_int
     lib.hs_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.hs_set_update_mode.argtypes = [C.c_void_p, C.c_int]
+    lib.hs_set_world.argtypes = [C.c_void_p, C.c_int]
     lib.hs_set_her.argtypes = [C.c_void_p, C.POINTER(_abi.HerSamplingDesc)]
     lib.hs_grad.restype = C.POINTER(C.c_float)
     lib.hs_grad.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]

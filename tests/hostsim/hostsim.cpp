@@ -25,6 +25,7 @@ struct HostSim {
   int generic_rows;     // 1: force the generic per-row kernels (cross-check of the fast row jobs)
   int update_mode = 0;  // UpdateMode of the next hs_train calls
   HerSampling her = {};  // relabel-at-sample of the next hs_train calls (hs_set_her)
+  int world = 1;         // > 1: run the N-replica program (COND_WORLD_N phases) with R IDENTICAL replicas emulated
   std::vector<float> rowbuf;
 };
 
@@ -66,7 +67,17 @@ static void run_op(HostSim* hs, const Program& P, const Op& o, const RunArgs& a,
   } else if (o.kind == OP_ADAM) {
     if (o.adam.fused_only) return;                 // applied by the GEMM epilogues that reference it
     AdamCoef cf = adam_coef(o.adam, adam_t(a, c.hp, o.adam.slot, s), a.world);
-    for (int i = o.adam.begin; i < o.adam.n; ++i) adam_elem(o.adam, cf, i);
+    if (a.world > 1 && o.adam.grad_scale_world) {
+      // the exchange of R identical replicas: every receive slot holds this replica's gradient; summed in rank order and
+      // scaled by 1/R exactly as replica_reduced_grad + adam_job do on the device
+      for (int i = o.adam.begin; i < o.adam.n; ++i) {
+        float gs = 0.f;
+        for (int r = 0; r < a.world; ++r) gs += o.adam.g[i];
+        adam_elem_g(o.adam, cf, i, gs * cf.gscale);
+      }
+    } else {
+      for (int i = o.adam.begin; i < o.adam.n; ++i) adam_elem(o.adam, cf, i);
+    }
   } else if (o.kind == OP_POLYAK) {
     for (int i = 0; i < o.polyak.n; ++i) polyak_elem(o.polyak, i);
   }
@@ -127,7 +138,7 @@ int hs_train(void* p, const float* ring, int stride, int size, const float* erin
     a.has_direct = 1;
     a.direct = {batch->obs, batch->act, batch->rew, batch->term, batch->next_obs};
   }
-  a.world = 1; a.rank = 0; a.loss_log_offset = 0;
+  a.world = h->world; a.rank = 0; a.loss_log_offset = 0;
   a.update_mode = h->update_mode;
   a.her = h->her;
   const Program& P = h->prog;
@@ -143,6 +154,7 @@ int hs_train(void* p, const float* ring, int stride, int size, const float* erin
 
 void hs_set_generic_rows(void* p, int flag) { ((HostSim*)p)->generic_rows = flag; }
 void hs_set_update_mode(void* p, int mode) { ((HostSim*)p)->update_mode = mode; }
+void hs_set_world(void* p, int world) { ((HostSim*)p)->world = world > 1 ? world : 1; }
 void hs_set_her(void* p, const ilsw_her_sampling* her) {
   HostSim* h = (HostSim*)p;
   memset(&h->her, 0, sizeof(h->her));

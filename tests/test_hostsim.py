@@ -170,3 +170,30 @@ def test_hostsim_her_relabel_at_sample_matches_oracle(lib, name):
     L2 = np.ctypeslib.as_array(lib.hs_losses(run.h), shape=(2, 16)).copy()
     assert np.isfinite(L2[:, :2]).all()
     run.close()
+
+
+@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper", "sacv_hopper"])
+@pytest.mark.parametrize("world", [2, 8])
+def test_hostsim_replica_program_with_identical_replicas_equals_single_replica(lib, name, world):
+    """SURVEY.md 8e on the CPU: the N-replica step program (un-fused policy weight gradients -> exchange -> flat Adam of the
+    averaged gradient, COND_WORLD_N phases) run with R identical replicas is bit-identical to the single-replica program
+    (Adam fused into the weight-gradient epilogues) at R = 2, where (g + g) / 2 == g exactly; at R = 8 the rank-order sum
+    g + g + ... rounds (3g is not exact), so the two programs agree to round-off only."""
+    case = CFG.CASES[name]
+    inj = case_injection(case)
+    a = HostSimRun(lib, case)
+    La = a.train(case["steps"], inj)
+    b = HostSimRun(lib, case)
+    lib.hs_set_world(b.h, world)
+    Lb = b.train(case["steps"], inj)
+    if world == 2:
+        np.testing.assert_array_equal(np.nan_to_num(La), np.nan_to_num(Lb))
+        for k in a.arenas:
+            np.testing.assert_array_equal(a.arenas[k], b.arenas[k], err_msg=k)
+        for k in a.moms:
+            np.testing.assert_array_equal(a.moms[k][0], b.moms[k][0], err_msg=k + ".m")
+    else:
+        np.testing.assert_allclose(np.nan_to_num(La), np.nan_to_num(Lb), rtol=2e-5, atol=1e-6)
+        for k in a.arenas:
+            assert_params_close(b.arenas[k], a.arenas[k], case["steps"], msg=k)
+    a.close(); b.close()
