@@ -88,3 +88,60 @@ class MakeDeterministic:
 
     def to(self, device):
         self.stochastic_policy.to(device)
+
+
+class HerDevicePolicy(DevicePolicy):
+    """Goal-conditioned exploration policy of the HER scripts (MlpGaussianAndEpsilonConditionPolicy,
+    rlkit/torch/common/policies.py:481-560 + ConditionPolicy.get_actions :618-642) on the device round trip.
+
+    Observations may be the goal environments' dicts (or lists of dicts): cat(observation, desired_goal) goes to the kernel
+    (deterministic forward, max_act * tanh), and the exploration rule of the reference runs on the host with the SAME
+    random sources and call order (:546-560): with probability epsilon (python `random`) the whole batch is replaced by
+    action_space samples, otherwise Gaussian noise (numpy global RNG) with the decayed sigma is added and the result
+    clipped to [min_act, max_act]."""
+
+    def __init__(self, trainer, action_space, epsilon=0.3, max_sigma=0.2, min_sigma=0.2, decay_period=1000000,
+                 max_act=1.0, min_act=-1.0, observation_key="observation", desired_goal_key="desired_goal",
+                 achieved_goal_key="achieved_goal", seed=None):
+        super().__init__(trainer, seed=seed)
+        self._action_space, self._epsilon = action_space, epsilon
+        self._max_sigma, self._min_sigma = max_sigma, (max_sigma if min_sigma is None else min_sigma)
+        self._decay_period, self.max_act, self.min_act = decay_period, max_act, min_act
+        self.sigma, self.t = max_sigma, 0
+        self.observation_key, self.desired_goal_key, self.achieved_goal_key = observation_key, desired_goal_key, achieved_goal_key
+
+    def set_num_steps_total(self, t):
+        self.t = t
+
+    def _flatten(self, obs):
+        if isinstance(obs, dict):
+            return np.concatenate([obs[self.observation_key], obs[self.desired_goal_key]], axis=-1)
+        if len(obs) and isinstance(obs[0], dict):
+            return np.array([np.concatenate([x[self.observation_key], x[self.desired_goal_key]], axis=-1) for x in obs])
+        return np.asarray(obs)
+
+    def _deterministic(self, obs2d):
+        self._calls += 1
+        return self.trainer.engine.policy_act_host(obs2d, deterministic=True, seed=(self._seed << 20) + self._calls)
+
+    def get_actions(self, obs_np, deterministic=False):
+        import random
+
+        obs = np.asarray(self._flatten(obs_np), dtype=np.float32)
+        single = obs.ndim == 1
+        action = self._deterministic(obs[None] if single else obs)
+        action = action[0] if single else action
+        if deterministic:
+            return action
+        if random.random() < self._epsilon:                                           # :546-550
+            action = self._action_space.sample()             # drawn (and discarded for a batch) exactly as the reference does
+            if not single:
+                action = [self._action_space.sample() for _ in range(obs.shape[0])]
+            return action
+        self.sigma = self._max_sigma - (self._max_sigma - self._min_sigma) * min(1.0, self.t * 1.0 / self._decay_period)
+        return np.clip(action + np.random.normal(size=np.shape(action)) * self.sigma, self.min_act, self.max_act)
+
+    def get_action(self, obs_np, deterministic=False):
+        obs = self._flatten(obs_np)
+        actions = self.get_actions(np.asarray(obs)[None], deterministic=deterministic)
+        return np.asarray(actions)[0, :], {}
