@@ -222,6 +222,33 @@ class DeviceHERMixin:
     replay_buffer=DeviceEnvHindsightReplayBuffer(...) and an ilswiss_b200 HerTD3 / HerSAC trainer.  A train call is one
     launch whose gather phase does the hindsight sampling + relabel; get_batch keeps the reference's host semantics."""
 
+    def _ilsw_her_policy(self):
+        dp = getattr(self, "_ilsw_dp", None)
+        if dp is None:
+            from .sampler import HerDevicePolicy
+
+            pol = getattr(self.trainer, "policy", None)
+            ok = (pol is not None and self.exploration_policy is pol and hasattr(self.trainer, "engine")
+                  and all(hasattr(pol, a) for a in ("_epsilon", "_max_sigma", "_min_sigma", "_decay_period", "_action_space")))
+            dp = False
+            if ok:      # MlpGaussianAndEpsilonConditionPolicy (policies.py:481-560, 645-684): same rule, device forward
+                dp = HerDevicePolicy(self.trainer, pol._action_space, epsilon=pol._epsilon, max_sigma=pol._max_sigma,
+                                     min_sigma=pol._min_sigma, decay_period=pol._decay_period, max_act=pol.max_act,
+                                     min_act=pol.min_act, observation_key=getattr(pol, "observation_key", "observation"),
+                                     desired_goal_key=getattr(pol, "desired_goal_key", "desired_goal"),
+                                     achieved_goal_key=getattr(pol, "achieved_goal_key", "achieved_goal"))
+            self._ilsw_dp = dp
+        return dp
+
+    def _get_action_and_info(self, observation):
+        # her.py:33-42 with the policy forward on the device round trip
+        dp = self._ilsw_her_policy()
+        if dp is False:
+            return super()._get_action_and_info(observation)
+        self.exploration_policy.set_num_steps_total(self._n_env_steps_total)
+        dp.set_num_steps_total(self._n_env_steps_total)
+        return dp.get_actions(observation)
+
     def get_batch(self, keys=None):
         from .replay_buffer import DeviceHindsightReplayBuffer
 

@@ -14,6 +14,16 @@ def host_row_floats(obs_dim, act_dim):
     return 2 * obs_dim + act_dim + 5
 
 
+def derive_seed(salt=0):
+    """A Philox seed that is reproducible under np.random.seed(...) but does NOT advance numpy's global stream: that stream
+    belongs to the reference's own code (buffer seeds drawn by the run scripts, exploration noise, hindsight sampling), and
+    its call order must stay what it is without this package."""
+    st = np.random.get_state()
+    key, pos = st[1], int(st[2])
+    h = int(key[pos % 624]) ^ (int(key[(pos + 1) % 624]) << 1) ^ pos ^ int(salt)
+    return h % (2 ** 31 - 2) + 1
+
+
 def pack_host_rows(observations, actions, rewards, terminals, next_observations, absorbing=None,
                    timeouts=None, out=None):
     """float64/uint8 reference-typed fields (simple_replay_buffer.py:48-60) -> float32 staging

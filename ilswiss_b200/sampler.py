@@ -18,6 +18,8 @@ same bit stream (documented deviation, as for the in-kernel index sampling).
 """
 import numpy as np
 
+from . import layout
+
 
 class DevicePolicy:
     """Numpy-interface exploration policy backed by a fused trainer's policy arena.
@@ -28,7 +30,9 @@ class DevicePolicy:
     def __init__(self, trainer, seed=None):
         self.trainer = trainer
         self.stochastic_policy = trainer.policy
-        self._seed = int(np.random.randint(1, 2 ** 31 - 1)) if seed is None else int(seed)
+        # the numpy / python global RNG streams belong to the reference's code (exploration noise, hindsight sampling) and
+        # must not be advanced here: the default seed is derived from numpy's state without drawing from it
+        self._seed = layout.derive_seed(salt=0x5a17) if seed is None else int(seed)
         self._calls = 0
 
     def get_actions(self, obs_np, deterministic=False):

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 import torch.optim as optim
 
-from . import _abi
+from . import _abi, layout
 from .engine import NetArena, StepEngine, require_cuda
 
 
@@ -86,7 +86,7 @@ class _FusedTrainer:
         require_cuda()
         self.engine = StepEngine(cfg, nets)
         self._cfg, self._nets = cfg, list(nets)
-        self._seed = int(np.random.randint(1, 2 ** 31 - 1))
+        self._seed = layout.derive_seed(salt=id(self) & 0xffff)
         self._launch = 0
 
     def ensure_batch(self, batch_size, max_steps_per_call=None):
