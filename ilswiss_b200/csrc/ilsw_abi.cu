@@ -11,6 +11,7 @@
 
 #include "../../include/ilswiss_b200.h"
 #include "ilsw_engine.cuh"
+#include "ilsw_tmap.h"
 #include "ilsw_program.h"
 
 using namespace ilsw;
@@ -65,6 +66,7 @@ struct ilsw_rb {
   int64_t staging_cap, pending;
   cudaEvent_t staged;
   bool staged_valid;
+  cudaStream_t last_stream;   // compute stream of the latest commit (scatter kernels run there, never on the copy stream)
 };
 
 // one warp per staged transition: staging row -> hot row at (top+i) % capacity, cold row
@@ -174,21 +176,20 @@ extern "C" int ilsw_rb_append(ilsw_rb* rb, const float* host_rows, int64_t n, vo
   if (n == 0) return ILSW_OK;
   if (n > rb->capacity) return fail(ILSW_ERR_ARG, "rb_append: burst larger than the ring");
   cudaStream_t cs = (cudaStream_t)copy_stream;
+  // more pending rows than ring slots would make two rows of one scatter race for a slot: drain first.  The scatter
+  // always runs on the COMPUTE stream last used with this ring (never on the copy stream, where it could overwrite rows
+  // an engine kernel is gathering); the copy stream then waits for it before reusing the staging area.
+  if (rb->pending > 0 && (rb->pending + n > rb->capacity || rb->pending + n > rb->staging_cap)) {
+    int rc = ilsw_rb_commit(rb, (void*)rb->last_stream);
+    if (rc) return rc;
+  }
   if (rb->pending == 0 && rb->staged_valid) CU(cudaStreamWaitEvent(cs, rb->staged, 0));  // staging reuse after the scatter
-  if (rb->pending + n > rb->staging_cap) {
-    // grow staging (rare; flushes what is pending first so no data is lost)
-    if (rb->pending > 0) {
-      int rc = ilsw_rb_commit(rb, copy_stream);
-      if (rc) return rc;
-      CU(cudaStreamSynchronize(cs));
-    }
+  if (n > rb->staging_cap) {
     int64_t cap = rb->staging_cap ? rb->staging_cap : 1024;
     while (cap < n) cap *= 2;
-    if (cap != rb->staging_cap) {
-      if (rb->staging) { CU(cudaDeviceSynchronize()); CU(cudaFree(rb->staging)); }
-      CU(cudaMalloc(&rb->staging, (size_t)cap * rb->host_w * sizeof(float)));
-      rb->staging_cap = cap;
-    }
+    if (rb->staging) { CU(cudaDeviceSynchronize()); CU(cudaFree(rb->staging)); }
+    CU(cudaMalloc(&rb->staging, (size_t)cap * rb->host_w * sizeof(float)));
+    rb->staging_cap = cap;
   }
   CU(cudaMemcpyAsync(rb->staging + rb->pending * rb->host_w, host_rows, (size_t)n * rb->host_w * sizeof(float),
                      cudaMemcpyHostToDevice, cs));
@@ -202,6 +203,7 @@ extern "C" int ilsw_rb_commit(ilsw_rb* rb, void* stream) {
   if (!rb) return fail(ILSW_ERR_ARG, "rb_commit: null");
   if (rb->pending == 0) return ILSW_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  rb->last_stream = st;
   if (rb->staged_valid) CU(cudaStreamWaitEvent(st, rb->staged, 0));
   const int64_t n = rb->pending;
   const int wpb = 8;
@@ -288,6 +290,9 @@ struct ilsw_trainer {
   BarrierState* bar;
   int grid;
   int ctas;
+  int tc5;                // engine variant with the tcgen05/TMA GEMM tile (ilsw_tc5.cuh)
+  int sms;
+  void* tmaps;            // device CUtensorMap[2 * kMaxOps]: A / B operand maps of the tcgen05 GEMM ops
   size_t smem_bytes;
   int t[kMaxNets];
   int n_total;
@@ -307,23 +312,77 @@ struct ilsw_trainer {
 };
 static const int kMaxActRows = 4096;
 
+static const void* engine_fn(const ilsw_trainer* tr) {
+  if (tr->tc5) return (const void*)ilsw_engine_kernel<1, true>;
+  return tr->ctas == 2 ? (const void*)ilsw_engine_kernel<2, false> : (const void*)ilsw_engine_kernel<1, false>;
+}
+static size_t engine_smem(const ilsw_trainer* tr, int n_ops) {
+  return engine_staging_bytes(tr->ctas, tr->tc5 != 0) + ((sizeof(Phase) * kMaxPhases + 15) & ~size_t(15)) +
+         ((sizeof(Op) * (size_t)n_ops + 15) & ~size_t(15)) + sizeof(Ctx) + 64;
+}
+// occupancy variant + launch geometry of the program just built
+static int engine_configure(ilsw_trainer* tr) {
+  // 2 CTAs/SM pays off when the mma.sync GEMM phases have more than 2 tiles per SM (B >= 512); the tcgen05 variant is 1 CTA/SM
+  tr->ctas = (!tr->tc5 && tr->spec.cfg.batch >= 512) ? 2 : 1;
+  const char* cv = getenv("ILSW_CTAS_PER_SM");
+  if (!tr->tc5 && cv && (atoi(cv) == 1 || atoi(cv) == 2)) tr->ctas = atoi(cv);
+  tr->smem_bytes = engine_smem(tr, kMaxOps);
+  const void* kfn = engine_fn(tr);
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr->smem_bytes);
+  if (e != cudaSuccess) return fail(ILSW_ERR_CUDA, "engine smem opt-in (%zu B): %s", tr->smem_bytes, cudaGetErrorString(e));
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kThreads, tr->smem_bytes);
+  if (e != cudaSuccess || per_sm < 1) return fail(ILSW_ERR_CUDA, "engine kernel cannot be resident (%s)", cudaGetErrorString(e));
+  if (per_sm < tr->ctas) return fail(ILSW_ERR_CUDA, "engine kernel: only %d CTA/SM resident, need %d", per_sm, tr->ctas);
+  tr->grid = tr->sms * tr->ctas;  // persistent: all CTAs co-resident (cooperative launch)
+  const char* g = getenv("ILSW_GRID");
+  if (g && atoi(g) > 0 && atoi(g) <= tr->sms * tr->ctas) tr->grid = atoi(g);
+  return ILSW_OK;
+}
+
 static int trainer_build(ilsw_trainer* tr) {
   std::string why;
   int rc = validate_spec(tr->spec, &why);
   if (rc) return fail(rc, "trainer spec invalid: %s", why.c_str());
+  const char* tv = getenv("ILSW_TC5");
+  tr->tc5 = (tc5_wanted(tr->spec) && tmap_encoder() != nullptr && !(tv && atoi(tv) == 0)) ? 1 : 0;
   Bump measure;
   Program* tmp = new Program();
-  rc = assemble(*tmp, tr->spec, measure);
+  rc = assemble(*tmp, tr->spec, measure, tr->tc5 != 0);
   delete tmp;
   if (rc) return fail(rc, "program assembly failed (too many phases/ops?)");
-  if (tr->scratch) { CU(cudaDeviceSynchronize()); CU(cudaFree(tr->scratch)); tr->scratch = nullptr; }
+  // a rebuild (attach_disc after load_snapshot) keeps the device-resident optimiser state of alpha
+  DynState old_dyn;
+  bool have_old = false;
+  if (tr->scratch) {
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(&old_dyn, tr->host_prog.ctx.dyn, sizeof(old_dyn), cudaMemcpyDeviceToHost));
+    have_old = true;
+    CU(cudaFree(tr->scratch)); tr->scratch = nullptr;
+  }
   tr->scratch_bytes = measure.off + 256;
   CU(cudaMalloc(&tr->scratch, tr->scratch_bytes));
   CU(cudaMemset(tr->scratch, 0, tr->scratch_bytes));
   Bump mem;
   mem.base = tr->scratch;
-  rc = assemble(tr->host_prog, tr->spec, mem);
+  rc = assemble(tr->host_prog, tr->spec, mem, tr->tc5 != 0);
   if (rc) return fail(rc, "program assembly failed");
+  if (tr->tc5) {           // TMA tensor maps of every tcgen05 GEMM operand (box shapes: ilsw_tc5.cuh)
+    static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+    if (!tr->tmaps) CU(cudaMalloc(&tr->tmaps, sizeof(CUtensorMap) * 2 * kMaxOps));
+    std::vector<CUtensorMap> maps(2 * kMaxOps);
+    Program& P = tr->host_prog;
+    for (int i = 0; i < P.n_ops; ++i) {
+      if (P.ops[i].kind != OP_GEMM || !P.ops[i].gemm.tc5) continue;
+      GemmOp& g = P.ops[i].gemm;
+      const int ra = g.a_mc ? make_tmap_2d(&maps[2 * i], g.A, g.lda, g.M, g.K, 32, true) : make_tmap_2d(&maps[2 * i], g.A, g.lda, g.K, g.M, tc5::kBM, false);
+      const int rb = g.b_nc ? make_tmap_2d(&maps[2 * i + 1], g.B, g.ldb, g.N, g.K, 32, true) : make_tmap_2d(&maps[2 * i + 1], g.B, g.ldb, g.K, g.N, kTc5BN, false);
+      if (ra || rb) return fail(ILSW_ERR_CUDA, "tensor map encode failed for GEMM op %d (%dx%dx%d): %d %d", i, g.M, g.N, g.K, ra, rb);
+      g.tmapA = reinterpret_cast<const CUtensorMap*>(tr->tmaps) + 2 * i;
+      g.tmapB = reinterpret_cast<const CUtensorMap*>(tr->tmaps) + 2 * i + 1;
+    }
+    CU(cudaMemcpy(tr->tmaps, maps.data(), sizeof(CUtensorMap) * 2 * kMaxOps, cudaMemcpyHostToDevice));
+  }
   // development aid (tools/phase_profile.py): ILSW_DEBUG_DUP_PHASE=k runs phase k twice in a row -- only meaningful for
   // idempotent phases (forward / row phases); the second run shows the phase's warm-code, warm-data time
   if (const char* dp = getenv("ILSW_DEBUG_DUP_PHASE")) {
@@ -341,8 +400,9 @@ static int trainer_build(ilsw_trainer* tr) {
   d.log_alpha = log(tr->spec.cfg.alpha > 0 ? tr->spec.cfg.alpha : 1.0);
   d.alpha = (float)exp(d.log_alpha);
   d.alpha_p1 = d.alpha_p2 = 1.0;
+  if (have_old) { d = old_dyn; d.abort_flag = 0; d.error_code = 0; }
   CU(cudaMemcpy(tr->host_prog.ctx.dyn, &d, sizeof(d), cudaMemcpyHostToDevice));
-  return ILSW_OK;
+  return engine_configure(tr);
 }
 
 extern "C" int ilsw_trainer_create(ilsw_trainer** out, const ilsw_trainer_config* cfg, const ilsw_mlp* nets, int n_nets) {
@@ -357,27 +417,12 @@ extern "C" int ilsw_trainer_create(ilsw_trainer** out, const ilsw_trainer_config
   tr->spec.cfg = *cfg;
   for (int i = 0; i < n_nets; ++i) tr->spec.nets[i] = nets[i];
   tr->spec.n_nets = n_nets;
+  tr->sms = sms;
   int rc = trainer_build(tr);
   if (rc) { ilsw_trainer_destroy(tr); return rc; }
   cudaError_t e = cudaMalloc(&tr->bar, sizeof(BarrierState));
   if (e == cudaSuccess) e = cudaMemset(tr->bar, 0, sizeof(BarrierState));
   if (e != cudaSuccess) { ilsw_trainer_destroy(tr); return fail(ILSW_ERR_CUDA, "barrier alloc: %s", cudaGetErrorString(e)); }
-  int per_sm = 0;
-  // occupancy variant: 2 CTAs/SM pays off when the GEMM phases have more than 2 tiles per SM (B >= 512)
-  tr->ctas = cfg->batch >= 512 ? 2 : 1;
-  const char* cv = getenv("ILSW_CTAS_PER_SM");
-  if (cv && (atoi(cv) == 1 || atoi(cv) == 2)) tr->ctas = atoi(cv);
-  tr->smem_bytes = (size_t)tc_smem_floats(tr->ctas) * sizeof(float) + ((sizeof(Phase) * kMaxPhases + 15) & ~size_t(15)) +
-                   ((sizeof(Op) * (size_t)kMaxOps + 15) & ~size_t(15)) + sizeof(Ctx) + 64;
-  const void* kfn = tr->ctas == 2 ? (const void*)ilsw_engine_kernel<2> : (const void*)ilsw_engine_kernel<1>;
-  e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr->smem_bytes);
-  if (e != cudaSuccess) { ilsw_trainer_destroy(tr); return fail(ILSW_ERR_CUDA, "engine smem opt-in (%zu B): %s", tr->smem_bytes, cudaGetErrorString(e)); }
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kThreads, tr->smem_bytes);
-  if (e != cudaSuccess || per_sm < 1) { ilsw_trainer_destroy(tr); return fail(ILSW_ERR_CUDA, "engine kernel cannot be resident (%s)", cudaGetErrorString(e)); }
-  if (per_sm < tr->ctas) { ilsw_trainer_destroy(tr); return fail(ILSW_ERR_CUDA, "engine kernel: only %d CTA/SM resident, need %d", per_sm, tr->ctas); }
-  tr->grid = sms * tr->ctas;  // persistent: all CTAs co-resident (cooperative launch)
-  const char* g = getenv("ILSW_GRID");
-  if (g && atoi(g) > 0 && atoi(g) <= sms * tr->ctas) tr->grid = atoi(g);
   tr->rep.world = 1;
   *out = tr;
   return ILSW_OK;
@@ -424,6 +469,7 @@ extern "C" int ilsw_trainer_destroy(ilsw_trainer* tr) {
   if (tr->act_pin) cudaFreeHost(tr->act_pin);
   if (tr->act_dev) cudaFree(tr->act_dev);
   if (tr->scratch) cudaFree(tr->scratch);
+  if (tr->tmaps) cudaFree(tr->tmaps);
   if (tr->dev_prog) cudaFree(tr->dev_prog);
   if (tr->bar) cudaFree(tr->bar);
   delete tr;
@@ -492,9 +538,8 @@ extern "C" int ilsw_train(ilsw_trainer* tr, ilsw_rb* policy_rb, ilsw_rb* expert_
   BarrierState* bar = tr->bar;
   CU(cudaMemsetAsync(bar, 0, sizeof(BarrierState), st));   // monotonic barrier counter restarts at 0
   void* args[] = {(void*)&dp, (void*)&a, (void*)&bar, (void*)&rp};
-  const size_t smem = (size_t)tc_smem_floats(tr->ctas) * sizeof(float) + ((sizeof(Phase) * kMaxPhases + 15) & ~size_t(15)) +
-                      ((sizeof(Op) * (size_t)tr->host_prog.n_ops + 15) & ~size_t(15)) + sizeof(Ctx) + 64;
-  CU(cudaLaunchCooperativeKernel(tr->ctas == 2 ? (void*)ilsw_engine_kernel<2> : (void*)ilsw_engine_kernel<1>, dim3(tr->grid), dim3(kThreads), args, smem, st));
+  const size_t smem = engine_smem(tr, tr->host_prog.n_ops);
+  CU(cudaLaunchCooperativeKernel(engine_fn(tr), dim3(tr->grid), dim3(kThreads), args, smem, st));
   tr->launches += 1;
   // host mirrors of the on-device counters
   if (a.update_mode != UPDATE_DISC_ONLY)

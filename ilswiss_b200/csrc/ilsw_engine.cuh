@@ -10,6 +10,7 @@
 
 #include "ilsw_ops.cuh"
 #include "ilsw_rows_fast.cuh"
+#include "ilsw_tc5.cuh"
 
 // experiment switches of the tensor-core tile (see DESIGN.md 4.4 for the measurements behind the defaults)
 #ifndef ILSW_ADAM_PREFETCH
@@ -317,6 +318,11 @@ template <int KC> struct TcGeom {
   static constexpr int kSmemFloats = 2 * kStageFloats;  // 2 stages x (A,B): 160 KB (KC=256) / 80 KB (KC=128)
 };
 constexpr int tc_smem_floats(int ctas) { return ctas == 2 ? TcGeom<128>::kSmemFloats : TcGeom<256>::kSmemFloats; }
+// bytes of the GEMM staging area at the start of dynamic shared memory; the tcgen05 engine variant (one CTA per SM)
+// also fits the TMA stages of ilsw_tc5.cuh (+ 1 KB to align them to the 1024-byte swizzle atom)
+constexpr size_t engine_staging_bytes(int ctas, bool tc5) {
+  return tc5 ? (size_t)tc5::Geom<kTc5BN>::kSmemBytes + 1024 : (size_t)tc_smem_floats(ctas) * sizeof(float);
+}
 // The engine is compiled in two occupancy variants: CTAS=1 (255 registers/thread, lowest single-job
 // latency: B=256 workloads) and CTAS=2 (128 registers, twice the tile parallelism per SM: B=1024).
 
@@ -855,9 +861,11 @@ __device__ __noinline__ void adam_job(const AdamOp& ao, const AdamCoef& cfs, int
   }
 }
 
-template <int CTAS>
+template <int CTAS, bool TC5>
 __global__ void __launch_bounds__(kThreads, CTAS)
 ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierState* bar, Replica rp_param) {
+  static_assert(!TC5 || CTAS == 1, "the tcgen05 variant runs one CTA per SM");
+  static_assert(!TC5 || engine_staging_bytes(1, true) >= (size_t)tc_smem_floats(1) * sizeof(float), "staging area also serves the mma.sync tile");
   unsigned char* dyn_smem = reinterpret_cast<unsigned char*>(ilsw_dyn_smem_f);
   float* smem = ilsw_dyn_smem_f;
   // launch arguments live in shared memory: row kernels take them by reference and the replica tables are indexed
@@ -869,9 +877,13 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
   __shared__ unsigned s_gen;
   __shared__ double s_p1[kMaxNets], s_p2[kMaxNets], s_b1[kMaxNets], s_b2[kMaxNets];   // running beta^t per Adam slot
   __shared__ int s_pt[kMaxNets];
+  __shared__ tc5::Sync s_tc5;
   const int n_phases = prog->n_phases, n_ops = prog->n_ops;
   constexpr int KC = CTAS == 2 ? 128 : 256;
-  unsigned char* pbase = dyn_smem + (size_t)TcGeom<KC>::kSmemFloats * sizeof(float);
+  unsigned char* pbase = dyn_smem + engine_staging_bytes(CTAS, TC5);
+  unsigned char* tc5_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
+  tc5::State tc5_state{0u, 0u};
+  if (TC5) tc5::setup<kTc5BN>(s_tc5, tc5_smem);
   Phase* s_phases = reinterpret_cast<Phase*>(pbase);
   Op* s_ops = reinterpret_cast<Op*>(pbase + align16(sizeof(Phase) * kMaxPhases));
   Ctx* s_ctx = reinterpret_cast<Ctx*>(reinterpret_cast<unsigned char*>(s_ops) + align16(sizeof(Op) * (size_t)n_ops));
@@ -906,7 +918,10 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
   const int prec = c.hp.gemm_precision;
   const bool fast_rows = fast_rows_ok(c);
 
-  for (int s = 0; s < a.n_steps; ++s) {
+  // a failed barrier / exchange / tile wait ends the launch for every thread of the CTA (uniform), through the common exit:
+  // tensor memory must be released before the CTA retires
+  bool alive = true;
+  for (int s = 0; s < a.n_steps && alive; ++s) {
     const bool stamp = (s == a.n_steps - 1) && blockIdx.x == 0 && threadIdx.x == 0;
     if (stamp) c.phase_ns[0] = globaltimer_ns();
     if (threadIdx.x < kMaxNets && s_pt[threadIdx.x] >= 0) {
@@ -915,21 +930,26 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
       s_coefs[threadIdx.x] = adam_coef_pw(s_ops[s_adam_op[threadIdx.x]].adam, s_p1[threadIdx.x], s_p2[threadIdx.x], 1);
     }
     __syncthreads();
-    for (int ph = 0; ph < n_phases; ++ph) {
+    for (int ph = 0; ph < n_phases && alive; ++ph) {
       const Phase& P = s_phases[ph];
       if (!phase_active(P, c.hp, a, s)) { if (stamp) c.phase_ns[ph + 1] = c.phase_ns[ph]; continue; }
       const bool exchange = P.collective && rp.world > 1;
       // exchange sequence number = number of policy updates so far (parity double-buffers the slots)
       const unsigned xseq = rp.seq0 + (unsigned)(adam_t(a, c.hp, SLOT_POLICY, s) - a.t0[SLOT_POLICY]);
-      if (exchange && !replica_exchange(rp, xseq, bar, gen, abort_flag)) return;
-      for (int job = blockIdx.x; job < P.total_jobs; job += gridDim.x) {
+      if (exchange && !replica_exchange(rp, xseq, bar, gen, abort_flag)) { alive = false; break; }
+      for (int job = blockIdx.x; job < P.total_jobs && alive; job += gridDim.x) {
         int j = job, oi = P.op_begin;
         while (j >= s_ops[oi].n_jobs) { j -= s_ops[oi].n_jobs; ++oi; }
         const Op& o = s_ops[oi];
         if (o.kind == OP_GEMM) {
           const AdamOp* ad = o.gemm.adam ? &s_ops[o.gemm.adam - 1].adam : nullptr;
           const AdamCoef* cf = ad ? &s_coefs[ad->slot] : nullptr;
-          if (gemm_is_skinny(o.gemm)) gemm_tile_skinny(o.gemm, j, smem, ad, cf);
+          if (TC5 && o.gemm.tc5) {
+            if (!tc5::gemm_tile<kTc5BN>(o.gemm, j, tc5_smem, s_tc5, tc5_state, ad, cf)) {
+              if (threadIdx.x == 0) atomicExch(abort_flag, 1);     // the other CTAs leave their barrier wait
+              alive = false;
+            }
+          } else if (gemm_is_skinny(o.gemm)) gemm_tile_skinny(o.gemm, j, smem, ad, cf);
           else if (prec == 0) gemm_tile_device(o.gemm, j, smem, ad, cf);
           else gemm_tile_tc<KC>(o.gemm, j, smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, ad, cf);
         } else if (o.kind == OP_ROW) {
@@ -955,16 +975,25 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
 #pragma unroll
           for (int u = 0; u < E; ++u) {
             const int i = beg + threadIdx.x + u * kThreads;
-            if (i < end) o.polyak.target[i] = tv[u] * om + sv[u] * o.polyak.tau;
+            if (i < end) {
+              const float tn = tv[u] * om + sv[u] * o.polyak.tau;
+              o.polyak.target[i] = tn;
+              shadow_store(o.polyak.sh_t, i, tn);
+            }
           }
+        } else if (o.kind == OP_SHADOW) {
+          const int beg = j * kAdamChunk, end = min(o.shadow.dst.n, beg + kAdamChunk);
+          for (int i = beg + threadIdx.x; i < end; i += kThreads) shadow_refresh_elem(o.shadow, i);
         }
       }
+      if (!alive) break;
       if (stamp) c.phase_ns[kMaxPhases + 1 + ph] = globaltimer_ns();
       if (a.profile && s == a.n_steps - 1 && threadIdx.x == 0 && blockIdx.x < kMaxGrid) c.cta_ns[ph * kMaxGrid + blockIdx.x] = globaltimer_ns();
-      if (!grid_barrier(bar, gridDim.x, gen, abort_flag)) return;
+      if (!grid_barrier(bar, gridDim.x, gen, abort_flag)) { alive = false; break; }
       if (stamp) c.phase_ns[ph + 1] = globaltimer_ns();
     }
   }
+  if (TC5) tc5::teardown<kTc5BN>(s_tc5);
 }
 
 // ------------------------------------------------------------------------------------------

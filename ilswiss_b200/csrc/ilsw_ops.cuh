@@ -230,7 +230,12 @@ ILSW_HD void adam_math_store(const AdamOp& o, const AdamCoef& c, int i, float g,
   o.m[i] = m;
   o.v[i] = v;
   o.p[i] = p;
-  if (o.target) o.target[i] = ILSW_FMA(tg, c.one_m_tau, ILSW_MUL(p, c.tau));
+  shadow_store(o.sh_p, i, p);
+  if (o.target) {
+    const float tn = ILSW_FMA(tg, c.one_m_tau, ILSW_MUL(p, c.tau));
+    o.target[i] = tn;
+    shadow_store(o.sh_t, i, tn);
+  }
 }
 ILSW_HD void adam_elem_g(const AdamOp& o, const AdamCoef& c, int i, float g) {
   adam_math_store(o, c, i, g, o.m[i], o.v[i], o.p[i], o.target ? o.target[i] : 0.f);
@@ -245,8 +250,11 @@ ILSW_HD int gemm_grad_index(const GemmOp& o, const AdamOp& ad, int m, int n) {
 
 ILSW_HD void polyak_elem(const PolyakOp& o, int i) {
   float om = (float)(1.0 - (double)o.tau);
-  o.target[i] = o.target[i] * om + ldg(o.src + i) * o.tau;
+  const float tn = o.target[i] * om + ldg(o.src + i) * o.tau;
+  o.target[i] = tn;
+  shadow_store(o.sh_t, i, tn);
 }
+ILSW_HD void shadow_refresh_elem(const ShadowOp& o, int i) { shadow_store(o.dst, i, ldg(o.src + i)); }
 
 // ------------------------------------------------------------------------------------------
 // Row kernels.  (c: context, a: launch args, s: step index within launch, r: row)

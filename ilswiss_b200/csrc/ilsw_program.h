@@ -71,16 +71,46 @@ struct Builder {
     ph.op_count++; ph.total_jobs += n_jobs;
     return &o;
   }
+  // tcgen05/TMA tile (ilsw_tc5.cuh): both operands must be TMA-addressable (16-byte aligned base and row stride); the
+  // skinny shapes (M <= 8 weight gradients) and accumulating GEMMs keep their own tiles
+  static bool tc5_operand_ok(const float* base, int ld) { return (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld & 3) == 0; }
+  bool tc5_eligible(const GemmOp& g) const {
+    if (!P.ctx.hp.use_tc5 || g.accumulate || g.C2) return false;
+    if (g.M <= 8 && g.a_mc && g.b_nc) return false;
+    if (g.aug_ones && !(g.a_mc && g.b_nc)) return false;
+    return tc5_operand_ok(g.A, g.lda) && tc5_operand_ok(g.B, g.ldb);
+  }
   void gemm(GemmOp g) {
-    g.tiles_m = (g.M + 31) / 32;
-    g.tiles_n = (g.N + 31) / 32;      // the aug (bias-gradient) column is produced by the tn==0 tiles
+    g.tc5 = tc5_eligible(g) ? 1 : 0;
+    g.tmapA = g.tmapB = nullptr;
+    if (g.tc5) { g.tiles_m = (g.M + 127) / 128; g.tiles_n = (g.N + kTc5BN - 1) / kTc5BN; }
+    else { g.tiles_m = (g.M + 31) / 32; g.tiles_n = (g.N + 31) / 32; }   // the aug (bias-gradient) column is produced by the tn==0 tiles
     Op* o = add(OP_GEMM, g.tiles_m * g.tiles_n);
     if (o) o->gemm = g;
+  }
+  // the aligned copy of a first-layer weight matrix, if `W` is one that has a copy (ShadowRef in ilsw_types.h)
+  const MlpPtrs* shadowed_net(const float* W) const {
+    const Ctx& c = P.ctx;
+    const MlpPtrs* nets[] = {&c.policy, &c.qf[0], &c.qf[1], &c.tqf[0], &c.tqf[1], &c.tpolicy, &c.vf, &c.tvf, &c.disc};
+    for (const MlpPtrs* n : nets)
+      if (n->p && n->w0p && W == n->p + n->oW0) return n;
+    return nullptr;
+  }
+  static ShadowRef shadow_of(const MlpPtrs* n) {
+    ShadowRef r; r.ptr = nullptr; r.in = r.ld = r.n = 0;
+    if (n && n->w0p) { r.ptr = n->w0p; r.in = n->in_dim; r.ld = n->ld_w0p; r.n = n->hid * n->in_dim; }
+    return r;
+  }
+  void shadow_refresh(const MlpPtrs& n) {
+    if (!n.p || !n.w0p) return;
+    Op* o = add(OP_SHADOW, (n.hid * n.in_dim + kAdamChunk - 1) / kAdamChunk);
+    if (o) { o->shadow.src = n.p + n.oW0; o->shadow.dst = shadow_of(&n); }
   }
   // Y[M,N] = act(X[M,K] W[N,K]^T + b)          (N1: networks.py:85-101)
   void fwd(const float* X, int ldx, int M, int K, const float* W, const float* b, int N, float* Y, int ldy, int act) {
     GemmOp g; memset(&g, 0, sizeof(g));
     g.A = X; g.lda = ldx; g.a_mc = 0; g.B = W; g.ldb = K; g.b_nc = 0; g.M = M; g.N = N; g.K = K;
+    if (const MlpPtrs* sn = shadowed_net(W)) { g.B = sn->w0p; g.ldb = sn->ld_w0p; }   // packed W0 rows are not TMA-addressable
     g.C = Y; g.ldc = ldy; g.bias = b; g.act = act;
     gemm(g);
   }
@@ -115,6 +145,7 @@ struct Builder {
     o->adam.target = target ? target->p : nullptr;
     o->adam.n = n.n_params; o->adam.lr = lr; o->adam.beta1 = b1; o->adam.beta2 = b2; o->adam.eps = eps;
     o->adam.tau = tau; o->adam.slot = slot; o->adam.grad_scale_world = 0; o->adam.begin = 0; o->adam.fused_only = 1;
+    o->adam.sh_p = shadow_of(&n); o->adam.sh_t = shadow_of(target);
     return idx;
   }
   void adam(const MlpPtrs& n, const MlpPtrs* target, double lr, double b1, double b2, double eps, float tau, int slot,
@@ -125,11 +156,13 @@ struct Builder {
     o->adam.target = target ? target->p : nullptr;
     o->adam.n = n.n_params; o->adam.lr = lr; o->adam.beta1 = b1; o->adam.beta2 = b2; o->adam.eps = eps;
     o->adam.tau = tau; o->adam.slot = slot; o->adam.grad_scale_world = world_scale;
+    o->adam.sh_p = shadow_of(&n); o->adam.sh_t = shadow_of(target);
   }
   void polyak(const MlpPtrs& src, const MlpPtrs& tgt, float tau) {
     Op* o = add(OP_POLYAK, (src.n_params + kAdamChunk - 1) / kAdamChunk);
     if (!o) return;
     o->polyak.target = tgt.p; o->polyak.src = src.p; o->polyak.n = src.n_params; o->polyak.tau = tau;
+    o->polyak.sh_t = shadow_of(&tgt);
   }
 };
 
@@ -557,11 +590,18 @@ inline int validate_spec(const TrainerSpec& sp, std::string* why) {
 }
 
 // Lays out scratch in `mem` (two-pass capable), fills P.ctx and compiles the program.
-inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem) {
+// tcgen05/TMA tiles pay where the layer is a dense GEMM: batch >= 512 (TD3-Humanoid B = 1024, HER B = 4096), tensor-core
+// precision modes, no discriminator program (B = 256 everywhere)
+inline bool tc5_wanted(const TrainerSpec& sp) {
+  return sp.cfg.batch >= 512 && sp.cfg.gemm_precision != 0 && !sp.has_disc;
+}
+
+inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem, bool use_tc5 = false) {
   memset(&P, 0, sizeof(P));
   Ctx& c = P.ctx;
   const ilsw_trainer_config& cfg = sp.cfg;
   c.hp = make_hyper(cfg);
+  c.hp.use_tc5 = use_tc5 ? 1 : 0;
   if (sp.has_disc) apply_disc_hyper(c.hp, sp.dcfg);
   const int B = cfg.batch, O = cfg.obs_dim, A = cfg.act_dim, Hd = sp.nets[0].hidden;
   c.dyn = mem.take<DynState>(1);
@@ -587,6 +627,11 @@ inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem) {
     alloc_disc_bufs(mem, c.d, B, sp.dcfg.state_only ? 2 * O : O + A, sp.disc.hidden);
     c.disc = make_mlp(sp.disc, grad(sp.disc));
   }
+  if (use_tc5) {
+    MlpPtrs* nets[] = {&c.policy, &c.qf[0], &c.qf[1], &c.tqf[0], &c.tqf[1], &c.tpolicy, &c.vf, &c.tvf};
+    for (MlpPtrs* n : nets)
+      if (n->p && (n->in_dim & 3)) { n->ld_w0p = round_up(n->in_dim, 4); n->w0p = mem.f((size_t)n->hid * n->ld_w0p); }
+  }
   return build_program(P);
 }
 
@@ -594,6 +639,15 @@ inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem) {
 inline int build_program(Program& P) {
   Builder b(P);
   const Ctx& c = P.ctx;
+  if (c.hp.use_tc5) {      // parameters may have been written by the host since the last launch: refresh the aligned W0 copies
+    const MlpPtrs* nets[] = {&c.policy, &c.qf[0], &c.qf[1], &c.tqf[0], &c.tqf[1], &c.tpolicy, &c.vf, &c.tvf};
+    bool any = false;
+    for (const MlpPtrs* n : nets) any = any || (n->p && n->w0p);
+    if (any) {
+      b.phase(COND_FIRST_STEP);
+      for (const MlpPtrs* n : nets) b.shadow_refresh(*n);
+    }
+  }
   if (c.hp.has_disc) { b.base_cond = COND_DISC_PART; build_disc_step(b, c); b.base_cond = COND_POLICY_PART; }
   if (c.hp.algo == ILSW_ALGO_SAC_ALPHA) build_sac_alpha(b, c);
   else if (c.hp.algo == ILSW_ALGO_TD3) build_td3(b, c);
@@ -615,14 +669,16 @@ inline std::string describe_program(const Program& P) {
     for (int j = 0; j < ph.op_count; ++j) {
       const Op& o = P.ops[ph.op_begin + j];
       if (o.kind == OP_GEMM)
-        snprintf(line, sizeof(line), " GEMM(%dx%dx%d%s%s%s)", o.gemm.M, o.gemm.N, o.gemm.K, o.gemm.aug_ones ? "+1" : "",
-                 o.gemm.accumulate ? ",acc" : "", o.gemm.adam ? ",adam" : "");
+        snprintf(line, sizeof(line), " GEMM(%dx%dx%d%s%s%s%s)", o.gemm.M, o.gemm.N, o.gemm.K, o.gemm.aug_ones ? "+1" : "",
+                 o.gemm.accumulate ? ",acc" : "", o.gemm.adam ? ",adam" : "", o.gemm.tc5 ? ",tcgen05" : "");
       else if (o.kind == OP_ROW)
         snprintf(line, sizeof(line), " ROW(k%d,%d)", o.row.kind, o.row.rows);
       else if (o.kind == OP_ADAM && o.adam.fused_only)
         line[0] = 0;
       else if (o.kind == OP_ADAM)
         snprintf(line, sizeof(line), " ADAM(%d%s)", o.adam.n, o.adam.target ? ",polyak" : "");
+      else if (o.kind == OP_SHADOW)
+        snprintf(line, sizeof(line), " W0COPY(%d)", o.shadow.dst.n);
       else
         snprintf(line, sizeof(line), " %s(%d)", kinds[o.kind], o.polyak.n);
       out += line;

@@ -27,8 +27,9 @@ constexpr int kLossSlots = 16;    // floats per step in the loss log
 constexpr int kThreads = 256;     // CTA size of the engine kernel
 constexpr int kRowsPerJob = 8;    // one warp per batch row
 constexpr int kAdamChunk = 2048;  // elements per flat Adam/Polyak job
+constexpr int kTc5BN = 64;        // column width of the tcgen05 tile (ilsw_tc5.cuh is instantiated with it; rows: 128)
 
-enum OpKind : int { OP_GEMM = 1, OP_ADAM = 2, OP_ROW = 3, OP_POLYAK = 4 };
+enum OpKind : int { OP_GEMM = 1, OP_ADAM = 2, OP_ROW = 3, OP_POLYAK = 4, OP_SHADOW = 5 };
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 
@@ -68,11 +69,23 @@ struct GemmOp {
                         // the epilogue applies the Adam (+Polyak) update to every gradient element it produces, so the
                         // weight-gradient phase needs no separate optimiser phase (valid only without accumulate
                         // partners and without a cross-replica exchange)
+  int tc5;              // 1: 128 x 64 tcgen05/TMA tile (ilsw_tc5.cuh); tiles_m/tiles_n then count those tiles
+  const void* tmapA;    // device CUtensorMap of the A / B operand (SWIZZLE_128B boxes, see ilsw_tc5.cuh)
+  const void* tmapB;
 };
+
+// 16-byte-aligned copy of a first-layer weight matrix W0[hid x in] whose rows are not (in % 4 != 0: critics on Hopper /
+// Humanoid ...): row stride `ld` = in rounded up to 4.  TMA cannot address the packed nn.Linear layout, so the tcgen05
+// programs read the copy; whoever writes parameter element i < n (= hid * in) also writes its copy.
+struct ShadowRef { float* ptr; int in, ld, n; };
+ILSW_HD void shadow_store(const ShadowRef& sh, int i, float v) {
+  if (sh.ptr && i < sh.n) { const int r = i / sh.in; sh.ptr[(size_t)r * sh.ld + (i - r * sh.in)] = v; }
+}
 
 struct AdamOp {
   float* p; const float* g; float* m; float* v;
   float* target;        // optional Polyak target updated from the NEW p (nullptr: none)
+  ShadowRef sh_p, sh_t; // aligned copies of W0 of the network / of its target (ptr == nullptr: none)
   int n;
   double lr, beta1, beta2, eps; float tau;
   int slot;             // Adam step-counter slot
@@ -81,7 +94,8 @@ struct AdamOp {
   int fused_only;       // 1: descriptor for GEMM epilogues (GemmOp::adam); owns no jobs
 };
 
-struct PolyakOp { float* target; const float* src; int n; float tau; };
+struct PolyakOp { float* target; const float* src; int n; float tau; ShadowRef sh_t; };
+struct ShadowOp { const float* src; ShadowRef dst; };   // refresh of one aligned copy (first step of a launch)
 
 struct RowOp {
   int kind;             // algorithm-specific row kernel id
@@ -97,6 +111,7 @@ struct Op {
     AdamOp adam;
     PolyakOp polyak;
     RowOp row;
+    ShadowOp shadow;
   };
 };
 
@@ -113,6 +128,7 @@ struct MlpPtrs {        // canonical 2-hidden-layer layout inside one flat arena
   float* p; float* m; float* v; float* g;   // params, Adam moments, gradient arena
   int in_dim, hid, out_dim, heads;          // heads=2: extra log-std head (policy)
   int n_params;
+  float* w0p; int ld_w0p;                   // aligned copy of W0 (tcgen05 programs, in_dim % 4 != 0), else nullptr
   // element offsets
   int oW0, ob0, oW1, ob1, oW2, ob2, oW3, ob3;
 };
@@ -177,6 +193,7 @@ struct Hyper {
   int clip_min_on, clip_max_on; float rew_clip_min, rew_clip_max;
   int state_only;       // disc input = cat(obs, next_obs) (adv_irl.py:139-179)
   int n_from_expert;    // last n rows of the policy batch come from the expert ring (adv_irl.py:239-255)
+  int use_tc5;          // dense GEMM phases run on the tcgen05/TMA tile (ilsw_tc5.cuh): batch >= 512, tensor-core modes
 };
 
 struct Ctx {            // everything a row kernel needs

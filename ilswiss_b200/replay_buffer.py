@@ -31,7 +31,7 @@ class DeviceReplayBuffer:
         self._max_replay_buffer_size = int(max_replay_buffer_size)
         self.ring = ReplayRing(self._max_replay_buffer_size, self._observation_dim, self._action_dim)
         self._pending = []            # host rows not yet staged (episode-burst appends)
-        self._flush_threshold = flush_threshold
+        self._flush_threshold = max(1, min(int(flush_threshold), self._max_replay_buffer_size))   # a burst never exceeds the ring
         self._top = 0
         self._size = 0
         self._trajs = 0
@@ -141,8 +141,11 @@ class DeviceReplayBuffer:
         """Stage pending host rows: pinned cudaMemcpyAsync on the ring's side stream; they enter
         the ring (scatter kernel on the compute stream) right before the next sample / train call."""
         if self._pending:
-            self.ring.append_host(np.stack(self._pending))
+            rows = np.stack(self._pending)
             self._pending = []
+            cap = self._max_replay_buffer_size
+            for s0 in range(0, rows.shape[0], cap):     # a burst never exceeds the ring (ilsw_rb_append)
+                self.ring.append_host(rows[s0:s0 + cap])
 
     # -- sample side (R3/R4) -------------------------------------------------------------
     def num_steps_can_sample(self):
@@ -198,24 +201,38 @@ class DeviceReplayBuffer:
         """Downloads to the reference's numpy field layout so `extra_data.pkl` stays readable."""
         self.flush()
         self.ring.commit()
-        rows = self.ring.rows_view()[: self._max_replay_buffer_size].cpu().numpy()
+        nrows = self._max_replay_buffer_size
+        rows = self.ring.rows_view()[:nrows].cpu().numpy()
+        cold = (self.ring.gather(torch.arange(nrows, dtype=torch.int32, device="cuda"))[1].cpu().numpy()
+                if self.ring.committed_size > 0 else np.zeros((nrows, 4), np.float32))
         d = layout.unpack_hot_rows(rows, self._observation_dim, self._action_dim)
         return dict(
             _observation_dim=self._observation_dim, _action_dim=self._action_dim,
             _max_replay_buffer_size=self._max_replay_buffer_size, _observations=d["observations"],
             _next_obs=d["next_observations"], _actions=d["actions"], _rewards=d["rewards"],
-            _terminals=d["terminals"], _top=self._top, _size=self._size, _trajs=self._trajs,
+            _terminals=d["terminals"], _absorbing=cold[:, :2].astype(np.float64), _timeouts=(cold[:, 2:3] != 0).astype("uint8"),
+            _top=self._top, _size=self._size, _trajs=self._trajs,
             _cur_start=self._cur_start, _traj_endpoints=dict(self._traj_endpoints),
-            _np_rand_state=self._np_rand_state,
+            _np_rand_state=self._np_rand_state, _flush_threshold=self._flush_threshold,
         )
 
     def __setstate__(self, d):
-        self.__init__(d["_max_replay_buffer_size"], d["_observation_dim"], d["_action_dim"])
+        # the BASE constructor explicitly: subclasses have other signatures (env / goal dims) and restore their own fields
+        DeviceReplayBuffer.__init__(self, d["_max_replay_buffer_size"], d["_observation_dim"], d["_action_dim"],
+                                    flush_threshold=d.get("_flush_threshold", 4096))
         self._np_rand_state = d["_np_rand_state"]
         n = d["_size"]
-        hot = layout.pack_hot_rows(d["_observations"], d["_actions"], d["_rewards"], d["_terminals"], d["_next_obs"])
-        # restore the physical layout (slot i holds row i), then the ring cursor
-        self.ring.load_device(torch.from_numpy(hot[: self._max_replay_buffer_size]).cuda())
+        cap = self._max_replay_buffer_size
+        # restore the physical layout (slot i holds row i, cold side array included), then the ring cursor
+        rows = layout.pack_host_rows(d["_observations"][:cap], d["_actions"][:cap], np.asarray(d["_rewards"][:cap]).reshape(-1),
+                                     np.asarray(d["_terminals"][:cap]).reshape(-1), d["_next_obs"][:cap],
+                                     d.get("_absorbing", None) if d.get("_absorbing", None) is None else d["_absorbing"][:cap],
+                                     None if d.get("_timeouts", None) is None else np.asarray(d["_timeouts"][:cap]).reshape(-1))
+        self.ring.clear()
+        step = max(1, min(1 << 16, cap))
+        for s0 in range(0, rows.shape[0], step):
+            self.ring.append_host(rows[s0:s0 + step])
+            self.ring.commit()
         self.ring.set_cursor(d["_top"], n)
         self._top, self._size, self._trajs = d["_top"], n, d["_trajs"]
         self._cur_start, self._traj_endpoints = d["_cur_start"], dict(d["_traj_endpoints"])
@@ -228,6 +245,15 @@ class DeviceEnvReplayBuffer(DeviceReplayBuffer):
         self._ob_space = env.observation_space
         self._action_space = env.action_space
         super().__init__(max_replay_buffer_size, get_dim(self._ob_space), get_dim(self._action_space), random_seed)
+
+    def __getstate__(self):
+        d = super().__getstate__()
+        d["_ob_space"], d["_action_space"] = self._ob_space, self._action_space
+        return d
+
+    def __setstate__(self, d):
+        super().__setstate__(d)
+        self._ob_space, self._action_space = d.get("_ob_space"), d.get("_action_space")
 
 
 def get_dim(space):
@@ -272,6 +298,38 @@ class DeviceHindsightReplayBuffer(DeviceReplayBuffer):
         self._traj_dev = None         # (starts, lens) int32 CUDA tensors, rebuilt when the table changes
         self._traj_dirty = True
 
+    # the flat bulk-append paths of the base class know nothing about goal dicts, next achieved goals or the trajectory table
+    def add_samples(self, *a, **k):
+        raise NotImplementedError("DeviceHindsightReplayBuffer: append goal-dict transitions through add_sample")
+
+    def load_device_rows(self, *a, **k):
+        raise NotImplementedError("DeviceHindsightReplayBuffer: append goal-dict transitions through add_sample")
+
+    def add_path(self, path, absorbing=False, env=None):
+        """simple_replay_buffer.py:134-216 on goal-dict observations: the reference's per-transition add_sample loop."""
+        if absorbing:
+            raise NotImplementedError("wrap_absorbing is rejected by the reference itself (base_algorithm.py:137-139)")
+        for ob, ac, rw, nob, tm in zip(path["observations"], path["actions"], path["rewards"], path["next_observations"], path["terminals"]):
+            self.add_sample(ob, ac, rw, tm, nob)
+        self.terminate_episode()
+        self._trajs += 1
+
+    def __getstate__(self):
+        d = super().__getstate__()
+        d.update(_obs0_dim=self._obs0_dim, _goal_dim=self._goal_dim, relabel_type=self.relabel_type, her_ratio=self.her_ratio,
+                 distance_threshold=self.distance_threshold, observation_key=self.observation_key,
+                 desired_goal_key=self.desired_goal_key, achieved_goal_key=self.achieved_goal_key,
+                 _ag_next=self._ag_next.cpu().numpy())
+        return d
+
+    def __setstate__(self, d):
+        DeviceReplayBuffer.__setstate__(self, d)
+        self._obs0_dim, self._goal_dim = d["_obs0_dim"], d["_goal_dim"]
+        self.relabel_type, self.her_ratio, self.distance_threshold = d["relabel_type"], d["her_ratio"], d["distance_threshold"]
+        self.observation_key, self.desired_goal_key, self.achieved_goal_key = d["observation_key"], d["desired_goal_key"], d["achieved_goal_key"]
+        self._ag_next = torch.from_numpy(np.ascontiguousarray(d["_ag_next"], dtype=np.float32)).cuda()
+        self._ag_pending, self._traj_dev, self._traj_dirty = [], None, True
+
     def _cat(self, obs):
         return np.concatenate([np.asarray(obs[self.observation_key], dtype=np.float64).ravel(),
                                np.asarray(obs[self.desired_goal_key], dtype=np.float64).ravel()])
@@ -288,7 +346,7 @@ class DeviceHindsightReplayBuffer(DeviceReplayBuffer):
         self._traj_dirty = True
 
     def flush(self):
-        super().flush()
+        DeviceReplayBuffer.flush(self)
         if self._ag_pending:
             slots = torch.as_tensor(np.array([s for s, _ in self._ag_pending], dtype=np.int64), device="cuda")
             vals = torch.as_tensor(np.stack([v for _, v in self._ag_pending]), device="cuda")
@@ -349,6 +407,11 @@ class DeviceHindsightReplayBuffer(DeviceReplayBuffer):
                    observations=full["observations"][:, :O0], next_observations=full["next_observations"][:, :O0],
                    desired_goals=full["observations"][:, O0:].copy(), next_desired_goals=full["next_observations"][:, O0:].copy(),
                    next_achieved_goals=ag_next)
+        # :116-118 achieved_goals = the achieved goal of the CURRENT observation: the next achieved goal of the previous slot
+        # of the same trajectory (the ring keeps only next achieved goals); the first step of a trajectory has no
+        # predecessor in the ring, so the key is only provided on request
+        if keys is not None and "achieved_goals" in keys:
+            raise NotImplementedError("achieved_goals of the current observation are not stored in the device ring")
         if len(idx_her):
             n = int(self.her_ratio * batch_size)
             src = self._ag_next[torch.as_tensor(idx_her, device="cuda", dtype=torch.long)].cpu().numpy().astype(np.float64)
@@ -359,6 +422,26 @@ class DeviceHindsightReplayBuffer(DeviceReplayBuffer):
         return out
 
 
+def _check_sparse_reward_rule(env, goal_dim, thr):
+    """relabel_replay_buffer.py:36-37,139 recomputes rewards with env.compute_reward; the device path hard-wires the sparse
+    rule of the gym robotics environments the shipped HER yamls use.  Probe the environment's function on a few points and
+    refuse anything else (a dense or custom reward would otherwise be relabelled silently wrong)."""
+    fn = getattr(env, "compute_reward", None)
+    if fn is None:
+        return
+    rs = np.random.RandomState(0)
+    ag = rs.uniform(-1, 1, (16, goal_dim))
+    g = ag + rs.uniform(-2 * thr, 2 * thr, (16, goal_dim)) / np.sqrt(goal_dim)
+    try:
+        got = np.asarray(fn(ag, g, None), dtype=np.float64).reshape(-1)
+    except Exception:
+        return                      # cannot be probed without an episode context: trust the threshold attribute
+    want = -(np.linalg.norm(ag - g, axis=-1) > thr).astype(np.float64)
+    if got.shape != want.shape or not np.array_equal(got, want):
+        raise NotImplementedError("env.compute_reward is not the sparse goal reward -(||ag - g|| > distance_threshold): use the "
+                                  "reference's host HindsightReplayBuffer with HerTD3.train_step(batch) for this environment")
+
+
 class DeviceEnvHindsightReplayBuffer(DeviceHindsightReplayBuffer):
     """HindsightReplayBuffer's own constructor signature (relabel_replay_buffer.py:13-48): dims from the goal environment's
     Dict observation space, the sparse-reward threshold from `env.distance_threshold` (gym robotics; default 0.05)."""
@@ -367,8 +450,22 @@ class DeviceEnvHindsightReplayBuffer(DeviceHindsightReplayBuffer):
                  observation_key="observation", desired_goal_key="desired_goal", achieved_goal_key="achieved_goal"):
         spaces = env.observation_space.spaces
         self._ob_space, self._action_space = env.observation_space, env.action_space
-        thr = float(getattr(getattr(env, "unwrapped", env), "distance_threshold", getattr(env, "distance_threshold", 0.05)))
+        base_env = getattr(env, "unwrapped", env)
+        if not hasattr(base_env, "distance_threshold") and not hasattr(env, "distance_threshold"):
+            raise NotImplementedError("DeviceEnvHindsightReplayBuffer: the environment exposes no distance_threshold; the device "
+                                      "relabel implements the sparse goal reward -(||ag - g|| > threshold) only")
+        thr = float(getattr(base_env, "distance_threshold", getattr(env, "distance_threshold", 0.05)))
+        _check_sparse_reward_rule(env, get_dim(spaces[desired_goal_key]), thr)
         super().__init__(max_replay_buffer_size, get_dim(spaces[observation_key]), get_dim(spaces[desired_goal_key]),
                          get_dim(self._action_space), random_seed=random_seed, relabel_type=relabel_type, her_ratio=her_ratio,
                          distance_threshold=thr, observation_key=observation_key, desired_goal_key=desired_goal_key,
                          achieved_goal_key=achieved_goal_key)
+
+    def __getstate__(self):
+        d = super().__getstate__()
+        d["_ob_space"], d["_action_space"] = self._ob_space, self._action_space
+        return d
+
+    def __setstate__(self, d):
+        super().__setstate__(d)
+        self._ob_space, self._action_space = d.get("_ob_space"), d.get("_action_space")

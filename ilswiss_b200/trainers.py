@@ -94,16 +94,21 @@ class _FusedTrainer:
     def ensure_batch(self, batch_size, max_steps_per_call=None):
         """The step program is compiled for ONE batch size, but the reference hands `batch_size` to the ALGORITHM
         (rl_alg_params, torch_rl_algorithm.py:16-18), not to the trainer: adopt the algorithm's value the first time it
-        is seen.  Rebuilds the engine (fresh optimiser counters), so it is only legal before the first gradient step."""
+        is seen.  Rebuilds the engine for the new shapes and carries the optimiser state over."""
         B = int(batch_size)
         M = max(int(self._cfg.max_steps_per_call), int(max_steps_per_call or 0))
         if B == self._cfg.batch and M == self._cfg.max_steps_per_call:
             return
-        if self.engine.get_state().n_train_steps_total != 0 or getattr(self.engine, "disc", None) is not None:
-            raise ValueError("batch size %d != trainer batch %d, and the engine has already been used: construct the trainer "
+        if getattr(self.engine, "disc", None) is not None:
+            raise ValueError("batch size %d != trainer batch %d, and a discriminator is attached: construct the trainer "
                              "with batch_size=%d" % (B, self._cfg.batch, B))
+        # the optimiser state (Adam step counters, log_alpha and its moments, the train-step counter) lives in the engine:
+        # carry it over, so that load_snapshot() followed by the first _do_training with the algorithm's batch size resumes
+        # exactly (the parameter / moment arenas are shared between the two engines)
+        st = self.engine.get_state()
         self._cfg.batch, self._cfg.max_steps_per_call = B, M
         self.engine = StepEngine(self._cfg, self._nets)
+        self.engine.set_state(st)
 
     # -- the two ways to run gradient steps ------------------------------------------------
     def train_step(self, batch):

@@ -344,7 +344,7 @@ def np_ptr(a):
 class HostSimRun:
     """Runs one parity case through the host simulator with injected randomness."""
 
-    def __init__(self, lib, case, max_steps=64):
+    def __init__(self, lib, case, max_steps=64, precision=0):
         self.lib, self.case = lib, case
         self.arenas = initial_arenas(case)
         self.moms = {}
@@ -357,7 +357,7 @@ class HostSimRun:
             m, v = np.zeros_like(a), np.zeros_like(a)
             self.moms[n] = (m, v)
             mlps[i] = _abi.Mlp(np_ptr(a), np_ptr(m), np_ptr(v), i_d, h_d, o_d, ls)
-        cfg = trainer_config(case, max_steps)
+        cfg = trainer_config(case, max_steps, precision)
         dcfg_p, disc_p = None, None
         if case["algo"] == "adv_irl":
             self.dcfg = disc_config(case)

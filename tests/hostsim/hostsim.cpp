@@ -80,6 +80,8 @@ static void run_op(HostSim* hs, const Program& P, const Op& o, const RunArgs& a,
     }
   } else if (o.kind == OP_POLYAK) {
     for (int i = 0; i < o.polyak.n; ++i) polyak_elem(o.polyak, i);
+  } else if (o.kind == OP_SHADOW) {
+    for (int i = 0; i < o.shadow.dst.n; ++i) shadow_refresh_elem(o.shadow, i);
   }
 }
 
@@ -99,13 +101,17 @@ void* hs_create(const ilsw_trainer_config* cfg, const ilsw_mlp* nets, int n_nets
     delete h;
     return nullptr;
   }
+  // ILSW_HOSTSIM_TC5=1: compile the program variant of the tcgen05/TMA engine (aligned W0 copies, 128-row tile counts) --
+  // the host executes GEMMs element by element, so this checks the program wiring of that variant, not the tile
+  const char* tv = getenv("ILSW_HOSTSIM_TC5");
+  const bool tc5 = tv && atoi(tv) != 0 && tc5_wanted(h->spec);
   Bump measure;
   Program tmp;
-  assemble(tmp, h->spec, measure);
+  assemble(tmp, h->spec, measure, tc5);
   h->scratch.assign(measure.off + 256, 0);
   Bump mem;
   mem.base = h->scratch.data();
-  if (assemble(h->prog, h->spec, mem) != 0) { delete h; return nullptr; }
+  if (assemble(h->prog, h->spec, mem, tc5) != 0) { delete h; return nullptr; }
   DynState* d = h->prog.ctx.dyn;
   memset(d, 0, sizeof(*d));
   d->log_alpha = log(cfg->alpha);

@@ -41,6 +41,36 @@ def test_hostsim_matches_oracle(lib, name):
     run.close()
 
 
+@pytest.mark.parametrize("name", ["sac_hopper_b512_fixed_alpha", "td3_humanoid"])
+def test_hostsim_tcgen05_program_variant(lib, name, monkeypatch):
+    """The program variant of the tcgen05/TMA engine (batch >= 512): 128-row tile counts and, where a first layer has
+    in_dim % 4 != 0, the 16-byte aligned W0 copies that every writer of W0 (fused Adam epilogues, Polyak, the
+    first-step refresh) keeps in sync.  The host executes GEMMs element-wise, so this pins the WIRING of that variant
+    against the oracle; the tile itself is checked on the GPU (tools/tc5_test.cu, tests/test_gpu_engine.py)."""
+    import ctypes as C
+    torch.set_num_threads(1)
+    monkeypatch.setenv("ILSW_HOSTSIM_TC5", "1")
+    case = CFG.CASES[name]
+    rows, final, _ = G.run_oracle(case)
+    run = HostSimRun(lib, case, precision=3)
+    buf = C.create_string_buffer(1 << 15)
+    lib.hs_describe(run.h, buf, 1 << 15)
+    text = buf.value.decode()
+    assert "tcgen05" in text
+    assert ("W0COPY" in text) == ((case["obs_dim"] + case["act_dim"]) % 4 != 0 or case["obs_dim"] % 4 != 0)
+    L = run.train(case["steps"], case_injection(case))
+    for t, row in enumerate(rows):
+        for k, ref in row.items():
+            if k not in STAT_TO_SLOT or ref is None or np.isnan(L[t, STAT_TO_SLOT[k]]):
+                continue
+            tol = 1e-4 * max(abs(ref), 1e-3) if k != "Policy Loss" else 1e-4 * max(abs(ref), 1.0)
+            assert abs(L[t, STAT_TO_SLOT[k]] - ref) <= tol, (name, t, k, L[t, STAT_TO_SLOT[k]], ref)
+    for k in final:
+        if k != "log_alpha":
+            assert_params_close(run.arenas[k], final[k], case["steps"], msg="%s/%s" % (name, k))
+    run.close()
+
+
 def test_hostsim_split_launches_equal_one_launch(lib):
     """State carried across launches (Adam step counts, alpha) == one long launch."""
     case = CFG.CASES["sac_hopper"]
