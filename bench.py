@@ -3,11 +3,14 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sac_hopper|gail_walker|td3_humanoid|sac_ant]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...        # the reference's CPU algorithm (oracle port) on the host cores
+    python bench.py --impl reference ...        # the reference's own classes (rlkit, via oracle/ref_shim) or the oracle port on the host cores
 
 A "step" = ONE gradient step (SAC/TD3: random_batch + train_step; GAIL: one AdvIRL loop iteration,
-SURVEY.md 8d), on synthetic MuJoCo-shaped transitions with random-init nets.  Default workload =
-BASELINE.json configs[1]: SAC Hopper (obs 11, act 3), 1M-transition HBM ring, batch 256.
+SURVEY.md 8d), on synthetic MuJoCo-shaped transitions with random-init nets.  The headline line is
+BASELINE.json configs[1]: SAC Hopper (obs 11, act 3), 1M-transition HBM ring, batch 256; the same
+line carries `workloads` sub-records measured the same way for the other BASELINE configs (GAIL
+Walker2d, TD3 Humanoid B1024, SAC Ant -- at N > 1 only SAC Ant, BASELINE config 5) and, at N > 1,
+`replica_check` (policies bit-equal across ranks; one step against the oracle's R-replica emulation).
 Prints ONE JSON line (see the task contract for the keys).
 """
 import argparse
@@ -56,37 +59,55 @@ def algorithmic_bytes_per_step(w):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons DURING the timed regions.  The driver times 20-step runs (a few ms), far below the
+    200 ms period of `nvidia-smi -lms`, so the clocks are polled through NVML (the library nvidia-smi itself uses) every
+    ~1 ms, and only samples that fall inside a timed region (mark()/unmark()) are reported."""
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+        self.gpu_index, self.samples, self._stop_flag, self._active = gpu_index, [], False, False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.nv = None
 
     def run(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
-        except Exception:
-            pass
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_flag:
+            if not self._active:
+                time.sleep(0.0005)
+                continue
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.samples.append((sm, rs))
+            except Exception:
+                break
+
+    def mark(self):
+        self._active = True
+
+    def unmark(self):
+        self._active = False
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop_flag = True
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": getattr(self, "max_sm", None), "reasons": [], "samples": 0}
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(k for k, bit in names.items() if any(rs & bit for _, rs in self.samples))
+        return {"sm_mhz": float(np.median([sm for sm, _ in self.samples])), "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(self.samples), "source": "NVML polled inside the timed regions"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -234,53 +255,44 @@ def cpu_model():
 
 
 # ------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
-    ap.add_argument("--warmup", type=int, default=2000)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sac_hopper", choices=sorted(WORKLOADS))
-    ap.add_argument("--e2e-steps", type=int, default=2000)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", type=int, default=None, help="GEMM mode: 0 fp32 SIMT, 1 TF32, 3 3xTF32 (default: library default)")
-    args = ap.parse_args()
-    if args.precision is not None:
-        os.environ["ILSW_GEMM_PRECISION"] = str(args.precision)
-    w = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    K, W = args.steps, max(args.warmup, 3)
-    metric = "%s gradient-steps/sec at batch %d" % ("HER-TD3" if w.get("her") else {"sac": "SAC", "gail": "GAIL (adv_irl)", "td3": "TD3"}[w["algo"]], w["B"])
-    config = {"workload": "%s: obs=%d act=%d batch=%d, %d-transition HBM replay ring, 2x%d MLPs, %d gradient steps per kernel launch"
-              % (args.workload, w["O"], w["A"], w["B"], w["N"], w.get("H", 256), LAUNCH), "parallelism": "replicas x%d" % max(world, args.gpus),
-              "global_batch": w["B"] * max(world, 1)}
+def time_reference_classes(w, steps, warmup, threads):
+    """The UNMODIFIED reference classes (rlkit SimpleReplayBuffer + trainers + AdvIRL) on the host cores, when the reference
+    is installed next to the repo (baseline/_ref, shipped with the lease) -- through oracle/ref_shim (checker infra).
+    Returns None when the reference is not importable here."""
+    try:
+        from oracle import ref_shim
+        if not ref_shim.reference_available():
+            return None
+        return ref_shim.time_reference(w, steps, warmup, threads)
+    except Exception as e:      # fall back to the port, say why
+        sys.stderr.write("reference classes unavailable (%s): timing the oracle port\n" % (e,))
+        return None
 
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        cores = best_cpu_threads(w)
-        steps = min(K, 1500 if w["algo"] != "td3" else 600)
-        sps, dt = time_cpu_port(w, steps, min(W, 30), cores)
-        line = {"impl": "reference", "metric": metric, "value": sps, "unit": "gradient-steps/s", "n_gpus": args.gpus,
-                "steps": steps, "warmup": min(W, 30), "ms_per_step": 1000.0 / sps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": sps, "unit": "gradient-steps/s", "cores": cores, "kind": "port",
-                                 "sample": "%d gradient steps (of the %d requested) of the same workload incl. random_batch + "
-                                           "np_to_pytorch_batch, torch CPU %d threads (best of a 1..32 thread calibration; host has %d cores), %s"
-                                           % (steps, K, cores, os.cpu_count() or 1, cpu_model())},
-                "e2e": {"value": sps, "unit": "gradient-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return
 
-    import torch.distributed as dist
+def cpu_arm(w, steps, warmup):
+    """(steps/s, seconds, cores, kind) of the reference's CPU path for workload `w`."""
+    cores = best_cpu_threads(w)
+    got = time_reference_classes(w, steps, warmup, cores)
+    if got is not None:
+        return got[0], got[1], cores, "reference"
+    sps, dt = time_cpu_port(w, steps, warmup, cores)
+    return sps, dt, cores, "port"
 
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+def metric_name(w):
+    return "%s gradient-steps/sec at batch %d" % ("HER-TD3" if w.get("her") else {"sac": "SAC", "gail": "GAIL (adv_irl)", "td3": "TD3"}[w["algo"]], w["B"])
+
+
+def workload_desc(name, w, launch):
+    return ("%s: obs=%d act=%d batch=%d, %d-transition HBM replay ring, 2x%d MLPs, %d gradient steps per kernel launch"
+            % (name, w["O"], w["A"], w["B"], w["N"], w.get("H", 256), launch))
+
+
+def measure(name, args, K, W, rank, world, dist, flush, clock, peak, peak_src, extras):
+    """One workload, measured the contract's way: W warm-up steps, EXACTLY K timed steps (CUDA events around every launch,
+    L2 flushed between launches, max over ranks), then the e2e legs through the public API with host buffers."""
     from ilswiss_b200 import replicas
-
+    w = WORKLOADS[name]
     launch = min(LAUNCH, K)
     tr, buf, irl = build_ours(w, seed=100 + rank, steps_per_launch=launch)
     tr._seed = replicas.replica_seed(12345, rank)
@@ -289,7 +301,6 @@ def main():
     tr.eval_statistics = {}          # no per-epoch stats read-back inside the timed region
     if irl is not None:
         irl.disc_eval_statistics = {}
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def sync_all():
         torch.cuda.synchronize()
@@ -303,12 +314,10 @@ def main():
         run_steps(tr, buf, irl, k)
         done += k
     sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = tr.engine.kernel_launches
     evs = []
     sync_all()
+    clock.mark()
     done = 0
     while done < K:                  # EXACTLY K gradient steps
         k = min(launch, K - done)
@@ -320,7 +329,7 @@ def main():
         evs.append((e0, e1, k))
         done += k
     sync_all()
-    clocks = sampler.stop() if rank == 0 else None
+    clock.unmark()
     ms = sum(a.elapsed_time(b) for a, b, _ in evs)
     launches = tr.engine.kernel_launches - launches0
     full = [a.elapsed_time(b) for a, b, k in evs if k == launch]
@@ -331,15 +340,18 @@ def main():
         ms = float(t.item())
     value = world * K / (ms / 1000.0)
 
-    # ---- e2e through the public API with HOST buffers: per gradient step one transition is appended
-    # from (pinned) host memory, one fused step runs, the step's losses are read back to the host.
-    Ke = min(args.e2e_steps, K)
+    # ---- e2e through the public API with HOST buffers: per gradient step one transition is appended from (pinned) host
+    # memory, one fused step runs, the step's losses are read back to the host.  At least 2000 steps: the per-call
+    # latency of a 1-step launch is what sac_ant.yaml / td3_humanoid.yaml (1 gradient step per train call) users see.
+    Ke = max(min(args.e2e_steps, 4000), 1)
     O, A = w["O"], w["A"]
     rs = np.random.RandomState(5)
     host_obs, host_act = rs.randn(Ke, O), rs.uniform(-1, 1, (Ke, A))
     host_nobs, host_rew = rs.randn(Ke, O), rs.randn(Ke)
+
     def e2e_loop(pipelined):
         sync_all()
+        clock.mark()
         t0 = time.perf_counter()
         for i in range(Ke):
             buf.add_sample(host_obs[i], host_act[i], host_rew[i], False, host_nobs[i])
@@ -354,6 +366,7 @@ def main():
             assert got.shape[0] == Ke and np.isfinite(got[:, :2]).all(), got.shape
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        clock.unmark()
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -383,10 +396,27 @@ def main():
                 "h2d_bytes_per_step": buf.ring.host_w * 4, "d2h_bytes_per_step": 16 * 4,
                 "mode": "per train call: %d-transition burst H2D -> %d-step launch -> loss log D2H" % (launch, launch)}
 
-    # ---- sampler coupling: the per-env-step get_actions round trip with host buffers, env_num = 4,
-    # through ilsw_policy_act_host (one kernel, one sync) next to the eager torch module path the reference uses
-    sampler = None
-    if world == 1:
+    bytes_step = algorithmic_bytes_per_step(w)
+    achieved = bytes_step * launch / (ms_per_launch / 1000.0) / 1e9
+    traffic = None
+    try:
+        per_step = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(name + "_per_step")
+        traffic = None if per_step is None else per_step * launch      # same launch the algorithmic bytes are for
+    except Exception:
+        pass
+    rec = {"metric": metric_name(w), "value": value, "unit": "gradient-steps/s", "steps": K, "warmup": W, "ms_per_step": ms / K,
+           "timing": "device-timed: sum of CUDA-event times around the %d launch(es), max over ranks" % len(evs),
+           "config": {"workload": workload_desc(name, w, launch), "parallelism": "replicas x%d" % world, "global_batch": w["B"] * world,
+                      "l2": "flushed between timed launches (256 MiB write, untimed)", "sampling": "in-kernel Philox, uniform with replacement",
+                      "engine": "tcgen05/TMA GEMM tiles" if getattr(tr.engine, "uses_tc5", lambda: False)() else "mma.sync 32x32 tiles"},
+           "e2e": e2e, "e2e_train_call": e2e_call, "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": traffic, "traffic_note": "ncu dram bytes per step (profiles/) x steps of this launch", "peak_source": peak_src,
+                        "kernel": "ilsw_engine_kernel", "launch_steps": launch, "algorithmic_bytes_per_launch": bytes_step * launch,
+                        "launch_ms": ms_per_launch}}
+
+    if world == 1 and extras:
+        # ---- sampler coupling: the per-env-step get_actions round trip with host buffers, env_num = 4
         from ilswiss_b200.sampler import DevicePolicy
         dp = DevicePolicy(tr, seed=1)
         obs4 = rs.randn(4, O)
@@ -403,13 +433,10 @@ def main():
             for _ in range(500):
                 tr.policy.get_actions(obs4)
         eager_us = (time.perf_counter() - t0) / 500 * 1e6
-        sampler = {"get_actions_us": ours_us, "eager_module_get_actions_us": eager_us, "env_num": 4,
-                   "note": "host numpy obs -> host numpy actions, stochastic; eager = the nn.Module forward the reference's eval_np runs on the same GPU"}
-
-    # ---- the replay ring's own kernel against the HBM roofline: in-kernel Philox sample + gather of a LARGE batch from this
-    # workload's ring (the per-step batch of B rows is gathered inside the engine kernel; this is what the kernel sustains)
-    replay = None
+        rec["sampler"] = {"get_actions_us": ours_us, "eager_module_get_actions_us": eager_us, "env_num": 4,
+                          "note": "host numpy obs -> host numpy actions, stochastic; eager = the nn.Module forward the reference's eval_np runs on the same GPU"}
     if world == 1:
+        # ---- the replay ring's own kernel against the HBM roofline: in-kernel Philox sample + gather of a LARGE batch
         rows_n = (1 << 20) if buf.ring.stride <= 64 else (1 << 18)
         for _ in range(3):
             buf.ring.sample(rows_n, 7, 1)
@@ -422,15 +449,167 @@ def main():
             ts.append(g0.elapsed_time(g1))
             del out
         gms = float(np.median(ts))
-        gby = rows_n * buf.ring.stride * 4 * 2 + rows_n * 4
-        replay = {"kernel": "rb_gather_kernel (Philox sample + gather)", "rows": rows_n, "row_bytes": buf.ring.stride * 4, "ms": gms,
-                  "algorithmic_bytes": gby, "achieved": gby / gms / 1e6, "unit": "GB/s", "l2": "flushed before every timed launch"}
+        row_bytes = (2 * O + A + 2) * 4
+        gby = rows_n * row_bytes * 2 + rows_n * 4
+        rec["replay_roofline"] = {"kernel": "rb_gather_kernel (Philox sample + gather)", "rows": rows_n, "row_bytes": row_bytes,
+                                  "ring_row_stride_bytes": buf.ring.stride * 4, "ms": gms, "algorithmic_bytes": gby,
+                                  "achieved": gby / gms / 1e6, "unit": "GB/s", "peak": peak, "frac": gby / gms / 1e6 / peak,
+                                  "l2": "flushed before every timed launch"}
+    if world == 1 and not args.no_cpu_baseline:
+        n_cpu = {"td3": 120, "gail": 250}.get(w["algo"], 400) if not extras else (600 if w["algo"] != "td3" else 250)
+        sps, dt, cores, kind = cpu_arm(w, n_cpu, 20)
+        rec["cpu_baseline"] = {"value": sps, "unit": "gradient-steps/s", "cores": cores, "kind": kind,
+                               "sample": "%d gradient steps of the same workload (%.1f s), %s on torch CPU with %d threads (best of a 1..32 calibration; host has %d cores), %s"
+                                         % (n_cpu, dt, "the reference's rlkit classes (oracle/ref_shim)" if kind == "reference" else "oracle/restate.py",
+                                            cores, os.cpu_count() or 1, cpu_model())}
+    check = None
+    if world > 1:
+        check = replica_check(tr, buf, w, rank, world, dist)
+    return rec, check, tr, buf, irl
+
+
+def replica_check(tr, buf, w, rank, world, dist):
+    """CHECKER (after the timed region; oracle/ is test infrastructure): (1) the policy arenas of all ranks are bit-equal
+    after the timed launches; (2) ONE more injected step on every rank against the oracle's R-replica emulation -- each
+    rank restates its own step on the CPU from its own critics and batch, the per-rank policy gradients are summed in rank
+    order / R (replicas.emulate_replica_average) and fed to the oracle's Adam; the device policy must match."""
+    from ilswiss_b200 import replicas
+    pol = tr._arenas["policy"]
+    gathered = [torch.empty_like(pol.p) for _ in range(world)]
+    dist.all_gather(gathered, pol.p.contiguous())
+    equal = all(torch.equal(gathered[0], g) for g in gathered[1:])
+    out = {"equal": bool(equal), "world": world}
+    if w["algo"] != "sac":
+        return out
+    try:
+        from oracle import restate as R
+        O, A, B = w["O"], w["A"], w["B"]
+        names = R.mlp_param_names(2)
+
+        def net_from(arena, extra=()):
+            shapes = [tuple(v.shape) for v in arena.views("p")]
+            flat = arena.p.detach().cpu().numpy()
+            keys = R.mlp_param_names(2, extra)
+            d, off = {}, 0
+            for k, shp in zip(keys, shapes):
+                n = int(np.prod(shp)); d[k] = flat[off:off + n].reshape(shp).copy(); off += n
+            net = R.Net(d)
+            for name, store in (("m", net.m), ("v", net.v)):
+                t = getattr(arena, name, None)
+                if t is not None:
+                    f, off = t.detach().cpu().numpy(), 0
+                    for k, shp in zip(keys, shapes):
+                        n = int(np.prod(shp)); store[k] = torch.from_numpy(f[off:off + n].reshape(shp).copy()); off += n
+            return net
+
+        st = tr.engine.get_state()
+        nets = {k: net_from(tr._arenas[k], ("last_fc_log_std",) if k == "policy" else ()) for k in ("policy", "qf1", "qf2", "target_qf1", "target_qf2")}
+        nets["policy"].t, nets["qf1"].t, nets["qf2"].t = int(st.adam_step[2]), int(st.adam_step[0]), int(st.adam_step[1])
+        ora = R.SacAlphaOracle(nets["policy"], nets["qf1"], nets["qf2"], A, reward_scale=w["reward_scale"], policy_lr=3e-4, qf_lr=3e-4,
+                               soft_target_tau=0.005, beta_1=w["beta_1"], target_entropy=w["target_entropy"])
+        ora.target_qf1, ora.target_qf2 = nets["target_qf1"], nets["target_qf2"]
+        ora.log_alpha = float(st.log_alpha)
+        rs = np.random.RandomState(1000 + rank)
+        idx = rs.randint(0, buf.num_steps_can_sample(), B).astype(np.int32)
+        eps_n, eps_c = rs.randn(B, A).astype(np.float32), rs.randn(B, A).astype(np.float32)
+        batch = buf.random_batch_device(B, indices=idx)
+        cpu_batch = {k: v.detach().cpu().clone() for k, v in batch.items()}
+        cpu_batch["rewards"] = cpu_batch["rewards"].reshape(B, 1); cpu_batch["terminals"] = cpu_batch["terminals"].reshape(B, 1)
+        pol0 = nets["policy"].clone()
+        res = ora.train_step(cpu_batch, torch.from_numpy(eps_n), torch.from_numpy(eps_c))
+        g_local = torch.from_numpy(np.concatenate([g.ravel() for g in res["grads"]["policy"]])).cuda()
+        gs = [torch.empty_like(g_local) for _ in range(world)]
+        dist.all_gather(gs, g_local)
+        g_avg = replicas.emulate_replica_average([g.cpu().numpy() for g in gs])
+        parts, off = [], 0
+        for v in pol0.p.values():
+            n = v.numel(); parts.append(torch.from_numpy(g_avg[off:off + n].reshape(tuple(v.shape)).copy())); off += n
+        R.adam_update(pol0, parts, 3e-4, w["beta_1"])
+        inj = dict(idx=torch.from_numpy(idx[None]).cuda(), eps_next=torch.from_numpy(eps_n[None]).cuda(), eps_cur=torch.from_numpy(eps_c[None]).cuda())
+        tr.train_from_buffer(buf, 1, inject=inj)
+        torch.cuda.synchronize()
+        got = tr._arenas["policy"].p.detach().cpu().numpy()
+        want = pol0.flat()
+        diff = np.abs(got - want)
+        out.update({"oracle_max_abs_err": float(diff.max()), "oracle_rel_err": float(diff.max() / max(np.abs(want).max(), 1e-12)),
+                    "frac_beyond_1e-5": float((diff > 1e-5).mean()), "qf1_loss_rel_err": None})
+        L = tr.engine.losses(1)
+        out["qf1_loss_rel_err"] = float(abs(L[0, 0] - res["qf1_loss"]) / max(abs(res["qf1_loss"]), 1e-12))
+        again = [torch.empty_like(pol.p) for _ in range(world)]
+        dist.all_gather(again, pol.p.contiguous())
+        out["equal_after_check_step"] = bool(all(torch.equal(again[0], g) for g in again[1:]))
+        out["ok"] = bool(out["equal"] and out["equal_after_check_step"] and out["frac_beyond_1e-5"] < 5e-3 and out["oracle_max_abs_err"] < 7e-4
+                         and out["qf1_loss_rel_err"] < 1e-4)
+    except Exception as e:
+        out["oracle_error"] = repr(e)
+        out["ok"] = False
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=2000)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sac_hopper", choices=sorted(WORKLOADS))
+    ap.add_argument("--sub", default=None, help="comma-separated sub-record workloads (default: the other BASELINE configs; 'none' to skip)")
+    ap.add_argument("--e2e-steps", type=int, default=2000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", type=int, default=None, help="GEMM mode: 0 fp32 SIMT, 1 TF32, 3 3xTF32 (default: library default)")
+    args = ap.parse_args()
+    if args.precision is not None:
+        os.environ["ILSW_GEMM_PRECISION"] = str(args.precision)
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    K, W = args.steps, max(args.warmup, 3)
+    launch = min(LAUNCH, K)
+    config = {"workload": workload_desc(args.workload, w, launch), "parallelism": "replicas x%d" % max(world, args.gpus),
+              "global_batch": w["B"] * max(world, 1)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = min(K, 1500 if w["algo"] != "td3" else 600)
+        sps, dt, cores, kind = cpu_arm(w, steps, min(W, 30))
+        line = {"impl": "reference", "metric": metric_name(w), "value": sps, "unit": "gradient-steps/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": min(W, 30), "ms_per_step": 1000.0 / sps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": sps, "unit": "gradient-steps/s", "cores": cores, "kind": kind,
+                                 "sample": "%d gradient steps (of the %d requested) of the same workload incl. random_batch + "
+                                           "np_to_pytorch_batch, %s, torch CPU %d threads (best of a 1..32 thread calibration; host has %d cores), %s"
+                                           % (steps, K, "the reference's own rlkit classes (baseline/_ref through oracle/ref_shim)" if kind == "reference"
+                                              else "oracle/restate.py (CPU port pinned to the executed reference)", cores, os.cpu_count() or 1, cpu_model())},
+                "e2e": {"value": sps, "unit": "gradient-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    peaks, peak_src = {}, "fallback"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    clock = ClockSampler(local_rank)
+    if rank == 0:
+        clock.start()
+
+    rec, check, tr, buf, irl = measure(args.workload, args, K, W, rank, world, dist, flush, clock, peak, peak_src, extras=True)
 
     # ---- the same metric in the other GEMM precision modes (short runs, same timing method)
     by_prec = {}
     if world == 1 and args.precision is None:
         cur = int(os.environ.get("ILSW_GEMM_PRECISION", "3"))
-        by_prec[{0: "fp32_simt", 1: "tf32", 3: "tf32x3"}[cur]] = value
+        by_prec[{0: "fp32_simt", 1: "tf32", 3: "tf32x3"}[cur]] = rec["value"]
         for pm in (0, 3, 1):
             if pm == cur:
                 continue
@@ -450,44 +629,41 @@ def main():
             by_prec[{0: "fp32_simt", 1: "tf32", 3: "tf32x3"}[pm]] = 3 * launch / (a0.elapsed_time(a1) / 1000.0)
             del tr2, buf2, irl2
         os.environ["ILSW_GEMM_PRECISION"] = str(cur)
+    del tr, buf, irl
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configs, measured the same way (sub-records of the same line)
+    if args.sub is None:
+        subs = [n for n in (("gail_walker", "td3_humanoid", "sac_ant") if world == 1 else ("sac_ant",)) if n != args.workload]
+    else:
+        subs = [n for n in args.sub.split(",") if n and n != "none"]
+    workloads, checks = {}, {}
+    if check is not None:
+        checks[args.workload] = check
+    for name in subs:
+        r2, c2, t2, b2, i2 = measure(name, args, K, W, rank, world, dist, flush, clock, peak, peak_src, extras=False)
+        workloads[name] = r2
+        if c2 is not None:
+            checks[name] = c2
+        del t2, b2, i2
+        torch.cuda.empty_cache()
+    clocks = clock.stop() if rank == 0 else None
     if rank != 0:
         return
-    peaks, peak_src = {}, "fallback"
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    bytes_step = algorithmic_bytes_per_step(w)
-    achieved = bytes_step * launch / (ms_per_launch / 1000.0) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
-    except Exception:
-        pass
-    line = {"metric": metric, "value": value, "unit": "gradient-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    line = {"metric": rec["metric"], "value": rec["value"], "unit": "gradient-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {0: "f32", 1: "tf32 (tensor-core GEMM operands, f32 accumulate; f32 everywhere else)",
                       3: "f32 via 3xTF32 split on tensor cores"}[int(os.environ.get("ILSW_GEMM_PRECISION", "3"))],
-            "value_by_gemm_precision": by_prec,
-            "data": "synthetic", "config": dict(config, l2="flushed between timed launches (256 MiB write, untimed)",
-                                                sampling="in-kernel Philox, uniform with replacement"),
-            "e2e": e2e, "e2e_train_call": e2e_call, "sampler": sampler, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "ilsw_engine_kernel",
-                         "algorithmic_bytes_per_launch": bytes_step * launch, "launch_ms": ms_per_launch},
-            "clocks": clocks}
-    if replay is not None:
-        replay["peak"], replay["frac"] = peak, replay["achieved"] / peak
-        line["replay_roofline"] = replay
-    if world == 1 and not args.no_cpu_baseline:
-        cores = best_cpu_threads(w)
-        n_cpu = 600 if w["algo"] != "td3" else 250
-        sps, dt = time_cpu_port(w, n_cpu, 20, cores)
-        line["cpu_baseline"] = {"value": sps, "unit": "gradient-steps/s", "cores": cores, "kind": "port",
-                                "sample": "%d gradient steps of the same workload (%.1f s), oracle/restate.py on torch CPU with %d threads (best of a 1..32 calibration; host has %d cores), %s"
-                                          % (n_cpu, dt, cores, os.cpu_count() or 1, cpu_model())}
+            "value_by_gemm_precision": by_prec, "data": "synthetic", "config": dict(config, **{k: v for k, v in rec["config"].items() if k not in config}),
+            "timing": rec["timing"], "e2e": rec["e2e"], "e2e_train_call": rec["e2e_train_call"], "sampler": rec.get("sampler"),
+            "gpu_launches": rec["gpu_launches"], "roofline": rec["roofline"], "clocks": clocks}
+    for k in ("replay_roofline", "cpu_baseline"):
+        if k in rec:
+            line[k] = rec[k]
+    if workloads:
+        line["workloads"] = workloads
+    if checks:
+        line["replica_check"] = checks
     print(json.dumps(line))
 
 

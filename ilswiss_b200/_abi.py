@@ -109,6 +109,7 @@ PROTOTYPES = {
     "ilsw_trainer_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "ilsw_read_cta_ns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ilsw_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "ilsw_trainer_uses_tc5": (C.c_int, [C.c_void_p]),
     "ilsw_policy_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "ilsw_policy_act_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "ilsw_replica_export": (C.c_int, [C.c_void_p, C.c_void_p]),

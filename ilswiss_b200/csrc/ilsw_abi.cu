@@ -534,6 +534,8 @@ extern "C" int ilsw_train(ilsw_trainer* tr, ilsw_rb* policy_rb, ilsw_rb* expert_
   if (a.update_mode == UPDATE_DISC_ONLY && batch) return fail(ILSW_ERR_ARG, "train: a disc-only launch samples from the rings (no direct batch)");
   Replica rp = tr->rep;
   rp.seq0 = tr->seq;
+  rp.grad = tr->host_prog.ctx.policy.g;
+  rp.g_splits = tr->host_prog.ctx.policy.g_splits; rp.g_split_stride = tr->host_prog.ctx.policy.g_stride;
   const Program* dp = tr->dev_prog;
   BarrierState* bar = tr->bar;
   CU(cudaMemsetAsync(bar, 0, sizeof(BarrierState), st));   // monotonic barrier counter restarts at 0
@@ -642,6 +644,7 @@ extern "C" int ilsw_trainer_set_profiling(ilsw_trainer* tr, int on) {
 }
 extern "C" int ilsw_num_phases(const ilsw_trainer* tr) { return tr ? tr->host_prog.n_phases : ILSW_ERR_ARG; }
 extern "C" int64_t ilsw_kernel_launches(const ilsw_trainer* tr) { return tr ? tr->launches : ILSW_ERR_ARG; }
+extern "C" int ilsw_trainer_uses_tc5(const ilsw_trainer* tr) { return tr ? tr->tc5 : ILSW_ERR_ARG; }
 
 extern "C" int ilsw_policy_act(ilsw_trainer* tr, const float* obs_dev, int n, int deterministic, uint64_t seed, float* act_dev,
                                void* stream) {

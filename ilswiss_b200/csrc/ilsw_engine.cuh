@@ -36,6 +36,7 @@ struct Replica {
   int n;                      // policy parameter count
   int nstride;                // slot stride (n rounded up to 4 floats: 16-byte aligned slots)
   const float* grad;          // local policy gradient arena
+  int g_splits, g_split_stride;   // > 1: the local gradient is the sum of split-K partial arenas (see AdamOp)
   float* recv_local;          // [2][world][n]  (parity, source rank)
   float* recv_peer[8];        // recv_local of every rank (self included)
   unsigned* flags_local;      // [8] sequence numbers written by the peers
@@ -716,8 +717,18 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
 // Exact fp32 on the SIMT pipes, straight from L2 (no panels, no MMA): thread -> (col = tid % 32, k = tid / 32 + 8 i), 8 k's
 // of loads in flight per thread; the 8 k-groups are summed through shared memory in a fixed order.  A ragged MMA tile
 // for these shapes costs a full tile (5 us); this is ~1.5 us.
-__device__ __noinline__ void gemm_tile_skinny(const GemmOp& og, int tile, float* smem, const AdamOp* ad, const AdamCoef* cf) {
-  const GemmOp o = og;
+// Split along K (tcgen05 programs, K = batch >= 512): job (ks, tile) sums k in [ks * K / S, (ks + 1) * K / S) into the
+// partial gradient arena ks (C + ks * split_stride); one CTA walking K = 1024 alone took 23 us.
+__device__ __noinline__ void gemm_tile_skinny(const GemmOp& og, int tile_in, float* smem, const AdamOp* ad, const AdamCoef* cf) {
+  GemmOp o = og;
+  const int nsplit = o.ksplit > 1 ? o.ksplit : 1;
+  const int ks = tile_in / o.tiles_n, tile = tile_in - ks * o.tiles_n;
+  const int kbeg = (int)(((long long)ks * o.K) / nsplit), kend = (int)(((long long)(ks + 1) * o.K) / nsplit);
+  if (nsplit > 1) {
+    o.A += (size_t)kbeg * o.lda; o.B += (size_t)kbeg * o.ldb; o.K = kend - kbeg;
+    o.C += (size_t)ks * o.split_stride;
+    if (o.bias_out) o.bias_out += (size_t)ks * o.split_stride;
+  }
   const int tid = threadIdx.x, col = tid & 31, kg = tid >> 5;
   const int n = tile * 32 + col;
   const int M = o.M;
@@ -790,10 +801,15 @@ __device__ __forceinline__ bool replica_exchange(const Replica& rp, unsigned seq
   const int n4 = rp.n >> 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
     float4 v = __ldcg(reinterpret_cast<const float4*>(rp.grad) + i);
+    for (int sp = 1; sp < rp.g_splits; ++sp) {
+      const float4 w = __ldcg(reinterpret_cast<const float4*>(rp.grad + (size_t)sp * rp.g_split_stride) + i);
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
     for (int r = 0; r < rp.world; ++r) reinterpret_cast<float4*>(rp.recv_peer[r] + slot)[i] = v;
   }
   for (int i = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < rp.n; i += gridDim.x * blockDim.x) {
     float v = __ldcg(rp.grad + i);
+    for (int sp = 1; sp < rp.g_splits; ++sp) v += __ldcg(rp.grad + (size_t)sp * rp.g_split_stride + i);
     for (int r = 0; r < rp.world; ++r) rp.recv_peer[r][slot + i] = v;
   }
   __threadfence_system();
@@ -849,7 +865,7 @@ __device__ __noinline__ void adam_job(const AdamOp& ao, const AdamCoef& cfs, int
       // __fmul_rn: the scaled gradient must be ROUNDED before Adam consumes it -- a plain `* gscale` gets contracted into
       // the first FMA of adam_math_store ((s * gscale) - m), which made R identical replicas differ from one replica by an
       // ulp (tools/replica_check.py, test A: the single-replica program applies Adam in the weight-gradient epilogues)
-      g[u] = __fmul_rn(reduced ? replica_reduced_grad(rp, xseq, i) : __ldcg(ao.g + i), gscale);
+      g[u] = __fmul_rn(reduced ? replica_reduced_grad(rp, xseq, i) : adam_grad(ao, i), gscale);
       m[u] = ao.m[i]; v[u] = ao.v[i]; p[u] = ao.p[i];
       tg[u] = ao.target ? ao.target[i] : 0.f;
     }
@@ -945,7 +961,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
           const AdamOp* ad = o.gemm.adam ? &s_ops[o.gemm.adam - 1].adam : nullptr;
           const AdamCoef* cf = ad ? &s_coefs[ad->slot] : nullptr;
           if (TC5 && o.gemm.tc5) {
-            if (!tc5::gemm_tile<kTc5BN>(o.gemm, j, tc5_smem, s_tc5, tc5_state, ad, cf)) {
+            if (!tc5::gemm_tile<kTc5BN>(o.gemm, j, tc5_smem, s_tc5, tc5_state)) {
               if (threadIdx.x == 0) atomicExch(abort_flag, 1);     // the other CTAs leave their barrier wait
               alive = false;
             }

@@ -240,7 +240,23 @@ ILSW_HD void adam_math_store(const AdamOp& o, const AdamCoef& c, int i, float g,
 ILSW_HD void adam_elem_g(const AdamOp& o, const AdamCoef& c, int i, float g) {
   adam_math_store(o, c, i, g, o.m[i], o.v[i], o.p[i], o.target ? o.target[i] : 0.f);
 }
-ILSW_HD void adam_elem(const AdamOp& o, const AdamCoef& c, int i) { adam_elem_g(o, c, i, ldg(o.g + i) * c.gscale); }
+// gradient element i: the sum of the split-K partial arenas in a fixed order (one arena without splits)
+// All partial loads are issued before the first add (a runtime-trip-count loop of load + add serialises one L2 round
+// trip per split: measured 17 us per 2048-element Adam job on the B200).
+ILSW_HD float adam_grad(const AdamOp& o, int i) {
+  float part[kMaxGradSplits];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int s = 0; s < kMaxGradSplits; ++s) part[s] = (s == 0 || s < o.g_splits) ? ldg(o.g + (size_t)s * o.g_split_stride + i) : 0.f;
+  float g = part[0];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int s = 1; s < kMaxGradSplits; ++s) g += part[s];
+  return g;
+}
+ILSW_HD void adam_elem(const AdamOp& o, const AdamCoef& c, int i) { adam_elem_g(o, c, i, adam_grad(o, i) * c.gscale); }
 
 // fused optimiser epilogue: element (m,n) of GEMM `o` is gradient element `gi` of the arena described by `ad`
 ILSW_HD int gemm_grad_index(const GemmOp& o, const AdamOp& ad, int m, int n) {
@@ -323,19 +339,37 @@ ILSW_HDN void row_sac_gather(const Ctx& c, const RunArgs& a, int s, int b, int l
     rew = (sqrtf(ss) > a.her.threshold) ? -1.0f : -0.0f;
   }
   if (lane == 0) { S.rew[b] = rew; S.term[b] = term; }
-  for (int k = lane; k < O; k += nl) {
-    float o = obs[k], n = nobs[k];
-    if (relabel && k >= g0) o = n = goal_src[k - g0];
-    S.Xoa[(size_t)b * S.ld_oa + k] = o;
-    S.Xon[(size_t)b * S.ld_oa + k] = o;
-    S.Xna[(size_t)b * S.ld_oa + k] = n;
-    if (c.hp.has_disc && c.hp.state_only) {          // reward relabel input cat(obs, next_obs) (adv_irl.py:265-269)
-      c.d.Xsn[(size_t)b * c.d.ld_sn + k] = o;
-      c.d.Xsn[(size_t)b * c.d.ld_sn + O + k] = n;
+  // ring rows come from HBM: all loads of a batch of 8 elements per lane are issued before the first store (a plain
+  // load/store loop serialises one DRAM round trip per 32 floats: 25 us for 1024 Humanoid rows)
+  constexpr int kGB = 8;
+  for (int k0 = 0; k0 < O; k0 += kGB * nl) {
+    float ov[kGB], nv[kGB];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int u = 0; u < kGB; ++u) {
+      const int k = k0 + lane + u * nl;
+      if (k < O) { ov[u] = obs[k]; nv[u] = nobs[k]; }
     }
-    if (!td3) {
-      S.Xpi[(size_t)b * S.ld_o + k] = n;            // rows [0,B): next_obs
-      S.Xpi[(size_t)(B + b) * S.ld_o + k] = o;      // rows [B,2B): obs
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int u = 0; u < kGB; ++u) {
+      const int k = k0 + lane + u * nl;
+      if (k >= O) continue;
+      float o = ov[u], n = nv[u];
+      if (relabel && k >= g0) o = n = goal_src[k - g0];
+      S.Xoa[(size_t)b * S.ld_oa + k] = o;
+      S.Xon[(size_t)b * S.ld_oa + k] = o;
+      S.Xna[(size_t)b * S.ld_oa + k] = n;
+      if (c.hp.has_disc && c.hp.state_only) {          // reward relabel input cat(obs, next_obs) (adv_irl.py:265-269)
+        c.d.Xsn[(size_t)b * c.d.ld_sn + k] = o;
+        c.d.Xsn[(size_t)b * c.d.ld_sn + O + k] = n;
+      }
+      if (!td3) {
+        S.Xpi[(size_t)b * S.ld_o + k] = n;            // rows [0,B): next_obs
+        S.Xpi[(size_t)(B + b) * S.ld_o + k] = o;      // rows [B,2B): obs
+      }
     }
   }
   for (int j = lane; j < A; j += nl) {
@@ -668,6 +702,9 @@ ILSW_HDN void row_td3_final_policy(const Ctx& c, const RunArgs& a, int s, int r,
   if (r != 0) return;
   float pl = wmean(c.s.plterm, c.s.B, lane, nl);
   if (lane == 0) c.loss_log[(size_t)(a.loss_log_offset + s) * kLossSlots + L_POLICY] = pl;
+  // "Policy Action" of the logged step = the deterministic policy actions of THIS step (td3.py:113-136), computed after
+  // row_td3_final took its snapshot
+  if (s == a.stats_step) stats_copy(c.stats + 6 * c.s.B, c.s.act, c.s.B * c.s.A, lane, nl);
 }
 
 // ---- AdvIRL discriminator --------------------------------------------------------------
@@ -951,6 +988,10 @@ ILSW_HD bool phase_active(const Phase& ph, const Hyper& hp, const RunArgs& a, in
   if (ph.cond & COND_TD3_POLICY) {
     int per = hp.period > 0 ? hp.period : 1;
     return ((a.step0 + s) % per) == 0;
+  }
+  if (ph.cond & COND_TD3_POLICY_OR_STATS) {
+    int per = hp.period > 0 ? hp.period : 1;
+    return ((a.step0 + s) % per) == 0 || s == a.stats_step;
   }
   return true;
 }

@@ -13,6 +13,7 @@
 namespace ilsw {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+constexpr int kMaxKSplits = kMaxGradSplits;   // partial gradient arenas of a tcgen05 program (adam_grad sums exactly this many)
 
 // two-pass bump allocator: pass 1 (base==nullptr) measures, pass 2 hands out pointers
 struct Bump {
@@ -85,7 +86,10 @@ struct Builder {
     g.tmapA = g.tmapB = nullptr;
     if (g.tc5) { g.tiles_m = (g.M + 127) / 128; g.tiles_n = (g.N + kTc5BN - 1) / kTc5BN; }
     else { g.tiles_m = (g.M + 31) / 32; g.tiles_n = (g.N + 31) / 32; }   // the aug (bias-gradient) column is produced by the tn==0 tiles
-    Op* o = add(OP_GEMM, g.tiles_m * g.tiles_n);
+    const bool skinny = g.M <= 8 && g.a_mc && g.b_nc && g.tiles_m == 1;        // gemm_is_skinny (ilsw_engine.cuh)
+    if (!(g.tc5 || skinny) || g.ksplit < 1) g.ksplit = 1;
+    g.ksplit = g.ksplit < (g.K + 63) / 64 ? g.ksplit : (g.K + 63) / 64;
+    Op* o = add(OP_GEMM, g.ksplit * g.tiles_m * g.tiles_n);
     if (o) o->gemm = g;
   }
   // the aligned copy of a first-layer weight matrix, if `W` is one that has a copy (ShadowRef in ilsw_types.h)
@@ -124,14 +128,29 @@ struct Builder {
   }
   // G[Mout,Nin] (+)= D[Kb,Mout]^T X[Kb,Nin] ; gbias[Mout] (+)= colsum(D)   (weight gradient)
   // adam_op >= 0: index of an adam_desc() op -- the epilogue applies the optimiser step to what it produces
+  // net != nullptr (tcgen05 programs): the GEMM may be split along K over net->g_splits partial gradient arenas
+  int dw_splits = 1;    // K splits requested for the following dw() calls (set per phase by the program builders)
   void dw(const float* D, int ldd, int Mout, const float* X, int ldx, int Nin, int Kb, float* G, float* gbias,
-          int accumulate = 0, int adam_op = -1) {
+          int accumulate = 0, int adam_op = -1, const MlpPtrs* net = nullptr) {
     GemmOp g; memset(&g, 0, sizeof(g));
     g.A = D; g.lda = ldd; g.a_mc = 1; g.B = X; g.ldb = ldx; g.b_nc = 1; g.M = Mout; g.N = Nin; g.K = Kb;
     g.C = G; g.ldc = Nin; g.aug_ones = gbias ? 1 : 0; g.bias_out = gbias; g.accumulate = accumulate;
     g.adam = adam_op >= 0 ? adam_op + 1 : 0;
+    if (net && net->g_splits > 1 && adam_op < 0 && !accumulate) {
+      g.ksplit = dw_splits < net->g_splits ? dw_splits : net->g_splits;
+      g.split_stride = net->g_stride;
+    }
     gemm(g);
   }
+  // K splits that bring a weight-gradient phase of `tiles` tcgen05 tiles close to one wave of the 148-SM grid
+  static int pick_splits(int tiles, int Kb, int max_splits) {
+    int s = tiles > 0 ? 148 / tiles : 1;
+    const int nkb = (Kb + 31) / 32;
+    if (s > nkb / 4) s = nkb / 4;          // at least 4 K blocks (one pipeline depth) per split
+    if (s > max_splits) s = max_splits;
+    return s < 1 ? 1 : s;
+  }
+  static int tc5_tiles(int M, int N) { return ((M + 127) / 128) * ((N + kTc5BN - 1) / kTc5BN); }
   void row(int kind, int rows, int next_step = 0, int row_offset = 0) {
     Op* o = add(OP_ROW, (rows + kRowsPerJob - 1) / kRowsPerJob);
     if (o) { o->row.kind = kind; o->row.rows = rows + row_offset; o->row.arg0 = next_step; o->row.arg1 = row_offset; }
@@ -146,6 +165,7 @@ struct Builder {
     o->adam.n = n.n_params; o->adam.lr = lr; o->adam.beta1 = b1; o->adam.beta2 = b2; o->adam.eps = eps;
     o->adam.tau = tau; o->adam.slot = slot; o->adam.grad_scale_world = 0; o->adam.begin = 0; o->adam.fused_only = 1;
     o->adam.sh_p = shadow_of(&n); o->adam.sh_t = shadow_of(target);
+    o->adam.g_splits = n.g_splits; o->adam.g_split_stride = n.g_stride;
     return idx;
   }
   void adam(const MlpPtrs& n, const MlpPtrs* target, double lr, double b1, double b2, double eps, float tau, int slot,
@@ -157,6 +177,7 @@ struct Builder {
     o->adam.n = n.n_params; o->adam.lr = lr; o->adam.beta1 = b1; o->adam.beta2 = b2; o->adam.eps = eps;
     o->adam.tau = tau; o->adam.slot = slot; o->adam.grad_scale_world = world_scale;
     o->adam.sh_p = shadow_of(&n); o->adam.sh_t = shadow_of(target);
+    o->adam.g_splits = n.g_splits; o->adam.g_split_stride = n.g_stride;
   }
   void polyak(const MlpPtrs& src, const MlpPtrs& tgt, float tau) {
     Op* o = add(OP_POLYAK, (src.n_params + kAdamChunk - 1) / kAdamChunk);
@@ -319,23 +340,40 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
   b.phase();
   for (int i = 0; i < 2; ++i) b.fwd(S.h0t[i], Hd, B, Hd, c.tqf[i].p + c.tqf[i].oW1, c.tqf[i].p + c.tqf[i].ob1, Hd, S.h1t[i], Hd, ACT_RELU);
   b.phase(); b.row(ROW_SAC_TARGET, B);
-  b.phase();   // backward-data of both critics: one full tile per CTA
-  {
-    int ad[2];
-    for (int i = 0; i < 2; ++i) ad[i] = b.adam_desc(c.qf[i], &c.tqf[i], c.hp.qf_lr, b1, b2, eps, c.hp.tau, i == 0 ? SLOT_QF1 : SLOT_QF2);
+  const bool tc5 = c.hp.use_tc5 != 0;
+  if (tc5) {
+    // tcgen05 programs: weight gradients are split along K (= batch) over partial arenas and the optimiser runs as flat
+    // jobs over the whole grid (see ilsw_tc5.cuh); the Polyak update of the targets rides in the same Adam jobs
+    b.phase();
     for (int i = 0; i < 2; ++i)
       b.dx(S.d1q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
-    // the output-layer gradient (+ Adam/Polyak of W2, b2) needs only dq and h1 and nothing reads W2 any more this
-    // step: when the backward-data phase leaves CTAs idle its skinny tiles run there, which keeps the weight-gradient
-    // phase within one wave of the grid (160 -> 144 jobs at B = 256)
-    const bool early_w2 = early_out_layer_grad(B, Hd);
-    if (early_w2)
-      for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
-    b.phase();   // the other weight gradients of both critics; Adam + Polyak of the targets fused into the tile epilogues
-    for (int i = 0; i < 2; ++i) b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW1, c.qf[i].g + c.qf[i].ob1, 0, ad[i]);
-    for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0, 0, ad[i]);
-    if (!early_w2)
-      for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
+    b.dw_splits = kMaxKSplits;       // skinny output-layer gradients: K = batch split over the partial arenas too
+    for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, -1, &c.qf[i]);
+    b.phase();
+    b.dw_splits = Builder::pick_splits(2 * (Builder::tc5_tiles(Hd, Hd) + Builder::tc5_tiles(Hd, K0)), B, kMaxKSplits);
+    for (int i = 0; i < 2; ++i) b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW1, c.qf[i].g + c.qf[i].ob1, 0, -1, &c.qf[i]);
+    for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0, 0, -1, &c.qf[i]);
+    b.phase();
+    for (int i = 0; i < 2; ++i) b.adam(c.qf[i], &c.tqf[i], c.hp.qf_lr, b1, b2, eps, c.hp.tau, i == 0 ? SLOT_QF1 : SLOT_QF2);
+  } else {
+    b.phase();   // backward-data of both critics: one full tile per CTA
+    {
+      int ad[2];
+      for (int i = 0; i < 2; ++i) ad[i] = b.adam_desc(c.qf[i], &c.tqf[i], c.hp.qf_lr, b1, b2, eps, c.hp.tau, i == 0 ? SLOT_QF1 : SLOT_QF2);
+      for (int i = 0; i < 2; ++i)
+        b.dx(S.d1q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
+      // the output-layer gradient (+ Adam/Polyak of W2, b2) needs only dq and h1 and nothing reads W2 any more this
+      // step: when the backward-data phase leaves CTAs idle its skinny tiles run there, which keeps the weight-gradient
+      // phase within one wave of the grid (160 -> 144 jobs at B = 256)
+      const bool early_w2 = early_out_layer_grad(B, Hd);
+      if (early_w2)
+        for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
+      b.phase();   // the other weight gradients of both critics; Adam + Polyak of the targets fused into the tile epilogues
+      for (int i = 0; i < 2; ++i) b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW1, c.qf[i].g + c.qf[i].ob1, 0, ad[i]);
+      for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0, 0, ad[i]);
+      if (!early_w2)
+        for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
+    }
   }
   b.phase();
   for (int i = 0; i < 2; ++i) b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0n[i], Hd, ACT_RELU);
@@ -347,6 +385,20 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
   b.phase(); b.row(ROW_SAC_PIBWD_DA, B);      // dA = e0 . W0[:, O:O+A] fused into the head backward rows
   b.phase();
   b.dx(S.d1p, Hd, B, Hd, P.p + P.oW1, Hd, Hd, h0p_obs, Hd, ACT_RELU, S.d0p, Hd);
+  if (tc5) {
+    // gradients (split along K), then the exchange (replicas only) + flat Adam of the (averaged) gradient
+    b.phase();
+    b.dw_splits = Builder::pick_splits(Builder::tc5_tiles(Hd, Hd) + Builder::tc5_tiles(Hd, O) + (A > 8 ? 2 * Builder::tc5_tiles(A, Hd) : 0), B, kMaxKSplits);
+    b.dw(S.d1p, Hd, Hd, h0p_obs, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1, 0, -1, &P);
+    b.dw(S.d0p, Hd, Hd, obs_rows, S.ld_o, O, B, P.g + P.oW0, P.g + P.ob0, 0, -1, &P);
+    b.dw(S.dmean, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2, 0, -1, &P);
+    b.dw(S.dlraw, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW3, P.g + P.ob3, 0, -1, &P);
+    b.phase(COND_ALWAYS, 1);
+    b.adam(P, nullptr, c.hp.policy_lr, b1, b2, eps, 0.f, SLOT_POLICY, 1);
+    b.row(ROW_SAC_FINAL, 1);
+    b.row(ROW_SAC_GATHER, B, /*next_step=*/1);
+    return;
+  }
   // one replica: the policy's Adam step is fused into its weight-gradient tiles
   b.phase(COND_WORLD_1);
   {
@@ -393,34 +445,67 @@ inline void build_td3(Builder& b, const Ctx& c) {
   b.phase();
   for (int i = 0; i < 2; ++i) b.fwd(S.h0t[i], Hd, B, Hd, c.tqf[i].p + c.tqf[i].oW1, c.tqf[i].p + c.tqf[i].ob1, Hd, S.h1t[i], Hd, ACT_RELU);
   b.phase(); b.row(ROW_TD3_TARGET, B);
-  b.phase();
-  {
-    int ad[2];
-    for (int i = 0; i < 2; ++i) ad[i] = b.adam_desc(c.qf[i], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, i == 0 ? SLOT_QF1 : SLOT_QF2);
+  const bool tc5 = c.hp.use_tc5 != 0;
+  if (tc5) {        // see build_sac_alpha: split-K weight gradients, flat Adam jobs
+    b.phase();
     for (int i = 0; i < 2; ++i)
       b.dx(S.d1q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
-    const bool early_w2 = early_out_layer_grad(B, Hd);      // see build_sac_alpha
-    if (early_w2)
-      for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
-    b.phase();   // weight gradients of both critics with the Adam step fused into the tile epilogues
-    for (int i = 0; i < 2; ++i) b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW1, c.qf[i].g + c.qf[i].ob1, 0, ad[i]);
-    for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0, 0, ad[i]);
-    if (!early_w2)
-      for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
-  }
+    b.dw_splits = kMaxKSplits;       // skinny output-layer gradients: K = batch split over the partial arenas too
+    for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, -1, &c.qf[i]);
+    b.phase();
+    b.dw_splits = Builder::pick_splits(2 * (Builder::tc5_tiles(Hd, Hd) + Builder::tc5_tiles(Hd, K0)), B, kMaxKSplits);
+    for (int i = 0; i < 2; ++i) b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW1, c.qf[i].g + c.qf[i].ob1, 0, -1, &c.qf[i]);
+    for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0, 0, -1, &c.qf[i]);
+    b.phase();
+    for (int i = 0; i < 2; ++i) b.adam(c.qf[i], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, i == 0 ? SLOT_QF1 : SLOT_QF2);
+  } else {
+  b.phase();
+    {
+      int ad[2];
+      for (int i = 0; i < 2; ++i) ad[i] = b.adam_desc(c.qf[i], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, i == 0 ? SLOT_QF1 : SLOT_QF2);
+      for (int i = 0; i < 2; ++i)
+        b.dx(S.d1q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0q[i], Hd, ACT_RELU, S.d0q[i], Hd);
+      const bool early_w2 = early_out_layer_grad(B, Hd);      // see build_sac_alpha
+      if (early_w2)
+        for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
+      b.phase();   // weight gradients of both critics with the Adam step fused into the tile epilogues
+      for (int i = 0; i < 2; ++i) b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW1, c.qf[i].g + c.qf[i].ob1, 0, ad[i]);
+      for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0, 0, ad[i]);
+      if (!early_w2)
+        for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
+    }
+}
   b.row(ROW_TD3_FINAL, 1);
   // delayed policy + target update (td3.py:113-124), steps with (n_train_steps_total % period)==0
   const int PC = COND_TD3_POLICY;
-  b.phase(PC); b.fwd(S.Xoa, S.ld_oa, B, O, P.p + P.oW0, P.p + P.ob0, Hd, S.h0p, Hd, ACT_RELU);
-  b.phase(PC); b.fwd(S.h0p, Hd, B, Hd, P.p + P.oW1, P.p + P.ob1, Hd, S.h1p, Hd, ACT_RELU);
-  b.phase(PC); b.row(ROW_TD3_PHEAD, B);
-  b.phase(PC); b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[0].p + c.qf[0].oW0, c.qf[0].p + c.qf[0].ob0, Hd, S.h0n[0], Hd, ACT_RELU);
-  b.phase(PC); b.fwd(S.h0n[0], Hd, B, Hd, c.qf[0].p + c.qf[0].oW1, c.qf[0].p + c.qf[0].ob1, Hd, S.h1n[0], Hd, ACT_RELU);
-  b.phase(PC); b.row(ROW_TD3_PLOSS, B);
-  b.phase(PC); b.dx(S.e1[0], Hd, B, Hd, c.qf[0].p + c.qf[0].oW1, Hd, Hd, S.h0n[0], Hd, ACT_RELU, S.e0[0], Hd);
+  // the forward half also runs on the statistics step of a launch when that is not a policy step: the reference logs a
+  // stats-only policy loss -mean(Q1(obs, pi(obs))) and its actions there (td3.py:131-136)
+  const int PS = COND_TD3_POLICY_OR_STATS;
+  b.phase(PS); b.fwd(S.Xoa, S.ld_oa, B, O, P.p + P.oW0, P.p + P.ob0, Hd, S.h0p, Hd, ACT_RELU);
+  b.phase(PS); b.fwd(S.h0p, Hd, B, Hd, P.p + P.oW1, P.p + P.ob1, Hd, S.h1p, Hd, ACT_RELU);
+  b.phase(PS); b.row(ROW_TD3_PHEAD, B);
+  b.phase(PS); b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[0].p + c.qf[0].oW0, c.qf[0].p + c.qf[0].ob0, Hd, S.h0n[0], Hd, ACT_RELU);
+  b.phase(PS); b.fwd(S.h0n[0], Hd, B, Hd, c.qf[0].p + c.qf[0].oW1, c.qf[0].p + c.qf[0].ob1, Hd, S.h1n[0], Hd, ACT_RELU);
+  b.phase(PS); b.row(ROW_TD3_PLOSS, B);
+  // the policy loss of this step is complete: log it here (policy steps and the statistics step alike; on a stats-only
+  // step the backward-data tile of this phase is dead work, once per epoch)
+  b.phase(PS); b.dx(S.e1[0], Hd, B, Hd, c.qf[0].p + c.qf[0].oW1, Hd, Hd, S.h0n[0], Hd, ACT_RELU, S.e0[0], Hd);
+  b.row(ROW_TD3_FINAL_POLICY, 1);
   b.phase(PC); b.row(ROW_TD3_PIBWD_DA, B);
   b.phase(PC);
   b.dx(S.d1p, Hd, B, Hd, P.p + P.oW1, Hd, Hd, S.h0p, Hd, ACT_RELU, S.d0p, Hd);
+  if (tc5) {
+    b.phase(PC);
+    b.dw_splits = Builder::pick_splits(Builder::tc5_tiles(Hd, Hd) + Builder::tc5_tiles(Hd, O) + (A > 8 ? Builder::tc5_tiles(A, Hd) : 0), B, kMaxKSplits);
+    b.dw(S.d1p, Hd, Hd, S.h0p, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1, 0, -1, &P);
+    b.dw(S.d0p, Hd, Hd, S.Xoa, S.ld_oa, O, B, P.g + P.oW0, P.g + P.ob0, 0, -1, &P);
+    b.dw(S.dmean, A, A, S.h1p, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2, 0, -1, &P);
+    b.phase(PC, 1);
+    b.adam(P, &c.tpolicy, c.hp.policy_lr, b1, b2, eps, c.hp.tau, SLOT_POLICY, 1);
+    b.polyak(c.qf[0], c.tqf[0], c.hp.tau);
+    b.polyak(c.qf[1], c.tqf[1], c.hp.tau);
+    return;
+  }
   b.phase(PC | COND_WORLD_1);
   {
     const int ad = b.adam_desc(P, &c.tpolicy, c.hp.policy_lr, b1, b2, eps, c.hp.tau, SLOT_POLICY);
@@ -430,7 +515,6 @@ inline void build_td3(Builder& b, const Ctx& c) {
   }
   b.polyak(c.qf[0], c.tqf[0], c.hp.tau);
   b.polyak(c.qf[1], c.tqf[1], c.hp.tau);
-  b.row(ROW_TD3_FINAL_POLICY, 1);
   b.phase(PC | COND_WORLD_N);
   b.dw(S.d1p, Hd, Hd, S.h0p, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);
   b.dw(S.d0p, Hd, Hd, S.Xoa, S.ld_oa, O, B, P.g + P.oW0, P.g + P.ob0);
@@ -439,7 +523,6 @@ inline void build_td3(Builder& b, const Ctx& c) {
   b.adam(P, &c.tpolicy, c.hp.policy_lr, b1, b2, eps, c.hp.tau, SLOT_POLICY, 1);
   b.polyak(c.qf[0], c.tqf[0], c.hp.tau);
   b.polyak(c.qf[1], c.tqf[1], c.hp.tau);
-  b.row(ROW_TD3_FINAL_POLICY, 1);
 }
 
 // S2: SAC with a V function and a fixed entropy coefficient (sac.py:70-179, 242-243)
@@ -475,19 +558,36 @@ inline void build_sac_v(Builder& b, const Ctx& c) {
   // all three backward passes first, then the three Adam steps (sac.py:132-139): the weight-gradient tiles read
   // only deltas and activations computed above, so fusing each Adam (+ Polyak of the target V, :242-243) into
   // their epilogues keeps that order
+  const bool tc5 = c.hp.use_tc5 != 0;
+  if (tc5) {        // see build_sac_alpha: split-K weight gradients, flat Adam jobs (all three after all three backwards)
+    b.phase();
+    b.dw_splits = Builder::pick_splits(3 * Builder::tc5_tiles(Hd, Hd) + 2 * Builder::tc5_tiles(Hd, K0) + Builder::tc5_tiles(Hd, O), B, kMaxKSplits);
+    for (int i = 0; i < 2; ++i) b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW1, c.qf[i].g + c.qf[i].ob1, 0, -1, &c.qf[i]);
+    b.dw(S.d1v, Hd, Hd, S.h0v, Hd, Hd, B, V.g + V.oW1, V.g + V.ob1, 0, -1, &V);
+    for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0, 0, -1, &c.qf[i]);
+    b.dw(S.d0v, Hd, Hd, S.Xoa, S.ld_oa, O, B, V.g + V.oW0, V.g + V.ob0, 0, -1, &V);
+    b.dw_splits = kMaxKSplits;       // skinny output-layer gradients: K = batch split over the partial arenas too
+    for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, -1, &c.qf[i]);
+    b.dw(S.dv, 1, 1, S.h1v, Hd, Hd, B, V.g + V.oW2, V.g + V.ob2, 0, -1, &V);
+    b.phase();
+    b.adam(c.qf[0], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF1);
+    b.adam(c.qf[1], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF2);
+    b.adam(V, &c.tvf, c.hp.vf_lr, b1, b2, eps, c.hp.tau, SLOT_VF);
+  } else {
   b.phase();
-  {
-    const int aq0 = b.adam_desc(c.qf[0], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF1);
-    const int aq1 = b.adam_desc(c.qf[1], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF2);
-    const int av = b.adam_desc(V, &c.tvf, c.hp.vf_lr, b1, b2, eps, c.hp.tau, SLOT_VF);
-    const int ad[2] = {aq0, aq1};
-    for (int i = 0; i < 2; ++i) b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW1, c.qf[i].g + c.qf[i].ob1, 0, ad[i]);
-    b.dw(S.d1v, Hd, Hd, S.h0v, Hd, Hd, B, V.g + V.oW1, V.g + V.ob1, 0, av);
-    for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0, 0, ad[i]);
-    b.dw(S.d0v, Hd, Hd, S.Xoa, S.ld_oa, O, B, V.g + V.oW0, V.g + V.ob0, 0, av);
-    for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
-    b.dw(S.dv, 1, 1, S.h1v, Hd, Hd, B, V.g + V.oW2, V.g + V.ob2, 0, av);
-  }
+    {
+      const int aq0 = b.adam_desc(c.qf[0], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF1);
+      const int aq1 = b.adam_desc(c.qf[1], nullptr, c.hp.qf_lr, b1, b2, eps, 0.f, SLOT_QF2);
+      const int av = b.adam_desc(V, &c.tvf, c.hp.vf_lr, b1, b2, eps, c.hp.tau, SLOT_VF);
+      const int ad[2] = {aq0, aq1};
+      for (int i = 0; i < 2; ++i) b.dw(S.d1q[i], Hd, Hd, S.h0q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW1, c.qf[i].g + c.qf[i].ob1, 0, ad[i]);
+      b.dw(S.d1v, Hd, Hd, S.h0v, Hd, Hd, B, V.g + V.oW1, V.g + V.ob1, 0, av);
+      for (int i = 0; i < 2; ++i) b.dw(S.d0q[i], Hd, Hd, S.Xoa, S.ld_oa, K0, B, c.qf[i].g + c.qf[i].oW0, c.qf[i].g + c.qf[i].ob0, 0, ad[i]);
+      b.dw(S.d0v, Hd, Hd, S.Xoa, S.ld_oa, O, B, V.g + V.oW0, V.g + V.ob0, 0, av);
+      for (int i = 0; i < 2; ++i) b.dw(S.dq[i], 1, 1, S.h1q[i], Hd, Hd, B, c.qf[i].g + c.qf[i].oW2, c.qf[i].g + c.qf[i].ob2, 0, ad[i]);
+      b.dw(S.dv, 1, 1, S.h1v, Hd, Hd, B, V.g + V.oW2, V.g + V.ob2, 0, av);
+    }
+}
   b.phase();   // policy loss re-evaluates the UPDATED critics on the SAME action sample (:150-153)
   for (int i = 0; i < 2; ++i) b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0n[i], Hd, ACT_RELU);
   b.phase();
@@ -498,6 +598,18 @@ inline void build_sac_v(Builder& b, const Ctx& c) {
   b.phase(); b.row(ROW_SAC_PIBWD_DA, B);
   b.phase();
   b.dx(S.d1p, Hd, B, Hd, P.p + P.oW1, Hd, Hd, h0p_obs, Hd, ACT_RELU, S.d0p, Hd);
+  if (tc5) {
+    b.phase();
+    b.dw_splits = Builder::pick_splits(Builder::tc5_tiles(Hd, Hd) + Builder::tc5_tiles(Hd, O) + (A > 8 ? 2 * Builder::tc5_tiles(A, Hd) : 0), B, kMaxKSplits);
+    b.dw(S.d1p, Hd, Hd, h0p_obs, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1, 0, -1, &P);
+    b.dw(S.d0p, Hd, Hd, obs_rows, S.ld_o, O, B, P.g + P.oW0, P.g + P.ob0, 0, -1, &P);
+    b.dw(S.dmean, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2, 0, -1, &P);
+    b.dw(S.dlraw, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW3, P.g + P.ob3, 0, -1, &P);
+    b.phase(COND_ALWAYS, 1);
+    b.adam(P, nullptr, c.hp.policy_lr, b1, b2, eps, 0.f, SLOT_POLICY, 1);
+    b.row(ROW_SACV_FINAL, 1);
+    return;
+  }
   b.phase(COND_WORLD_1);
   {
     const int ad = b.adam_desc(P, nullptr, c.hp.policy_lr, b1, b2, eps, 0.f, SLOT_POLICY);
@@ -611,12 +723,20 @@ inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem, bool use_tc5 =
   c.phase_ns = mem.take<unsigned long long>(2 * (kMaxPhases + 1));
   c.cta_ns = mem.take<unsigned long long>((size_t)kMaxPhases * kMaxGrid);
   alloc_sac_bufs(mem, c.s, cfg.algo, B, O, A, Hd);
-  auto grad = [&](const ilsw_mlp& n) { return mem.f(mlp_num_params(n.in_dim, n.hidden, n.out_dim, n.log_std_head)); };
-  c.policy = make_mlp(sp.nets[0], grad(sp.nets[0]));
-  c.qf[0] = make_mlp(sp.nets[1], grad(sp.nets[1]));
-  c.qf[1] = make_mlp(sp.nets[2], grad(sp.nets[2]));
+  // tcgen05 programs: kMaxKSplits partial gradient arenas per trainable net (split-K weight gradients; the scratch is
+  // zero-filled once, and elements no split GEMM produces stay zero in the arenas s >= 1)
+  const int nsplit = use_tc5 ? kMaxKSplits : 1;
+  auto grad = [&](const ilsw_mlp& n) { return mem.f((size_t)nsplit * round_up(mlp_num_params(n.in_dim, n.hidden, n.out_dim, n.log_std_head), 4)); };
+  auto mk = [&](const ilsw_mlp& n) {
+    MlpPtrs m = make_mlp(n, grad(n));
+    m.g_splits = nsplit; m.g_stride = round_up(m.n_params, 4);
+    return m;
+  };
+  c.policy = mk(sp.nets[0]);
+  c.qf[0] = mk(sp.nets[1]);
+  c.qf[1] = mk(sp.nets[2]);
   if (cfg.algo == ILSW_ALGO_SAC_V) {
-    c.vf = make_mlp(sp.nets[3], grad(sp.nets[3]));
+    c.vf = mk(sp.nets[3]);
     c.tvf = make_mlp(sp.nets[4], nullptr);
   } else {
     c.tqf[0] = make_mlp(sp.nets[3], nullptr);
@@ -625,7 +745,7 @@ inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem, bool use_tc5 =
   if (cfg.algo == ILSW_ALGO_TD3) c.tpolicy = make_mlp(sp.nets[5], nullptr);
   if (sp.has_disc) {
     alloc_disc_bufs(mem, c.d, B, sp.dcfg.state_only ? 2 * O : O + A, sp.disc.hidden);
-    c.disc = make_mlp(sp.disc, grad(sp.disc));
+    c.disc = mk(sp.disc);
   }
   if (use_tc5) {
     MlpPtrs* nets[] = {&c.policy, &c.qf[0], &c.qf[1], &c.tqf[0], &c.tqf[1], &c.tpolicy, &c.vf, &c.tvf};
@@ -662,7 +782,7 @@ inline std::string describe_program(const Program& P) {
   static const char* kinds[] = {"?", "GEMM", "ADAM", "ROW", "POLYAK"};
   for (int i = 0; i < P.n_phases; ++i) {
     const Phase& ph = P.phases[i];
-    snprintf(line, sizeof(line), "phase %2d jobs=%4d%s%s%s%s%s:", i, ph.total_jobs, (ph.cond & COND_TD3_POLICY) ? " [td3-policy-step]" : "",
+    snprintf(line, sizeof(line), "phase %2d jobs=%4d%s%s%s%s%s:", i, ph.total_jobs, (ph.cond & COND_TD3_POLICY) ? " [td3-policy-step]" : ((ph.cond & COND_TD3_POLICY_OR_STATS) ? " [td3-policy-or-stats-step]" : ""),
              (ph.cond & COND_FIRST_STEP) ? " [first-step]" : "", (ph.cond & COND_WORLD_1) ? " [1-replica]" : "",
              (ph.cond & COND_WORLD_N) ? " [n-replicas]" : "", ph.collective ? " [replica-exchange]" : "");
     out += line;

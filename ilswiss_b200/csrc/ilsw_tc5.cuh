@@ -180,14 +180,21 @@ __device__ __forceinline__ void teardown(Sync& sy) {
 
 // One 128 x BN output tile of GEMM `og` (tiles_m = ceil(M/128), tiles_n = ceil(N/BN)).  Returns false when a pipeline
 // wait timed out (the engine then aborts the launch).
+// Weight-gradient GEMMs (K = batch) can be split along K over `ksplit` tiles: split ks writes its partial tile to
+// C + ks * split_stride (bias_out likewise) and the flat Adam job sums the partial gradient arenas in a fixed order.
+// The optimiser is never fused into this tile: 128 x 64 outputs on 256 threads would serialise 32 Adam updates per thread
+// on the few CTAs that own a weight-gradient tile, the flat Adam phase spreads them over the whole grid.
 template <int BN>
-__device__ __noinline__ bool gemm_tile(const GemmOp& og, int tile, unsigned char* smem, Sync& sy, State& st, const AdamOp* ad, const AdamCoef* cf) {
+__device__ __noinline__ bool gemm_tile(const GemmOp& og, int tile, unsigned char* smem, Sync& sy, State& st) {
   using G = Geom<BN>;
   const GemmOp o = og;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tm = tile / o.tiles_n, tn = tile - tm * o.tiles_n;
+  const int per_split = o.tiles_m * o.tiles_n;
+  const int ks = tile / per_split, t2 = tile - ks * per_split;
+  const int tm = t2 / o.tiles_n, tn = t2 - tm * o.tiles_n;
   const int m0 = tm * kBM, n0 = tn * BN;
-  const int nkb = (o.K + kBK - 1) / kBK;
+  const int nkb_all = (o.K + kBK - 1) / kBK, nsplit = o.ksplit > 1 ? o.ksplit : 1;
+  const int kb_first = (ks * nkb_all) / nsplit, nkb = ((ks + 1) * nkb_all) / nsplit - kb_first;
   const bool do_aug = o.aug_ones && tn == 0;
   const uint32_t sb = smem_u32(smem);
   const uint32_t it0 = st.it;
@@ -198,7 +205,7 @@ __device__ __noinline__ bool gemm_tile(const GemmOp& og, int tile, unsigned char
       const uint32_t it = it0 + kb, s = it % kStages, ph = (it / kStages) & 1u;
       if (!mbar_wait(&sy.empty[s], ph ^ 1u)) { ok = false; break; }
       const uint32_t a_raw = sb + s * G::kStageBytes, b_raw = a_raw + 2 * G::kABytes;
-      const int k0 = kb * kBK;
+      const int k0 = (kb_first + kb) * kBK;
       if (elect_one()) {
         mbar_arrive_expect_tx(&sy.full_raw[s], G::kABytes + G::kBBytes);
         if (!o.a_mc) tma_load_2d(a_raw, o.tmapA, k0, m0, &sy.full_raw[s]);
@@ -232,7 +239,7 @@ __device__ __noinline__ bool gemm_tile(const GemmOp& og, int tile, unsigned char
       const uint32_t a_raw = sb + s * G::kStageBytes, a_lo = a_raw + G::kABytes, b_raw = a_raw + 2 * G::kABytes, b_lo = b_raw + G::kBBytes;
       const uint64_t da_hi = smem_desc(a_raw, a_lbo, a_sbo, a_lt), da_lo = smem_desc(a_lo, a_lbo, a_sbo, a_lt);
       const uint64_t db_hi = smem_desc(b_raw, b_lbo, b_sbo, b_lt), db_lo = smem_desc(b_lo, b_lbo, b_sbo, b_lt);
-      const int ksteps = min(kBK / 8, (o.K - kb * kBK + 7) >> 3);
+      const int ksteps = min(kBK / 8, (o.K - (kb_first + kb) * kBK + 7) >> 3);
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < kBK / 8; ++kk) {
@@ -296,79 +303,92 @@ __device__ __noinline__ bool gemm_tile(const GemmOp& og, int tile, unsigned char
   if (tid == 128) TC5_STAMP(3, 0);
   if (!mbar_wait(&sy.acc_full, st.ntile & 1u)) ok = false;
   if (tid == 128) TC5_STAMP(3, 1);
-  ok = __syncthreads_and(ok);
-  if (tid == 128) TC5_STAMP(3, 2);              // also: every TMA box has been consumed -> the stage area is free for the transpose
+  ok = __syncthreads_and(ok);              // also: every TMA box has been consumed -> the stage area is free for the staging tile
   if (!ok) return false;
   tc_fence_after();
+  // TMEM -> registers (thread = row, 32 columns) -> shared staging tile T[128][BN + 4] (16-byte rows, conflict-free both
+  // ways) -> row-coalesced, 128-bit global traffic: thread (rb = tid / 16, cg = tid % 16) owns columns 4 cg .. 4 cg + 3 of
+  // rows rb, rb + 16, ...  The epilogue kind is decided ONCE per tile (the per-element generic epilogue of the 32 x 32
+  // tiles costs ~40 dependent instructions per element: 0.8 us per 4 rows with 2 warps per scheduler).
+  constexpr int kTLd = BN + 4;
+  float* T = reinterpret_cast<float*>(smem);
   {
     const int q = warp & 3, half = warp >> 2;
-    float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 33);
-#pragma unroll 1
-    for (int cb = half * (BN / 2); cb < (half + 1) * (BN / 2); cb += 32) {
-      if (n0 + cb >= o.N) break;           // warp-uniform
-      uint32_t v[32];
-      tmem_ld32(sy.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
-      tmem_wait_ld();
-      if (tid == 128) TC5_STAMP(3, 3);
-      __syncwarp();
+    static_assert(BN == 64, "two 32-column halves per lane quarter");
+    uint32_t v[32];
+    tmem_ld32(sy.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32), v);
+    tmem_wait_ld();
+    float* trow = T + (q * 32 + lane) * kTLd + half * 32;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(v[j]);
-      __syncwarp();
-      if (tid == 128) TC5_STAMP(3, 6);
-      const int n = n0 + cb + lane;
-      const bool nok = n < o.N;
-      constexpr int U = 4;
-#pragma unroll 1
-      for (int r0 = 0; r0 < 32; r0 += U) {
-        float val[U]; EpiIn ein[U]; bool live[U];
-        int gi[U]; float am[U], av[U], ap[U], at[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int m = m0 + q * 32 + r0 + u;
-          live[u] = nok && m < o.M;
-          val[u] = tr[(r0 + u) * 33 + lane];
-          if (live[u]) {
-            ein[u] = epi_load(o, m, n);
-            if (ad) {
-              gi[u] = gemm_grad_index(o, *ad, m, n);
-              am[u] = __ldcg(ad->m + gi[u]); av[u] = __ldcg(ad->v + gi[u]); ap[u] = __ldcg(ad->p + gi[u]);
-              at[u] = ad->target ? __ldcg(ad->target + gi[u]) : 0.f;
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int m = m0 + q * 32 + r0 + u;
-          if (live[u]) {
-            if (ad) {
-              const float gv = o.accumulate ? val[u] + ein[u].prev : val[u];
-              o.C[(size_t)m * o.ldc + n] = gv;
-              adam_math_store(*ad, *cf, gi[u], gv, am[u], av[u], ap[u], at[u]);
-            } else {
-              epi_store(o, m, n, val[u], ein[u]);
-            }
-          }
-        }
-        if (tid == 128) TC5_STAMP(3, 7 + (r0 >> 2));
-      }
-    }
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(trow + 4 * j) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
     if (do_aug && half == 0) {             // bias gradient: column BN of the accumulator (all 16 spare columns are equal)
       const float bsum = __uint_as_float(tmem_ld1(sy.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)BN));
       tmem_wait_ld();
       const int m = m0 + q * 32 + lane;
-      if (m < o.M) {
-        const EpiIn e = epi_load(o, m, o.N);
-        epi_store(o, m, o.N, bsum, e);
-        if (ad) adam_elem_g(*ad, *cf, gemm_grad_index(o, *ad, m, o.N), o.accumulate ? bsum + e.prev : bsum);
+      if (m < o.M) o.bias_out[(size_t)ks * o.split_stride + m] = bsum;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 128) TC5_STAMP(3, 2);
+  {
+    const int cg = tid & 15, rb = tid >> 4;
+    const int n = n0 + 4 * cg;
+    float* Cb = o.C + (size_t)ks * o.split_stride;
+    const bool vec_c = ((o.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0) && (n + 3 < o.N);
+    const bool vec_h = o.mask != ACT_NONE && ((o.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(o.H) & 15) == 0) && (n + 3 < o.N);
+    float b4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (o.bias) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (n + j < o.N) b4[j] = __ldcg(o.bias + n + j);
+    }
+    if (n < o.N) {
+      constexpr int R = kBM / 16;          // 8 rows per thread
+      float h[R][4];
+      if (o.mask != ACT_NONE) {            // all mask loads in flight before the first store
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const int m = m0 + i * 16 + rb;
+          if (m < o.M) {
+            const float* hp = o.H + (size_t)m * o.ldh + n;
+            if (vec_h) { const float4 t4 = __ldcg(reinterpret_cast<const float4*>(hp)); h[i][0] = t4.x; h[i][1] = t4.y; h[i][2] = t4.z; h[i][3] = t4.w; }
+            else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) h[i][j] = (n + j < o.N) ? __ldcg(hp + j) : 0.f;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int row = i * 16 + rb, m = m0 + row;
+        if (m < o.M) {
+          const float4 a4 = *reinterpret_cast<const float4*>(T + row * kTLd + 4 * cg);
+          float a[4] = {a4.x + b4[0], a4.y + b4[1], a4.z + b4[2], a4.w + b4[3]};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (o.act == ACT_RELU) a[j] = fmaxf(a[j], 0.f);
+            else if (o.act == ACT_TANH) a[j] = tanhf(a[j]);
+            if (o.mask == ACT_RELU) a[j] = h[i][j] > 0.f ? a[j] : 0.f;
+            else if (o.mask == ACT_TANH) a[j] *= (1.0f - h[i][j] * h[i][j]);
+          }
+          float* cp = Cb + (size_t)m * o.ldc + n;
+          if (vec_c) *reinterpret_cast<float4*>(cp) = make_float4(a[0], a[1], a[2], a[3]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (n + j < o.N) cp[j] = a[j];
+          }
+        }
       }
     }
   }
   if (tid == 128) TC5_STAMP(3, 4);
   st.it = it0 + nkb;
   st.ntile += 1;
-  tc_fence_before();
-  __syncthreads();
-  if (tid == 128) TC5_STAMP(3, 5);                         // TMEM and the stage area are reused by the next job
+  __syncthreads();                         // the staging tile is read before the next job's TMA boxes land in it
+  if (tid == 128) TC5_STAMP(3, 5);
   return true;
 }
 

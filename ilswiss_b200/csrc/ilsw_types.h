@@ -27,6 +27,7 @@ constexpr int kLossSlots = 16;    // floats per step in the loss log
 constexpr int kThreads = 256;     // CTA size of the engine kernel
 constexpr int kRowsPerJob = 8;    // one warp per batch row
 constexpr int kAdamChunk = 2048;  // elements per flat Adam/Polyak job
+constexpr int kMaxGradSplits = 4;  // split-K partial gradient arenas summed by the flat Adam jobs (adam_grad)
 constexpr int kTc5BN = 64;        // column width of the tcgen05 tile (ilsw_tc5.cuh is instantiated with it; rows: 128)
 
 enum OpKind : int { OP_GEMM = 1, OP_ADAM = 2, OP_ROW = 3, OP_POLYAK = 4, OP_SHADOW = 5 };
@@ -36,7 +37,9 @@ enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 // phase conditions (bit mask: every set condition must hold)
 enum Cond : int { COND_ALWAYS = 0, COND_TD3_POLICY = 1, COND_FIRST_STEP = 2, COND_WORLD_1 = 4, COND_WORLD_N = 8,
                   COND_DISC_PART = 16,      // phase of the discriminator update (D1); skipped by policy-only launches
-                  COND_POLICY_PART = 32 };  // phase of the policy update (D2 + S1) of an AdvIRL program; skipped by disc-only launches
+                  COND_POLICY_PART = 32,    // phase of the policy update (D2 + S1) of an AdvIRL program; skipped by disc-only launches
+                  COND_TD3_POLICY_OR_STATS = 64 };   // TD3 policy steps AND the statistics step of a launch: td3.py:131-136 evaluates a
+                                                     // stats-only policy loss when the logged step is not a policy step
 // AdvIRL launches (adv_irl.py:126-131): one engine step = one disc update + one policy update (UPDATE_BOTH, the
 // num_*_updates_per_loop_iter = 1 case of every shipped yaml but one), or n disc-only / n policy-only steps
 enum UpdateMode : int { UPDATE_BOTH = 0, UPDATE_DISC_ONLY = 1, UPDATE_POLICY_ONLY = 2 };
@@ -70,6 +73,8 @@ struct GemmOp {
                         // weight-gradient phase needs no separate optimiser phase (valid only without accumulate
                         // partners and without a cross-replica exchange)
   int tc5;              // 1: 128 x 64 tcgen05/TMA tile (ilsw_tc5.cuh); tiles_m/tiles_n then count those tiles
+  int ksplit;           // tcgen05 weight-gradient GEMMs: number of K splits (jobs = ksplit * tiles_m * tiles_n); split s writes
+  int split_stride;     //   its partial sums to C + s * split_stride / bias_out + s * split_stride (floats); 0 / 1: no split
   const void* tmapA;    // device CUtensorMap of the A / B operand (SWIZZLE_128B boxes, see ilsw_tc5.cuh)
   const void* tmapB;
 };
@@ -92,6 +97,8 @@ struct AdamOp {
   int grad_scale_world; // 1: divide g by world size (replica-averaged policy gradient)
   int begin;            // first element of the flat job range [begin, n)
   int fused_only;       // 1: descriptor for GEMM epilogues (GemmOp::adam); owns no jobs
+  int g_splits;         // > 1: the gradient is the sum of g_splits partial arenas g + s * g_split_stride (split-K GEMMs)
+  int g_split_stride;
 };
 
 struct PolyakOp { float* target; const float* src; int n; float tau; ShadowRef sh_t; };
@@ -129,6 +136,7 @@ struct MlpPtrs {        // canonical 2-hidden-layer layout inside one flat arena
   int in_dim, hid, out_dim, heads;          // heads=2: extra log-std head (policy)
   int n_params;
   float* w0p; int ld_w0p;                   // aligned copy of W0 (tcgen05 programs, in_dim % 4 != 0), else nullptr
+  int g_splits, g_stride;                   // split-K partial gradient arenas g + s * g_stride, s < g_splits (0 / 1: one arena)
   // element offsets
   int oW0, ob0, oW1, ob1, oW2, ob2, oW3, ob3;
 };

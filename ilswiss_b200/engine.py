@@ -274,6 +274,10 @@ class StepEngine:
     def set_state(self, st):
         check(self.lib.ilsw_set_state(self.h, C.byref(st), _stream_ptr()), "set_state")
 
+    def uses_tc5(self):
+        """True when the dense GEMM phases of this program run on the tcgen05/TMA tile (batch >= 512)."""
+        return bool(self.lib.ilsw_trainer_uses_tc5(self.h))
+
     def describe(self):
         buf = C.create_string_buffer(1 << 15)
         check(self.lib.ilsw_describe_program(self.h, buf, len(buf)), "describe_program")

@@ -446,11 +446,9 @@ class TD3(_FusedTrainer):
         st = OrderedDict()
         st["QF1 Loss"] = float(L[_abi.L_QF1])
         st["QF2 Loss"] = float(L[_abi.L_QF2])
-        # on non-policy steps the reference evaluates a stats-only policy loss (td3.py:131-136);
-        # the engine reports the loss of the most recent policy update instead
-        pl = float(L[_abi.L_POLICY])
-        self._last_policy_loss = pl if not np.isnan(pl) else getattr(self, "_last_policy_loss", float("nan"))
-        st["Policy Loss"] = self._last_policy_loss
+        # on non-policy steps the reference evaluates a stats-only policy loss (td3.py:131-136): the step program runs the
+        # policy / Q1 forward passes on the statistics step of a launch too (COND_TD3_POLICY_OR_STATS)
+        st["Policy Loss"] = float(L[_abi.L_POLICY])
         st.update(_stats("Q1 Predictions", vec[0:B]))
         st.update(_stats("Q2 Predictions", vec[B:2 * B]))
         st.update(_stats("Q Targets", vec[2 * B:3 * B]))

@@ -249,6 +249,7 @@ int ilsw_trainer_set_profiling(ilsw_trainer* tr, int on);
 /* profiling on: jobs-done time (ns) of every CTA in every phase of the last step: out[96][304] */
 int ilsw_read_cta_ns(ilsw_trainer* tr, unsigned long long* host_out, void* stream);
 int64_t ilsw_kernel_launches(const ilsw_trainer* tr);   /* engine launches so far */
+int ilsw_trainer_uses_tc5(const ilsw_trainer* tr);      /* 1: the program runs its dense GEMM phases on the tcgen05/TMA tile (batch >= 512) */
 
 /* A1: sampler-side policy inference for <= 4096 env rows (policies.py:245-246, core.py:74-89).
  * obs_dev [n,O] -> act_dev [n,A]; deterministic: tanh(mean) (SAC) / no noise (TD3). */

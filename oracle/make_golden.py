@@ -307,6 +307,8 @@ def run_oracle(case):
             row.update({"QF1 Loss": s["qf1_loss"], "QF2 Loss": s["qf2_loss"]})
             if s["policy_loss"] is not None:
                 row["Policy Loss"] = s["policy_loss"]
+            if "stats_policy_loss" in s:
+                row["Stats Policy Loss"] = s["stats_policy_loss"]     # td3.py:131-136 (what the epoch log shows)
             row.update({"Q1 Predictions Mean": float(s["q1_pred"].mean()),
                         "Q Targets Mean": float(s["q_target"].mean())})
         rows.append(row)

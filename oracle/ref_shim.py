@@ -10,8 +10,9 @@ Why a shim is needed:
   * rlkit/torch/algorithms/torch_base_algorithm.py:24 uses `torch` without
     importing it (NameError on import) -> we inject builtins.torch.
 
-/root/reference does NOT exist on the GPU box: only oracle/make_golden.py and
-the `-m "not gpu"` validation tests (skipped when the directory is absent) use it.
+/root/reference does NOT exist on the GPU box: oracle/make_golden.py and the `-m "not gpu"` validation
+tests use it here; on the GPU box the same unmodified sources are importable from baseline/_ref (pip
+--target install, see _find_root) for bench.py's reference arm and the drop-in loop tests.
 """
 import builtins
 import os
@@ -21,7 +22,23 @@ import types
 import numpy as np
 import torch
 
-REFERENCE_ROOT = os.environ.get("ILSWISS_REFERENCE_ROOT", "/root/reference")
+# Where the unmodified reference lives: the read-only checkout of the build container, or -- on the GPU boxes, where that
+# does not exist -- the pip --target install of the same sources under baseline/_ref (git-ignored, ships with the lease;
+# installed from a /tmp copy with a 3-line setup.py because the reference has no packaging metadata).
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    env = os.environ.get("ILSWISS_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "rlkit")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
@@ -135,3 +152,70 @@ def import_reference():
     ptu.device = torch.device("cpu")
     ns = types.SimpleNamespace(**{k: v for k, v in locals().items() if k != "ns"})
     return ns
+
+
+def time_reference(w, steps, warmup, threads):
+    """bench.py's reference arm: the reference's OWN classes (SimpleReplayBuffer.random_batch -> np_to_pytorch_batch ->
+    trainer.train_step; AdvIRL._do_reward_training + _do_policy_training for GAIL) on the host cores, on the synthetic
+    workload `w` of bench.WORKLOADS.  Returns (gradient steps / s, seconds)."""
+    import time
+
+    from oracle import restate as R
+
+    ref = import_reference()
+    torch.set_num_threads(threads)
+    O, A, B = w["O"], w["A"], w["B"]
+    H = w.get("H", 256)
+    n = min(w["N"], 1_000_000)
+    env = FakeEnv(O, A)
+    torch.manual_seed(0)
+    qf1 = ref.FlattenMlp(hidden_sizes=[H, H], input_size=O + A, output_size=1)
+    qf2 = ref.FlattenMlp(hidden_sizes=[H, H], input_size=O + A, output_size=1)
+
+    def fill(buf, m, seed, term_p):
+        d = R.synth_transitions(m, O, A, seed, term_p)
+        buf._observations[:m] = d["observations"]; buf._actions[:m] = d["actions"]; buf._rewards[:m] = d["rewards"]
+        buf._terminals[:m] = d["terminals"]; buf._next_obs[:m] = d["next_observations"]
+        buf._top, buf._size = m % buf._max_replay_buffer_size, m
+
+    buf = ref.SimpleReplayBuffer(n, O, A, random_seed=1)
+    fill(buf, n, 7, 0.0 if w["algo"] == "gail" else 0.01)
+    if w["algo"] == "td3" and w.get("her"):
+        raise RuntimeError("the HER workload is timed with the oracle port")
+    if w["algo"] == "td3":
+        policy = ref.MlpGaussianNoisePolicy(hidden_sizes=[H, H], obs_dim=O, action_dim=A, policy_noise=0.2, policy_noise_clip=0.5,
+                                            output_activation=torch.tanh)
+        trainer = ref.TD3(policy=policy, qf1=qf1, qf2=qf2, reward_scale=1.0, discount=0.99, policy_lr=3e-4, qf_lr=3e-4,
+                          policy_and_target_update_period=2, tau=0.005)
+    else:
+        policy = ref.ReparamTanhMultivariateGaussianPolicy(hidden_sizes=[H, H], obs_dim=O, action_dim=A)
+        kw = dict(policy=policy, qf1=qf1, qf2=qf2, env=env, reward_scale=w["reward_scale"], discount=0.99, policy_lr=3e-4, qf_lr=3e-4,
+                  alpha_lr=3e-4, soft_target_tau=0.005, alpha=0.2, train_alpha=True, policy_mean_reg_weight=1e-3,
+                  policy_std_reg_weight=1e-3, beta_1=w["beta_1"])
+        if w["target_entropy"] is not None:
+            kw["target_entropy"] = w["target_entropy"]
+        trainer = ref.SacAlpha(**kw)
+    alg = None
+    if w["algo"] == "gail":
+        ebuf = ref.SimpleReplayBuffer(n, O, A, random_seed=3)
+        fill(ebuf, w["NE"], 8, 0.0)
+        disc = ref.MLPDisc(O + A, num_layer_blocks=2, hid_dim=128, hid_act="tanh", use_bn=False, clamp_magnitude=10.0)
+        alg = ref.AdvIRL(mode="gail2", discriminator=disc, policy_trainer=trainer, expert_replay_buffer=ebuf, state_only=False,
+                         disc_optim_batch_size=B, policy_optim_batch_size=B, policy_optim_batch_size_from_expert=0,
+                         num_update_loops_per_train_call=1, num_disc_updates_per_loop_iter=1, num_policy_updates_per_loop_iter=1,
+                         disc_lr=3e-4, disc_momentum=0.9, use_grad_pen=True, grad_pen_weight=8.0, env=env, training_env=None,
+                         exploration_policy=policy, replay_buffer=buf, max_path_length=1000, no_terminal=True)
+
+    def one():
+        if alg is not None:
+            alg._do_training(0)       # adv_irl.py:126-131: one reward update + one policy update
+        else:
+            trainer.train_step(ref.np_to_pytorch_batch(buf.random_batch(B)))     # torch_rl_algorithm.py:28-34
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return steps / dt, dt

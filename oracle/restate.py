@@ -631,9 +631,16 @@ class TD3Oracle:
             polyak(self.policy, self.target_policy, self.tau)  # td3.py:180-183
             polyak(self.qf1, self.target_qf1, self.tau)
             polyak(self.qf2, self.target_qf2, self.tau)
+        # td3.py:126-136: when statistics are collected on a step without a policy update, the reference evaluates the
+        # policy loss once more, for logging only (updated critics, unchanged policy)
+        stats_pl = policy_loss
+        if stats_pl is None:
+            with torch.no_grad():
+                w1n = [t.detach() for t in self.qf1.p.values()]
+                stats_pl = -q_forward(w1n, obs, td3_policy_forward([t.detach() for t in wp], obs, None)).mean()
         self.n_total += 1
         return dict(qf1_loss=float(qf1_loss), qf2_loss=float(qf2_loss),
-                    policy_loss=None if policy_loss is None else float(policy_loss),
+                    policy_loss=None if policy_loss is None else float(policy_loss), stats_policy_loss=float(stats_pl),
                     q1_pred=q1_pred.detach().numpy().ravel(), q_target=q_target.numpy().ravel())
 
 

@@ -477,15 +477,20 @@ def test_algorithm_mixins_drive_one_launch_per_train_call():
     assert b["observations"].is_cuda and b["observations"].shape == (B, O) and b["rewards"].shape == (B, 1)
     assert "QF1 Loss" in alg.trainer.get_eval_statistics()
     # the reference gives batch_size to the ALGORITHM, not the trainer: a trainer built with the default batch adopts it
-    # on first use (ensure_batch) and refuses to change once it has trained
+    # on first use (ensure_batch)
     tr_default = SoftActorCritic(modules.TanhGaussianPolicy([256, 256], O, A), modules.FlattenMlp([256, 256], 1, O + A),
                                  modules.FlattenMlp([256, 256], 1, O + A))
     assert tr_default._cfg.batch == 256
     alg2 = Alg(tr_default, mk_buf(1))
     alg2._do_training(0)
     assert tr_default._cfg.batch == B and tr_default.engine.get_state().n_train_steps_total == 37
-    with pytest.raises(ValueError):
-        tr_default.ensure_batch(2 * B)
+    # a later batch-size change rebuilds the step program and CARRIES the optimiser state (resume path: load_snapshot,
+    # then the algorithm's batch size on the first _do_training -- ADVICE r1)
+    st0 = tr_default.engine.get_state()
+    tr_default.ensure_batch(2 * B)
+    st1 = tr_default.engine.get_state()
+    assert tr_default._cfg.batch == 2 * B and st1.n_train_steps_total == 37 and list(st1.adam_step) == list(st0.adam_step)
+    assert st1.log_alpha == st0.log_alpha and st1.alpha_exp_avg == st0.alpha_exp_avg and st1.alpha_step == st0.alpha_step
     tr_step = SoftActorCritic(modules.TanhGaussianPolicy([256, 256], O, A), modules.FlattenMlp([256, 256], 1, O + A),
                               modules.FlattenMlp([256, 256], 1, O + A))
     tr_step.train_step(alg.get_batch())                # Trainer.train_step(batch) with a 64-row batch

@@ -97,6 +97,24 @@ def test_td3_delay_across_launches(lib):
     a.close(); b.close()
 
 
+def test_td3_stats_only_policy_loss(lib):
+    """td3.py:126-136: when the logged step is not a policy step the reference evaluates -mean(Q1(obs, pi(obs))) for the
+    log only.  The step program runs its policy / Q1 forward phases on the statistics step of a launch as well."""
+    torch.set_num_threads(1)
+    case = CFG.CASES["td3_hopper"]
+    rows, _, _ = G.run_oracle(case)
+    inj = case_injection(case)
+    for t in (1, 2, 3):                     # odd steps have no policy update (period 2, starting at step 0)
+        run = HostSimRun(lib, case)
+        L = run.train(case["steps"], inj, stats_step=t)
+        ref = rows[t]["Stats Policy Loss"]
+        assert abs(L[t, STAT_TO_SLOT["Policy Loss"]] - ref) <= 1e-4 * max(abs(ref), 1.0), (t, L[t, STAT_TO_SLOT["Policy Loss"]], ref)
+        for u in range(case["steps"]):      # every other non-policy step logs no policy loss
+            if u != t and u % 2 == 1:
+                assert np.isnan(L[u, STAT_TO_SLOT["Policy Loss"]])
+        run.close()
+
+
 def test_program_shape(lib):
     import ctypes as C
     run = HostSimRun(lib, CFG.CASES["gail_walker"])

@@ -1,0 +1,20 @@
+#!/bin/bash
+# development job for one gpurun call: tile check, GPU tests, phase profiles.  Usage: tools/gpu_job.sh <tag> [steps...]
+TAG=$1; shift
+mkdir -p gpurun_out
+for step in "$@"; do
+  case $step in
+    tc5) timeout 200 ./tools/tc5_test > gpurun_out/${TAG}_tc5.txt 2>&1; echo "rc=$?" >> gpurun_out/${TAG}_tc5.txt ;;
+    tests) timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_tests.log 2>&1; echo "rc=$?" >> gpurun_out/${TAG}_tests.log ;;
+    tests_all) timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_tests.log 2>&1; echo "rc=$?" >> gpurun_out/${TAG}_tests.log ;;
+    pp_td3) timeout 300 python tools/phase_profile.py td3_humanoid > gpurun_out/${TAG}_pp_td3.txt 2>&1 ;;
+    pp_her) timeout 300 python tools/phase_profile.py her_td3_pick > gpurun_out/${TAG}_pp_her.txt 2>&1 ;;
+    pp_sac) timeout 300 python tools/phase_profile.py sac_hopper > gpurun_out/${TAG}_pp_sac.txt 2>&1 ;;
+    pp_gail) timeout 300 python tools/phase_profile.py gail_walker > gpurun_out/${TAG}_pp_gail.txt 2>&1 ;;
+    pp_ant) timeout 300 python tools/phase_profile.py sac_ant > gpurun_out/${TAG}_pp_ant.txt 2>&1 ;;
+    bench) timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
+    benchlong) timeout 600 python bench.py > gpurun_out/${TAG}_benchlong.json 2> gpurun_out/${TAG}_benchlong.err ;;
+    *) echo "unknown step $step" ;;
+  esac
+done
+for f in gpurun_out/${TAG}_*; do echo "== $f"; tail -c 1500 $f; echo; done

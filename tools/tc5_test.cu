@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256, 1) tc5_kernel(GemmOp o, int ntiles, int* 
     int nt = 0;
     if (stamp) stamps[7] = gtime();
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      if (!tc5::gemm_tile<BN>(o, tile, smem, sy, st, nullptr, nullptr)) { if (threadIdx.x == 0) atomicExch(fail, 1); good = false; break; }
+      if (!tc5::gemm_tile<BN>(o, tile, smem, sy, st)) { if (threadIdx.x == 0) atomicExch(fail, 1); good = false; break; }
       if (stamp && nt < 4) stamps[2 + nt] = gtime();
       ++nt;
     }
@@ -44,16 +44,18 @@ __global__ void __launch_bounds__(256, 1) tc5_kernel(GemmOp o, int ntiles, int* 
 
 static float frand() { return (float)rand() / (float)RAND_MAX * 2.f - 1.f; }
 
-struct Case { const char* name; int M, N, K, a_mc, b_nc, aug, act, mask, bias; };
+struct Case { const char* name; int M, N, K, a_mc, b_nc, aug, act, mask, bias, ksplit; };
 
 static double run_case(const Case& c, bool timing) {
   const int M = c.M, N = c.N, K = c.K;
   // leading dimensions: multiples of 4 floats
   const int lda = c.a_mc ? (M + 3) / 4 * 4 : (K + 3) / 4 * 4;
   const int ldb = c.b_nc ? (N + 3) / 4 * 4 : (K + 3) / 4 * 4;
-  const int ldc = (N + 3) / 4 * 4;
-  const size_t nA = (size_t)(c.a_mc ? K : M) * lda, nB = (size_t)(c.b_nc ? K : N) * ldb, nC = (size_t)M * ldc;
+  const int ldc = strstr(c.name, "unaligned") ? N : (N + 3) / 4 * 4;   // packed rows exercise the scalar store path
+  const int S = c.ksplit > 1 ? c.ksplit : 1;
+  const size_t nA = (size_t)(c.a_mc ? K : M) * lda, nB = (size_t)(c.b_nc ? K : N) * ldb, nC1 = (size_t)M * ldc + M, nC = nC1 * S;
   std::vector<float> hA(nA), hB(nB), hH(nC), hbias(N), hC(nC, -777.f), hbo(M, -777.f);
+  // split-K layout: partial s of C at dC + s * nC1, of bias_out at dC + s * nC1 + M * ldc
   for (auto& v : hA) v = frand();
   for (auto& v : hB) v = frand();
   for (auto& v : hH) v = frand();
@@ -72,10 +74,11 @@ static double run_case(const Case& c, bool timing) {
   CK(cudaMalloc(&dm, sizeof(hm))); CK(cudaMemcpy(dm, hm, sizeof(hm), cudaMemcpyHostToDevice));
   GemmOp o; memset(&o, 0, sizeof(o));
   o.A = dA; o.lda = lda; o.a_mc = c.a_mc; o.B = dB; o.ldb = ldb; o.b_nc = c.b_nc; o.M = M; o.N = N; o.K = K;
-  o.aug_ones = c.aug; o.C = dC; o.ldc = ldc; o.bias_out = c.aug ? dbo : nullptr; o.bias = c.bias ? dbias : nullptr;
+  o.aug_ones = c.aug; o.C = dC; o.ldc = ldc; o.bias_out = c.aug ? (S > 1 ? dC + (size_t)M * ldc : dbo) : nullptr; o.bias = c.bias ? dbias : nullptr;
+  o.ksplit = S; o.split_stride = (int)nC1;
   o.H = c.mask ? dH : nullptr; o.ldh = ldc; o.act = c.act; o.mask = c.mask;
   o.tiles_m = (M + 127) / 128; o.tiles_n = (N + BN - 1) / BN; o.tc5 = 1; o.tmapA = dm; o.tmapB = dm + 1;
-  const int ntiles = o.tiles_m * o.tiles_n;
+  const int ntiles = S * o.tiles_m * o.tiles_n;
   const size_t smem = tc5::Geom<BN>::kSmemBytes + 1024;
   CK(cudaFuncSetAttribute(tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = ntiles < 148 ? ntiles : 148;
@@ -85,6 +88,10 @@ static double run_case(const Case& c, bool timing) {
   int fail = 0; CK(cudaMemcpy(&fail, dfail, 4, cudaMemcpyDeviceToHost));
   if (fail) { printf("%s: PIPELINE TIMEOUT\n", c.name); return 1.0; }
   CK(cudaMemcpy(hC.data(), dC, nC * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hbo.data(), dbo, M * 4, cudaMemcpyDeviceToHost));
+  if (S > 1) {     // sum the partial arenas in split order (what the flat Adam job does)
+    for (size_t i = 0; i < nC1; ++i) { float a = hC[i]; for (int sp = 1; sp < S; ++sp) a += hC[sp * nC1 + i]; hC[i] = a; }
+    for (int m = 0; m < M; ++m) hbo[m] = hC[(size_t)M * ldc + m];
+  }
   double worst = 0; int nbad = 0;
   for (int m = 0; m < M; ++m) {
     for (int n = 0; n < N; ++n) {
@@ -111,7 +118,7 @@ static double run_case(const Case& c, bool timing) {
     }
   }
   // untouched padding columns stay untouched
-  for (int m = 0; m < M; ++m) for (int n = N; n < ldc; ++n) if (hC[(size_t)m * ldc + n] != -777.f) { printf("%s: wrote padding\n", c.name); worst = 1.0; m = M; break; }
+  for (int m = 0; m < M; ++m) for (int n = N; n < ldc; ++n) if (S == 1 && hC[(size_t)m * ldc + n] != -777.f) { printf("%s: wrote padding\n", c.name); worst = 1.0; m = M; break; }
   double us = 0;
   if (timing) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -132,7 +139,7 @@ static double run_case(const Case& c, bool timing) {
     printf(" us");
     unsigned long long ht[4][16]; CK(cudaMemcpyFromSymbol(ht, tc5::g_tc5_t, sizeof(ht)));
     const unsigned long long t0 = hs[7];
-    const char* names[4] = {"producer", "mma(wait,commit)", "splitter(w2: landed,arrived)", "epilogue(start,acc_full,sync,ld,done,end,transposed,8 x row groups)"};
+    const char* names[4] = {"producer", "mma(wait,commit)", "splitter(w2: landed,arrived)", "epilogue(start,acc_full,staged,-,done,end)"};
     for (int r = 0; r < 4; ++r) { printf("\n      %s:", names[r]); for (int i = 0; i < 16; ++i) if (ht[r][i] >= t0) printf(" %.2f", (ht[r][i] - t0) * 1e-3); }
   }
   cudaFree(dst);
@@ -146,14 +153,16 @@ int main() {
   printf("device %s, %d SMs, tile 128x%d, %d stages, %d B shared\n", p.name, p.multiProcessorCount, BN, tc5::kStages, tc5::Geom<BN>::kSmemBytes);
   srand(1);
   const Case cases[] = {
-      {"fwd small", 128, 64, 32, 0, 0, 0, ACT_NONE, ACT_NONE, 0},
-      {"fwd bias+relu", 1024, 256, 393, 0, 0, 0, ACT_RELU, ACT_NONE, 1},
-      {"dx relu-mask", 1024, 256, 256, 0, 1, 0, ACT_NONE, ACT_RELU, 0},
-      {"dw +bias-grad", 256, 393, 1024, 1, 1, 1, ACT_NONE, ACT_NONE, 0},
-      {"dw K=4096 (HER)", 300, 300, 4096, 1, 1, 1, ACT_NONE, ACT_NONE, 0},
-      {"fwd ragged", 300, 300, 100, 0, 0, 0, ACT_RELU, ACT_NONE, 1},
-      {"dx ragged", 1000, 300, 300, 0, 1, 0, ACT_NONE, ACT_RELU, 0},
-      {"dw ragged", 300, 28, 1000, 1, 1, 1, ACT_NONE, ACT_NONE, 0},
+      {"fwd small", 128, 64, 32, 0, 0, 0, ACT_NONE, ACT_NONE, 0, 1},
+      {"fwd bias+relu", 1024, 256, 393, 0, 0, 0, ACT_RELU, ACT_NONE, 1, 1},
+      {"dx relu-mask", 1024, 256, 256, 0, 1, 0, ACT_NONE, ACT_RELU, 0, 1},
+      {"dw +bias-grad", 256, 393, 1024, 1, 1, 1, ACT_NONE, ACT_NONE, 0, 1},
+      {"dw +bias-grad split-K 3", 256, 393, 1024, 1, 1, 1, ACT_NONE, ACT_NONE, 0, 3},
+      {"dw K=4096 (HER) split-K 4", 300, 300, 4096, 1, 1, 1, ACT_NONE, ACT_NONE, 0, 4},
+      {"fwd ragged", 300, 300, 100, 0, 0, 0, ACT_RELU, ACT_NONE, 1, 1},
+      {"dx ragged", 1000, 300, 300, 0, 1, 0, ACT_NONE, ACT_RELU, 0, 1},
+      {"dw ragged", 300, 28, 1000, 1, 1, 1, ACT_NONE, ACT_NONE, 0, 1},
+      {"fwd unaligned ldc (N=393)", 256, 393, 256, 0, 0, 0, ACT_NONE, ACT_NONE, 1, 1},
   };
   double worst = 0;
   for (const Case& c : cases) {
