@@ -126,6 +126,12 @@ struct TileLoader {
 
 __device__ __forceinline__ void tile_load_A(const GemmOp& o, int m0, int k0, float* r, bool fast) {
   const int tid = threadIdx.x;
+  if (o.a0_X) {   // fused first layer (GemmOp::a0_X): produced element by element in the exact mode
+    const int m = m0 + (tid >> 3), k = k0 + ((tid & 7) << 2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = (m < o.M && k + i < o.K) ? gemm_A_fused(o, m, k + i) : 0.f;
+    return;
+  }
   if (!o.a_mc) {  // k contiguous: thread -> (m = tid/8, k = (tid%8)*4 .. +3)
     int m = m0 + (tid >> 3), k = k0 + ((tid & 7) << 2);
     if (m < o.M && fast && k + 3 < o.K) {
@@ -208,7 +214,7 @@ __device__ __forceinline__ void tile_store_B(const GemmOp& o, float* Bs, const f
 
 // fused optimiser step on gradient element gi (value g) -- the tile epilogues' Adam(+Polyak)
 __device__ __forceinline__ void adam_fused_elem(const AdamOp& ad, const AdamCoef& cf, int gi, float g) {
-  adam_elem_g(ad, cf, gi, g);
+  adam_elem_g(ad, cf, gi, g, adam_has_shadow(ad));
 }
 
 __device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* smem, const AdamOp* ad, const AdamCoef* cf) {
@@ -293,6 +299,12 @@ __device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* 
     const EpiIn e = epi_load(o, mm, o.N);
     epi_store(o, mm, o.N, ssum, e);
     if (ad) adam_fused_elem(*ad, *cf, gemm_grad_index(o, *ad, mm, o.N), o.accumulate ? ssum + e.prev : ssum);
+  }
+  if (o.a0_X && tn == 0) {     // materialise the fused first layer of this row block (backward pass)
+    for (int e = tid; e < kTM * o.K; e += kThreads) {
+      const int r = e / o.K, k = e - r * o.K;
+      if (m0 + r < o.M) o.a0_out[(size_t)(m0 + r) * o.a0_ldo + k] = gemm_A_fused(o, m0 + r, k);
+    }
   }
   __syncthreads();
 }
@@ -447,7 +459,7 @@ __device__ __noinline__ void tc_fill_stage(const GemmOp& o, float* stage, int m0
   const int tid = threadIdx.x;
   const int kpad = (klen + 15) & ~15;    // zero padded to TWO MMA k-steps (the k loop is unrolled by 2, unguarded)
 #pragma unroll 1
-  for (int op = 0; op < 2; ++op) {
+  for (int op = o.a0_X ? 1 : 0; op < 2; ++op) {      // a fused first layer produces its own A panel (tc_produce_l0)
     const bool isB = op != 0;
     const bool contig_k = isB ? !o.b_nc : !o.a_mc;
     const float* base = isB ? o.B : o.A;
@@ -505,6 +517,60 @@ __device__ __noinline__ void tc_fill_stage(const GemmOp& o, float* stage, int m0
         r += rq; k += kq;
         if (contig_k && k >= kpad) { k -= kpad; r += 1; }
       }
+    }
+  }
+}
+
+// Fused first layer (GemmOp::a0_X): the k-contiguous A panel [32 rows][kKS] of one stage is PRODUCED here instead of
+// copied: W0^T and the 32 input rows are staged in `scratch` (the idle second stage buffer: K <= KC), thread k owns
+// column k of the panel for all 32 rows (fp32 FMA chain over the K0 <= 32 inputs, bias first -- the order of
+// gemm_A_fused), applies the activation, writes the panel and, in the tn == 0 tile, the activations for the backward pass.
+template <int KC>
+__device__ __noinline__ void tc_produce_l0(const GemmOp& og, float* panel, float* scratch, int m0, int k0, int klen, bool store_out) {
+  constexpr int kKS = TcGeom<KC>::kKS;
+  static_assert(kThreads >= KC, "one thread per panel column");
+  const GemmOp o = og;
+  const int tid = threadIdx.x, K0 = o.a0_K;
+  float* Wt = scratch;                       // [K0][KC]: Wt[j*KC + k] = W0[(k0+k)*K0 + j]
+  float* Xs = scratch + kFuseL0MaxK * KC;    // [K0][32]: Xs[j*32 + r] = X[(m0+r)*ldx + j]
+  float bk = 0.f;
+  if (tid < klen) {
+    const float* w = o.a0_W + (size_t)(k0 + tid) * K0;
+    bk = __ldcg(o.a0_b + k0 + tid);
+    float wr[kFuseL0MaxK];
+#pragma unroll
+    for (int j = 0; j < kFuseL0MaxK; ++j) wr[j] = j < K0 ? __ldcg(w + j) : 0.f;
+#pragma unroll
+    for (int j = 0; j < kFuseL0MaxK; ++j) if (j < K0) Wt[j * KC + tid] = wr[j];
+  }
+  for (int e = tid; e < 32 * K0; e += kThreads) {
+    const int r = e / K0, j = e - r * K0;
+    Xs[j * 32 + r] = (m0 + r < o.M) ? __ldcg(o.a0_X + (size_t)(m0 + r) * o.a0_ldx + j) : 0.f;
+  }
+  __syncthreads();
+  const int kpad = (klen + 15) & ~15;
+  if (tid < kpad) {
+    float acc[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) acc[r] = bk;
+    if (tid < klen) {
+#pragma unroll 2
+      for (int j = 0; j < K0; ++j) {
+        const float w = Wt[j * KC + tid];
+        const float4* xr = reinterpret_cast<const float4*>(Xs + j * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 x = xr[q];
+          acc[4 * q] = fmaf(x.x, w, acc[4 * q]); acc[4 * q + 1] = fmaf(x.y, w, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(x.z, w, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(x.w, w, acc[4 * q + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const float v = tid < klen ? act_apply(acc[r], o.a0_act) : 0.f;     // zero padding up to two MMA k-steps
+      panel[r * kKS + tid] = v;
+      if (store_out && tid < klen && m0 + r < o.M) o.a0_out[(size_t)(m0 + r) * o.a0_ldo + k0 + tid] = v;
     }
   }
 }
@@ -598,6 +664,19 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
       const int k0 = (st + 1) * kKC;
       tc_fill_stage<KC>(og, smem + ((st + 1) & 1) * kTcStageFloats, m0, n0, k0, min(kKC, o.K - k0), vecA, vecB);
       cp_async_commit();
+      if (o.a0_X) {      // the B panel is in flight; produce the A panel meanwhile (single-stage GEMMs: the other stage buffer is scratch)
+        if (nstages == 1) tc_produce_l0<KC>(og, smem + ((st + 1) & 1) * kTcStageFloats, smem + (st & 1) * kTcStageFloats, m0, k0, min(kKC, o.K - k0), tn == 0);
+        else {
+          float* panel = smem + ((st + 1) & 1) * kTcStageFloats;
+          const int klen = min(kKC, o.K - k0), kpad = (klen + 15) & ~15;
+          for (int e = tid; e < 32 * kpad; e += kThreads) {
+            const int r = e / kpad, k = e - r * kpad;
+            const float v = (m0 + r < o.M && k < klen) ? gemm_A_fused(o, m0 + r, k0 + k) : 0.f;
+            panel[r * kKS + k] = v;
+            if (tn == 0 && m0 + r < o.M && k < klen) o.a0_out[(size_t)(m0 + r) * o.a0_ldo + k0 + k] = v;
+          }
+        }
+      }
     }
     if (st < 0) {
 #if !ILSW_EIN_FIRST
@@ -681,6 +760,7 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
   }
   ILSW_TSTAMP(3);
   const float outv[4] = {sum.x, sum.y, sum.z, sum.w};
+  const bool ad_sh = ad && adam_has_shadow(*ad);      // aligned W0 copies to maintain (tcgen05 programs only)
 #if !ILSW_ADAM_PREFETCH
   int gi[4] = {-1, -1, -1, -1}, gib = -1;
   float am[4], av[4], ap[4], at[4], bm = 0.f, bv = 0.f, bp = 0.f, bt = 0.f;
@@ -693,7 +773,7 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
       if (gi[i] >= 0) {
         const float gv = o.accumulate ? outv[i] + ein[i].prev : outv[i];
         o.C[(size_t)er * o.ldc + ec + i] = gv;
-        adam_math_store(*ad, *cf, gi[i], gv, am[i], av[i], ap[i], at[i]);
+        adam_math_store(*ad, *cf, gi[i], gv, am[i], av[i], ap[i], at[i], ad_sh);
       }
   } else {
 #pragma unroll
@@ -706,7 +786,7 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
     for (int w = 0; w < 8; ++w) bsum += smem[kRedFloats + w * 32 + tid];
     const EpiIn e = epi_load(o, m0 + tid, o.N);
     epi_store(o, m0 + tid, o.N, bsum, e);
-    if (ad) adam_math_store(*ad, *cf, gib, o.accumulate ? bsum + e.prev : bsum, bm, bv, bp, bt);
+    if (ad) adam_math_store(*ad, *cf, gib, o.accumulate ? bsum + e.prev : bsum, bm, bv, bp, bt, ad_sh);
   }
   __syncthreads();     // the partial tiles are read before the next job's panels overwrite them
   ILSW_TSTAMP(4);
@@ -719,16 +799,8 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
 // for these shapes costs a full tile (5 us); this is ~1.5 us.
 // Split along K (tcgen05 programs, K = batch >= 512): job (ks, tile) sums k in [ks * K / S, (ks + 1) * K / S) into the
 // partial gradient arena ks (C + ks * split_stride); one CTA walking K = 1024 alone took 23 us.
-__device__ __noinline__ void gemm_tile_skinny(const GemmOp& og, int tile_in, float* smem, const AdamOp* ad, const AdamCoef* cf) {
-  GemmOp o = og;
-  const int nsplit = o.ksplit > 1 ? o.ksplit : 1;
-  const int ks = tile_in / o.tiles_n, tile = tile_in - ks * o.tiles_n;
-  const int kbeg = (int)(((long long)ks * o.K) / nsplit), kend = (int)(((long long)(ks + 1) * o.K) / nsplit);
-  if (nsplit > 1) {
-    o.A += (size_t)kbeg * o.lda; o.B += (size_t)kbeg * o.ldb; o.K = kend - kbeg;
-    o.C += (size_t)ks * o.split_stride;
-    if (o.bias_out) o.bias_out += (size_t)ks * o.split_stride;
-  }
+__device__ __noinline__ void gemm_tile_skinny(const GemmOp& og, int tile, float* smem, const AdamOp* ad, const AdamCoef* cf) {
+  const GemmOp o = og;
   const int tid = threadIdx.x, col = tid & 31, kg = tid >> 5;
   const int n = tile * 32 + col;
   const int M = o.M;
@@ -786,6 +858,22 @@ __device__ __noinline__ void gemm_tile_skinny(const GemmOp& og, int tile_in, flo
     }
   }
   __syncthreads();
+}
+// split form (tcgen05 programs only): a shifted copy of the descriptor per K range, then the same tile
+__device__ __noinline__ void gemm_tile_skinny_split(const GemmOp& og, int tile_in, float* smem) {
+  __shared__ GemmOp s_split;
+  const int nsplit = og.ksplit, ks = tile_in / og.tiles_n, tile = tile_in - ks * og.tiles_n;
+  const int kbeg = (ks * og.K) / nsplit, kend = ((ks + 1) * og.K) / nsplit;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    GemmOp o = og;
+    o.A += (size_t)kbeg * o.lda; o.B += (size_t)kbeg * o.ldb; o.K = kend - kbeg;
+    o.C += (size_t)ks * o.split_stride;
+    if (o.bias_out) o.bias_out += (size_t)ks * o.split_stride;
+    s_split = o;
+  }
+  __syncthreads();
+  gemm_tile_skinny(s_split, tile, smem, nullptr, nullptr);
 }
 ILSW_HD bool gemm_is_skinny(const GemmOp& o) { return o.M <= 8 && o.a_mc && o.b_nc && o.tiles_m == 1; }
 
@@ -870,10 +958,11 @@ __device__ __noinline__ void adam_job(const AdamOp& ao, const AdamCoef& cfs, int
       tg[u] = ao.target ? ao.target[i] : 0.f;
     }
   }
+  const bool sh = adam_has_shadow(ao);
 #pragma unroll
   for (int u = 0; u < E; ++u) {
     const int i = beg + threadIdx.x + u * kThreads;
-    if (i < end) adam_math_store(ao, cf, i, g[u], m[u], v[u], p[u], tg[u]);
+    if (i < end) adam_math_store(ao, cf, i, g[u], m[u], v[u], p[u], tg[u], sh);
   }
 }
 
@@ -897,9 +986,18 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
   const int n_phases = prog->n_phases, n_ops = prog->n_ops;
   constexpr int KC = CTAS == 2 ? 128 : 256;
   unsigned char* pbase = dyn_smem + engine_staging_bytes(CTAS, TC5);
-  unsigned char* tc5_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
-  tc5::State tc5_state{0u, 0u};
-  if (TC5) tc5::setup<kTc5BN>(s_tc5, tc5_smem);
+  // tcgen05 variant only (the B = 256 variant keeps its loop state minimal: everything live across a grid barrier that
+  // does not fit the register file is reloaded from local memory through L2 -- the barrier's acquire invalidates L1)
+  [[maybe_unused]] unsigned char* tc5_smem = nullptr;
+  [[maybe_unused]] tc5::State tc5_state{0u, 0u};
+  if constexpr (TC5) {
+    tc5_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
+    tc5::setup<kTc5BN>(s_tc5, tc5_smem);
+  }
+// a failed barrier / exchange / tile wait ends the launch for every thread of the CTA (uniform); the tcgen05 variant leaves
+// through the common exit because tensor memory must be released before the CTA retires
+#define ILSW_ALIVE (!TC5 || alive)
+#define ILSW_DIE() { if constexpr (TC5) { alive = false; break; } else { return; } }
   Phase* s_phases = reinterpret_cast<Phase*>(pbase);
   Op* s_ops = reinterpret_cast<Op*>(pbase + align16(sizeof(Phase) * kMaxPhases));
   Ctx* s_ctx = reinterpret_cast<Ctx*>(reinterpret_cast<unsigned char*>(s_ops) + align16(sizeof(Op) * (size_t)n_ops));
@@ -934,10 +1032,8 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
   const int prec = c.hp.gemm_precision;
   const bool fast_rows = fast_rows_ok(c);
 
-  // a failed barrier / exchange / tile wait ends the launch for every thread of the CTA (uniform), through the common exit:
-  // tensor memory must be released before the CTA retires
-  bool alive = true;
-  for (int s = 0; s < a.n_steps && alive; ++s) {
+  [[maybe_unused]] bool alive = true;
+  for (int s = 0; s < a.n_steps && ILSW_ALIVE; ++s) {
     const bool stamp = (s == a.n_steps - 1) && blockIdx.x == 0 && threadIdx.x == 0;
     if (stamp) c.phase_ns[0] = globaltimer_ns();
     if (threadIdx.x < kMaxNets && s_pt[threadIdx.x] >= 0) {
@@ -946,14 +1042,14 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
       s_coefs[threadIdx.x] = adam_coef_pw(s_ops[s_adam_op[threadIdx.x]].adam, s_p1[threadIdx.x], s_p2[threadIdx.x], 1);
     }
     __syncthreads();
-    for (int ph = 0; ph < n_phases && alive; ++ph) {
+    for (int ph = 0; ph < n_phases && ILSW_ALIVE; ++ph) {
       const Phase& P = s_phases[ph];
       if (!phase_active(P, c.hp, a, s)) { if (stamp) c.phase_ns[ph + 1] = c.phase_ns[ph]; continue; }
       const bool exchange = P.collective && rp.world > 1;
       // exchange sequence number = number of policy updates so far (parity double-buffers the slots)
       const unsigned xseq = rp.seq0 + (unsigned)(adam_t(a, c.hp, SLOT_POLICY, s) - a.t0[SLOT_POLICY]);
-      if (exchange && !replica_exchange(rp, xseq, bar, gen, abort_flag)) { alive = false; break; }
-      for (int job = blockIdx.x; job < P.total_jobs && alive; job += gridDim.x) {
+      if (exchange && !replica_exchange(rp, xseq, bar, gen, abort_flag)) ILSW_DIE()
+      for (int job = blockIdx.x; job < P.total_jobs && ILSW_ALIVE; job += gridDim.x) {
         int j = job, oi = P.op_begin;
         while (j >= s_ops[oi].n_jobs) { j -= s_ops[oi].n_jobs; ++oi; }
         const Op& o = s_ops[oi];
@@ -961,11 +1057,14 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
           const AdamOp* ad = o.gemm.adam ? &s_ops[o.gemm.adam - 1].adam : nullptr;
           const AdamCoef* cf = ad ? &s_coefs[ad->slot] : nullptr;
           if (TC5 && o.gemm.tc5) {
-            if (!tc5::gemm_tile<kTc5BN>(o.gemm, j, tc5_smem, s_tc5, tc5_state)) {
-              if (threadIdx.x == 0) atomicExch(abort_flag, 1);     // the other CTAs leave their barrier wait
-              alive = false;
+            if constexpr (TC5) {
+              if (!tc5::gemm_tile<kTc5BN>(o.gemm, j, tc5_smem, s_tc5, tc5_state)) {
+                if (threadIdx.x == 0) atomicExch(abort_flag, 1);     // the other CTAs leave their barrier wait
+                alive = false;
+              }
             }
-          } else if (gemm_is_skinny(o.gemm)) gemm_tile_skinny(o.gemm, j, smem, ad, cf);
+          } else if (TC5 && gemm_is_skinny(o.gemm) && o.gemm.ksplit > 1) gemm_tile_skinny_split(o.gemm, j, smem);
+          else if (gemm_is_skinny(o.gemm)) gemm_tile_skinny(o.gemm, j, smem, ad, cf);
           else if (prec == 0) gemm_tile_device(o.gemm, j, smem, ad, cf);
           else gemm_tile_tc<KC>(o.gemm, j, smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, ad, cf);
         } else if (o.kind == OP_ROW) {
@@ -1002,14 +1101,16 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
           for (int i = beg + threadIdx.x; i < end; i += kThreads) shadow_refresh_elem(o.shadow, i);
         }
       }
-      if (!alive) break;
+      if constexpr (TC5) { if (!alive) break; }
       if (stamp) c.phase_ns[kMaxPhases + 1 + ph] = globaltimer_ns();
       if (a.profile && s == a.n_steps - 1 && threadIdx.x == 0 && blockIdx.x < kMaxGrid) c.cta_ns[ph * kMaxGrid + blockIdx.x] = globaltimer_ns();
-      if (!grid_barrier(bar, gridDim.x, gen, abort_flag)) { alive = false; break; }
+      if (!grid_barrier(bar, gridDim.x, gen, abort_flag)) ILSW_DIE()
       if (stamp) c.phase_ns[ph + 1] = globaltimer_ns();
     }
   }
-  if (TC5) tc5::teardown<kTc5BN>(s_tc5);
+  if constexpr (TC5) tc5::teardown<kTc5BN>(s_tc5);
+#undef ILSW_ALIVE
+#undef ILSW_DIE
 }
 
 // ------------------------------------------------------------------------------------------

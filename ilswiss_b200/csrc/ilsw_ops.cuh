@@ -121,7 +121,21 @@ ILSW_HD float round_bf16(float x) {   // cvt.rn.bf16.f32
 
 // GEMM operand accessors + epilogue (shared by the device tile kernel and the host simulator)
 // ------------------------------------------------------------------------------------------
+ILSW_HD float act_apply(float v, int act) {
+  if (act == ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == ACT_TANH) return tanhf(v);
+  return v;
+}
+// element (m,k) of a fused first layer (GemmOp::a0_X): fp32 FMA chain in input order
+ILSW_HD float gemm_A_fused(const GemmOp& o, int m, int k) {
+  float acc = ldg(o.a0_b + k);
+  const float* x = o.a0_X + (size_t)m * o.a0_ldx;
+  const float* w = o.a0_W + (size_t)k * o.a0_K;
+  for (int j = 0; j < o.a0_K; ++j) acc = fmaf(ldg(x + j), ldg(w + j), acc);
+  return act_apply(acc, o.a0_act);
+}
 ILSW_HD float gemm_A(const GemmOp& o, int m, int k) {
+  if (o.a0_X) return gemm_A_fused(o, m, k);
   return ldg(o.A + (o.a_mc ? (size_t)k * o.lda + m : (size_t)m * o.lda + k));
 }
 ILSW_HD float gemm_B(const GemmOp& o, int k, int n) {
@@ -219,7 +233,8 @@ ILSW_HD AdamCoef adam_coef(const AdamOp& o, int t, int world) {
 #define ILSW_DIV(a, b) ((a) / (b))
 #define ILSW_SQRT(a) sqrtf(a)
 #endif
-ILSW_HD void adam_math_store(const AdamOp& o, const AdamCoef& c, int i, float g, float m, float v, float p, float tg) {
+// sh: false when the caller has checked once (per tile / job) that the optimiser has no aligned W0 copies to maintain
+ILSW_HD void adam_math_store(const AdamOp& o, const AdamCoef& c, int i, float g, float m, float v, float p, float tg, bool sh = true) {
   // exp_avg.lerp_(grad, 1-beta1)
   const float d = ILSW_SUB(g, m);
   m = (c.w1 < 0.5f) ? ILSW_FMA(c.w1, d, m) : ILSW_SUB(g, ILSW_MUL(d, c.one_m_w1));
@@ -230,15 +245,16 @@ ILSW_HD void adam_math_store(const AdamOp& o, const AdamCoef& c, int i, float g,
   o.m[i] = m;
   o.v[i] = v;
   o.p[i] = p;
-  shadow_store(o.sh_p, i, p);
+  if (sh) shadow_store(o.sh_p, i, p);
   if (o.target) {
     const float tn = ILSW_FMA(tg, c.one_m_tau, ILSW_MUL(p, c.tau));
     o.target[i] = tn;
-    shadow_store(o.sh_t, i, tn);
+    if (sh) shadow_store(o.sh_t, i, tn);
   }
 }
-ILSW_HD void adam_elem_g(const AdamOp& o, const AdamCoef& c, int i, float g) {
-  adam_math_store(o, c, i, g, o.m[i], o.v[i], o.p[i], o.target ? o.target[i] : 0.f);
+ILSW_HD bool adam_has_shadow(const AdamOp& o) { return o.sh_p.ptr != nullptr || o.sh_t.ptr != nullptr; }
+ILSW_HD void adam_elem_g(const AdamOp& o, const AdamCoef& c, int i, float g, bool sh = true) {
+  adam_math_store(o, c, i, g, o.m[i], o.v[i], o.p[i], o.target ? o.target[i] : 0.f, sh);
 }
 // gradient element i: the sum of the split-K partial arenas in a fixed order (one arena without splits)
 // All partial loads are issued before the first add (a runtime-trip-count loop of load + add serialises one L2 round

@@ -118,6 +118,45 @@ struct Builder {
     g.C = Y; g.ldc = ldy; g.bias = b; g.act = act;
     gemm(g);
   }
+  // Two layers in one phase: H0 = act0(X W0^T + b0) [M, hid] is produced inside the tiles of Y = act(H0 W1^T + b1)
+  // (GemmOp::a0_X) when the first layer's input is narrow; otherwise two phases.  H0 is materialised for the backward pass.
+  bool fuse_l0_ok(int K0, int hid) const {
+    return !P.ctx.hp.use_tc5 && K0 <= kFuseL0MaxK && hid <= 256 && P.ctx.s.B < 512;
+  }
+  void fwd2_fused(const float* X, int ldx, int M, int K0, const float* W0, const float* b0, int act0, int hid, float* H0,
+                  const float* W1, const float* b1, int N, float* Y, int ldy, int act) {
+    GemmOp g; memset(&g, 0, sizeof(g));
+    g.A = H0; g.lda = hid; g.a_mc = 0; g.B = W1; g.ldb = hid; g.b_nc = 0; g.M = M; g.N = N; g.K = hid;
+    g.C = Y; g.ldc = ldy; g.bias = b1; g.act = act;
+    g.a0_X = X; g.a0_ldx = ldx; g.a0_K = K0; g.a0_W = W0; g.a0_b = b0; g.a0_act = act0; g.a0_out = H0; g.a0_ldo = hid;
+    gemm(g);
+  }
+  // the first two layers of several networks, side by side: one fused phase when every first layer is narrow, else a
+  // phase of first layers followed by a phase of second layers.  Opens its own phase(s); the caller may add further
+  // ops to the last one.
+  struct TwoLayers { const float* X; int ldx, M, K0; const MlpPtrs* net; float* H0; float* H1; int act; };
+  void two_layers(const TwoLayers* L, int n, int cond = COND_ALWAYS) {
+    bool fz = true;
+    for (int i = 0; i < n; ++i) fz = fz && fuse_l0_ok(L[i].K0, L[i].net->hid);
+    phase(cond);
+    if (fz) {
+      for (int i = 0; i < n; ++i) {
+        const MlpPtrs& N = *L[i].net;
+        fwd2_fused(L[i].X, L[i].ldx, L[i].M, L[i].K0, N.p + N.oW0, N.p + N.ob0, L[i].act, N.hid, L[i].H0, N.p + N.oW1, N.p + N.ob1,
+                   N.hid, L[i].H1, N.hid, L[i].act);
+      }
+      return;
+    }
+    for (int i = 0; i < n; ++i) {
+      const MlpPtrs& N = *L[i].net;
+      fwd(L[i].X, L[i].ldx, L[i].M, L[i].K0, N.p + N.oW0, N.p + N.ob0, N.hid, L[i].H0, N.hid, L[i].act);
+    }
+    phase(cond);
+    for (int i = 0; i < n; ++i) {
+      const MlpPtrs& N = *L[i].net;
+      fwd(L[i].H0, N.hid, L[i].M, N.hid, N.p + N.oW1, N.p + N.ob1, N.hid, L[i].H1, N.hid, L[i].act);
+    }
+  }
   // dX[M,Nin] = (D[M,Kred] W[Kred, ldw(:Nin)]) (.) act'(Hm)      (backward through a Linear)
   void dx(const float* D, int ldd, int M, int Kred, const float* W, int ldw, int Nin, const float* Hm, int ldh,
           int mask, float* out, int ldo, float* raw = nullptr) {
@@ -269,8 +308,7 @@ inline void build_disc_step(Builder& b, const Ctx& c) {
   const float* h1i = D.h1 + (size_t)2 * B * Hd;
 
   b.phase(); b.row(ROW_DISC_GATHER, B);
-  b.phase(); b.fwd(D.X3, ld, R, Din, W1, b1, Hd, D.h1, Hd, ACT_TANH);
-  b.phase(); b.fwd(D.h1, Hd, R, Hd, W2, b2, Hd, D.h2, Hd, ACT_TANH);
+  { Builder::TwoLayers L[1] = {{D.X3, ld, R, Din, &N, D.h1, D.h2, ACT_TANH}}; b.two_layers(L, 1); }
   b.phase(); b.row(ROW_DISC_HEAD, R);
   b.phase();
   b.dx(D.d2, Hd, 2 * B, Hd, W2, Hd, Hd, D.h1, Hd, ACT_TANH, D.d1, Hd);          // CE: delta1
@@ -322,23 +360,43 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
   // the batch of step s+1 is gathered in the LAST phase of step s (independent of everything that
   // phase does); only the first step of a launch needs a gather phase of its own
   b.phase(COND_FIRST_STEP); b.row(ROW_SAC_GATHER, B);
+  // narrow first layers (Hopper / Walker: 14 .. 23 inputs) are folded into the tiles of the second layer (fwd2_fused)
+  const bool fz = b.fuse_l0_ok(K0, Hd) && (!disc || b.fuse_l0_ok(c.hp.state_only ? 2 * O : K0, c.d.Hd));
+  const float* dX = (disc && c.hp.state_only) ? c.d.Xsn : S.Xoa;
+  const int dld = (disc && c.hp.state_only) ? c.d.ld_sn : S.ld_oa, dK = (disc && c.hp.state_only) ? 2 * O : K0;
   b.phase();
-  for (int i = 0; i < 2; ++i) b.fwd(S.Xoa, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0q[i], Hd, ACT_RELU);
-  b.fwd(S.Xpi, S.ld_o, 2 * B, O, P.p + P.oW0, P.p + P.ob0, Hd, S.h0p, Hd, ACT_RELU);
-  if (disc && c.hp.state_only) b.fwd(c.d.Xsn, c.d.ld_sn, B, 2 * O, c.disc.p + c.disc.oW0, c.disc.p + c.disc.ob0, c.d.Hd, c.d.rh1, c.d.Hd, ACT_TANH);
-  else if (disc) b.fwd(S.Xoa, S.ld_oa, B, K0, c.disc.p + c.disc.oW0, c.disc.p + c.disc.ob0, c.d.Hd, c.d.rh1, c.d.Hd, ACT_TANH);
-  b.phase();
-  for (int i = 0; i < 2; ++i) b.fwd(S.h0q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1q[i], Hd, ACT_RELU);
-  b.fwd(S.h0p, Hd, 2 * B, Hd, P.p + P.oW1, P.p + P.ob1, Hd, S.h1p, Hd, ACT_RELU);
-  if (disc) b.fwd(c.d.rh1, c.d.Hd, B, c.d.Hd, c.disc.p + c.disc.oW1, c.disc.p + c.disc.ob1, c.d.Hd, c.d.rh2, c.d.Hd, ACT_TANH);
+  if (fz) {
+    for (int i = 0; i < 2; ++i)
+      b.fwd2_fused(S.Xoa, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, ACT_RELU, Hd, S.h0q[i],
+                   c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1q[i], Hd, ACT_RELU);
+    b.fwd2_fused(S.Xpi, S.ld_o, 2 * B, O, P.p + P.oW0, P.p + P.ob0, ACT_RELU, Hd, S.h0p, P.p + P.oW1, P.p + P.ob1, Hd, S.h1p, Hd, ACT_RELU);
+    if (disc)
+      b.fwd2_fused(dX, dld, B, dK, c.disc.p + c.disc.oW0, c.disc.p + c.disc.ob0, ACT_TANH, c.d.Hd, c.d.rh1,
+                   c.disc.p + c.disc.oW1, c.disc.p + c.disc.ob1, c.d.Hd, c.d.rh2, c.d.Hd, ACT_TANH);
+  } else {
+    for (int i = 0; i < 2; ++i) b.fwd(S.Xoa, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0q[i], Hd, ACT_RELU);
+    b.fwd(S.Xpi, S.ld_o, 2 * B, O, P.p + P.oW0, P.p + P.ob0, Hd, S.h0p, Hd, ACT_RELU);
+    if (disc) b.fwd(dX, dld, B, dK, c.disc.p + c.disc.oW0, c.disc.p + c.disc.ob0, c.d.Hd, c.d.rh1, c.d.Hd, ACT_TANH);
+    b.phase();
+    for (int i = 0; i < 2; ++i) b.fwd(S.h0q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1q[i], Hd, ACT_RELU);
+    b.fwd(S.h0p, Hd, 2 * B, Hd, P.p + P.oW1, P.p + P.ob1, Hd, S.h1p, Hd, ACT_RELU);
+    if (disc) b.fwd(c.d.rh1, c.d.Hd, B, c.d.Hd, c.disc.p + c.disc.oW1, c.disc.p + c.disc.ob1, c.d.Hd, c.d.rh2, c.d.Hd, ACT_TANH);
+  }
   b.phase();
   b.row(ROW_SAC_HEADS, 2 * B);
   if (disc) b.row(ROW_DISC_REWARD, B);
   b.phase();
-  for (int i = 0; i < 2; ++i) b.fwd(S.Xna, S.ld_oa, B, K0, c.tqf[i].p + c.tqf[i].oW0, c.tqf[i].p + c.tqf[i].ob0, Hd, S.h0t[i], Hd, ACT_RELU);
-  if (disc) b.row(ROW_DISC_REWARD_FINAL, 1);
-  b.phase();
-  for (int i = 0; i < 2; ++i) b.fwd(S.h0t[i], Hd, B, Hd, c.tqf[i].p + c.tqf[i].oW1, c.tqf[i].p + c.tqf[i].ob1, Hd, S.h1t[i], Hd, ACT_RELU);
+  if (fz) {
+    for (int i = 0; i < 2; ++i)
+      b.fwd2_fused(S.Xna, S.ld_oa, B, K0, c.tqf[i].p + c.tqf[i].oW0, c.tqf[i].p + c.tqf[i].ob0, ACT_RELU, Hd, S.h0t[i],
+                   c.tqf[i].p + c.tqf[i].oW1, c.tqf[i].p + c.tqf[i].ob1, Hd, S.h1t[i], Hd, ACT_RELU);
+    if (disc) b.row(ROW_DISC_REWARD_FINAL, 1);
+  } else {
+    for (int i = 0; i < 2; ++i) b.fwd(S.Xna, S.ld_oa, B, K0, c.tqf[i].p + c.tqf[i].oW0, c.tqf[i].p + c.tqf[i].ob0, Hd, S.h0t[i], Hd, ACT_RELU);
+    if (disc) b.row(ROW_DISC_REWARD_FINAL, 1);
+    b.phase();
+    for (int i = 0; i < 2; ++i) b.fwd(S.h0t[i], Hd, B, Hd, c.tqf[i].p + c.tqf[i].oW1, c.tqf[i].p + c.tqf[i].ob1, Hd, S.h1t[i], Hd, ACT_RELU);
+  }
   b.phase(); b.row(ROW_SAC_TARGET, B);
   const bool tc5 = c.hp.use_tc5 != 0;
   if (tc5) {
@@ -376,9 +434,15 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
     }
   }
   b.phase();
-  for (int i = 0; i < 2; ++i) b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0n[i], Hd, ACT_RELU);
-  b.phase();
-  for (int i = 0; i < 2; ++i) b.fwd(S.h0n[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1n[i], Hd, ACT_RELU);
+  if (fz) {
+    for (int i = 0; i < 2; ++i)
+      b.fwd2_fused(S.Xon, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, ACT_RELU, Hd, S.h0n[i],
+                   c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1n[i], Hd, ACT_RELU);
+  } else {
+    for (int i = 0; i < 2; ++i) b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0n[i], Hd, ACT_RELU);
+    b.phase();
+    for (int i = 0; i < 2; ++i) b.fwd(S.h0n[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1n[i], Hd, ACT_RELU);
+  }
   b.phase(); b.row(ROW_SAC_PLOSS, B);
   b.phase();
   for (int i = 0; i < 2; ++i) b.dx(S.e1[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0n[i], Hd, ACT_RELU, S.e0[i], Hd);
@@ -431,19 +495,20 @@ inline void build_td3(Builder& b, const Ctx& c) {
   const double b1 = 0.9, b2 = 0.999, eps = c.hp.adam_eps;   // optimizer defaults (td3.py:56-67)
 
   b.phase(); b.row(ROW_TD3_GATHER, B);
-  b.phase();
-  for (int i = 0; i < 2; ++i) b.fwd(S.Xoa, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0q[i], Hd, ACT_RELU);
   // HER-TD3 overwrites the target policy's action with clipped noise (her/td3.py:103-112): its forward pass is dead code
   const bool her = c.hp.her != 0;
-  if (!her) b.fwd(S.Xna, S.ld_oa, B, O, TP.p + TP.oW0, TP.p + TP.ob0, Hd, S.h0tp, Hd, ACT_RELU);
-  b.phase();
-  for (int i = 0; i < 2; ++i) b.fwd(S.h0q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1q[i], Hd, ACT_RELU);
-  if (!her) b.fwd(S.h0tp, Hd, B, Hd, TP.p + TP.oW1, TP.p + TP.ob1, Hd, S.h1tp, Hd, ACT_RELU);
+  {
+    Builder::TwoLayers L[3] = {{S.Xoa, S.ld_oa, B, K0, &c.qf[0], S.h0q[0], S.h1q[0], ACT_RELU},
+                               {S.Xoa, S.ld_oa, B, K0, &c.qf[1], S.h0q[1], S.h1q[1], ACT_RELU},
+                               {S.Xna, S.ld_oa, B, O, &TP, S.h0tp, S.h1tp, ACT_RELU}};
+    b.two_layers(L, her ? 2 : 3);
+  }
   b.phase(); b.row(ROW_TD3_THEAD, B);
-  b.phase();
-  for (int i = 0; i < 2; ++i) b.fwd(S.Xna, S.ld_oa, B, K0, c.tqf[i].p + c.tqf[i].oW0, c.tqf[i].p + c.tqf[i].ob0, Hd, S.h0t[i], Hd, ACT_RELU);
-  b.phase();
-  for (int i = 0; i < 2; ++i) b.fwd(S.h0t[i], Hd, B, Hd, c.tqf[i].p + c.tqf[i].oW1, c.tqf[i].p + c.tqf[i].ob1, Hd, S.h1t[i], Hd, ACT_RELU);
+  {
+    Builder::TwoLayers L[2] = {{S.Xna, S.ld_oa, B, K0, &c.tqf[0], S.h0t[0], S.h1t[0], ACT_RELU},
+                               {S.Xna, S.ld_oa, B, K0, &c.tqf[1], S.h0t[1], S.h1t[1], ACT_RELU}};
+    b.two_layers(L, 2);
+  }
   b.phase(); b.row(ROW_TD3_TARGET, B);
   const bool tc5 = c.hp.use_tc5 != 0;
   if (tc5) {        // see build_sac_alpha: split-K weight gradients, flat Adam jobs
@@ -481,11 +546,9 @@ inline void build_td3(Builder& b, const Ctx& c) {
   // the forward half also runs on the statistics step of a launch when that is not a policy step: the reference logs a
   // stats-only policy loss -mean(Q1(obs, pi(obs))) and its actions there (td3.py:131-136)
   const int PS = COND_TD3_POLICY_OR_STATS;
-  b.phase(PS); b.fwd(S.Xoa, S.ld_oa, B, O, P.p + P.oW0, P.p + P.ob0, Hd, S.h0p, Hd, ACT_RELU);
-  b.phase(PS); b.fwd(S.h0p, Hd, B, Hd, P.p + P.oW1, P.p + P.ob1, Hd, S.h1p, Hd, ACT_RELU);
+  { Builder::TwoLayers L[1] = {{S.Xoa, S.ld_oa, B, O, &P, S.h0p, S.h1p, ACT_RELU}}; b.two_layers(L, 1, PS); }
   b.phase(PS); b.row(ROW_TD3_PHEAD, B);
-  b.phase(PS); b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[0].p + c.qf[0].oW0, c.qf[0].p + c.qf[0].ob0, Hd, S.h0n[0], Hd, ACT_RELU);
-  b.phase(PS); b.fwd(S.h0n[0], Hd, B, Hd, c.qf[0].p + c.qf[0].oW1, c.qf[0].p + c.qf[0].ob1, Hd, S.h1n[0], Hd, ACT_RELU);
+  { Builder::TwoLayers L[1] = {{S.Xon, S.ld_oa, B, K0, &c.qf[0], S.h0n[0], S.h1n[0], ACT_RELU}}; b.two_layers(L, 1, PS); }
   b.phase(PS); b.row(ROW_TD3_PLOSS, B);
   // the policy loss of this step is complete: log it here (policy steps and the statistics step alike; on a stats-only
   // step the backward-data tile of this phase is dead work, once per epoch)
@@ -535,21 +598,20 @@ inline void build_sac_v(Builder& b, const Ctx& c) {
   float* h1p_obs = S.h1p + (size_t)B * Hd;
   const float* obs_rows = S.Xpi + (size_t)B * S.ld_o;
   b.phase(); b.row(ROW_SAC_GATHER, B);
-  b.phase();
-  for (int i = 0; i < 2; ++i) b.fwd(S.Xoa, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0q[i], Hd, ACT_RELU);
-  b.fwd(S.Xna, S.ld_oa, B, O, TV.p + TV.oW0, TV.p + TV.ob0, Hd, S.h0tv, Hd, ACT_RELU);
-  b.fwd(S.Xoa, S.ld_oa, B, O, V.p + V.oW0, V.p + V.ob0, Hd, S.h0v, Hd, ACT_RELU);
-  b.fwd(obs_rows, S.ld_o, B, O, P.p + P.oW0, P.p + P.ob0, Hd, h0p_obs, Hd, ACT_RELU);
-  b.phase();
-  for (int i = 0; i < 2; ++i) b.fwd(S.h0q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1q[i], Hd, ACT_RELU);
-  b.fwd(S.h0tv, Hd, B, Hd, TV.p + TV.oW1, TV.p + TV.ob1, Hd, S.h1tv, Hd, ACT_RELU);
-  b.fwd(S.h0v, Hd, B, Hd, V.p + V.oW1, V.p + V.ob1, Hd, S.h1v, Hd, ACT_RELU);
-  b.fwd(h0p_obs, Hd, B, Hd, P.p + P.oW1, P.p + P.ob1, Hd, h1p_obs, Hd, ACT_RELU);
+  {
+    Builder::TwoLayers L[5] = {{S.Xoa, S.ld_oa, B, K0, &c.qf[0], S.h0q[0], S.h1q[0], ACT_RELU},
+                               {S.Xoa, S.ld_oa, B, K0, &c.qf[1], S.h0q[1], S.h1q[1], ACT_RELU},
+                               {S.Xna, S.ld_oa, B, O, &TV, S.h0tv, S.h1tv, ACT_RELU},
+                               {S.Xoa, S.ld_oa, B, O, &V, S.h0v, S.h1v, ACT_RELU},
+                               {obs_rows, S.ld_o, B, O, &P, h0p_obs, h1p_obs, ACT_RELU}};
+    b.two_layers(L, 5);
+  }
   b.phase(); b.row(ROW_SAC_HEADS, B, 0, /*row_offset=*/B);          // one eps draw: a~, log pi on the obs rows
-  b.phase();   // min Q(obs, a~) with the PRE-update critics (V regression target, sac.py:121-129)
-  for (int i = 0; i < 2; ++i) b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0n[i], Hd, ACT_RELU);
-  b.phase();
-  for (int i = 0; i < 2; ++i) b.fwd(S.h0n[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1n[i], Hd, ACT_RELU);
+  {   // min Q(obs, a~) with the PRE-update critics (V regression target, sac.py:121-129)
+    Builder::TwoLayers L[2] = {{S.Xon, S.ld_oa, B, K0, &c.qf[0], S.h0n[0], S.h1n[0], ACT_RELU},
+                               {S.Xon, S.ld_oa, B, K0, &c.qf[1], S.h0n[1], S.h1n[1], ACT_RELU}};
+    b.two_layers(L, 2);
+  }
   b.phase(); b.row(ROW_SACV_TARGET, B);
   b.phase();
   for (int i = 0; i < 2; ++i)
@@ -588,10 +650,11 @@ inline void build_sac_v(Builder& b, const Ctx& c) {
       b.dw(S.dv, 1, 1, S.h1v, Hd, Hd, B, V.g + V.oW2, V.g + V.ob2, 0, av);
     }
 }
-  b.phase();   // policy loss re-evaluates the UPDATED critics on the SAME action sample (:150-153)
-  for (int i = 0; i < 2; ++i) b.fwd(S.Xon, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0n[i], Hd, ACT_RELU);
-  b.phase();
-  for (int i = 0; i < 2; ++i) b.fwd(S.h0n[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1n[i], Hd, ACT_RELU);
+  {   // policy loss re-evaluates the UPDATED critics on the SAME action sample (:150-153)
+    Builder::TwoLayers L[2] = {{S.Xon, S.ld_oa, B, K0, &c.qf[0], S.h0n[0], S.h1n[0], ACT_RELU},
+                               {S.Xon, S.ld_oa, B, K0, &c.qf[1], S.h0n[1], S.h1n[1], ACT_RELU}};
+    b.two_layers(L, 2);
+  }
   b.phase(); b.row(ROW_SAC_PLOSS, B);
   b.phase();
   for (int i = 0; i < 2; ++i) b.dx(S.e1[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, Hd, Hd, S.h0n[i], Hd, ACT_RELU, S.e0[i], Hd);

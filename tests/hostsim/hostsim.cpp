@@ -32,7 +32,12 @@ struct HostSim {
 static void run_op(HostSim* hs, const Program& P, const Op& o, const RunArgs& a, int s) {
   const Ctx& c = P.ctx;
   if (o.kind == OP_GEMM) {
-    const GemmOp& g = o.gemm;
+    GemmOp g = o.gemm;
+    if (g.a0_X) {        // fused first layer: materialise it (the device's tn == 0 tiles do), then read it as a plain operand
+      for (int m = 0; m < g.M; ++m)
+        for (int k = 0; k < g.K; ++k) g.a0_out[(size_t)m * g.a0_ldo + k] = gemm_A_fused(g, m, k);
+      g.A = g.a0_out; g.lda = g.a0_ldo; g.a_mc = 0; g.a0_X = nullptr;
+    }
     int Nt = g.N + g.aug_ones;
     const AdamOp* ad = g.adam ? &P.ops[g.adam - 1].adam : nullptr;     // fused optimiser epilogue
     AdamCoef acf;
