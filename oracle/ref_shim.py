@@ -85,6 +85,45 @@ class FakeGoalEnv:
 _installed = False
 
 
+def _install_gtimer(mod):
+    """Just enough of `gtimer` for BaseAlgorithm.start_training (base_algorithm.py:152-157,166-172,281-291,330-340):
+    timed_for(iterable, save_itrs), stamp(name), get_times().stamps.itrs[name][-1], get_times().total, reset(),
+    set_def_unique().  Per iteration of timed_for every stamp name gets one entry (the time since the previous stamp,
+    summed when a name is stamped more than once in the iteration)."""
+    import time as _time
+
+    state = types.SimpleNamespace(itrs={}, cur={}, last=_time.time(), start=_time.time())
+
+    def reset():
+        state.itrs, state.cur = {}, {}
+        state.last = state.start = _time.time()
+
+    def stamp(name, *a, **k):
+        now = _time.time()
+        state.cur[name] = state.cur.get(name, 0.0) + (now - state.last)
+        state.last = now
+
+    def _close_iteration():
+        for k, v in state.cur.items():
+            state.itrs.setdefault(k, []).append(v)
+        state.cur = {}
+
+    def timed_for(iterable, *a, **k):
+        for x in iterable:
+            yield x
+            _close_iteration()
+
+    def get_times():
+        # _try_to_eval runs INSIDE an iteration: the entries of the running iteration are visible as the last element
+        itrs = {k: list(v) for k, v in state.itrs.items()}
+        for k, v in state.cur.items():
+            itrs.setdefault(k, []).append(v)
+        return types.SimpleNamespace(stamps=types.SimpleNamespace(itrs=itrs), total=_time.time() - state.start)
+
+    mod.reset, mod.stamp, mod.timed_for, mod.get_times = reset, stamp, timed_for, get_times
+    mod.set_def_unique = lambda *a, **k: None
+
+
 def install():
     """Idempotent.  Stubs absent third-party modules and puts the reference on sys.path."""
     global _installed
@@ -109,6 +148,7 @@ def install():
     ]:
         if name not in sys.modules:
             sys.modules[name] = types.ModuleType(name)
+    _install_gtimer(sys.modules["gtimer"])
     sys.modules["matplotlib"].use = lambda *a, **k: None
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
     sys.modules["matplotlib"].animation = sys.modules["matplotlib.animation"]
