@@ -326,7 +326,7 @@ static int engine_configure(ilsw_trainer* tr) {
   tr->ctas = (!tr->tc5 && tr->spec.cfg.batch >= 512) ? 2 : 1;
   const char* cv = getenv("ILSW_CTAS_PER_SM");
   if (!tr->tc5 && cv && (atoi(cv) == 1 || atoi(cv) == 2)) tr->ctas = atoi(cv);
-  tr->smem_bytes = engine_smem(tr, kMaxOps);
+  tr->smem_bytes = engine_smem(tr, tr->host_prog.n_ops);     // the program is built: its op table is what the kernel copies
   const void* kfn = engine_fn(tr);
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tr->smem_bytes);
   if (e != cudaSuccess) return fail(ILSW_ERR_CUDA, "engine smem opt-in (%zu B): %s", tr->smem_bytes, cudaGetErrorString(e));
@@ -712,6 +712,8 @@ extern "C" int ilsw_replica_connect(ilsw_trainer* tr, int rank, int world, const
   const int n = tr->host_prog.ctx.policy.n_params;
   Replica& rp = tr->rep;
   memset(&rp, 0, sizeof(rp));
+  CU(cudaMemset(tr->ipc_buf, 0, kFlagBytes));      // sequence flags and push counter restart with tr->seq (peers push only after the caller's barrier)
+  CU(cudaDeviceSynchronize());
   rp.world = world; rp.rank = rank; rp.n = n; rp.nstride = round_up(n, 4);
   rp.grad = tr->host_prog.ctx.policy.g;
   for (int r = 0; r < world; ++r) {
@@ -724,8 +726,10 @@ extern "C" int ilsw_replica_connect(ilsw_trainer* tr, int rank, int world, const
     }
     tr->peer_bases[r] = base;
     rp.flags_peer[r] = reinterpret_cast<unsigned*>(base);
+    rp.cnt_peer[r] = reinterpret_cast<unsigned long long*>((char*)base + 128);     // [0,32): sequence flags; 128: push counter
     rp.recv_peer[r] = reinterpret_cast<float*>((char*)base + kFlagBytes);
   }
+  rp.cnt_local = rp.cnt_peer[rank];
   rp.flags_local = rp.flags_peer[rank];
   rp.recv_local = rp.recv_peer[rank];
   tr->seq = 0;

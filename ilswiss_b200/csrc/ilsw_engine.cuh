@@ -42,6 +42,8 @@ struct Replica {
   unsigned* flags_local;      // [8] sequence numbers written by the peers
   unsigned* flags_peer[8];
   unsigned seq0;              // exchanges completed before this launch
+  unsigned long long* cnt_local;      // arrival counter of the epilogue-push exchange: every CTA of every replica adds 1 per
+  unsigned long long* cnt_peer[8];    // policy update (after a system fence behind its pushes); never reset
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
@@ -56,6 +58,15 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 }
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_add_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 constexpr long long kSpinLimit = 4000000000LL;  // ~2 s at 2 GHz: a hung peer/CTA aborts the launch
@@ -217,7 +228,7 @@ __device__ __forceinline__ void adam_fused_elem(const AdamOp& ad, const AdamCoef
   adam_elem_g(ad, cf, gi, g, adam_has_shadow(ad));
 }
 
-__device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* smem, const AdamOp* ad, const AdamCoef* cf) {
+__device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* smem, const AdamOp* ad, const AdamCoef* cf, const PushCtx* push) {
   const int tid = threadIdx.x;
   const int tm = tile / o.tiles_n, tn = tile - tm * o.tiles_n;
   const int m0 = tm * kTM, n0 = tn * kTN;
@@ -288,7 +299,7 @@ __device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* 
   for (int j = 0; j < 4; ++j) {
     const int n = n0 + tx * 4 + j;
     if (m < o.M && n < Nt) {
-      epi_store(o, m, n, vout[j], ein[j]);
+      epi_store(o, m, n, vout[j], ein[j], push);
       if (ad) adam_fused_elem(*ad, *cf, gemm_grad_index(o, *ad, m, n), o.accumulate ? vout[j] + ein[j].prev : vout[j]);
     }
   }
@@ -297,7 +308,7 @@ __device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* 
     float ssum = 0.f;
     for (int k = 0; k < o.K; ++k) ssum += gemm_A(o, mm, k);
     const EpiIn e = epi_load(o, mm, o.N);
-    epi_store(o, mm, o.N, ssum, e);
+    epi_store(o, mm, o.N, ssum, e, push);
     if (ad) adam_fused_elem(*ad, *cf, gemm_grad_index(o, *ad, mm, o.N), o.accumulate ? ssum + e.prev : ssum);
   }
   if (o.a0_X && tn == 0) {     // materialise the fused first layer of this row block (backward pass)
@@ -585,7 +596,7 @@ constexpr int kRedFloats = 8 * 32 * kRedLd;   // 36 KB: fits one staging stage o
 // (fixed order: bit-reproducible).  Measured predecessor (one 16x8 accumulator per warp over the full K,
 // 96 dependent MMAs): 3.3 us of a 5.9 us tile.
 template <int KC>
-__device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* smem, int mode, int prof_phase, const AdamOp* ad, const AdamCoef* cf) {
+__device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* smem, int mode, int prof_phase, const AdamOp* ad, const AdamCoef* cf, const PushCtx* push) {
   constexpr int kKC = KC, kKS = TcGeom<KC>::kKS, kOperandFloats = TcGeom<KC>::kOperandFloats, kTcStageFloats = TcGeom<KC>::kStageFloats;
   static_assert(kRedFloats <= TcGeom<KC>::kStageFloats, "partial tiles must fit one stage");
   const GemmOp o = og;                       // registers / local copy: the op descriptor lives in shared memory
@@ -778,14 +789,14 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      if (er < o.M && ec + i < Nt) epi_store(o, er, ec + i, outv[i], ein[i]);
+      if (er < o.M && ec + i < Nt) epi_store(o, er, ec + i, outv[i], ein[i], push);
   }
   if (do_aug && tid < 32 && m0 + tid < o.M) {
     float bsum = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) bsum += smem[kRedFloats + w * 32 + tid];
     const EpiIn e = epi_load(o, m0 + tid, o.N);
-    epi_store(o, m0 + tid, o.N, bsum, e);
+    epi_store(o, m0 + tid, o.N, bsum, e, push);
     if (ad) adam_math_store(*ad, *cf, gib, o.accumulate ? bsum + e.prev : bsum, bm, bv, bp, bt, ad_sh);
   }
   __syncthreads();     // the partial tiles are read before the next job's panels overwrite them
@@ -799,7 +810,7 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
 // for these shapes costs a full tile (5 us); this is ~1.5 us.
 // Split along K (tcgen05 programs, K = batch >= 512): job (ks, tile) sums k in [ks * K / S, (ks + 1) * K / S) into the
 // partial gradient arena ks (C + ks * split_stride); one CTA walking K = 1024 alone took 23 us.
-__device__ __noinline__ void gemm_tile_skinny(const GemmOp& og, int tile, float* smem, const AdamOp* ad, const AdamCoef* cf) {
+__device__ __noinline__ void gemm_tile_skinny(const GemmOp& og, int tile, float* smem, const AdamOp* ad, const AdamCoef* cf, const PushCtx* push) {
   const GemmOp o = og;
   const int tid = threadIdx.x, col = tid & 31, kg = tid >> 5;
   const int n = tile * 32 + col;
@@ -845,7 +856,7 @@ __device__ __noinline__ void gemm_tile_skinny(const GemmOp& og, int tile, float*
 #pragma unroll
       for (int w = 0; w < 8; ++w) v += smem[(w * 8 + m) * 32 + col];
       const EpiIn e = epi_load(o, m, n);
-      epi_store(o, m, n, v, e);
+      epi_store(o, m, n, v, e, push);
       if (ad) adam_fused_elem(*ad, *cf, gemm_grad_index(o, *ad, m, n), o.accumulate ? v + e.prev : v);
     }
     if (o.aug_ones && tile == 0 && tid < M) {     // bias gradient
@@ -853,7 +864,7 @@ __device__ __noinline__ void gemm_tile_skinny(const GemmOp& og, int tile, float*
 #pragma unroll
       for (int w = 0; w < 8; ++w) v += smem[2048 + w * 8 + tid];
       const EpiIn e = epi_load(o, tid, o.N);
-      epi_store(o, tid, o.N, v, e);
+      epi_store(o, tid, o.N, v, e, push);
       if (ad) adam_fused_elem(*ad, *cf, gemm_grad_index(o, *ad, tid, o.N), o.accumulate ? v + e.prev : v);
     }
   }
@@ -873,7 +884,7 @@ __device__ __noinline__ void gemm_tile_skinny_split(const GemmOp& og, int tile_i
     s_split = o;
   }
   __syncthreads();
-  gemm_tile_skinny(s_split, tile, smem, nullptr, nullptr);
+  gemm_tile_skinny(s_split, tile, smem, nullptr, nullptr, nullptr);
 }
 ILSW_HD bool gemm_is_skinny(const GemmOp& o) { return o.M <= 8 && o.a_mc && o.b_nc && o.tiles_m == 1; }
 
@@ -920,6 +931,29 @@ __device__ __forceinline__ bool replica_exchange(const Replica& rp, unsigned seq
   }
   __syncthreads();
   return s_ok2 != 0;
+}
+
+// epilogue-push exchange, consumer side: wait until every CTA of every replica has signalled update `seq` (1-based)
+__device__ __forceinline__ bool replica_wait_pushes(const Replica& rp, unsigned seq, int* abort_flag) {
+  __shared__ int s_ok3;
+  if (threadIdx.x == 0) {
+    const unsigned long long want = (unsigned long long)seq * (unsigned long long)rp.world * (unsigned long long)gridDim.x;
+    int ok = 1;
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(rp.cnt_local) < want) {
+      const long long dt = clock64() - t0;
+      if (dt > kSpinLimit && (*(volatile int*)abort_flag || dt > 10 * kSpinLimit)) { atomicExch(abort_flag, 1); ok = 0; break; }
+    }
+    s_ok3 = ok;
+  }
+  __syncthreads();
+  return s_ok3 != 0;
+}
+// producer side: this CTA's pushes of the phase are complete and visible system-wide before the peers see the count
+__device__ __forceinline__ void replica_signal_pushes(const Replica& rp) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < rp.world) red_add_release_sys_u64(rp.cnt_peer[threadIdx.x], 1ull);
 }
 
 __device__ __forceinline__ float replica_reduced_grad(const Replica& rp, unsigned seq, int i) {
@@ -983,6 +1017,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
   __shared__ double s_p1[kMaxNets], s_p2[kMaxNets], s_b1[kMaxNets], s_b2[kMaxNets];   // running beta^t per Adam slot
   __shared__ int s_pt[kMaxNets];
   __shared__ tc5::Sync s_tc5;
+  __shared__ PushCtx s_push;
   const int n_phases = prog->n_phases, n_ops = prog->n_ops;
   constexpr int KC = CTAS == 2 ? 128 : 256;
   unsigned char* pbase = dyn_smem + engine_staging_bytes(CTAS, TC5);
@@ -1048,7 +1083,16 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
       const bool exchange = P.collective && rp.world > 1;
       // exchange sequence number = number of policy updates so far (parity double-buffers the slots)
       const unsigned xseq = rp.seq0 + (unsigned)(adam_t(a, c.hp, SLOT_POLICY, s) - a.t0[SLOT_POLICY]);
-      if (exchange && !replica_exchange(rp, xseq, bar, gen, abort_flag)) ILSW_DIE()
+      if (exchange && P.collective == 1 && !replica_exchange(rp, xseq, bar, gen, abort_flag)) ILSW_DIE()
+      if (exchange && P.collective == 2 && !replica_wait_pushes(rp, xseq, abort_flag)) ILSW_DIE()
+      const bool pushing = P.push && rp.world > 1;
+      if (pushing) {       // this rank's receive slot (parity of this update) on every replica
+        if (threadIdx.x < rp.world)
+          s_push.peer[threadIdx.x] = rp.recv_peer[threadIdx.x] + ((size_t)(xseq & 1u) * rp.world + rp.rank) * (size_t)rp.nstride;
+        if (threadIdx.x == 0) { s_push.grad_base = rp.grad; s_push.world = rp.world; }
+        __syncthreads();
+      }
+      const PushCtx* push = pushing ? &s_push : nullptr;
       for (int job = blockIdx.x; job < P.total_jobs && ILSW_ALIVE; job += gridDim.x) {
         int j = job, oi = P.op_begin;
         while (j >= s_ops[oi].n_jobs) { j -= s_ops[oi].n_jobs; ++oi; }
@@ -1064,9 +1108,9 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
               }
             }
           } else if (TC5 && gemm_is_skinny(o.gemm) && o.gemm.ksplit > 1) gemm_tile_skinny_split(o.gemm, j, smem);
-          else if (gemm_is_skinny(o.gemm)) gemm_tile_skinny(o.gemm, j, smem, ad, cf);
-          else if (prec == 0) gemm_tile_device(o.gemm, j, smem, ad, cf);
-          else gemm_tile_tc<KC>(o.gemm, j, smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, ad, cf);
+          else if (gemm_is_skinny(o.gemm)) gemm_tile_skinny(o.gemm, j, smem, ad, cf, push);
+          else if (prec == 0) gemm_tile_device(o.gemm, j, smem, ad, cf, push);
+          else gemm_tile_tc<KC>(o.gemm, j, smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, ad, cf, push);
         } else if (o.kind == OP_ROW) {
           RowEnv env; env.lane = lane; env.nl = 32; env.warp = warp; env.sm = smem;
           env.prof = (a.profile && blockIdx.x == 0) ? ph : -1;
@@ -1102,6 +1146,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
         }
       }
       if constexpr (TC5) { if (!alive) break; }
+      if (pushing) replica_signal_pushes(rp);
       if (stamp) c.phase_ns[kMaxPhases + 1 + ph] = globaltimer_ns();
       if (a.profile && s == a.n_steps - 1 && threadIdx.x == 0 && blockIdx.x < kMaxGrid) c.cta_ns[ph * kMaxGrid + blockIdx.x] = globaltimer_ns();
       if (!grid_barrier(bar, gridDim.x, gen, abort_flag)) ILSW_DIE()

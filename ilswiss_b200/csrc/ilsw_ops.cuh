@@ -157,9 +157,23 @@ ILSW_HD EpiIn epi_load(const GemmOp& o, int m, int n) {
   if (o.accumulate) e.prev = ldg(o.C + (size_t)m * o.ldc + n);
   return e;
 }
-ILSW_HD void epi_store(const GemmOp& o, int m, int n, float v, const EpiIn& e) {
+// device only: the produced gradient element also goes to every replica's receive slot (plain stores on peer-mapped
+// memory; the CTA fences and signals once, after its jobs of the phase)
+ILSW_HD void push_elem(const PushCtx* push, const float* where, float v) {
+#ifdef __CUDA_ARCH__
+  if (push) {
+    const size_t gi = (size_t)(where - push->grad_base);
+    for (int r = 0; r < push->world; ++r) push->peer[r][gi] = v;
+  }
+#else
+  (void)push; (void)where; (void)v;
+#endif
+}
+ILSW_HD void epi_store(const GemmOp& o, int m, int n, float v, const EpiIn& e, const PushCtx* push = nullptr) {
   if (o.aug_ones && n == o.N) {
-    o.bias_out[m] = o.accumulate ? v + e.prev : v;
+    const float bv = o.accumulate ? v + e.prev : v;
+    o.bias_out[m] = bv;
+    push_elem(push, o.bias_out + m, bv);
     return;
   }
   if (o.bias) v += e.bias;
@@ -171,6 +185,7 @@ ILSW_HD void epi_store(const GemmOp& o, int m, int n, float v, const EpiIn& e) {
   else if (o.mask == ACT_TANH) v *= (1.0f - e.h * e.h);
   if (o.accumulate) v += e.prev;
   o.C[ci] = v;
+  push_elem(push, o.C + ci, v);
 }
 ILSW_HD void gemm_epilogue(const GemmOp& o, int m, int n, float v) { epi_store(o, m, n, v, epi_load(o, m, n)); }
 

@@ -58,10 +58,10 @@ struct Builder {
   bool overflow = false;
   int base_cond = COND_ALWAYS;   // OR-ed into every phase (COND_DISC_PART / COND_POLICY_PART of AdvIRL programs)
 
-  void phase(int cond = COND_ALWAYS, int collective = 0) {
+  void phase(int cond = COND_ALWAYS, int collective = 0, int push = 0) {
     if (P.n_phases >= kMaxPhases) { overflow = true; return; }
     Phase& ph = P.phases[P.n_phases++];
-    ph.op_begin = P.n_ops; ph.op_count = 0; ph.total_jobs = 0; ph.cond = cond | base_cond; ph.collective = collective;
+    ph.op_begin = P.n_ops; ph.op_count = 0; ph.total_jobs = 0; ph.cond = cond | base_cond; ph.collective = collective; ph.push = push;
   }
   Op* add(int kind, int n_jobs) {
     if (P.n_ops >= kMaxOps || P.n_phases == 0) { overflow = true; return nullptr; }
@@ -475,13 +475,15 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
   b.phase(COND_WORLD_1);
   b.row(ROW_SAC_FINAL, 1);
   b.row(ROW_SAC_GATHER, B, /*next_step=*/1);
-  // replicas: gradients first, then exchange + Adam of the averaged gradient
-  b.phase(COND_WORLD_N);
+  // replicas: the weight-gradient tiles push what they produce into every replica's receive slot from their epilogues (the
+  // NVLink transfer overlaps the rest of the phase), then the Adam phase waits for the peers' pushes and applies the
+  // rank-ordered sum
+  b.phase(COND_WORLD_N, 0, /*push=*/1);
   b.dw(S.d1p, Hd, Hd, h0p_obs, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);
   b.dw(S.d0p, Hd, Hd, obs_rows, S.ld_o, O, B, P.g + P.oW0, P.g + P.ob0);
   b.dw(S.dmean, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2);
   b.dw(S.dlraw, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW3, P.g + P.ob3);
-  b.phase(COND_WORLD_N, 1);
+  b.phase(COND_WORLD_N, 2);
   b.adam(P, nullptr, c.hp.policy_lr, b1, b2, eps, 0.f, SLOT_POLICY, 1);
   b.row(ROW_SAC_FINAL, 1);
   b.row(ROW_SAC_GATHER, B, /*next_step=*/1);
@@ -578,11 +580,11 @@ inline void build_td3(Builder& b, const Ctx& c) {
   }
   b.polyak(c.qf[0], c.tqf[0], c.hp.tau);
   b.polyak(c.qf[1], c.tqf[1], c.hp.tau);
-  b.phase(PC | COND_WORLD_N);
+  b.phase(PC | COND_WORLD_N, 0, /*push=*/1);
   b.dw(S.d1p, Hd, Hd, S.h0p, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);
   b.dw(S.d0p, Hd, Hd, S.Xoa, S.ld_oa, O, B, P.g + P.oW0, P.g + P.ob0);
   b.dw(S.dmean, A, A, S.h1p, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2);
-  b.phase(PC | COND_WORLD_N, 1);
+  b.phase(PC | COND_WORLD_N, 2);
   b.adam(P, &c.tpolicy, c.hp.policy_lr, b1, b2, eps, c.hp.tau, SLOT_POLICY, 1);
   b.polyak(c.qf[0], c.tqf[0], c.hp.tau);
   b.polyak(c.qf[1], c.tqf[1], c.hp.tau);
@@ -682,12 +684,12 @@ inline void build_sac_v(Builder& b, const Ctx& c) {
     b.dw(S.dlraw, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW3, P.g + P.ob3, 0, ad);
   }
   b.row(ROW_SACV_FINAL, 1);
-  b.phase(COND_WORLD_N);
+  b.phase(COND_WORLD_N, 0, /*push=*/1);
   b.dw(S.d1p, Hd, Hd, h0p_obs, Hd, Hd, B, P.g + P.oW1, P.g + P.ob1);
   b.dw(S.d0p, Hd, Hd, obs_rows, S.ld_o, O, B, P.g + P.oW0, P.g + P.ob0);
   b.dw(S.dmean, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW2, P.g + P.ob2);
   b.dw(S.dlraw, A, A, h1p_obs, Hd, Hd, B, P.g + P.oW3, P.g + P.ob3);
-  b.phase(COND_WORLD_N, 1);
+  b.phase(COND_WORLD_N, 2);
   b.adam(P, nullptr, c.hp.policy_lr, b1, b2, eps, 0.f, SLOT_POLICY, 1);
   b.row(ROW_SACV_FINAL, 1);
 }
@@ -847,7 +849,7 @@ inline std::string describe_program(const Program& P) {
     const Phase& ph = P.phases[i];
     snprintf(line, sizeof(line), "phase %2d jobs=%4d%s%s%s%s%s:", i, ph.total_jobs, (ph.cond & COND_TD3_POLICY) ? " [td3-policy-step]" : ((ph.cond & COND_TD3_POLICY_OR_STATS) ? " [td3-policy-or-stats-step]" : ""),
              (ph.cond & COND_FIRST_STEP) ? " [first-step]" : "", (ph.cond & COND_WORLD_1) ? " [1-replica]" : "",
-             (ph.cond & COND_WORLD_N) ? " [n-replicas]" : "", ph.collective ? " [replica-exchange]" : "");
+             (ph.cond & COND_WORLD_N) ? " [n-replicas]" : "", ph.collective ? " [replica-exchange]" : (ph.push ? " [pushes to replicas]" : ""));
     out += line;
     for (int j = 0; j < ph.op_count; ++j) {
       const Op& o = P.ops[ph.op_begin + j];

@@ -109,6 +109,10 @@ struct AdamOp {
   int g_split_stride;
 };
 
+// replica exchange from the tile epilogues (Phase::push): where element `p` of the local policy gradient arena goes on
+// every replica -- peer[r] is this rank's receive slot on replica r (NVLink peer mapping), offset by the arena position
+struct PushCtx { float* peer[8]; const float* grad_base; int world; };
+
 struct PolyakOp { float* target; const float* src; int n; float tau; ShadowRef sh_t; };
 struct ShadowOp { const float* src; ShadowRef dst; };   // refresh of one aligned copy (first step of a launch)
 
@@ -134,7 +138,10 @@ struct Phase {
   int op_begin, op_count;
   int total_jobs;
   int cond;
-  int collective;       // 1: cross-replica gradient exchange happens at the START of this phase
+  int collective;       // cross-replica gradient exchange at the START of this phase: 1 = push loop + flags (gradient arenas
+                        // pushed whole), 2 = only wait for the pushes the weight-gradient tiles made from their epilogues
+  int push;             // 1: the GEMM tiles of this phase also store what they produce into every replica's receive slot
+                        // (NVLink peer stores) and every CTA signals the peers when its jobs are done
 };
 
 // ---- per-algorithm buffer tables (device or host pointers) --------------------------------

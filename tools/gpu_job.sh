@@ -14,6 +14,7 @@ for step in "$@"; do
     pp_ant) timeout 300 python tools/phase_profile.py sac_ant > gpurun_out/${TAG}_pp_ant.txt 2>&1 ;;
     bench) timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
     benchlong) timeout 600 python bench.py > gpurun_out/${TAG}_benchlong.json 2> gpurun_out/${TAG}_benchlong.err ;;
+    pp_sac_stamps) timeout 300 python tools/phase_profile.py sac_hopper gail_walker > gpurun_out/${TAG}_pp_sac_stamps.txt 2>&1 ;;
     ab_sac) timeout 600 tools/ab.sh "sac_hopper --no-tile-stamps" variants/r1.so ilswiss_b200/csrc/libilswiss_b200.so variants/r1.so ilswiss_b200/csrc/libilswiss_b200.so > gpurun_out/${TAG}_ab_sac.txt 2>&1 ;;
     smi) nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.draw,temperature.gpu --format=csv > gpurun_out/${TAG}_smi.txt 2>&1 ;;
     *) echo "unknown step $step" ;;
