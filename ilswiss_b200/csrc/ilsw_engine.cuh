@@ -135,12 +135,12 @@ struct TileLoader {
   float ra[4], rb[4];
 };
 
-__device__ __forceinline__ void tile_load_A(const GemmOp& o, int m0, int k0, float* r, bool fast) {
+__device__ __forceinline__ void tile_load_A(const GemmOp& o, int m0, int k0, float* r, bool fast, const L0FuseOp* fz) {
   const int tid = threadIdx.x;
-  if (o.a0_X) {   // fused first layer (GemmOp::a0_X): produced element by element in the exact mode
+  if (fz) {       // fused first layer (GemmOp::a0): produced element by element in the exact mode
     const int m = m0 + (tid >> 3), k = k0 + ((tid & 7) << 2);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) r[i] = (m < o.M && k + i < o.K) ? gemm_A_fused(o, m, k + i) : 0.f;
+    for (int i = 0; i < 4; ++i) r[i] = (m < o.M && k + i < o.K) ? gemm_A_fused(*fz, m, k + i) : 0.f;
     return;
   }
   if (!o.a_mc) {  // k contiguous: thread -> (m = tid/8, k = (tid%8)*4 .. +3)
@@ -228,7 +228,7 @@ __device__ __forceinline__ void adam_fused_elem(const AdamOp& ad, const AdamCoef
   adam_elem_g(ad, cf, gi, g, adam_has_shadow(ad));
 }
 
-__device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* smem, const AdamOp* ad, const AdamCoef* cf, const PushCtx* push) {
+__device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* smem, const AdamOp* ad, const AdamCoef* cf, const PushCtx* push, const L0FuseOp* fz) {
   const int tid = threadIdx.x;
   const int tm = tile / o.tiles_n, tn = tile - tm * o.tiles_n;
   const int m0 = tm * kTM, n0 = tn * kTN;
@@ -242,7 +242,7 @@ __device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float ra[4], rb[4];
-  tile_load_A(o, m0, 0, ra, fastA);
+  tile_load_A(o, m0, 0, ra, fastA, fz);
   tile_load_B(o, n0, 0, rb, fastB);
   tile_store_A(o, smem, ra);
   tile_store_B(o, smem + kStageFloats, rb);
@@ -251,7 +251,7 @@ __device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* 
     float* As = smem + (c & 1) * 2 * kStageFloats;
     float* Bs = As + kStageFloats;
     if (c + 1 < nchunks) {
-      tile_load_A(o, m0, (c + 1) * kTK, ra, fastA);
+      tile_load_A(o, m0, (c + 1) * kTK, ra, fastA, fz);
       tile_load_B(o, n0, (c + 1) * kTK, rb, fastB);
     }
 #pragma unroll
@@ -311,10 +311,10 @@ __device__ __noinline__ void gemm_tile_device(const GemmOp& o, int tile, float* 
     epi_store(o, mm, o.N, ssum, e, push);
     if (ad) adam_fused_elem(*ad, *cf, gemm_grad_index(o, *ad, mm, o.N), o.accumulate ? ssum + e.prev : ssum);
   }
-  if (o.a0_X && tn == 0) {     // materialise the fused first layer of this row block (backward pass)
+  if (fz && tn == 0) {         // materialise the fused first layer of this row block (backward pass)
     for (int e = tid; e < kTM * o.K; e += kThreads) {
       const int r = e / o.K, k = e - r * o.K;
-      if (m0 + r < o.M) o.a0_out[(size_t)(m0 + r) * o.a0_ldo + k] = gemm_A_fused(o, m0 + r, k);
+      if (m0 + r < o.M) fz->out[(size_t)(m0 + r) * fz->ldo + k] = gemm_A_fused(*fz, m0 + r, k);
     }
   }
   __syncthreads();
@@ -470,7 +470,7 @@ __device__ __noinline__ void tc_fill_stage(const GemmOp& o, float* stage, int m0
   const int tid = threadIdx.x;
   const int kpad = (klen + 15) & ~15;    // zero padded to TWO MMA k-steps (the k loop is unrolled by 2, unguarded)
 #pragma unroll 1
-  for (int op = o.a0_X ? 1 : 0; op < 2; ++op) {      // a fused first layer produces its own A panel (tc_produce_l0)
+  for (int op = o.a0 ? 1 : 0; op < 2; ++op) {      // a fused first layer produces its own A panel (tc_produce_l0)
     const bool isB = op != 0;
     const bool contig_k = isB ? !o.b_nc : !o.a_mc;
     const float* base = isB ? o.B : o.A;
@@ -532,56 +532,93 @@ __device__ __noinline__ void tc_fill_stage(const GemmOp& o, float* stage, int m0
   }
 }
 
-// Fused first layer (GemmOp::a0_X): the k-contiguous A panel [32 rows][kKS] of one stage is PRODUCED here instead of
-// copied: W0^T and the 32 input rows are staged in `scratch` (the idle second stage buffer: K <= KC), thread k owns
-// column k of the panel for all 32 rows (fp32 FMA chain over the K0 <= 32 inputs, bias first -- the order of
-// gemm_A_fused), applies the activation, writes the panel and, in the tn == 0 tile, the activations for the backward pass.
+// Fused first layer (GemmOp::a0): the k-contiguous A panel [32 rows][kKS] of one stage is PRODUCED here instead of
+// copied -- on the tensor cores, like the layer it feeds: warp w computes panel columns [32 w, 32 w + 32) (output features
+// of the first layer) for the 32 rows of the tile as 2 x 4 m16n8k8 tiles over the K0 <= 32 inputs, fragments loaded
+// straight from global memory (one L2 round trip, no staging, no CTA barrier), same operand split as the main loop
+// (mode 3: lo*hi, hi*lo, hi*hi).  Bias + activation are applied on the accumulators, which go to the panel and -- in the
+// tn == 0 tile -- to L0FuseOp::out for the backward pass.  (A first version on the SIMT pipes, thread per column with W0^T
+// staged in shared memory, took 8 us per tile: profiles/r2_phase_profile_l0_simt.txt.)
 template <int KC>
-__device__ __noinline__ void tc_produce_l0(const GemmOp& og, float* panel, float* scratch, int m0, int k0, int klen, bool store_out) {
+__device__ __forceinline__ void tc_produce_l0(const L0FuseOp& f, int M, float* panel, int m0, int k0, int klen, bool store_out, int mode) {
   constexpr int kKS = TcGeom<KC>::kKS;
-  static_assert(kThreads >= KC, "one thread per panel column");
-  const GemmOp o = og;
-  const int tid = threadIdx.x, K0 = o.a0_K;
-  float* Wt = scratch;                       // [K0][KC]: Wt[j*KC + k] = W0[(k0+k)*K0 + j]
-  float* Xs = scratch + kFuseL0MaxK * KC;    // [K0][32]: Xs[j*32 + r] = X[(m0+r)*ldx + j]
-  float bk = 0.f;
-  if (tid < klen) {
-    const float* w = o.a0_W + (size_t)(k0 + tid) * K0;
-    bk = __ldcg(o.a0_b + k0 + tid);
-    float wr[kFuseL0MaxK];
-#pragma unroll
-    for (int j = 0; j < kFuseL0MaxK; ++j) wr[j] = j < K0 ? __ldcg(w + j) : 0.f;
-#pragma unroll
-    for (int j = 0; j < kFuseL0MaxK; ++j) if (j < K0) Wt[j * KC + tid] = wr[j];
-  }
-  for (int e = tid; e < 32 * K0; e += kThreads) {
-    const int r = e / K0, j = e - r * K0;
-    Xs[j * 32 + r] = (m0 + r < o.M) ? __ldcg(o.a0_X + (size_t)(m0 + r) * o.a0_ldx + j) : 0.f;
-  }
-  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
   const int kpad = (klen + 15) & ~15;
-  if (tid < kpad) {
-    float acc[32];
+  const int n_base = 32 * warp;                       // first panel column of this warp
+  if (n_base >= kpad) return;
+  const int K0 = f.K0, nks = (K0 + 7) >> 3;         // <= kFuseL0MaxK / 8 k-steps
+  float acc[8][4];
 #pragma unroll
-    for (int r = 0; r < 32; ++r) acc[r] = bk;
-    if (tid < klen) {
-#pragma unroll 2
-      for (int j = 0; j < K0; ++j) {
-        const float w = Wt[j * KC + tid];
-        const float4* xr = reinterpret_cast<const float4*>(Xs + j * 32);
+  for (int u = 0; u < 8; ++u)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 x = xr[q];
-          acc[4 * q] = fmaf(x.x, w, acc[4 * q]); acc[4 * q + 1] = fmaf(x.y, w, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(x.z, w, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(x.w, w, acc[4 * q + 3]);
-        }
+    for (int i = 0; i < 4; ++i) acc[u][i] = 0.f;
+  constexpr int kMaxKs = kFuseL0MaxK / 8;
+  float af[kMaxKs][8], bf[kMaxKs][8];
+  // all fragment loads first
+#pragma unroll
+  for (int ks = 0; ks < kMaxKs; ++ks) {
+    if (ks < nks) {
+      const int c0 = 8 * ks + q, c1 = c0 + 4;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r0 = m0 + 16 * mt + g, r1 = r0 + 8;
+        const float* x0 = f.X + (size_t)r0 * f.ldx;
+        const float* x1 = f.X + (size_t)r1 * f.ldx;
+        af[ks][4 * mt + 0] = (r0 < M && c0 < K0) ? __ldcg(x0 + c0) : 0.f;
+        af[ks][4 * mt + 1] = (r1 < M && c0 < K0) ? __ldcg(x1 + c0) : 0.f;
+        af[ks][4 * mt + 2] = (r0 < M && c1 < K0) ? __ldcg(x0 + c1) : 0.f;
+        af[ks][4 * mt + 3] = (r1 < M && c1 < K0) ? __ldcg(x1 + c1) : 0.f;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int n = n_base + 8 * nt + g;            // output feature within the stage
+        const float* w = f.W + (size_t)(k0 + n) * K0;
+        bf[ks][2 * nt + 0] = (n < klen && c0 < K0) ? __ldcg(w + c0) : 0.f;
+        bf[ks][2 * nt + 1] = (n < klen && c1 < K0) ? __ldcg(w + c1) : 0.f;
       }
     }
+  }
 #pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      const float v = tid < klen ? act_apply(acc[r], o.a0_act) : 0.f;     // zero padding up to two MMA k-steps
-      panel[r * kKS + tid] = v;
-      if (store_out && tid < klen && m0 + r < o.M) o.a0_out[(size_t)(m0 + r) * o.a0_ldo + k0 + tid] = v;
+  for (int ks = 0; ks < kMaxKs; ++ks) {
+    if (ks < nks) {
+      uint32_t ah[8], bh[8], al[8], bl[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        ah[i] = cvt_tf32(af[ks][i]); bh[i] = cvt_tf32(bf[ks][i]);
+        al[i] = cvt_tf32(af[ks][i] - __uint_as_float(ah[i])); bl[i] = cvt_tf32(bf[ks][i] - __uint_as_float(bh[i]));
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          if (mode == 3) {
+            mma_tf32p(acc[mt * 4 + nt], al + 4 * mt, bh + 2 * nt);
+            mma_tf32p(acc[mt * 4 + nt], ah + 4 * mt, bl + 2 * nt);
+          }
+          mma_tf32p(acc[mt * 4 + nt], ah + 4 * mt, bh + 2 * nt);
+        }
+    }
+  }
+  // accumulator layout of m16n8: c0,c1 -> (row g, cols 2q, 2q+1); c2,c3 -> (row g+8, same cols)
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int n = n_base + 8 * nt + 2 * q;
+    const bool live0 = n < klen, live1 = n + 1 < klen;
+    const float b0v = live0 ? __ldcg(f.b + k0 + n) : 0.f, b1v = live1 ? __ldcg(f.b + k0 + n + 1) : 0.f;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = 16 * mt + g + 8 * h;
+        const float v0 = live0 ? act_apply(acc[mt * 4 + nt][2 * h] + b0v, f.act) : 0.f;      // zero padding beyond klen
+        const float v1 = live1 ? act_apply(acc[mt * 4 + nt][2 * h + 1] + b1v, f.act) : 0.f;
+        *reinterpret_cast<float2*>(panel + r * kKS + n) = make_float2(v0, v1);
+        if (store_out && m0 + r < M) {
+          float* dst = f.out + (size_t)(m0 + r) * f.ldo + k0 + n;
+          if (live1) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+          else if (live0) *dst = v0;
+        }
+      }
     }
   }
 }
@@ -596,7 +633,7 @@ constexpr int kRedFloats = 8 * 32 * kRedLd;   // 36 KB: fits one staging stage o
 // (fixed order: bit-reproducible).  Measured predecessor (one 16x8 accumulator per warp over the full K,
 // 96 dependent MMAs): 3.3 us of a 5.9 us tile.
 template <int KC>
-__device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* smem, int mode, int prof_phase, const AdamOp* ad, const AdamCoef* cf, const PushCtx* push) {
+__device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* smem, int mode, int prof_phase, const AdamOp* ad, const AdamCoef* cf, const PushCtx* push, const L0FuseOp* fz) {
   constexpr int kKC = KC, kKS = TcGeom<KC>::kKS, kOperandFloats = TcGeom<KC>::kOperandFloats, kTcStageFloats = TcGeom<KC>::kStageFloats;
   static_assert(kRedFloats <= TcGeom<KC>::kStageFloats, "partial tiles must fit one stage");
   const GemmOp o = og;                       // registers / local copy: the op descriptor lives in shared memory
@@ -675,19 +712,8 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
       const int k0 = (st + 1) * kKC;
       tc_fill_stage<KC>(og, smem + ((st + 1) & 1) * kTcStageFloats, m0, n0, k0, min(kKC, o.K - k0), vecA, vecB);
       cp_async_commit();
-      if (o.a0_X) {      // the B panel is in flight; produce the A panel meanwhile (single-stage GEMMs: the other stage buffer is scratch)
-        if (nstages == 1) tc_produce_l0<KC>(og, smem + ((st + 1) & 1) * kTcStageFloats, smem + (st & 1) * kTcStageFloats, m0, k0, min(kKC, o.K - k0), tn == 0);
-        else {
-          float* panel = smem + ((st + 1) & 1) * kTcStageFloats;
-          const int klen = min(kKC, o.K - k0), kpad = (klen + 15) & ~15;
-          for (int e = tid; e < 32 * kpad; e += kThreads) {
-            const int r = e / kpad, k = e - r * kpad;
-            const float v = (m0 + r < o.M && k < klen) ? gemm_A_fused(o, m0 + r, k0 + k) : 0.f;
-            panel[r * kKS + k] = v;
-            if (tn == 0 && m0 + r < o.M && k < klen) o.a0_out[(size_t)(m0 + r) * o.a0_ldo + k0 + k] = v;
-          }
-        }
-      }
+      if (fz)           // the B panel is in flight; produce the A panel meanwhile
+        tc_produce_l0<KC>(*fz, o.M, smem + ((st + 1) & 1) * kTcStageFloats, m0, k0, min(kKC, o.K - k0), tn == 0, mode);
     }
     if (st < 0) {
 #if !ILSW_EIN_FIRST
@@ -787,9 +813,15 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
         adam_math_store(*ad, *cf, gi[i], gv, am[i], av[i], ap[i], at[i], ad_sh);
       }
   } else {
+    if (push) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (er < o.M && ec + i < Nt) epi_store(o, er, ec + i, outv[i], ein[i], push);
+      for (int i = 0; i < 4; ++i)
+        if (er < o.M && ec + i < Nt) epi_store(o, er, ec + i, outv[i], ein[i], push);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (er < o.M && ec + i < Nt) epi_store(o, er, ec + i, outv[i], ein[i]);
+    }
   }
   if (do_aug && tid < 32 && m0 + tid < o.M) {
     float bsum = 0.f;
@@ -1100,6 +1132,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
         if (o.kind == OP_GEMM) {
           const AdamOp* ad = o.gemm.adam ? &s_ops[o.gemm.adam - 1].adam : nullptr;
           const AdamCoef* cf = ad ? &s_coefs[ad->slot] : nullptr;
+          const L0FuseOp* fz = o.gemm.a0 ? &s_ops[o.gemm.a0 - 1].l0 : nullptr;
           if (TC5 && o.gemm.tc5) {
             if constexpr (TC5) {
               if (!tc5::gemm_tile<kTc5BN>(o.gemm, j, tc5_smem, s_tc5, tc5_state)) {
@@ -1109,8 +1142,8 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
             }
           } else if (TC5 && gemm_is_skinny(o.gemm) && o.gemm.ksplit > 1) gemm_tile_skinny_split(o.gemm, j, smem);
           else if (gemm_is_skinny(o.gemm)) gemm_tile_skinny(o.gemm, j, smem, ad, cf, push);
-          else if (prec == 0) gemm_tile_device(o.gemm, j, smem, ad, cf, push);
-          else gemm_tile_tc<KC>(o.gemm, j, smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, ad, cf, push);
+          else if (prec == 0) gemm_tile_device(o.gemm, j, smem, ad, cf, push, fz);
+          else gemm_tile_tc<KC>(o.gemm, j, smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, ad, cf, push, fz);
         } else if (o.kind == OP_ROW) {
           RowEnv env; env.lane = lane; env.nl = 32; env.warp = warp; env.sm = smem;
           env.prof = (a.profile && blockIdx.x == 0) ? ph : -1;

@@ -126,16 +126,15 @@ ILSW_HD float act_apply(float v, int act) {
   if (act == ACT_TANH) return tanhf(v);
   return v;
 }
-// element (m,k) of a fused first layer (GemmOp::a0_X): fp32 FMA chain in input order
-ILSW_HD float gemm_A_fused(const GemmOp& o, int m, int k) {
-  float acc = ldg(o.a0_b + k);
-  const float* x = o.a0_X + (size_t)m * o.a0_ldx;
-  const float* w = o.a0_W + (size_t)k * o.a0_K;
-  for (int j = 0; j < o.a0_K; ++j) acc = fmaf(ldg(x + j), ldg(w + j), acc);
-  return act_apply(acc, o.a0_act);
+// element (m,k) of a fused first layer (GemmOp::a0 -> L0FuseOp): fp32 FMA chain in input order
+ILSW_HD float gemm_A_fused(const L0FuseOp& f, int m, int k) {
+  float acc = ldg(f.b + k);
+  const float* x = f.X + (size_t)m * f.ldx;
+  const float* w = f.W + (size_t)k * f.K0;
+  for (int j = 0; j < f.K0; ++j) acc = fmaf(ldg(x + j), ldg(w + j), acc);
+  return act_apply(acc, f.act);
 }
 ILSW_HD float gemm_A(const GemmOp& o, int m, int k) {
-  if (o.a0_X) return gemm_A_fused(o, m, k);
   return ldg(o.A + (o.a_mc ? (size_t)k * o.lda + m : (size_t)m * o.lda + k));
 }
 ILSW_HD float gemm_B(const GemmOp& o, int k, int n) {

@@ -119,16 +119,20 @@ struct Builder {
     gemm(g);
   }
   // Two layers in one phase: H0 = act0(X W0^T + b0) [M, hid] is produced inside the tiles of Y = act(H0 W1^T + b1)
-  // (GemmOp::a0_X) when the first layer's input is narrow; otherwise two phases.  H0 is materialised for the backward pass.
+  // (GemmOp::a0) when the first layer's input is narrow; otherwise two phases.  H0 is materialised for the backward pass.
   bool fuse_l0_ok(int K0, int hid) const {
-    return !P.ctx.hp.use_tc5 && K0 <= kFuseL0MaxK && hid <= 256 && P.ctx.s.B < 512;
+    return !P.ctx.hp.use_tc5 && K0 <= kFuseL0MaxK && hid <= 256 && (hid & 1) == 0 && P.ctx.s.B < 512;
   }
   void fwd2_fused(const float* X, int ldx, int M, int K0, const float* W0, const float* b0, int act0, int hid, float* H0,
                   const float* W1, const float* b1, int N, float* Y, int ldy, int act) {
+    const int fidx = P.n_ops;
+    Op* fo = add(OP_L0FUSE, 0);
+    if (!fo) return;
+    fo->l0.X = X; fo->l0.ldx = ldx; fo->l0.K0 = K0; fo->l0.W = W0; fo->l0.b = b0; fo->l0.act = act0; fo->l0.out = H0; fo->l0.ldo = hid;
     GemmOp g; memset(&g, 0, sizeof(g));
     g.A = H0; g.lda = hid; g.a_mc = 0; g.B = W1; g.ldb = hid; g.b_nc = 0; g.M = M; g.N = N; g.K = hid;
     g.C = Y; g.ldc = ldy; g.bias = b1; g.act = act;
-    g.a0_X = X; g.a0_ldx = ldx; g.a0_K = K0; g.a0_W = W0; g.a0_b = b0; g.a0_act = act0; g.a0_out = H0; g.a0_ldo = hid;
+    g.a0 = fidx + 1;
     gemm(g);
   }
   // the first two layers of several networks, side by side: one fused phase when every first layer is narrow, else a
@@ -854,8 +858,8 @@ inline std::string describe_program(const Program& P) {
     for (int j = 0; j < ph.op_count; ++j) {
       const Op& o = P.ops[ph.op_begin + j];
       if (o.kind == OP_GEMM)
-        snprintf(line, sizeof(line), " GEMM(%dx%dx%d%s%s%s%s)", o.gemm.M, o.gemm.N, o.gemm.K, o.gemm.aug_ones ? "+1" : "",
-                 o.gemm.accumulate ? ",acc" : "", o.gemm.adam ? ",adam" : "", o.gemm.tc5 ? ",tcgen05" : "");
+        snprintf(line, sizeof(line), " GEMM(%dx%dx%d%s%s%s%s%s)", o.gemm.M, o.gemm.N, o.gemm.K, o.gemm.aug_ones ? "+1" : "",
+                 o.gemm.accumulate ? ",acc" : "", o.gemm.adam ? ",adam" : "", o.gemm.tc5 ? ",tcgen05" : "", o.gemm.a0 ? ",fused-L0" : "");
       else if (o.kind == OP_ROW)
         snprintf(line, sizeof(line), " ROW(k%d,%d)", o.row.kind, o.row.rows);
       else if (o.kind == OP_ADAM && o.adam.fused_only)
@@ -864,6 +868,8 @@ inline std::string describe_program(const Program& P) {
         snprintf(line, sizeof(line), " ADAM(%d%s)", o.adam.n, o.adam.target ? ",polyak" : "");
       else if (o.kind == OP_SHADOW)
         snprintf(line, sizeof(line), " W0COPY(%d)", o.shadow.dst.n);
+      else if (o.kind == OP_L0FUSE)
+        line[0] = 0;
       else
         snprintf(line, sizeof(line), " %s(%d)", kinds[o.kind], o.polyak.n);
       out += line;

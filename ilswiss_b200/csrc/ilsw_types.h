@@ -27,11 +27,11 @@ constexpr int kLossSlots = 16;    // floats per step in the loss log
 constexpr int kThreads = 256;     // CTA size of the engine kernel
 constexpr int kRowsPerJob = 8;    // one warp per batch row
 constexpr int kAdamChunk = 2048;  // elements per flat Adam/Polyak job
-constexpr int kFuseL0MaxK = 32;   // widest first-layer input folded into the second layer's GEMM tiles (GemmOp::a0_X)
+constexpr int kFuseL0MaxK = 32;   // widest first-layer input folded into the second layer's GEMM tiles (GemmOp::a0)
 constexpr int kMaxGradSplits = 4;  // split-K partial gradient arenas summed by the flat Adam jobs (adam_grad)
 constexpr int kTc5BN = 64;        // column width of the tcgen05 tile (ilsw_tc5.cuh is instantiated with it; rows: 128)
 
-enum OpKind : int { OP_GEMM = 1, OP_ADAM = 2, OP_ROW = 3, OP_POLYAK = 4, OP_SHADOW = 5 };
+enum OpKind : int { OP_GEMM = 1, OP_ADAM = 2, OP_ROW = 3, OP_POLYAK = 4, OP_SHADOW = 5, OP_L0FUSE = 6 };
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 
@@ -73,13 +73,8 @@ struct GemmOp {
                         // the epilogue applies the Adam (+Polyak) update to every gradient element it produces, so the
                         // weight-gradient phase needs no separate optimiser phase (valid only without accumulate
                         // partners and without a cross-replica exchange)
-  // Fused first layer (A-operand producer, small-input nets: K0 = O + A <= kFuseL0MaxK): when a0_X != nullptr the A
-  // operand is not read from memory but produced inside the tile,
-  //   A(m,k) = act0( sum_j a0_X[m*a0_ldx + j] * a0_W[k*a0_K + j] + a0_b[k] ),  j < a0_K,  k < K (= hidden width),
-  // i.e. Linear(K0 -> hidden) + activation of networks.py:85-101 folded into the GEMM of the second layer: one phase
-  // (and one grid barrier) less per forward pass.  The tn == 0 tile of every row block also stores A(m, :) to a0_out
-  // (the backward pass needs the first-layer activations).
-  const float* a0_X; int a0_ldx; int a0_K; const float* a0_W; const float* a0_b; int a0_act; float* a0_out; int a0_ldo;
+  int a0;               // 0: none; k+1: ops[k] is an OP_L0FUSE descriptor -- the A operand is PRODUCED inside the tile (fused
+                        // first layer, see L0FuseOp) instead of read from memory
   int tc5;              // 1: 128 x 64 tcgen05/TMA tile (ilsw_tc5.cuh); tiles_m/tiles_n then count those tiles
   int ksplit;           // tcgen05 weight-gradient GEMMs: number of K splits (jobs = ksplit * tiles_m * tiles_n); split s writes
   int split_stride;     //   its partial sums to C + s * split_stride / bias_out + s * split_stride (floats); 0 / 1: no split
@@ -113,6 +108,13 @@ struct AdamOp {
 // every replica -- peer[r] is this rank's receive slot on replica r (NVLink peer mapping), offset by the arena position
 struct PushCtx { float* peer[8]; const float* grad_base; int world; };
 
+// Fused first layer (A-operand producer of a second-layer GEMM, small-input nets: K0 = O + A <= kFuseL0MaxK):
+//   A(m,k) = act( sum_j X[m*ldx + j] * W[k*K0 + j] + b[k] ),  j < K0,  k < K (= hidden width),
+// i.e. Linear(K0 -> hidden) + activation of networks.py:85-101 folded into the GEMM of the second layer: one phase (and
+// one grid barrier) less per forward pass.  The tn == 0 tile of every row block also stores A(m, :) to `out` (the
+// backward pass needs the first-layer activations).  Descriptor op without jobs, referenced by GemmOp::a0.
+struct L0FuseOp { const float* X; int ldx; int K0; const float* W; const float* b; int act; float* out; int ldo; };
+
 struct PolyakOp { float* target; const float* src; int n; float tau; ShadowRef sh_t; };
 struct ShadowOp { const float* src; ShadowRef dst; };   // refresh of one aligned copy (first step of a launch)
 
@@ -131,6 +133,7 @@ struct Op {
     PolyakOp polyak;
     RowOp row;
     ShadowOp shadow;
+    L0FuseOp l0;
   };
 };
 

@@ -33,10 +33,11 @@ static void run_op(HostSim* hs, const Program& P, const Op& o, const RunArgs& a,
   const Ctx& c = P.ctx;
   if (o.kind == OP_GEMM) {
     GemmOp g = o.gemm;
-    if (g.a0_X) {        // fused first layer: materialise it (the device's tn == 0 tiles do), then read it as a plain operand
+    if (g.a0) {          // fused first layer: materialise it (the device's tn == 0 tiles do), then read it as a plain operand
+      const L0FuseOp& f = P.ops[g.a0 - 1].l0;
       for (int m = 0; m < g.M; ++m)
-        for (int k = 0; k < g.K; ++k) g.a0_out[(size_t)m * g.a0_ldo + k] = gemm_A_fused(g, m, k);
-      g.A = g.a0_out; g.lda = g.a0_ldo; g.a_mc = 0; g.a0_X = nullptr;
+        for (int k = 0; k < g.K; ++k) f.out[(size_t)m * f.ldo + k] = gemm_A_fused(f, m, k);
+      g.A = f.out; g.lda = f.ldo; g.a_mc = 0; g.a0 = 0;
     }
     int Nt = g.N + g.aug_ones;
     const AdamOp* ad = g.adam ? &P.ops[g.adam - 1].adam : nullptr;     // fused optimiser epilogue
