@@ -128,7 +128,9 @@ extern "C" int ilsw_rb_create(ilsw_rb** out, int64_t capacity, int obs_dim, int 
   ilsw_rb* rb = new ilsw_rb();
   memset(rb, 0, sizeof(*rb));
   rb->capacity = capacity; rb->O = obs_dim; rb->A = act_dim;
-  rb->stride = round_up(2 * obs_dim + act_dim + 2, 4);
+  // rows start on 64-byte boundaries (the DRAM access granule): a sampled row then costs exactly its own blocks -- with the
+  // packed 16-byte-aligned layout of round 1 a 112-byte Hopper row dragged in 1.69x its size (profiles/r1_replay_bench.txt)
+  rb->stride = round_up(2 * obs_dim + act_dim + 2, 16);
   rb->host_w = 2 * obs_dim + act_dim + 5;
   cudaError_t e = cudaMalloc(&rb->rows, (size_t)capacity * rb->stride * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&rb->cold, (size_t)capacity * 4 * sizeof(float));
@@ -237,8 +239,73 @@ extern "C" int ilsw_rb_load_device(ilsw_rb* rb, const float* dev_hot_rows, int64
   return ILSW_OK;
 }
 
+// R3/R4 on the TMA unit: ring rows are 64-byte aligned (stride % 16 floats == 0, see ilsw_rb_create), so a sampled row is ONE
+// 1-D bulk copy (cp.async.bulk global -> shared, SASS UBLKCP) issued by one lane; a warp stages up to kGatherStageBytes
+// of rows behind its own mbarrier and, because consecutive batch rows are contiguous in the output tile, writes them back
+// with ONE bulk store (shared -> global).  No data passes through registers; only the sampled indices (Philox or caller
+// supplied) and the 16-byte cold rows do.  DRAM sees whole 64-byte blocks of exactly the sampled rows.
+constexpr int kGatherStageBytes = 4096;
+__global__ void __launch_bounds__(256) rb_gather_bulk_kernel(const float* __restrict__ rows, const float* __restrict__ cold,
+                                                             const int32_t* __restrict__ idx, int B, int stride, float* out_hot,
+                                                             float* out_cold, int64_t size, uint64_t seed, uint64_t counter,
+                                                             int32_t* idx_out, int rows_per_warp) {
+  extern __shared__ __align__(128) unsigned char gsm[];
+  __shared__ unsigned long long bars[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t row_bytes = (uint32_t)stride * 4u;
+  const uint32_t stage_bytes = (uint32_t)rows_per_warp * row_bytes;
+  const uint32_t sm_w = tc5::smem_u32(gsm) + (uint32_t)w * stage_bytes;
+  if (lane == 0) tc5::mbar_init(&bars[w], 1);
+  tc5::fence_barrier_init();
+  __syncthreads();
+  uint32_t phase = 0;
+  const int64_t warps_total = (int64_t)gridDim.x * 8;
+  for (int64_t base = ((int64_t)blockIdx.x * 8 + w) * rows_per_warp; base < B; base += warps_total * rows_per_warp) {
+    const int nrow = (int)min((int64_t)rows_per_warp, (int64_t)B - base);
+    int64_t r = 0;
+    if (lane < nrow) {
+      const int b = (int)(base + lane);
+      if (idx) r = idx[b];
+      else {
+        r = philox_index(seed, (uint32_t)counter, (uint32_t)b, (uint32_t)(counter >> 32) + 0x51u, (int)size);
+        if (idx_out) idx_out[b] = (int32_t)r;
+      }
+    }
+    if (lane == 0) tc5::mbar_arrive_expect_tx(&bars[w], (uint32_t)nrow * row_bytes);
+    __syncwarp();
+    if (lane < nrow) tc5::bulk_g2s(sm_w + (uint32_t)lane * row_bytes, rows + r * stride, row_bytes, &bars[w]);
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (out_cold && lane < nrow) c = __ldg(reinterpret_cast<const float4*>(cold) + r);
+    tc5::mbar_wait(&bars[w], phase);
+    phase ^= 1u;
+    if (lane == 0) {
+      tc5::bulk_s2g(out_hot + (size_t)base * stride, sm_w, (uint32_t)nrow * row_bytes);
+      tc5::bulk_commit();
+      tc5::bulk_wait_read();          // the staging block may be refilled once the store has read it
+    }
+    if (out_cold && lane < nrow) reinterpret_cast<float4*>(out_cold)[base + lane] = c;
+    __syncwarp();
+  }
+}
+
 static void launch_gather(const ilsw_rb* rb, const int32_t* idx, int B, float* out_hot, float* out_cold, uint64_t seed,
                           uint64_t counter, int32_t* idx_out, cudaStream_t st) {
+  static const bool legacy = getenv("ILSW_GATHER_LEGACY") != nullptr;   // development aid (tools/replay_bench.py): the register-path kernels
+  if (!legacy && (rb->stride & 15) == 0) {
+    const int row_bytes = rb->stride * 4;
+    int rpw = kGatherStageBytes / row_bytes;
+    rpw = rpw < 1 ? 1 : (rpw > 32 ? 32 : rpw);
+    const size_t smem = (size_t)8 * rpw * row_bytes;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    if (smem > 48 * 1024) cudaFuncSetAttribute(rb_gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t warps_needed = ((int64_t)B + rpw - 1) / rpw;
+    int64_t grid = (warps_needed + 7) / 8;
+    const int64_t cap = (int64_t)sms * 6;      // persistent-ish: up to 6 CTAs (48 warps, <= 192 KB of staged rows) per SM
+    if (grid > cap) grid = cap;
+    rb_gather_bulk_kernel<<<(unsigned)grid, 256, smem, st>>>(rb->rows, rb->cold, idx, B, rb->stride, out_hot, out_cold, rb->size, seed, counter, idx_out, rpw);
+    return;
+  }
   const int nv = rb->stride >> 2;           // 16-byte vectors per row: Hopper 7, Walker 11, Ant 58, Humanoid 193
   static const bool v1 = getenv("ILSW_GATHER_V1") != nullptr;   // development aid (tools/replay_bench.py): warp per row, no batching
   if (v1)

@@ -5,8 +5,8 @@ import numpy as np
 
 def hot_row_stride(obs_dim, act_dim):
     """Padded stride (floats) of one transition in the HBM ring:
-    [obs | act | reward | terminal | next_obs | pad->multiple of 4]."""
-    return (2 * obs_dim + act_dim + 2 + 3) // 4 * 4
+    [obs | act | reward | terminal | next_obs | pad->multiple of 16 floats = 64 bytes, the DRAM access granule]."""
+    return (2 * obs_dim + act_dim + 2 + 15) // 16 * 16
 
 
 def host_row_floats(obs_dim, act_dim):

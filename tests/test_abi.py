@@ -61,7 +61,7 @@ def test_row_layout_roundtrip():
     obs, act = rs.randn(n, O), rs.uniform(-1, 1, (n, A))
     rew, term, nobs = rs.randn(n, 1), (rs.rand(n, 1) < 0.3).astype(np.uint8), rs.randn(n, O)
     hot = layout.pack_hot_rows(obs, act, rew, term, nobs)
-    assert hot.shape == (n, layout.hot_row_stride(O, A)) == (n, 28)
+    assert hot.shape == (n, layout.hot_row_stride(O, A)) == (n, 32)
     back = layout.unpack_hot_rows(hot, O, A)
     np.testing.assert_array_equal(back["observations"], obs.astype(np.float32).astype(np.float64))
     np.testing.assert_array_equal(back["terminals"], term)
@@ -70,4 +70,4 @@ def test_row_layout_roundtrip():
     assert host.shape == (n, layout.host_row_floats(O, A))
     np.testing.assert_array_equal(host[:, :2 * O + A + 2], hot[:, :2 * O + A + 2])
     assert (host[:, -3:] == 1).all()
-    assert layout.hot_row_stride(376, 17) == 772 and layout.hot_row_stride(17, 6) == 44
+    assert layout.hot_row_stride(376, 17) == 784 and layout.hot_row_stride(17, 6) == 48      # 64-byte row alignment
