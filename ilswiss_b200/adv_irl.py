@@ -273,6 +273,23 @@ class DeviceAdvIRLMixin(_DeviceSamplerMixin):
         eng = getattr(self, "_ilsw_eng", None)
         if eng is None:
             self.policy_trainer.ensure_batch(self.policy_optim_batch_size, self.num_update_loops_per_train_call)
+            try:
+                eng = self._ilsw_build_engine()
+            except NotImplementedError as e:
+                # discriminators outside the fused program (simple_disc_models.py:29-38,51-93: BatchNorm / ReLU MLPDisc,
+                # ResNetAIRLDisc -- no shipped yaml uses them): the reference's own _do_reward_training /
+                # _do_policy_training run (adv_irl.py:133-314), with the discriminator and its optimiser as eager torch
+                # modules ON THE DEVICE, batches gathered in HBM (get_batch below) and every policy update still ONE fused
+                # SAC step (policy_trainer.train_step on the relabelled device batch)
+                import warnings
+                warnings.warn("ilswiss_b200: discriminator outside the fused AdvIRL program (%s): eager device "
+                              "discriminator + fused SAC steps" % (e,))
+                eng = False
+            self._ilsw_eng = eng
+        return eng
+
+    def _ilsw_build_engine(self):
+        if True:
             eng = AdvIRLEngine(
                 self.mode, self.discriminator, self.policy_trainer, self.expert_replay_buffer, self.replay_buffer,
                 state_only=self.state_only, disc_optim_batch_size=self.disc_optim_batch_size,
@@ -287,7 +304,6 @@ class DeviceAdvIRLMixin(_DeviceSamplerMixin):
                 rew_clip_min=self.rew_clip_min, rew_clip_max=self.rew_clip_max,
                 wrap_absorbing=getattr(self, "wrap_absorbing", False))
             self.disc_optimizer = eng.disc_optimizer
-            self._ilsw_eng = eng
         return eng
 
     def get_batch(self, batch_size, from_expert, keys=None):
@@ -297,6 +313,9 @@ class DeviceAdvIRLMixin(_DeviceSamplerMixin):
 
     def _do_training(self, epoch):
         eng = self._ilsw_engine()
+        if eng is False:
+            self.discriminator.to("cuda")
+            return super()._do_training(epoch)
         eng.disc_eval_statistics = self.disc_eval_statistics
         eng.do_training()
         self.disc_eval_statistics = eng.disc_eval_statistics

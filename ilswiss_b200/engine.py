@@ -12,6 +12,27 @@ from . import _abi, layout
 from ._lib import IlswError, check, load
 
 
+# NVTX ranges around every call that launches work (tracing) -- visible in nsys / ncu timelines;
+# ILSW_NVTX=0 removes them (two ~0.3 us calls per train call when no profiler is attached)
+import os as _os
+_NVTX = _os.environ.get("ILSW_NVTX", "1") != "0"
+
+
+class _Range:
+    __slots__ = ("name",)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+
+
 def _stream_ptr(stream=None):
     s = stream if stream is not None else torch.cuda.current_stream()
     return C.c_void_p(s.cuda_stream)
@@ -89,7 +110,8 @@ class ReplayRing:
             self.commit()
 
     def commit(self, stream=None):
-        check(self.lib.ilsw_rb_commit(self.h, _stream_ptr(stream)), "rb_commit")
+        with _Range("ilsw_rb_commit"):
+            check(self.lib.ilsw_rb_commit(self.h, _stream_ptr(stream)), "rb_commit")
         self.pending = 0
 
     def load_device(self, hot_rows):
@@ -105,7 +127,8 @@ class ReplayRing:
         B = idx.numel()
         hot = torch.empty((B, self.stride), dtype=torch.float32, device=idx.device)
         cold = torch.empty((B, 4), dtype=torch.float32, device=idx.device)
-        check(self.lib.ilsw_rb_gather(self.h, _ptr(idx), B, _ptr(hot), _ptr(cold), _stream_ptr()), "rb_gather")
+        with _Range("ilsw_rb_gather"):
+            check(self.lib.ilsw_rb_gather(self.h, _ptr(idx), B, _ptr(hot), _ptr(cold), _stream_ptr()), "rb_gather")
         return hot, cold
 
     def sample(self, batch_size, seed, counter):
@@ -205,10 +228,11 @@ class StepEngine:
             ring.pending = 0
         if expert_ring is not None:
             expert_ring.pending = 0
-        check(self.lib.ilsw_train(self.h, ring.h if ring is not None else None,
-                                  expert_ring.h if expert_ring is not None else None, n_steps,
-                                  C.byref(ij) if ij is not None else None, C.byref(bt) if bt is not None else None,
-                                  C.c_uint64(seed), stats_step, _stream_ptr()), "train")
+        with _Range("ilsw_train"):
+            check(self.lib.ilsw_train(self.h, ring.h if ring is not None else None,
+                                      expert_ring.h if expert_ring is not None else None, n_steps,
+                                      C.byref(ij) if ij is not None else None, C.byref(bt) if bt is not None else None,
+                                      C.c_uint64(seed), stats_step, _stream_ptr()), "train")
         self.last_steps = n_steps
 
     def set_her(self, desc=None):

@@ -129,7 +129,8 @@ def run_sac_loop(log_dir, device, epochs=2, env_num=2, O=11, A=3, B=64, hidden=2
             dropin.uninstall()
 
 
-def run_advirl_loop(log_dir, device, epochs=2, env_num=2, O=11, A=3, B=64, hidden=256, steps_per_epoch=200, seed=0):
+def run_advirl_loop(log_dir, device, epochs=2, env_num=2, O=11, A=3, B=64, hidden=256, steps_per_epoch=200, seed=0,
+                    disc_kind="mlp_tanh", use_grad_pen=True):
     """AdvIRL.train() (GAIL) the way run_scripts/adv_irl_exp_script.py builds it, with a synthetic expert buffer."""
     import torch
     from oracle import ref_shim
@@ -141,7 +142,7 @@ def run_advirl_loop(log_dir, device, epochs=2, env_num=2, O=11, A=3, B=64, hidde
     try:
         from rlkit.torch.common.networks import FlattenMlp
         from rlkit.torch.common.policies import ReparamTanhMultivariateGaussianPolicy
-        from rlkit.torch.algorithms.adv_irl.disc_models.simple_disc_models import MLPDisc
+        from rlkit.torch.algorithms.adv_irl.disc_models.simple_disc_models import MLPDisc, ResNetAIRLDisc
         import rlkit.torch.algorithms.sac.sac_alpha as sac_mod
         import rlkit.torch.algorithms.adv_irl.adv_irl as irl_mod
         import rlkit.data_management.env_replay_buffer as erb
@@ -162,14 +163,21 @@ def run_advirl_loop(log_dir, device, epochs=2, env_num=2, O=11, A=3, B=64, hidde
         qf1 = FlattenMlp(hidden_sizes=[hidden, hidden], input_size=O + A, output_size=1)
         qf2 = FlattenMlp(hidden_sizes=[hidden, hidden], input_size=O + A, output_size=1)
         policy = ReparamTanhMultivariateGaussianPolicy(hidden_sizes=[hidden, hidden], obs_dim=O, action_dim=A)
-        disc = MLPDisc(O + A, num_layer_blocks=2, hid_dim=128, hid_act="tanh", use_bn=False, clamp_magnitude=10.0)
+        if disc_kind == "mlp_tanh":          # every shipped yaml (exp_specs/gail/*.yaml:24-28): the fused program
+            disc = MLPDisc(O + A, num_layer_blocks=2, hid_dim=128, hid_act="tanh", use_bn=False, clamp_magnitude=10.0)
+        elif disc_kind == "mlp_bn_relu":     # the class defaults (simple_disc_models.py:9-16)
+            disc = MLPDisc(O + A, num_layer_blocks=2, hid_dim=128, hid_act="relu", use_bn=True, clamp_magnitude=10.0)
+        elif disc_kind == "resnet":
+            disc = ResNetAIRLDisc(O + A, num_layer_blocks=3, hid_dim=128, hid_act="relu", use_bn=True, clamp_magnitude=10.0)
+        else:
+            raise ValueError(disc_kind)
         trainer = sac_mod.SoftActorCritic(policy=policy, qf1=qf1, qf2=qf2, env=env, reward_scale=2.0, discount=0.99, policy_lr=3e-4,
                                           qf_lr=3e-4, soft_target_tau=0.005, beta_1=0.25)
         algorithm = irl_mod.AdvIRL(mode="gail2", discriminator=disc, policy_trainer=trainer, expert_replay_buffer=expert,
                                    state_only=False, disc_optim_batch_size=B, policy_optim_batch_size=B,
                                    policy_optim_batch_size_from_expert=0, num_update_loops_per_train_call=10,
                                    num_disc_updates_per_loop_iter=1, num_policy_updates_per_loop_iter=1, disc_lr=3e-4,
-                                   disc_momentum=0.9, use_grad_pen=True, grad_pen_weight=8.0, env=env, training_env=train_env,
+                                   disc_momentum=0.9, use_grad_pen=use_grad_pen, grad_pen_weight=8.0, env=env, training_env=train_env,
                                    eval_env=eval_env, exploration_policy=policy, num_epochs=epochs - 1,
                                    num_steps_per_epoch=steps_per_epoch, num_steps_between_train_calls=20, num_steps_per_eval=60,
                                    max_path_length=1000, min_steps_before_training=60, replay_buffer_size=5000, freq_saving=1,

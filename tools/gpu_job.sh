@@ -17,6 +17,7 @@ for step in "$@"; do
     pp_sac_stamps) timeout 300 python tools/phase_profile.py sac_hopper gail_walker > gpurun_out/${TAG}_pp_sac_stamps.txt 2>&1 ;;
     ncu_td3) timeout 600 ncu --set full --clock-control none --import-source on -k regex:ilsw_engine_kernel -s 2 -c 1 -f -o gpurun_out/${TAG}_ncu_td3 python tools/ncu_target.py td3_humanoid 4 3 > gpurun_out/${TAG}_ncu_td3.log 2>&1 ;;
     ncu_sac) timeout 600 ncu --set full --clock-control none --import-source on -k regex:ilsw_engine_kernel -s 2 -c 1 -f -o gpurun_out/${TAG}_ncu_sac python tools/ncu_target.py sac_hopper 10 3 > gpurun_out/${TAG}_ncu_sac.log 2>&1 ;;
+    sanitize) timeout 3000 tools/sanitize.sh ${TAG} > gpurun_out/${TAG}_sanitize_summary.txt 2>&1 ;;
     ab_sac) timeout 600 tools/ab.sh "sac_hopper --no-tile-stamps" variants/r1.so ilswiss_b200/csrc/libilswiss_b200.so variants/r1.so ilswiss_b200/csrc/libilswiss_b200.so > gpurun_out/${TAG}_ab_sac.txt 2>&1 ;;
     smi) nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.draw,temperature.gpu --format=csv > gpurun_out/${TAG}_smi.txt 2>&1 ;;
     *) echo "unknown step $step" ;;
