@@ -101,8 +101,8 @@ struct Builder {
     return nullptr;
   }
   static ShadowRef shadow_of(const MlpPtrs* n) {
-    ShadowRef r; r.ptr = nullptr; r.in = r.ld = r.n = 0;
-    if (n && n->w0p) { r.ptr = n->w0p; r.in = n->in_dim; r.ld = n->ld_w0p; r.n = n->hid * n->in_dim; }
+    ShadowRef r; r.ptr = nullptr; r.in = r.ld = r.n = 0; r.inv_in = 0.f;
+    if (n && n->w0p) { r.ptr = n->w0p; r.in = n->in_dim; r.ld = n->ld_w0p; r.n = n->hid * n->in_dim; r.inv_in = 1.0f / (float)n->in_dim; }
     return r;
   }
   void shadow_refresh(const MlpPtrs& n) {

@@ -85,9 +85,15 @@ struct GemmOp {
 // 16-byte-aligned copy of a first-layer weight matrix W0[hid x in] whose rows are not (in % 4 != 0: critics on Hopper /
 // Humanoid ...): row stride `ld` = in rounded up to 4.  TMA cannot address the packed nn.Linear layout, so the tcgen05
 // programs read the copy; whoever writes parameter element i < n (= hid * in) also writes its copy.
-struct ShadowRef { float* ptr; int in, ld, n; };
+struct ShadowRef { float* ptr; int in, ld, n; float inv_in; };
 ILSW_HD void shadow_store(const ShadowRef& sh, int i, float v) {
-  if (sh.ptr && i < sh.n) { const int r = i / sh.in; sh.ptr[(size_t)r * sh.ld + (i - r * sh.in)] = v; }
+  if (sh.ptr && i < sh.n) {
+    // row = i / in without the integer-division sequence: float estimate (exact for i < 2^23) + one correction step
+    int r = (int)(((float)i + 0.5f) * sh.inv_in);
+    int c = i - r * sh.in;
+    if (c < 0) { --r; c += sh.in; } else if (c >= sh.in) { ++r; c -= sh.in; }
+    sh.ptr[(size_t)r * sh.ld + c] = v;
+  }
 }
 
 struct AdamOp {
