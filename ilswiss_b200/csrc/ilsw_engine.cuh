@@ -25,6 +25,13 @@
 #ifndef ILSW_VECRAG
 #define ILSW_VECRAG 1
 #endif
+// epilogue inputs (bias / mask source / previous value) of a tile are prefetched with cp.async into a shared scratch
+// instead of registers: at the 255-register cap the twelve values were spilled to local memory right after their loads,
+// and every spill store waits for its load -- four serialised L2 round trips (~1.3 us) in the prologue of EVERY tile
+// (ncu source view, profiles/r2_ncu_engine_sac_hopper_prefix.txt: STL ... stall_long_sb)
+#ifndef ILSW_EIN_CPASYNC
+#define ILSW_EIN_CPASYNC 1
+#endif
 
 namespace ilsw {
 
@@ -344,8 +351,9 @@ template <int KC> struct TcGeom {
 constexpr int tc_smem_floats(int ctas) { return ctas == 2 ? TcGeom<128>::kSmemFloats : TcGeom<256>::kSmemFloats; }
 // bytes of the GEMM staging area at the start of dynamic shared memory; the tcgen05 engine variant (one CTA per SM)
 // also fits the TMA stages of ilsw_tc5.cuh (+ 1 KB to align them to the 1024-byte swizzle atom)
+constexpr int kEpiScratchFloats = 12 * kThreads;      // [12 slots][256 threads]: bias, mask source, previous value x 4 columns
 constexpr size_t engine_staging_bytes(int ctas, bool tc5) {
-  return tc5 ? (size_t)tc5::Geom<kTc5BN>::kSmemBytes + 1024 : (size_t)tc_smem_floats(ctas) * sizeof(float);
+  return tc5 ? (size_t)tc5::Geom<kTc5BN>::kSmemBytes + 1024 : (size_t)(tc_smem_floats(ctas) + kEpiScratchFloats) * sizeof(float);
 }
 // The engine is compiled in two occupancy variants: CTAS=1 (255 registers/thread, lowest single-job
 // latency: B=256 workloads) and CTAS=2 (128 registers, twice the tile parallelism per SM: B=1024).
@@ -540,7 +548,7 @@ __device__ __noinline__ void tc_fill_stage(const GemmOp& o, float* stage, int m0
 // tn == 0 tile -- to L0FuseOp::out for the backward pass.  (A first version on the SIMT pipes, thread per column with W0^T
 // staged in shared memory, took 8 us per tile: profiles/r2_phase_profile_l0_simt.txt.)
 template <int KC>
-__device__ __forceinline__ void tc_produce_l0(const L0FuseOp& f, int M, float* panel, int m0, int k0, int klen, bool store_out, int mode) {
+__device__ __noinline__ void tc_produce_l0(const L0FuseOp& f, int M, float* panel, int m0, int k0, int klen, bool store_out, int mode) {
   constexpr int kKS = TcGeom<KC>::kKS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
   const int kpad = (klen + 15) & ~15;
@@ -716,7 +724,22 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
         tc_produce_l0<KC>(*fz, o.M, smem + ((st + 1) & 1) * kTcStageFloats, m0, k0, min(kKC, o.K - k0), tn == 0, mode);
     }
     if (st < 0) {
-#if !ILSW_EIN_FIRST
+#if ILSW_EIN_CPASYNC
+      {
+        const unsigned sc = sbase + 4u * (unsigned)(TcGeom<KC>::kSmemFloats + tid);
+        if (er < o.M) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (ec + i < Nt) {
+              if (o.bias) cp_async4(sc + 4u * (unsigned)(i * kThreads), o.bias + ec + i);
+              if (o.mask != ACT_NONE) cp_async4(sc + 4u * (unsigned)((4 + i) * kThreads), o.H + (size_t)er * o.ldh + ec + i);
+              if (o.accumulate) cp_async4(sc + 4u * (unsigned)((8 + i) * kThreads), o.C + (size_t)er * o.ldc + ec + i);
+            }
+          }
+        }
+        cp_async_commit();
+      }
+#elif !ILSW_EIN_FIRST
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         if (er < o.M && ec + i < Nt) ein[i] = epi_load(o, er, ec + i);
@@ -797,6 +820,17 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
   }
   ILSW_TSTAMP(3);
   const float outv[4] = {sum.x, sum.y, sum.z, sum.w};
+#if ILSW_EIN_CPASYNC
+  {
+    const float* sc = smem + TcGeom<KC>::kSmemFloats + tid;       // landed with the last stage's cp.async.wait_group 0
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ein[i].bias = o.bias ? sc[i * kThreads] : 0.f;
+      ein[i].h = (o.mask != ACT_NONE) ? sc[(4 + i) * kThreads] : 0.f;
+      ein[i].prev = o.accumulate ? sc[(8 + i) * kThreads] : 0.f;
+    }
+  }
+#endif
   const bool ad_sh = ad && adam_has_shadow(*ad);      // aligned W0 copies to maintain (tcgen05 programs only)
 #if !ILSW_ADAM_PREFETCH
   int gi[4] = {-1, -1, -1, -1}, gib = -1;
@@ -1036,7 +1070,8 @@ template <int CTAS, bool TC5>
 __global__ void __launch_bounds__(kThreads, CTAS)
 ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierState* bar, Replica rp_param) {
   static_assert(!TC5 || CTAS == 1, "the tcgen05 variant runs one CTA per SM");
-  static_assert(!TC5 || engine_staging_bytes(1, true) >= (size_t)tc_smem_floats(1) * sizeof(float), "staging area also serves the mma.sync tile");
+  static_assert(!TC5 || engine_staging_bytes(1, true) >= (size_t)(tc_smem_floats(1) + kEpiScratchFloats) * sizeof(float), "staging area also serves the mma.sync tile");
+  static_assert(!TC5 || (size_t)(tc_smem_floats(1) + kEpiScratchFloats) * sizeof(float) + 1024 <= (size_t)tc5::kStages * tc5::Geom<kTc5BN>::kStageBytes, "the all-ones tile of the tcgen05 path lies beyond the mma.sync tile's scratch");
   unsigned char* dyn_smem = reinterpret_cast<unsigned char*>(ilsw_dyn_smem_f);
   float* smem = ilsw_dyn_smem_f;
   // launch arguments live in shared memory: row kernels take them by reference and the replica tables are indexed
