@@ -69,19 +69,44 @@ struct ilsw_rb {
   cudaStream_t last_stream;   // compute stream of the latest commit (scatter kernels run there, never on the copy stream)
 };
 
-// one warp per staged transition: staging row -> hot row at (top+i) % capacity, cold row
+// R2 commit: staged transitions -> hot rows at (top + i) % capacity (+ cold rows).  The destination is a CONTIGUOUS range of
+// ring rows (at most one wrap), so the kernel is a flat, fully coalesced copy over the destination floats: thread -> output
+// float e = row * stride + k, 4 independent elements per thread in flight; the source is the packed staging row (host_w
+// floats, 4-byte aligned).  (Round 1: one warp per row, one dependent load -> store and a 64-bit modulo per row: 0.12-0.35 of
+// the HBM roofline, profiles/r1_replay_bench.txt.)
 __global__ void __launch_bounds__(256) rb_scatter_kernel(const float* __restrict__ staging, int64_t n, float* rows,
                                                           float* cold, int64_t top, int64_t capacity, int O, int A,
                                                           int stride, int host_w) {
-  const int lane = threadIdx.x & 31;
-  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= n) return;
-  const float* src = staging + i * host_w;
-  const int64_t slot = (top + i) % capacity;
-  float* dst = rows + slot * stride;
   const int hot = 2 * O + A + 2;
-  for (int k = lane; k < stride; k += 32) dst[k] = k < hot ? src[k] : 0.f;
-  if (lane < 4) cold[slot * 4 + lane] = lane < 3 ? src[hot + lane] : 0.f;
+  const int64_t total = n * stride;
+  constexpr int U = 4;
+  const int64_t e0 = ((int64_t)blockIdx.x * blockDim.x * U) + threadIdx.x;
+  float v[U];
+  int64_t slot[U]; int kk[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t e = e0 + (int64_t)u * blockDim.x;
+    v[u] = 0.f; slot[u] = -1; kk[u] = 0;
+    if (e < total) {
+      const int64_t i = e / stride;
+      const int k = (int)(e - i * stride);
+      int64_t sl = top + i;
+      if (sl >= capacity) sl -= capacity;           // i < capacity (commits are chunked): one wrap at most
+      slot[u] = sl; kk[u] = k;
+      if (k < hot) v[u] = __ldg(staging + i * host_w + k);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (slot[u] >= 0) rows[slot[u] * stride + kk[u]] = v[u];
+  // cold rows: 4 floats per transition (absorbing flags / timeout), one thread per float
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n * 4) {
+    const int64_t i = c >> 2; const int l = (int)(c & 3);
+    int64_t sl = top + i;
+    if (sl >= capacity) sl -= capacity;
+    cold[sl * 4 + l] = l < 3 ? __ldg(staging + i * host_w + hot + l) : 0.f;
+  }
 }
 
 // R3/R4: uniform sample + minibatch gather.  A group of LPR lanes (8 / 16 / 32, chosen from the row length) owns one sampled
@@ -208,9 +233,9 @@ extern "C" int ilsw_rb_commit(ilsw_rb* rb, void* stream) {
   rb->last_stream = st;
   if (rb->staged_valid) CU(cudaStreamWaitEvent(st, rb->staged, 0));
   const int64_t n = rb->pending;
-  const int wpb = 8;
-  rb_scatter_kernel<<<(unsigned)((n + wpb - 1) / wpb), 256, 0, st>>>(rb->staging, n, rb->rows, rb->cold, rb->top,
-                                                                     rb->capacity, rb->O, rb->A, rb->stride, rb->host_w);
+  const int64_t per_cta = 256 * 4;                 // destination floats per CTA (rb_scatter_kernel: 4 per thread)
+  rb_scatter_kernel<<<(unsigned)((n * rb->stride + per_cta - 1) / per_cta), 256, 0, st>>>(rb->staging, n, rb->rows, rb->cold, rb->top,
+                                                                                        rb->capacity, rb->O, rb->A, rb->stride, rb->host_w);
   CU(cudaGetLastError());
   // the staging area may be overwritten by the next append on the copy stream only after this
   // scatter has run: make later copies wait on it
@@ -260,17 +285,24 @@ __global__ void __launch_bounds__(256) rb_gather_bulk_kernel(const float* __rest
   __syncthreads();
   uint32_t phase = 0;
   const int64_t warps_total = (int64_t)gridDim.x * 8;
-  for (int64_t base = ((int64_t)blockIdx.x * 8 + w) * rows_per_warp; base < B; base += warps_total * rows_per_warp) {
+  const int64_t step = warps_total * rows_per_warp;
+  int64_t base = ((int64_t)blockIdx.x * 8 + w) * rows_per_warp;
+  // caller-supplied indices are read one iteration ahead: the index load (a DRAM round trip of its own) then overlaps the
+  // row copies of the current iteration instead of preceding them (gather(idx) ran at 0.66 vs 0.78 for the Philox mode)
+  int32_t r_pre = 0;
+  if (idx && base + lane < B && lane < rows_per_warp) r_pre = __ldg(idx + base + lane);
+  for (; base < B; base += step) {
     const int nrow = (int)min((int64_t)rows_per_warp, (int64_t)B - base);
     int64_t r = 0;
     if (lane < nrow) {
       const int b = (int)(base + lane);
-      if (idx) r = idx[b];
+      if (idx) r = r_pre;
       else {
         r = philox_index(seed, (uint32_t)counter, (uint32_t)b, (uint32_t)(counter >> 32) + 0x51u, (int)size);
         if (idx_out) idx_out[b] = (int32_t)r;
       }
     }
+    if (idx && base + step + lane < B && lane < rows_per_warp) r_pre = __ldg(idx + base + step + lane);
     if (lane == 0) tc5::mbar_arrive_expect_tx(&bars[w], (uint32_t)nrow * row_bytes);
     __syncwarp();
     if (lane < nrow) tc5::bulk_g2s(sm_w + (uint32_t)lane * row_bytes, rows + r * stride, row_bytes, &bars[w]);
@@ -291,7 +323,10 @@ __global__ void __launch_bounds__(256) rb_gather_bulk_kernel(const float* __rest
 static void launch_gather(const ilsw_rb* rb, const int32_t* idx, int B, float* out_hot, float* out_cold, uint64_t seed,
                           uint64_t counter, int32_t* idx_out, cudaStream_t st) {
   static const bool legacy = getenv("ILSW_GATHER_LEGACY") != nullptr;   // development aid (tools/replay_bench.py): the register-path kernels
-  if (!legacy && (rb->stride & 15) == 0) {
+  // rows up to 512 B go through the TMA unit (one bulk copy per row: Hopper 128 B 0.78 vs 0.65 of the HBM roofline, Walker
+  // 192 B 0.80 vs 0.55); longer rows (Ant 960 B, Humanoid 3136 B) keep a warp's 128-bit loads busy on their own and the
+  // register path wins (0.90 vs 0.83, 0.93 vs 0.88) -- profiles/r2_replay_bench.txt
+  if (!legacy && (rb->stride & 15) == 0 && rb->stride * 4 <= 512) {
     const int row_bytes = rb->stride * 4;
     int rpw = kGatherStageBytes / row_bytes;
     rpw = rpw < 1 ? 1 : (rpw > 32 ? 32 : rpw);
@@ -415,7 +450,11 @@ static int trainer_build(ilsw_trainer* tr) {
   tr->tc5 = (tc5_wanted(tr->spec) && tmap_encoder() != nullptr && !(tv && atoi(tv) == 0)) ? 1 : 0;
   Bump measure;
   Program* tmp = new Program();
-  rc = assemble(*tmp, tr->spec, measure, tr->tc5 != 0);
+  const char* fv = getenv("ILSW_FUSE_L0");
+  // first-layer fusion is OFF by default: measured on the B200 it lengthens the fused phases more than the saved phase +
+  // barrier gives back (SAC Hopper 149.9 vs 147.0 us/step, GAIL Walker 272.8 vs 263.9; profiles/r2_ab_fuse_l0.txt)
+  const bool fuse_l0 = fv ? atoi(fv) != 0 : false;
+  rc = assemble(*tmp, tr->spec, measure, tr->tc5 != 0, fuse_l0);
   delete tmp;
   if (rc) return fail(rc, "program assembly failed (too many phases/ops?)");
   // a rebuild (attach_disc after load_snapshot) keeps the device-resident optimiser state of alpha
@@ -432,15 +471,33 @@ static int trainer_build(ilsw_trainer* tr) {
   CU(cudaMemset(tr->scratch, 0, tr->scratch_bytes));
   Bump mem;
   mem.base = tr->scratch;
-  rc = assemble(tr->host_prog, tr->spec, mem, tr->tc5 != 0);
+  rc = assemble(tr->host_prog, tr->spec, mem, tr->tc5 != 0, fuse_l0);
   if (rc) return fail(rc, "program assembly failed");
-  if (tr->tc5) {           // TMA tensor maps of every tcgen05 GEMM operand (box shapes: ilsw_tc5.cuh)
+  // TMA panels of the mma.sync tile (tensor-core precision modes): every operand TMA can address gets a map with
+  // {32 floats, 32 rows} boxes (k-contiguous: plain 128-byte swizzle; m/n-contiguous: 32-byte atoms, see gemm_tile_tc)
+  const char* tpv = getenv("ILSW_TMA_PANELS");
+  const bool tma_panels = tmap_encoder() != nullptr && tr->spec.cfg.gemm_precision != 0 && !(tpv && atoi(tpv) == 0);
+  if (tr->tc5 || tma_panels) {           // TMA tensor maps of the GEMM operands (tcgen05 box shapes: ilsw_tc5.cuh)
     static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
     if (!tr->tmaps) CU(cudaMalloc(&tr->tmaps, sizeof(CUtensorMap) * 2 * kMaxOps));
     std::vector<CUtensorMap> maps(2 * kMaxOps);
     Program& P = tr->host_prog;
     for (int i = 0; i < P.n_ops; ++i) {
-      if (P.ops[i].kind != OP_GEMM || !P.ops[i].gemm.tc5) continue;
+      if (P.ops[i].kind != OP_GEMM) continue;
+      if (!P.ops[i].gemm.tc5) {
+        GemmOp& g = P.ops[i].gemm;
+        g.tma = 0;
+        if (!tma_panels || gemm_is_skinny(g)) continue;
+        if (!g.a0 && tmap_operand_ok(g.A, g.lda) &&
+            (g.a_mc ? make_tmap_2d(&maps[2 * i], g.A, g.lda, g.M, g.K, 32, true) : make_tmap_2d(&maps[2 * i], g.A, g.lda, g.K, g.M, 32, false)) == 0)
+          g.tma |= 1;
+        if (tmap_operand_ok(g.B, g.ldb) &&
+            (g.b_nc ? make_tmap_2d(&maps[2 * i + 1], g.B, g.ldb, g.N, g.K, 32, true) : make_tmap_2d(&maps[2 * i + 1], g.B, g.ldb, g.K, g.N, 32, false)) == 0)
+          g.tma |= 2;
+        g.tmapA = reinterpret_cast<const CUtensorMap*>(tr->tmaps) + 2 * i;
+        g.tmapB = reinterpret_cast<const CUtensorMap*>(tr->tmaps) + 2 * i + 1;
+        continue;
+      }
       GemmOp& g = P.ops[i].gemm;
       const int ra = g.a_mc ? make_tmap_2d(&maps[2 * i], g.A, g.lda, g.M, g.K, 32, true) : make_tmap_2d(&maps[2 * i], g.A, g.lda, g.K, g.M, tc5::kBM, false);
       const int rb = g.b_nc ? make_tmap_2d(&maps[2 * i + 1], g.B, g.ldb, g.N, g.K, 32, true) : make_tmap_2d(&maps[2 * i + 1], g.B, g.ldb, g.K, g.N, kTc5BN, false);

@@ -29,6 +29,13 @@
 // instead of registers: at the 255-register cap the twelve values were spilled to local memory right after their loads,
 // and every spill store waits for its load -- four serialised L2 round trips (~1.3 us) in the prologue of EVERY tile
 // (ncu source view, profiles/r2_ncu_engine_sac_hopper_prefix.txt: STL ... stall_long_sb)
+// cross-proxy fence in front of the TMA panel loads of the mma.sync tile.  The operands were written with generic stores by
+// OTHER CTAs in an earlier phase and published through the grid barrier (release / acquire at gpu scope); the TMA unit reads
+// them from L2, where those stores are already performed.  The tcgen05 tile has always issued its loads without the fence
+// (parity green on every TD3 / HER case), so it is off by default; -DILSW_TMA_GLOBAL_FENCE=1 restores it.
+#ifndef ILSW_TMA_GLOBAL_FENCE
+#define ILSW_TMA_GLOBAL_FENCE 0
+#endif
 #ifndef ILSW_EIN_CPASYNC
 #define ILSW_EIN_CPASYNC 1
 #endif
@@ -56,6 +63,11 @@ struct Replica {
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
@@ -110,7 +122,14 @@ __device__ __forceinline__ bool grid_barrier(BarrierState* bar, unsigned nblocks
     red_add_release_gpu(&bar->count, 1u);
     long long t0 = 0;
     unsigned spins = 0;
+#ifndef ILSW_BARRIER_RELAXED
+#define ILSW_BARRIER_RELAXED 0
+#endif
+#if ILSW_BARRIER_RELAXED
+    while ((int)(ld_relaxed_gpu(&bar->count) - target) < 0) {
+#else
     while ((int)(ld_acquire_gpu(&bar->count) - target) < 0) {
+#endif
       if ((++spins & 1023u) == 0u) {
         if (t0 == 0) t0 = clock64();
         long long dt = clock64() - t0;
@@ -353,7 +372,8 @@ constexpr int tc_smem_floats(int ctas) { return ctas == 2 ? TcGeom<128>::kSmemFl
 // also fits the TMA stages of ilsw_tc5.cuh (+ 1 KB to align them to the 1024-byte swizzle atom)
 constexpr int kEpiScratchFloats = 12 * kThreads;      // [12 slots][256 threads]: bias, mask source, previous value x 4 columns
 constexpr size_t engine_staging_bytes(int ctas, bool tc5) {
-  return tc5 ? (size_t)tc5::Geom<kTc5BN>::kSmemBytes + 1024 : (size_t)(tc_smem_floats(ctas) + kEpiScratchFloats) * sizeof(float);
+  // + 1 KB: the tile's staging area starts on a 1024-byte boundary (TMA boxes with the 128-byte swizzle)
+  return tc5 ? (size_t)tc5::Geom<kTc5BN>::kSmemBytes + 1024 : (size_t)(tc_smem_floats(ctas) + kEpiScratchFloats) * sizeof(float) + 1024;
 }
 // The engine is compiled in two occupancy variants: CTAS=1 (255 registers/thread, lowest single-job
 // latency: B=256 workloads) and CTAS=2 (128 registers, twice the tile parallelism per SM: B=1024).
@@ -390,7 +410,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 // Explicit 32-bit shared addresses, the 16 loads issued back to back.
 struct FragSet { float a[8]; float b[8]; };
 __device__ __forceinline__ void fragset_load(FragSet& f, unsigned ap, unsigned a_row8, unsigned a_k4, unsigned a_mt,
-                                             unsigned bp, unsigned b_k4, unsigned b_nt) {
+                                             unsigned bp, unsigned b_k4, unsigned b_nt, unsigned b_nt2) {
   asm volatile(
       "ld.shared.f32 %0, [%8];\n\t"
       "ld.shared.f32 %1, [%9];\n\t"
@@ -415,7 +435,7 @@ __device__ __forceinline__ void fragset_load(FragSet& f, unsigned ap, unsigned a
       "ld.shared.f32 %7, [%15];"
       : "=f"(f.b[0]), "=f"(f.b[1]), "=f"(f.b[2]), "=f"(f.b[3]), "=f"(f.b[4]), "=f"(f.b[5]), "=f"(f.b[6]), "=f"(f.b[7])
       : "r"(bp), "r"(bp + b_k4), "r"(bp + b_nt), "r"(bp + b_nt + b_k4),
-        "r"(bp + 2u * b_nt), "r"(bp + 2u * b_nt + b_k4), "r"(bp + 3u * b_nt), "r"(bp + 3u * b_nt + b_k4)
+        "r"(bp + b_nt2), "r"(bp + b_nt2 + b_k4), "r"(bp + b_nt2 + b_nt), "r"(bp + b_nt2 + b_nt + b_k4)
       : "memory");
 }
 __device__ __forceinline__ void mma_tf32p(float* d, const uint32_t* a, const uint32_t* b) {
@@ -472,13 +492,14 @@ __device__ __forceinline__ void sts_u32(unsigned addr, float v) {
 //         of a stage are in flight together.  (.ca allocates in L1: safe because every grid
 //         barrier's ld.acquire.gpu invalidates the L1 -- CCTL.IVALL -- before a new phase reads.)
 template <int KC>
-__device__ __noinline__ void tc_fill_stage(const GemmOp& o, float* stage, int m0, int n0, int k0, int klen, bool vecA, bool vecB) {
+__device__ __noinline__ void tc_fill_stage(const GemmOp& o, float* stage, int m0, int n0, int k0, int klen, bool vecA, bool vecB, int skip_mask) {
   constexpr int kKS = TcGeom<KC>::kKS, kOperandFloats = TcGeom<KC>::kOperandFloats;
   constexpr int kVecPerRow = KC / 4, kVecShift = (KC == 256 ? 6 : 5), kVecIters = 32 * KC / 4 / kThreads;
   const int tid = threadIdx.x;
   const int kpad = (klen + 15) & ~15;    // zero padded to TWO MMA k-steps (the k loop is unrolled by 2, unguarded)
 #pragma unroll 1
   for (int op = o.a0 ? 1 : 0; op < 2; ++op) {      // a fused first layer produces its own A panel (tc_produce_l0)
+    if ((skip_mask >> op) & 1) continue;             // this panel arrives through the TMA unit (tc_tma_stage)
     const bool isB = op != 0;
     const bool contig_k = isB ? !o.b_nc : !o.a_mc;
     const float* base = isB ? o.B : o.A;
@@ -631,6 +652,40 @@ __device__ __noinline__ void tc_produce_l0(const L0FuseOp& f, int M, float* pane
   }
 }
 
+// TMA panels (GemmOp::tma): the panel of a stage is a row of boxes {32 floats, 32 rows} of the operand's tensor map, 4 KB
+// each, box j = k range [32 j, 32 j + 32) of the stage.  Warp w issues box w of both operands (one elected lane: two
+// instructions per warp instead of sixteen cp.async per thread -- the panel issue was 1.7 us of a 6.3 us tile,
+// profiles/r2_phase_profile.txt); out-of-range rows / k's are zero-filled by the TMA unit, ragged extents need no code.
+//   k-contiguous operand (element(r,k) = base[r*ld + k]): box = [32 r][32 k], SWIZZLE_128B:
+//       byte(r,k) = (k>>5)*4096 + r*128 + ((((k&31)>>2) ^ (r&7)) << 4) + (k&3)*4
+//   m/n-contiguous operand (element(r,k) = base[k*ld + r]): box = [32 k][32 r], SWIZZLE_128B_ATOM_32B:
+//       byte(r,k) = (k>>5)*4096 + (k&31)*128 + (((r>>3) ^ (k&3)) << 5) + (r&7)*4
+// Both keep the m16n8k8 fragment loads bank-conflict free, and because warp w owns k-steps w, w + 8, ... the swizzle
+// terms are loop invariant per lane (see the address set-up in gemm_tile_tc).
+struct TmaState { unsigned long long* bar; unsigned par; };     // two stage barriers; bit s of par = phase parity of bar[s]
+__device__ __forceinline__ void tc_tma_stage(const GemmOp& o, unsigned stage_addr, unsigned operand_bytes, int m0, int n0, int k0,
+                                             int klen, unsigned long long* bar) {
+  const int warp = threadIdx.x >> 5;
+  const int nb = (klen + 31) >> 5;                 // boxes per operand
+  const int nops = (o.tma & 1) + ((o.tma >> 1) & 1);
+  if (threadIdx.x == 0) tc5::mbar_arrive_expect_tx(bar, (unsigned)(nb * nops) * 4096u);
+  if (warp < nb && tc5::elect_one()) {
+#if ILSW_TMA_GLOBAL_FENCE
+    asm volatile("fence.proxy.async.global;" ::: "memory");     // operands written by generic stores of the previous phase
+#endif
+    const int kk = k0 + 32 * warp;
+    if (o.tma & 1) {
+      if (o.a_mc) tc5::tma_load_2d(stage_addr + 4096u * warp, o.tmapA, m0, kk, bar);
+      else tc5::tma_load_2d(stage_addr + 4096u * warp, o.tmapA, kk, m0, bar);
+    }
+    if (o.tma & 2) {
+      if (o.b_nc) tc5::tma_load_2d(stage_addr + operand_bytes + 4096u * warp, o.tmapB, n0, kk, bar);
+      else tc5::tma_load_2d(stage_addr + operand_bytes + 4096u * warp, o.tmapB, kk, n0, bar);
+    }
+  }
+  __syncwarp();
+}
+
 constexpr int kRedLd = 36;                    // row stride of a per-warp partial tile (floats; 16-byte aligned rows)
 constexpr int kRedFloats = 8 * 32 * kRedLd;   // 36 KB: fits one staging stage of either occupancy variant
 
@@ -641,10 +696,10 @@ constexpr int kRedFloats = 8 * 32 * kRedLd;   // 36 KB: fits one staging stage o
 // (fixed order: bit-reproducible).  Measured predecessor (one 16x8 accumulator per warp over the full K,
 // 96 dependent MMAs): 3.3 us of a 5.9 us tile.
 template <int KC>
-__device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* smem, int mode, int prof_phase, const AdamOp* ad, const AdamCoef* cf, const PushCtx* push, const L0FuseOp* fz) {
+__device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* smem, int mode, int prof_phase, const AdamOp* ad, const AdamCoef* cf, const PushCtx* push, const L0FuseOp* fz, TmaState& tma) {
   constexpr int kKC = KC, kKS = TcGeom<KC>::kKS, kOperandFloats = TcGeom<KC>::kOperandFloats, kTcStageFloats = TcGeom<KC>::kStageFloats;
   static_assert(kRedFloats <= TcGeom<KC>::kStageFloats, "partial tiles must fit one stage");
-  const GemmOp o = og;                       // registers / local copy: the op descriptor lives in shared memory
+  const GemmOp o = og;                       // registers / local copy: the op descriptor lives in shared memory (reading it in place measured 4 us/step slower)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tm = tile / o.tiles_n, tn = tile - tm * o.tiles_n;
   const int m0 = tm * 32, n0 = tn * 32;
@@ -708,17 +763,38 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
 #endif
   // fragment addressing (32-bit shared addresses, bytes)
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
-  const unsigned a_off = 4u * (a_kc ? g * kKS + q : q * kMS + g);
-  const unsigned b_off = 4u * (b_kc ? g * kKS + q : q * kMS + g);
-  const unsigned a_row8 = 4u * (a_kc ? 8 * kKS : 8), a_k4 = 4u * (a_kc ? 4 : 4 * kMS), a_k8 = 2u * a_k4;
-  const unsigned a_mt = 2u * a_row8;                                   // next m16 tile
-  const unsigned b_k4 = 4u * (b_kc ? 4 : 4 * kMS), b_k8 = 2u * b_k4;
-  const unsigned b_nt = 4u * (b_kc ? 8 * kKS : 8);                     // next n8 tile
+  const bool a_tma = (o.tma & 1) != 0, b_tma = (o.tma & 2) != 0;
+  // per operand: offset of this lane's first fragment word for k-step `warp` (x_w), advance per 8 k-steps (x_it), and the
+  // offsets between the fragment words of one k-step.  The TMA layouts are swizzled; all offsets wrap in 32 bits.
+  unsigned a_w, a_it, a_row8, a_k4, a_mt, b_w, b_it, b_k4, b_nt, b_nt2;
+  if (a_tma) {
+    a_it = 8192u;
+    if (a_kc) { a_w = (unsigned)((warp >> 2) * 4096 + g * 128 + (((2 * (warp & 3)) ^ g) << 4) + q * 4); a_row8 = 1024u; a_mt = 2048u; a_k4 = (g & 1) ? 0u - 16u : 16u; }
+    else { a_w = (unsigned)((warp >> 2) * 4096 + (8 * (warp & 3) + q) * 128 + (q << 5) + g * 4); a_k4 = 512u;
+           // rows g, g + 8, g + 16, g + 24 = atoms 0..3, XORed with k & 3 = q (the same for k and k + 4)
+           a_row8 = (q & 1) ? 0u - 32u : 32u; a_mt = (q & 2) ? 0u - 64u : 64u; }
+  } else {
+    const unsigned a_k8 = 8u * (a_kc ? 4 : 4 * kMS);
+    a_w = 4u * (a_kc ? g * kKS + q : q * kMS + g) + (unsigned)warp * a_k8; a_it = 8u * a_k8;
+    a_row8 = 4u * (a_kc ? 8 * kKS : 8); a_k4 = 4u * (a_kc ? 4 : 4 * kMS); a_mt = 2u * a_row8;
+  }
+  if (b_tma) {
+    b_it = 8192u;
+    if (b_kc) { b_w = (unsigned)((warp >> 2) * 4096 + g * 128 + (((2 * (warp & 3)) ^ g) << 4) + q * 4); b_nt = 1024u; b_nt2 = 2048u; b_k4 = (g & 1) ? 0u - 16u : 16u; }
+    else { b_w = (unsigned)((warp >> 2) * 4096 + (8 * (warp & 3) + q) * 128 + (q << 5) + g * 4); b_k4 = 512u;
+           b_nt = (q & 1) ? 0u - 32u : 32u; b_nt2 = (q & 2) ? 0u - 64u : 64u; }
+  } else {
+    const unsigned b_k8 = 8u * (b_kc ? 4 : 4 * kMS);
+    b_w = 4u * (b_kc ? g * kKS + q : q * kMS + g) + (unsigned)warp * b_k8; b_it = 8u * b_k8;
+    b_k4 = 4u * (b_kc ? 4 : 4 * kMS); b_nt = 4u * (b_kc ? 8 * kKS : 8); b_nt2 = 2u * b_nt;
+  }
 #pragma unroll 1
   for (int st = -1; st < nstages; ++st) {
     if (st + 1 < nstages) {
       const int k0 = (st + 1) * kKC;
-      tc_fill_stage<KC>(og, smem + ((st + 1) & 1) * kTcStageFloats, m0, n0, k0, min(kKC, o.K - k0), vecA, vecB);
+      if (o.tma) tc_tma_stage(o, sbase + 4u * (unsigned)(((st + 1) & 1) * kTcStageFloats), 4u * (unsigned)kOperandFloats, m0, n0, k0,
+                              min(kKC, o.K - k0), &tma.bar[(st + 1) & 1]);
+      if (o.tma != 3) tc_fill_stage<KC>(og, smem + ((st + 1) & 1) * kTcStageFloats, m0, n0, k0, min(kKC, o.K - k0), vecA, vecB, o.tma);
       cp_async_commit();
       if (fz)           // the B panel is in flight; produce the A panel meanwhile
         tc_produce_l0<KC>(*fz, o.M, smem + ((st + 1) & 1) * kTcStageFloats, m0, k0, min(kKC, o.K - k0), tn == 0, mode);
@@ -748,36 +824,43 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
       continue;
     }
     if (st + 1 < nstages) cp_async_wait<1>(); else cp_async_wait<0>();
+    if (o.tma) {       // every consuming thread observes the completion of the stage's boxes
+      if (!tc5::mbar_wait(&tma.bar[st & 1], (tma.par >> (st & 1)) & 1u)) __trap();
+      tma.par ^= 1u << (st & 1);
+    }
     __syncthreads();
     if (st == 0) ILSW_TSTAMP(2);
     {
       const int klen = min(kKC, o.K - st * kKC);
       const int ksteps = (klen + 7) >> 3;            // panels are zero padded up to a multiple of 16
-      const unsigned a0 = sbase + 4u * (unsigned)((st & 1) * kTcStageFloats) + a_off;
-      const unsigned b0 = sbase + 4u * (unsigned)((st & 1) * kTcStageFloats + kOperandFloats) + b_off;
+      unsigned pa = sbase + 4u * (unsigned)((st & 1) * kTcStageFloats) + a_w;
+      unsigned pb = sbase + 4u * (unsigned)((st & 1) * kTcStageFloats + kOperandFloats) + b_w;
       // software pipeline over this warp's k-steps: the fragment loads of the next k-step are issued
       // before the MMAs of the current one (ping-pong fragment registers)
       FragSet f0, f1;
       int ks = warp;
-      if (ks < ksteps) fragset_load(f0, a0 + (unsigned)ks * a_k8, a_row8, a_k4, a_mt, b0 + (unsigned)ks * b_k8, b_k4, b_nt);
+      if (ks < ksteps) fragset_load(f0, pa, a_row8, a_k4, a_mt, pb, b_k4, b_nt, b_nt2);
       if (full && KC == 128 && ILSW_TC128_SIMPLE) {
         // two CTAs per SM (128-register cap): one fragment set, no ping-pong -- four warps per scheduler hide the shared
         // memory latency, and the second fragment set is what pushed this variant into local-memory spills
 #pragma unroll 1
         for (; ks < ksteps; ks += 8) {
           fragset_mma<true>(acc, f0, mode, 2, 4);
-          if (ks + 8 < ksteps) fragset_load(f0, a0 + (unsigned)(ks + 8) * a_k8, a_row8, a_k4, a_mt, b0 + (unsigned)(ks + 8) * b_k8, b_k4, b_nt);
+          pa += a_it; pb += b_it;
+          if (ks + 8 < ksteps) fragset_load(f0, pa, a_row8, a_k4, a_mt, pb, b_k4, b_nt, b_nt2);
         }
       } else if (full) {          // all 8 fragment tiles live: straight-line MMAs, no guards
 #pragma unroll 1
         while (ks < ksteps) {
           int kn = ks + 8;
-          if (kn < ksteps) fragset_load(f1, a0 + (unsigned)kn * a_k8, a_row8, a_k4, a_mt, b0 + (unsigned)kn * b_k8, b_k4, b_nt);
+          pa += a_it; pb += b_it;
+          if (kn < ksteps) fragset_load(f1, pa, a_row8, a_k4, a_mt, pb, b_k4, b_nt, b_nt2);
           fragset_mma<true>(acc, f0, mode, 2, 4);
           ks = kn;
           if (ks >= ksteps) break;
           kn = ks + 8;
-          if (kn < ksteps) fragset_load(f0, a0 + (unsigned)kn * a_k8, a_row8, a_k4, a_mt, b0 + (unsigned)kn * b_k8, b_k4, b_nt);
+          pa += a_it; pb += b_it;
+          if (kn < ksteps) fragset_load(f0, pa, a_row8, a_k4, a_mt, pb, b_k4, b_nt, b_nt2);
           fragset_mma<true>(acc, f1, mode, 2, 4);
           ks = kn;
         }
@@ -785,15 +868,22 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
 #pragma unroll 1
         for (; ks < ksteps; ks += 8) {
           fragset_mma<false>(acc, f0, mode, n_mt, n_nt);
-          if (ks + 8 < ksteps) fragset_load(f0, a0 + (unsigned)(ks + 8) * a_k8, a_row8, a_k4, a_mt, b0 + (unsigned)(ks + 8) * b_k8, b_k4, b_nt);
+          pa += a_it; pb += b_it;
+          if (ks + 8 < ksteps) fragset_load(f0, pa, a_row8, a_k4, a_mt, pb, b_k4, b_nt, b_nt2);
         }
       }
     }
-    if (do_aug) {      // thread -> (m = tid % 32, k = tid / 32 + 8 i): conflict-free reads of the [k][kMS] panel
+    if (do_aug) {      // thread -> (m = tid % 32, k = tid / 32 + 8 i): conflict-free reads of the m-contiguous A panel
       const int klen = min(kKC, o.K - st * kKC);
-      const float* As = smem + (st & 1) * kTcStageFloats + (tid >> 5) * kMS + (tid & 31);
       float sacc = 0.f;
-      for (int k = tid >> 5; k < klen; k += 8, As += 8 * kMS) sacc += *As;
+      if (a_tma) {     // swizzled boxes [32 k][32 m]: word(m,k) = (k>>5)*1024 + (k&31)*32 + (((m>>3) ^ (k&3)) << 3) + (m&7)
+        const float* As = smem + (st & 1) * kTcStageFloats;
+        const int m = tid & 31;
+        for (int k = tid >> 5; k < klen; k += 8) sacc += As[(k >> 5) * 1024 + (k & 31) * 32 + (((m >> 3) ^ (k & 3)) << 3) + (m & 7)];
+      } else {
+        const float* As = smem + (st & 1) * kTcStageFloats + (tid >> 5) * kMS + (tid & 31);
+        for (int k = tid >> 5; k < klen; k += 8, As += 8 * kMS) sacc += *As;
+      }
       colsum += sacc;
     }
     __syncthreads();   // stage buffer may be refilled by the next iteration's prefetch / reused for the partials
@@ -865,6 +955,7 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
     epi_store(o, m0 + tid, o.N, bsum, e, push);
     if (ad) adam_math_store(*ad, *cf, gib, o.accumulate ? bsum + e.prev : bsum, bm, bv, bp, bt, ad_sh);
   }
+  tc5::fence_proxy_async();   // this tile's generic accesses to the staging area precede the next tile's TMA writes
   __syncthreads();     // the partial tiles are read before the next job's panels overwrite them
   ILSW_TSTAMP(4);
 }
@@ -1039,30 +1130,92 @@ struct SmemProgram { const Phase* phases; const Op* ops; const Ctx* ctx; int n_p
 
 __device__ __forceinline__ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
-// one flat Adam(+Polyak) chunk of kAdamChunk elements: ALL loads first, then the arithmetic, then the stores
-__device__ __noinline__ void adam_job(const AdamOp& ao, const AdamCoef& cfs, int j, bool reduced, const Replica& rp, unsigned xseq, int world) {
+// one flat Adam(+Polyak) chunk of kAdamChunk elements: ALL loads first, then the arithmetic, then the stores.
+// The load half is BRANCH FREE (out-of-range lanes read a valid address and are masked at the stores): with a branch per
+// element the compiler kept the state arrays in local memory and stored every value right after loading it, so each
+// element waited for its own L2 round trips in turn -- 14 us per job on the B200 (ncu: STL ... stall_long_sb).
+__device__ __noinline__ void adam_job(const AdamOp& aos, const AdamCoef& cfs, int j, bool reduced, const Replica& rp, unsigned xseq, int world) {
+  const AdamOp ao = aos;
   const AdamCoef cf = cfs;
   const float gscale = (ao.grad_scale_world && world > 1) ? 1.0f / (float)world : 1.0f;
   const int beg = ao.begin + j * kAdamChunk, end = min(ao.n, beg + kAdamChunk);
   constexpr int E = kAdamChunk / kThreads;
   float g[E], m[E], v[E], p[E], tg[E];
+  int idx[E];
 #pragma unroll
   for (int u = 0; u < E; ++u) {
     const int i = beg + threadIdx.x + u * kThreads;
-    if (i < end) {
-      // __fmul_rn: the scaled gradient must be ROUNDED before Adam consumes it -- a plain `* gscale` gets contracted into
-      // the first FMA of adam_math_store ((s * gscale) - m), which made R identical replicas differ from one replica by an
-      // ulp (tools/replica_check.py, test A: the single-replica program applies Adam in the weight-gradient epilogues)
-      g[u] = __fmul_rn(reduced ? replica_reduced_grad(rp, xseq, i) : adam_grad(ao, i), gscale);
-      m[u] = ao.m[i]; v[u] = ao.v[i]; p[u] = ao.p[i];
-      tg[u] = ao.target ? ao.target[i] : 0.f;
+    idx[u] = i < end ? i : beg;
+  }
+  if (reduced) {                // rank-ordered sum of the replicas' receive slots
+    const size_t base = (size_t)(xseq & 1u) * rp.world * (size_t)rp.nstride;
+#pragma unroll
+    for (int u = 0; u < E; ++u) {
+      float part[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float x = __ldcv(rp.recv_local + base + (size_t)(r < rp.world ? r : 0) * rp.nstride + idx[u]);
+        part[r] = r < rp.world ? x : 0.f;
+      }
+      float acc = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc += part[r];
+      g[u] = acc;
     }
+  } else {                      // split-K partial arenas in split order (one arena without splits)
+#pragma unroll
+    for (int u = 0; u < E; ++u) {
+      float part[kMaxGradSplits];
+#pragma unroll
+      for (int sp = 0; sp < kMaxGradSplits; ++sp) {
+        const bool live = sp == 0 || sp < ao.g_splits;
+        const float x = __ldcg(ao.g + (size_t)(live ? sp : 0) * ao.g_split_stride + idx[u]);
+        part[sp] = live ? x : 0.f;
+      }
+      float acc = part[0];
+#pragma unroll
+      for (int sp = 1; sp < kMaxGradSplits; ++sp) acc += part[sp];
+      g[u] = acc;
+    }
+  }
+  const float* tptr = ao.target ? ao.target : ao.p;
+#pragma unroll
+  for (int u = 0; u < E; ++u) {
+    // __fmul_rn: the scaled gradient must be ROUNDED before Adam consumes it -- a plain `* gscale` gets contracted into
+    // the first FMA of adam_math_store ((s * gscale) - m), which made R identical replicas differ from one replica by an
+    // ulp (tools/replica_check.py, test A: the single-replica program applies Adam in the weight-gradient epilogues)
+    g[u] = __fmul_rn(g[u], gscale);
+    m[u] = ao.m[idx[u]]; v[u] = ao.v[idx[u]]; p[u] = ao.p[idx[u]];
+    tg[u] = tptr[idx[u]];
   }
   const bool sh = adam_has_shadow(ao);
 #pragma unroll
   for (int u = 0; u < E; ++u) {
     const int i = beg + threadIdx.x + u * kThreads;
     if (i < end) adam_math_store(ao, cf, i, g[u], m[u], v[u], p[u], tg[u], sh);
+  }
+}
+
+// flat Polyak chunk, same structure
+__device__ __noinline__ void polyak_job(const PolyakOp& pos, int j) {
+  const PolyakOp po = pos;
+  const int beg = j * kAdamChunk, end = min(po.n, beg + kAdamChunk);
+  constexpr int E = kAdamChunk / kThreads;
+  float tv[E], sv[E];
+  const float om = (float)(1.0 - (double)po.tau);
+#pragma unroll
+  for (int u = 0; u < E; ++u) {
+    const int i = beg + threadIdx.x + u * kThreads, ii = i < end ? i : beg;
+    tv[u] = po.target[ii]; sv[u] = __ldcg(po.src + ii);
+  }
+#pragma unroll
+  for (int u = 0; u < E; ++u) {
+    const int i = beg + threadIdx.x + u * kThreads;
+    if (i < end) {
+      const float tn = tv[u] * om + sv[u] * po.tau;
+      po.target[i] = tn;
+      shadow_store(po.sh_t, i, tn);
+    }
   }
 }
 
@@ -1085,6 +1238,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
   __shared__ int s_pt[kMaxNets];
   __shared__ tc5::Sync s_tc5;
   __shared__ PushCtx s_push;
+  __shared__ unsigned long long s_tma_bar[2];  // stage barriers of the mma.sync tile's TMA panels (tc_tma_stage)
   const int n_phases = prog->n_phases, n_ops = prog->n_ops;
   constexpr int KC = CTAS == 2 ? 128 : 256;
   unsigned char* pbase = dyn_smem + engine_staging_bytes(CTAS, TC5);
@@ -1112,7 +1266,11 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
     src = reinterpret_cast<const int*>(&prog->ctx); dst = reinterpret_cast<int*>(s_ctx); n = (int)(sizeof(Ctx) / 4);
     for (int i = threadIdx.x; i < n; i += kThreads) dst[i] = src[i];
   }
-  if (threadIdx.x == 0) { s_gen = 0u; s_a = a_param; s_rp = rp_param; }   // the host zeroes the barrier state before every launch
+  if (threadIdx.x == 0) {
+    s_gen = 0u; s_a = a_param; s_rp = rp_param;   // the host zeroes the barrier state before every launch
+    tc5::mbar_init(&s_tma_bar[0], 1); tc5::mbar_init(&s_tma_bar[1], 1);
+    tc5::fence_barrier_init();
+  }
   if (threadIdx.x < kMaxNets) { s_pt[threadIdx.x] = -1; s_adam_op[threadIdx.x] = -1; }
   __syncthreads();
   const RunArgs& a = s_a;
@@ -1135,6 +1293,9 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
   const bool fast_rows = fast_rows_ok(c);
 
   [[maybe_unused]] bool alive = true;
+  // staging area of the mma.sync tile on a 1024-byte boundary (its TMA boxes are swizzled on absolute address bits)
+  float* tile_smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~uintptr_t(1023));
+  TmaState tma_state{s_tma_bar, 0u};
   for (int s = 0; s < a.n_steps && ILSW_ALIVE; ++s) {
     const bool stamp = (s == a.n_steps - 1) && blockIdx.x == 0 && threadIdx.x == 0;
     if (stamp) c.phase_ns[0] = globaltimer_ns();
@@ -1178,7 +1339,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
           } else if (TC5 && gemm_is_skinny(o.gemm) && o.gemm.ksplit > 1) gemm_tile_skinny_split(o.gemm, j, smem);
           else if (gemm_is_skinny(o.gemm)) gemm_tile_skinny(o.gemm, j, smem, ad, cf, push);
           else if (prec == 0) gemm_tile_device(o.gemm, j, smem, ad, cf, push, fz);
-          else gemm_tile_tc<KC>(o.gemm, j, smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, ad, cf, push, fz);
+          else gemm_tile_tc<KC>(o.gemm, j, tile_smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, ad, cf, push, fz, tma_state);
         } else if (o.kind == OP_ROW) {
           RowEnv env; env.lane = lane; env.nl = 32; env.warp = warp; env.sm = smem;
           env.prof = (a.profile && blockIdx.x == 0) ? ph : -1;
@@ -1190,24 +1351,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
         } else if (o.kind == OP_ADAM) {
           adam_job(o.adam, s_coefs[o.adam.slot], j, exchange && o.adam.grad_scale_world, rp, xseq, a.world);
         } else if (o.kind == OP_POLYAK) {
-          const int beg = j * kAdamChunk, end = min(o.polyak.n, beg + kAdamChunk);
-          constexpr int E = kAdamChunk / kThreads;
-          float tv[E], sv[E];
-          const float om = (float)(1.0 - (double)o.polyak.tau);
-#pragma unroll
-          for (int u = 0; u < E; ++u) {
-            const int i = beg + threadIdx.x + u * kThreads;
-            if (i < end) { tv[u] = o.polyak.target[i]; sv[u] = __ldcg(o.polyak.src + i); }
-          }
-#pragma unroll
-          for (int u = 0; u < E; ++u) {
-            const int i = beg + threadIdx.x + u * kThreads;
-            if (i < end) {
-              const float tn = tv[u] * om + sv[u] * o.polyak.tau;
-              o.polyak.target[i] = tn;
-              shadow_store(o.polyak.sh_t, i, tn);
-            }
-          }
+          polyak_job(o.polyak, j);
         } else if (o.kind == OP_SHADOW) {
           const int beg = j * kAdamChunk, end = min(o.shadow.dst.n, beg + kAdamChunk);
           for (int i = beg + threadIdx.x; i < end; i += kThreads) shadow_refresh_elem(o.shadow, i);

@@ -121,7 +121,7 @@ struct Builder {
   // Two layers in one phase: H0 = act0(X W0^T + b0) [M, hid] is produced inside the tiles of Y = act(H0 W1^T + b1)
   // (GemmOp::a0) when the first layer's input is narrow; otherwise two phases.  H0 is materialised for the backward pass.
   bool fuse_l0_ok(int K0, int hid) const {
-    return !P.ctx.hp.use_tc5 && K0 <= kFuseL0MaxK && hid <= 256 && (hid & 1) == 0 && P.ctx.s.B < 512;
+    return P.ctx.hp.fuse_l0 && !P.ctx.hp.use_tc5 && K0 <= kFuseL0MaxK && hid <= 256 && (hid & 1) == 0 && P.ctx.s.B < 512;
   }
   void fwd2_fused(const float* X, int ldx, int M, int K0, const float* W0, const float* b0, int act0, int hid, float* H0,
                   const float* W1, const float* b1, int N, float* Y, int ldy, int act) {
@@ -777,12 +777,13 @@ inline bool tc5_wanted(const TrainerSpec& sp) {
   return sp.cfg.batch >= 512 && sp.cfg.gemm_precision != 0 && !sp.has_disc;
 }
 
-inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem, bool use_tc5 = false) {
+inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem, bool use_tc5 = false, bool fuse_l0 = true) {
   memset(&P, 0, sizeof(P));
   Ctx& c = P.ctx;
   const ilsw_trainer_config& cfg = sp.cfg;
   c.hp = make_hyper(cfg);
   c.hp.use_tc5 = use_tc5 ? 1 : 0;
+  c.hp.fuse_l0 = fuse_l0 ? 1 : 0;
   if (sp.has_disc) apply_disc_hyper(c.hp, sp.dcfg);
   const int B = cfg.batch, O = cfg.obs_dim, A = cfg.act_dim, Hd = sp.nets[0].hidden;
   c.dyn = mem.take<DynState>(1);

@@ -80,6 +80,8 @@ struct GemmOp {
   int split_stride;     //   its partial sums to C + s * split_stride / bias_out + s * split_stride (floats); 0 / 1: no split
   const void* tmapA;    // device CUtensorMap of the A / B operand (SWIZZLE_128B boxes, see ilsw_tc5.cuh)
   const void* tmapB;
+  int tma;              // mma.sync tile (ilsw_engine.cuh): bit 0 / bit 1 = the A / B panels of a stage are brought in by TMA boxes
+                        // {32 floats, 32 rows} of tmapA / tmapB instead of per-thread cp.async (16-byte aligned operands only)
 };
 
 // 16-byte-aligned copy of a first-layer weight matrix W0[hid x in] whose rows are not (in % 4 != 0: critics on Hopper /
@@ -226,6 +228,7 @@ struct Hyper {
   int state_only;       // disc input = cat(obs, next_obs) (adv_irl.py:139-179)
   int n_from_expert;    // last n rows of the policy batch come from the expert ring (adv_irl.py:239-255)
   int use_tc5;          // dense GEMM phases run on the tcgen05/TMA tile (ilsw_tc5.cuh): batch >= 512, tensor-core modes
+  int fuse_l0;          // narrow first layers are produced inside the second layer's tiles (GemmOp::a0)
 };
 
 struct Ctx {            // everything a row kernel needs

@@ -10,8 +10,20 @@ import torch
 from helpers import CFG, G, DeviceRun, STAT_TO_SLOT, assert_params_close, case_injection, run_loop_case
 
 pytestmark = pytest.mark.gpu
+import json
+
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 CASES = [n for n, c in CFG.CASES.items() if c["algo"] in ("sac_alpha", "sac_v", "td3", "adv_irl")]
+# measured on a B200 (tools/measure_param_frac.py): per case, the worst net's fraction of parameter elements that end more
+# than 1e-5 away from the oracle in the tensor-core GEMM modes.  The tests allow TWICE the measured fraction (never less
+# than the 5e-4 of the exact mode -- Adam's sign-sensitive elements, see assert_params_close).
+PARAM_FRAC = json.load(open(os.path.join(GOLDEN, "param_frac.json")))["cases"]
+
+
+def param_frac_bar(name, precision):
+    if precision == 0:
+        return 5e-4
+    return max(2.0 * PARAM_FRAC[name]["p%d" % precision]["frac_beyond_1e-5"], 5e-4)
 
 
 def loss_tol(k, ref, precision=0, n_rows=512):
@@ -60,17 +72,17 @@ def test_cuda_step_matches_oracle(name, precision):
             # tensor-core modes perturb gradients (TF32: 1e-3 relative, 3xTF32: ~5e-7 + the tensor
             # core's truncating fp32 accumulation): more elements fall into Adam's sign-sensitive
             # regime (see assert_params_close); the 2*lr*steps bound holds in every mode
-            frac = {0: 5e-4, 3: 0.1, 1: 1.0}[precision]
-            assert_params_close(run.arena(k), final[k], case["steps"], msg="%s/%s" % (name, k), frac=frac)
+            assert_params_close(run.arena(k), final[k], case["steps"], msg="%s/%s" % (name, k), frac=param_frac_bar(name, precision))
 
 
+@pytest.mark.parametrize("precision", [0, 3])      # 3 = the production default (bench.py)
 @pytest.mark.parametrize("name", CASES)
-def test_cuda_step_matches_reference_golden(name):
+def test_cuda_step_matches_reference_golden(name, precision):
     """Directly against the transcript of the executed reference (no oracle in between)."""
     case = CFG.CASES[name]
     gold = np.load(os.path.join(GOLDEN, name + ".npz"))
     keys = [str(k) for k in gold["stat_keys"]]
-    run = DeviceRun(case)
+    run = DeviceRun(case, precision=precision)
     L = run.train(case["steps"], case_injection(case))
     for t in range(case["steps"]):
         for j, k in enumerate(keys):
@@ -87,7 +99,38 @@ def test_cuda_step_matches_reference_golden(name):
         v = run.arena(k[len("sample_"):])
         sample = v[:: max(1, v.size // 256)][:256]
         assert np.max(np.abs(sample - gold[k])) <= 2 * 3e-4 * case["steps"] + 1e-6
-        assert (np.abs(sample - gold[k]) > 1e-5).sum() <= 1
+        assert (np.abs(sample - gold[k]) > 1e-5).sum() <= max(1, int(np.ceil(param_frac_bar(name, precision) * sample.size)))
+
+
+def test_fused_first_layer_program_matches_oracle(monkeypatch):
+    """ILSW_FUSE_L0=1 (first layers produced inside the second layer's tiles; off by default since it measured slower)
+    stays a supported program: same parity bar."""
+    monkeypatch.setenv("ILSW_FUSE_L0", "1")
+    torch.set_num_threads(1)
+    for name in ("sac_hopper", "gail_walker"):
+        case = CFG.CASES[name]
+        rows, final, _ = G.run_oracle(case)
+        run = DeviceRun(case, precision=3)
+        assert "fused-L0" in run.eng.describe()
+        L = run.train(case["steps"], case_injection(case))
+        for t, row in enumerate(rows):
+            for k in ("QF1 Loss", "QF2 Loss", "Policy Loss"):
+                assert abs(float(L[t, STAT_TO_SLOT[k]]) - row[k]) <= loss_tol(k, row[k], 3), (name, t, k)
+        assert_params_close(run.arena("policy"), final["policy"], case["steps"], msg=name, frac=param_frac_bar(name, 3))
+
+
+def test_tma_panels_on_and_off_agree(monkeypatch):
+    """The TMA panel path of the mma.sync tile (GemmOp::tma) and the cp.async path compute the same tile: bit-identical
+    losses and parameters (same fragment values, same MMA order)."""
+    case = CFG.CASES["sac_hopper"]
+    inj = case_injection(case)
+    a = DeviceRun(case, precision=3)
+    La = a.train(case["steps"], inj)
+    monkeypatch.setenv("ILSW_TMA_PANELS", "0")
+    b = DeviceRun(case, precision=3)
+    Lb = b.train(case["steps"], inj)
+    np.testing.assert_array_equal(La[:, :5], Lb[:, :5])
+    np.testing.assert_array_equal(a.arena("policy"), b.arena("policy"))
 
 
 def test_split_launches_equal_one_launch():

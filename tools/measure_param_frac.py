@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Measures, per parity case, the fraction of parameter elements whose final value differs from the oracle's by more than
+1e-5 in the tensor-core GEMM modes (precision 3 = 3xTF32, the production default; precision 1 = single-pass TF32).
+Writes tests/golden/param_frac.json; tests/test_gpu_engine.py asserts <= 2x the committed value.
+Needs a GPU:  python tools/measure_param_frac.py"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import CFG, G, DeviceRun, case_injection  # noqa: E402
+
+torch.set_num_threads(1)
+out = {}
+for name, case in CFG.CASES.items():
+    if case["algo"] not in ("sac_alpha", "sac_v", "td3", "adv_irl"):
+        continue
+    rows, final, _ = G.run_oracle(case)
+    rec = {}
+    for prec in (3, 1):
+        run = DeviceRun(case, precision=prec)
+        run.train(case["steps"], case_injection(case))
+        worst, worst_net, worst_max = 0.0, None, 0.0
+        for k in final:
+            if k == "log_alpha":
+                continue
+            d = np.abs(np.asarray(run.arena(k), np.float64).ravel() - np.asarray(final[k], np.float64).ravel())
+            f = float((d > 1e-5).sum()) / d.size
+            if f >= worst:
+                worst, worst_net = f, k
+            worst_max = max(worst_max, float(d.max()))
+        rec["p%d" % prec] = {"frac_beyond_1e-5": worst, "net": worst_net, "max_abs_diff": worst_max}
+    out[name] = rec
+    print(name, rec, flush=True)
+with open(os.path.join(ROOT, "tests", "golden", "param_frac.json"), "w") as f:
+    json.dump({"note": "measured on a B200 by tools/measure_param_frac.py: worst net's fraction of parameter elements beyond 1e-5 of the oracle", "cases": out}, f, indent=1, sort_keys=True)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+with open(os.path.join(ROOT, "gpurun_out", "param_frac.json"), "w") as f:
+    json.dump({"cases": out}, f, indent=1, sort_keys=True)
