@@ -296,7 +296,21 @@ def measure(name, args, K, W, rank, world, dist, flush, clock, peak, peak_src, e
     launch = min(LAUNCH, K)
     tr, buf, irl = build_ours(w, seed=100 + rank, steps_per_launch=launch)
     tr._seed = replicas.replica_seed(12345, rank)
+    solo = None
     if world > 1:
+        # diagnostic (untimed region): every rank's step time BEFORE the replicas are connected.  Lock-step replicas run at
+        # the pace of the slowest GPU, so mean(solo) / max(solo) bounds the scaling efficiency from above.
+        run_steps(tr, buf, irl, launch)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        run_steps(tr, buf, irl, launch)
+        s1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([s0.elapsed_time(s1) * 1000.0 / launch], dtype=torch.float64, device="cuda")
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        solo = [float(x.item()) for x in allt]
         replicas.connect_replicas(tr)
     tr.eval_statistics = {}          # no per-epoch stats read-back inside the timed region
     if irl is not None:
@@ -408,13 +422,19 @@ def measure(name, args, K, W, rank, world, dist, flush, clock, peak, peak_src, e
            "timing": "device-timed: sum of CUDA-event times around the %d launch(es), max over ranks" % len(evs),
            "config": {"workload": workload_desc(name, w, launch), "parallelism": "replicas x%d" % world, "global_batch": w["B"] * world,
                       "l2": "flushed between timed launches (256 MiB write, untimed)", "sampling": "in-kernel Philox, uniform with replacement",
-                      "engine": "tcgen05/TMA GEMM tiles" if getattr(tr.engine, "uses_tc5", lambda: False)() else "mma.sync 32x32 tiles"},
+                      "engine": "tcgen05/TMA GEMM tiles" if getattr(tr.engine, "uses_tc5", lambda: False)() else "mma.sync 32x32 tiles (TMA panels)",
+                      "exchange": ("none (1 replica)" if world == 1 else
+                                   ("in-kernel push from the weight-gradient epilogues, NVLS multicast stores" if getattr(tr.engine, "replica_multicast", False)
+                                    else "in-kernel push from the weight-gradient epilogues, per-peer NVLink stores"))},
            "e2e": e2e, "e2e_train_call": e2e_call, "gpu_launches": int(launches),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "traffic_note": "ncu dram bytes per step (profiles/) x steps of this launch", "peak_source": peak_src,
                         "kernel": "ilsw_engine_kernel", "launch_steps": launch, "algorithmic_bytes_per_launch": bytes_step * launch,
                         "launch_ms": ms_per_launch}}
 
+    if solo is not None:
+        rec["replicas_unconnected_us_per_step"] = {"per_rank": solo, "min": min(solo), "max": max(solo), "mean": float(np.mean(solo)),
+                                                   "note": "each GPU alone, same program without the exchange, measured before connect_replicas"}
     if world == 1 and extras:
         # ---- sampler coupling: the per-env-step get_actions round trip with host buffers, env_num = 4
         from ilswiss_b200.sampler import DevicePolicy
@@ -657,7 +677,7 @@ def main():
             "value_by_gemm_precision": by_prec, "data": "synthetic", "config": dict(config, **{k: v for k, v in rec["config"].items() if k not in config}),
             "timing": rec["timing"], "e2e": rec["e2e"], "e2e_train_call": rec["e2e_train_call"], "sampler": rec.get("sampler"),
             "gpu_launches": rec["gpu_launches"], "roofline": rec["roofline"], "clocks": clocks}
-    for k in ("replay_roofline", "cpu_baseline"):
+    for k in ("replay_roofline", "cpu_baseline", "replicas_unconnected_us_per_step"):
         if k in rec:
             line[k] = rec[k]
     if workloads:

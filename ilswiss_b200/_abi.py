@@ -114,6 +114,8 @@ PROTOTYPES = {
     "ilsw_policy_act_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "ilsw_replica_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ilsw_replica_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ilsw_replica_buffer_bytes": (C.c_int64, [C.c_void_p]),
+    "ilsw_replica_connect_symm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_uint64, C.c_int64]),
 }
 
 

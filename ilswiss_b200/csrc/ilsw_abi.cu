@@ -830,6 +830,43 @@ extern "C" int ilsw_replica_export(ilsw_trainer* tr, void* handle_out) {
   return ILSW_OK;
 }
 
+// Exchange buffer provided by the caller (symmetric memory: the same allocation on every rank, mapped into every process,
+// optionally with an NVLS multicast mapping).  Layout as in ilsw_replica_export: [kFlagBytes flags / counter][2][world][nstride].
+extern "C" int64_t ilsw_replica_buffer_bytes(ilsw_trainer* tr) {
+  if (!tr) return ILSW_ERR_ARG;
+  return (int64_t)(kFlagBytes + (size_t)2 * 8 * round_up(tr->host_prog.ctx.policy.n_params, 4) * sizeof(float));
+}
+extern "C" int ilsw_replica_connect_symm(ilsw_trainer* tr, int rank, int world, const uint64_t* peer_ptrs, uint64_t multicast_ptr,
+                                         int64_t bytes) {
+  if (!tr || !peer_ptrs || world < 1 || world > 8 || rank < 0 || rank >= world) return fail(ILSW_ERR_ARG, "replica_connect_symm: bad arguments");
+  if (bytes < ilsw_replica_buffer_bytes(tr)) return fail(ILSW_ERR_ARG, "replica_connect_symm: buffer of %lld B, need %lld", (long long)bytes, (long long)ilsw_replica_buffer_bytes(tr));
+  const int n = tr->host_prog.ctx.policy.n_params;
+  Replica& rp = tr->rep;
+  memset(&rp, 0, sizeof(rp));
+  rp.world = world; rp.rank = rank; rp.n = n; rp.nstride = round_up(n, 4);
+  rp.grad = tr->host_prog.ctx.policy.g;
+  for (int r = 0; r < world; ++r) {
+    char* base = reinterpret_cast<char*>((uintptr_t)peer_ptrs[r]);
+    if (!base || (reinterpret_cast<uintptr_t>(base) & 127)) return fail(ILSW_ERR_ARG, "replica_connect_symm: peer pointer %d null or unaligned", r);
+    tr->peer_bases[r] = nullptr;                 // not ours to unmap
+    rp.flags_peer[r] = reinterpret_cast<unsigned*>(base);
+    rp.cnt_peer[r] = reinterpret_cast<unsigned long long*>(base + 128);
+    rp.recv_peer[r] = reinterpret_cast<float*>(base + kFlagBytes);
+  }
+  rp.cnt_local = rp.cnt_peer[rank];
+  rp.flags_local = rp.flags_peer[rank];
+  rp.recv_local = rp.recv_peer[rank];
+  if (multicast_ptr) {
+    char* mc = reinterpret_cast<char*>((uintptr_t)multicast_ptr);
+    rp.cnt_mc = reinterpret_cast<unsigned long long*>(mc + 128);
+    rp.recv_mc = reinterpret_cast<float*>(mc + kFlagBytes);
+  }
+  CU(cudaMemset(rp.flags_local, 0, kFlagBytes));
+  CU(cudaDeviceSynchronize());
+  tr->seq = 0;
+  return ILSW_OK;
+}
+
 extern "C" int ilsw_replica_connect(ilsw_trainer* tr, int rank, int world, const void* all_handles) {
   if (!tr || !all_handles || world < 1 || world > 8 || rank < 0 || rank >= world) return fail(ILSW_ERR_ARG, "replica_connect: bad arguments");
   if (!tr->ipc_buf) return fail(ILSW_ERR_STATE, "replica_connect: call ilsw_replica_export first");

@@ -58,6 +58,10 @@ struct Replica {
   unsigned seq0;              // exchanges completed before this launch
   unsigned long long* cnt_local;      // arrival counter of the epilogue-push exchange: every CTA of every replica adds 1 per
   unsigned long long* cnt_peer[8];    // policy update (after a system fence behind its pushes); never reset
+  // NVLS multicast mapping of the same exchange buffer (ilsw_replica_connect_symm): a store / reduction on these addresses is
+  // replicated to every replica by the NVSwitch -- the epilogue push costs ONE store per element instead of `world`
+  float* recv_mc;                     // nullptr: no multicast mapping, per-peer stores
+  unsigned long long* cnt_mc;
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
@@ -1110,7 +1114,9 @@ __device__ __forceinline__ bool replica_wait_pushes(const Replica& rp, unsigned 
 __device__ __forceinline__ void replica_signal_pushes(const Replica& rp) {
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x < rp.world) red_add_release_sys_u64(rp.cnt_peer[threadIdx.x], 1ull);
+  if (rp.cnt_mc) {
+    if (threadIdx.x == 0) asm volatile("multimem.red.release.sys.global.add.u64 [%0], %1;" ::"l"(rp.cnt_mc), "l"(1ull) : "memory");
+  } else if (threadIdx.x < rp.world) red_add_release_sys_u64(rp.cnt_peer[threadIdx.x], 1ull);
 }
 
 __device__ __forceinline__ float replica_reduced_grad(const Replica& rp, unsigned seq, int i) {
@@ -1317,7 +1323,10 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
       if (pushing) {       // this rank's receive slot (parity of this update) on every replica
         if (threadIdx.x < rp.world)
           s_push.peer[threadIdx.x] = rp.recv_peer[threadIdx.x] + ((size_t)(xseq & 1u) * rp.world + rp.rank) * (size_t)rp.nstride;
-        if (threadIdx.x == 0) { s_push.grad_base = rp.grad; s_push.world = rp.world; }
+        if (threadIdx.x == 0) {
+          s_push.grad_base = rp.grad; s_push.world = rp.world;
+          s_push.mc = rp.recv_mc ? rp.recv_mc + ((size_t)(xseq & 1u) * rp.world + rp.rank) * (size_t)rp.nstride : nullptr;
+        }
         __syncthreads();
       }
       const PushCtx* push = pushing ? &s_push : nullptr;

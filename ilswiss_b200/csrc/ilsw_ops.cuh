@@ -162,7 +162,9 @@ ILSW_HD void push_elem(const PushCtx* push, const float* where, float v) {
 #ifdef __CUDA_ARCH__
   if (push) {
     const size_t gi = (size_t)(where - push->grad_base);
-    for (int r = 0; r < push->world; ++r) push->peer[r][gi] = v;
+    if (push->mc) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(push->mc + gi), "f"(v) : "memory");
+    else
+      for (int r = 0; r < push->world; ++r) push->peer[r][gi] = v;
   }
 #else
   (void)push; (void)where; (void)v;

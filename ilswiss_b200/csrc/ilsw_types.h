@@ -114,7 +114,9 @@ struct AdamOp {
 
 // replica exchange from the tile epilogues (Phase::push): where element `p` of the local policy gradient arena goes on
 // every replica -- peer[r] is this rank's receive slot on replica r (NVLink peer mapping), offset by the arena position
-struct PushCtx { float* peer[8]; const float* grad_base; int world; };
+// `mc` != nullptr: the same slot through an NVLS multicast mapping (one store reaches every replica: the NVSwitch replicates
+// it), the per-peer pointers are then unused
+struct PushCtx { float* peer[8]; const float* grad_base; int world; float* mc; };
 
 // Fused first layer (A-operand producer of a second-layer GEMM, small-input nets: K0 = O + A <= kFuseL0MaxK):
 //   A(m,k) = act( sum_j X[m*ldx + j] * W[k*K0 + j] + b[k] ),  j < K0,  k < K (= hidden width),

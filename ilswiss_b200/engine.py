@@ -346,6 +346,21 @@ class StepEngine:
         check(self.lib.ilsw_replica_export(self.h, buf), "replica_export")
         return buf.raw
 
+    def replica_buffer_bytes(self):
+        n = int(self.lib.ilsw_replica_buffer_bytes(self.h))
+        if n <= 0:
+            raise IlswError("replica_buffer_bytes failed")
+        return n
+
+    def replica_connect_symm(self, rank, world, peer_ptrs, multicast_ptr, nbytes, keepalive=None):
+        """Exchange over a symmetric buffer (same allocation on every rank, mapped here at peer_ptrs[r]); multicast_ptr != 0
+        switches the gradient push to NVLS multicast stores.  `keepalive` (the tensor / handle owning the mapping) is held."""
+        arr = (C.c_uint64 * world)(*[int(p) for p in peer_ptrs])
+        check(self.lib.ilsw_replica_connect_symm(self.h, rank, world, arr, C.c_uint64(int(multicast_ptr)), C.c_int64(int(nbytes))),
+              "replica_connect_symm")
+        self._symm_keepalive = keepalive
+        self.replica_multicast = bool(multicast_ptr)
+
     def replica_connect(self, rank, world, handles):
         blob = b"".join(handles)
         assert len(blob) == world * _abi.IPC_HANDLE_BYTES

@@ -269,6 +269,14 @@ int ilsw_policy_act_host(ilsw_trainer* tr, const float* obs_host, int n, int det
 int ilsw_replica_export(ilsw_trainer* tr, void* handle_out /* ILSW_IPC_HANDLE_BYTES */);
 int ilsw_replica_connect(ilsw_trainer* tr, int rank, int world,
                          const void* all_handles /* world * ILSW_IPC_HANDLE_BYTES */);
+/* Same exchange over a caller-provided symmetric buffer (e.g. torch.distributed._symmetric_memory): peer_ptrs[r] = the
+ * buffer of rank r mapped into THIS process (peer_ptrs[rank] = the local one), multicast_ptr = its NVLS multicast mapping
+ * or 0.  With a multicast mapping the gradient push is one multimem store per element (the NVSwitch replicates it) instead
+ * of `world` peer stores.  Replaces the torch.distributed all-reduce a data-parallel port of
+ * torch_rl_algorithm.py:28-34 would issue after policy_loss.backward() (sac_alpha.py:150-152). */
+int64_t ilsw_replica_buffer_bytes(ilsw_trainer* tr);
+int ilsw_replica_connect_symm(ilsw_trainer* tr, int rank, int world, const uint64_t* peer_ptrs /* world */,
+                              uint64_t multicast_ptr, int64_t bytes);
 
 #ifdef __cplusplus
 }
