@@ -1245,6 +1245,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
   __shared__ tc5::Sync s_tc5;
   __shared__ PushCtx s_push;
   __shared__ unsigned long long s_tma_bar[2];  // stage barriers of the mma.sync tile's TMA panels (tc_tma_stage)
+  __shared__ int s_last_ph;                    // last active phase of the current step (hosts Ctx::tail_op1)
   const int n_phases = prog->n_phases, n_ops = prog->n_ops;
   constexpr int KC = CTAS == 2 ? 128 : 256;
   unsigned char* pbase = dyn_smem + engine_staging_bytes(CTAS, TC5);
@@ -1310,6 +1311,12 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
       while (s_pt[threadIdx.x] < tn) { s_p1[threadIdx.x] *= s_b1[threadIdx.x]; s_p2[threadIdx.x] *= s_b2[threadIdx.x]; s_pt[threadIdx.x]++; }
       s_coefs[threadIdx.x] = adam_coef_pw(s_ops[s_adam_op[threadIdx.x]].adam, s_p1[threadIdx.x], s_p2[threadIdx.x], 1);
     }
+    if (c.tail_op1 && threadIdx.x == 32) {      // which phase carries the next-step row op this step
+      int last = -1;
+      for (int ph = n_phases - 1; ph >= 0 && last < 0; --ph)
+        if (phase_active(s_phases[ph], c.hp, a, s)) last = ph;
+      s_last_ph = last;
+    }
     __syncthreads();
     for (int ph = 0; ph < n_phases && ILSW_ALIVE; ++ph) {
       const Phase& P = s_phases[ph];
@@ -1330,9 +1337,11 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
         __syncthreads();
       }
       const PushCtx* push = pushing ? &s_push : nullptr;
-      for (int job = blockIdx.x; job < P.total_jobs && ILSW_ALIVE; job += gridDim.x) {
+      const int tail_jobs = (c.tail_op1 && ph == s_last_ph) ? s_ops[c.tail_op1 - 1].n_jobs : 0;
+      for (int job = blockIdx.x; job < P.total_jobs + tail_jobs && ILSW_ALIVE; job += gridDim.x) {
         int j = job, oi = P.op_begin;
-        while (j >= s_ops[oi].n_jobs) { j -= s_ops[oi].n_jobs; ++oi; }
+        if (job >= P.total_jobs) { j = job - P.total_jobs; oi = c.tail_op1 - 1; }
+        else { while (j >= s_ops[oi].n_jobs) { j -= s_ops[oi].n_jobs; ++oi; } }
         const Op& o = s_ops[oi];
         if (o.kind == OP_GEMM) {
           const AdamOp* ad = o.gemm.adam ? &s_ops[o.gemm.adam - 1].adam : nullptr;

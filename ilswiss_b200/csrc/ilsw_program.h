@@ -194,6 +194,16 @@ struct Builder {
     return s < 1 ? 1 : s;
   }
   static int tc5_tiles(int M, int N) { return ((M + 127) / 128) * ((N + kTc5BN - 1) / kTc5BN); }
+  // next-step row op that runs with the last active phase of every step (Ctx::tail_op1).  Must be the LAST op added: the ops
+  // of a phase are contiguous, and this one belongs to none.
+  void tail_row(int kind, int rows) {
+    if (P.n_ops >= kMaxOps) { overflow = true; return; }
+    Op& o = P.ops[P.n_ops++];
+    memset(&o, 0, sizeof(o));
+    o.kind = OP_ROW; o.n_jobs = (rows + kRowsPerJob - 1) / kRowsPerJob;
+    o.row.kind = kind; o.row.rows = rows; o.row.arg0 = 1; o.row.arg1 = 0;
+    P.ctx.tail_op1 = P.n_ops;
+  }
   void row(int kind, int rows, int next_step = 0, int row_offset = 0) {
     Op* o = add(OP_ROW, (rows + kRowsPerJob - 1) / kRowsPerJob);
     if (o) { o->row.kind = kind; o->row.rows = rows + row_offset; o->row.arg0 = next_step; o->row.arg1 = row_offset; }
@@ -500,7 +510,11 @@ inline void build_td3(Builder& b, const Ctx& c) {
   const MlpPtrs& P = c.policy; const MlpPtrs& TP = c.tpolicy;
   const double b1 = 0.9, b2 = 0.999, eps = c.hp.adam_eps;   // optimizer defaults (td3.py:56-67)
 
-  b.phase(); b.row(ROW_TD3_GATHER, B);
+  // tcgen05 programs (and only those: their last phase on every kind of step is a flat Adam / statistics phase that reads
+  // none of the gathered buffers) gather the batch of step s + 1 alongside the last active phase of step s (Builder::tail_row):
+  // 1024 random Humanoid rows are a 19 us phase of DRAM latency when gathered on the critical path
+  const bool hoist_gather = c.hp.use_tc5 != 0;
+  b.phase(hoist_gather ? COND_FIRST_STEP : COND_ALWAYS); b.row(ROW_TD3_GATHER, B);
   // HER-TD3 overwrites the target policy's action with clipped noise (her/td3.py:103-112): its forward pass is dead code
   const bool her = c.hp.her != 0;
   {
@@ -573,6 +587,7 @@ inline void build_td3(Builder& b, const Ctx& c) {
     b.adam(P, &c.tpolicy, c.hp.policy_lr, b1, b2, eps, c.hp.tau, SLOT_POLICY, 1);
     b.polyak(c.qf[0], c.tqf[0], c.hp.tau);
     b.polyak(c.qf[1], c.tqf[1], c.hp.tau);
+    if (hoist_gather) b.tail_row(ROW_TD3_GATHER, B);
     return;
   }
   b.phase(PC | COND_WORLD_1);
@@ -876,6 +891,11 @@ inline std::string describe_program(const Program& P) {
       out += line;
     }
     out += "\n";
+  }
+  if (P.ctx.tail_op1) {
+    const Op& o = P.ops[P.ctx.tail_op1 - 1];
+    snprintf(line, sizeof(line), "with the last active phase of every step: ROW(k%d,%d) for step s+1, jobs=%d\n", o.row.kind, o.row.rows, o.n_jobs);
+    out += line;
   }
   return out;
 }

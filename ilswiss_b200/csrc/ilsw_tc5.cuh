@@ -310,6 +310,34 @@ __device__ __noinline__ bool gemm_tile(const GemmOp& og, int tile, unsigned char
       if (tid == 64) TC5_STAMP(2, kb + 1);
     }
   }
+  // ---- epilogue inputs (bias, mask source) are requested BEFORE the wait for the accumulator: their L2 round trip overlaps
+  // the tail of the MMA pipeline instead of following it (thread (rb = tid / 16, cg = tid % 16) owns columns 4 cg .. 4 cg + 3
+  // of rows rb, rb + 16, ... -- the mapping of the store loop below)
+  constexpr int kER = kBM / 16;            // 8 rows per thread
+  const int e_cg = tid & 15, e_rb = tid >> 4, e_n = n0 + 4 * e_cg;
+  const bool vec_h = o.mask != ACT_NONE && ((o.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(o.H) & 15) == 0) && (e_n + 3 < o.N);
+  float b4[4] = {0.f, 0.f, 0.f, 0.f};
+  float h[kER][4];
+  if (e_n < o.N) {
+    if (o.bias) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (e_n + j < o.N) b4[j] = __ldcg(o.bias + e_n + j);
+    }
+    if (o.mask != ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < kER; ++i) {
+        const int m = m0 + i * 16 + e_rb;
+        if (m < o.M) {
+          const float* hp = o.H + (size_t)m * o.ldh + e_n;
+          if (vec_h) { const float4 t4 = __ldcg(reinterpret_cast<const float4*>(hp)); h[i][0] = t4.x; h[i][1] = t4.y; h[i][2] = t4.z; h[i][3] = t4.w; }
+          else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[i][j] = (e_n + j < o.N) ? __ldcg(hp + j) : 0.f;
+          }
+        }
+      }
+    }
+  }
   // ---- epilogue: accumulator ready when every MMA of this tile has retired
   if (tid == 128) TC5_STAMP(3, 0);
   if (!mbar_wait(&sy.acc_full, st.ntile & 1u)) ok = false;
@@ -345,54 +373,41 @@ __device__ __noinline__ bool gemm_tile(const GemmOp& og, int tile, unsigned char
   __syncthreads();
   if (tid == 128) TC5_STAMP(3, 2);
   {
-    const int cg = tid & 15, rb = tid >> 4;
-    const int n = n0 + 4 * cg;
+    const int cg = e_cg, rb = e_rb, n = e_n;
     float* Cb = o.C + (size_t)ks * o.split_stride;
     const bool vec_c = ((o.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0) && (n + 3 < o.N);
-    const bool vec_h = o.mask != ACT_NONE && ((o.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(o.H) & 15) == 0) && (n + 3 < o.N);
-    float b4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (o.bias) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (n + j < o.N) b4[j] = __ldcg(o.bias + n + j);
-    }
+    // the epilogue kind is decided ONCE per tile; the three kinds the step programs use are straight-line loops
+    const int kind = (o.act == ACT_NONE && o.mask == ACT_NONE) ? 0 : (o.act == ACT_RELU && o.mask == ACT_NONE) ? 1
+                   : (o.act == ACT_NONE && o.mask == ACT_RELU) ? 2 : 3;
     if (n < o.N) {
-      constexpr int R = kBM / 16;          // 8 rows per thread
-      float h[R][4];
-      if (o.mask != ACT_NONE) {            // all mask loads in flight before the first store
-#pragma unroll
-        for (int i = 0; i < R; ++i) {
-          const int m = m0 + i * 16 + rb;
-          if (m < o.M) {
-            const float* hp = o.H + (size_t)m * o.ldh + n;
-            if (vec_h) { const float4 t4 = __ldcg(reinterpret_cast<const float4*>(hp)); h[i][0] = t4.x; h[i][1] = t4.y; h[i][2] = t4.z; h[i][3] = t4.w; }
-            else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) h[i][j] = (n + j < o.N) ? __ldcg(hp + j) : 0.f;
-            }
-          }
-        }
+#define ILSW_TC5_STORE_ROWS(EXPR) \
+      _Pragma("unroll") \
+      for (int i = 0; i < kER; ++i) { \
+        const int row = i * 16 + rb, m = m0 + row; \
+        if (m < o.M) { \
+          const float4 a4 = *reinterpret_cast<const float4*>(T + row * kTLd + 4 * cg); \
+          float a[4] = {a4.x + b4[0], a4.y + b4[1], a4.z + b4[2], a4.w + b4[3]}; \
+          _Pragma("unroll") \
+          for (int j = 0; j < 4; ++j) { EXPR; } \
+          float* cp = Cb + (size_t)m * o.ldc + n; \
+          if (vec_c) *reinterpret_cast<float4*>(cp) = make_float4(a[0], a[1], a[2], a[3]); \
+          else { \
+            _Pragma("unroll") \
+            for (int j = 0; j < 4; ++j) if (n + j < o.N) cp[j] = a[j]; \
+          } \
+        } \
       }
-#pragma unroll
-      for (int i = 0; i < R; ++i) {
-        const int row = i * 16 + rb, m = m0 + row;
-        if (m < o.M) {
-          const float4 a4 = *reinterpret_cast<const float4*>(T + row * kTLd + 4 * cg);
-          float a[4] = {a4.x + b4[0], a4.y + b4[1], a4.z + b4[2], a4.w + b4[3]};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (o.act == ACT_RELU) a[j] = fmaxf(a[j], 0.f);
-            else if (o.act == ACT_TANH) a[j] = tanhf(a[j]);
-            if (o.mask == ACT_RELU) a[j] = h[i][j] > 0.f ? a[j] : 0.f;
-            else if (o.mask == ACT_TANH) a[j] *= (1.0f - h[i][j] * h[i][j]);
-          }
-          float* cp = Cb + (size_t)m * o.ldc + n;
-          if (vec_c) *reinterpret_cast<float4*>(cp) = make_float4(a[0], a[1], a[2], a[3]);
-          else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) if (n + j < o.N) cp[j] = a[j];
-          }
-        }
+      if (kind == 0) { ILSW_TC5_STORE_ROWS((void)0) }
+      else if (kind == 1) { ILSW_TC5_STORE_ROWS(a[j] = fmaxf(a[j], 0.f)) }
+      else if (kind == 2) { ILSW_TC5_STORE_ROWS(a[j] = h[i][j] > 0.f ? a[j] : 0.f) }
+      else {
+        ILSW_TC5_STORE_ROWS(
+          if (o.act == ACT_RELU) a[j] = fmaxf(a[j], 0.f);
+          else if (o.act == ACT_TANH) a[j] = tanhf(a[j]);
+          if (o.mask == ACT_RELU) a[j] = h[i][j] > 0.f ? a[j] : 0.f;
+          else if (o.mask == ACT_TANH) a[j] *= (1.0f - h[i][j] * h[i][j]))
       }
+#undef ILSW_TC5_STORE_ROWS
     }
   }
   if (tid == 128) TC5_STAMP(3, 4);

@@ -242,6 +242,8 @@ struct Ctx {            // everything a row kernel needs
   float* loss_log;      // [max_steps x kLossSlots]
   float* stats;         // snapshot area (see ilsw_stats layout in include/ilswiss_b200.h)
   int stats_floats;
+  int tail_op1;         // 0: none; k + 1: ops[k] (a next-step row op, RowOp::arg0 = 1, owned by no phase) runs alongside the LAST
+                        // ACTIVE phase of every step -- which phase that is depends on the step (TD3 policy / statistics steps)
   unsigned long long* phase_ns;  // [2*(kMaxPhases+1)] globaltimer stamps of the LAST step of a launch (profiling):
                                  // [i] = after the barrier of phase i-1; [kMaxPhases+1+i] = CTA 0 finished its jobs of phase i
   unsigned long long* cta_ns;    // [kMaxPhases x kMaxGrid] (profiling on): every CTA's jobs-done time per phase, last step

@@ -154,12 +154,15 @@ int hs_train(void* p, const float* ring, int stride, int size, const float* erin
   a.update_mode = h->update_mode;
   a.her = h->her;
   const Program& P = h->prog;
-  for (int s = 0; s < n_steps; ++s)
+  for (int s = 0; s < n_steps; ++s) {
     for (int ph = 0; ph < P.n_phases; ++ph) {
       const Phase& phs = P.phases[ph];
       if (!phase_active(phs, P.ctx.hp, a, s)) continue;
       for (int j = 0; j < phs.op_count; ++j) run_op(h, P, P.ops[phs.op_begin + j], a, s);
     }
+    // the next-step row op (Ctx::tail_op1) runs with the last active phase of the step: sequentially, after it
+    if (P.ctx.tail_op1) run_op(h, P, P.ops[P.ctx.tail_op1 - 1], a, s);
+  }
   commit_counters(h->t, h->n_total, a, P.ctx.hp, n_steps);
   return 0;
 }
