@@ -29,9 +29,9 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: algo, O, A, B, ring capacity, extra
-    "sac_hopper": dict(algo="sac", O=11, A=3, B=256, N=1_000_000, target_entropy=None, reward_scale=1.0, beta_1=0.9),
+    "sac_hopper": dict(algo="sac", O=11, A=3, B=256, N=1_000_000, target_entropy=None, reward_scale=1.0, beta_1=0.9, steps_per_train_call=1000),
     "sac_ant": dict(algo="sac", O=111, A=8, B=256, N=1_000_000, target_entropy=-4.0, reward_scale=1.0, beta_1=0.9),
-    "gail_walker": dict(algo="gail", O=17, A=6, B=256, N=20_000, NE=4000, target_entropy=None, reward_scale=2.0, beta_1=0.25),
+    "gail_walker": dict(algo="gail", O=17, A=6, B=256, N=20_000, NE=4000, target_entropy=None, reward_scale=2.0, beta_1=0.25, steps_per_train_call=1000),
     "td3_humanoid": dict(algo="td3", O=376, A=17, B=1024, N=2_000_000),
     # exp_specs/her/her_pick_td3.yaml (her/td3.py): FetchPickAndPlace observation 25 + desired_goal 3, act 4, batch 4096, net_size 300
     "her_td3_pick": dict(algo="td3", her=True, O=28, A=4, B=4096, N=1_000_000, H=300),
@@ -389,13 +389,8 @@ def measure(name, args, K, W, rank, world, dist, flush, clock, peak, peak_src, e
 
     e2e_sync_dt = e2e_loop(False)
     e2e_dt = e2e_loop(True)
-    e2e = {"value": world * Ke / e2e_dt, "unit": "gradient-steps/s", "h2d_bytes_per_step": buf.ring.host_w * 4,
-           "d2h_bytes_per_step": 16 * 4, "steps": Ke,
-           "mode": "per-step API calls with host buffers: add_sample+flush (pinned H2D, side stream) -> 1-step launch -> "
-                   "loss D2H into a pinned ring (stream-ordered, collected once at the end)",
-           "value_with_host_sync_every_step": world * Ke / e2e_sync_dt}
     # train-call granularity (what _do_training does): burst of `launch` transitions + `launch` steps + loss log D2H
-    reps = 3
+    reps = max(3, -(-3000 // launch))          # >= 3000 gradient steps: a 20-step launch (driver default) alone is a 3 ms sample
     burst = dict(observations=rs.randn(launch, O), actions=rs.uniform(-1, 1, (launch, A)), rewards=rs.randn(launch, 1),
                  terminals=np.zeros((launch, 1)), next_observations=rs.randn(launch, O))
     sync_all()
@@ -409,6 +404,22 @@ def measure(name, args, K, W, rank, world, dist, flush, clock, peak, peak_src, e
     e2e_call = {"value": world * reps * launch / call_dt, "unit": "gradient-steps/s",
                 "h2d_bytes_per_step": buf.ring.host_w * 4, "d2h_bytes_per_step": 16 * 4,
                 "mode": "per train call: %d-transition burst H2D -> %d-step launch -> loss log D2H" % (launch, launch)}
+    # The headline e2e is measured at the call granularity the reference's OWN yaml of this workload uses
+    # (num_train_steps_per_train_call): sac_hopper.yaml:19-20 / gail_walker.yaml:39,51 train 1000 steps per train call,
+    # sac_ant.yaml:19-20 / td3_humanoid.yaml:21-22 ONE step per env step with the next get_actions waiting on it -- there
+    # the figure a user sees is the per-step loop WITH a host sync every step.
+    per_call = w.get("steps_per_train_call", 1)
+    per_step_sync = world * Ke / e2e_sync_dt
+    per_step_pipe = world * Ke / e2e_dt
+    if per_call > 1:
+        e2e = {"value": e2e_call["value"], "granularity": "train call of %d gradient steps (the workload's yaml: %d per call)" % (launch, per_call),
+               "mode": e2e_call["mode"]}
+    else:
+        e2e = {"value": per_step_sync, "granularity": "one gradient step per call, host sync after every step (the workload's yaml: 1 per call)",
+               "mode": "per step: add_sample + flush (pinned H2D, side stream) -> 1-step launch -> losses read on the host (mailbox poll)"}
+    e2e.update({"unit": "gradient-steps/s", "h2d_bytes_per_step": buf.ring.host_w * 4, "d2h_bytes_per_step": 16 * 4, "steps_per_step_loops": Ke,
+                "per_step_host_sync": per_step_sync, "per_step_pipelined": per_step_pipe, "per_train_call": e2e_call["value"],
+                "value_with_host_sync_every_step": per_step_sync})
 
     bytes_step = algorithmic_bytes_per_step(w)
     achieved = bytes_step * launch / (ms_per_launch / 1000.0) / 1e9

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -389,7 +390,13 @@ struct ilsw_trainer {
   Program* dev_prog;
   char* scratch;
   size_t scratch_bytes;
-  BarrierState* bar;
+  BarrierState* bar;      // [2]: launches alternate (bar_cur), each zeroes the other one
+  int bar_cur;
+  int bar_dirty;          // an aborted launch may leave its barrier state non-zero: the next launch memsets both
+  void* mail_host;        // pinned mapped mailbox: [0] u64 done sequence, [64..] loss rows of the latest launch
+  void* mail_dev;
+  unsigned long long mail_seq;     // sequence number of the latest launch
+  int mail_steps;                  // its step count
   int grid;
   int ctas;
   int tc5;                // engine variant with the tcgen05/TMA GEMM tile (ilsw_tc5.cuh)
@@ -544,8 +551,16 @@ extern "C" int ilsw_trainer_create(ilsw_trainer** out, const ilsw_trainer_config
   tr->sms = sms;
   int rc = trainer_build(tr);
   if (rc) { ilsw_trainer_destroy(tr); return rc; }
-  cudaError_t e = cudaMalloc(&tr->bar, sizeof(BarrierState));
-  if (e == cudaSuccess) e = cudaMemset(tr->bar, 0, sizeof(BarrierState));
+  // two barrier states used by alternate launches: a launch zeroes the one its successor will use (no memset node per launch)
+  cudaError_t e = cudaMalloc(&tr->bar, 2 * sizeof(BarrierState));
+  if (e == cudaSuccess) e = cudaMemset(tr->bar, 0, 2 * sizeof(BarrierState));
+  // host mailbox for the loss log (pinned + mapped; see RunArgs::mail_losses)
+  if (e == cudaSuccess) {
+    const size_t mb = 64 + (size_t)cfg->max_steps_per_call * kLossSlots * sizeof(float);
+    e = cudaHostAlloc(&tr->mail_host, mb, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e == cudaSuccess) { memset(tr->mail_host, 0, mb); e = cudaHostGetDevicePointer(&tr->mail_dev, tr->mail_host, 0); }
+    if (e != cudaSuccess) { tr->mail_host = nullptr; tr->mail_dev = nullptr; e = cudaSuccess; cudaGetLastError(); }   // optional: fall back to copies
+  }
   if (e != cudaSuccess) { ilsw_trainer_destroy(tr); return fail(ILSW_ERR_CUDA, "barrier alloc: %s", cudaGetErrorString(e)); }
   tr->rep.world = 1;
   *out = tr;
@@ -596,6 +611,7 @@ extern "C" int ilsw_trainer_destroy(ilsw_trainer* tr) {
   if (tr->tmaps) cudaFree(tr->tmaps);
   if (tr->dev_prog) cudaFree(tr->dev_prog);
   if (tr->bar) cudaFree(tr->bar);
+  if (tr->mail_host) cudaFreeHost(tr->mail_host);
   delete tr;
   return ILSW_OK;
 }
@@ -661,8 +677,16 @@ extern "C" int ilsw_train(ilsw_trainer* tr, ilsw_rb* policy_rb, ilsw_rb* expert_
   rp.grad = tr->host_prog.ctx.policy.g;
   rp.g_splits = tr->host_prog.ctx.policy.g_splits; rp.g_split_stride = tr->host_prog.ctx.policy.g_stride;
   const Program* dp = tr->dev_prog;
-  BarrierState* bar = tr->bar;
-  CU(cudaMemsetAsync(bar, 0, sizeof(BarrierState), st));   // monotonic barrier counter restarts at 0
+  if (tr->bar_dirty) { CU(cudaMemsetAsync(tr->bar, 0, 2 * sizeof(BarrierState), st)); tr->bar_dirty = 0; }
+  BarrierState* bar = tr->bar + tr->bar_cur;               // zeroed by the previous launch (or at creation)
+  a.bar_other = &tr->bar[tr->bar_cur ^ 1].count;
+  tr->bar_cur ^= 1;
+  if (tr->mail_dev) {
+    tr->mail_seq += 1; tr->mail_steps = n_steps;
+    a.mail_done = reinterpret_cast<unsigned long long*>(tr->mail_dev);
+    a.mail_losses = reinterpret_cast<float*>(reinterpret_cast<char*>(tr->mail_dev) + 64);
+    a.mail_seq = tr->mail_seq;
+  }
   void* args[] = {(void*)&dp, (void*)&a, (void*)&bar, (void*)&rp};
   const size_t smem = engine_smem(tr, tr->host_prog.n_ops);
   CU(cudaLaunchCooperativeKernel(engine_fn(tr), dim3(tr->grid), dim3(kThreads), args, smem, st));
@@ -679,13 +703,31 @@ static int check_abort(ilsw_trainer* tr, cudaStream_t st) {
   DynState d;
   CU(cudaMemcpyAsync(&d, tr->host_prog.ctx.dyn, sizeof(d), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  if (d.abort_flag) return fail(ILSW_ERR_ABORTED, "engine launch aborted (barrier/replica wait timed out)");
+  if (d.abort_flag) { tr->bar_dirty = 1; return fail(ILSW_ERR_ABORTED, "engine launch aborted (barrier/replica wait timed out)"); }
   return ILSW_OK;
+}
+// losses of the LATEST launch through the host mailbox: poll the sequence word the kernel publishes after its last step.
+// Returns 1 when served, 0 when the caller must take the copy path (no mailbox, other step count, or ~2 s without progress).
+static int mailbox_losses(ilsw_trainer* tr, float* host_out, int n_steps) {
+  if (!tr->mail_host || tr->mail_seq == 0 || n_steps > tr->mail_steps) return 0;
+  volatile unsigned long long* done = reinterpret_cast<volatile unsigned long long*>(tr->mail_host);
+  const unsigned long long want = tr->mail_seq;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (long long spin = 0; *done < want; ++spin) {
+    if ((spin & 4095) == 4095 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(6)) return 0;   // the engine's own watchdog fires after ~4 s
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  memcpy(host_out, reinterpret_cast<char*>(tr->mail_host) + 64, (size_t)n_steps * kLossSlots * sizeof(float));
+  return 1;
 }
 
 extern "C" int ilsw_read_losses(ilsw_trainer* tr, float* host_out, int n_steps, void* stream) {
   if (!tr || !host_out || n_steps <= 0 || n_steps > tr->spec.cfg.max_steps_per_call) return fail(ILSW_ERR_ARG, "read_losses: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
+  if (mailbox_losses(tr, host_out, n_steps)) return ILSW_OK;       // a launch that aborted never publishes: copy path below reports it
   CU(cudaMemcpyAsync(host_out, tr->host_prog.ctx.loss_log, (size_t)n_steps * kLossSlots * sizeof(float), cudaMemcpyDeviceToHost, st));
   return check_abort(tr, st);
 }

@@ -1275,6 +1275,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
   }
   if (threadIdx.x == 0) {
     s_gen = 0u; s_a = a_param; s_rp = rp_param;   // the host zeroes the barrier state before every launch
+    if (blockIdx.x == 0 && a_param.bar_other) *a_param.bar_other = 0u;     // the previous launch's barrier state: idle, reused by the next
     tc5::mbar_init(&s_tma_bar[0], 1); tc5::mbar_init(&s_tma_bar[1], 1);
     tc5::fence_barrier_init();
   }
@@ -1382,6 +1383,15 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
       if (!grid_barrier(bar, gridDim.x, gen, abort_flag)) ILSW_DIE()
       if (stamp) c.phase_ns[ph + 1] = globaltimer_ns();
     }
+  }
+  // the launch's losses go to the host mailbox (every loss row was written before the last grid barrier of its step)
+  if (ILSW_ALIVE && blockIdx.x == 0 && a.mail_losses) {
+    const int nl = a.n_steps * kLossSlots;
+    const float* src = c.loss_log + (size_t)a.loss_log_offset * kLossSlots;
+    for (int i = threadIdx.x; i < nl; i += kThreads) a.mail_losses[i] = __ldcg(src + i);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.mail_done), "l"(a.mail_seq) : "memory");
   }
   if constexpr (TC5) tc5::teardown<kTc5BN>(s_tc5);
 #undef ILSW_ALIVE

@@ -289,6 +289,13 @@ struct RunArgs {
   int profile;          // 1: CTA 0 stamps the stages of its GEMM tiles (tools/phase_profile.py); 0 in production
   int update_mode;      // UpdateMode (AdvIRL programs only)
   HerSampling her;
+  // host mailbox (pinned, mapped): after the last step CTA 0 copies the launch's loss rows there and publishes `mail_seq`
+  // with a system-scope release store -- the host reads a launch's losses by polling memory, without a stream
+  // synchronisation or a copy of its own (ilsw_read_losses)
+  float* mail_losses;                  // [max_steps x kLossSlots] device view of the mapped buffer; nullptr: off
+  unsigned long long* mail_done;       // device view of the sequence word
+  unsigned long long mail_seq;         // value to publish for this launch
+  unsigned* bar_other;                 // counter of the barrier state the NEXT launch uses: zeroed by this launch
 };
 
 struct Program {
