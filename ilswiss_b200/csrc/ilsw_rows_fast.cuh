@@ -168,7 +168,16 @@ ILSW_HD void cta_stage_multi(const RowEnv& e, const StageReq (&rq)[N], SPtr (&ou
     out[r].p = nullptr; out[r].off = rq[r].off;
     const float* src = rq[r].src;
     const int n = rq[r].n;
-    if ((STRIDED_MASK >> r) & 1) {
+    if (((STRIDED_MASK >> r) & 1) && rq[r].inner <= T && n <= U * rq[r].inner) {
+      // common strided shape (W0[:, O:O+A] of a critic: inner = hidden <= 256 threads, A <= 8 blocks): thread -> nn = tid,
+      // slot u -> j = u.  No index division / carry chain, and a thread's A loads are adjacent words of ONE row of W0
+      // (same 32-byte sector) instead of A different rows: the generic form below cost ~4 us of the 9 us staging stage of
+      // the policy-backward row job (profiles/r2_phase_profile.txt, ROW(k29))
+      const int inner = rq[r].inner, si = rq[r].s_inner;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (u * inner < n) v[r][u] = (tid < inner) ? __ldcg(src + (size_t)tid * si + u) : 0.f;
+    } else if ((STRIDED_MASK >> r) & 1) {
       const int inner = rq[r].inner, si = rq[r].s_inner;
       int j = tid / inner, nn = tid - j * inner;
       const int dj = T / inner, dn = T - dj * inner;
@@ -188,13 +197,21 @@ ILSW_HD void cta_stage_multi(const RowEnv& e, const StageReq (&rq)[N], SPtr (&ou
   }
 #pragma unroll
   for (int r = 0; r < N; ++r) {
+    if (((STRIDED_MASK >> r) & 1) && rq[r].inner <= T && rq[r].n <= U * rq[r].inner) {
+      const int inner = rq[r].inner;
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (u * T < rq[r].n && tid + u * T < rq[r].n) ilsw_dyn_smem_f[rq[r].off + tid + u * T] = v[r][u];
+      for (int u = 0; u < U; ++u)
+        if (u * inner < rq[r].n && tid < inner) ilsw_dyn_smem_f[rq[r].off + u * inner + tid] = v[r][u];
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (u * T < rq[r].n && tid + u * T < rq[r].n) ilsw_dyn_smem_f[rq[r].off + tid + u * T] = v[r][u];
+    }
   }
   // blocks larger than U*T elements (wide action spaces): the rest in plain loops
 #pragma unroll
   for (int r = 0; r < N; ++r) {
+    if (((STRIDED_MASK >> r) & 1) && rq[r].inner <= T && rq[r].n <= U * rq[r].inner) continue;
     for (int i = U * T + tid; i < rq[r].n; i += T) {
       const int inner = rq[r].inner;
       const size_t idx = ((STRIDED_MASK >> r) & 1) ? (size_t)(i % inner) * rq[r].s_inner + i / inner : (size_t)i;
