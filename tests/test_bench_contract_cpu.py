@@ -41,3 +41,24 @@ def test_algorithmic_bytes_match_the_survey():
     exp = {"sac_hopper": 6_190_312, "sac_ant": 8_796_632, "gail_walker": 6_947_216, "td3_humanoid": 15_171_912}
     for name, want in exp.items():
         assert int(bench.algorithmic_bytes_per_step(bench.WORKLOADS[name])) == want, name
+
+
+def test_round2_default_line_covers_the_other_baseline_configs():
+    """the default bench line carries GAIL Walker / TD3 Humanoid / SAC Ant sub-records measured the same way,
+    the real launch size, and (N > 1) the replica check."""
+    for fn in ("r2_bench_sac_hopper.json", "r2_bench_sac_hopper_steps20.json"):
+        d = json.load(open(os.path.join(ROOT, "profiles", fn)))
+        assert set(d["workloads"]) == {"gail_walker", "td3_humanoid", "sac_ant"}
+        for name, r in d["workloads"].items():
+            for k in ("value", "ms_per_step", "e2e", "roofline", "cpu_baseline", "gpu_launches"):
+                assert k in r, (name, k)
+            assert r["e2e"]["value"] > 0 and r["gpu_launches"] > 0
+        launch = min(1000, d["steps"])
+        assert d["roofline"]["launch_steps"] == launch and ("%d gradient steps per kernel launch" % launch) in d["config"]["workload"]
+        assert d["cpu_baseline"]["kind"] == "reference"          # the reference's own rlkit classes (baseline/_ref)
+        assert d["clocks"]["samples"] > 0
+    for fn, n in (("r2_bench_sac_hopper_n2.json", 2), ("r2_bench_sac_hopper_n8.json", 8)):
+        d = json.load(open(os.path.join(ROOT, "profiles", fn)))
+        assert d["n_gpus"] == n and set(d["workloads"]) == {"sac_ant"}
+        for name, c in d["replica_check"].items():
+            assert c["equal"] and c["ok"] and c["world"] == n, (fn, name, c)
