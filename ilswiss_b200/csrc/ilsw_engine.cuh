@@ -727,6 +727,33 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
   const bool full = (n_mt == 2) && (n_nt == 4);
   // epilogue mapping: thread -> (row = tid / 8, 4 consecutive columns)
   const int er = m0 + (tid >> 3), ec = n0 + ((tid & 7) << 2);
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+  // Stage 0 and the epilogue inputs are requested FIRST: the accumulator / fragment-address set-up below (~100 dependent
+  // instructions at 8 warps per SM) then runs while the panels are in flight instead of in front of them
+  ILSW_TSTAMP(0);
+  {
+    const int klen0 = min(kKC, o.K);
+    if (o.tma) tc_tma_stage(o, sbase, 4u * (unsigned)kOperandFloats, m0, n0, 0, klen0, &tma.bar[0]);
+    if (o.tma != 3) tc_fill_stage<KC>(og, smem, m0, n0, 0, klen0, vecA, vecB, o.tma);
+    cp_async_commit();
+    if (fz)           // the B panel is in flight; produce the A panel meanwhile
+      tc_produce_l0<KC>(*fz, o.M, smem, m0, 0, klen0, tn == 0, mode);
+#if ILSW_EIN_CPASYNC
+    const unsigned sc = sbase + 4u * (unsigned)(TcGeom<KC>::kSmemFloats + tid);
+    if (er < o.M) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (ec + i < Nt) {
+          if (o.bias) cp_async4(sc + 4u * (unsigned)(i * kThreads), o.bias + ec + i);
+          if (o.mask != ACT_NONE) cp_async4(sc + 4u * (unsigned)((4 + i) * kThreads), o.H + (size_t)er * o.ldh + ec + i);
+          if (o.accumulate) cp_async4(sc + 4u * (unsigned)((8 + i) * kThreads), o.C + (size_t)er * o.ldc + ec + i);
+        }
+      }
+    }
+    cp_async_commit();
+#endif
+  }
+  ILSW_TSTAMP(1);
   float acc[8][4];
 #pragma unroll
   for (int u = 0; u < 8; ++u)
@@ -739,10 +766,8 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
   int gi[4] = {-1, -1, -1, -1}, gib = -1;
   float am[4], av[4], ap[4], at[4], bm = 0.f, bv = 0.f, bp = 0.f, bt = 0.f;
 #endif
-  ILSW_TSTAMP(0);
-  // epilogue inputs (bias / mask source / previous value, Adam state) are requested BEFORE the panel copies: behind
-  // 64 KB of cp.async traffic in the load/store queue they would return last
-#if ILSW_EIN_FIRST
+  // epilogue inputs by register loads (builds without ILSW_EIN_CPASYNC)
+#if ILSW_EIN_FIRST || !ILSW_EIN_CPASYNC
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     if (er < o.M && ec + i < Nt) ein[i] = epi_load(o, er, ec + i);
@@ -766,7 +791,6 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
   ILSW_ADAM_STATE_LOADS();
 #endif
   // fragment addressing (32-bit shared addresses, bytes)
-  const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
   const bool a_tma = (o.tma & 1) != 0, b_tma = (o.tma & 2) != 0;
   // per operand: offset of this lane's first fragment word for k-step `warp` (x_w), advance per 8 k-steps (x_it), and the
   // offsets between the fragment words of one k-step.  The TMA layouts are swizzled; all offsets wrap in 32 bits.
@@ -793,7 +817,7 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
     b_k4 = 4u * (b_kc ? 4 : 4 * kMS); b_nt = 4u * (b_kc ? 8 * kKS : 8); b_nt2 = 2u * b_nt;
   }
 #pragma unroll 1
-  for (int st = -1; st < nstages; ++st) {
+  for (int st = 0; st < nstages; ++st) {
     if (st + 1 < nstages) {
       const int k0 = (st + 1) * kKC;
       if (o.tma) tc_tma_stage(o, sbase + 4u * (unsigned)(((st + 1) & 1) * kTcStageFloats), 4u * (unsigned)kOperandFloats, m0, n0, k0,
@@ -802,30 +826,6 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
       cp_async_commit();
       if (fz)           // the B panel is in flight; produce the A panel meanwhile
         tc_produce_l0<KC>(*fz, o.M, smem + ((st + 1) & 1) * kTcStageFloats, m0, k0, min(kKC, o.K - k0), tn == 0, mode);
-    }
-    if (st < 0) {
-#if ILSW_EIN_CPASYNC
-      {
-        const unsigned sc = sbase + 4u * (unsigned)(TcGeom<KC>::kSmemFloats + tid);
-        if (er < o.M) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (ec + i < Nt) {
-              if (o.bias) cp_async4(sc + 4u * (unsigned)(i * kThreads), o.bias + ec + i);
-              if (o.mask != ACT_NONE) cp_async4(sc + 4u * (unsigned)((4 + i) * kThreads), o.H + (size_t)er * o.ldh + ec + i);
-              if (o.accumulate) cp_async4(sc + 4u * (unsigned)((8 + i) * kThreads), o.C + (size_t)er * o.ldc + ec + i);
-            }
-          }
-        }
-        cp_async_commit();
-      }
-#elif !ILSW_EIN_FIRST
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (er < o.M && ec + i < Nt) ein[i] = epi_load(o, er, ec + i);
-#endif
-      ILSW_TSTAMP(1);
-      continue;
     }
     if (st + 1 < nstages) cp_async_wait<1>(); else cp_async_wait<0>();
     if (o.tma) {       // every consuming thread observes the completion of the stage's boxes
@@ -1246,6 +1246,9 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
   __shared__ PushCtx s_push;
   __shared__ unsigned long long s_tma_bar[2];  // stage barriers of the mma.sync tile's TMA panels (tc_tma_stage)
   __shared__ int s_last_ph;                    // last active phase of the current step (hosts Ctx::tail_op1)
+  __shared__ int s_job0[kMaxPhases];           // (op index << 16 | job within the op) of this CTA's FIRST job of every phase, -1: none
+  __shared__ unsigned char s_pinfo[kMaxPhases];  // per phase, resolved once per launch: 1 = can be active in this launch, 2 = also has a
+                                                 // per-step condition (first step / TD3 policy / statistics step), 4 = exchange, 8 = push
   const int n_phases = prog->n_phases, n_ops = prog->n_ops;
   constexpr int KC = CTAS == 2 ? 128 : 256;
   unsigned char* pbase = dyn_smem + engine_staging_bytes(CTAS, TC5);
@@ -1293,6 +1296,27 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
       }
   }
   __syncthreads();
+  // job -> (op, local job) of this CTA's first job per phase, resolved once per launch: the dispatch of a phase is then one
+  // shared-memory load instead of a dependent walk over the phase's op list behind every grid barrier
+  for (int ph = threadIdx.x; ph < n_phases; ph += kThreads) {
+    const Phase& P = s_phases[ph];
+    int j = (int)blockIdx.x, oi = P.op_begin, v = -1;
+    if (j < P.total_jobs) {
+      while (j >= s_ops[oi].n_jobs) { j -= s_ops[oi].n_jobs; ++oi; }
+      v = (oi << 16) | j;
+    }
+    s_job0[ph] = v;
+    // launch-invariant half of phase_active(): replica count and update mode are fixed for the launch
+    const RunArgs& a0 = s_a;
+    bool on = true;
+    if ((P.cond & COND_DISC_PART) && a0.update_mode == UPDATE_POLICY_ONLY) on = false;
+    if ((P.cond & COND_POLICY_PART) && a0.update_mode == UPDATE_DISC_ONLY) on = false;
+    if ((P.cond & COND_WORLD_1) && a0.world > 1) on = false;
+    if ((P.cond & COND_WORLD_N) && a0.world <= 1) on = false;
+    const bool dyn = (P.cond & (COND_FIRST_STEP | COND_TD3_POLICY | COND_TD3_POLICY_OR_STATS)) != 0;
+    s_pinfo[ph] = (unsigned char)((on ? 1 : 0) | (dyn ? 2 : 0) | ((P.collective && s_rp.world > 1) ? 4 : 0) | ((P.push && s_rp.world > 1) ? 8 : 0));
+  }
+  __syncthreads();
   const Ctx& c = *s_ctx;
   int* abort_flag = &c.dyn->abort_flag;
   unsigned gen = s_gen;
@@ -1321,13 +1345,14 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
     __syncthreads();
     for (int ph = 0; ph < n_phases && ILSW_ALIVE; ++ph) {
       const Phase& P = s_phases[ph];
-      if (!phase_active(P, c.hp, a, s)) { if (stamp) c.phase_ns[ph + 1] = c.phase_ns[ph]; continue; }
-      const bool exchange = P.collective && rp.world > 1;
+      const unsigned pinfo = s_pinfo[ph];
+      if (!(pinfo & 1u) || ((pinfo & 2u) && !phase_active(P, c.hp, a, s))) { if (stamp) c.phase_ns[ph + 1] = c.phase_ns[ph]; continue; }
+      const bool exchange = (pinfo & 4u) != 0, pushing = (pinfo & 8u) != 0;
       // exchange sequence number = number of policy updates so far (parity double-buffers the slots)
-      const unsigned xseq = rp.seq0 + (unsigned)(adam_t(a, c.hp, SLOT_POLICY, s) - a.t0[SLOT_POLICY]);
+      unsigned xseq = 0u;
+      if (pinfo & 12u) xseq = rp.seq0 + (unsigned)(adam_t(a, c.hp, SLOT_POLICY, s) - a.t0[SLOT_POLICY]);
       if (exchange && P.collective == 1 && !replica_exchange(rp, xseq, bar, gen, abort_flag)) ILSW_DIE()
       if (exchange && P.collective == 2 && !replica_wait_pushes(rp, xseq, abort_flag)) ILSW_DIE()
-      const bool pushing = P.push && rp.world > 1;
       if (pushing) {       // this rank's receive slot (parity of this update) on every replica
         if (threadIdx.x < rp.world)
           s_push.peer[threadIdx.x] = rp.recv_peer[threadIdx.x] + ((size_t)(xseq & 1u) * rp.world + rp.rank) * (size_t)rp.nstride;
@@ -1342,6 +1367,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
       for (int job = blockIdx.x; job < P.total_jobs + tail_jobs && ILSW_ALIVE; job += gridDim.x) {
         int j = job, oi = P.op_begin;
         if (job >= P.total_jobs) { j = job - P.total_jobs; oi = c.tail_op1 - 1; }
+        else if (job == (int)blockIdx.x) { const int v = s_job0[ph]; oi = v >> 16; j = v & 0xffff; }
         else { while (j >= s_ops[oi].n_jobs) { j -= s_ops[oi].n_jobs; ++oi; } }
         const Op& o = s_ops[oi];
         if (o.kind == OP_GEMM) {
@@ -1380,6 +1406,17 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
       if (pushing) replica_signal_pushes(rp);
       if (stamp) c.phase_ns[kMaxPhases + 1 + ph] = globaltimer_ns();
       if (a.profile && s == a.n_steps - 1 && threadIdx.x == 0 && blockIdx.x < kMaxGrid) c.cta_ns[ph * kMaxGrid + blockIdx.x] = globaltimer_ns();
+      // descriptor prefetch for this CTA's first tile of the next phase (a wrong guess -- inactive phase -- is harmless)
+      if (threadIdx.x == 0) {
+        const int nph = ph + 1 < n_phases ? ph + 1 : 0, v = s_job0[nph];
+        if (v >= 0) {
+          const Op& no = s_ops[v >> 16];
+          if (no.kind == OP_GEMM && (no.gemm.tma || no.gemm.tc5)) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(no.gemm.tmapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(no.gemm.tmapB) : "memory");
+          }
+        }
+      }
       if (!grid_barrier(bar, gridDim.x, gen, abort_flag)) ILSW_DIE()
       if (stamp) c.phase_ns[ph + 1] = globaltimer_ns();
     }
