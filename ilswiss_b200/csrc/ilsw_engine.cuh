@@ -371,7 +371,16 @@ template <int KC> struct TcGeom {
   static constexpr int kStageFloats = 2 * kOperandFloats;
   static constexpr int kSmemFloats = 2 * kStageFloats;  // 2 stages x (A,B): 160 KB (KC=256) / 80 KB (KC=128)
 };
-constexpr int tc_smem_floats(int ctas) { return ctas == 2 ? TcGeom<128>::kSmemFloats : TcGeom<256>::kSmemFloats; }
+// K per stage of the one-CTA/SM variant.  128 (two stages of 40 KB: a K = 256 GEMM has both stages in flight at once) keeps the
+// kernel's dynamic shared memory near 105 KB, so the SM's unified L1/shared carve-out leaves 124 KB of L1 instead of 60 KB
+// (256: 190 KB of shared memory) -- the engine spills to a 1.8 KB stack frame and every phase starts with a cold L1, so the
+// L1 size is worth more than the single-stage K = 256 panel (measured: growing shared memory past the next carve-out step,
+// 28 KB of L1, cost 16 us per SAC step).
+#ifndef ILSW_KC1
+#define ILSW_KC1 128
+#endif
+constexpr int kKC1 = ILSW_KC1;
+constexpr int tc_smem_floats(int ctas) { return ctas == 2 ? TcGeom<128>::kSmemFloats : TcGeom<kKC1>::kSmemFloats; }
 // bytes of the GEMM staging area at the start of dynamic shared memory; the tcgen05 engine variant (one CTA per SM)
 // also fits the TMA stages of ilsw_tc5.cuh (+ 1 KB to align them to the 1024-byte swizzle atom)
 constexpr int kEpiScratchFloats = 12 * kThreads;      // [12 slots][256 threads]: bias, mask source, previous value x 4 columns
@@ -699,7 +708,7 @@ constexpr int kRedFloats = 8 * 32 * kRedLd;   // 36 KB: fits one staging stage o
 // fragment word feeds 2-4 MMAs), then the 8 partial tiles are summed through shared memory in warp order
 // (fixed order: bit-reproducible).  Measured predecessor (one 16x8 accumulator per warp over the full K,
 // 96 dependent MMAs): 3.3 us of a 5.9 us tile.
-template <int KC>
+template <int KC, int CT>      // CT: CTAs per SM of the engine variant (register budget 255 / 128)
 __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* smem, int mode, int prof_phase, const AdamOp* ad, const AdamCoef* cf, const PushCtx* push, const L0FuseOp* fz, TmaState& tma) {
   constexpr int kKC = KC, kKS = TcGeom<KC>::kKS, kOperandFloats = TcGeom<KC>::kOperandFloats, kTcStageFloats = TcGeom<KC>::kStageFloats;
   static_assert(kRedFloats <= TcGeom<KC>::kStageFloats, "partial tiles must fit one stage");
@@ -844,7 +853,7 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
       FragSet f0, f1;
       int ks = warp;
       if (ks < ksteps) fragset_load(f0, pa, a_row8, a_k4, a_mt, pb, b_k4, b_nt, b_nt2);
-      if (full && KC == 128 && ILSW_TC128_SIMPLE) {
+      if (full && CT == 2 && ILSW_TC128_SIMPLE) {
         // two CTAs per SM (128-register cap): one fragment set, no ping-pong -- four warps per scheduler hide the shared
         // memory latency, and the second fragment set is what pushed this variant into local-memory spills
 #pragma unroll 1
@@ -1250,7 +1259,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
   __shared__ unsigned char s_pinfo[kMaxPhases];  // per phase, resolved once per launch: 1 = can be active in this launch, 2 = also has a
                                                  // per-step condition (first step / TD3 policy / statistics step), 4 = exchange, 8 = push
   const int n_phases = prog->n_phases, n_ops = prog->n_ops;
-  constexpr int KC = CTAS == 2 ? 128 : 256;
+  constexpr int KC = CTAS == 2 ? 128 : kKC1;
   unsigned char* pbase = dyn_smem + engine_staging_bytes(CTAS, TC5);
   // tcgen05 variant only (the B = 256 variant keeps its loop state minimal: everything live across a grid barrier that
   // does not fit the register file is reloaded from local memory through L2 -- the barrier's acquire invalidates L1)
@@ -1384,7 +1393,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
           } else if (TC5 && gemm_is_skinny(o.gemm) && o.gemm.ksplit > 1) gemm_tile_skinny_split(o.gemm, j, smem);
           else if (gemm_is_skinny(o.gemm)) gemm_tile_skinny(o.gemm, j, smem, ad, cf, push);
           else if (prec == 0) gemm_tile_device(o.gemm, j, smem, ad, cf, push, fz);
-          else gemm_tile_tc<KC>(o.gemm, j, tile_smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, ad, cf, push, fz, tma_state);
+          else gemm_tile_tc<KC, CTAS>(o.gemm, j, tile_smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, ad, cf, push, fz, tma_state);
         } else if (o.kind == OP_ROW) {
           RowEnv env; env.lane = lane; env.nl = 32; env.warp = warp; env.sm = smem;
           env.prof = (a.profile && blockIdx.x == 0) ? ph : -1;
