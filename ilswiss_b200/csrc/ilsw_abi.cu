@@ -426,7 +426,7 @@ static const void* engine_fn(const ilsw_trainer* tr) {
   return tr->ctas == 2 ? (const void*)ilsw_engine_kernel<2, false> : (const void*)ilsw_engine_kernel<1, false>;
 }
 static size_t engine_smem(const ilsw_trainer* tr, int n_ops) {
-  return engine_staging_bytes(tr->ctas, tr->tc5 != 0) + ((sizeof(Phase) * kMaxPhases + 15) & ~size_t(15)) +
+  return engine_staging_bytes(tr->ctas, tr->tc5 != 0) + ((sizeof(Phase) * (size_t)tr->host_prog.n_phases + 15) & ~size_t(15)) +
          ((sizeof(Op) * (size_t)n_ops + 15) & ~size_t(15)) + sizeof(Ctx) + 64;
 }
 // occupancy variant + launch geometry of the program just built

@@ -1274,7 +1274,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
 #define ILSW_ALIVE (!TC5 || alive)
 #define ILSW_DIE() { if constexpr (TC5) { alive = false; break; } else { return; } }
   Phase* s_phases = reinterpret_cast<Phase*>(pbase);
-  Op* s_ops = reinterpret_cast<Op*>(pbase + align16(sizeof(Phase) * kMaxPhases));
+  Op* s_ops = reinterpret_cast<Op*>(pbase + align16(sizeof(Phase) * (size_t)n_phases));
   Ctx* s_ctx = reinterpret_cast<Ctx*>(reinterpret_cast<unsigned char*>(s_ops) + align16(sizeof(Op) * (size_t)n_ops));
   {
     const int* src; int* dst; int n;

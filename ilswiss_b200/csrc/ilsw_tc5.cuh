@@ -33,7 +33,13 @@ namespace tc5 {
 
 constexpr int kBM = 128;          // tile rows = TMEM lanes (cta_group::1, M = 128)
 constexpr int kBK = 32;           // K per stage: one 128-byte swizzle row of fp32
-constexpr int kStages = 4;
+// 3 stages of 48 KB (147 KB + program copy: the 164 KB carve-out step, 92 KB of L1) instead of 4 (196 KB: 228 KB step, 28 KB of
+// L1).  The K loop is paced by shared-memory bandwidth at 0.65 us per block, TMA latency is ~1.2 us: three blocks in flight
+// cover it, and the engine's spill traffic gets three times the L1 (see ILSW_KC1 in ilsw_engine.cuh).
+#ifndef ILSW_TC5_STAGES
+#define ILSW_TC5_STAGES 3
+#endif
+constexpr int kStages = ILSW_TC5_STAGES;
 constexpr int kSplitWarps = 6;    // warps 2..7
 constexpr int kSplitGroupWarps = 3;   // two groups, alternate K blocks
 constexpr int kOnesBytes = 2048;  // 16 rows x 128 B of 1.0f (B operand of the bias-gradient MMAs)
