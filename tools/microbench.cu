@@ -62,6 +62,25 @@ __device__ __forceinline__ void bar_v3(Bar* b, unsigned n, unsigned& gen) {
   __syncthreads(); gen++;
 }
 
+// variant 5/6: NPOLL warps poll the counter (their requests are naturally staggered, so the completion is seen after a
+// fraction of a round trip on average), whoever sees it first releases the CTA through a shared-memory flag; no closing
+// __syncthreads
+template <int NPOLL>
+__device__ __forceinline__ void bar_multi(Bar* b, unsigned n, unsigned& gen) {
+  __shared__ volatile unsigned s_flag;
+  __syncthreads();
+  const unsigned target = (gen + 1) * n, want = gen + 1;
+  if (threadIdx.x == 0) red_add_release(&b->count, 1);
+  if ((threadIdx.x >> 5) < NPOLL) {
+    while (s_flag != want) {
+      if ((int)(ld_acquire_gpu(&b->count) - target) >= 0) { s_flag = want; break; }
+    }
+  } else {
+    while (s_flag != want) {}
+  }
+  gen++;
+}
+
 template <int V>
 __global__ void __launch_bounds__(256, 1) k_bar(Bar* b, int iters, unsigned gen0, float* sink, int work) {
   unsigned gen = gen0;
@@ -72,6 +91,9 @@ __global__ void __launch_bounds__(256, 1) k_bar(Bar* b, int iters, unsigned gen0
     else if (V == 1) bar_v1(b, gridDim.x, gen);
     else if (V == 2) bar_v2(b, gridDim.x, gen);
     else if (V == 3) bar_v3(b, gridDim.x, gen);
+    else if (V == 5) bar_multi<2>(b, gridDim.x, gen);
+    else if (V == 6) bar_multi<4>(b, gridDim.x, gen);
+    else if (V == 7) bar_multi<1>(b, gridDim.x, gen);
     else cg::this_grid().sync();
   }
   if (acc < 0) sink[0] = acc;
@@ -114,6 +136,9 @@ int main() {
     printf("work=%d  v2(fence + relaxed atom/poll + fence): %.0f ns\n", work, run_bar<2>(b, grid, iters, sink, work, gen));
     printf("work=%d  v3(per-CTA flags + master): %.0f ns\n", work, run_bar<3>(b, grid, iters, sink, work, gen));
     printf("work=%d  v4(cooperative_groups grid.sync): %.0f ns\n", work, run_bar<4>(b, grid, iters, sink, work, gen));
+    printf("work=%d  v7(1 polling warp + shared flag, no closing sync): %.0f ns\n", work, run_bar<7>(b, grid, iters, sink, work, gen));
+    printf("work=%d  v5(2 polling warps + shared flag): %.0f ns\n", work, run_bar<5>(b, grid, iters, sink, work, gen));
+    printf("work=%d  v6(4 polling warps + shared flag): %.0f ns\n", work, run_bar<6>(b, grid, iters, sink, work, gen));
   }
   for (int g : {8, 32, 74}) printf("grid=%d v1: %.0f ns\n", g, run_bar<1>(b, g, iters, sink, 1, gen));
   // L2 pointer chase (working set 4 MB, resident in L2)
