@@ -712,7 +712,9 @@ template <int KC, int CT>      // CT: CTAs per SM of the engine variant (registe
 __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* smem, int mode, int prof_phase, const AdamOp* ad, const AdamCoef* cf, const PushCtx* push, const L0FuseOp* fz, TmaState& tma) {
   constexpr int kKC = KC, kKS = TcGeom<KC>::kKS, kOperandFloats = TcGeom<KC>::kOperandFloats, kTcStageFloats = TcGeom<KC>::kStageFloats;
   static_assert(kRedFloats <= TcGeom<KC>::kStageFloats, "partial tiles must fit one stage");
-  const GemmOp o = og;                       // registers / local copy: the op descriptor lives in shared memory (reading it in place measured 4 us/step slower)
+  const GemmOp o = og;                       // registers / local copy: the op descriptor lives in shared memory (reading it in place measured 4 us/step slower;
+                                             // a NON-const copy, patched in place for K splits, cost 25 us/step: every field then lives in local memory)
+  const int kbase = o.kbase;                 // first K index of this job's K range in the TMA maps (split-K jobs, see gemm_tile_tc_split)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tm = tile / o.tiles_n, tn = tile - tm * o.tiles_n;
   const int m0 = tm * 32, n0 = tn * 32;
@@ -742,7 +744,7 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
   ILSW_TSTAMP(0);
   {
     const int klen0 = min(kKC, o.K);
-    if (o.tma) tc_tma_stage(o, sbase, 4u * (unsigned)kOperandFloats, m0, n0, 0, klen0, &tma.bar[0]);
+    if (o.tma) tc_tma_stage(o, sbase, 4u * (unsigned)kOperandFloats, m0, n0, kbase, klen0, &tma.bar[0]);
     if (o.tma != 3) tc_fill_stage<KC>(og, smem, m0, n0, 0, klen0, vecA, vecB, o.tma);
     cp_async_commit();
     if (fz)           // the B panel is in flight; produce the A panel meanwhile
@@ -829,7 +831,7 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
   for (int st = 0; st < nstages; ++st) {
     if (st + 1 < nstages) {
       const int k0 = (st + 1) * kKC;
-      if (o.tma) tc_tma_stage(o, sbase + 4u * (unsigned)(((st + 1) & 1) * kTcStageFloats), 4u * (unsigned)kOperandFloats, m0, n0, k0,
+      if (o.tma) tc_tma_stage(o, sbase + 4u * (unsigned)(((st + 1) & 1) * kTcStageFloats), 4u * (unsigned)kOperandFloats, m0, n0, kbase + k0,
                               min(kKC, o.K - k0), &tma.bar[(st + 1) & 1]);
       if (o.tma != 3) tc_fill_stage<KC>(og, smem + ((st + 1) & 1) * kTcStageFloats, m0, n0, k0, min(kKC, o.K - k0), vecA, vecB, o.tma);
       cp_async_commit();
@@ -971,6 +973,28 @@ __device__ __noinline__ void gemm_tile_tc(const GemmOp& og, int tile, float* sme
   tc5::fence_proxy_async();   // this tile's generic accesses to the staging area precede the next tile's TMA writes
   __syncthreads();     // the partial tiles are read before the next job's panels overwrite them
   ILSW_TSTAMP(4);
+}
+
+// Weight-gradient GEMM split along K (= batch) over partial gradient arenas (GemmOp::ksplit on a plain tile; operands k-major:
+// a_mc && b_nc): job (ks, tile) sums the 32-deep K blocks [b0, b1) into arena ks.  Tiny outputs (the discriminator's W1: 128 x 23)
+// would otherwise walk K = 512 on 4 CTAs while 144 SMs wait (GAIL phase 5: 15 us).  A shifted copy of the descriptor in shared
+// memory, then the same tile.
+template <int KC, int CT>
+__device__ __noinline__ void gemm_tile_tc_split(const GemmOp& og, int tile_in, float* smem, int mode, int prof_phase, TmaState& tma) {
+  __shared__ GemmOp s_tsplit;
+  const int per = og.tiles_m * og.tiles_n, ks = tile_in / per, tile = tile_in - ks * per;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    GemmOp o = og;
+    const int nkb = (o.K + 31) >> 5;
+    const int kb = 32 * ((ks * nkb) / o.ksplit), ke = min(o.K, 32 * (((ks + 1) * nkb) / o.ksplit));
+    o.A += (size_t)kb * o.lda; o.B += (size_t)kb * o.ldb; o.K = ke - kb; o.kbase = kb;
+    o.C += (size_t)ks * o.split_stride;
+    if (o.bias_out) o.bias_out += (size_t)ks * o.split_stride;
+    s_tsplit = o;
+  }
+  __syncthreads();
+  gemm_tile_tc<KC, CT>(s_tsplit, tile, smem, mode, prof_phase, nullptr, nullptr, nullptr, nullptr, tma);
 }
 
 // Skinny weight-gradient tile: M <= 8 output rows (critic output layer M = 1, policy heads M = A), a_mc && b_nc.
@@ -1383,17 +1407,20 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
           const AdamOp* ad = o.gemm.adam ? &s_ops[o.gemm.adam - 1].adam : nullptr;
           const AdamCoef* cf = ad ? &s_coefs[ad->slot] : nullptr;
           const L0FuseOp* fz = o.gemm.a0 ? &s_ops[o.gemm.a0 - 1].l0 : nullptr;
-          if (TC5 && o.gemm.tc5) {
+          const int gk = o.gemm.kind;
+          if (gk == GK_TILE && prec != 0) {       // the common case first
+            gemm_tile_tc<KC, CTAS>(o.gemm, j, tile_smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, ad, cf, push, fz, tma_state);
+          } else if (TC5 && gk == GK_TC5) {
             if constexpr (TC5) {
               if (!tc5::gemm_tile<kTc5BN>(o.gemm, j, tc5_smem, s_tc5, tc5_state)) {
                 if (threadIdx.x == 0) atomicExch(abort_flag, 1);     // the other CTAs leave their barrier wait
                 alive = false;
               }
             }
-          } else if (TC5 && gemm_is_skinny(o.gemm) && o.gemm.ksplit > 1) gemm_tile_skinny_split(o.gemm, j, smem);
-          else if (gemm_is_skinny(o.gemm)) gemm_tile_skinny(o.gemm, j, smem, ad, cf, push);
+          } else if (TC5 && gk == GK_SKINNY_SPLIT) gemm_tile_skinny_split(o.gemm, j, smem);
+          else if (gk == GK_SKINNY || gk == GK_SKINNY_SPLIT) gemm_tile_skinny(o.gemm, j, smem, ad, cf, push);
           else if (prec == 0) gemm_tile_device(o.gemm, j, smem, ad, cf, push, fz);
-          else gemm_tile_tc<KC, CTAS>(o.gemm, j, tile_smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, ad, cf, push, fz, tma_state);
+          else gemm_tile_tc_split<KC, CTAS>(o.gemm, j, tile_smem, prec, (a.profile && blockIdx.x == 0) ? ph : -1, tma_state);
         } else if (o.kind == OP_ROW) {
           RowEnv env; env.lane = lane; env.nl = 32; env.warp = warp; env.sm = smem;
           env.prof = (a.profile && blockIdx.x == 0) ? ph : -1;

@@ -13,6 +13,7 @@
 namespace ilsw {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+constexpr int kDiscGradSplits = kMaxGradSplits;     // partial gradient arenas of the discriminator (all GEMM modes but the exact one)
 constexpr int kMaxKSplits = kMaxGradSplits;   // partial gradient arenas of a tcgen05 program (adam_grad sums exactly this many)
 
 // two-pass bump allocator: pass 1 (base==nullptr) measures, pass 2 hands out pointers
@@ -87,8 +88,12 @@ struct Builder {
     if (g.tc5) { g.tiles_m = (g.M + 127) / 128; g.tiles_n = (g.N + kTc5BN - 1) / kTc5BN; }
     else { g.tiles_m = (g.M + 31) / 32; g.tiles_n = (g.N + 31) / 32; }   // the aug (bias-gradient) column is produced by the tn==0 tiles
     const bool skinny = g.M <= 8 && g.a_mc && g.b_nc && g.tiles_m == 1;        // gemm_is_skinny (ilsw_engine.cuh)
-    if (!(g.tc5 || skinny) || g.ksplit < 1) g.ksplit = 1;
+    // K splits: tcgen05 tiles, skinny tiles of tcgen05 programs, and plain weight-gradient tiles (k-major operands, optimiser not fused)
+    const bool split_ok = g.tc5 || skinny || (g.a_mc && g.b_nc && !g.adam && P.ctx.hp.gemm_precision != 0);
+    if (!split_ok || g.ksplit < 1) g.ksplit = 1;
+    if (skinny && !P.ctx.hp.use_tc5) g.ksplit = 1;          // gemm_tile_skinny_split exists in the tcgen05 engine variant only
     g.ksplit = g.ksplit < (g.K + 63) / 64 ? g.ksplit : (g.K + 63) / 64;
+    g.kind = g.tc5 ? GK_TC5 : skinny ? (g.ksplit > 1 ? GK_SKINNY_SPLIT : GK_SKINNY) : (g.ksplit > 1 ? GK_TILE_SPLIT : GK_TILE);
     Op* o = add(OP_GEMM, g.ksplit * g.tiles_m * g.tiles_n);
     if (o) o->gemm = g;
   }
@@ -179,7 +184,7 @@ struct Builder {
     g.A = D; g.lda = ldd; g.a_mc = 1; g.B = X; g.ldb = ldx; g.b_nc = 1; g.M = Mout; g.N = Nin; g.K = Kb;
     g.C = G; g.ldc = Nin; g.aug_ones = gbias ? 1 : 0; g.bias_out = gbias; g.accumulate = accumulate;
     g.adam = adam_op >= 0 ? adam_op + 1 : 0;
-    if (net && net->g_splits > 1 && adam_op < 0 && !accumulate) {
+    if (net && net->g_splits > 1 && adam_op < 0 && (!accumulate || !P.ctx.hp.use_tc5)) {     // mma.sync tiles accumulate per arena
       g.ksplit = dw_splits < net->g_splits ? dw_splits : net->g_splits;
       g.split_stride = net->g_stride;
     }
@@ -330,13 +335,16 @@ inline void build_disc_step(Builder& b, const Ctx& c) {
   b.dw(D.dlogit, 1, 1, D.h2, Hd, Hd, 2 * B, G3, gb3);                            // CE: dw3,db3
   if (gp) b.dx(D.dl2, Hd, B, Hd, W2, Hd, Hd, h1i, Hd, ACT_TANH, D.dl1, Hd, D.u1);  // u1, delta1_gp
   b.phase();
-  b.dw(D.d1, Hd, Hd, D.X3, ld, Din, 2 * B, G1, gb1);                             // CE: dW1,db1
+  // W1's gradient is a 128 x Din output over K = 2B / B rows: 4 tiles.  Split along K over the partial arenas (the flat Adam
+  // job sums them); the first, non-accumulating GEMM uses every arena, so the accumulating ones below find fresh partials.
+  b.dw_splits = kDiscGradSplits;
+  b.dw(D.d1, Hd, Hd, D.X3, ld, Din, 2 * B, G1, gb1, 0, -1, &N);                  // CE: dW1,db1
   if (gp) b.dx(D.dl1, Hd, B, Hd, W1, Din, Din, nullptr, 0, ACT_NONE, D.g, ld);   // g = delta1 W1
   if (gp) {
     b.phase(); b.row(ROW_DISC_GNORM, B);
     b.phase();
     b.fwd(D.gbar, ld, B, Din, W1, nullptr, Hd, D.db1, Hd, ACT_NONE);             // dbar1 = gbar W1^T
-    b.dw(D.dl1, Hd, Hd, D.gbar, ld, Din, B, G1, nullptr, 1);                     // dW1 += delta1^T gbar
+    b.dw(D.dl1, Hd, Hd, D.gbar, ld, Din, B, G1, nullptr, 1, -1, &N);             // dW1 += delta1^T gbar
     b.phase(); b.row(ROW_DISC_EW1, B);
     b.phase();
     b.fwd(D.ub1, Hd, B, Hd, W2, nullptr, Hd, D.db2, Hd, ACT_NONE);               // dbar2 = ubar1 W2^T
@@ -347,7 +355,7 @@ inline void build_disc_step(Builder& b, const Ctx& c) {
     b.dw(D.cmask, 1, 1, D.t3, Hd, Hd, B, G3, nullptr, 1);                        // dw3 += c^T (dbar2*s2)
     b.dx(D.zb2, Hd, B, Hd, W2, Hd, Hd, nullptr, 0, ACT_NONE, D.hb1, Hd);         // hbar1_raw = zbar2 W2
     b.phase(); b.row(ROW_DISC_EW3, B);
-    b.phase(); b.dw(D.zb1, Hd, Hd, xhat, ld, Din, B, G1, gb1, 1);                // dW1 += zbar1^T xhat ; db1
+    b.phase(); b.dw(D.zb1, Hd, Hd, xhat, ld, Din, B, G1, gb1, 1, -1, &N);        // dW1 += zbar1^T xhat ; db1
   }
   b.phase();
   b.adam(N, nullptr, c.hp.disc_lr, c.hp.disc_beta1, 0.999, c.hp.adam_eps, 0.f, SLOT_DISC);
@@ -830,7 +838,11 @@ inline int assemble(Program& P, const TrainerSpec& sp, Bump& mem, bool use_tc5 =
   if (cfg.algo == ILSW_ALGO_TD3) c.tpolicy = make_mlp(sp.nets[5], nullptr);
   if (sp.has_disc) {
     alloc_disc_bufs(mem, c.d, B, sp.dcfg.state_only ? 2 * O : O + A, sp.disc.hidden);
-    c.disc = mk(sp.disc);
+    {   // the discriminator's gradient lives in kDiscGradSplits partial arenas (split-K first-layer weight gradient, build_disc_step)
+      const int ns = cfg.gemm_precision != 0 ? kDiscGradSplits : 1;
+      c.disc = make_mlp(sp.disc, mem.f((size_t)ns * round_up(mlp_num_params(sp.disc.in_dim, sp.disc.hidden, sp.disc.out_dim, sp.disc.log_std_head), 4)));
+      c.disc.g_splits = ns; c.disc.g_stride = round_up(c.disc.n_params, 4);
+    }
   }
   if (use_tc5) {
     MlpPtrs* nets[] = {&c.policy, &c.qf[0], &c.qf[1], &c.tqf[0], &c.tqf[1], &c.tpolicy, &c.vf, &c.tvf};

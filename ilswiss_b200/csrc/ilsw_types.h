@@ -80,6 +80,8 @@ struct GemmOp {
   int split_stride;     //   its partial sums to C + s * split_stride / bias_out + s * split_stride (floats); 0 / 1: no split
   const void* tmapA;    // device CUtensorMap of the A / B operand (SWIZZLE_128B boxes, see ilsw_tc5.cuh)
   const void* tmapB;
+  int kbase;            // first K index of the job's K range in the tensor maps (0 except in the shifted copies of split-K jobs)
+  int kind;             // tile routine, resolved by the program builder (GemmKind): the engine's dispatch is one load + compare
   int tma;              // mma.sync tile (ilsw_engine.cuh): bit 0 / bit 1 = the A / B panels of a stage are brought in by TMA boxes
                         // {32 floats, 32 rows} of tmapA / tmapB instead of per-thread cp.async (16-byte aligned operands only)
 };
@@ -97,6 +99,8 @@ ILSW_HD void shadow_store(const ShadowRef& sh, int i, float v) {
     sh.ptr[(size_t)r * sh.ld + c] = v;
   }
 }
+
+enum GemmKind : int { GK_TILE = 0, GK_TC5 = 1, GK_SKINNY = 2, GK_SKINNY_SPLIT = 3, GK_TILE_SPLIT = 4 };
 
 struct AdamOp {
   float* p; const float* g; float* m; float* v;
