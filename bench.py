@@ -483,7 +483,7 @@ def measure(name, args, K, W, rank, world, dist, flush, clock, peak, peak_src, e
         row_bytes = (2 * O + A + 2) * 4
         gby = rows_n * row_bytes * 2 + rows_n * 4
         ring_bytes = w["N"] * buf.ring.stride * 4
-        in_l2 = ring_bytes < (256 << 20)          # a ring that fits the 126 MB L2 (GAIL: 20 000 rows) is not an HBM measurement
+        in_l2 = ring_bytes < (64 << 20)           # a ring far below the 126 MB L2 (GAIL: 20 000 rows = 3.8 MB, every row sampled ~50 times) is not an HBM measurement
         gby_stride = rows_n * buf.ring.stride * 4 * 2 + rows_n * 4
         rec["replay_roofline"] = {"kernel": "%s (Philox sample + gather)" % ("rb_gather_bulk_kernel: one TMA bulk copy per row" if buf.ring.stride * 4 <= 512 else "rb_gather_kernel: 128-bit loads"),
                                   "rows": rows_n, "row_bytes": row_bytes,
@@ -493,7 +493,8 @@ def measure(name, args, K, W, rank, world, dist, flush, clock, peak, peak_src, e
                                   "frac_of_padded_rows": None if in_l2 else gby_stride / gms / 1e6 / peak,
                                   "note": ("ring of %.0f MB is L2 resident: not an HBM-roofline measurement" % (ring_bytes / 1e6)) if in_l2 else
                                           "frac counts the payload bytes of a row (2O+A+2 floats, read + written); rows are padded to 64-byte multiples in the ring "
-                                          "(frac_of_padded_rows counts the stride)",
+                                          "(frac_of_padded_rows counts the stride); sampling is with replacement, so repeated rows of a "
+                                          "batch are L2 hits (%d samples from %d ring rows)" % (rows_n, w["N"]),
                                   "l2": "flushed before every timed launch"}
     if world == 1 and not args.no_cpu_baseline:
         n_cpu = {"td3": 120, "gail": 250}.get(w["algo"], 400) if not extras else (600 if w["algo"] != "td3" else 250)

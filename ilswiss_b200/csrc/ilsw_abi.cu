@@ -898,6 +898,7 @@ extern "C" int ilsw_replica_connect_symm(ilsw_trainer* tr, int rank, int world, 
   rp.cnt_local = rp.cnt_peer[rank];
   rp.flags_local = rp.flags_peer[rank];
   rp.recv_local = rp.recv_peer[rank];
+  rp.arrive_local = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(rp.flags_local) + 192);     // [192,196) of the flag area
   if (multicast_ptr) {
     char* mc = reinterpret_cast<char*>((uintptr_t)multicast_ptr);
     rp.cnt_mc = reinterpret_cast<unsigned long long*>(mc + 128);
@@ -935,6 +936,7 @@ extern "C" int ilsw_replica_connect(ilsw_trainer* tr, int rank, int world, const
   rp.cnt_local = rp.cnt_peer[rank];
   rp.flags_local = rp.flags_peer[rank];
   rp.recv_local = rp.recv_peer[rank];
+  rp.arrive_local = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(rp.flags_local) + 192);
   tr->seq = 0;
   return ILSW_OK;
 }

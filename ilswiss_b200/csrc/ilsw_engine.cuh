@@ -56,8 +56,9 @@ struct Replica {
   unsigned* flags_local;      // [8] sequence numbers written by the peers
   unsigned* flags_peer[8];
   unsigned seq0;              // exchanges completed before this launch
-  unsigned long long* cnt_local;      // arrival counter of the epilogue-push exchange: every CTA of every replica adds 1 per
-  unsigned long long* cnt_peer[8];    // policy update (after a system fence behind its pushes); never reset
+  unsigned long long* cnt_local;      // arrival counter of the epilogue-push exchange: every REPLICA adds 1 per policy update, when the
+  unsigned long long* cnt_peer[8];    // last of its CTAs has arrived on `arrive_local` (a system fence behind its pushes); never reset
+  unsigned* arrive_local;             // this replica's own CTA arrival counter (local memory, monotonic)
   // NVLS multicast mapping of the same exchange buffer (ilsw_replica_connect_symm): a store / reduction on these addresses is
   // replicated to every replica by the NVSwitch -- the epilogue push costs ONE store per element instead of `world`
   float* recv_mc;                     // nullptr: no multicast mapping, per-peer stores
@@ -1127,11 +1128,11 @@ __device__ __forceinline__ bool replica_exchange(const Replica& rp, unsigned seq
   return s_ok2 != 0;
 }
 
-// epilogue-push exchange, consumer side: wait until every CTA of every replica has signalled update `seq` (1-based)
+// epilogue-push exchange, consumer side: wait until every replica has signalled update `seq` (1-based)
 __device__ __forceinline__ bool replica_wait_pushes(const Replica& rp, unsigned seq, int* abort_flag) {
   __shared__ int s_ok3;
   if (threadIdx.x == 0) {
-    const unsigned long long want = (unsigned long long)seq * (unsigned long long)rp.world * (unsigned long long)gridDim.x;
+    const unsigned long long want = (unsigned long long)seq * (unsigned long long)rp.world;
     int ok = 1;
     const long long t0 = clock64();
     while (ld_acquire_sys_u64(rp.cnt_local) < want) {
@@ -1143,13 +1144,23 @@ __device__ __forceinline__ bool replica_wait_pushes(const Replica& rp, unsigned 
   __syncthreads();
   return s_ok3 != 0;
 }
-// producer side: this CTA's pushes of the phase are complete and visible system-wide before the peers see the count
-__device__ __forceinline__ void replica_signal_pushes(const Replica& rp) {
+// producer side, two levels: every CTA fences its pushes system-wide and arrives on the replica's LOCAL counter; the CTA that
+// completes the replica's arrivals for update `seq` signals the peers ONCE (one multimem.red through the NVSwitch, or `world`
+// peer reductions).  The flat form -- every CTA of every replica adding to every replica's counter -- put world x 148
+// serialised system-scope atomics on one address per step: 296 at N = 2, 1 184 at N = 8, the part of the exchange cost that
+// grew with N (per-replica step 159.7 -> 175.4 us from N = 2 to N = 8 with per-GPU step times equal to 0.6 %).
+__device__ __forceinline__ void replica_signal_pushes(const Replica& rp, unsigned seq) {
   __threadfence_system();
   __syncthreads();
-  if (rp.cnt_mc) {
-    if (threadIdx.x == 0) asm volatile("multimem.red.release.sys.global.add.u64 [%0], %1;" ::"l"(rp.cnt_mc), "l"(1ull) : "memory");
-  } else if (threadIdx.x < rp.world) red_add_release_sys_u64(rp.cnt_peer[threadIdx.x], 1ull);
+  if (threadIdx.x == 0) {
+    const unsigned old = atom_add_acq_rel_gpu(rp.arrive_local, 1u);
+    if (old + 1u == seq * gridDim.x) {          // modular arithmetic: consistent across a wrap of the 32-bit counter
+      __threadfence_system();
+      if (rp.cnt_mc) asm volatile("multimem.red.release.sys.global.add.u64 [%0], %1;" ::"l"(rp.cnt_mc), "l"(1ull) : "memory");
+      else
+        for (int r = 0; r < rp.world; ++r) red_add_release_sys_u64(rp.cnt_peer[r], 1ull);
+    }
+  }
 }
 
 __device__ __forceinline__ float replica_reduced_grad(const Replica& rp, unsigned seq, int i) {
@@ -1439,7 +1450,7 @@ ilsw_engine_kernel(const Program* __restrict__ prog, RunArgs a_param, BarrierSta
         }
       }
       if constexpr (TC5) { if (!alive) break; }
-      if (pushing) replica_signal_pushes(rp);
+      if (pushing) replica_signal_pushes(rp, xseq);
       if (stamp) c.phase_ns[kMaxPhases + 1 + ph] = globaltimer_ns();
       if (a.profile && s == a.n_steps - 1 && threadIdx.x == 0 && blockIdx.x < kMaxGrid) c.cta_ns[ph * kMaxGrid + blockIdx.x] = globaltimer_ns();
       // descriptor prefetch for this CTA's first tile of the next phase (a wrong guess -- inactive phase -- is harmless)
