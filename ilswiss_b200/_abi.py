@@ -10,6 +10,7 @@ IPC_HANDLE_BYTES = 64
 
 ALGO_SAC_ALPHA, ALGO_TD3, ALGO_SAC_V = 1, 2, 3
 DISC_MODES = {"airl": 0, "gail": 1, "gail2": 2, "fairl": 3}
+DISC_ACTS = {"tanh": 0, "relu": 1}     # ilsw_disc_act
 
 (L_QF1, L_QF2, L_POLICY, L_ALPHA_LOSS, L_ALPHA, L_VF, L_DISC_CE, L_DISC_ACC, L_GRAD_PEN,
  L_REW_MEAN, L_REW_STD, L_REW_MAX, L_REW_MIN, L_Q1_MEAN, L_LOGPI_MEAN, L_QT_MEAN) = range(16)
@@ -43,7 +44,7 @@ class DiscConfig(C.Structure):
                 ("use_grad_pen", C.c_int), ("grad_pen_weight", C.c_double), ("clamp_magnitude", C.c_double),
                 ("rew_clip_min_on", C.c_int), ("rew_clip_max_on", C.c_int),
                 ("rew_clip_min", C.c_double), ("rew_clip_max", C.c_double),
-                ("state_only", C.c_int), ("policy_batch_from_expert", C.c_int)]
+                ("state_only", C.c_int), ("policy_batch_from_expert", C.c_int), ("hid_act", C.c_int)]
 
 
 class HerSamplingDesc(C.Structure):

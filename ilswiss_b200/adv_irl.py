@@ -22,6 +22,25 @@ from . import _abi
 from .trainers import SoftActorCritic, adopt_module, module_dims
 
 
+def disc_hidden_activation(discriminator):
+    """'tanh' or 'relu' for an MLPDisc(num_layer_blocks=2, use_bn=False) (simple_disc_models.py:8-48: `model` =
+    Sequential(Linear, act, Linear, act, Linear)); NotImplementedError for every other discriminator -- BatchNorm blocks
+    (:31-32,37-38), other depths, ResNetAIRLDisc (:51-93, whose num_layer_blocks=2 / use_bn=False instance has the SAME six
+    parameter tensors as the MLP but a linear first layer and a skip connection, so the parameter list alone cannot tell)."""
+    import torch.nn as nn
+
+    model = getattr(discriminator, "model", None)
+    if not isinstance(model, nn.Sequential):
+        raise NotImplementedError("%s is not an MLPDisc (no `model` Sequential)" % type(discriminator).__name__)
+    mods = list(model)
+    kinds = [type(m) for m in mods]
+    for act, name in ((nn.Tanh, "tanh"), (nn.ReLU, "relu")):
+        if kinds == [nn.Linear, act, nn.Linear, act, nn.Linear]:
+            return name
+    raise NotImplementedError("expects MLPDisc(num_layer_blocks=2, hid_act='tanh'|'relu', use_bn=False), got [%s]"
+                              % ", ".join(k.__name__ for k in kinds))
+
+
 class AdvIRLEngine:
     def __init__(self, mode, discriminator, policy_trainer, expert_replay_buffer, replay_buffer,
                  state_only=False, disc_optim_batch_size=1024, policy_optim_batch_size=1024,
@@ -45,9 +64,10 @@ class AdvIRLEngine:
             unsupported.append("non-Adam disc optimizer")
         if unsupported:
             raise NotImplementedError("fused AdvIRL engine (SURVEY.md 8f rank 4): " + ", ".join(unsupported))
+        hid_act = disc_hidden_activation(discriminator)
         in_dim, H, out_dim, ls = module_dims(discriminator)
         if out_dim != 1 or ls or getattr(discriminator, "clamp_magnitude", None) is None:
-            raise NotImplementedError("expects MLPDisc(num_layer_blocks=2, hid_act='tanh', use_bn=False)")
+            raise NotImplementedError("expects MLPDisc(num_layer_blocks=2, hid_act='tanh'|'relu', use_bn=False)")
         cfg = policy_trainer._cfg
         want_in = 2 * cfg.obs_dim if state_only else cfg.obs_dim + cfg.act_dim      # adv_irl_exp_script.py:150-156
         if in_dim != want_in:
@@ -68,6 +88,7 @@ class AdvIRLEngine:
         dc.rew_clip_min_on, dc.rew_clip_max_on = int(rew_clip_min is not None), int(rew_clip_max is not None)
         dc.rew_clip_min, dc.rew_clip_max = float(rew_clip_min or 0.0), float(rew_clip_max or 0.0)
         dc.state_only, dc.policy_batch_from_expert = int(bool(state_only)), int(policy_optim_batch_size_from_expert)
+        dc.hid_act = _abi.DISC_ACTS[hid_act]
         self.state_only, self.policy_optim_batch_size_from_expert = bool(state_only), int(policy_optim_batch_size_from_expert)
         self._dc = dc
         eng = policy_trainer.engine
@@ -276,8 +297,8 @@ class DeviceAdvIRLMixin(_DeviceSamplerMixin):
             try:
                 eng = self._ilsw_build_engine()
             except NotImplementedError as e:
-                # discriminators outside the fused program (simple_disc_models.py:29-38,51-93: BatchNorm / ReLU MLPDisc,
-                # ResNetAIRLDisc -- no shipped yaml uses them): the reference's own _do_reward_training /
+                # discriminators outside the fused program (simple_disc_models.py:29-38,51-93: BatchNorm MLPDisc, other
+                # depths, ResNetAIRLDisc -- no shipped yaml uses them): the reference's own _do_reward_training /
                 # _do_policy_training run (adv_irl.py:133-314), with the discriminator and its optimiser as eager torch
                 # modules ON THE DEVICE, batches gathered in HBM (get_batch below) and every policy update still ONE fused
                 # SAC step (policy_trainer.train_step on the relabelled device batch)

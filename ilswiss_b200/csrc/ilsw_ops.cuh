@@ -755,6 +755,9 @@ ILSW_HDN void row_td3_final_policy(const Ctx& c, const RunArgs& a, int s, int r,
 }
 
 // ---- AdvIRL discriminator --------------------------------------------------------------
+// hidden activation of the discriminator blocks, from its OUTPUT h: act'(z) and act''(z)/act'(z) (tanh: 1-h^2, -2h; relu: [h>0], 0)
+ILSW_HD float disc_dact(int act, float h) { return act == ACT_RELU ? (h > 0.f ? 1.f : 0.f) : 1.0f - h * h; }
+ILSW_HD float disc_curv(int act, float h) { return act == ACT_RELU ? 0.f : -2.0f * h; }
 ILSW_HDN void row_disc_gather(const Ctx& c, const RunArgs& a, int s, int b, int lane, int nl) {
   const DiscBufs& Dd = c.d;
   const int B = Dd.B, D = Dd.D;
@@ -809,7 +812,7 @@ ILSW_HDN void row_disc_head(const Ctx& c, const RunArgs& a, int s, int r, int la
     float* d2 = Dd.d2 + (size_t)r * Hd;
     for (int k = lane; k < Hd; k += nl) {
       float h = ldg(h2 + k);
-      d2[k] = dl * ldg(w3 + k) * (1.0f - h * h);
+      d2[k] = dl * ldg(w3 + k) * disc_dact(c.hp.disc_act, h);
     }
   } else {
     int b = r - 2 * B;
@@ -817,7 +820,7 @@ ILSW_HDN void row_disc_head(const Ctx& c, const RunArgs& a, int s, int r, int la
     float* dl2 = Dd.dl2 + (size_t)b * Hd;
     for (int k = lane; k < Hd; k += nl) {
       float h = ldg(h2 + k);
-      dl2[k] = pass * ldg(w3 + k) * (1.0f - h * h);
+      dl2[k] = pass * ldg(w3 + k) * disc_dact(c.hp.disc_act, h);
     }
   }
 }
@@ -844,7 +847,7 @@ ILSW_HDN void row_disc_ew1(const Ctx& c, const RunArgs& a, int s, int b, int lan
     size_t i = (size_t)b * Hd + k;
     float h1 = ldg(Dd.h1 + (size_t)(2 * B + b) * Hd + k);
     float db = ldg(Dd.db1 + i);
-    Dd.ub1[i] = db * (1.0f - h1 * h1);
+    Dd.ub1[i] = db * disc_dact(c.hp.disc_act, h1);
     Dd.sb1[i] = db * ldg(Dd.u1 + i);
   }
 }
@@ -857,11 +860,11 @@ ILSW_HDN void row_disc_ew2(const Ctx& c, const RunArgs& a, int s, int b, int lan
   for (int k = lane; k < Hd; k += nl) {
     size_t i = (size_t)b * Hd + k;
     float h2 = ldg(Dd.h2 + (size_t)(2 * B + b) * Hd + k);
-    float s2 = 1.0f - h2 * h2;
+    float s2 = disc_dact(c.hp.disc_act, h2);
     float db = ldg(Dd.db2 + i);
     Dd.t3[i] = db * s2;                       // multiplied by c through the A operand (cmask)
     float sb2 = db * (cmk * ldg(w3 + k));
-    Dd.zb2[i] = (-2.0f * h2 * sb2) * s2;
+    Dd.zb2[i] = (disc_curv(c.hp.disc_act, h2) * sb2) * s2;
   }
 }
 // zbar1 = (hbar1_raw - 2 h1 sbar1) * s1
@@ -871,7 +874,7 @@ ILSW_HDN void row_disc_ew3(const Ctx& c, const RunArgs& a, int s, int b, int lan
   for (int k = lane; k < Hd; k += nl) {
     size_t i = (size_t)b * Hd + k;
     float h1 = ldg(Dd.h1 + (size_t)(2 * B + b) * Hd + k);
-    Dd.zb1[i] = (ldg(Dd.hb1 + i) - 2.0f * h1 * ldg(Dd.sb1 + i)) * (1.0f - h1 * h1);
+    Dd.zb1[i] = (ldg(Dd.hb1 + i) + disc_curv(c.hp.disc_act, h1) * ldg(Dd.sb1 + i)) * disc_dact(c.hp.disc_act, h1);
   }
 }
 ILSW_HDN void row_disc_final(const Ctx& c, const RunArgs& a, int s, int r, int lane, int nl) {

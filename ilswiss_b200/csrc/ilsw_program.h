@@ -317,6 +317,10 @@ inline void build_disc_step(Builder& b, const Ctx& c) {
   const MlpPtrs& N = c.disc;
   const int B = D.B, Hd = D.Hd, Din = D.D, ld = D.ld_d;
   const bool gp = c.hp.use_gp != 0;
+  const int act = c.hp.disc_act;
+  // ReLU blocks have no second derivative: every term of the penalty's double backward that carries act'' vanishes
+  // (zbar2 = 0, hence hbar1 = 0 and zbar1 = 0), so the three GEMMs and the row phase that only move those zeros are left out
+  const bool curved = act == ACT_TANH;
   const int R = gp ? 3 * B : 2 * B;
   const float* W1 = N.p + N.oW0; const float* b1 = N.p + N.ob0;
   const float* W2 = N.p + N.oW1; const float* b2 = N.p + N.ob1;
@@ -327,13 +331,13 @@ inline void build_disc_step(Builder& b, const Ctx& c) {
   const float* h1i = D.h1 + (size_t)2 * B * Hd;
 
   b.phase(); b.row(ROW_DISC_GATHER, B);
-  { Builder::TwoLayers L[1] = {{D.X3, ld, R, Din, &N, D.h1, D.h2, ACT_TANH}}; b.two_layers(L, 1); }
+  { Builder::TwoLayers L[1] = {{D.X3, ld, R, Din, &N, D.h1, D.h2, act}}; b.two_layers(L, 1); }
   b.phase(); b.row(ROW_DISC_HEAD, R);
   b.phase();
-  b.dx(D.d2, Hd, 2 * B, Hd, W2, Hd, Hd, D.h1, Hd, ACT_TANH, D.d1, Hd);          // CE: delta1
+  b.dx(D.d2, Hd, 2 * B, Hd, W2, Hd, Hd, D.h1, Hd, act, D.d1, Hd);               // CE: delta1
   b.dw(D.d2, Hd, Hd, D.h1, Hd, Hd, 2 * B, G2, gb2);                             // CE: dW2,db2
   b.dw(D.dlogit, 1, 1, D.h2, Hd, Hd, 2 * B, G3, gb3);                            // CE: dw3,db3
-  if (gp) b.dx(D.dl2, Hd, B, Hd, W2, Hd, Hd, h1i, Hd, ACT_TANH, D.dl1, Hd, D.u1);  // u1, delta1_gp
+  if (gp) b.dx(D.dl2, Hd, B, Hd, W2, Hd, Hd, h1i, Hd, act, D.dl1, Hd, D.u1);       // u1, delta1_gp
   b.phase();
   // W1's gradient is a 128 x Din output over K = 2B / B rows: 4 tiles.  Split along K over the partial arenas (the flat Adam
   // job sums them); the first, non-accumulating GEMM uses every arena, so the accumulating ones below find fresh partials.
@@ -351,11 +355,13 @@ inline void build_disc_step(Builder& b, const Ctx& c) {
     b.dw(D.dl2, Hd, Hd, D.ub1, Hd, Hd, B, G2, nullptr, 1);                       // dW2 += delta2^T ubar1
     b.phase(); b.row(ROW_DISC_EW2, B);
     b.phase();
-    b.dw(D.zb2, Hd, Hd, h1i, Hd, Hd, B, G2, gb2, 1);                             // dW2 += zbar2^T h1 ; db2
+    if (curved) b.dw(D.zb2, Hd, Hd, h1i, Hd, Hd, B, G2, gb2, 1);                 // dW2 += zbar2^T h1 ; db2
     b.dw(D.cmask, 1, 1, D.t3, Hd, Hd, B, G3, nullptr, 1);                        // dw3 += c^T (dbar2*s2)
-    b.dx(D.zb2, Hd, B, Hd, W2, Hd, Hd, nullptr, 0, ACT_NONE, D.hb1, Hd);         // hbar1_raw = zbar2 W2
-    b.phase(); b.row(ROW_DISC_EW3, B);
-    b.phase(); b.dw(D.zb1, Hd, Hd, xhat, ld, Din, B, G1, gb1, 1, -1, &N);        // dW1 += zbar1^T xhat ; db1
+    if (curved) {
+      b.dx(D.zb2, Hd, B, Hd, W2, Hd, Hd, nullptr, 0, ACT_NONE, D.hb1, Hd);       // hbar1_raw = zbar2 W2
+      b.phase(); b.row(ROW_DISC_EW3, B);
+      b.phase(); b.dw(D.zb1, Hd, Hd, xhat, ld, Din, B, G1, gb1, 1, -1, &N);      // dW1 += zbar1^T xhat ; db1
+    }
   }
   b.phase();
   b.adam(N, nullptr, c.hp.disc_lr, c.hp.disc_beta1, 0.999, c.hp.adam_eps, 0.f, SLOT_DISC);
@@ -393,16 +399,16 @@ inline void build_sac_alpha(Builder& b, const Ctx& c) {
                    c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1q[i], Hd, ACT_RELU);
     b.fwd2_fused(S.Xpi, S.ld_o, 2 * B, O, P.p + P.oW0, P.p + P.ob0, ACT_RELU, Hd, S.h0p, P.p + P.oW1, P.p + P.ob1, Hd, S.h1p, Hd, ACT_RELU);
     if (disc)
-      b.fwd2_fused(dX, dld, B, dK, c.disc.p + c.disc.oW0, c.disc.p + c.disc.ob0, ACT_TANH, c.d.Hd, c.d.rh1,
-                   c.disc.p + c.disc.oW1, c.disc.p + c.disc.ob1, c.d.Hd, c.d.rh2, c.d.Hd, ACT_TANH);
+      b.fwd2_fused(dX, dld, B, dK, c.disc.p + c.disc.oW0, c.disc.p + c.disc.ob0, c.hp.disc_act, c.d.Hd, c.d.rh1,
+                   c.disc.p + c.disc.oW1, c.disc.p + c.disc.ob1, c.d.Hd, c.d.rh2, c.d.Hd, c.hp.disc_act);
   } else {
     for (int i = 0; i < 2; ++i) b.fwd(S.Xoa, S.ld_oa, B, K0, c.qf[i].p + c.qf[i].oW0, c.qf[i].p + c.qf[i].ob0, Hd, S.h0q[i], Hd, ACT_RELU);
     b.fwd(S.Xpi, S.ld_o, 2 * B, O, P.p + P.oW0, P.p + P.ob0, Hd, S.h0p, Hd, ACT_RELU);
-    if (disc) b.fwd(dX, dld, B, dK, c.disc.p + c.disc.oW0, c.disc.p + c.disc.ob0, c.d.Hd, c.d.rh1, c.d.Hd, ACT_TANH);
+    if (disc) b.fwd(dX, dld, B, dK, c.disc.p + c.disc.oW0, c.disc.p + c.disc.ob0, c.d.Hd, c.d.rh1, c.d.Hd, c.hp.disc_act);
     b.phase();
     for (int i = 0; i < 2; ++i) b.fwd(S.h0q[i], Hd, B, Hd, c.qf[i].p + c.qf[i].oW1, c.qf[i].p + c.qf[i].ob1, Hd, S.h1q[i], Hd, ACT_RELU);
     b.fwd(S.h0p, Hd, 2 * B, Hd, P.p + P.oW1, P.p + P.ob1, Hd, S.h1p, Hd, ACT_RELU);
-    if (disc) b.fwd(c.d.rh1, c.d.Hd, B, c.d.Hd, c.disc.p + c.disc.oW1, c.disc.p + c.disc.ob1, c.d.Hd, c.d.rh2, c.d.Hd, ACT_TANH);
+    if (disc) b.fwd(c.d.rh1, c.d.Hd, B, c.d.Hd, c.disc.p + c.disc.oW1, c.disc.p + c.disc.ob1, c.d.Hd, c.d.rh2, c.d.Hd, c.hp.disc_act);
   }
   b.phase();
   b.row(ROW_SAC_HEADS, 2 * B);
@@ -745,6 +751,7 @@ inline void apply_disc_hyper(Hyper& h, const ilsw_disc_config& d) {
   h.clip_min_on = d.rew_clip_min_on; h.clip_max_on = d.rew_clip_max_on;
   h.rew_clip_min = (float)d.rew_clip_min; h.rew_clip_max = (float)d.rew_clip_max;
   h.state_only = d.state_only; h.n_from_expert = d.policy_batch_from_expert;
+  h.disc_act = d.hid_act == ILSW_DISC_ACT_RELU ? ACT_RELU : ACT_TANH;
 }
 
 inline int build_program(Program& P);
@@ -789,6 +796,7 @@ inline int validate_spec(const TrainerSpec& sp, std::string* why) {
     if (sp.dcfg.policy_batch_from_expert < 0 || sp.dcfg.policy_batch_from_expert >= c.batch) return fail("policy_batch_from_expert must be in [0, batch)");
     if (!sp.disc.p || !sp.disc.m || !sp.disc.v) return fail("disc arenas");
     if (sp.dcfg.mode < 0 || sp.dcfg.mode > 3) return fail("disc mode");
+    if (sp.dcfg.hid_act != ILSW_DISC_ACT_TANH && sp.dcfg.hid_act != ILSW_DISC_ACT_RELU) return fail("disc hid_act");
   }
   return ILSW_OK;
 }

@@ -642,7 +642,7 @@ ILSW_HDN void job_td3_pibwd(const Ctx& c, int job, const RowEnv& e, bool with_da
 ILSW_HDN void job_disc_head(const Ctx& c, int job, const RowEnv& e, int rows) {
   const DiscBufs& Dd = c.d;
   const MlpPtrs& N = c.disc;
-  const int B = Dd.B, Hd = Dd.Hd, lane = e.lane, nl = e.nl;
+  const int B = Dd.B, Hd = Dd.Hd, lane = e.lane, nl = e.nl, act = c.hp.disc_act;
   const int r = job * kRowsPerJob + e.warp;
   Vec h2;
   float b3 = 0.f;
@@ -667,13 +667,13 @@ ILSW_HDN void job_disc_head(const Ctx& c, int job, const RowEnv& e, int rows) {
         Dd.accterm[r] = ((x > 0.f ? 1.f : 0.f) == t) ? 1.f : 0.f;
       }
 #pragma unroll
-      for (int xx = 0; xx < ILSW_VL; ++xx) w.v[xx] = dl * w.v[xx] * (1.0f - h2.v[xx] * h2.v[xx]);
+      for (int xx = 0; xx < ILSW_VL; ++xx) w.v[xx] = dl * w.v[xx] * disc_dact(act, h2.v[xx]);
       vstore(Dd.d2 + (size_t)r * Hd, w, Hd, lane, nl);
     } else {
       const int b = r - 2 * B;
       if (lane == 0) Dd.cmask[b] = pass;
 #pragma unroll
-      for (int xx = 0; xx < ILSW_VL; ++xx) w.v[xx] = pass * w.v[xx] * (1.0f - h2.v[xx] * h2.v[xx]);
+      for (int xx = 0; xx < ILSW_VL; ++xx) w.v[xx] = pass * w.v[xx] * disc_dact(act, h2.v[xx]);
       vstore(Dd.dl2 + (size_t)b * Hd, w, Hd, lane, nl);
     }
   }
@@ -682,7 +682,7 @@ ILSW_HDN void job_disc_head(const Ctx& c, int job, const RowEnv& e, int rows) {
 
 ILSW_HDN void job_disc_ew(const Ctx& c, int kind, int job, const RowEnv& e) {
   const DiscBufs& Dd = c.d;
-  const int Hd = Dd.Hd, B = Dd.B, lane = e.lane, nl = e.nl;
+  const int Hd = Dd.Hd, B = Dd.B, lane = e.lane, nl = e.nl, act = c.hp.disc_act;
   const int b = job * kRowsPerJob + e.warp;
   if (b >= B) return;
   const size_t ro = (size_t)b * Hd, ri = (size_t)(2 * B + b) * Hd;
@@ -690,7 +690,7 @@ ILSW_HDN void job_disc_ew(const Ctx& c, int kind, int job, const RowEnv& e) {
     Vec h1, db, u1;
     vload(h1, Dd.h1 + ri, Hd, lane, nl); vload(db, Dd.db1 + ro, Hd, lane, nl); vload(u1, Dd.u1 + ro, Hd, lane, nl);
 #pragma unroll
-    for (int x = 0; x < ILSW_VL; ++x) { h1.v[x] = db.v[x] * (1.0f - h1.v[x] * h1.v[x]); u1.v[x] = db.v[x] * u1.v[x]; }
+    for (int x = 0; x < ILSW_VL; ++x) { h1.v[x] = db.v[x] * disc_dact(act, h1.v[x]); u1.v[x] = db.v[x] * u1.v[x]; }
     vstore(Dd.ub1 + ro, h1, Hd, lane, nl);
     vstore(Dd.sb1 + ro, u1, Hd, lane, nl);
   } else if (kind == ROW_DISC_EW2) {
@@ -699,9 +699,9 @@ ILSW_HDN void job_disc_ew(const Ctx& c, int kind, int job, const RowEnv& e) {
     const float cmk = ldg(Dd.cmask + b);
 #pragma unroll
     for (int x = 0; x < ILSW_VL; ++x) {
-      const float s2 = 1.0f - h2.v[x] * h2.v[x];
+      const float s2 = disc_dact(act, h2.v[x]);
       const float sb2 = db.v[x] * (cmk * w3.v[x]);
-      w3.v[x] = (-2.0f * h2.v[x] * sb2) * s2;
+      w3.v[x] = (disc_curv(act, h2.v[x]) * sb2) * s2;
       db.v[x] = db.v[x] * s2;
     }
     vstore(Dd.t3 + ro, db, Hd, lane, nl);
@@ -710,7 +710,7 @@ ILSW_HDN void job_disc_ew(const Ctx& c, int kind, int job, const RowEnv& e) {
     Vec h1, hb, sb;
     vload(h1, Dd.h1 + ri, Hd, lane, nl); vload(hb, Dd.hb1 + ro, Hd, lane, nl); vload(sb, Dd.sb1 + ro, Hd, lane, nl);
 #pragma unroll
-    for (int x = 0; x < ILSW_VL; ++x) hb.v[x] = (hb.v[x] - 2.0f * h1.v[x] * sb.v[x]) * (1.0f - h1.v[x] * h1.v[x]);
+    for (int x = 0; x < ILSW_VL; ++x) hb.v[x] = (hb.v[x] + disc_curv(act, h1.v[x]) * sb.v[x]) * disc_dact(act, h1.v[x]);
     vstore(Dd.zb1 + ro, hb, Hd, lane, nl);
   }
 }

@@ -232,6 +232,7 @@ struct Hyper {
   double disc_lr, disc_beta1; float gp_weight, disc_clamp; int use_gp;
   int clip_min_on, clip_max_on; float rew_clip_min, rew_clip_max;
   int state_only;       // disc input = cat(obs, next_obs) (adv_irl.py:139-179)
+  int disc_act;         // MLPDisc hid_act (simple_disc_models.py:19-24): ACT_TANH (every shipped yaml) or ACT_RELU
   int n_from_expert;    // last n rows of the policy batch come from the expert ring (adv_irl.py:239-255)
   int use_tc5;          // dense GEMM phases run on the tcgen05/TMA tile (ilsw_tc5.cuh): batch >= 512, tensor-core modes
   int fuse_l0;          // narrow first layers are produced inside the second layer's tiles (GemmOp::a0)

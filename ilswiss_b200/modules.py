@@ -87,12 +87,13 @@ class DeterministicNoisePolicy(Mlp):
 
 
 class MLPDisc(nn.Module):
-    """simple_disc_models.py:8-48 with num_layer_blocks=2, hid_act='tanh', use_bn=False."""
+    """simple_disc_models.py:8-48 with num_layer_blocks=2, use_bn=False; hid_act 'tanh' (the shipped yamls) or 'relu'."""
 
-    def __init__(self, input_dim, hid_dim=128, clamp_magnitude=10.0):
+    def __init__(self, input_dim, hid_dim=128, clamp_magnitude=10.0, hid_act="tanh"):
         super().__init__()
+        act = {"tanh": nn.Tanh, "relu": nn.ReLU}[hid_act]
         self.clamp_magnitude = clamp_magnitude
-        self.mod_list = nn.ModuleList([nn.Linear(input_dim, hid_dim), nn.Tanh(), nn.Linear(hid_dim, hid_dim), nn.Tanh(),
+        self.mod_list = nn.ModuleList([nn.Linear(input_dim, hid_dim), act(), nn.Linear(hid_dim, hid_dim), act(),
                                        nn.Linear(hid_dim, 1)])
         self.model = nn.Sequential(*self.mod_list)
 

@@ -39,9 +39,29 @@ def _stats(name, data):
                         (name + " Max", np.max(data)), (name + " Min", np.min(data))])
 
 
+def _fn_name(fn):
+    return (getattr(fn, "__name__", None) or type(fn).__name__).lower()
+
+
+def check_activations(module, output=None):
+    """The step programs hard-wire what the run scripts build (networks.py:23-101): ReLU hidden layers, identity output
+    on the critics, tanh output on the TD3 policy (td3_exp_script.py:71-78).  A module built with anything else has the same
+    parameter list, so it is refused here rather than trained as something it is not."""
+    hid = getattr(module, "hidden_activation", None)
+    if hid is not None and _fn_name(hid) != "relu":
+        raise NotImplementedError("hidden_activation %s: the fused engine implements ReLU hidden layers" % _fn_name(hid))
+    out = getattr(module, "output_activation", None)
+    if output == "identity" and out is not None and _fn_name(out) != "identity":
+        raise NotImplementedError("output_activation %s on a critic: the fused engine implements identity" % _fn_name(out))
+    if output == "tanh" and (out is None or _fn_name(out) != "tanh"):
+        raise NotImplementedError("TD3 policy output_activation %s: the fused engine implements max_act * tanh "
+                                  "(policies.py:178, td3_exp_script.py:75)" % (None if out is None else _fn_name(out)))
+
+
 def module_dims(module):
     """(in_dim, hidden, out_dim, log_std_head) of a 2-hidden-layer reference MLP from its
     parameter list (networks.py:23-83 / policies.py:191-243 / simple_disc_models.py:8-41)."""
+    check_activations(module)
     ps = list(module.parameters())
     if len(ps) not in (6, 8):
         raise NotImplementedError("fused engine supports MLPs with exactly two hidden layers (got %d parameter tensors)" % len(ps))
@@ -196,6 +216,8 @@ class SoftActorCritic(_FusedTrainer):
         in_dim, H, act_dim, ls = module_dims(policy)
         if not ls:
             raise NotImplementedError("SAC needs a ReparamTanhMultivariateGaussianPolicy (conditioned_std=True)")
+        for q in (qf1, qf2):
+            check_activations(q, "identity")
         self.target_entropy = target_entropy
         if target_entropy is None:   # sac_alpha.py:55-58
             if "env" in kwargs:
@@ -316,6 +338,8 @@ class SoftActorCriticV(_FusedTrainer):
         in_dim, H, act_dim, ls = module_dims(policy)
         if not ls:
             raise NotImplementedError("SAC needs a ReparamTanhMultivariateGaussianPolicy (conditioned_std=True)")
+        for q in (qf1, qf2, vf):
+            check_activations(q, "identity")
         self.target_vf = clone_module(vf)
         self._arenas = OrderedDict(policy=adopt_module(policy), qf1=adopt_module(qf1), qf2=adopt_module(qf2),
                                    vf=adopt_module(vf), target_vf=adopt_module(self.target_vf, False))
@@ -405,6 +429,9 @@ class TD3(_FusedTrainer):
         in_dim, H, act_dim, ls = module_dims(policy)
         if ls:
             raise NotImplementedError("TD3 needs a deterministic MlpGaussianNoisePolicy")
+        check_activations(policy, "tanh")
+        for q in (qf1, qf2):
+            check_activations(q, "identity")
         self.target_policy = clone_module(policy)
         self.target_qf1, self.target_qf2 = clone_module(qf1), clone_module(qf2)
         self._arenas = OrderedDict(

@@ -93,6 +93,7 @@ int ilsw_mlp_num_params(int in_dim, int hidden, int out_dim, int log_std_head);
 
 typedef enum { ILSW_ALGO_SAC_ALPHA = 1, ILSW_ALGO_TD3 = 2, ILSW_ALGO_SAC_V = 3 } ilsw_algo;
 typedef enum { ILSW_DISC_AIRL = 0, ILSW_DISC_GAIL = 1, ILSW_DISC_GAIL2 = 2, ILSW_DISC_FAIRL = 3 } ilsw_disc_mode;
+typedef enum { ILSW_DISC_ACT_TANH = 0, ILSW_DISC_ACT_RELU = 1 } ilsw_disc_act;
 
 typedef struct {
   int algo;                 /* ilsw_algo */
@@ -131,6 +132,9 @@ typedef struct {
   /* adv_irl.py:239-255 policy_optim_batch_size_from_expert: the LAST n rows of every policy batch are sampled from the expert
    * ring (injected idx rows >= batch - n index the expert ring) */
   int policy_batch_from_expert;
+  /* MLPDisc hid_act (simple_disc_models.py:19-24), use_bn=False, num_layer_blocks=2: ilsw_disc_act.  0 = tanh, what every
+   * shipped exp_specs/gail yaml sets; relu blocks run the same step program minus the act'' terms of the penalty */
+  int hid_act;
 } ilsw_disc_config;
 
 typedef struct ilsw_trainer ilsw_trainer;

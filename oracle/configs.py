@@ -74,6 +74,16 @@ CASES = {
                             mode="gail", from_expert=32,
                             disc=dict(disc_lr=3e-4, disc_momentum=0.9, use_grad_pen=True, grad_pen_weight=4.0),
                             sac=dict(SAC_KW, reward_scale=1.0, alpha=0.2), seed=29),
+    # MLPDisc(hid_act="relu", use_bn=False) (simple_disc_models.py:19-24; the class default activation): no act'' terms in the
+    # penalty's double backward -- with and without the penalty, and on ragged shapes
+    "gail_hopper_relu": dict(algo="adv_irl", obs_dim=11, act_dim=3, batch=128, n_fill=5000, n_expert=2000, steps=3,
+                             mode="gail", disc_act="relu",
+                             disc=dict(disc_lr=3e-4, disc_momentum=0.9, use_grad_pen=True, grad_pen_weight=4.0),
+                             sac=dict(SAC_KW, reward_scale=1.0, alpha=0.2), seed=30),
+    "gail2_relu_nogp_ragged": dict(algo="adv_irl", obs_dim=5, act_dim=2, batch=40, n_fill=400, n_expert=90, steps=3,
+                                   mode="gail2", hidden=64, disc_hid=48, disc_act="relu",
+                                   disc=dict(disc_lr=3e-4, disc_momentum=0.0, use_grad_pen=False, grad_pen_weight=10.0),
+                                   sac=dict(SAC_KW, reward_scale=2.0, alpha=0.2), seed=31),
     # ragged shapes: batch not a multiple of the 32-row tile / of 4, odd hidden widths, tiny dims
     "sac_ragged": dict(algo="sac_alpha", obs_dim=5, act_dim=2, batch=70, n_fill=300, steps=3, hidden=64,
                        sac=dict(SAC_KW, alpha=0.2), seed=21),

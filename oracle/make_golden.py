@@ -145,8 +145,8 @@ def run_reference(case):
         mods["policy"] = ref.ReparamTanhMultivariateGaussianPolicy(
             hidden_sizes=list(HID), obs_dim=O, action_dim=A)
     if algo == "adv_irl":
-        mods["disc"] = ref.MLPDisc(2 * O if case.get("state_only") else O + A, num_layer_blocks=2, hid_dim=DH, hid_act="tanh",
-                                   use_bn=False, clamp_magnitude=10.0)
+        mods["disc"] = ref.MLPDisc(2 * O if case.get("state_only") else O + A, num_layer_blocks=2, hid_dim=DH,
+                                   hid_act=case.get("disc_act", "tanh"), use_bn=False, clamp_magnitude=10.0)
     for k, m in mods.items():
         _load_into_module(m, nets[k])
 
@@ -243,7 +243,7 @@ def run_oracle(case):
     else:
         tr = R.TD3Oracle(nets["policy"], nets["qf1"], nets["qf2"], policy_noise=case["policy_noise"],
                          policy_noise_clip=case["policy_noise_clip"], **case["td3"])
-    disc = R.DiscOracle(nets["disc"], **case["disc"]) if algo == "adv_irl" else None
+    disc = R.DiscOracle(nets["disc"], hid_act=case.get("disc_act", "tanh"), **case["disc"]) if algo == "adv_irl" else None
     rows = []
     for t in range(case["steps"]):
         torch.manual_seed(C.EPS_SEED0 + t)

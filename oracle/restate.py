@@ -397,10 +397,11 @@ def td3_policy_forward(w, obs, noise=None, policy_noise=0.2, noise_clip=0.5, max
     return a
 
 
-def disc_forward(w, x, clamp=10.0):
-    """MLPDisc.forward, 2 tanh blocks, no BN (simple_disc_models.py:43-48)."""
-    h = torch.tanh(F.linear(x, w[0], w[1]))
-    h = torch.tanh(F.linear(h, w[2], w[3]))
+def disc_forward(w, x, clamp=10.0, hid_act="tanh"):
+    """MLPDisc.forward, 2 Linear + hid_act blocks, no BN (simple_disc_models.py:19-24,29-48)."""
+    act = {"tanh": torch.tanh, "relu": torch.relu}[hid_act]
+    h = act(F.linear(x, w[0], w[1]))
+    h = act(F.linear(h, w[2], w[3]))
     return torch.clamp(F.linear(h, w[4], w[5]), -clamp, clamp)
 
 
@@ -720,8 +721,8 @@ def disc_reward(logits, mode, rew_clip_min=None, rew_clip_max=None):
 
 class DiscOracle:
     def __init__(self, disc, disc_lr=3e-4, disc_momentum=0.9, use_grad_pen=True,
-                 grad_pen_weight=10.0, clamp=10.0):
-        self.disc = disc
+                 grad_pen_weight=10.0, clamp=10.0, hid_act="tanh"):
+        self.disc, self.hid_act = disc, hid_act
         self.lr, self.beta1 = disc_lr, disc_momentum  # adv_irl.py:75-77
         self.use_grad_pen, self.gp_w, self.clamp = use_grad_pen, grad_pen_weight, clamp
 
@@ -731,14 +732,14 @@ class DiscOracle:
         B = expert_x.shape[0]
         x = torch.cat([expert_x, policy_x], dim=0)
         targets = torch.cat([torch.ones(B, 1), torch.zeros(B, 1)], dim=0)
-        logits = disc_forward(w, x, self.clamp)
+        logits = disc_forward(w, x, self.clamp, self.hid_act)
         ce = F.binary_cross_entropy_with_logits(logits, targets)
         acc = ((logits > 0).float() == targets).float().mean()
         gp = torch.zeros(())
         total = ce
         if self.use_grad_pen:
             interp = (gp_eps * expert_x + (1 - gp_eps) * policy_x).detach().requires_grad_(True)
-            (g,) = torch.autograd.grad(disc_forward(w, interp, self.clamp).sum(), [interp],
+            (g,) = torch.autograd.grad(disc_forward(w, interp, self.clamp, self.hid_act).sum(), [interp],
                                        create_graph=True, retain_graph=True)
             gp = ((g.norm(2, dim=1) - 1) ** 2).mean()
             total = ce + gp * self.gp_w
@@ -751,7 +752,7 @@ class DiscOracle:
         """adv_irl.py:266-298 (disc in eval mode, logits detached).  `act` is next_obs in state_only mode (:265-269)."""
         with torch.no_grad():
             w = list(self.disc.p.values())
-            return disc_reward(disc_forward(w, torch.cat([obs, act], dim=1), self.clamp), mode,
+            return disc_reward(disc_forward(w, torch.cat([obs, act], dim=1), self.clamp, self.hid_act), mode,
                                rew_clip_min, rew_clip_max)
 
 

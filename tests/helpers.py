@@ -258,6 +258,7 @@ def disc_config(case):
     dc.disc_lr, dc.disc_momentum = d["disc_lr"], d["disc_momentum"]
     dc.use_grad_pen, dc.grad_pen_weight = int(d["use_grad_pen"]), d["grad_pen_weight"]
     dc.clamp_magnitude = 10.0
+    dc.hid_act = _abi.DISC_ACTS[case.get("disc_act", "tanh")]
     dc.rew_clip_min_on = int(case.get("rew_clip_min") is not None)
     dc.rew_clip_max_on = int(case.get("rew_clip_max") is not None)
     dc.rew_clip_min = case.get("rew_clip_min") or 0.0

@@ -23,7 +23,7 @@ def build_modules(case):
     else:
         mods["policy"] = modules.TanhGaussianPolicy([256, 256], O, A)
     if case["algo"] == "adv_irl":
-        mods["disc"] = modules.MLPDisc(O + A, 128)
+        mods["disc"] = modules.MLPDisc(O + A, 128, hid_act=case.get("disc_act", "tanh"))
     for k, m in mods.items():
         with torch.no_grad():
             for p, v in zip(m.parameters(), nets[k].p.values()):
@@ -288,13 +288,14 @@ def test_expert_demo_ingest_and_save_data(tmp_path):
     np.testing.assert_array_equal(d["observations"].astype(np.float32), ora._observations[:4 * T].astype(np.float32))
 
 
-def test_adv_irl_engine_matches_oracle_and_stats_keys():
+@pytest.mark.parametrize("name", ["gail_walker", "gail_hopper_relu"])      # tanh (the shipped yamls) and relu MLPDisc blocks
+def test_adv_irl_engine_matches_oracle_and_stats_keys(name):
     from ilswiss_b200.adv_irl import AdvIRLEngine
     from ilswiss_b200.replay_buffer import DeviceReplayBuffer
     from ilswiss_b200.trainers import SoftActorCritic
 
     torch.set_num_threads(1)
-    case = CFG.CASES["gail_walker"]
+    case = CFG.CASES[name]
     mods, _ = build_modules(case)
     tr = SoftActorCritic(mods["policy"], mods["qf1"], mods["qf2"], batch_size=case["batch"], gemm_precision=3, **case["sac"])
     data, edata = case_data(case)

@@ -126,7 +126,7 @@ def test_program_shape(lib):
     run.close()
 
 
-@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper", "gail_walker"])
+@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper", "gail_walker", "gail_hopper_relu"])
 def test_fast_row_jobs_equal_generic_row_kernels(lib, name):
     """Two independent implementations of every row kernel (latency-optimised job form vs the
     generic per-row form) must agree bit for bit on the host."""

@@ -2,7 +2,7 @@
 """Measures, per parity case, the fraction of parameter elements whose final value differs from the oracle's by more than
 1e-5 in the tensor-core GEMM modes (precision 3 = 3xTF32, the production default; precision 1 = single-pass TF32).
 Writes tests/golden/param_frac.json; tests/test_gpu_engine.py asserts <= 2x the committed value.
-Needs a GPU:  python tools/measure_param_frac.py"""
+Needs a GPU:  python tools/measure_param_frac.py [case ...]     (named cases are merged into the committed file)"""
 import json
 import os
 import sys
@@ -16,9 +16,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import CFG, G, DeviceRun, case_injection  # noqa: E402
 
 torch.set_num_threads(1)
-out = {}
+PATH = os.path.join(ROOT, "tests", "golden", "param_frac.json")
+only = sys.argv[1:]
+out = json.load(open(PATH))["cases"] if only else {}
 for name, case in CFG.CASES.items():
-    if case["algo"] not in ("sac_alpha", "sac_v", "td3", "adv_irl"):
+    if case["algo"] not in ("sac_alpha", "sac_v", "td3", "adv_irl") or (only and name not in only):
         continue
     rows, final, _ = G.run_oracle(case)
     rec = {}
@@ -37,7 +39,7 @@ for name, case in CFG.CASES.items():
         rec["p%d" % prec] = {"frac_beyond_1e-5": worst, "net": worst_net, "max_abs_diff": worst_max}
     out[name] = rec
     print(name, rec, flush=True)
-with open(os.path.join(ROOT, "tests", "golden", "param_frac.json"), "w") as f:
+with open(PATH, "w") as f:
     json.dump({"note": "measured on a B200 by tools/measure_param_frac.py: worst net's fraction of parameter elements beyond 1e-5 of the oracle", "cases": out}, f, indent=1, sort_keys=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", "param_frac.json"), "w") as f:
