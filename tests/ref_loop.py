@@ -165,6 +165,8 @@ def run_advirl_loop(log_dir, device, epochs=2, env_num=2, O=11, A=3, B=64, hidde
         policy = ReparamTanhMultivariateGaussianPolicy(hidden_sizes=[hidden, hidden], obs_dim=O, action_dim=A)
         if disc_kind == "mlp_tanh":          # every shipped yaml (exp_specs/gail/*.yaml:24-28): the fused program
             disc = MLPDisc(O + A, num_layer_blocks=2, hid_dim=128, hid_act="tanh", use_bn=False, clamp_magnitude=10.0)
+        elif disc_kind == "mlp_relu":        # relu blocks without BatchNorm: the same step program minus the act'' terms
+            disc = MLPDisc(O + A, num_layer_blocks=2, hid_dim=128, hid_act="relu", use_bn=False, clamp_magnitude=10.0)
         elif disc_kind == "mlp_bn_relu":     # the class defaults (simple_disc_models.py:9-16)
             disc = MLPDisc(O + A, num_layer_blocks=2, hid_dim=128, hid_act="relu", use_bn=True, clamp_magnitude=10.0)
         elif disc_kind == "resnet":

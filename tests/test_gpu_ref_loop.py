@@ -42,11 +42,17 @@ def test_torch_rl_algorithm_train_runs_on_the_device_path(tmp_path):
         assert [r[j] for r in dev["rows"]] == [r[j] for r in ref["rows"]], key
 
 
-def test_adv_irl_train_runs_on_the_device_path(tmp_path):
+@pytest.mark.parametrize("disc_kind", ["mlp_tanh", "mlp_relu"])
+def test_adv_irl_train_runs_on_the_device_path(tmp_path, disc_kind):
+    import warnings
+
     import ref_loop
 
-    ref = ref_loop.run_advirl_loop(str(tmp_path / "ref"), device=False, epochs=2, steps_per_epoch=200)
-    dev = ref_loop.run_advirl_loop(str(tmp_path / "dev"), device=True, epochs=2, steps_per_epoch=200)
+    ref = ref_loop.run_advirl_loop(str(tmp_path / "ref"), device=False, epochs=2, steps_per_epoch=200, disc_kind=disc_kind)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        dev = ref_loop.run_advirl_loop(str(tmp_path / "dev"), device=True, epochs=2, steps_per_epoch=200, disc_kind=disc_kind)
+    assert not any("outside the fused AdvIRL program" in str(x.message) for x in w)      # the step program, not the eager fallback
     assert dev["header"] == ref["header"]
     _finite(dev["rows"])
     for key in ("Number of env steps total", "Number of train calls total", "Epoch"):
