@@ -71,3 +71,38 @@ def test_row_layout_roundtrip():
     np.testing.assert_array_equal(host[:, :2 * O + A + 2], hot[:, :2 * O + A + 2])
     assert (host[:, -3:] == 1).all()
     assert layout.hot_row_stride(376, 17) == 784 and layout.hot_row_stride(17, 6) == 48      # 64-byte row alignment
+
+
+def test_ctypes_struct_layouts_equal_the_c_header(tmp_path):
+    """Every struct that crosses the boundary: sizeof and each field's offsetof, as gcc lays include/ilswiss_b200.h out,
+    against the ctypes mirror (a field added on one side only would shift everything behind it silently)."""
+    import subprocess
+
+    pairs = [("ilsw_mlp", _abi.Mlp), ("ilsw_trainer_config", _abi.TrainerConfig), ("ilsw_disc_config", _abi.DiscConfig),
+             ("ilsw_her_sampling", _abi.HerSamplingDesc), ("ilsw_inject", _abi.Inject), ("ilsw_batch", _abi.Batch),
+             ("ilsw_state", _abi.State)]
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "ilswiss_b200.h"', "int main(void) {"]
+    for cname, cls in pairs:
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["  return 0;", "}"]
+    src, exe = tmp_path / "layout.c", tmp_path / "layout"
+    src.write_text("\n".join(lines) + "\n")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)]).decode().splitlines())
+    for cname, cls in pairs:
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+    # and the header declares no struct field the mirror lacks
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ilswiss_b200.h")).read(), flags=re.S)
+    bodies = {name: body for body, name in re.findall(r"typedef struct \{([^}]*)\} (\w+);", text)}
+    for cname, cls in pairs:
+        body = bodies[cname]
+        declared = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                declared += [re.sub(r"\[.*?\]", "", d).replace("*", " ").split()[-1] for d in decl.split(",")]
+        assert declared == [f for f, _ in cls._fields_], cname
