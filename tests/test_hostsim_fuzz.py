@@ -34,3 +34,25 @@ def test_random_case_matches_oracle(lib, seed):
 @pytest.mark.parametrize("seed", [1005, 1012, 1034, 1044])      # adv_irl relu, td3, adv_irl tanh + expert mix, sac_v
 def test_random_case_program_variants_agree_bit_for_bit(lib, seed):
     fuzz_hostsim.check_variants(lib, fuzz_hostsim.random_case(seed))
+
+
+@pytest.mark.parametrize("seed", [3001, 3005, 3004])      # HER-SAC, TD3 period 1..3, SAC-V at batch 512..640
+def test_random_tcgen05_program_variant_case_matches_oracle(lib, seed, monkeypatch):
+    torch.set_num_threads(1)
+    monkeypatch.setenv("ILSW_HOSTSIM_TC5", "1")
+    case = fuzz_hostsim.random_tc5_case(seed)
+    import ctypes as C
+
+    from helpers import HostSimRun
+
+    probe, buf = HostSimRun(lib, case, precision=3), C.create_string_buffer(1 << 15)
+    lib.hs_describe(probe.h, buf, 1 << 15)
+    probe.close()
+    assert "tcgen05" in buf.value.decode()
+    fuzz_hostsim.check_case(lib, case, precision=3, frac=2.5e-3, lr=case.get("td3", {}).get("policy_lr", 3e-4))
+
+
+@pytest.mark.parametrize("seed", [4100, 4101, 4102, 4103])
+def test_random_relabel_at_sample_case_matches_oracle(lib, seed):
+    torch.set_num_threads(1)
+    fuzz_hostsim.check_her_relabel_case(lib, fuzz_hostsim.random_her_relabel_case(seed))
