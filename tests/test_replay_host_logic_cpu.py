@@ -1,0 +1,89 @@
+"""The product's DeviceReplayBuffer HOST logic (cursor, size, trajectory table, burst staging and its chunking, row packing)
+against the reference's own SimpleReplayBuffer under random operation sequences -- the device ring is replaced by a numpy
+ring with the C ABI's append semantics (slot = (top + i) % capacity), so no GPU is needed.  The gather / sample side is
+covered on the GPU (tests/test_gpu_replay.py)."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference checkout absent")
+
+
+class NumpyRing:
+    """What engine.ReplayRing does to host rows (ilsw_rb_append + ilsw_rb_commit), in numpy."""
+
+    def __init__(self, capacity, obs_dim, act_dim):
+        self.cap, self.W = capacity, 2 * obs_dim + act_dim + 5
+        self.rows = np.zeros((capacity, self.W), np.float32)
+        self.top = self.size = 0
+        self.bursts = []
+
+    def append_host(self, rows):
+        assert rows.dtype == np.float32 and rows.shape[1] == self.W and 0 < rows.shape[0] <= self.cap     # ilsw_rb_append
+        self.bursts.append(rows.shape[0])
+        for r in rows:
+            self.rows[self.top] = r
+            self.top = (self.top + 1) % self.cap
+        self.size = min(self.size + rows.shape[0], self.cap)
+
+    def clear(self):
+        self.top = self.size = 0
+
+
+def _drive(cap, O, A, ops, flush_threshold, monkeypatch):
+    ref_shim.install()
+    from rlkit.data_management.simple_replay_buffer import SimpleReplayBuffer
+
+    import ilswiss_b200.replay_buffer as rb
+
+    monkeypatch.setattr(rb, "ReplayRing", NumpyRing)
+    ref = SimpleReplayBuffer(cap, O, A, random_seed=5)
+    dev = rb.DeviceReplayBuffer(cap, O, A, random_seed=5, flush_threshold=flush_threshold)
+    rs = np.random.RandomState(len(ops) + cap)
+    for op in ops:
+        if op == "term":
+            ref.terminate_episode(); dev.terminate_episode()
+        elif isinstance(op, tuple):                      # ("path", T): a whole trajectory, last transition terminal or not
+            T, last_terminal = op[1], op[2]
+            terms = np.zeros((T, 1)); terms[-1, 0] = float(last_terminal)
+            path = dict(observations=rs.randn(T, O), actions=rs.uniform(-1, 1, (T, A)), rewards=rs.randn(T, 1),
+                        next_observations=rs.randn(T, O), terminals=terms, absorbings=np.zeros((T, 2)),
+                        env_infos=[{}] * T, agent_infos=[{}] * T)
+            ref.add_path(path); dev.add_path(path)
+        else:                                            # one transition, terminal with probability op
+            o, a, r, no = rs.randn(O), rs.uniform(-1, 1, A), rs.randn(), rs.randn(O)
+            d = bool(rs.rand() < op)
+            ref.add_sample(o, a, r, d, no); dev.add_sample(o, a, r, d, no)
+        assert (dev._top, dev._size, dev._cur_start) == (ref._top, ref._size, ref._cur_start)
+        assert dev._traj_endpoints == ref._traj_endpoints
+        assert dev.num_steps_can_sample() == ref.num_steps_can_sample() and dev.get_traj_num() == ref.get_traj_num()
+    dev.flush()
+    return ref, dev
+
+
+@settings(max_examples=60, deadline=None)
+@given(cap=st.integers(3, 40), O=st.integers(1, 6), A=st.integers(1, 3), thr=st.sampled_from([1, 4, 4096]),
+       ops=st.lists(st.one_of(st.sampled_from([0.0, 0.1, 0.5]), st.just("term"),
+                              st.tuples(st.just("path"), st.integers(1, 12), st.booleans())), min_size=1, max_size=60))
+def test_bookkeeping_and_staged_rows_equal_the_reference_buffer(cap, O, A, thr, ops):
+    with pytest.MonkeyPatch.context() as mp:
+        ops = [op for op in ops if not (isinstance(op, tuple) and op[1] >= cap)]      # the reference's own precondition (:130-131)
+        if not ops:
+            return
+        ref, dev = _drive(cap, O, A, ops, thr, mp)
+    ring = dev.ring
+    assert (ring.top, ring.size) == (ref._top, ref._size)
+    assert all(n <= cap for n in ring.bursts)
+    # every slot the reference holds, rounded to float32 as np_to_pytorch_batch does (rlkit/torch/core.py:124-143)
+    n = ref._size
+    f32 = lambda x: np.asarray(x, dtype=np.float32)
+    np.testing.assert_array_equal(ring.rows[:n, :O], f32(ref._observations[:n]))
+    np.testing.assert_array_equal(ring.rows[:n, O:O + A], f32(ref._actions[:n]))
+    np.testing.assert_array_equal(ring.rows[:n, O + A], f32(ref._rewards[:n, 0]))
+    np.testing.assert_array_equal(ring.rows[:n, O + A + 1], f32(ref._terminals[:n, 0]))
+    np.testing.assert_array_equal(ring.rows[:n, O + A + 2:2 * O + A + 2], f32(ref._next_obs[:n]))
+    # and the index stream of the next random_batch is the reference's
+    if ref._size:
+        np.testing.assert_array_equal(dev.sample_indices(7), ref._np_randint(0, ref._size, 7))
