@@ -31,6 +31,13 @@ class NumpyRing:
     def clear(self):
         self.top = self.size = 0
 
+    def commit(self):
+        pass
+
+    def set_cursor(self, top, size):
+        assert 0 <= top < self.cap and 0 <= size <= self.cap      # ilsw_rb_set_cursor
+        self.top, self.size = top, size
+
 
 def _drive(cap, O, A, ops, flush_threshold, monkeypatch):
     ref_shim.install()
@@ -87,3 +94,47 @@ def test_bookkeeping_and_staged_rows_equal_the_reference_buffer(cap, O, A, thr, 
     # and the index stream of the next random_batch is the reference's
     if ref._size:
         np.testing.assert_array_equal(dev.sample_indices(7), ref._np_randint(0, ref._size, 7))
+
+
+@pytest.mark.parametrize("n_steps", [17, 40, 95])          # partly filled, exactly full, wrapped twice
+def test_reference_buffer_state_restores_into_the_device_classes(n_steps, monkeypatch):
+    """base_algorithm.py:562-580 save_replay_buffer -> extra_data.pkl -> resume: the state of the reference's own
+    EnvReplayBuffer (its attribute dict is what it pickles) loads into DeviceEnvReplayBuffer / DeviceReplayBuffer through
+    __setstate__ -- which must not go through the subclass constructor (env-based signature) -- with every slot, the cursor,
+    the trajectory table, the spaces and the RandomState stream carried over."""
+    import pickle
+
+    ref_shim.install()
+    from rlkit.data_management.env_replay_buffer import EnvReplayBuffer
+
+    import ilswiss_b200.replay_buffer as rb
+
+    monkeypatch.setattr(rb, "ReplayRing", NumpyRing)
+    O, A, cap = 4, 2, 40
+    env = ref_shim.FakeEnv(O, A)
+    ref = EnvReplayBuffer(cap, env, random_seed=9)
+    rs = np.random.RandomState(1)
+    for i in range(n_steps):
+        ref.add_sample(rs.randn(O), rs.uniform(-1, 1, A), rs.randn(), bool(i % 11 == 10), rs.randn(O), timeout=bool(i % 11 == 10),
+                       absorbing=np.array([0.0, float(i % 2)]))
+    # the attribute dict is what extra_data.pkl holds (the gym stub spaces of the shim are not picklable: copy field by field)
+    state = {k: (pickle.loads(pickle.dumps(v)) if k not in ("_ob_space", "_action_space") else v) for k, v in ref.__dict__.items()}
+    for cls in (rb.DeviceEnvReplayBuffer, rb.DeviceReplayBuffer):
+        dev = cls.__new__(cls)
+        dev.__setstate__({k: (pickle.loads(pickle.dumps(v)) if k == "_np_rand_state" else v) for k, v in state.items()})
+        assert type(dev.ring) is NumpyRing and (dev.ring.top, dev.ring.size) == (ref._top, ref._size)
+        assert (dev._top, dev._size, dev._cur_start, dev._trajs) == (ref._top, ref._size, ref._cur_start, ref._trajs)
+        assert dev._traj_endpoints == ref._traj_endpoints and dev._max_replay_buffer_size == cap
+        n = ref._size
+        np.testing.assert_array_equal(dev.ring.rows[:n, :O], ref._observations[:n].astype(np.float32))
+        np.testing.assert_array_equal(dev.ring.rows[:n, O + A + 1], ref._terminals[:n, 0].astype(np.float32))
+        np.testing.assert_array_equal(dev.ring.rows[:n, O + A + 2:2 * O + A + 2], ref._next_obs[:n].astype(np.float32))
+        np.testing.assert_array_equal(dev.ring.rows[:n, 2 * O + A + 2:2 * O + A + 4], ref._absorbing[:n].astype(np.float32))
+        np.testing.assert_array_equal(dev.ring.rows[:n, 2 * O + A + 4], ref._timeouts[:n, 0].astype(np.float32))
+        np.testing.assert_array_equal(dev.sample_indices(5), pickle.loads(pickle.dumps(ref._np_rand_state)).randint(0, n, 5))
+        if cls is rb.DeviceEnvReplayBuffer:
+            assert dev._ob_space is not None and dev._action_space is not None
+        # appending goes on where the reference stopped
+        dev.add_sample(np.zeros(O), np.zeros(A), 1.5, False, np.ones(O))
+        dev.flush()
+        assert dev._top == (ref._top + 1) % cap and dev.ring.rows[ref._top, O + A] == 1.5
