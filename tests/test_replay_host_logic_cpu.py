@@ -38,6 +38,56 @@ class NumpyRing:
         assert 0 <= top < self.cap and 0 <= size <= self.cap      # ilsw_rb_set_cursor
         self.top, self.size = top, size
 
+    # the sample side, as ilsw_rb_gather lays it out: hot rows [n, stride] + cold rows [n, 4] (absorbing x2, timeout, 0)
+    @property
+    def committed_size(self):
+        return self.size
+
+    def gather(self, idx):
+        import torch
+
+        i = np.asarray(idx, dtype=np.int64)
+        hot_w = self.W - 3
+        hot = np.zeros((len(i), (hot_w + 15) // 16 * 16), np.float32)
+        hot[:, :hot_w] = self.rows[i, :hot_w]
+        cold = np.zeros((len(i), 4), np.float32)
+        cold[:, :3] = self.rows[i, hot_w:]
+        return torch.from_numpy(hot), torch.from_numpy(cold)
+
+    def rows_view(self):
+        import torch
+
+        return self.gather(np.arange(self.cap))[0]
+
+
+class _TorchOnCpu:
+    """`torch` as replay_buffer.py sees it, with device="cuda" requests served on the CPU (no GPU in this container)."""
+
+    def __getattr__(self, name):
+        import torch
+
+        return getattr(torch, name)
+
+    @staticmethod
+    def _strip(kw):
+        kw.pop("device", None)
+        return kw
+
+    def zeros(self, *a, **kw):
+        import torch
+
+        return torch.zeros(*a, **self._strip(kw))
+
+    def as_tensor(self, *a, **kw):
+        import torch
+
+        return torch.as_tensor(*a, **self._strip(kw))
+
+    def arange(self, *a, **kw):
+        import torch
+
+        return torch.arange(*a, **self._strip(kw))
+
 
 def _drive(cap, O, A, ops, flush_threshold, monkeypatch):
     ref_shim.install()
@@ -138,3 +188,59 @@ def test_reference_buffer_state_restores_into_the_device_classes(n_steps, monkey
         dev.add_sample(np.zeros(O), np.zeros(A), 1.5, False, np.ones(O))
         dev.flush()
         assert dev._top == (ref._top + 1) % cap and dev.ring.rows[ref._top, O + A] == 1.5
+
+
+@pytest.mark.parametrize("cap, n_ep, T", [(400, 7, 50), (130, 9, 20), (61, 12, 7)])      # no wrap, wrapped once, wrapped often
+def test_hindsight_buffer_host_path_equals_the_reference_buffer(cap, n_ep, T, monkeypatch):
+    """DeviceEnvHindsightReplayBuffer.random_batch (relabel_replay_buffer.py:63-131 on the host: trajectory shuffle,
+    trajectory / step / future-step draws from the reference's two RNG streams, goal substitution, sparse reward) against the
+    executed HindsightReplayBuffer, including rings that wrapped over old episodes -- and the same after a pickle-state
+    round trip of the device class (its own __getstate__ / __setstate__, env-based constructor not re-run)."""
+    import torch
+
+    from oracle.restate import synth_goal_episodes
+
+    ref_shim.install()
+    from rlkit.data_management.relabel_replay_buffer import HindsightReplayBuffer
+
+    import ilswiss_b200.replay_buffer as rb
+
+    monkeypatch.setattr(rb, "ReplayRing", NumpyRing)
+    monkeypatch.setattr(rb, "torch", _TorchOnCpu())
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    O0, G, A = 6, 3, 2
+    env = ref_shim.FakeGoalEnv(O0, G, A)
+    ref = HindsightReplayBuffer(cap, env, random_seed=5, relabel_type="future", her_ratio=0.8)
+    dev = rb.DeviceEnvHindsightReplayBuffer(cap, env, random_seed=5, relabel_type="future", her_ratio=0.8)
+    rs = np.random.RandomState(0)
+    for ep in synth_goal_episodes(rs, n_ep, T, O0, G, A):
+        for (o, a, r, d, no) in ep:
+            ref.add_sample(o, a, r, d, no)
+            dev.add_sample(o, a, r, d, no)
+        ref.terminate_episode()
+        dev.terminate_episode()
+    assert (dev._top, dev._size, dev._traj_endpoints) == (ref._top, ref._size, ref._traj_endpoints)
+
+    def compare(buf, trial):
+        np.random.seed(100 + trial)
+        want = ref.random_batch(48)
+        np.random.seed(100 + trial)
+        got = buf.random_batch(48)
+        for k in got:                       # every key the device class returns (achieved_goals of the current step is not stored)
+            np.testing.assert_array_equal(np.asarray(got[k], dtype=np.float32), np.asarray(want[k], dtype=np.float32), err_msg=k)
+        assert set(want.keys()) - set(got.keys()) <= {"achieved_goals"}
+
+    for trial in range(3):
+        compare(dev, trial)
+    starts, lens = dev.trajectory_table()
+    assert sorted(zip(starts.tolist(), lens.tolist())) == sorted(
+        (s, (e - s) % ref._size) for s, e in ref._traj_endpoints.items() if (e - s) % ref._size > 0)
+    # snapshot round trip: same class, same state, same RandomState position as the original
+    clone = rb.DeviceEnvHindsightReplayBuffer.__new__(rb.DeviceEnvHindsightReplayBuffer)
+    clone.__setstate__(dev.__getstate__())
+    assert (clone._top, clone._size, clone._goal_dim, clone.her_ratio, clone.distance_threshold) == (
+        dev._top, dev._size, G, 0.8, env.distance_threshold)
+    np.testing.assert_array_equal(clone._ag_next.numpy(), dev._ag_next.numpy())
+    np.testing.assert_array_equal(clone.ring.rows[:ref._size], dev.ring.rows[:ref._size])
+    # the RandomState object is SHARED through the state dict here (no pickling): advance the clone only
+    compare(clone, 7)
