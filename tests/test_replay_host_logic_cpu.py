@@ -96,6 +96,7 @@ def _drive(cap, O, A, ops, flush_threshold, monkeypatch):
     import ilswiss_b200.replay_buffer as rb
 
     monkeypatch.setattr(rb, "ReplayRing", NumpyRing)
+    monkeypatch.setattr(rb, "torch", _TorchOnCpu())
     ref = SimpleReplayBuffer(cap, O, A, random_seed=5)
     dev = rb.DeviceReplayBuffer(cap, O, A, random_seed=5, flush_threshold=flush_threshold)
     rs = np.random.RandomState(len(ops) + cap)
@@ -130,6 +131,10 @@ def test_bookkeeping_and_staged_rows_equal_the_reference_buffer(cap, O, A, thr, 
         if not ops:
             return
         ref, dev = _drive(cap, O, A, ops, thr, mp)
+        _compare_with_reference(ref, dev, cap, O, A)
+
+
+def _compare_with_reference(ref, dev, cap, O, A):
     ring = dev.ring
     assert (ring.top, ring.size) == (ref._top, ref._size)
     assert all(n <= cap for n in ring.bursts)
@@ -144,6 +149,16 @@ def test_bookkeeping_and_staged_rows_equal_the_reference_buffer(cap, O, A, thr, 
     # and the index stream of the next random_batch is the reference's
     if ref._size:
         np.testing.assert_array_equal(dev.sample_indices(7), ref._np_randint(0, ref._size, 7))
+        # random_batch: the reference's dict (simple_replay_buffer.py:239-293) -- keys, dtypes, shapes, float32-rounded values
+        for keys in (None, ["observations", "actions"]):
+            want, got = ref.random_batch(9, keys=keys), dev.random_batch(9, keys=keys)
+            assert set(got.keys()) == set(want.keys())
+            for k in want:
+                assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape, k
+                np.testing.assert_array_equal(got[k].astype(np.float32), want[k].astype(np.float32), err_msg=k)
+        want, got = ref.get_all(), dev.get_all()
+        for k in want:
+            np.testing.assert_array_equal(got[k].astype(np.float32), want[k].astype(np.float32), err_msg=k)
 
 
 @pytest.mark.parametrize("n_steps", [17, 40, 95])          # partly filled, exactly full, wrapped twice
