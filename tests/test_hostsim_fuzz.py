@@ -56,3 +56,9 @@ def test_random_tcgen05_program_variant_case_matches_oracle(lib, seed, monkeypat
 def test_random_relabel_at_sample_case_matches_oracle(lib, seed):
     torch.set_num_threads(1)
     fuzz_hostsim.check_her_relabel_case(lib, fuzz_hostsim.random_her_relabel_case(seed))
+
+
+@pytest.mark.parametrize("seed", [9001, 9002, 9003])      # relu 2/1, tanh 3/2, state_only 3/2 updates per loop iteration
+def test_random_loop_count_case_matches_oracle(lib, seed):
+    torch.set_num_threads(1)
+    fuzz_hostsim.check_loop_case(lib, fuzz_hostsim.random_loop_case(seed))

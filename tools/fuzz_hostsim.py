@@ -1,11 +1,13 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE -- random parity cases (algorithm, dims, batch, hidden widths, AdvIRL mode / options, discriminator
 activation) through the host simulator of the product's step programs against the oracle, at the parity tests' bars.
-    python tools/fuzz_hostsim.py <first seed> <number of cases> [--variants | --tc5 | --her]
+    python tools/fuzz_hostsim.py <first seed> <number of cases> [--variants | --tc5 | --her | --loops]
 --variants adds the bit-for-bit invariants between variants of one program (check_variants); --tc5 draws batch >= 512 cases
-for the program variant of the tcgen05 engine (incl. HER-TD3 / HER-SAC settings); --her draws relabel-at-sample cases.
+for the program variant of the tcgen05 engine (incl. HER-TD3 / HER-SAC settings); --her draws relabel-at-sample cases;
+--loops draws AdvIRL cases with 1..3 discriminator / policy updates per loop iteration (disc-only / policy-only launches).
 tests/test_hostsim_fuzz.py runs a fixed handful of seeds; round 2 ran seeds 1000..1149 against the oracle, 2000..2091
-through the variants, 3000..3069 with --tc5 and 4100..4179 with --her without a failure."""
+through the variants, 3000..3069 with --tc5 and 4100..4179 with --her without a failure, then 964 more seeds
+(profiles/r2_hostsim_fuzz.txt) with one event: a ReLU pre-activation of -2.2e-8 whose sign depends on the summation order."""
 import os
 import sys
 
@@ -126,13 +128,60 @@ def check_her_relabel_case(lib, case):
     for t, row in enumerate(rows):
         for k, ref in row.items():
             got = L[t, STAT_TO_SLOT[k]]
-            tol = 1e-4 * max(abs(ref), 1e-3) if k != "Policy Loss" else 1e-4 * max(abs(ref), 1.0)
+            tol = stat_tol(k, ref)
             worst = max(worst, abs(got - ref) / tol)
             assert abs(got - ref) <= tol, (t, k, got, ref)
     for k in final:
         assert_params_close(run.arenas[k], final[k], case["steps"], lr=6e-4, msg=k)
     run.close()
     return worst
+
+
+def random_loop_case(seed):
+    """adv_irl.py:126-131 with num_disc_updates_per_loop_iter / num_policy_updates_per_loop_iter in 1..3 (gail_humanoid.yaml
+    uses 100 / 100): an AdvIRL case of random_case run as alternating disc-only / policy-only launches."""
+    rs = np.random.RandomState(seed)
+    sub = seed * 7919
+    while True:
+        c = random_case(sub)
+        if c["algo"] == "adv_irl":
+            break
+        sub += 1
+    c.pop("from_expert", None)
+    c.update(steps=2, n_disc=int(rs.randint(1, 4)), n_policy=int(rs.randint(1, 4)))
+    return c
+
+
+def check_loop_case(lib, case):
+    from helpers import run_loop_case
+
+    rows, final, _ = G.run_oracle(case)
+    run = HostSimRun(lib, case)
+    got_rows = run_loop_case(run, case, lambda m: lib.hs_set_update_mode(run.h, m))
+    worst = 0.0
+    for t, (row, got) in enumerate(zip(rows, got_rows)):
+        for k, ref in row.items():
+            if k not in STAT_TO_SLOT or ref is None:
+                continue
+            tol = stat_tol(k, ref)
+            worst = max(worst, abs(got[k] - ref) / tol)
+            assert abs(got[k] - ref) <= tol, (t, k, got[k], ref)
+    n_updates = case["steps"] * max(case["n_disc"], case["n_policy"])
+    for k in final:
+        if k == "log_alpha":
+            assert abs(lib.hs_log_alpha(run.h) - final[k][0]) < 1e-6
+        else:
+            assert_params_close(run.arenas[k], final[k], n_updates, msg=k)
+    run.close()
+    return worst
+
+
+def stat_tol(k, ref):
+    """tests/test_gpu_engine.py:_loss_tol -- 1e-4 relative on losses; batch means of O(1)-spread vectors and the policy loss
+    (a cancellation of O(1) terms) at 1e-4 of that scale."""
+    if k == "Policy Loss" or k.endswith(" Mean") or k.endswith(" Std"):
+        return 1e-4 * max(abs(ref), 1.0)
+    return 1e-4 * max(abs(ref), 1e-3)
 
 
 def check_case(lib, case, precision=0, frac=5e-4, lr=3e-4):
@@ -146,7 +195,7 @@ def check_case(lib, case, precision=0, frac=5e-4, lr=3e-4):
             if k not in STAT_TO_SLOT or ref is None or np.isnan(L[t, STAT_TO_SLOT[k]]):
                 continue
             got = L[t, STAT_TO_SLOT[k]]
-            tol = 1e-4 * max(abs(ref), 1e-3) if k != "Policy Loss" else 1e-4 * max(abs(ref), 1.0)
+            tol = stat_tol(k, ref)
             worst = max(worst, abs(got - ref) / tol)
             assert abs(got - ref) <= tol, (t, k, got, ref)
     for k in final:
@@ -211,6 +260,9 @@ if __name__ == "__main__":
             elif "--her" in sys.argv:
                 case = random_her_relabel_case(seed)
                 worst = check_her_relabel_case(lib, case)
+            elif "--loops" in sys.argv:
+                case = random_loop_case(seed)
+                worst = check_loop_case(lib, case)
             else:
                 case = random_case(seed)
                 worst = check_case(lib, case)
