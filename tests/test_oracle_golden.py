@@ -99,3 +99,20 @@ def test_hindsight_oracle_matches_reference_buffer():
         for k in want:
             np.testing.assert_array_equal(np.asarray(got[k]), np.asarray(want[k]), err_msg=k)
         assert (want["rewards"] == 0).any() and (want["rewards"] == -1).any()          # both reward values occur
+
+
+@pytest.mark.parametrize("seed", [1000, 1001, 1004, 1010, 1017])      # AIRL relu + expert mix, SAC-V, TD3, GAIL tanh, relu state_only no penalty
+def test_oracle_matches_the_executed_reference_on_random_cases(seed):
+    """Beyond the committed goldens: random shapes / options (tools/fuzz_hostsim.random_case) run through the UNMODIFIED
+    reference classes and through the oracle in this container -- 2e-5 relative on statistics, 2e-6 absolute on parameters."""
+    import sys
+
+    from oracle import ref_shim
+
+    if not ref_shim.reference_available():
+        pytest.skip("reference checkout absent")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_hostsim
+
+    torch.set_num_threads(1)
+    fuzz_hostsim.check_oracle_against_reference(fuzz_hostsim.random_case(seed))

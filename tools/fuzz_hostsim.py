@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE -- random parity cases (algorithm, dims, batch, hidden widths, AdvIRL mode / options, discriminator
 activation) through the host simulator of the product's step programs against the oracle, at the parity tests' bars.
-    python tools/fuzz_hostsim.py <first seed> <number of cases> [--variants | --tc5 | --her | --loops]
+    python tools/fuzz_hostsim.py <first seed> <number of cases> [--variants | --tc5 | --her | --loops | --reference]
 --variants adds the bit-for-bit invariants between variants of one program (check_variants); --tc5 draws batch >= 512 cases
 for the program variant of the tcgen05 engine (incl. HER-TD3 / HER-SAC settings); --her draws relabel-at-sample cases;
---loops draws AdvIRL cases with 1..3 discriminator / policy updates per loop iteration (disc-only / policy-only launches).
+--loops draws AdvIRL cases with 1..3 discriminator / policy updates per loop iteration (disc-only / policy-only launches);
+--reference checks the ORACLE against the executed reference on the default cases (no simulator involved).
 tests/test_hostsim_fuzz.py runs a fixed handful of seeds; round 2 ran seeds 1000..1149 against the oracle, 2000..2091
 through the variants, 3000..3069 with --tc5 and 4100..4179 with --her without a failure, then 964 more seeds
 (profiles/r2_hostsim_fuzz.txt) with one event: a ReLU pre-activation of -2.2e-8 whose sign depends on the summation order."""
@@ -176,6 +177,30 @@ def check_loop_case(lib, case):
     return worst
 
 
+def check_oracle_against_reference(case):
+    """The other link of the chain (build container only: needs /root/reference): the UNMODIFIED reference classes executed on
+    the case (oracle/make_golden.run_reference) against oracle/restate.py, at make_golden's own bars (2e-5 relative on every
+    statistic, 2e-6 absolute on the parameters).  Returns (worst statistic error, worst parameter error)."""
+    import contextlib
+    import io
+
+    from oracle import make_golden
+
+    with contextlib.redirect_stdout(io.StringIO()):          # the reference prints its hyper-parameters
+        ref_rows, ref_final, _ = make_golden.run_reference(case)
+        ora_rows, ora_final, _ = make_golden.run_oracle(case)
+    worst = make_golden.compare_rows(ref_rows, ora_rows, 2e-5)
+    pmax = 0.0
+    for k in ref_final:
+        d = np.abs(ref_final[k] - ora_final[k])
+        pmax = max(pmax, float(d.max()))
+        # 2e-6 on every element but the odd one whose true gradient is ~0, where Adam's normalised first steps turn summation
+        # noise into +-lr (assert_params_close): at most 2 per tensor, bounded by 2*lr*steps.  Seen in 3 of 142 random cases,
+        # one element each (5e-6 .. 1.2e-5)
+        assert int((d > 2e-6).sum()) <= 2 and d.max() <= 2 * 6e-4 * case["steps"], (k, int((d > 2e-6).sum()), float(d.max()))
+    return worst, pmax
+
+
 def stat_tol(k, ref):
     """tests/test_gpu_engine.py:_loss_tol -- 1e-4 relative on losses; batch means of O(1)-spread vectors and the policy loss
     (a cancellation of O(1) terms) at 1e-4 of that scale."""
@@ -260,6 +285,9 @@ if __name__ == "__main__":
             elif "--her" in sys.argv:
                 case = random_her_relabel_case(seed)
                 worst = check_her_relabel_case(lib, case)
+            elif "--reference" in sys.argv:
+                case = random_case(seed)
+                worst = check_oracle_against_reference(case)[0] / 2e-5
             elif "--loops" in sys.argv:
                 case = random_loop_case(seed)
                 worst = check_loop_case(lib, case)
