@@ -205,8 +205,22 @@ def test_reference_buffer_state_restores_into_the_device_classes(n_steps, monkey
         assert dev._top == (ref._top + 1) % cap and dev.ring.rows[ref._top, O + A] == 1.5
 
 
+@settings(max_examples=25, deadline=None)
+@given(cap=st.integers(20, 200), n_ep=st.integers(2, 12), T=st.integers(2, 19), ratio=st.sampled_from([0.3, 0.8, 1.0]),
+       G=st.integers(1, 4), seed=st.integers(0, 1000))
+def test_hindsight_buffer_random_episode_tables(cap, n_ep, T, ratio, G, seed):
+    """The same comparison over random ring sizes / episode counts and lengths (rings that wrapped several times included),
+    goal dims and her_ratio."""
+    with pytest.MonkeyPatch.context() as mp:
+        _hindsight_vs_reference(cap, n_ep, T, mp, ratio=ratio, G=G, seed=seed, round_trip=False)
+
+
 @pytest.mark.parametrize("cap, n_ep, T", [(400, 7, 50), (130, 9, 20), (61, 12, 7)])      # no wrap, wrapped once, wrapped often
 def test_hindsight_buffer_host_path_equals_the_reference_buffer(cap, n_ep, T, monkeypatch):
+    _hindsight_vs_reference(cap, n_ep, T, monkeypatch)
+
+
+def _hindsight_vs_reference(cap, n_ep, T, monkeypatch, ratio=0.8, G=3, seed=0, round_trip=True):
     """DeviceEnvHindsightReplayBuffer.random_batch (relabel_replay_buffer.py:63-131 on the host: trajectory shuffle,
     trajectory / step / future-step draws from the reference's two RNG streams, goal substitution, sparse reward) against the
     executed HindsightReplayBuffer, including rings that wrapped over old episodes -- and the same after a pickle-state
@@ -223,11 +237,11 @@ def test_hindsight_buffer_host_path_equals_the_reference_buffer(cap, n_ep, T, mo
     monkeypatch.setattr(rb, "ReplayRing", NumpyRing)
     monkeypatch.setattr(rb, "torch", _TorchOnCpu())
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
-    O0, G, A = 6, 3, 2
+    O0, A = 6, 2
     env = ref_shim.FakeGoalEnv(O0, G, A)
-    ref = HindsightReplayBuffer(cap, env, random_seed=5, relabel_type="future", her_ratio=0.8)
-    dev = rb.DeviceEnvHindsightReplayBuffer(cap, env, random_seed=5, relabel_type="future", her_ratio=0.8)
-    rs = np.random.RandomState(0)
+    ref = HindsightReplayBuffer(cap, env, random_seed=5, relabel_type="future", her_ratio=ratio)
+    dev = rb.DeviceEnvHindsightReplayBuffer(cap, env, random_seed=5, relabel_type="future", her_ratio=ratio)
+    rs = np.random.RandomState(seed)
     for ep in synth_goal_episodes(rs, n_ep, T, O0, G, A):
         for (o, a, r, d, no) in ep:
             ref.add_sample(o, a, r, d, no)
@@ -250,11 +264,13 @@ def test_hindsight_buffer_host_path_equals_the_reference_buffer(cap, n_ep, T, mo
     starts, lens = dev.trajectory_table()
     assert sorted(zip(starts.tolist(), lens.tolist())) == sorted(
         (s, (e - s) % ref._size) for s, e in ref._traj_endpoints.items() if (e - s) % ref._size > 0)
+    if not round_trip:
+        return
     # snapshot round trip: same class, same state, same RandomState position as the original
     clone = rb.DeviceEnvHindsightReplayBuffer.__new__(rb.DeviceEnvHindsightReplayBuffer)
     clone.__setstate__(dev.__getstate__())
     assert (clone._top, clone._size, clone._goal_dim, clone.her_ratio, clone.distance_threshold) == (
-        dev._top, dev._size, G, 0.8, env.distance_threshold)
+        dev._top, dev._size, G, ratio, env.distance_threshold)
     np.testing.assert_array_equal(clone._ag_next.numpy(), dev._ag_next.numpy())
     np.testing.assert_array_equal(clone.ring.rows[:ref._size], dev.ring.rows[:ref._size])
     # the RandomState object is SHARED through the state dict here (no pickling): advance the clone only
